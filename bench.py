@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the env hot path at 8 UAV / 64 PoI / 65 536 envs per GPU (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU arm (oracle port, all host threads)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # one rank per GPU, envs sharded (weak scaling)
+
+One "step" = one `env.step` of all E env instances of a rank (one kernel launch).  Prints ONE JSON line:
+  value        whole-job agent-steps/s, inputs (actions) resident in HBM, device-timed with CUDA events
+  e2e          same metric through the host-buffer C entry point `dcc_env_step_host` (numpy in / numpy out):
+               pinned H2D of the actions and D2H of obs/reward/done/coverage inside the timed region
+  roofline     algorithmic bytes per launch / average launch time vs the measured HBM copy bandwidth
+  cpu_baseline the CPU oracle port (oracle/dcc_env_oracle.c) timed on this box's host cores, bounded sample
+The reference itself is pure Python and /root/reference does not exist on the GPU box, so the CPU arm is the
+C port of its algorithm (kind "port"); the unmodified reference's own numbers measured in the build container
+are in BASELINE.md §2.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS, N_POIS, ENVS_PER_GPU = 8, 64, 65536
+METRIC = "agent-steps/sec at 8 UAV / 64 PoI (env step, 65536 envs per GPU)"
+UNIT = "agent-steps/s"
+
+
+def obs_dim(n, m):
+    return 4 + 2 * (n - 1) + 5 * m
+
+
+def alg_bytes_per_agent_step(n, m):
+    """obs write 4D + action read 8 + reward 4 + done 1 + pos/vel f64 r+w 64
+    + per env (PoI energy u8 r+w 2M, coverage_rate 4, connect 1) / N."""
+    return 4 * obs_dim(n, m) + 8 + 4 + 1 + 64 + (2 * m + 5) / n
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_cpu_port(n_envs, steps, warmup, threads, seed=0):
+    """Times the CPU oracle port (test infrastructure; here only as the measured CPU baseline)."""
+    from oracle.env_oracle import OracleEnv
+    from dcc_b200.envs.cuda_vec_env import synthetic_pois
+    env = OracleEnv(n_envs, N_AGENTS, N_POIS, synthetic_pois(N_POIS), comm_r_scale=0.9, contact_force=0.0,
+                    n_threads=threads)
+    rng = np.random.default_rng(seed)
+    acts = [rng.standard_normal((n_envs, N_AGENTS, 2)).astype(np.float32) for _ in range(4)]
+    env.reset()
+    for t in range(warmup):
+        env.step(acts[t % 4], want_aux=False)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        env.step(acts[t % 4], want_aux=False)
+    dt = time.perf_counter() - t0
+    return n_envs * N_AGENTS * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.env_oracle import max_threads
+    threads = max_threads()
+    n_envs = 8192
+    value, dt = time_cpu_port(n_envs, args.steps, args.warmup, threads)
+    sample = "%d envs x %d steps of the 8 UAV / 64 PoI env step, float64 C port of the reference algorithm" % (
+        n_envs, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "env-step-only, 8 UAV / 64 PoI, %d envs per CPU step (bounded sample of the 65536-env "
+                               "workload)" % n_envs, "n_agents": N_AGENTS, "n_pois": N_POIS, "envs": n_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from dcc_b200.envs import CudaVecEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    E, N, M = ENVS_PER_GPU, N_AGENTS, N_POIS
+    D = obs_dim(N, M)
+    env = CudaVecEnv(E, N, M, reference_compat=True, device=local_rank)  # shipped semantics, synthetic PoI layout
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    acts = [torch.randn((E, N, 2), generator=gen, device=dev, dtype=torch.float32) for _ in range(8)]
+    env.reset()
+    for t in range(max(args.warmup, 3)):
+        env.step(acts[t % 8])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, CUDA events on the launching (current) stream ----------------
+    sampler = ClockSampler(local_rank)
+    launches0 = env.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0.record()
+    for t in range(args.steps):
+        env.step(acts[t % 8])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launch_count() - launches0
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * E * N * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C entry point -----------------------------------------------
+    e2e_steps = max(3, min(args.steps, 20))
+    hb = env._host_buffers()
+    host_acts = [a.cpu().numpy() for a in acts[:4]]
+    for t in range(2):
+        env.step_host(host_acts[t % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(e2e_steps):
+        np.copyto(hb["actions"], host_acts[t % 4])
+        env.step_host(hb["actions"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * E * N * e2e_steps / e2e_s
+    h2d = E * N * 2 * 4
+    d2h = E * N * D * 4 + E * N * 4 + E * N + E * 4
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        b_alg = alg_bytes_per_agent_step(N, M)
+        launch_s = ms * 1e-3 / args.steps
+        achieved = E * N * b_alg / launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle.env_oracle import max_threads
+            threads = max_threads()
+            n_envs_cpu, steps_cpu = 8192, 30
+            v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 2, threads)
+            # grow the sample to >= ~10 s of CPU work
+            if dt < 10.0:
+                steps_cpu = int(min(2000, steps_cpu * 10.0 / max(dt, 1e-3)))
+                v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 0, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "%d envs x %d steps (%.1f s) of the same 8/64 env step, float64 C port of the reference "
+                             "algorithm (oracle/dcc_env_oracle.c), %d POSIX threads" % (n_envs_cpu, steps_cpu, dt, threads)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "env-step-only (BASELINE configs[1]): 8 UAV / 64 PoI, 65536 envs per GPU, N(0,1) float32 "
+                                   "actions, auto-reset on, shipped semantics (reference_compat)",
+                       "n_agents": N, "n_pois": M, "envs_per_gpu": E, "obs_dim": D, "poi_layout": "uniform(-1,1), seed 0",
+                       "l2": "no flush needed: %.0f MB written per step > 126 MB L2" % (E * N * D * 4 / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_agent_step": b_alg,
+                         "alg_bytes_per_launch": E * N * b_alg, "kernel": "dcc_env_kernel<true>",
+                         "avg_launch_us": launch_s * 1e6},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "CudaVecEnv.step_host -> dcc_env_step_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=150)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""ctypes binding of the C ABI declared in include/dcc_b200.h.
+
+Fails loudly: if libdcc_b200.so is missing or a call returns a non-zero status a DccError is raised —
+there is no CPU or PyTorch fallback for any entry point.
+"""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libdcc_b200.so")
+
+
+class DccError(RuntimeError):
+    pass
+
+
+class EnvCfg(C.Structure):
+    """struct dcc_env_cfg (include/dcc_b200.h)."""
+    _fields_ = [
+        ("n_envs", C.c_int32), ("n_agents", C.c_int32), ("n_pois", C.c_int32), ("max_ep_len", C.c_int32),
+        ("reference_compat", C.c_int32), ("reserved0", C.c_int32),
+        ("r_cover", C.c_double), ("r_comm", C.c_double), ("comm_r_scale", C.c_double),
+        ("comm_force_scale", C.c_double), ("dt", C.c_double), ("damping", C.c_double), ("max_speed", C.c_double),
+        ("sensitivity", C.c_double), ("m_energy", C.c_double), ("rew_cover", C.c_double), ("rew_done", C.c_double),
+        ("rew_out", C.c_double), ("contact_margin", C.c_double),
+    ]
+
+
+_VP = C.c_void_p
+# name -> (restype, argtypes); every symbol include/dcc_b200.h declares
+SIGNATURES = {
+    "dcc_env_cfg_default": (C.c_int, [C.POINTER(EnvCfg)]),
+    "dcc_env_obs_dim": (C.c_int, [C.c_int32, C.c_int32]),
+    "dcc_env_create": (C.c_int, [C.POINTER(EnvCfg), _VP, C.c_int, C.POINTER(_VP)]),
+    "dcc_env_destroy": (C.c_int, [_VP]),
+    "dcc_env_reset": (C.c_int, [_VP, _VP, _VP]),
+    "dcc_env_step": (C.c_int, [_VP] * 10),
+    "dcc_env_step_host": (C.c_int, [_VP] * 7),
+    "dcc_env_reset_host": (C.c_int, [_VP, _VP, _VP]),
+    "dcc_env_get_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "dcc_env_set_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "dcc_env_state_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
+    "dcc_env_set_launch": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "dcc_env_launch_count": (C.c_int64, [_VP]),
+    "dcc_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
+    "dcc_host_free": (C.c_int, [_VP]),
+    "dcc_status_string": (C.c_char_p, [C.c_int]),
+    "dcc_last_cuda_error": (C.c_char_p, []),
+    "dcc_abi_version": (C.c_int, []),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libdcc_b200.so and bind every declared symbol.  Raises DccError if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DccError("%s is missing: build it with `python -m dcc_b200.build` (nvcc, sm_100a). "
+                       "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        lib = load()
+        msg = lib.dcc_status_string(int(status)).decode()
+        if status == -2:
+            msg += ": " + lib.dcc_last_cuda_error().decode()
+        raise DccError("%s failed: %s (status %d)" % (what or "dcc call", msg, status))

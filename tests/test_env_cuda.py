@@ -1,0 +1,169 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA env path, called through the C ABI,
+against (1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on seeded
+random batches.  Bar: observations, UAV/PoI state, done / connect / connect_ / adjacency bit-exact;
+reward within 1e-6 relative of float32(reference float64 reward) (north_star asks 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import assert_step_matches, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REW_RTOL = 1e-6
+
+
+def _mk_cuda(g, E, numpy_compat=False):
+    from dcc_b200.envs import CudaVecEnv
+    c = g["cfg"]
+    # golden cfg stores the WORLD's values; reference_compat=False passes ours through unchanged
+    return CudaVecEnv(E, c["n_agents"], c["n_pois"], r_cover=c["r_cover"], r_comm=c["r_comm"],
+                      comm_r_scale=c["comm_r_scale"], comm_force_scale=c["contact_force"] / 100.0,
+                      reference_compat=False, pos_pois=g["poi"], numpy_compat=numpy_compat, want_connectivity=True)
+
+
+def _result(env, obs, rew, done, infos):
+    torch.cuda.synchronize()
+    pv, en = env.get_state()
+    cb = env.connect_bits.cpu().numpy()
+    return dict(obs=obs.cpu().numpy(), reward=rew.cpu().numpy()[:, 0, 0], done=done.cpu().numpy()[:, 0],
+                coverage_rate=infos.coverage_rate.cpu().numpy(), connect=(cb & 1).astype(bool),
+                connect_=((cb >> 1) & 1).astype(bool), adj=env.adj.cpu().numpy().view(np.uint32),
+                adj_=env.adj_s.cpu().numpy().view(np.uint32), pos_vel=pv, energy=en,
+                rew_all=rew.cpu().numpy(), done_all=done.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", golden_cases("traj"))
+def test_cuda_trajectory_vs_reference_golden(name):
+    g = load_golden(name)
+    E = 3  # replicas of the same env: also checks env indexing
+    env = _mk_cuda(g, E)
+    obs0 = env.reset()
+    torch.cuda.synchronize()
+    for e in range(E):
+        assert np.array_equal(obs0[e].cpu().numpy(), g["obs0"])
+    obs_at = {int(t): k for k, t in enumerate(g["obs_steps"])}
+    for t in range(g["cfg"]["T"]):
+        a = torch.from_numpy(np.repeat(g["actions"][t][None], E, 0)).cuda()
+        a_before = a.clone()
+        r = _result(env, *env.step(a))
+        assert torch.equal(a, a_before), "actions must not be mutated"
+        k = obs_at.get(t)
+        for e in range(E):
+            assert_step_matches(name, r, g, t, e=e, obs_ref=None if k is None else g["obs"][k],
+                                rew_rtol=REW_RTOL, rew_dtype=np.float32)
+        assert np.all(r["rew_all"] == r["rew_all"][:, :1]) and np.all(r["done_all"] == r["done_all"][:, :1])
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_cases("unit"))
+def test_cuda_unit_steps_vs_reference_golden(name):
+    g = load_golden(name)
+    K = g["cfg"]["K"]
+    env = _mk_cuda(g, K)
+    env.reset()
+    env.set_state(g["pos_vel_in"], g["energy_in"])
+    r = _result(env, *env.step(torch.from_numpy(g["actions"]).cuda()))
+    for k in range(K):
+        assert_step_matches(name, r, g, k, e=k, obs_ref=g["obs"][k], rew_rtol=REW_RTOL, rew_dtype=np.float32)
+    env.close()
+
+
+@pytest.mark.parametrize("N,M,E,force,steps", [(8, 64, 4096, 0.0, 12), (8, 64, 2048, 1.0, 12), (16, 256, 512, 1.0, 6),
+                                               (4, 20, 4099, 0.0, 12), (3, 21, 257, 1.0, 8), (5, 9, 130, 1.0, 8),
+                                               (32, 40, 64, 1.0, 4), (1, 3, 33, 0.0, 5), (2, 70, 65, 1.0, 6)])
+def test_cuda_batch_vs_oracle(N, M, E, force, steps):
+    """Seeded random batch, several steps, vs the CPU oracle: everything bit-exact (reward: fp32 of the
+    float64 oracle value up to 1e-6).  (3,21) and (5,9) have env blocks that are not 16-byte multiples
+    and take the non-bulk store path; E values that are not multiples of the CTA size cover ragged grids."""
+    from dcc_b200.envs import CudaVecEnv
+    from oracle.env_oracle import OracleEnv
+    rng = np.random.RandomState(N * 1000 + M)
+    poi = rng.uniform(-1, 1, (M, 2))
+    crs = 0.95
+    env = CudaVecEnv(E, N, M, comm_r_scale=crs, comm_force_scale=force, reference_compat=False, pos_pois=poi,
+                     want_connectivity=True)
+    orc = OracleEnv(E, N, M, poi, comm_r_scale=crs, contact_force=100.0 * force, n_threads=8)
+    pv = np.zeros((E, N, 4)); pv[..., :2] = rng.uniform(-1.45, 1.45, (E, N, 2)) * rng.uniform(0.1, 1, (E, 1, 1))
+    pv[..., 2:] = rng.uniform(-0.4, 0.4, (E, N, 2))
+    en = rng.randint(0, 8, (E, M)).astype(np.uint8)
+    en[::5] = np.where(rng.rand(*en[::5].shape) < 0.95, 6, 4)
+    env.reset(); env.set_state(pv, en); orc.set_state(pv, en)
+    n_done = 0
+    for t in range(steps):
+        a = (rng.standard_normal((E, N, 2)) * (1.0 + (t % 3))).astype(np.float32)
+        r = _result(env, *env.step(torch.from_numpy(a).cuda()))
+        o = orc.step(a)
+        for key in ("done", "connect", "connect_", "adj", "adj_", "energy", "pos_vel", "obs"):
+            assert np.array_equal(r[key], o[key]), "t=%d %s mismatch (%d envs)" % (
+                t, key, int(np.sum(np.any((r[key] != o[key]).reshape(E, -1), axis=1))))
+        ref = o["reward"].astype(np.float32)
+        assert np.all(np.abs(r["reward"] - ref) <= REW_RTOL * np.maximum(1.0, np.abs(ref))), "t=%d reward" % t
+        assert np.allclose(r["coverage_rate"], o["coverage_rate"], atol=1e-7)
+        n_done += int(o["done"].sum())
+    assert n_done > 0 or N == 1
+    env.close()
+
+
+def test_cuda_numpy_compat_matches_reference_shapes_and_golden():
+    g = load_golden("ship_4x20_random")
+    env = _mk_cuda(g, 2, numpy_compat=True)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.shape == (2, 4, 110)
+    assert np.array_equal(obs[0].astype(np.float32), g["obs0"])
+    obs_at = {int(t): k for k, t in enumerate(g["obs_steps"])}
+    for t in range(60):
+        a = np.repeat(g["actions"][t][None], 2, 0)
+        a0 = a.copy()
+        obs, rew, done, infos = env.step(a)
+        assert np.array_equal(a, a0)
+        assert obs.dtype == np.float64 and rew.dtype == np.float64 and rew.shape == (2, 4, 1)
+        assert done.dtype == bool and done.shape == (2, 4) and len(infos) == 2
+        assert np.array_equal(obs[1].astype(np.float32), g["obs"][obs_at[t]])
+        assert abs(rew[0, 0, 0] - np.float32(g["reward"][t])) <= REW_RTOL * max(1, abs(g["reward"][t]))
+        assert bool(done[0, 0]) == bool(g["done"][t])
+        assert abs(infos[1]["coverage_rate"] - g["coverage_rate"][t]) < 1e-6
+    env.close()
+
+
+def test_make_env_boundary():
+    from argparse import Namespace
+    from dcc_b200.envs import make_env
+    cfg = Namespace(env_file="mpe.uav_dcc", env_class="DCEnv", scenario_name="coverage", num_agents=4, num_pois=20,
+                    max_ep_len=150, r_cover=0.2, r_comm=0.4, comm_r_scale=0.95, comm_force_scale=0.0,
+                    n_rollout_threads=16, seed=0)
+    env = make_env(cfg)
+    assert env.n_envs == 16 and env.n_agents == 4 and len(env.observation_space) == 4
+    assert env.observation_space[0].shape == (110,) and env.share_observation_space[0].shape == (440,)
+    assert env.action_space[0].__class__.__name__ == "Box" and env.action_space[0].shape == (2,)
+    obs = env.reset()
+    assert tuple(obs.shape) == (16, 4, 110)
+    o, r, d, infos = env.step(torch.zeros(16, 4, 2, device="cuda"))
+    assert tuple(r.shape) == (16, 4, 1) and tuple(d.shape) == (16, 4) and d.dtype == torch.bool
+    assert "coverage_rate" in infos[0]
+    env.close()
+    cfg.env_file = "something_else"
+    with pytest.raises(NotImplementedError):
+        make_env(cfg)
+
+
+def test_launch_geometry_does_not_change_results():
+    from dcc_b200.envs import CudaVecEnv
+    rng = np.random.RandomState(5)
+    E, N, M = 1500, 8, 64
+    poi = rng.uniform(-1, 1, (M, 2))
+    a = torch.from_numpy(rng.standard_normal((4, E, N, 2)).astype(np.float32)).cuda()
+    outs = []
+    for wpc, ctas in ((4, 0), (1, 7), (8, 0), (16, 3), (2, 1000)):
+        env = CudaVecEnv(E, N, M, comm_force_scale=1.0, reference_compat=False, pos_pois=poi)
+        env.set_launch(wpc, ctas)
+        env.reset()
+        acc = []
+        for t in range(4):
+            o, r, d, i = env.step(a[t])
+            acc += [o.clone(), r.clone(), d.clone(), i.coverage_rate.clone()]
+        outs.append(acc)
+        env.close()
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
