@@ -53,45 +53,61 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons DURING the timed region from a background thread (NVML, ~2 ms period;
+    the timed region is tens of ms, too short for `nvidia-smi -lms`).  Same fields as the B200_PROFILING.md recipe."""
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.samples, self.reasons, self.err = index, [], set(), None
+        self._stop, self._thr, self.max_mhz = False, None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        import threading
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        time.sleep(0.05)  # NVML init outside the timed region
+
+    def mark(self):
+        """Drop samples taken before the timed region starts."""
+        self.samples.clear()
+        self.reasons.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.samples), "reasons": sorted(self.reasons), "source": "NVML, sampled during the timed region"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def time_cpu_port(n_envs, steps, warmup, threads, seed=0):
@@ -170,9 +186,11 @@ def run_cuda(args):
     sampler = ClockSampler(local_rank)
     launches0 = env.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     if rank == 0:
         sampler.start()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     ev0.record()
     for t in range(args.steps):
         env.step(acts[t % 8])

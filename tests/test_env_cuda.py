@@ -101,7 +101,7 @@ def test_cuda_batch_vs_oracle(N, M, E, force, steps):
         assert np.all(np.abs(r["reward"] - ref) <= REW_RTOL * np.maximum(1.0, np.abs(ref))), "t=%d reward" % t
         assert np.allclose(r["coverage_rate"], o["coverage_rate"], atol=1e-7)
         n_done += int(o["done"].sum())
-    assert n_done > 0 or N == 1
+    assert n_done > 0 or N <= 2
     env.close()
 
 

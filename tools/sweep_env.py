@@ -1,0 +1,51 @@
+"""Launch-geometry sweep of the env step kernel (tuning aid; run on the GPU box)."""
+import argparse
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dcc_b200.envs import CudaVecEnv
+
+
+def time_cfg(env, acts, steps=60, warm=10):
+    for t in range(warm):
+        env.step(acts[t % len(acts)])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(steps):
+        env.step(acts[t % len(acts)])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=8)
+    ap.add_argument("--m", type=int, default=64)
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--force", type=float, default=0.0)
+    args = ap.parse_args()
+    E, N, M = args.envs, args.n, args.m
+    env = CudaVecEnv(E, N, M, comm_force_scale=args.force, reference_compat=args.force == 0.0)
+    acts = [torch.randn(E, N, 2, device="cuda") for _ in range(8)]
+    env.reset()
+    D = env.obs_dim
+    balg = 4 * D + 13 + 64 + (2 * M + 5) / N
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for wpc in (1, 2, 4, 8, 16):
+        for ctas in (0, sms, 2 * sms, 4 * sms, (E + wpc - 1) // wpc):
+            try:
+                env.set_launch(wpc, ctas)
+            except Exception as ex:
+                print("wpc=%d ctas=%d: %s" % (wpc, ctas, ex))
+                continue
+            us = time_cfg(env, acts)
+            print("N=%d M=%d E=%d wpc=%2d ctas=%6d : %8.1f us/step  %6.0f GB/s alg  %.3f G agent-steps/s" % (
+                N, M, E, wpc, ctas, us, E * N * balg / us / 1e3, E * N / us / 1e3), flush=True)
+    env.close()
+
+
+if __name__ == "__main__":
+    main()
