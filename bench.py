@@ -261,7 +261,7 @@ def run_cuda(args):
                        "l2": "no flush needed: %.0f MB written per step > 126 MB L2" % (E * N * D * 4 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_agent_step": b_alg,
-                         "alg_bytes_per_launch": E * N * b_alg, "kernel": "dcc_env_kernel<true>",
+                         "alg_bytes_per_launch": E * N * b_alg, "kernel": "dcc_env_spec_kernel<8,64,true>",
                          "avg_launch_us": launch_s * 1e6},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

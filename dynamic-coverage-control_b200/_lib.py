@@ -41,6 +41,7 @@ SIGNATURES = {
     "dcc_env_set_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "dcc_env_state_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "dcc_env_set_launch": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "dcc_env_use_specialized": (C.c_int, [_VP, C.c_int]),
     "dcc_env_launch_count": (C.c_int64, [_VP]),
     "dcc_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
     "dcc_host_free": (C.c_int, [_VP]),

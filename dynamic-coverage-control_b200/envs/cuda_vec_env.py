@@ -115,6 +115,10 @@ class CudaVecEnv:
     def launch_count(self):
         return int(self.lib.dcc_env_launch_count(self._h))
 
+    def use_specialized(self, enable=True):
+        """Toggle the compile-time specialised kernel (4/20, 8/64, 16/256).  Returns True if it is in use."""
+        return bool(self.lib.dcc_env_use_specialized(self._h, 1 if enable else 0))
+
     def set_launch(self, warps_per_cta, ctas=0):
         _lib.check(self.lib.dcc_env_set_launch(self._h, int(warps_per_cta), int(ctas)), "dcc_env_set_launch")
 

@@ -146,6 +146,9 @@ int dcc_env_state_ptrs(void *handle, double **d_pos_vel, uint8_t **d_energy);
 
 /* Launch geometry knobs (tuning / tests).  warps_per_cta in {1,2,4,8,16}; ctas <= 0 = auto. */
 int dcc_env_set_launch(void *handle, int warps_per_cta, int ctas);
+/* (N, M) shapes with a compile-time specialised kernel (4/20, 8/64, 16/256) use it by default; enable = 0 forces the
+ * generic runtime-shape kernel (tests compare the two).  Returns 1 if the specialised kernel is in use, 0 if not. */
+int dcc_env_use_specialized(void *handle, int enable);
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t dcc_env_launch_count(void *handle);
 

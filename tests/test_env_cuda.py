@@ -33,11 +33,14 @@ def _result(env, obs, rew, done, infos):
                 rew_all=rew.cpu().numpy(), done_all=done.cpu().numpy())
 
 
+@pytest.mark.parametrize("spec", [True, False])
 @pytest.mark.parametrize("name", golden_cases("traj"))
-def test_cuda_trajectory_vs_reference_golden(name):
+def test_cuda_trajectory_vs_reference_golden(name, spec):
     g = load_golden(name)
     E = 3  # replicas of the same env: also checks env indexing
     env = _mk_cuda(g, E)
+    if env.use_specialized(spec) != spec:
+        pytest.skip("no specialised kernel for this shape (covered by the generic-kernel run)")
     obs0 = env.reset()
     torch.cuda.synchronize()
     for e in range(E):
@@ -69,10 +72,12 @@ def test_cuda_unit_steps_vs_reference_golden(name):
     env.close()
 
 
-@pytest.mark.parametrize("N,M,E,force,steps", [(8, 64, 4096, 0.0, 12), (8, 64, 2048, 1.0, 12), (16, 256, 512, 1.0, 6),
-                                               (4, 20, 4099, 0.0, 12), (3, 21, 257, 1.0, 8), (5, 9, 130, 1.0, 8),
-                                               (32, 40, 64, 1.0, 4), (1, 3, 33, 0.0, 5), (2, 70, 65, 1.0, 6)])
-def test_cuda_batch_vs_oracle(N, M, E, force, steps):
+@pytest.mark.parametrize("N,M,E,force,steps,spec", [
+    (8, 64, 4096, 0.0, 12, True), (8, 64, 2048, 1.0, 12, True), (8, 64, 2048, 1.0, 12, False),
+    (16, 256, 512, 1.0, 6, True), (16, 256, 300, 1.0, 6, False), (4, 20, 4099, 0.0, 12, True), (4, 20, 4099, 1.0, 12, False),
+    (3, 21, 257, 1.0, 8, False), (5, 9, 130, 1.0, 8, False), (32, 40, 64, 1.0, 4, False), (1, 3, 33, 0.0, 5, False),
+    (2, 70, 65, 1.0, 6, False)])
+def test_cuda_batch_vs_oracle(N, M, E, force, steps, spec):
     """Seeded random batch, several steps, vs the CPU oracle: everything bit-exact (reward: fp32 of the
     float64 oracle value up to 1e-6).  (3,21) and (5,9) have env blocks that are not 16-byte multiples
     and take the non-bulk store path; E values that are not multiples of the CTA size cover ragged grids."""
@@ -83,6 +88,7 @@ def test_cuda_batch_vs_oracle(N, M, E, force, steps):
     crs = 0.95
     env = CudaVecEnv(E, N, M, comm_r_scale=crs, comm_force_scale=force, reference_compat=False, pos_pois=poi,
                      want_connectivity=True)
+    assert env.use_specialized(spec) == spec  # compile-time specialised kernel vs generic runtime-shape kernel
     orc = OracleEnv(E, N, M, poi, comm_r_scale=crs, contact_force=100.0 * force, n_threads=8)
     pv = np.zeros((E, N, 4)); pv[..., :2] = rng.uniform(-1.45, 1.45, (E, N, 2)) * rng.uniform(0.1, 1, (E, 1, 1))
     pv[..., 2:] = rng.uniform(-0.4, 0.4, (E, N, 2))
@@ -154,9 +160,10 @@ def test_launch_geometry_does_not_change_results():
     poi = rng.uniform(-1, 1, (M, 2))
     a = torch.from_numpy(rng.standard_normal((4, E, N, 2)).astype(np.float32)).cuda()
     outs = []
-    for wpc, ctas in ((4, 0), (1, 7), (8, 0), (16, 3), (2, 1000)):
+    for wpc, ctas in ((4, 0), (1, 7), (8, 0), (16, 3), (2, 1000), (-4, 0), (-4, 5)):
         env = CudaVecEnv(E, N, M, comm_force_scale=1.0, reference_compat=False, pos_pois=poi)
-        env.set_launch(wpc, ctas)
+        env.use_specialized(wpc < 0)
+        env.set_launch(abs(wpc), ctas)
         env.reset()
         acc = []
         for t in range(4):

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--m", type=int, default=64)
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--force", type=float, default=0.0)
+    ap.add_argument("--generic", action="store_true")
     args = ap.parse_args()
     E, N, M = args.envs, args.n, args.m
     env = CudaVecEnv(E, N, M, comm_force_scale=args.force, reference_compat=args.force == 0.0)
@@ -34,8 +35,10 @@ def main():
     D = env.obs_dim
     balg = 4 * D + 13 + 64 + (2 * M + 5) / N
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for wpc in (1, 2, 4, 8, 16):
-        for ctas in (0, sms, 2 * sms, 4 * sms, (E + wpc - 1) // wpc):
+    spec = env.use_specialized(not args.generic)
+    print("specialised kernel:", spec)
+    for wpc in ((4,) if spec else (1, 2, 4, 8, 16)):
+        for ctas in (0, 4 * sms, 5 * sms, 8 * sms, 16 * sms, 32 * sms, (E + wpc - 1) // wpc // 4, (E + wpc - 1) // wpc // 2, (E + wpc - 1) // wpc):
             try:
                 env.set_launch(wpc, ctas)
             except Exception as ex:
