@@ -1,0 +1,136 @@
+"""Generate MAPPO golden vectors by running the UNMODIFIED reference learner
+(/root/reference/uav_dcc_control: learner.py, algos/mappo.py, algos/r_actor_critic.py, buffer/shared_buffer.py,
+utils/valuenorm.py) for two iterations on a small config, via the stub shim.
+
+    python tests/golden/make_golden_mappo.py        # writes tests/golden/mappo_*.npz
+
+Harness-only changes (the arithmetic is the reference's own): SubprocVecEnv is swapped for the reference's
+in-process DummyVecEnv, the scenario's hard-coded 4/20 is lifted through GenScenario for other shapes, and the
+networks' parameters are overwritten with the seeded recipe in tests/mappo_util.py so the fixture does not
+have to store megabytes of initial weights.
+
+Per iteration it records the rollout buffer the reference collected (obs, sampled actions, log-probs, value
+predictions, rewards, masks, GAE returns), the ValueNorm state before/after, lr, train_info and the
+post-update parameters (small tensors in full; big ones as a strided sample + float64 sum / sum of squares).
+"""
+import json
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from ref_harness import REF_ROOT, load_reference  # noqa: E402
+from mappo_util import actor_param_shapes, critic_param_shapes, make_params, sample_tensor  # noqa: E402
+
+
+def build_learner(N, M, E, T, hidden, ppo_epoch, seed, force_scale=0.0):
+    import torch
+    ref = load_reference()
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        from omegaconf import OmegaConf
+        import utils.pytorch_utils as ptu
+        import envs.make_env as mk
+        import envs.mpe.uav_dcc as uav
+        from learner import Learner
+        cfg = OmegaConf.merge(OmegaConf.load("./config/env_config/dcc.yaml"),
+                              OmegaConf.load("./config/algo_config/mappo.yaml"), OmegaConf.load("./config/expt.yaml"))
+    finally:
+        os.chdir(cwd)
+    ptu.set_gpu_mode(False, 0)
+    torch.set_num_threads(1)
+    cfg.update(num_agents=N, num_pois=M, n_rollout_threads=E, n_eval_rollout_threads=0, n_render_rollout_threads=0,
+               max_ep_len=T, algo_hidden_size=hidden, ppo_epoch=ppo_epoch, log_wandb=False, save_model=False,
+               seed=seed, comm_force_scale=force_scale)
+    mk.SubprocVecEnv = ref["wrappers"].DummyVecEnv          # in-process fan-out, same auto-reset rule
+    if (N, M) != (4, 20) or force_scale > 0:
+        Gen = ref["GenScenario"]
+
+        class _Mod:
+            Scenario = Gen
+        uav.scenarios = Namespace(load=lambda name: _Mod)  # only make_world's literals are lifted
+    else:
+        uav.scenarios = ref["scenarios"]
+    lr = Learner(cfg)
+    return lr, cfg
+
+
+def set_params(module, params):
+    import torch
+    sd = module.state_dict()
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), (k, sd[k].shape, v.shape)
+        sd[k] = torch.from_numpy(v.copy())
+    module.load_state_dict(sd)
+
+
+def vn_state(vn):
+    return np.array([float(vn.running_mean[0] if vn.running_mean.ndim else vn.running_mean),
+                     float(vn.running_mean_sq[0] if vn.running_mean_sq.ndim else vn.running_mean_sq),
+                     float(vn.debiasing_term)], dtype=np.float64)
+
+
+def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2):
+    lr, cfg = build_learner(N, M, E, T, hidden, ppo_epoch, seed)
+    D = lr.obs_dim_n[0]
+    a_shapes, c_shapes = actor_param_shapes(D, hidden), critic_param_shapes(N * D, hidden)
+    set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
+    set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
+    out = {}
+    buf = lr.rl_buffer
+    for it in range(1, iters + 1):
+        lr.trainer.policy.lr_decay(it, cfg.n_iters)
+        lrate = lr.policy.actor_optimizer.param_groups[0]["lr"]
+        vn0 = vn_state(lr.trainer.value_normalizer)
+        info = lr.rollout(buf, lr.train_envs)
+        p = "it%d_" % it
+        out[p + "obs"] = buf.obs.copy()
+        out[p + "actions"] = buf.actions.copy()
+        out[p + "logp"] = buf.action_log_probs[..., 0:1].copy()
+        assert np.array_equal(buf.action_log_probs[..., 0], buf.action_log_probs[..., 1])
+        assert np.array_equal(buf.share_obs[:, :, 0], buf.obs.reshape(T + 1, E, -1))
+        out[p + "value_preds"] = buf.value_preds.copy()
+        out[p + "rewards"] = buf.rewards.copy()
+        out[p + "masks"] = buf.masks.copy()
+        out[p + "returns"] = buf.returns.copy()
+        out[p + "vn_before"] = vn0
+        out[p + "lr"] = np.array(lrate)
+        out[p + "rollout_info"] = np.array([info["reward"], info["coverage_rate"]])
+        tinfo = lr.rl_update()
+        out[p + "train_info"] = np.array([float(tinfo[k]) for k in ("value_loss", "policy_loss", "dist_entropy",
+                                                                    "actor_grad_norm", "critic_grad_norm", "ratio")])
+        out[p + "vn_after"] = vn_state(lr.trainer.value_normalizer)
+        for tag, mod, shapes in (("actor", lr.policy.actor, a_shapes), ("critic", lr.policy.critic, c_shapes)):
+            sd = mod.state_dict()
+            for k in shapes:
+                s = sample_tensor(sd[k].numpy())
+                key = p + tag + "." + k
+                out[key + ":sample"] = s["sample"]
+                out[key + ":meta"] = np.array([s["stride"], s["sum"], s["sumsq"]], dtype=np.float64)
+        print(name, "iter", it, "rollout", info, "train", {k: round(float(v), 6) for k, v in tinfo.items()})
+    meta = dict(name=name, n_agents=N, n_pois=M, n_envs=E, T=T, hidden=hidden, ppo_epoch=ppo_epoch, seed=seed,
+                iters=iters, obs_dim=D, actor_seed=seed * 2 + 1, critic_seed=seed * 2 + 2,
+                gamma=cfg.gamma, gae_lambda=cfg.gae_lambda, clip_param=cfg.clip_param, entropy_coef=cfg.entropy_coef,
+                value_loss_coef=cfg.value_loss_coef, max_grad_norm=cfg.max_grad_norm, huber_delta=cfg.huber_delta,
+                actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr, opti_eps=cfg.opti_eps, n_iters=cfg.n_iters)
+    out["cfg"] = np.array(json.dumps(meta))
+    path = os.path.join(HERE, "mappo_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.0f KB" % (os.path.getsize(path) / 1024))
+    lr.train_envs.close()
+
+
+def main():
+    load_reference()
+    run_case("ship_4x20_h256", 4, 20, 4, 30, 256, 15, seed=0)     # shipped shapes + hyper-parameters, short rollout
+    run_case("gen_8x64_h64", 8, 64, 2, 12, 64, 4, seed=1)         # BASELINE shape, small hidden size
+    run_case("gen_3x20_h32", 3, 20, 3, 10, 32, 3, seed=2)
+
+
+if __name__ == "__main__":
+    main()

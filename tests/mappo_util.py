@@ -1,0 +1,54 @@
+"""Shared by the MAPPO golden generator (reference side) and the parity tests (product side):
+deterministic parameter recipe with the reference's state_dict key names."""
+import numpy as np
+
+
+def actor_param_shapes(obs_dim, hidden, act_dim=2):
+    return {
+        "base.feature_norm.weight": (obs_dim,), "base.feature_norm.bias": (obs_dim,),
+        "base.mlp.fc1.0.weight": (hidden, obs_dim), "base.mlp.fc1.0.bias": (hidden,),
+        "base.mlp.fc1.2.weight": (hidden,), "base.mlp.fc1.2.bias": (hidden,),
+        "base.mlp.fc2.0.0.weight": (hidden, hidden), "base.mlp.fc2.0.0.bias": (hidden,),
+        "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
+        "act.action_out.fc_mean.weight": (act_dim, hidden), "act.action_out.fc_mean.bias": (act_dim,),
+        "act.action_out.logstd._bias": (act_dim, 1),
+    }
+
+
+def critic_param_shapes(share_dim, hidden):
+    return {
+        "base.feature_norm.weight": (share_dim,), "base.feature_norm.bias": (share_dim,),
+        "base.mlp.fc1.0.weight": (hidden, share_dim), "base.mlp.fc1.0.bias": (hidden,),
+        "base.mlp.fc1.2.weight": (hidden,), "base.mlp.fc1.2.bias": (hidden,),
+        "base.mlp.fc2.0.0.weight": (hidden, hidden), "base.mlp.fc2.0.0.bias": (hidden,),
+        "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
+        "v_out.weight": (1, hidden), "v_out.bias": (1,),
+    }
+
+
+def make_params(shapes, seed):
+    """Seeded, platform-independent parameter values (numpy Generator): non-trivial LN affine, biases and logstd so
+    that every term of the forward/backward is exercised (the reference's own init has zero biases and logstd)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shp in shapes.items():
+        if name.endswith("logstd._bias"):
+            v = rng.normal(0.0, 0.15, shp)
+        elif "feature_norm.weight" in name or name.endswith(".2.weight"):
+            v = 1.0 + rng.normal(0.0, 0.1, shp)
+        elif name.endswith("bias"):
+            v = rng.normal(0.0, 0.05, shp)
+        elif "fc_mean.weight" in name:
+            v = rng.normal(0.0, 0.3 / np.sqrt(shp[1]), shp)
+        else:  # Linear weights (out, in)
+            v = rng.normal(0.0, np.sqrt(2.0 / shp[1]), shp)
+        out[name] = v.astype(np.float32)
+    return out
+
+
+def sample_tensor(a, max_full=4096):
+    """Golden-side compression of a big 'after' tensor: strided sample + float64 sum / sum of squares."""
+    flat = np.asarray(a, dtype=np.float32).reshape(-1)
+    stride = 1 if flat.size <= max_full else int(np.ceil(flat.size / max_full))
+    return dict(stride=stride, sample=flat[::stride].copy(), sum=float(flat.astype(np.float64).sum()),
+                sumsq=float((flat.astype(np.float64) ** 2).sum()))
