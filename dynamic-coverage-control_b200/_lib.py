@@ -26,6 +26,17 @@ class EnvCfg(C.Structure):
     ]
 
 
+class MappoCfg(C.Structure):
+    """struct dcc_mappo_cfg (include/dcc_b200.h)."""
+    _fields_ = [
+        ("n_agents", C.c_int32), ("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32),
+        ("chunk_rows", C.c_int32), ("gemm_backend", C.c_int32),
+        ("clip_param", C.c_float), ("entropy_coef", C.c_float), ("value_loss_coef", C.c_float),
+        ("huber_delta", C.c_float), ("max_grad_norm", C.c_float), ("gamma", C.c_float), ("gae_lambda", C.c_float),
+        ("opti_eps", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("vn_beta", C.c_double),
+    ]
+
+
 _VP = C.c_void_p
 # name -> (restype, argtypes); every symbol include/dcc_b200.h declares
 SIGNATURES = {
@@ -43,6 +54,22 @@ SIGNATURES = {
     "dcc_env_set_launch": (C.c_int, [_VP, C.c_int, C.c_int]),
     "dcc_env_use_specialized": (C.c_int, [_VP, C.c_int]),
     "dcc_env_launch_count": (C.c_int64, [_VP]),
+    "dcc_mappo_cfg_default": (C.c_int, [C.POINTER(MappoCfg)]),
+    "dcc_mappo_create": (C.c_int, [C.POINTER(MappoCfg), C.c_int, C.POINTER(_VP)]),
+    "dcc_mappo_destroy": (C.c_int, [_VP]),
+    "dcc_mappo_param_count": (C.c_int64, [_VP, C.c_int]),
+    "dcc_mappo_chunk_rows": (C.c_int, [_VP]),
+    "dcc_mappo_gemm_backend": (C.c_int, [_VP]),
+    "dcc_mappo_launch_count": (C.c_int64, [_VP]),
+    "dcc_mappo_act": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _VP, _VP, _VP, _VP]),
+    "dcc_mappo_evaluate": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "dcc_rollout_insert": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "dcc_mappo_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_mappo_train_begin": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_mappo_epoch_grads": (C.c_int, [_VP] * 12 + [C.c_double, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_mappo_apply": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, C.c_float, C.c_int64, _VP, _VP]),
+    "dcc_op_gemm": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP, C.c_int,
+                              _VP, C.c_int, C.c_int, _VP]),
     "dcc_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
     "dcc_host_free": (C.c_int, [_VP]),
     "dcc_status_string": (C.c_char_p, [C.c_int]),

@@ -1,0 +1,396 @@
+"""MAPPOPolicy / MAPPOTrainer — the reference's algo boundary (algos/mappo.py:15-247) on the CUDA learner kernels.
+
+Same class names, method names, argument order and return values as the reference, so `Learner` reads the same;
+the bodies call the C ABI (`dcc_mappo_*`, include/dcc_b200.h) instead of torch.nn / autograd:
+
+  MAPPOPolicy.get_actions / get_values / act / evaluate_actions  -> dcc_mappo_act / dcc_mappo_evaluate
+  MAPPOPolicy.lr_decay                                           -> utils/util.py:29-33 (a float, no kernel)
+  MAPPOTrainer.train                                             -> dcc_mappo_train_begin, then per epoch
+                                                                    dcc_mappo_epoch_grads [+ all-reduce] + dcc_mappo_apply x2
+
+Parameters live in flat float32 CUDA tensors (layout in include/dcc_b200.h); `state_dict()` / `load_state_dict()`
+speak the reference's key names so weights round-trip with reference checkpoints.
+Tensors in, tensors out: no numpy on the hot path.  There is no fallback: a missing library raises DccError.
+"""
+import ctypes as C
+import math
+import os
+import pickle
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..parallel import Comm
+from .valuenorm import ValueNorm
+
+TRUNK = ("base.feature_norm.weight", "base.feature_norm.bias", "base.mlp.fc1.0.weight", "base.mlp.fc1.0.bias",
+         "base.mlp.fc1.2.weight", "base.mlp.fc1.2.bias", "base.mlp.fc2.0.0.weight", "base.mlp.fc2.0.0.bias",
+         "base.mlp.fc2.0.2.weight", "base.mlp.fc2.0.2.bias")
+FC_H = ("base.mlp.fc_h.0.weight", "base.mlp.fc_h.0.bias", "base.mlp.fc_h.2.weight", "base.mlp.fc_h.2.bias")
+
+
+def net_layout(in_dim, hidden, out_dim, head, logstd=False):
+    """name -> (offset, shape) of the flat parameter buffer, in the order include/dcc_b200.h documents."""
+    shapes = [(in_dim,), (in_dim,), (hidden, in_dim), (hidden,), (hidden,), (hidden,), (hidden, hidden), (hidden,),
+              (hidden,), (hidden,)]
+    lay, off = OrderedDict(), 0
+    for k, shp in zip(TRUNK, shapes):
+        lay[k] = (off, shp)
+        off += int(np.prod(shp))
+    lay[head + ".weight"] = (off, (out_dim, hidden)); off += out_dim * hidden
+    lay[head + ".bias"] = (off, (out_dim,)); off += out_dim
+    if logstd:
+        lay["act.action_out.logstd._bias"] = (off, (out_dim, 1)); off += out_dim
+    return lay, off
+
+
+def _reference_init(in_dim, hidden, out_dim, head_gain):
+    """Initial parameters drawn exactly as the reference constructs a net (same torch RNG consumption order):
+    MLPBase -> LayerNorm, fc1 = Linear+orthogonal(gain sqrt 2), fc_h likewise, fc2 = deepcopy(fc_h)
+    (algos/algo_utils/mlp.py:13-23), then the head Linear with orthogonal(gain) (distributions.py:76-80,
+    r_actor_critic.py:101-107).  Host-side torch, construction time only."""
+    import torch.nn as nn
+    gain = nn.init.calculate_gain("relu")
+
+    def lin(i, o, g):
+        m = nn.Linear(i, o)
+        nn.init.orthogonal_(m.weight.data, gain=g)
+        nn.init.constant_(m.bias.data, 0)
+        return m
+    fc1 = lin(in_dim, hidden, gain)
+    fc_h = lin(hidden, hidden, gain)
+    head = lin(hidden, out_dim, head_gain)
+    ones, zeros = torch.ones, torch.zeros
+    sd = OrderedDict()
+    sd["base.feature_norm.weight"], sd["base.feature_norm.bias"] = ones(in_dim), zeros(in_dim)
+    sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"] = fc1.weight.data.clone(), fc1.bias.data.clone()
+    sd["base.mlp.fc1.2.weight"], sd["base.mlp.fc1.2.bias"] = ones(hidden), zeros(hidden)
+    sd["base.mlp.fc_h.0.weight"], sd["base.mlp.fc_h.0.bias"] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
+    sd["base.mlp.fc_h.2.weight"], sd["base.mlp.fc_h.2.bias"] = ones(hidden), zeros(hidden)
+    sd["base.mlp.fc2.0.0.weight"], sd["base.mlp.fc2.0.0.bias"] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
+    sd["base.mlp.fc2.0.2.weight"], sd["base.mlp.fc2.0.2.bias"] = ones(hidden), zeros(hidden)
+    return sd, head
+
+
+class _Net:
+    """Flat parameter / gradient / Adam-moment storage of one network + its named views."""
+
+    def __init__(self, layout, total, grad_storage, device):
+        self.layout, self.total = layout, total
+        self.params = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grads = grad_storage
+        self.adam_m = torch.zeros(total, dtype=torch.float32, device=device)
+        self.adam_v = torch.zeros(total, dtype=torch.float32, device=device)
+        self.adam_step = 0
+        self.fc_h = {}   # the never-used fc_h block (mlp.py:21-23): kept only so checkpoints round-trip
+
+    def view(self, name, which="params"):
+        off, shp = self.layout[name]
+        return getattr(self, which)[off:off + int(np.prod(shp))].view(*shp)
+
+    def state_dict(self):
+        sd = OrderedDict()
+        for k in self.layout:
+            sd[k] = self.view(k).detach().clone()
+            if k == "base.mlp.fc1.2.bias":
+                for kk in FC_H:
+                    if kk in self.fc_h:
+                        sd[kk] = self.fc_h[kk].clone()
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        for k in self.layout:
+            if k not in sd:
+                if strict:
+                    raise KeyError("missing key %s" % k)
+                continue
+            v = torch.as_tensor(np.asarray(sd[k].detach().cpu() if isinstance(sd[k], torch.Tensor) else sd[k]),
+                                dtype=torch.float32)
+            off, shp = self.layout[k]
+            if int(v.numel()) != int(np.prod(shp)):
+                raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(v.shape), shp))
+            self.view(k).copy_(v.reshape(*shp))
+        for kk in FC_H:
+            if kk in sd:
+                self.fc_h[kk] = torch.as_tensor(np.asarray(sd[kk].detach().cpu() if isinstance(sd[kk], torch.Tensor)
+                                                           else sd[kk]), dtype=torch.float32)
+
+
+class MAPPOPolicy:
+    """algos/mappo.py:15-65.  obs_space / cent_obs_space / act_space: objects with `.shape` (gym-like Box)."""
+
+    def __init__(self, cfg, obs_space, cent_obs_space, act_space, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DccError("MAPPOPolicy needs a CUDA device (sm_100); there is no CPU fallback")
+        if act_space.__class__.__name__ != "Box":
+            raise NotImplementedError("only the continuous Box(2) action space of the env is implemented")
+        from ..utils.config import check_supported
+        check_supported(cfg)
+        self.device = torch.device("cuda", int(getattr(cfg, "device", 0) or 0)) if device is None else torch.device(device)
+        self.actor_lr, self.critic_lr = float(cfg.actor_lr), float(cfg.critic_lr)
+        self.opti_eps, self.weight_decay = float(cfg.opti_eps), float(cfg.weight_decay)
+        self.obs_space, self.share_obs_space, self.act_space = obs_space, cent_obs_space, act_space
+        self.obs_dim = int(obs_space.shape[0])
+        self.share_dim = int(cent_obs_space.shape[0])
+        if self.share_dim % self.obs_dim:
+            raise ValueError("centralised obs dim %d is not a multiple of obs dim %d" % (self.share_dim, self.obs_dim))
+        self.n_agents = self.share_dim // self.obs_dim
+        self.hidden = int(cfg.algo_hidden_size)
+        self.act_dim = int(act_space.shape[0])
+
+        mc = _lib.MappoCfg()
+        _lib.check(self.lib.dcc_mappo_cfg_default(C.byref(mc)), "dcc_mappo_cfg_default")
+        mc.n_agents, mc.obs_dim, mc.hidden, mc.act_dim = self.n_agents, self.obs_dim, self.hidden, self.act_dim
+        mc.chunk_rows = int(getattr(cfg, "chunk_rows", 0) or 0)
+        mc.gemm_backend = int(getattr(cfg, "gemm_backend", 0) or 0)
+        mc.clip_param, mc.entropy_coef = float(cfg.clip_param), float(cfg.entropy_coef)
+        mc.value_loss_coef, mc.huber_delta = float(cfg.value_loss_coef), float(cfg.huber_delta)
+        mc.max_grad_norm, mc.gamma, mc.gae_lambda = float(cfg.max_grad_norm), float(cfg.gamma), float(cfg.gae_lambda)
+        mc.opti_eps = self.opti_eps
+        self.mcfg = mc
+        h = C.c_void_p()
+        _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
+        self._h = h
+
+        la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True)
+        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out")
+        assert na == self.lib.dcc_mappo_param_count(h, 0) and nc == self.lib.dcc_mappo_param_count(h, 1)
+        # one flat gradient buffer for both nets: a single all-reduce per PPO epoch
+        self.flat_grads = torch.zeros(na + nc, dtype=torch.float32, device=self.device)
+        self.actor = _Net(la, na, self.flat_grads[:na], self.device)
+        self.critic = _Net(lc, nc, self.flat_grads[na:], self.device)
+        # initial weights: the reference's construction order — actor first, then critic (mappo.py:27-28)
+        sd, head = _reference_init(self.obs_dim, self.hidden, self.act_dim, float(cfg.gain))
+        sd["act.action_out.fc_mean.weight"], sd["act.action_out.fc_mean.bias"] = head.weight.data, head.bias.data
+        sd["act.action_out.logstd._bias"] = torch.zeros(self.act_dim, 1)
+        self.actor.load_state_dict(sd)
+        sd, head = _reference_init(self.share_dim, self.hidden, 1, 1.0)
+        sd["v_out.weight"], sd["v_out.bias"] = head.weight.data, head.bias.data
+        self.critic.load_state_dict(sd)
+
+        self.lr_actor_now, self.lr_critic_now = self.actor_lr, self.critic_lr
+        self.seed = int(getattr(cfg, "seed", 0))
+        self._rng_offset = 0
+        self._scratch = {}
+
+    # ---- helpers -----------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _out(self, key, shape):
+        t = self._scratch.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    def _as_obs(self, obs):
+        if not (isinstance(obs, torch.Tensor) and obs.is_cuda and obs.dtype == torch.float32):
+            obs = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device)
+        obs = obs.contiguous()
+        n = obs.numel() // (self.n_agents * self.obs_dim)
+        if n * self.n_agents * self.obs_dim != obs.numel():
+            raise ValueError("obs has %d elements, not a multiple of N*D = %d" % (obs.numel(), self.n_agents * self.obs_dim))
+        return obs, n
+
+    def launch_count(self):
+        return int(self.lib.dcc_mappo_launch_count(self._h))
+
+    def gemm_backend(self):
+        return {1: "simt-fp32", 2: "tcgen05-3xtf32"}[int(self.lib.dcc_mappo_gemm_backend(self._h))]
+
+    # ---- reference surface ---------------------------------------------------------------------------------
+    def lr_decay(self, episode, episodes):
+        """update_linear_schedule (utils/util.py:29-33) for both optimisers."""
+        self.lr_actor_now = max(self.actor_lr - self.actor_lr * (episode / float(episodes)), 0.0)
+        self.lr_critic_now = max(self.critic_lr - self.critic_lr * (episode / float(episodes)), 0.0)
+
+    def get_actions(self, cent_obs, obs, rnn_states_actor=None, rnn_states_critic=None, masks=None,
+                    available_actions=None, deterministic=False, out_actions=None, out_logp=None, out_values=None):
+        """obs: (E*N, D) or (E, N, D) CUDA float32, the env's observation buffer.  cent_obs is accepted for signature
+        parity and NOT read: the centralised input of env e is its N obs rows concatenated (learner.py:219-220),
+        i.e. the same memory, evaluated once per env instead of N identical times.
+        Returns (values (E*N,1), actions (E*N,2), action_log_probs (E*N,1), rnn_states_actor, rnn_states_critic)."""
+        obs, n = self._as_obs(obs)
+        N = self.n_agents
+        actions = out_actions if out_actions is not None else self._out("actions", (n * N, 2))
+        logp = out_logp if out_logp is not None else self._out("logp", (n * N,))
+        values = out_values if out_values is not None else self._out("values", (n,))
+        self._rng_offset += 1
+        _lib.check(self.lib.dcc_mappo_act(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
+                                          self._ptr(obs), n, self.seed, self._rng_offset, 1 if deterministic else 0,
+                                          self._ptr(actions), self._ptr(logp), self._ptr(values), self._stream()),
+                   "dcc_mappo_act")
+        v = values.view(n, 1).expand(n, N).reshape(n * N, 1)
+        return v, actions.view(n * N, 2), logp.view(n * N, 1), rnn_states_actor, rnn_states_critic
+
+    def get_values(self, cent_obs, rnn_states_critic=None, masks=None, out_values=None, rows_repeated=False):
+        """cent_obs: (E, N*D), or the obs buffer (E, N, D) — one centralised row per env.  rows_repeated=True takes the
+        reference's layout instead, (E*N, N*D) with N identical rows per env (learner.py:281-285), and evaluates
+        every N-th row.  Returns (E*N, 1), the reference's shape."""
+        N, S = self.n_agents, self.share_dim
+        if not (isinstance(cent_obs, torch.Tensor) and cent_obs.is_cuda and cent_obs.dtype == torch.float32):
+            cent_obs = torch.as_tensor(np.asarray(cent_obs), dtype=torch.float32).to(self.device)
+        if rows_repeated:
+            cent_obs = cent_obs.reshape(-1, S)[::N]
+        cent_obs = cent_obs.contiguous()
+        n = cent_obs.numel() // S
+        if n * S != cent_obs.numel():
+            raise ValueError("cent_obs has %d elements, not a multiple of N*D = %d" % (cent_obs.numel(), S))
+        values = out_values if out_values is not None else self._out("values", (n,))
+        _lib.check(self.lib.dcc_mappo_act(self._h, None, self._ptr(self.critic.params), self._ptr(cent_obs), n, 0, 0, 0,
+                                          None, None, self._ptr(values), self._stream()), "dcc_mappo_act(values)")
+        return values.view(n, 1).expand(n, N).reshape(n * N, 1)
+
+    def evaluate_actions(self, cent_obs, obs, rnn_states_actor, rnn_states_critic, action, masks=None,
+                         available_actions=None, active_masks=None):
+        """Forward-only evaluation: returns (values (B,1), action_log_probs (B,1), dist_entropy scalar tensor)."""
+        obs, n = self._as_obs(obs)
+        N = self.n_agents
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
+        logp = self._out("ev_logp", (n * N,))
+        values = self._out("ev_values", (n,))
+        _lib.check(self.lib.dcc_mappo_evaluate(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
+                                               self._ptr(obs), self._ptr(action), n, self._ptr(logp), self._ptr(values),
+                                               None, self._stream()), "dcc_mappo_evaluate")
+        logstd = self.actor.view("act.action_out.logstd._bias")
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum()
+        return values.view(n, 1).expand(n, N).reshape(n * N, 1), logp.view(n * N, 1), ent
+
+    def act(self, obs, rnn_states_actor=None, masks=None, available_actions=None, deterministic=False):
+        obs, n = self._as_obs(obs)
+        actions = self._out("actions", (n * self.n_agents, 2))
+        self._rng_offset += 1
+        _lib.check(self.lib.dcc_mappo_act(self._h, self._ptr(self.actor.params), None, self._ptr(obs), n, self.seed,
+                                          self._rng_offset, 1 if deterministic else 0, self._ptr(actions), None, None,
+                                          self._stream()), "dcc_mappo_act(actor)")
+        return actions, rnn_states_actor
+
+    # ---- checkpoints -----------------------------------------------------------------------------------------
+    def state_dict(self):
+        return {"actor": self.actor.state_dict(), "critic": self.critic.state_dict(),
+                "actor_optimizer": {"step": self.actor.adam_step, "exp_avg": self.actor.adam_m.clone(),
+                                    "exp_avg_sq": self.actor.adam_v.clone()},
+                "critic_optimizer": {"step": self.critic.adam_step, "exp_avg": self.critic.adam_m.clone(),
+                                     "exp_avg_sq": self.critic.adam_v.clone()}}
+
+    def load_state_dict(self, sd):
+        self.actor.load_state_dict(sd["actor"])
+        self.critic.load_state_dict(sd["critic"])
+        for net, key in ((self.actor, "actor_optimizer"), (self.critic, "critic_optimizer")):
+            if key in sd:
+                net.adam_step = int(sd[key]["step"])
+                net.adam_m.copy_(sd[key]["exp_avg"])
+                net.adam_v.copy_(sd[key]["exp_avg_sq"])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dcc_mappo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MAPPOTrainer:
+    """algos/mappo.py:68-247.  `train(buffer)` runs the reference's update — advantage normalisation, ppo_epoch
+    passes over the whole rollout as one minibatch, ValueNorm update each epoch, separate grad-norm clips, two
+    Adam steps — as kernels; with a process group, gradients are all-reduced once per epoch."""
+
+    def __init__(self, cfg, policy, agent_id=0, comm=None):
+        self.policy = policy
+        self.clip_param = cfg.clip_param
+        self.ppo_epoch = int(cfg.ppo_epoch)
+        self.num_mini_batch = int(cfg.num_mini_batch)
+        self.value_loss_coef = cfg.value_loss_coef
+        self.entropy_coef = cfg.entropy_coef
+        self.max_grad_norm = cfg.max_grad_norm
+        self.huber_delta = cfg.huber_delta
+        self._use_valuenorm = cfg.use_valuenorm
+        self.value_normalizer = ValueNorm(1, device=policy.device)
+        self.comm = comm if comm is not None else Comm()
+        dev = policy.device
+        self._stats4 = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._epoch_stats = torch.zeros((self.ppo_epoch, 4), dtype=torch.float64, device=dev)
+        self._gnorm_sq = torch.zeros((self.ppo_epoch, 2), dtype=torch.float64, device=dev)
+        self.training = False
+
+    def train(self, buffer, update_actor=True):
+        p, lib = self.policy, self.policy.lib
+        T, E, N = buffer.episode_length, buffer.n_rollout_threads, p.n_agents
+        s = p._stream()
+        ptr = p._ptr
+        vn = self.value_normalizer.state
+        _lib.check(lib.dcc_mappo_train_begin(p._h, ptr(buffer.returns_te), ptr(buffer.values_te), ptr(vn), T, E,
+                                             ptr(self._stats4), s), "dcc_mappo_train_begin")
+        self.comm.all_reduce_sum_(self._stats4)
+        rows_global = float(T) * float(E) * self.comm.world if getattr(buffer, "n_envs_global", None) is None \
+            else float(T) * float(buffer.n_envs_global)
+        self._epoch_stats.zero_()
+        self._gnorm_sq.zero_()
+        for ep in range(self.ppo_epoch):
+            _lib.check(lib.dcc_mappo_epoch_grads(
+                p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
+                ptr(buffer.obs), ptr(buffer.actions), ptr(buffer.action_log_probs_ten), ptr(buffer.values_te),
+                ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, T, E, ptr(self._epoch_stats[ep]), s),
+                "dcc_mappo_epoch_grads")
+            self.comm.all_reduce_sum_(p.flat_grads)            # the one data-path collective
+            for which, net, lr in ((0, p.actor, p.lr_actor_now), (1, p.critic, p.lr_critic_now)):
+                if which == 0 and not update_actor:
+                    continue
+                net.adam_step += 1
+                _lib.check(lib.dcc_mappo_apply(p._h, which, ptr(net.params), ptr(net.grads), ptr(net.adam_m),
+                                               ptr(net.adam_v), float(lr), net.adam_step,
+                                               ptr(self._gnorm_sq[ep, which:which + 1]), s), "dcc_mappo_apply")
+        # epoch sums -> the reference's train_info (means over epochs; one device->host read per update)
+        es = self._epoch_stats.clone()
+        es[:, 3] = 0
+        self.comm.all_reduce_sum_(es)
+        es = es.cpu().numpy()
+        ent = self._epoch_stats[:, 3].cpu().numpy()
+        gn = np.sqrt(self._gnorm_sq.cpu().numpy())
+        B = rows_global * N
+        k = float(self.ppo_epoch * self.num_mini_batch)
+        return {"value_loss": float(es[:, 1].sum() / B / k), "policy_loss": float(es[:, 0].sum() / B / k),
+                "dist_entropy": float(ent.sum() / k), "actor_grad_norm": float(gn[:, 0].sum() / k),
+                "critic_grad_norm": float(gn[:, 1].sum() / k), "ratio": float(es[:, 2].sum() / B / k)}
+
+    def prep_training(self):
+        self.training = True
+
+    def prep_rollout(self):
+        self.training = False
+
+    def save_model(self, save_path):
+        """Reference: pickle of the policy object (mappo.py:237-240).  Here: a pickle of plain CPU tensors keyed by
+        the reference's state_dict names (+ Adam moments and the ValueNorm state, which the reference drops)."""
+        sd = self.policy.state_dict()
+        sd["value_normalizer"] = self.value_normalizer.state_dict()
+        cpu = _to_cpu(sd)
+        with open(os.path.join(save_path, "agent.pkl"), "wb") as f:
+            pickle.dump(cpu, f)
+
+    def load_model(self, load_path):
+        with open(os.path.join(load_path, "agent.pkl"), "rb") as f:
+            sd = pickle.load(f)
+        self.policy.load_state_dict(sd)
+        if "value_normalizer" in sd:
+            self.value_normalizer.load_state_dict(sd["value_normalizer"])
+
+
+def _to_cpu(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu()
+    if isinstance(x, dict):
+        return {k: _to_cpu(v) for k, v in x.items()}
+    return x

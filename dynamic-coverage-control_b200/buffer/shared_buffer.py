@@ -1,0 +1,154 @@
+"""SharedReplayBuffer — the reference's rollout storage (buffer/shared_buffer.py:14-279), resident in HBM.
+
+Same constructor and method names (`insert`, `compute_returns`, `after_update`) and the same logical arrays, but:
+  * tensors live on the GPU and the env / policy kernels write straight into them (no numpy, no per-step copies of
+    obs: `obs[t+1]` IS the env kernel's output buffer for step t);
+  * `share_obs` is never materialised: the centralised observation of env e is its N obs rows concatenated
+    (learner.py:219-220, 270-271), i.e. `obs` viewed as (T+1, E, N*D);
+  * quantities that are identical for the N agents of an env (reward, mask, value prediction, return — shared reward
+    environment.py:106-108, identical critic input) are stored once per env: (T(+1), E).  The reference-shaped
+    (T(+1), E, N, 1) arrays are exposed as expanded views (`rewards`, `masks`, `value_preds`, `returns`);
+  * the unused rnn_states arrays, bad_masks, active_masks (all ones) and available_actions are not stored.
+GAE (`compute_returns`, shared_buffer.py:199-208) is one kernel, `dcc_mappo_gae`.
+Memory at 8 UAV / 64 PoI / 65 536 envs / T = 150: obs 107 GB float32 of the 180 GB HBM3e; everything else < 1 GB.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+
+class SharedReplayBuffer(object):
+    def __init__(self, cfg, obs_space, cent_obs_space, act_space, device=None):
+        self.lib = _lib.load()
+        self.episode_length = int(cfg.max_ep_len)
+        self.n_rollout_threads = int(cfg.n_rollout_threads)
+        self.gamma, self.gae_lambda = float(cfg.gamma), float(cfg.gae_lambda)
+        self.num_agents = int(cfg.num_agents)
+        self.obs_dim = int(obs_space.shape[0])
+        self.act_dim = int(act_space.shape[0])
+        self.device = torch.device("cuda", int(getattr(cfg, "device", 0) or 0)) if device is None else torch.device(device)
+        T, E, N, D = self.episode_length, self.n_rollout_threads, self.num_agents, self.obs_dim
+        kw = dict(dtype=torch.float32, device=self.device)
+        self.obs = torch.zeros((T + 1, E, N, D), **kw)
+        self.actions = torch.zeros((T, E, N, self.act_dim), **kw)
+        self.action_log_probs_ten = torch.zeros((T, E, N), **kw)   # one column (the reference stores 2 equal ones)
+        self.values_te = torch.zeros((T + 1, E), **kw)
+        self.returns_te = torch.zeros((T + 1, E), **kw)
+        self.rewards_te = torch.zeros((T, E), **kw)
+        self.masks_te = torch.ones((T + 1, E), **kw)
+        self.step = 0
+
+    # ---- reference-shaped views (no copies) ---------------------------------------------------------------
+    @property
+    def share_obs(self):
+        T1, E, N, D = self.obs.shape
+        return self.obs.view(T1, E, 1, N * D).expand(T1, E, N, N * D)
+
+    def _per_agent(self, x):
+        return x[:, :, None, None].expand(x.shape[0], x.shape[1], self.num_agents, 1)
+
+    @property
+    def value_preds(self):
+        return self._per_agent(self.values_te)
+
+    @property
+    def returns(self):
+        return self._per_agent(self.returns_te)
+
+    @property
+    def rewards(self):
+        return self._per_agent(self.rewards_te)
+
+    @property
+    def masks(self):
+        return self._per_agent(self.masks_te)
+
+    @property
+    def action_log_probs(self):
+        return self.action_log_probs_ten[..., None].expand(*self.action_log_probs_ten.shape, self.act_dim)
+
+    # ---- writers -----------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def insert(self, share_obs, obs, rnn_states_actor, rnn_states_critic, actions, action_log_probs, value_preds,
+               rewards, masks, bad_masks=None, active_masks=None, available_actions=None):
+        """shared_buffer.py:72-105 with CUDA tensors.  share_obs / rnn states are accepted and ignored.  Arguments
+        that already ARE the destination slice (the zero-copy rollout) are not copied again."""
+        t, E, N = self.step, self.n_rollout_threads, self.num_agents
+
+        def put(dst, src):
+            if src is None:
+                return
+            src = torch.as_tensor(src, dtype=torch.float32, device=self.device)
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src.reshape(dst.shape))
+
+        def per_env(x):   # (E,N,1) / (E*N,1) / (E,) -> (E,)
+            x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
+            return x if x.numel() == E else x.reshape(E, N, -1)[:, 0, 0]
+
+        put(self.obs[t + 1], obs)
+        put(self.actions[t], actions)
+        alp = torch.as_tensor(action_log_probs, dtype=torch.float32, device=self.device)
+        put(self.action_log_probs_ten[t], alp if alp.numel() == E * N else alp.reshape(E, N, -1)[..., 0])
+        put(self.values_te[t], per_env(value_preds))
+        put(self.rewards_te[t], per_env(rewards))
+        put(self.masks_te[t + 1], per_env(masks))
+        self.step = (self.step + 1) % self.episode_length
+
+    def insert_env_step(self, rew_en, done_en):
+        """Zero-copy rollout step: obs[t+1], actions[t], log-probs[t] and values[t] were written in place by the env
+        and policy kernels; this stores the per-env reward and mask = 1 - done (learner.py:266-267) — one kernel."""
+        t = self.step
+        _lib.check(self.lib.dcc_rollout_insert(C.c_void_p(rew_en.data_ptr()), C.c_void_p(done_en.data_ptr()),
+                                               self.n_rollout_threads, self.num_agents,
+                                               C.c_void_p(self.rewards_te[t].data_ptr()),
+                                               C.c_void_p(self.masks_te[t + 1].data_ptr()), self._stream()),
+                   "dcc_rollout_insert")
+        self.step = (self.step + 1) % self.episode_length
+
+    def compute_returns(self, next_value, value_normalizer, policy=None):
+        """shared_buffer.py:199-208 (use_gae + ValueNorm branch).  next_value: (E,) / (E*N,1) / (E,N,1), or None if the
+        bootstrap value already sits in values_te[T]."""
+        T, E, N = self.episode_length, self.n_rollout_threads, self.num_agents
+        if next_value is not None:
+            nv = torch.as_tensor(next_value, dtype=torch.float32, device=self.device)
+            nv = nv if nv.numel() == E else nv.reshape(E, N, -1)[:, 0, 0]
+            if nv.data_ptr() != self.values_te[T].data_ptr():
+                self.values_te[T].copy_(nv.reshape(E))
+        h = policy._h if policy is not None else self._gae_handle()
+        p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+        _lib.check(self.lib.dcc_mappo_gae(h, p(self.rewards_te), p(self.values_te), p(self.masks_te),
+                                          p(value_normalizer.state), T, E, p(self.returns_te), self._stream()),
+                   "dcc_mappo_gae")
+
+    def _gae_handle(self):
+        # a minimal learner handle just for its gamma / lambda (when the caller has no policy at hand)
+        if getattr(self, "_h", None) is None:
+            mc = _lib.MappoCfg()
+            _lib.check(self.lib.dcc_mappo_cfg_default(C.byref(mc)), "dcc_mappo_cfg_default")
+            mc.n_agents, mc.obs_dim, mc.hidden, mc.chunk_rows = 1, 1, 1, 64
+            mc.gamma, mc.gae_lambda = self.gamma, self.gae_lambda
+            h = C.c_void_p()
+            _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
+            self._h = h
+        return self._h
+
+    def after_update(self):
+        """shared_buffer.py:142-152: the last step becomes the first of the next rollout."""
+        self.obs[0].copy_(self.obs[-1])
+        self.masks_te[0].copy_(self.masks_te[-1])
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self.lib.dcc_mappo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,485 @@
+// dcc_mappo.cu — C ABI of the MAPPO learner path: policy forward (get_actions / get_values / evaluate_actions),
+// GAE returns, and the PPO update split into "epoch gradients" and "clip + Adam apply" so that the host can put one
+// NCCL all-reduce of the flat gradient buffers between the two.
+//
+// Parameters, gradients and Adam moments are CALLER-owned flat float32 buffers (torch tensors) in the reference's
+// state_dict order without the never-used fc_h block:
+//   [feature_norm.weight, feature_norm.bias, fc1.0.weight (H x in), fc1.0.bias, fc1.2.weight, fc1.2.bias,
+//    fc2.0.0.weight (H x H), fc2.0.0.bias, fc2.0.2.weight, fc2.0.2.bias, head.weight (out x H), head.bias, (logstd)]
+// The handle owns only activation scratch sized for `chunk_rows` env-step rows; larger batches are streamed in
+// chunks with gradient accumulation, which equals the reference's single giant minibatch (num_mini_batch = 1).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "dcc_ops.cuh"
+
+namespace dcc {
+
+struct NetLayout {
+    int in, H, out;
+    size_t ln0_g, ln0_b, W1, b1, ln1_g, ln1_b, W2, b2, ln2_g, ln2_b, Wh, bh, logstd, total;
+    void init(int in_, int H_, int out_, bool has_logstd) {
+        in = in_; H = H_; out = out_;
+        size_t o = 0;
+        ln0_g = o; o += in; ln0_b = o; o += in;
+        W1 = o; o += (size_t)H * in; b1 = o; o += H; ln1_g = o; o += H; ln1_b = o; o += H;
+        W2 = o; o += (size_t)H * H; b2 = o; o += H; ln2_g = o; o += H; ln2_b = o; o += H;
+        Wh = o; o += (size_t)out * H; bh = o; o += out;
+        logstd = o; if (has_logstd) o += out;
+        total = o;
+    }
+};
+
+struct MappoHandle {
+    uint32_t magic;
+    dcc_mappo_cfg cfg;
+    int device, sm_count;
+    int backend;     // 1 = SIMT fp32, 2 = tcgen05 3xTF32
+    NetLayout la, lc;
+    int chunk_rows;  // env-step rows per chunk
+    // scratch
+    float *x0;       // [chunk*N, D] == [chunk, N*D]: xhat = input LayerNorm without affine
+    float *a1, *h1, *a2, *h2, *dA, *dB;   // [chunk*N, H]
+    float *mean1, *rstd1, *mean2, *rstd2;   // [chunk*N]
+    float *w1g_a, *b1g_a, *w1g_c, *b1g_c;   // fc1 weights with the input LayerNorm affine folded in (per call)
+    float *mu, *logp, *dmu, *vnew, *dv;   // [chunk*N,2], [chunk*N], [chunk*N,2], [chunk], [chunk]
+    double *dsums;   // small float64 scratch: [4] actor grad sumsq, [5] critic grad sumsq
+    float *vn_gae;   // ValueNorm state snapshot taken at train_begin (3 floats)
+    int64_t launches;
+};
+constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
+
+static MappoHandle *as_mappo(void *h) {
+    MappoHandle *m = static_cast<MappoHandle *>(h);
+    return (m && m->magic == MAPPO_MAGIC) ? m : nullptr;
+}
+
+// the tcgen05 3xTF32 kernels cover the shipped trunk width only
+static inline bool tc_supported(const dcc_mappo_cfg *c) { return false && c->hidden == 256; }
+
+static inline int grid_for_rows(const MappoHandle *h, long rows, int warps_per_block) {
+    long b = (rows + warps_per_block - 1) / warps_per_block;
+    const long cap = (long)h->sm_count * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// kernels that end with per-warp atomics into a small parameter-gradient vector: keep the grid at 2 CTAs per SM
+static inline int grid_for_reduce(const MappoHandle *h, long rows, int warps_per_block) {
+    long b = (rows + warps_per_block - 1) / warps_per_block;
+    const long cap = (long)h->sm_count * 2;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// C (+)= op(A) op(B), see gemm_kernel.  accumulate != 0 adds into C (float atomics); split-K is used when the
+// output grid alone cannot fill the GPU (the weight-gradient GEMMs: tiny M x N, huge K).
+static int launch_gemm(MappoHandle *h, bool ta, bool tb, int M, int N, int K, const float *A, int lda, const float *B,
+                       int ldb, float *C, int ldc, bool accumulate, cudaStream_t s) {
+    if (M <= 0 || N <= 0 || K <= 0) return DCC_OK;
+    const int gx = (N + GM_BN - 1) / GM_BN, gy = (M + GM_BM - 1) / GM_BM;
+    int splits = 1;
+    const long tiles = (long)gx * gy;
+    if (tiles < 2L * h->sm_count && K >= 8 * GM_BK) {
+        splits = (int)((4L * h->sm_count + tiles - 1) / tiles);
+        const int max_splits = (K + 4 * GM_BK - 1) / (4 * GM_BK);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    int kps = (K + splits - 1) / splits;
+    kps = (kps + GM_BK - 1) / GM_BK * GM_BK;
+    splits = (K + kps - 1) / kps;
+    const bool atomic = accumulate || splits > 1;
+    if (atomic && !accumulate) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
+    dim3 grid(gx, gy, splits), block(256);
+#define DCC_GEMM_CASE(TA_, TB_)                                                                                   \
+    if (ta == TA_ && tb == TB_) {                                                                                 \
+        if (atomic) gemm_kernel<TA_, TB_, true><<<grid, block, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, kps);    \
+        else gemm_kernel<TA_, TB_, false><<<grid, block, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, kps);          \
+    }
+    DCC_GEMM_CASE(false, false)
+    DCC_GEMM_CASE(false, true)
+    DCC_GEMM_CASE(true, false)
+    DCC_GEMM_CASE(true, true)
+#undef DCC_GEMM_CASE
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
+// fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
+static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, float *w1g, float *b1g, cudaStream_t s) {
+    fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W1, P + L.b1, P + L.ln0_g, P + L.ln0_b, w1g, b1g, L.H, L.in);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+// trunk forward on `rows` rows of width L.in: x -> h2.  save = keep a1/a2/stats for the backward pass.
+static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, const float *w1g, const float *b1g,
+                         const float *x, int rows, bool save, cudaStream_t s) {
+    const int H = L.H;
+    const int wpb = 8;
+    ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in);
+    h->launches++;
+    int rc = launch_gemm(h, false, true, rows, H, L.in, h->x0, L.in, w1g, L.in, h->a1, H, false, s);
+    if (rc) return rc;
+    bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a1, b1g, P + L.ln1_g, P + L.ln1_b,
+                                                                            save ? h->a1 : nullptr, h->h1, h->mean1,
+                                                                            h->rstd1, rows, H);
+    h->launches++;
+    rc = launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
+    if (rc) return rc;
+    bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a2, P + L.b2, P + L.ln2_g, P + L.ln2_b,
+                                                                            save ? h->a2 : nullptr, h->h2, h->mean2,
+                                                                            h->rstd2, rows, H);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+// trunk backward: dA holds dL/dh2 on entry; x0 still holds this chunk's xhat.  Accumulates into grads G; the fc1
+// weight slot receives G1 = dz1^T xhat (turned into dW1 / dgamma0 / dbeta0 by ln0_finalize once per epoch).
+static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, float *G, int rows, cudaStream_t s) {
+    const int H = L.H;
+    const int wpb = 8;
+    const int gr = grid_for_reduce(h, rows, wpb);
+    relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dA, h->a2, h->mean2, h->rstd2, P + L.ln2_g, h->dA, G + L.ln2_g,
+                                               G + L.ln2_b, G + L.b2, rows, H);   // dA := dz2
+    h->launches++;
+    int rc = launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);          // dW2 += dz2^T h1
+    if (rc) return rc;
+    rc = launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);           // dh1 = dz2 W2
+    if (rc) return rc;
+    relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
+                                               G + L.ln1_b, G + L.b1, rows, H);   // dB := dz1
+    h->launches++;
+    rc = launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.in, G + L.W1, L.in, true, s);     // G1 += dz1^T xhat
+    if (rc) return rc;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+static int ln0_finalize(MappoHandle *h, const NetLayout &L, const float *P, float *G, cudaStream_t s) {
+    ln0_finalize_kernel<<<(L.in + 127) / 128, 128, 0, s>>>(P + L.W1, P + L.ln0_g, P + L.ln0_b, G + L.W1, G + L.b1, G + L.ln0_g,
+                                                          G + L.ln0_b, L.H, L.in);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+__global__ void expand_values_kernel(const float *__restrict__ v, float *__restrict__ out, int rows, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * N) out[i] = v[i / N];
+}
+__global__ void add_scalar_kernel(float *p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += v;
+}
+__global__ void entropy_stat_kernel(const float *logstd, int A, double *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double e = 0.0;
+        for (int d = 0; d < A; ++d) e += 0.5 + 0.5 * (double)LOG_2PI + (double)logstd[d];
+        *out += e;
+    }
+}
+
+}  // namespace dcc
+
+using namespace dcc;
+
+extern "C" {
+
+int dcc_mappo_cfg_default(dcc_mappo_cfg *c) {
+    if (!c) return DCC_ERR_INVALID_ARG;
+    memset(c, 0, sizeof *c);
+    c->n_agents = 4; c->obs_dim = 110; c->hidden = 256; c->act_dim = 2; c->chunk_rows = 0; c->gemm_backend = 0;
+    c->clip_param = 0.2f; c->entropy_coef = 0.01f; c->value_loss_coef = 1.0f; c->huber_delta = 10.0f;
+    c->max_grad_norm = 10.0f; c->gamma = 0.99f; c->gae_lambda = 0.95f; c->opti_eps = 1e-5f; c->vn_beta = 0.99999;
+    c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f;
+    return DCC_OK;
+}
+
+int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
+    if (!cfg || !handle) return DCC_ERR_INVALID_ARG;
+    *handle = nullptr;
+    if (cfg->n_agents < 1 || cfg->obs_dim < 1 || cfg->hidden < 1 || cfg->chunk_rows < 0) return DCC_ERR_INVALID_ARG;
+    if (cfg->hidden > 256 || cfg->act_dim != 2 || cfg->gemm_backend < 0 || cfg->gemm_backend > 2)
+        return DCC_ERR_UNSUPPORTED;  // MLP trunk with hidden <= 256 and the Box(2) action space of the env
+    if (cfg->gemm_backend == 2 && !tc_supported(cfg)) return DCC_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return DCC_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DCC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return DCC_ERR_NO_DEVICE;
+    MappoHandle *h = new (std::nothrow) MappoHandle();
+    if (!h) return DCC_ERR_ALLOC;
+    memset(h, 0, sizeof *h);
+    h->magic = MAPPO_MAGIC; h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
+    h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
+    const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
+    h->la.init(D, H, cfg->act_dim, true);
+    h->lc.init(N * D, H, 1, false);
+    // chunk: bound the scratch to ~1.5 GB unless the caller asks for a size
+    long chunk = cfg->chunk_rows;
+    if (chunk <= 0) {
+        const double per_row = (double)N * (D + 6.0 * H + 16) * 4.0;
+        chunk = (long)(1.5e9 / per_row);
+        if (chunk > 131072) chunk = 131072;
+        if (chunk < 64) chunk = 64;
+    }
+    h->chunk_rows = (int)chunk;
+    const size_t RA = (size_t)chunk * N;
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](float **p, size_t n) { if (ce == cudaSuccess) ce = cudaMalloc(p, n * sizeof(float)); };
+    alloc(&h->x0, RA * D);
+    alloc(&h->a1, RA * H); alloc(&h->h1, RA * H); alloc(&h->a2, RA * H); alloc(&h->h2, RA * H);
+    alloc(&h->dA, RA * H); alloc(&h->dB, RA * H);
+    alloc(&h->mean1, RA); alloc(&h->rstd1, RA); alloc(&h->mean2, RA); alloc(&h->rstd2, RA);
+    alloc(&h->w1g_a, (size_t)H * D); alloc(&h->b1g_a, H); alloc(&h->w1g_c, (size_t)H * N * D); alloc(&h->b1g_c, H);
+    alloc(&h->mu, RA * 2); alloc(&h->logp, RA); alloc(&h->dmu, RA * 2); alloc(&h->vnew, chunk); alloc(&h->dv, chunk);
+    alloc(&h->vn_gae, 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
+    if (ce != cudaSuccess) {
+        set_last_cuda_error(ce, "cudaMalloc(mappo scratch)", __FILE__, __LINE__);
+        dcc_mappo_destroy(h);
+        return DCC_ERR_ALLOC;
+    }
+    *handle = h;
+    return DCC_OK;
+}
+
+int dcc_mappo_destroy(void *handle) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h) return DCC_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    float *bufs[] = {h->x0, h->a1, h->h1, h->a2, h->h2, h->dA, h->dB, h->mean1, h->rstd1, h->mean2, h->rstd2,
+                     h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv, h->vn_gae};
+    for (float *b : bufs) cudaFree(b);
+    cudaFree(h->dsums);
+    h->magic = 0;
+    delete h;
+    return DCC_OK;
+}
+
+int64_t dcc_mappo_param_count(void *handle, int which) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || (which != 0 && which != 1)) return -1;
+    return (int64_t)(which == 0 ? h->la.total : h->lc.total);
+}
+
+int dcc_mappo_chunk_rows(void *handle) {
+    MappoHandle *h = as_mappo(handle);
+    return h ? h->chunk_rows : -1;
+}
+
+int dcc_mappo_gemm_backend(void *handle) {
+    MappoHandle *h = as_mappo(handle);
+    return h ? h->backend : -1;
+}
+
+int64_t dcc_mappo_launch_count(void *handle) {
+    MappoHandle *h = as_mappo(handle);
+    return h ? h->launches : -1;
+}
+
+// shared body of get_actions / evaluate_actions.  mode 0 = sample, 1 = evaluate given actions.
+static int policy_forward(MappoHandle *h, const float *actor, const float *critic, const float *d_obs, int n_envs, int mode,
+                          uint64_t seed, uint64_t offset, int deterministic, float *d_actions, float *d_logp,
+                          float *d_values, float *d_mu, cudaStream_t s) {
+    const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
+    const bool do_actor = actor && d_actions && (mode == 0 || d_logp);
+    const bool do_critic = critic && d_values;
+    int rc;
+    if (do_actor && (rc = fold_ln0(h, h->la, actor, h->w1g_a, h->b1g_a, s))) return rc;
+    if (do_critic && (rc = fold_ln0(h, h->lc, critic, h->w1g_c, h->b1g_c, s))) return rc;
+    for (int e0 = 0; e0 < n_envs; e0 += h->chunk_rows) {
+        const int ne = min(h->chunk_rows, n_envs - e0);
+        const float *x = d_obs + (size_t)e0 * N * D;
+        if (do_actor) {
+            const int rows = ne * N;
+            if ((rc = trunk_forward(h, h->la, actor, h->w1g_a, h->b1g_a, x, rows, false, s))) return rc;
+            actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
+                h->h2, actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
+                d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
+                deterministic, seed, offset, (uint64_t)e0 * N);
+            h->launches++;
+        }
+        if (do_critic) {
+            if ((rc = trunk_forward(h, h->lc, critic, h->w1g_c, h->b1g_c, x, ne, false, s))) return rc;
+            critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->h2, critic + h->lc.Wh, critic + h->lc.bh,
+                                                                      d_values + e0, ne, H);
+            h->launches++;
+        }
+    }
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_mappo_act(void *handle, const float *actor, const float *critic, const float *d_obs, int n_envs, uint64_t seed,
+                  uint64_t offset, int deterministic, float *d_actions, float *d_logp, float *d_values,
+                  dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
+    if ((actor && !d_actions) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    return policy_forward(h, actor, critic, d_obs, n_envs, 0, seed, offset, deterministic, d_actions, d_logp, d_values,
+                          nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int dcc_mappo_evaluate(void *handle, const float *actor, const float *critic, const float *d_obs, const float *d_actions,
+                       int n_envs, float *d_logp, float *d_values, float *d_mu, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
+    if ((actor && (!d_actions || !d_logp)) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    return policy_forward(h, actor, critic, d_obs, n_envs, 1, 0, 0, 0, const_cast<float *>(d_actions), d_logp, d_values,
+                          d_mu, static_cast<cudaStream_t>(stream));
+}
+
+int dcc_rollout_insert(const float *d_rew_in, const uint8_t *d_done_in, int n_envs, int n_agents, float *d_rew_out,
+                       float *d_mask_out, dcc_stream_t stream) {
+    if (!d_rew_in || !d_done_in || !d_rew_out || !d_mask_out || n_envs < 1 || n_agents < 1) return DCC_ERR_INVALID_ARG;
+    rollout_insert_kernel<<<(n_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_rew_in, d_done_in, n_envs,
+                                                                                            n_agents, d_rew_out, d_mask_out);
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, const float *d_masks,
+                  const float *d_vn_state, int T, int E, float *d_returns, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_rewards || !d_values || !d_masks || !d_vn_state || !d_returns || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    gae_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_masks, d_vn_state,
+                                                                            d_returns, T, E, h->cfg.gamma, h->cfg.gae_lambda);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
+int dcc_mappo_train_begin(void *handle, const float *d_returns, const float *d_values, const float *d_vn_state, int T, int E,
+                          double *d_stats_out, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_returns || !d_values || !d_vn_state || !d_stats_out || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)T * E;
+    DCC_CUDA_TRY(cudaMemsetAsync(d_stats_out, 0, 4 * sizeof(double), s));
+    DCC_CUDA_TRY(cudaMemcpyAsync(h->vn_gae, d_vn_state, 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+    sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, d_values, h->vn_gae, d_stats_out, n);
+    sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, nullptr, nullptr, d_stats_out + 2, n);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    return DCC_OK;
+}
+
+int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                          const float *d_obs, const float *d_actions, const float *d_logp_old, const float *d_values,
+                          const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global, int T,
+                          int E, double *d_epoch_stats, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_actions || !d_logp_old || !d_values ||
+        !d_returns || !d_vn_state || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
+    const NetLayout &LA = h->la, &LC = h->lc;
+    DCC_CUDA_TRY(cudaMemsetAsync(grad_actor, 0, LA.total * sizeof(float), s));
+    DCC_CUDA_TRY(cudaMemsetAsync(grad_critic, 0, LC.total * sizeof(float), s));
+    // ValueNorm.update(return_batch) happens inside cal_value_loss, every epoch, before normalising (mappo.py:107)
+    vn_update_kernel<<<1, 32, 0, s>>>(d_vn_state, d_stats4 + 2, n_rows_global, (float)h->cfg.vn_beta,
+                                      (float)(1.0 - h->cfg.vn_beta));
+    entropy_stat_kernel<<<1, 32, 0, s>>>(actor + LA.logstd, h->cfg.act_dim, d_epoch_stats + 3);
+    h->launches += 2;
+    int rc;
+    if ((rc = fold_ln0(h, LA, actor, h->w1g_a, h->b1g_a, s))) return rc;
+    if ((rc = fold_ln0(h, LC, critic, h->w1g_c, h->b1g_c, s))) return rc;
+    PpoLossParams P;
+    P.clip = h->cfg.clip_param; P.huber_delta = h->cfg.huber_delta; P.value_coef = h->cfg.value_loss_coef;
+    P.inv_rows = (float)(1.0 / (n_rows_global * N)); P.n_agents = N;
+    const long R = (long)T * E;
+    for (long r0 = 0; r0 < R; r0 += h->chunk_rows) {
+        const int nr = (int)std::min<long>(h->chunk_rows, R - r0);
+        const float *x = d_obs + (size_t)r0 * N * D;
+        // actor and critic share one activation scratch, so the chunk is processed net by net:
+        // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
+        if ((rc = trunk_forward(h, LA, actor, h->w1g_a, h->b1g_a, x, nr * N, true, s))) return rc;
+        actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
+            h->h2, actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+            h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
+        h->launches++;
+        ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
+            h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
+            d_values + r0, h->vn_gae, d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
+        h->launches++;
+        head_bwd_kernel<2><<<grid_for_reduce(h, nr * N, 8), 256, 0, s>>>(h->dmu, h->h2, actor + LA.Wh, h->dA,
+                                                                        grad_actor + LA.Wh, grad_actor + LA.bh, nr * N, H);
+        h->launches++;
+        if ((rc = trunk_backward(h, LA, actor, grad_actor, nr * N, s))) return rc;
+        // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
+        if ((rc = trunk_forward(h, LC, critic, h->w1g_c, h->b1g_c, x, nr, true, s))) return rc;
+        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
+        h->launches++;
+        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, d_vn_state, h->dv,
+                                                              d_epoch_stats, nr, P);
+        h->launches++;
+        head_bwd_kernel<1><<<grid_for_reduce(h, nr, 8), 256, 0, s>>>(h->dv, h->h2, critic + LC.Wh, h->dA, grad_critic + LC.Wh,
+                                                                    grad_critic + LC.bh, nr, H);
+        h->launches++;
+        if ((rc = trunk_backward(h, LC, critic, grad_critic, nr, s))) return rc;
+    }
+    if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
+    if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float *adam_m, float *adam_v, float lr,
+                    int64_t step, double *d_grad_norm_sq_out, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !params || !grads || !adam_m || !adam_v || step < 1 || (which != 0 && which != 1)) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const NetLayout &L = which == 0 ? h->la : h->lc;
+    if (which == 0) {
+        // d(-entropy_coef * dist_entropy)/dlogstd = -entropy_coef per action dim (act.py:172-184)
+        add_scalar_kernel<<<1, 32, 0, s>>>(grads + L.logstd, h->cfg.act_dim, -h->cfg.entropy_coef);
+        h->launches++;
+    }
+    double *sq = h->dsums + 4 + which;
+    DCC_CUDA_TRY(cudaMemsetAsync(sq, 0, sizeof(double), s));
+    const int blocks = (int)std::min<size_t>((L.total + 255) / 256, (size_t)h->sm_count * 4);
+    sumsq_kernel<<<blocks, 256, 0, s>>>(grads, L.total, sq);
+    const float b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+    const float bc2s = (float)sqrt(1.0 - pow((double)b2, (double)step));
+    clip_adam_kernel<<<blocks, 256, 0, s>>>(params, grads, adam_m, adam_v, L.total, sq, h->cfg.max_grad_norm, lr, b1, b2,
+                                            h->cfg.opti_eps, bc1, bc2s, 1.0f);
+    h->launches += 2;
+    if (d_grad_norm_sq_out) DCC_CUDA_TRY(cudaMemcpyAsync(d_grad_norm_sq_out, sq, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *A, int lda, const float *B,
+                int ldb, float *C, int ldc, int accumulate, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !A || !B || !C || backend < 0 || backend > 2) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    const int saved = h->backend;
+    if (backend) h->backend = backend;
+    const int rc = launch_gemm(h, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, accumulate != 0,
+                               static_cast<cudaStream_t>(stream));
+    h->backend = saved;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,587 @@
+// dcc_ops.cuh — device kernels of the MAPPO learner path (actor/critic MLP forward+backward, Gaussian head,
+// PPO loss, GAE, grad-norm clip + Adam).  Launch wrappers live in dcc_mappo.cu.
+//
+// Reference math (paths relative to /root/reference/uav_dcc_control/): algos/algo_utils/mlp.py:19-29,46-58
+// (LayerNorm -> [Linear, ReLU, LayerNorm] x 2), algos/algo_utils/distributions.py:33-41,83-92 (diagonal Gaussian),
+// algos/mappo.py:103-187 (PPO update), buffer/shared_buffer.py:199-208 (GAE), utils/valuenorm.py:32-79.
+#pragma once
+#include "dcc_common.cuh"
+
+namespace dcc {
+
+constexpr float LN_EPS = 1e-5f;
+constexpr float LOG_2PI = 1.8378770664093453f;
+
+// ---- SIMT fp32 GEMM ---------------------------------------------------------------------------------
+// C[M,N] (+)= sum_k A(m,k) * B(k,n);  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tiles, register-staged double buffering.  blockIdx.z splits K
+// (results combined with float atomics when ATOMIC).  fp32 FFMA accumulate = the reference's own precision.
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_PAD = 4;
+
+template <bool TRANS>
+__device__ __forceinline__ void gemm_fetch(const float *__restrict__ P, int ld, int r0, int k0, int R, int Kend, int t,
+                                           float (&v)[8]) {
+    // fetch this thread's 8 elements of a [128 (r) x 16 (k)] operand tile
+    if (!TRANS) {  // element (r,k) at P[r*ld + k]: k contiguous.  thread -> row t/2, k segment (t%2)*8
+        const int r = r0 + (t >> 1), kb = k0 + (t & 1) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (r < R && kb + i < Kend) ? P[(size_t)r * ld + kb + i] : 0.f;
+    } else {       // element (r,k) at P[k*ld + r]: r contiguous.  thread -> k t/16, r segment (t%16)*8
+        const int k = k0 + (t >> 4), rb = r0 + (t & 15) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (k < Kend && rb + i < R) ? P[(size_t)k * ld + rb + i] : 0.f;
+    }
+}
+template <bool TRANS>
+__device__ __forceinline__ void gemm_stash(float (*S)[GM_BM + GM_PAD], int t, const float (&v)[8]) {
+    if (!TRANS) {
+        const int r = t >> 1, kb = (t & 1) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) S[kb + i][r] = v[i];
+    } else {
+        const int k = t >> 4, rb = (t & 15) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) S[k][rb + i] = v[i];
+    }
+}
+
+template <bool TA, bool TB, bool ATOMIC>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                   const float *__restrict__ B, int ldb, float *__restrict__ C, int ldc,
+                                                   int k_per_split) {
+    __shared__ __align__(16) float As[2][GM_BK][GM_BM + GM_PAD];
+    __shared__ __align__(16) float Bs[2][GM_BK][GM_BN + GM_PAD];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    if (kbeg >= kend) return;
+    const int ty = t >> 4, tx = t & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float ra[8], rb[8];
+    // A tile indexed (m,k): "row-major [m][k]" is the non-transposed fetch; TA means A is stored [k][m]
+    gemm_fetch<TA>(A, lda, m0, kbeg, M, kend, t, ra);
+    // B tile indexed (n,k): B(k,n)=B[k*ldb+n] is the [k][n] (transposed-fetch) storage; TB means stored [n][k]
+    gemm_fetch<!TB>(B, ldb, n0, kbeg, N, kend, t, rb);
+    gemm_stash<TA>(As[0], t, ra);
+    gemm_stash<!TB>(Bs[0], t, rb);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += GM_BK) {
+        const bool more = k0 + GM_BK < kend;
+        if (more) {
+            gemm_fetch<TA>(A, lda, m0, k0 + GM_BK, M, kend, t, ra);
+            gemm_fetch<!TB>(B, ldb, n0, k0 + GM_BK, N, kend, t, rb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            gemm_stash<TA>(As[buf ^ 1], t, ra);
+            gemm_stash<!TB>(Bs[buf ^ 1], t, rb);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + tx * 8 + j;
+            if (n >= N) continue;
+            if (ATOMIC) atomicAdd(&C[(size_t)m * ldc + n], acc[i][j]);
+            else C[(size_t)m * ldc + n] = acc[i][j];
+        }
+    }
+}
+
+// ---- row-wise kernels: one warp per row ---------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// Input feature LayerNorm WITHOUT its affine part: xhat = (x - mean) * rstd over F features (two-pass mean /
+// biased variance, eps 1e-5).  The affine (gamma0, beta0) is folded into the first Linear (fold_ln0_kernel):
+//   LN(x) W1^T + b1 = xhat (W1 * gamma0)^T + (b1 + W1 beta0)
+// which makes xhat the only [rows, F] operand of the layer (forward GEMM and weight-gradient GEMM) and removes the
+// dX GEMM of layer 1 from the backward pass altogether (ln0_finalize_kernel).
+__global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const float *xr = x + (size_t)r * F;
+        float s = 0.f;
+        for (int c = lane; c < F; c += 32) s += xr[c];
+        const float mean = warp_sum_f(s) / (float)F;
+        float q = 0.f;
+        for (int c = lane; c < F; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
+        float *yr = xhat + (size_t)r * F;
+        for (int c = lane; c < F; c += 32) yr[c] = (xr[c] - mean) * rstd;
+    }
+}
+
+// W1g[h,c] = W1[h,c] * gamma0[c];  b1g[h] = b1[h] + sum_c W1[h,c] * beta0[c].  One warp per output unit h.
+__global__ void fold_ln0_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ g0,
+                                const float *__restrict__ be0, float *__restrict__ W1g, float *__restrict__ b1g, int H,
+                                int F) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= H) return;
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) {
+        const float w = W1[(size_t)h * F + c];
+        W1g[(size_t)h * F + c] = w * g0[c];
+        s = fmaf(w, be0[c], s);
+    }
+    s = warp_sum_f(s);
+    if (lane == 0) b1g[h] = b1[h] + s;
+}
+
+// Backward of the folded input LayerNorm, once per epoch after all chunks: G = sum_r dz1^T xhat sits in the fc1
+// weight-gradient slot and db1 in the bias slot.  Per input column c:
+//   dgamma0[c] = sum_h W1[h,c] G[h,c];  dbeta0[c] = sum_h W1[h,c] db1[h];
+//   dW1[h,c] = sum_r dz1[r,h] (xhat[r,c] gamma0[c] + beta0[c]) = G[h,c] gamma0[c] + db1[h] beta0[c]   (in place)
+__global__ void ln0_finalize_kernel(const float *__restrict__ W1, const float *__restrict__ g0,
+                                    const float *__restrict__ be0, float *__restrict__ G,
+                                    const float *__restrict__ db1, float *__restrict__ dg0, float *__restrict__ dbe0,
+                                    int H, int F) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    const float g = g0[c], b = be0[c];
+    float ag = 0.f, ab = 0.f;
+    for (int h = 0; h < H; ++h) {
+        const float w = W1[(size_t)h * F + c];
+        const float gv = G[(size_t)h * F + c];
+        const float d1 = db1[h];
+        ag = fmaf(w, gv, ag);
+        ab = fmaf(w, d1, ab);
+        G[(size_t)h * F + c] = fmaf(gv, g, d1 * b);
+    }
+    dg0[c] = ag;
+    dbe0[c] = ab;
+}
+
+// a = relu(z + bias); h = LayerNorm(a) * gamma + beta.  H <= 256 (8 columns per lane).  a_out optional.
+__global__ void bias_relu_ln_fwd_kernel(const float *__restrict__ z, const float *__restrict__ bias,
+                                        const float *__restrict__ gamma, const float *__restrict__ beta,
+                                        float *__restrict__ a_out, float *__restrict__ h_out, float *__restrict__ mean_out,
+                                        float *__restrict__ rstd_out, int rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        float a[8];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            a[j] = (c < H) ? fmaxf(z[(size_t)r * H + c] + bias[c], 0.f) : 0.f;
+            s += a[j];
+        }
+        const float mean = warp_sum_f(s) / (float)H;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = (lane + 32 * j < H) ? a[j] - mean : 0.f;
+            q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(warp_sum_f(q) / (float)H + LN_EPS);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) {
+                if (a_out) a_out[(size_t)r * H + c] = a[j];
+                h_out[(size_t)r * H + c] = (a[j] - mean) * rstd * gamma[c] + beta[c];
+            }
+        }
+        if (lane == 0) {
+            if (mean_out) mean_out[r] = mean;
+            if (rstd_out) rstd_out[r] = rstd;
+        }
+    }
+}
+
+// Backward of h = LN(a)*gamma+beta, a = relu(z+bias):  given dh, a, mean, rstd -> dz (in place over dh allowed),
+// and accumulates dgamma, dbeta, dbias (float atomics, one set per warp).  H <= 256.
+__global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
+                                   const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
+                                   float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
+                                   int H) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float g[8], acc_g[8], acc_b[8], acc_z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        g[j] = (c < H) ? gamma[c] : 0.f;
+        acc_g[j] = acc_b[j] = acc_z[j] = 0.f;
+    }
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const float m = mean[r], rs = rstd[r];
+        float xh[8], dxh[8], av[8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            const bool ok = c < H;
+            av[j] = ok ? a[(size_t)r * H + c] : 0.f;
+            const float d = ok ? dh[(size_t)r * H + c] : 0.f;
+            xh[j] = ok ? (av[j] - m) * rs : 0.f;
+            acc_g[j] = fmaf(d, xh[j], acc_g[j]);
+            acc_b[j] += d;
+            dxh[j] = d * g[j];
+            s1 += dxh[j];
+            s2 = fmaf(dxh[j], xh[j], s2);
+        }
+        const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) {
+                const float da = rs * (dxh[j] - c1 - xh[j] * c2);
+                const float v = (av[j] > 0.f) ? da : 0.f;
+                dz[(size_t)r * H + c] = v;
+                acc_z[j] += v;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < H) {
+            atomicAdd(&dgamma[c], acc_g[j]);
+            atomicAdd(&dbeta[c], acc_b[j]);
+            atomicAdd(&dbias[c], acc_z[j]);
+        }
+    }
+}
+
+// ---- counter-based RNG (Philox4x32-10) + Box-Muller: action sampling a = mu + sigma * eps ---------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float2 normal_pair(uint64_t seed, uint64_t offset, uint64_t row) {
+    // counter = (global agent row, call offset): the sample stream does not depend on chunking or launch geometry
+    uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u1 = ((float)c[0] + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+    const float u2 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincospif(2.f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+// Actor head: mu = h . Wm^T + bm (act_dim = 2), sigma = exp(logstd).
+//   mode 0 (rollout, R_Actor.forward): sample (or mode when deterministic) the action, write action + logp
+//   mode 1 (update, evaluate_actions): logp of the given action, also writes mu
+__global__ void actor_head_kernel(const float *__restrict__ h, const float *__restrict__ Wm, const float *__restrict__ bm,
+                                  const float *__restrict__ logstd, float *__restrict__ actions, float *__restrict__ mu_out,
+                                  float *__restrict__ logp_out, int rows, int H, int mode, int deterministic, uint64_t seed,
+                                  uint64_t offset, uint64_t row_base) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float ls0 = logstd[0], ls1 = logstd[1];
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            const float v = h[(size_t)r * H + c];
+            s0 = fmaf(v, Wm[c], s0);
+            s1 = fmaf(v, Wm[H + c], s1);
+        }
+        s0 = warp_sum_f(s0) + bm[0];
+        s1 = warp_sum_f(s1) + bm[1];
+        if (lane == 0) {
+            const float sd0 = expf(ls0), sd1 = expf(ls1);
+            float a0, a1;
+            if (mode == 0) {
+                if (deterministic) { a0 = s0; a1 = s1; }
+                else {
+                    const float2 e = normal_pair(seed, offset, row_base + (uint64_t)r);
+                    a0 = fmaf(sd0, e.x, s0); a1 = fmaf(sd1, e.y, s1);
+                }
+                actions[(size_t)r * 2 + 0] = a0; actions[(size_t)r * 2 + 1] = a1;
+            } else {
+                a0 = actions[(size_t)r * 2 + 0]; a1 = actions[(size_t)r * 2 + 1];
+            }
+            if (mu_out) { mu_out[(size_t)r * 2 + 0] = s0; mu_out[(size_t)r * 2 + 1] = s1; }
+            const float d0 = a0 - s0, d1 = a1 - s1;
+            // Normal.log_prob summed over the 2 action dims (distributions.py:33-35)
+            const float lp = -(d0 * d0) / (2.f * sd0 * sd0) - ls0 - 0.5f * LOG_2PI - (d1 * d1) / (2.f * sd1 * sd1) - ls1 -
+                             0.5f * LOG_2PI;
+            if (logp_out) logp_out[r] = lp;
+        }
+    }
+}
+
+// Critic head: v = h . wv + bv
+__global__ void critic_head_kernel(const float *__restrict__ h, const float *__restrict__ wv, const float *__restrict__ bv,
+                                   float *__restrict__ v_out, int rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        float s = 0.f;
+        for (int c = lane; c < H; c += 32) s = fmaf(h[(size_t)r * H + c], wv[c], s);
+        s = warp_sum_f(s);
+        if (lane == 0) v_out[r] = s + bv[0];
+    }
+}
+
+// Head backward: dh[r,c] = sum_o dout[r,o] * W[o,c];  dW[o,c] += sum_r dout[r,o]*h[r,c];  db[o] += sum_r dout[r,o].
+// OUT = 2 (actor) or 1 (critic).  H <= 256.
+template <int OUT>
+__global__ void head_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ h, const float *__restrict__ W,
+                                float *__restrict__ dh, float *__restrict__ dW, float *__restrict__ db, int rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float w[OUT][8], aw[OUT][8], ab[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+        ab[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            w[o][j] = (c < H) ? W[o * H + c] : 0.f;
+            aw[o][j] = 0.f;
+        }
+    }
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        float d[OUT];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) { d[o] = dout[(size_t)r * OUT + o]; ab[o] += d[o]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) {
+                const float hv = h[(size_t)r * H + c];
+                float acc = 0.f;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) { acc = fmaf(d[o], w[o][j], acc); aw[o][j] = fmaf(d[o], hv, aw[o][j]); }
+                dh[(size_t)r * H + c] = acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) atomicAdd(&dW[o * H + c], aw[o][j]);
+        }
+        if (lane == 0) atomicAdd(&db[o], ab[o]);
+    }
+}
+
+// ---- ValueNorm helpers (utils/valuenorm.py:32-36): state = {running_mean, running_mean_sq, debiasing_term} ----
+__device__ __forceinline__ void vn_mean_std(const float *vn, float &mean, float &stdv) {
+    const float c = fmaxf(vn[2], 1e-5f);
+    mean = vn[0] / c;
+    const float var = fmaxf(vn[1] / c - mean * mean, 1e-2f);
+    stdv = sqrtf(var);
+}
+
+// Learner.insert bookkeeping (learner.py:254-276): per-env reward and mask = 1 - done
+__global__ void rollout_insert_kernel(const float *__restrict__ rew_in, const uint8_t *__restrict__ done_in, int E, int N,
+                                      float *__restrict__ rew_out, float *__restrict__ mask_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    rew_out[e] = rew_in[(size_t)e * N];
+    mask_out[e] = done_in[(size_t)e * N] ? 0.f : 1.f;
+}
+
+// GAE over the rollout (shared_buffer.py:199-208): one thread per env, backwards in time, arrays [T(+1), E]
+// (coalesced over envs); masks cut the recurrence at episode ends (the "segments").
+__global__ void gae_kernel(const float *__restrict__ rew, const float *__restrict__ val, const float *__restrict__ masks,
+                           const float *__restrict__ vn, float *__restrict__ ret, int T, int E, float gamma, float lam) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float mean, sd;
+    vn_mean_std(vn, mean, sd);
+    float gae = 0.f;
+    float vnext = val[(size_t)T * E + e] * sd + mean;
+    for (int t = T - 1; t >= 0; --t) {
+        const float m = masks[(size_t)(t + 1) * E + e];
+        const float v = val[(size_t)t * E + e] * sd + mean;
+        const float delta = rew[(size_t)t * E + e] + gamma * vnext * m - v;
+        gae = delta + gamma * lam * m * gae;
+        ret[(size_t)t * E + e] = gae + v;
+        vnext = v;
+    }
+}
+
+// sums[0] += sum(x), sums[1] += sum(x^2) in float64 (advantage statistics, ValueNorm batch statistics)
+__global__ void sum_sumsq_kernel(const float *__restrict__ x, const float *__restrict__ sub, const float *__restrict__ vn,
+                                 double *__restrict__ sums, size_t n) {
+    // value = x[i] - (sub ? denormalize(sub[i]) : 0)
+    float mean = 0.f, sd = 1.f;
+    if (sub) vn_mean_std(vn, mean, sd);
+    double s = 0.0, q = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = sub ? x[i] - (sub[i] * sd + mean) : x[i];
+        s += v; q += (double)v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL_MASK, s, o); q += __shfl_xor_sync(FULL_MASK, q, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], s); atomicAdd(&sums[1], q); }
+}
+
+// ValueNorm.update with a precomputed batch mean / mean-square (valuenorm.py:38-55); sums = {sum, sumsq}, n rows
+// w = float(beta), omw = float(1.0 - beta) with the subtraction done in double on the host, as torch evaluates
+// `batch_mean * (1.0 - weight)` (1.0f - 0.99999f would be off by 0.14 %).
+__global__ void vn_update_kernel(float *vn, const double *sums, double n, float w, float omw) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float bm = (float)(sums[0] / n), bs = (float)(sums[1] / n);
+        vn[0] = __fadd_rn(__fmul_rn(vn[0], w), __fmul_rn(bm, omw));
+        vn[1] = __fadd_rn(__fmul_rn(vn[1], w), __fmul_rn(bs, omw));
+        vn[2] = __fadd_rn(__fmul_rn(vn[2], w), omw);
+    }
+}
+
+struct PpoLossParams {
+    float clip, huber_delta, value_coef, inv_rows;  // inv_rows = 1 / (total rows B of the WHOLE batch)
+    int n_agents;
+};
+
+// Fused PPO loss forward + backward for one chunk (algos/mappo.py:133-169 with cal_value_loss :103-131), split into
+// the policy part (needs the actor outputs) and the value part (needs the critic output) so that actor and critic
+// can share one activation scratch.  One thread per env-step row r; the N agent rows of r share adv / returns.
+// adv_stats = {sum, sumsq} of the raw advantages over all n_adv env-step rows (population std + 1e-5, mappo.py:195-198).
+__device__ __forceinline__ float normalized_adv(const float *ret, const float *v_old, const float *vn_gae,
+                                                const double *adv_stats, double n_adv, int r) {
+    float gm, gs;
+    vn_mean_std(vn_gae, gm, gs);
+    const double am = adv_stats[0] / n_adv;
+    const double avar = fmax(adv_stats[1] / n_adv - am * am, 0.0);
+    return (float)(((double)(ret[r] - (v_old[r] * gs + gm)) - am) / (sqrt(avar) + 1e-5));
+}
+
+// policy part: writes dmu [rows*N,2]; accumulates dlogstd[2] and stats {0: policy_loss_sum, 2: ratio_sum} over agent rows
+__global__ void ppo_policy_loss_kernel(const float *__restrict__ mu, const float *__restrict__ logp_new,
+                                       const float *__restrict__ actions, const float *__restrict__ logstd,
+                                       const float *__restrict__ logp_old, const float *__restrict__ ret,
+                                       const float *__restrict__ v_old, const float *__restrict__ vn_gae,
+                                       const double *__restrict__ adv_stats, double n_adv, float *__restrict__ dmu,
+                                       float *__restrict__ dlogstd, double *__restrict__ stats, int rows, PpoLossParams P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float pl = 0.f, rs = 0.f, dls0 = 0.f, dls1 = 0.f;
+    if (r < rows) {
+        const int N = P.n_agents;
+        const float adv = normalized_adv(ret, v_old, vn_gae, adv_stats, n_adv, r);
+        const float sd0 = expf(logstd[0]), sd1 = expf(logstd[1]);
+        const float iv0 = 1.f / (sd0 * sd0), iv1 = 1.f / (sd1 * sd1);
+        for (int n = 0; n < N; ++n) {
+            const size_t i = (size_t)r * N + n;
+            const float ratio = expf(logp_new[i] - logp_old[i]);
+            const float s1 = ratio * adv;
+            const float s2 = fminf(fmaxf(ratio, 1.f - P.clip), 1.f + P.clip) * adv;
+            pl += -2.f * fminf(s1, s2);  // two equal log-prob columns (shared_buffer.py:61-62): the loss is 2x
+            rs += ratio;
+            const bool inrange = (ratio >= 1.f - P.clip) && (ratio <= 1.f + P.clip);
+            const float dmin = inrange ? adv : ((s1 < s2) ? adv : 0.f);   // torch.min / clamp sub-gradients
+            const float dlogp = -2.f * P.inv_rows * dmin * ratio;
+            const float d0 = actions[i * 2 + 0] - mu[i * 2 + 0], d1 = actions[i * 2 + 1] - mu[i * 2 + 1];
+            dmu[i * 2 + 0] = dlogp * d0 * iv0;
+            dmu[i * 2 + 1] = dlogp * d1 * iv1;
+            dls0 = fmaf(dlogp, d0 * d0 * iv0 - 1.f, dls0);
+            dls1 = fmaf(dlogp, d1 * d1 * iv1 - 1.f, dls1);
+        }
+    }
+    double a = pl, c = rs;
+    float e0 = dls0, e1 = dls1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL_MASK, a, o); c += __shfl_xor_sync(FULL_MASK, c, o);
+        e0 += __shfl_xor_sync(FULL_MASK, e0, o); e1 += __shfl_xor_sync(FULL_MASK, e1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], a); atomicAdd(&stats[2], c);
+        atomicAdd(&dlogstd[0], e0); atomicAdd(&dlogstd[1], e1);
+    }
+}
+
+// value part: writes dv [rows]; accumulates stats[1] = value_loss_sum over agent rows.  vn_now = ValueNorm state
+// AFTER this epoch's update (cal_value_loss updates before normalising, mappo.py:107-109).
+__global__ void ppo_value_loss_kernel(const float *__restrict__ ret, const float *__restrict__ v_old,
+                                      const float *__restrict__ v_new, const float *__restrict__ vn_now,
+                                      float *__restrict__ dv, double *__restrict__ stats, int rows, PpoLossParams P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float vl = 0.f;
+    if (r < rows) {
+        const int N = P.n_agents;
+        float nm, ns;
+        vn_mean_std(vn_now, nm, ns);
+        const float nret = (ret[r] - nm) / ns;
+        const float v = v_new[r], vo = v_old[r];
+        const float e = nret - v;
+        const float ec = nret - (vo + fminf(fmaxf(v - vo, -P.clip), P.clip));
+        const float d = P.huber_delta;
+        // one-sided Huber, as the reference computes it (utils/util.py:36-39): zero for e < -d
+        const float h = (fabsf(e) <= d ? e * e * 0.5f : 0.f) + (e > d ? d * (fabsf(e) - 0.5f * d) : 0.f);
+        const float hc = (fabsf(ec) <= d ? ec * ec * 0.5f : 0.f) + (ec > d ? d * (fabsf(ec) - 0.5f * d) : 0.f);
+        const float dh = (fabsf(e) <= d ? e : 0.f) + (e > d ? d : 0.f);
+        const float dhc = (fabsf(ec) <= d ? ec : 0.f) + (ec > d ? d : 0.f);
+        const float w1 = h > hc ? 1.f : (h < hc ? 0.f : 0.5f);           // torch.max splits ties evenly
+        const float inv = (fabsf(v - vo) <= P.clip) ? 1.f : 0.f;          // clamp passes gradient inside the range
+        vl = (float)N * fmaxf(h, hc);
+        // N identical agent rows per env step: gradient = N * per-row term / B
+        dv[r] = (w1 * (-dh) + (1.f - w1) * (-dhc) * inv) * P.inv_rows * (float)N * P.value_coef;
+    }
+    double b = vl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(FULL_MASK, b, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[1], b);
+}
+
+// sum of squares of a flat gradient buffer -> out (float64)
+__global__ void sumsq_kernel(const float *__restrict__ g, size_t n, double *__restrict__ out) {
+    double q = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        q += (double)g[i] * g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL_MASK, q, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, q);
+}
+
+// clip_grad_norm_(max_norm) + Adam step (torch.optim.Adam, no weight decay / amsgrad), fused over the flat buffer.
+// sumsq = squared global grad norm of this net (after the cross-GPU all-reduce, if any).
+__global__ void clip_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                 float *__restrict__ v, size_t n, const double *__restrict__ sumsq, float max_norm, float lr,
+                                 float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+    const float total = (float)sqrt(*sumsq) * grad_scale;
+    const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * grad_scale;
+    const float step = lr / bc1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
+}  // namespace dcc

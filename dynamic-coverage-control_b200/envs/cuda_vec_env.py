@@ -123,27 +123,40 @@ class CudaVecEnv:
         _lib.check(self.lib.dcc_env_set_launch(self._h, int(warps_per_cta), int(ctas)), "dcc_env_set_launch")
 
     # ---- reference surface ---------------------------------------------------------------------------
-    def reset(self):
+    def _obs_out(self, out_obs):
+        if out_obs is None:
+            return self.obs
+        if not (isinstance(out_obs, torch.Tensor) and out_obs.is_cuda and out_obs.dtype == torch.float32 and
+                out_obs.is_contiguous() and out_obs.numel() == self.obs.numel()):
+            raise ValueError("out_obs must be a contiguous CUDA float32 tensor with E*N*D elements")
+        return out_obs
+
+    def reset(self, out_obs=None):
+        """out_obs (tensor mode): write the observations there instead of the env's own buffer — the rollout
+        storage passes `buffer.obs[0]` so nothing is copied afterwards."""
         if self.numpy_compat:
             hb = self._host_buffers()
             _lib.check(self.lib.dcc_env_reset_host(self._h, hb["obs"].ctypes.data, self._stream()), "dcc_env_reset_host")
             return hb["obs"].astype(np.float64)
-        _lib.check(self.lib.dcc_env_reset(self._h, self._ptr(self.obs), self._stream()), "dcc_env_reset")
-        return self.obs
+        obs = self._obs_out(out_obs)
+        _lib.check(self.lib.dcc_env_reset(self._h, self._ptr(obs), self._stream()), "dcc_env_reset")
+        return obs
 
-    def step(self, actions):
+    def step(self, actions, out_obs=None):
         if self.numpy_compat:
             return self._step_numpy(actions)
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32):
             raise TypeError("tensor mode expects a CUDA float32 tensor of shape (E,N,2); use numpy_compat=True for numpy")
-        if tuple(actions.shape) != (self.n_envs, self.n_agents, 2):
-            raise ValueError("actions shape %s != %s" % (tuple(actions.shape), (self.n_envs, self.n_agents, 2)))
+        if actions.numel() != self.n_envs * self.n_agents * 2:
+            raise ValueError("actions has %d elements, expected E*N*2 = %d" % (actions.numel(), self.n_envs * self.n_agents * 2))
         actions = actions.contiguous()
-        _lib.check(self.lib.dcc_env_step(self._h, self._ptr(actions), self._ptr(self.obs), self._ptr(self.rewards),
+        obs = self._obs_out(out_obs)
+        _lib.check(self.lib.dcc_env_step(self._h, self._ptr(actions), self._ptr(obs), self._ptr(self.rewards),
                                          self._ptr(self.dones_u8), self._ptr(self.coverage_rate),
                                          self._ptr(self.connect_bits), self._ptr(self.adj), self._ptr(self.adj_s),
                                          self._stream()), "dcc_env_step")
-        return self.obs, self.rewards, self.dones_u8.view(torch.bool), CoverageInfos(self.coverage_rate)
+        return obs.view(self.n_envs, self.n_agents, self.obs_dim), self.rewards, self.dones_u8.view(torch.bool), \
+            CoverageInfos(self.coverage_rate)
 
     def step_async(self, actions):
         self._pending = actions

@@ -156,6 +156,141 @@ int64_t dcc_env_launch_count(void *handle);
 int dcc_host_alloc(void **ptr, size_t bytes);
 int dcc_host_free(void *ptr);
 
+
+/* =====================================================================================================
+ * MAPPO learner path.
+ *
+ * Replaces, below the reference's algo boundary (algos/mappo.py: MAPPOPolicy.get_actions / get_values /
+ * evaluate_actions, MAPPOTrainer.train / ppo_update / cal_value_loss; buffer/shared_buffer.py:
+ * compute_returns; utils/valuenorm.py), the torch-CPU networks, the NumPy GAE loop and the autograd graph
+ * with CUDA kernels.  The Python host (dcc_b200/algos, dcc_b200/buffer) keeps the reference's class and
+ * method names.
+ *
+ * Memory conventions
+ *   - parameters, gradients and Adam moments of each net are CALLER-owned flat float32 device buffers in the
+ *     reference's state_dict order without the never-used fc_h block (mlp.py:21-23):
+ *       base.feature_norm.weight[in] .bias[in]  base.mlp.fc1.0.weight[H,in] .bias[H]  base.mlp.fc1.2.weight[H] .bias[H]
+ *       base.mlp.fc2.0.0.weight[H,H] .bias[H]  base.mlp.fc2.0.2.weight[H] .bias[H]
+ *       head.weight[out,H] head.bias[out]      (actor: act.action_out.fc_mean, out = 2; critic: v_out, out = 1)
+ *       actor only: act.action_out.logstd._bias[2]
+ *     (in = D for the actor, N*D for the critic);
+ *   - the rollout is stored per ENV-STEP row (t,e): the N agent rows of an env share reward, mask, value and
+ *     return (shared reward environment.py:106-108; identical critic input learner.py:219-220), so those
+ *     arrays are [T(+1), E]; obs is [T+1, E, N, D] and doubles as the critic input [T+1, E, N*D];
+ *   - ValueNorm state = 3 float32 {running_mean, running_mean_sq, debiasing_term} (valuenorm.py:24-26);
+ *   - the handle owns only activation scratch for `chunk_rows` env-step rows; bigger batches are streamed in
+ *     chunks with gradient accumulation == the reference's single minibatch (num_mini_batch 1, mappo.yaml:43).
+ * ===================================================================================================== */
+typedef struct dcc_mappo_cfg {
+    int32_t n_agents;        /* N */
+    int32_t obs_dim;         /* D (actor input); the critic input is N*D */
+    int32_t hidden;          /* algo_hidden_size, <= 256 (mappo.yaml: 256) */
+    int32_t act_dim;         /* 2 (Box(2), environment.py:52) */
+    int32_t chunk_rows;      /* env-step rows per activation chunk; 0 = auto (~1.5 GB of scratch) */
+    int32_t gemm_backend;    /* 0 = auto, 1 = SIMT fp32 FFMA, 2 = tcgen05 3xTF32 (hidden == 256 only) */
+    float clip_param;        /* 0.2     mappo.yaml */
+    float entropy_coef;      /* 0.01 */
+    float value_loss_coef;   /* 1.0 */
+    float huber_delta;       /* 10.0 */
+    float max_grad_norm;     /* 10.0 */
+    float gamma;             /* 0.99 */
+    float gae_lambda;        /* 0.95 */
+    float opti_eps;          /* 1e-5    Adam eps */
+    float adam_beta1;        /* 0.9 */
+    float adam_beta2;        /* 0.999 */
+    double vn_beta;          /* 0.99999 valuenorm.py:11 (double: torch forms 1.0 - beta in double before the float32 op) */
+} dcc_mappo_cfg;
+
+int dcc_mappo_cfg_default(dcc_mappo_cfg *cfg);
+int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle);
+int dcc_mappo_destroy(void *handle);
+/* Flat parameter count of a net: which = 0 actor, 1 critic. */
+int64_t dcc_mappo_param_count(void *handle, int which);
+int dcc_mappo_chunk_rows(void *handle);
+/* GEMM backend actually in use: 1 = SIMT fp32, 2 = tcgen05 3xTF32. */
+int dcc_mappo_gemm_backend(void *handle);
+int64_t dcc_mappo_launch_count(void *handle);
+
+/*
+ * Replaces MAPPOPolicy.get_actions (algos/mappo.py:43-49) -> R_Actor.forward (r_actor_critic.py:43-57) +
+ * R_Critic.forward (:111-121) on one vec-env step.
+ *   d_obs     [n_envs, N, D] float32 (the env's obs buffer; the critic reads it as [n_envs, N*D])
+ *   d_actions [n_envs*N, 2]  a = mu + exp(logstd) * eps, eps ~ N(0,1) from Philox4x32-10 keyed by (seed, offset,
+ *             agent row); deterministic != 0 returns mu (FixedNormal.mode)
+ *   d_logp    [n_envs*N]     sum over the 2 action dims of Normal.log_prob (distributions.py:33-35)     [opt]
+ *   d_values  [n_envs]       critic output in ValueNorm-normalised units, one per env (the reference
+ *             evaluates N identical rows per env)                                                     [opt]
+ * d_actor / d_critic may be NULL to skip that net (get_values = actor NULL; act = critic NULL).
+ */
+int dcc_mappo_act(void *handle, const float *d_actor, const float *d_critic, const float *d_obs, int n_envs,
+                  uint64_t seed, uint64_t offset, int deterministic, float *d_actions, float *d_logp, float *d_values,
+                  dcc_stream_t stream);
+
+/*
+ * Replaces MAPPOPolicy.evaluate_actions (algos/mappo.py:55-61), forward only: log-prob of GIVEN actions, the
+ * mean, and the values.  Shapes as dcc_mappo_act; d_mu [n_envs*N, 2] optional.
+ */
+int dcc_mappo_evaluate(void *handle, const float *d_actor, const float *d_critic, const float *d_obs,
+                       const float *d_actions, int n_envs, float *d_logp, float *d_values, float *d_mu,
+                       dcc_stream_t stream);
+
+/*
+ * Replaces the per-step bookkeeping of Learner.insert (learner.py:254-276): reward of the env (entry 0 of the N
+ * equal entries) and masks = 1 - done.  d_rew_in [E,N] float32, d_done_in [E,N] uint8 -> d_rew_out [E], d_mask_out [E].
+ */
+int dcc_rollout_insert(const float *d_rew_in, const uint8_t *d_done_in, int n_envs, int n_agents, float *d_rew_out,
+                       float *d_mask_out, dcc_stream_t stream);
+
+/*
+ * Replaces SharedReplayBuffer.compute_returns, live branch (buffer/shared_buffer.py:199-208) with
+ * ValueNorm.denormalize folded in (valuenorm.py:68-79).
+ *   d_rewards [T,E], d_values [T+1,E] (d_values[T] = bootstrap value), d_masks [T+1,E], d_vn_state[3]
+ *   -> d_returns [T+1,E] (rows 0..T-1 written)
+ */
+int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, const float *d_masks,
+                  const float *d_vn_state, int T, int E, float *d_returns, dcc_stream_t stream);
+
+/*
+ * MAPPOTrainer.train prologue (algos/mappo.py:189-198): advantage = returns - denormalize(value_preds) and its
+ * global mean / population std, plus the batch statistics ValueNorm.update needs every epoch.
+ * d_stats_out: 4 float64 {sum adv, sum adv^2, sum ret, sum ret^2} over this rank's T*E env-step rows — a
+ * caller-visible buffer so that a multi-GPU host can all-reduce (SUM) it before the epochs.
+ * Also snapshots the ValueNorm state (advantages use the state BEFORE this update's ValueNorm.update calls).
+ */
+int dcc_mappo_train_begin(void *handle, const float *d_returns, const float *d_values, const float *d_vn_state, int T,
+                          int E, double *d_stats_out, dcc_stream_t stream);
+
+/*
+ * One PPO epoch up to and including total_loss.backward() (algos/mappo.py:133-174) on this rank's rollout:
+ * ValueNorm.update (valuenorm.py:38-55, in place on d_vn_state), evaluate_actions, clipped-ratio policy loss
+ * (2x: two equal log-prob columns, shared_buffer.py:61-62), Gaussian entropy, clipped one-sided-Huber value
+ * loss (utils/util.py:36-39), and the gradients of both nets.
+ *   d_obs [T+1,E,N,D] (first T used), d_actions [T,E,N,2], d_logp_old [T,E,N], d_values / d_returns [T+1,E]
+ *   d_stats4        the (all-reduced) output of dcc_mappo_train_begin; n_rows_global = global T*E
+ *   d_grad_actor / d_grad_critic   flat, zeroed here then accumulated: SUM over this rank's rows of the
+ *                   per-row gradient already divided by the GLOBAL row count, so a SUM all-reduce across ranks
+ *                   yields the big-batch gradient (the entropy-bonus term is added once, in dcc_mappo_apply)
+ *   d_epoch_stats   4 float64, += {policy_loss_sum, value_loss_sum, ratio_sum (over agent rows), dist_entropy}
+ */
+int dcc_mappo_epoch_grads(void *handle, const float *d_actor, const float *d_critic, float *d_grad_actor,
+                          float *d_grad_critic, const float *d_obs, const float *d_actions, const float *d_logp_old,
+                          const float *d_values, const float *d_returns, float *d_vn_state, const double *d_stats4,
+                          double n_rows_global, int T, int E, double *d_epoch_stats, dcc_stream_t stream);
+
+/*
+ * clip_grad_norm_(max_grad_norm) + torch.optim.Adam.step for one net (algos/mappo.py:176-185), fused over the
+ * flat buffers, on the (all-reduced) gradient.  which = 0 actor (adds the entropy-bonus gradient first), 1 critic.
+ * step = 1-based Adam step count; lr = the decayed learning rate (utils/util.py:29-33).
+ * d_grad_norm_sq_out (1 float64, optional) receives the squared pre-clip gradient norm.
+ */
+int dcc_mappo_apply(void *handle, int which, float *d_params, float *d_grads, float *d_adam_m, float *d_adam_v,
+                    float lr, int64_t step, double *d_grad_norm_sq_out, dcc_stream_t stream);
+
+/* Kernel-level test hook: C[M,N] (+)= op(A)[M,K] op(B)[K,N], row-major with leading dimensions; ta/tb = operand
+ * stored transposed.  backend as dcc_mappo_cfg.gemm_backend (2 requires the shapes the tcgen05 kernels cover). */
+int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *d_A, int lda,
+                const float *d_B, int ldb, float *d_C, int ldc, int accumulate, dcc_stream_t stream);
+
 const char *dcc_status_string(int status);
 const char *dcc_last_cuda_error(void);
 int dcc_abi_version(void);

@@ -1,0 +1,282 @@
+"""GPU parity tests of the MAPPO learner path, through the C ABI.
+
+Checked against (1) golden vectors recorded from the UNMODIFIED reference learner (tests/golden/mappo_*.npz) and
+(2) the float64 NumPy oracle (oracle/mappo_oracle.py) on seeded inputs.  Tolerances (float32 path, BASELINE
+north_star: "rewards/obs/logits within fp32 1e-5"): log-probs / values 1e-5 relative + 2e-5 absolute, GAE returns
+1e-5 relative, train_info 5e-5, post-update parameters 2e-5 relative + 3e-6 absolute (15 Adam steps of fp32 noise).
+"""
+import ctypes as C
+import glob
+import json
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+from mappo_util import actor_param_shapes, critic_param_shapes, make_params
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "mappo_*.npz")))
+BACKENDS = [1, 0]   # SIMT fp32, auto (tcgen05 3xTF32 where the shape allows)
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, "mappo_%s.npz" % name))
+    g = {k: z[k] for k in z.files}
+    g["cfg"] = json.loads(str(g["cfg"]))
+    return g
+
+
+def make_cfg(c, E, T, **over):
+    from dcc_b200.utils.config import load_config
+    cfg = load_config(None, num_agents=c["n_agents"], num_pois=c["n_pois"], n_rollout_threads=E, max_ep_len=T,
+                      algo_hidden_size=c["hidden"], ppo_epoch=c["ppo_epoch"], seed=c["seed"], n_iters=c["n_iters"],
+                      n_eval_rollout_threads=0)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def build(c, E, T, **over):
+    import torch
+    from dcc_b200.algos import MAPPOPolicy, MAPPOTrainer
+    from dcc_b200.buffer import SharedReplayBuffer
+    from dcc_b200.envs.spaces import Box
+    cfg = make_cfg(c, E, T, **over)
+    N, D = c["n_agents"], c["obs_dim"]
+    obs_space, share_space, act_space = Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,))
+    pol = MAPPOPolicy(cfg, obs_space, share_space, act_space)
+    pol.actor.load_state_dict(make_params(actor_param_shapes(D, c["hidden"]), c["actor_seed"]))
+    pol.critic.load_state_dict(make_params(critic_param_shapes(N * D, c["hidden"]), c["critic_seed"]))
+    tr = MAPPOTrainer(cfg, pol)
+    buf = SharedReplayBuffer(cfg, obs_space, share_space, act_space)
+    torch.cuda.synchronize()
+    return cfg, pol, tr, buf
+
+
+def fill_buffer(buf, g, p):
+    import torch
+    dev = buf.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    buf.obs.copy_(t(g[p + "obs"]))
+    buf.actions.copy_(t(g[p + "actions"]))
+    buf.action_log_probs_ten.copy_(t(g[p + "logp"][..., 0]))
+    buf.values_te.copy_(t(g[p + "value_preds"][:, :, 0, 0]))
+    buf.rewards_te.copy_(t(g[p + "rewards"][:, :, 0, 0]))
+    buf.masks_te.copy_(t(g[p + "masks"][:, :, 0, 0]))
+
+
+def check_params(tag, net, g, prefix, rtol=2e-5, atol=3e-6):
+    for k in net.layout:
+        key = prefix + k
+        stride, s, ss = g[key + ":meta"]
+        flat = net.view(k).detach().cpu().numpy().astype(np.float64).reshape(-1)
+        ref = g[key + ":sample"].astype(np.float64)
+        got = flat[::int(stride)]
+        assert np.allclose(got, ref, rtol=rtol, atol=atol), "%s %s max|d|=%g" % (tag, k, np.abs(got - ref).max())
+        assert abs(flat.sum() - s) <= 1e-4 * max(1.0, np.abs(flat).sum()), (tag, k, "sum")
+        assert abs((flat ** 2).sum() - ss) <= 1e-4 * max(1.0, ss), (tag, k, "sumsq")
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", CASES)
+def test_learner_vs_reference_golden(name, backend):
+    """Teacher-forced replay of two reference iterations: forward, GAE, the whole 15-epoch update."""
+    import torch
+    g = load(name)
+    c = g["cfg"]
+    N, D = c["n_agents"], c["obs_dim"]
+    T, E = g["it1_actions"].shape[:2]
+    cfg, pol, tr, buf = build(c, E, T, gemm_backend=backend)
+    for it in range(1, c["iters"] + 1):
+        p = "it%d_" % it
+        fill_buffer(buf, g, p)
+        vn = tr.value_normalizer.state.cpu().numpy()[:3]
+        assert np.allclose(vn, g[p + "vn_before"], rtol=1e-5, atol=1e-12)
+        # evaluate_actions on the recorded (obs, action): log-probs and values of the rollout
+        v, logp, ent = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
+        assert np.allclose(logp.cpu().numpy().reshape(T, E, N, 1), g[p + "logp"], rtol=1e-5, atol=2e-5)
+        vals = pol.get_values(buf.obs.view((T + 1) * E, N * D)).cpu().numpy().reshape(T + 1, E, N, 1)
+        assert np.allclose(vals, g[p + "value_preds"], rtol=1e-5, atol=2e-5)
+        # the reference-style call (N identical rows per env) gives the same values
+        v2 = pol.get_values(buf.share_obs[3].reshape(E * N, N * D), rows_repeated=True).cpu().numpy().reshape(E, N, 1)
+        assert np.allclose(v2, vals[3], rtol=2e-6, atol=2e-6)   # batch size changes the split-K summation order
+        # GAE
+        buf.compute_returns(None, tr.value_normalizer, policy=pol)
+        ret = buf.returns_te.cpu().numpy()[:-1]
+        ref = g[p + "returns"][:-1, :, 0, 0]
+        assert np.allclose(ret, ref, rtol=1e-5, atol=1e-4), np.abs(ret - ref).max()
+        # the reference trains on ITS returns: replay them exactly
+        buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(g[p + "returns"][:, :, 0, 0])).to(buf.device))
+        pol.lr_decay(it, c["n_iters"])
+        assert abs(pol.lr_actor_now - float(g[p + "lr"])) < 1e-12
+        info = tr.train(buf)
+        ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
+                       g[p + "train_info"]))
+        for k in ref:
+            assert abs(info[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (it, k, info[k], ref[k])
+        vn = tr.value_normalizer.state.cpu().numpy()[:3]
+        assert np.allclose(vn, g[p + "vn_after"], rtol=1e-5, atol=1e-12)
+        check_params("actor it%d" % it, pol.actor, g, p + "actor.")
+        check_params("critic it%d" % it, pol.critic, g, p + "critic.")
+        buf.after_update()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_update_vs_oracle_random_batch(backend):
+    """Seeded synthetic rollout with clipped ratios, |error| > huber_delta on both sides, episode ends: one update
+    against the float64 oracle (gradient norms, losses, post-Adam parameters), plus chunking invariance."""
+    import torch
+    from oracle import mappo_oracle as mo
+    N, M, Hd, E, T = 4, 6, 256, 24, 20
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=3, seed=5, n_iters=10, actor_seed=11, critic_seed=12,
+             clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0, max_grad_norm=10.0, huber_delta=10.0, opti_eps=1e-5)
+    rng = np.random.default_rng(7)
+    obs = rng.normal(0, 1.5, (T + 1, E, N, D)).astype(np.float32)
+    act = rng.normal(0, 1.2, (T, E, N, 2)).astype(np.float32)
+    results = []
+    for chunk in (0, 37):
+        rng = np.random.default_rng(8)      # same synthetic rollout for both chunkings
+        cfg, pol, tr, buf = build(c, E, T, gemm_backend=backend, chunk_rows=chunk)
+        dev = buf.device
+        buf.obs.copy_(torch.from_numpy(obs).to(dev))
+        buf.actions.copy_(torch.from_numpy(act).to(dev))
+        tr.value_normalizer.state[:3] = torch.tensor([0.3, 4.0, 0.02], device=dev)
+        _, logp, _ = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
+        lp_old = logp.cpu().numpy().reshape(T, E, N) + rng.normal(0, 0.25, (T, E, N)).astype(np.float32)  # ratios leave [0.8,1.2]
+        vals = rng.normal(0, 1.0, (T + 1, E)).astype(np.float32)
+        rew = rng.normal(0, 30.0, (T, E)).astype(np.float32)
+        rew[rng.random((T, E)) < 0.05] += 400.0          # |normalised error| > huber_delta on the positive side
+        rew[rng.random((T, E)) < 0.05] -= 400.0          # ... and on the (zero-loss, utils/util.py:36-39) negative side
+        masks = (rng.random((T + 1, E)) > 0.1).astype(np.float32)
+        buf.action_log_probs_ten.copy_(torch.from_numpy(lp_old).to(dev))
+        buf.values_te.copy_(torch.from_numpy(vals).to(dev))
+        buf.rewards_te.copy_(torch.from_numpy(rew).to(dev))
+        buf.masks_te.copy_(torch.from_numpy(masks).to(dev))
+        buf.compute_returns(None, tr.value_normalizer, policy=pol)
+        ret = buf.returns_te.cpu().numpy()
+        ovn = mo.ValueNorm((0.3, 4.0, 0.02))
+        oret = mo.gae_returns(rew, vals, masks, ovn, cfg.gamma, cfg.gae_lambda)
+        assert np.allclose(ret[:-1], oret[:-1], rtol=1e-5, atol=1e-3)
+        pol.lr_decay(3, 10)
+        info = tr.train(buf)
+        otr = mo.Trainer(make_params(actor_param_shapes(D, Hd), 11), make_params(critic_param_shapes(N * D, Hd), 12), c,
+                         vn_state=(0.3, 4.0, 0.02))
+        ex = lambda a: np.broadcast_to(a[:, :, None, None], a.shape + (N, 1))   # noqa: E731
+        oinfo = otr.train(obs, act, lp_old[..., None], ex(vals), ex(ret), pol.lr_actor_now, 3)
+        for k in oinfo:
+            assert abs(info[k] - oinfo[k]) <= 5e-5 * max(1.0, abs(oinfo[k])), (k, info[k], oinfo[k])
+        for tag, net, onet in (("actor", pol.actor, otr.actor), ("critic", pol.critic, otr.critic)):
+            for k in net.layout:
+                got = net.view(k).cpu().numpy().astype(np.float64)
+                ref = onet.p[k].reshape(got.shape)
+                assert np.allclose(got, ref, rtol=2e-5, atol=3e-6), (tag, k, np.abs(got - ref).max())
+        assert np.allclose(tr.value_normalizer.state.cpu().numpy()[:3], otr.vn.state(), rtol=1e-5)
+        results.append((pol.actor.params.cpu().numpy(), pol.critic.params.cpu().numpy()))
+        assert info["ratio"] != 1.0 and 0.0 < abs(info["policy_loss"])
+    # chunked (37 env-step rows per chunk) and unchunked updates agree to float32 summation order
+    for a, b in zip(results[0], results[1]):
+        assert np.allclose(a, b, rtol=1e-5, atol=2e-6)
+
+
+def test_sampling_statistics_and_determinism():
+    """get_actions: a = mu + sigma*eps with Philox noise — mean/std/kurtosis of eps, log-prob consistency with
+    evaluate_actions, same seed/offset => same sample regardless of chunking, deterministic=True returns mu."""
+    import torch
+    N, M, Hd, E = 8, 64, 256, 4096
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=1, seed=3, n_iters=10, actor_seed=21, critic_seed=22)
+    obs = torch.from_numpy(np.random.default_rng(1).normal(0, 1, (E, N, D)).astype(np.float32)).cuda()
+    outs = []
+    for chunk in (0, 1000):
+        cfg, pol, tr, buf = build(c, 4, 2, chunk_rows=chunk)
+        v, a, lp, _, _ = pol.get_actions(None, obs)
+        a, lp, v = a.clone(), lp.clone(), v.clone()
+        mu, _ = pol.act(obs, deterministic=True)
+        mu = mu.clone()
+        v2, lp2, ent = pol.evaluate_actions(None, obs, None, None, a)
+        assert torch.allclose(lp, lp2, rtol=1e-6, atol=1e-6) and torch.allclose(v, v2, rtol=2e-6, atol=2e-6)
+        logstd = pol.actor.view("act.action_out.logstd._bias").reshape(1, 2)
+        eps = ((a - mu) / logstd.exp()).cpu().numpy().astype(np.float64)
+        n = eps.size
+        assert abs(eps.mean()) < 5 / np.sqrt(n) and abs(eps.std() - 1) < 5 / np.sqrt(2 * n)
+        assert abs((eps ** 4).mean() - 3.0) < 0.1 and abs(np.corrcoef(eps[:, 0], eps[:, 1])[0, 1]) < 5 / np.sqrt(n / 2)
+        assert abs(float(ent) - float((0.5 + 0.5 * np.log(2 * np.pi) + logstd).sum())) < 1e-6
+        v3, a3, _, _, _ = pol.get_actions(None, obs)
+        assert not torch.equal(a3, a)            # the offset advances: fresh noise on every call
+        outs.append((a.cpu().numpy(), v.cpu().numpy()))
+    # same noise stream whatever the chunking (mu itself moves in the last bits with the GEMM summation order)
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=2e-6) and np.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_primitive_vs_float64(backend):
+    """C = op(A) op(B) for the shapes / transposes the learner uses, against float64 NumPy."""
+    import torch
+    from dcc_b200 import _lib
+    c = dict(n_agents=8, n_pois=64, hidden=256, obs_dim=338, ppo_epoch=1, seed=0, n_iters=1, actor_seed=1, critic_seed=2)
+    cfg, pol, tr, buf = build(c, 2, 2)
+    lib = pol.lib
+    if backend == 2 and lib.dcc_mappo_gemm_backend(pol._h) != 2:
+        pytest.skip("tcgen05 backend not built for this shape")
+    rng = np.random.default_rng(0)
+    shapes = [  # (ta, tb, M, N, K)
+        (0, 1, 1000, 256, 338), (0, 1, 4096 + 17, 256, 256), (0, 1, 300, 256, 2704),      # forward  X W^T
+        (0, 0, 1000, 256, 256),                                                            # dX = dZ W
+        (1, 0, 256, 338, 5000), (1, 0, 256, 256, 4099), (1, 0, 256, 2704, 777),           # dW = dZ^T X
+    ]
+    for ta, tb, M, Nn, K in shapes:
+        A = rng.normal(0, 1, (K, M) if ta else (M, K)).astype(np.float32)
+        B = rng.normal(0, 1, (Nn, K) if tb else (K, Nn)).astype(np.float32)
+        C0 = rng.normal(0, 1, (M, Nn)).astype(np.float32)
+        ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+        dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        for acc in (0, 1):
+            dC = torch.from_numpy(C0).cuda()
+            _lib.check(lib.dcc_op_gemm(pol._h, backend, ta, tb, M, Nn, K, dA.data_ptr(), A.shape[1], dB.data_ptr(),
+                                       B.shape[1], dC.data_ptr(), Nn, acc, None), "dcc_op_gemm")
+            torch.cuda.synchronize()
+            want = ref + (C0 if acc else 0)
+            err = np.abs(dC.cpu().numpy() - want).max()
+            assert err <= 2e-6 * np.sqrt(K) * 4, (backend, ta, tb, M, Nn, K, acc, err)
+
+
+def test_learner_end_to_end_small():
+    """The re-hosted Learner on the reference's YAML-equivalent defaults, shrunk: runs, logs the reference's keys,
+    weights change, checkpoints round-trip with reference state_dict names."""
+    import tempfile
+    import torch
+    from dcc_b200.learner import Learner
+    from dcc_b200.utils.config import load_config
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg = load_config(None, n_rollout_threads=64, max_ep_len=25, ppo_epoch=3, n_iters=3, n_eval_rollout_threads=8,
+                          eval_interval=2, save_interval=3, main_save_path=tmp, save_model=True, log_interval=1)
+        lr = Learner(cfg)
+        w0 = lr.policy.actor.params.clone()
+        infos = []
+        lr.warmup(lr.rl_buffer, lr.train_envs)
+        for it in range(1, 4):
+            lr.policy.lr_decay(it, cfg.n_iters)
+            ri = lr.rollout(lr.rl_buffer, lr.train_envs)
+            ti = lr.rl_update()
+            infos.append((ri, ti))
+            assert set(ri) == {"reward", "coverage_rate"} and 0.0 <= ri["coverage_rate"] <= 1.0
+            assert set(ti) == {"value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"}
+            assert all(np.isfinite(v) for v in ti.values())
+        assert abs(infos[0][1]["dist_entropy"] - 2.837877) < 1e-3   # fresh policy: 2 * (0.5 + 0.5 ln 2 pi)
+        assert not torch.equal(w0, lr.policy.actor.params)
+        ti = lr.rollout(lr.test_buffer, lr.test_envs)
+        assert np.isfinite(ti["reward"])
+        d = os.path.join(tmp, "ck")
+        os.makedirs(d)
+        lr.save_model(d)
+        sd = lr.policy.actor.state_dict()
+        assert "base.mlp.fc_h.0.weight" in sd and "act.action_out.logstd._bias" in sd and len(sd) == 17
+        before = lr.policy.critic.params.clone()
+        lr.policy.critic.params.zero_()
+        lr.load_model(d)
+        assert torch.equal(before, lr.policy.critic.params)
