@@ -15,14 +15,16 @@
 #include <new>
 
 #include "dcc_ops.cuh"
+#include "dcc_tc.cuh"
 
 namespace dcc {
 
 struct NetLayout {
     int in, H, out;
+    int inp;   // `in` rounded up to a multiple of 32: leading dimension of the xhat scratch (zero-padded)
     size_t ln0_g, ln0_b, W1, b1, ln1_g, ln1_b, W2, b2, ln2_g, ln2_b, Wh, bh, logstd, total;
     void init(int in_, int H_, int out_, bool has_logstd) {
-        in = in_; H = H_; out = out_;
+        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32;
         size_t o = 0;
         ln0_g = o; o += in; ln0_b = o; o += in;
         W1 = o; o += (size_t)H * in; b1 = o; o += H; ln1_g = o; o += H; ln1_b = o; o += H;
@@ -45,6 +47,8 @@ struct MappoHandle {
     float *a1, *h1, *a2, *h2, *dA, *dB;   // [chunk*N, H]
     float *mean1, *rstd1, *mean2, *rstd2;   // [chunk*N]
     float *w1g_a, *b1g_a, *w1g_c, *b1g_c;   // fc1 weights with the input LayerNorm affine folded in (per call)
+    // tcgen05 backend: hi/lo-split, 128B-swizzled shared-memory images of the weights (per call), [actor, critic]
+    float *img_w1[2], *img_w2[2], *img_w2t[2];
     float *mu, *logp, *dmu, *vnew, *dv;   // [chunk*N,2], [chunk*N], [chunk*N,2], [chunk], [chunk]
     double *dsums;   // small float64 scratch: [4] actor grad sumsq, [5] critic grad sumsq
     float *vn_gae;   // ValueNorm state snapshot taken at train_begin (3 floats)
@@ -58,7 +62,7 @@ static MappoHandle *as_mappo(void *h) {
 }
 
 // the tcgen05 3xTF32 kernels cover the shipped trunk width only
-static inline bool tc_supported(const dcc_mappo_cfg *c) { return false && c->hidden == 256; }
+static inline bool tc_supported(const dcc_mappo_cfg *c) { return c->hidden == tc::TC_N; }
 
 static inline int grid_for_rows(const MappoHandle *h, long rows, int warps_per_block) {
     long b = (rows + warps_per_block - 1) / warps_per_block;
@@ -110,28 +114,85 @@ static int launch_gemm(MappoHandle *h, bool ta, bool tb, int M, int N, int K, co
     return DCC_OK;
 }
 
+// ---- tcgen05 backend launchers ---------------------------------------------------------------------------------
+static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transposed, int K, float *img, cudaStream_t s) {
+    const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
+    const int n = KT * tc::TC_N * 8;
+    tc::tc_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(W, ldw, transposed ? 1 : 0, K, KT, img);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
+// C[M,256] = A[M,K] * B^T with B given as a weight image (K-major on both sides).  With `bias` the epilogue is the
+// fused bias + ReLU + LayerNorm of an MLP block: a -> a_out (optional), LN(a) * gamma + beta -> h_out.
+static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
+                       cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
+                       const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr) {
+    if (M <= 0) return DCC_OK;
+    if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::TCF_SMEM_BYTES));
+        attr_set = true;
+    }
+    tc::TcfParams p;
+    memset(&p, 0, sizeof p);
+    p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = (K + tc::TC_BK - 1) / tc::TC_BK; p.lda = lda; p.ldc = ldc;
+    p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
+    p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
+    const int row_tiles = (M + tc::TC_BM - 1) / tc::TC_BM;
+    // split-K only to fill the GPU when there are few row tiles and a long K (raw-store epilogue only)
+    p.splits = 1;
+    if (!bias && row_tiles < 2 * h->sm_count && p.KT >= 16) {
+        p.splits = (3 * h->sm_count + row_tiles - 1) / row_tiles;
+        if (p.splits > p.KT / 8) p.splits = p.KT / 8;
+        if (p.splits < 1) p.splits = 1;
+    }
+    p.kt_per_split = (p.KT + p.splits - 1) / p.splits;
+    p.splits = (p.KT + p.kt_per_split - 1) / p.kt_per_split;
+    if (p.splits > 1) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)tc::TC_N * 4, M, s));
+    const int work = row_tiles * p.splits;
+    const int grid = work < h->sm_count ? work : h->sm_count;
+    tc::tc_gemm_fwd_kernel<<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
-static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, float *w1g, float *b1g, cudaStream_t s) {
+static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
+    float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
     fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W1, P + L.b1, P + L.ln0_g, P + L.ln0_b, w1g, b1g, L.H, L.in);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
+    if (h->backend == 2) {
+        int rc;
+        if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s))) return rc;
+        if ((rc = tc_prep_weights(h, P + L.W2, L.H, false, L.H, h->img_w2[net], s))) return rc;
+        if (for_backward && (rc = tc_prep_weights(h, P + L.W2, L.H, true, L.H, h->img_w2t[net], s))) return rc;
+    }
     return DCC_OK;
 }
 
 // trunk forward on `rows` rows of width L.in: x -> h2.  save = keep a1/a2/stats for the backward pass.
-static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, const float *w1g, const float *b1g,
-                         const float *x, int rows, bool save, cudaStream_t s) {
+static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int net, const float *x, int rows, bool save,
+                         cudaStream_t s) {
     const int H = L.H;
     const int wpb = 8;
-    ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in);
+    const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
+    ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
     h->launches++;
-    int rc = launch_gemm(h, false, true, rows, H, L.in, h->x0, L.in, w1g, L.in, h->a1, H, false, s);
+    int rc = h->backend == 2 ? tc_gemm_fwd(h, rows, L.inp, h->x0, L.inp, h->img_w1[net], h->a1, H, s)
+                             : launch_gemm(h, false, true, rows, H, L.in, h->x0, L.inp, w1g, L.in, h->a1, H, false, s);
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a1, b1g, P + L.ln1_g, P + L.ln1_b,
                                                                             save ? h->a1 : nullptr, h->h1, h->mean1,
                                                                             h->rstd1, rows, H);
     h->launches++;
-    rc = launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
+    rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->h1, H, h->img_w2[net], h->a2, H, s)
+                         : launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a2, P + L.b2, P + L.ln2_g, P + L.ln2_b,
                                                                             save ? h->a2 : nullptr, h->h2, h->mean2,
@@ -143,7 +204,7 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, con
 
 // trunk backward: dA holds dL/dh2 on entry; x0 still holds this chunk's xhat.  Accumulates into grads G; the fc1
 // weight slot receives G1 = dz1^T xhat (turned into dW1 / dgamma0 / dbeta0 by ln0_finalize once per epoch).
-static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, float *G, int rows, cudaStream_t s) {
+static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, int rows, cudaStream_t s) {
     const int H = L.H;
     const int wpb = 8;
     const int gr = grid_for_reduce(h, rows, wpb);
@@ -152,12 +213,13 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, fl
     h->launches++;
     int rc = launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);          // dW2 += dz2^T h1
     if (rc) return rc;
-    rc = launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);           // dh1 = dz2 W2
+    rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->dA, H, h->img_w2t[net], h->dB, H, s)                // dh1 = dz2 W2
+                         : launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);
     if (rc) return rc;
     relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
                                                G + L.ln1_b, G + L.b1, rows, H);   // dB := dz1
     h->launches++;
-    rc = launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.in, G + L.W1, L.in, true, s);     // G1 += dz1^T xhat
+    rc = launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.inp, G + L.W1, L.in, true, s);    // G1 += dz1^T xhat
     if (rc) return rc;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -237,7 +299,19 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     const size_t RA = (size_t)chunk * N;
     cudaError_t ce = cudaSuccess;
     auto alloc = [&](float **p, size_t n) { if (ce == cudaSuccess) ce = cudaMalloc(p, n * sizeof(float)); };
-    alloc(&h->x0, RA * D);
+    {   // xhat scratch: [chunk*N, pad32(D)] for the actor or [chunk, pad32(N*D)] for the critic, whichever is larger
+        const size_t xa = RA * (size_t)h->la.inp, xc = (size_t)chunk * h->lc.inp;
+        alloc(&h->x0, xa > xc ? xa : xc);
+    }
+    if (h->backend == 2) {
+        const NetLayout *Ls[2] = {&h->la, &h->lc};
+        for (int n = 0; n < 2; ++n) {
+            const size_t kt1 = Ls[n]->inp / tc::TC_BK, kt2 = (H + tc::TC_BK - 1) / tc::TC_BK;
+            alloc(&h->img_w1[n], kt1 * 2 * tc::TC_B_TILE_FLOATS);
+            alloc(&h->img_w2[n], kt2 * 2 * tc::TC_B_TILE_FLOATS);
+            alloc(&h->img_w2t[n], kt2 * 2 * tc::TC_B_TILE_FLOATS);
+        }
+    }
     alloc(&h->a1, RA * H); alloc(&h->h1, RA * H); alloc(&h->a2, RA * H); alloc(&h->h2, RA * H);
     alloc(&h->dA, RA * H); alloc(&h->dB, RA * H);
     alloc(&h->mean1, RA); alloc(&h->rstd1, RA); alloc(&h->mean2, RA); alloc(&h->rstd2, RA);
@@ -259,7 +333,8 @@ int dcc_mappo_destroy(void *handle) {
     if (!h) return DCC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
     float *bufs[] = {h->x0, h->a1, h->h1, h->a2, h->h2, h->dA, h->dB, h->mean1, h->rstd1, h->mean2, h->rstd2,
-                     h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv, h->vn_gae};
+                     h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv, h->vn_gae,
+                     h->img_w1[0], h->img_w1[1], h->img_w2[0], h->img_w2[1], h->img_w2t[0], h->img_w2t[1]};
     for (float *b : bufs) cudaFree(b);
     cudaFree(h->dsums);
     h->magic = 0;
@@ -296,14 +371,14 @@ static int policy_forward(MappoHandle *h, const float *actor, const float *criti
     const bool do_actor = actor && d_actions && (mode == 0 || d_logp);
     const bool do_critic = critic && d_values;
     int rc;
-    if (do_actor && (rc = fold_ln0(h, h->la, actor, h->w1g_a, h->b1g_a, s))) return rc;
-    if (do_critic && (rc = fold_ln0(h, h->lc, critic, h->w1g_c, h->b1g_c, s))) return rc;
+    if (do_actor && (rc = fold_ln0(h, h->la, actor, 0, false, s))) return rc;
+    if (do_critic && (rc = fold_ln0(h, h->lc, critic, 1, false, s))) return rc;
     for (int e0 = 0; e0 < n_envs; e0 += h->chunk_rows) {
         const int ne = min(h->chunk_rows, n_envs - e0);
         const float *x = d_obs + (size_t)e0 * N * D;
         if (do_actor) {
             const int rows = ne * N;
-            if ((rc = trunk_forward(h, h->la, actor, h->w1g_a, h->b1g_a, x, rows, false, s))) return rc;
+            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s))) return rc;
             actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
                 h->h2, actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
                 d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
@@ -311,7 +386,7 @@ static int policy_forward(MappoHandle *h, const float *actor, const float *criti
             h->launches++;
         }
         if (do_critic) {
-            if ((rc = trunk_forward(h, h->lc, critic, h->w1g_c, h->b1g_c, x, ne, false, s))) return rc;
+            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s))) return rc;
             critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->h2, critic + h->lc.Wh, critic + h->lc.bh,
                                                                       d_values + e0, ne, H);
             h->launches++;
@@ -400,8 +475,8 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
     entropy_stat_kernel<<<1, 32, 0, s>>>(actor + LA.logstd, h->cfg.act_dim, d_epoch_stats + 3);
     h->launches += 2;
     int rc;
-    if ((rc = fold_ln0(h, LA, actor, h->w1g_a, h->b1g_a, s))) return rc;
-    if ((rc = fold_ln0(h, LC, critic, h->w1g_c, h->b1g_c, s))) return rc;
+    if ((rc = fold_ln0(h, LA, actor, 0, true, s))) return rc;
+    if ((rc = fold_ln0(h, LC, critic, 1, true, s))) return rc;
     PpoLossParams P;
     P.clip = h->cfg.clip_param; P.huber_delta = h->cfg.huber_delta; P.value_coef = h->cfg.value_loss_coef;
     P.inv_rows = (float)(1.0 / (n_rows_global * N)); P.n_agents = N;
@@ -411,7 +486,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         const float *x = d_obs + (size_t)r0 * N * D;
         // actor and critic share one activation scratch, so the chunk is processed net by net:
         // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
-        if ((rc = trunk_forward(h, LA, actor, h->w1g_a, h->b1g_a, x, nr * N, true, s))) return rc;
+        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s))) return rc;
         actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
             h->h2, actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
             h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
@@ -423,9 +498,9 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         head_bwd_kernel<2><<<grid_for_reduce(h, nr * N, 8), 256, 0, s>>>(h->dmu, h->h2, actor + LA.Wh, h->dA,
                                                                         grad_actor + LA.Wh, grad_actor + LA.bh, nr * N, H);
         h->launches++;
-        if ((rc = trunk_backward(h, LA, actor, grad_actor, nr * N, s))) return rc;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, nr * N, s))) return rc;
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
-        if ((rc = trunk_forward(h, LC, critic, h->w1g_c, h->b1g_c, x, nr, true, s))) return rc;
+        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s))) return rc;
         critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
         h->launches++;
         ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, d_vn_state, h->dv,
@@ -434,7 +509,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         head_bwd_kernel<1><<<grid_for_reduce(h, nr, 8), 256, 0, s>>>(h->dv, h->h2, critic + LC.Wh, h->dA, grad_critic + LC.Wh,
                                                                     grad_critic + LC.bh, nr, H);
         h->launches++;
-        if ((rc = trunk_backward(h, LC, critic, grad_critic, nr, s))) return rc;
+        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, nr, s))) return rc;
     }
     if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
     if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
@@ -472,12 +547,25 @@ int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float 
 int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *A, int lda, const float *B,
                 int ldb, float *C, int ldc, int accumulate, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
-    if (!h || !A || !B || !C || backend < 0 || backend > 2) return DCC_ERR_INVALID_ARG;
+    if (!h || !A || !B || !C || backend < 0 || backend > 2 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
     DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (backend == 0) backend = h->backend;
+    if (backend == 2) {
+        // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features)
+        if (ta || N != tc::TC_N || accumulate) return DCC_ERR_UNSUPPORTED;
+        const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
+        float *img = nullptr;
+        DCC_CUDA_TRY(cudaMalloc(&img, (size_t)KT * 2 * tc::TC_B_TILE_FLOATS * sizeof(float)));
+        int rc = tc_prep_weights(h, B, ldb, tb == 0, K, img, s);
+        if (!rc) rc = tc_gemm_fwd(h, M, K, A, lda, img, C, ldc, s);
+        cudaStreamSynchronize(s);
+        cudaFree(img);
+        return rc;
+    }
     const int saved = h->backend;
-    if (backend) h->backend = backend;
-    const int rc = launch_gemm(h, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, accumulate != 0,
-                               static_cast<cudaStream_t>(stream));
+    h->backend = 1;
+    const int rc = launch_gemm(h, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, accumulate != 0, s);
     h->backend = saved;
     return rc;
 }

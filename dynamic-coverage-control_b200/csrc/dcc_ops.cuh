@@ -123,7 +123,9 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 //   LN(x) W1^T + b1 = xhat (W1 * gamma0)^T + (b1 + W1 beta0)
 // which makes xhat the only [rows, F] operand of the layer (forward GEMM and weight-gradient GEMM) and removes the
 // dX GEMM of layer 1 from the backward pass altogether (ln0_finalize_kernel).
-__global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F) {
+// The output rows have leading dimension ldo >= F; the pad columns are zero-filled (the tensor-core GEMMs read K in
+// multiples of 32).
+__global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
@@ -134,8 +136,8 @@ __global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__res
         float q = 0.f;
         for (int c = lane; c < F; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
         const float rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
-        float *yr = xhat + (size_t)r * F;
-        for (int c = lane; c < F; c += 32) yr[c] = (xr[c] - mean) * rstd;
+        float *yr = xhat + (size_t)r * ldo;
+        for (int c = lane; c < ldo; c += 32) yr[c] = (c < F) ? (xr[c] - mean) * rstd : 0.f;
     }
 }
 

@@ -1,0 +1,400 @@
+// dcc_tc.cuh — tcgen05 (5th-gen tensor core) GEMM kernels of the MAPPO learner path, sm_100a only.
+//
+// Precision: 3xTF32 split.  Every fp32 operand x is split into hi = tf32(x) and lo = tf32(x - hi); the product is
+// accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the lo*lo term, ~2^-22 relative, is dropped).  This
+// keeps logits / values within fp32 round-off of the reference's fp32 GEMMs (plain TF32 or bf16
+// miss the 1e-5 parity bar by 1-3 orders of magnitude) at one third of the TF32 tensor rate.
+//
+// Operand staging: tcgen05.mma reads both operands from shared memory in the canonical 128-byte-swizzled layouts
+// (8 rows x 128 B atoms, 16-byte chunks XOR-ed with the row index inside the atom):
+//   * activations are loaded by producer warps with coalesced 16-byte global loads, split into hi/lo in registers and
+//     stored straight into the swizzled layout (no TMA round trip: the split has to touch every element anyway);
+//   * weights are pre-split and pre-swizzled once per call into a global "image" of the shared-memory tiles, so a
+//     whole K-tile (hi + lo, 64 KB) arrives with cp.async.bulk (TMA, SASS UBLKCP) on an mbarrier.
+// Accumulators live in TMEM (2 x 256 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile
+// i+1); one thread issues the MMAs; tcgen05.commit arrives on the mbarriers that recycle the stages.
+#pragma once
+#include "dcc_common.cuh"
+
+namespace dcc {
+namespace tc {
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.commit: the mbarrier gets one arrival when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(const float4 &x, float4 &hi, float4 &lo) {
+    hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+    lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
+}
+
+// Shared-memory matrix descriptor (sm_100 UMMA), SWIZZLE_128B: start address, leading / stride byte offsets in
+// 16-byte units, descriptor version 1, layout type 2 (bits 61-63).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::tf32: D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9 / 10-12 = 2), majors (bit 15 / 16:
+// 0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- weight image: [KT] x { hi tile, lo tile }, each tile = 256 (n) rows x 32 (k) floats, K-major, 128B-swizzled ----
+constexpr int TC_N = 256;            // output features per tile == hidden size
+constexpr int TC_BK = 32;            // K per stage: one 128-byte swizzle row
+constexpr int TC_BM = 128;           // rows per accumulator tile
+constexpr int TC_B_TILE_FLOATS = TC_N * TC_BK;       // 8192 floats = 32 KB
+constexpr int TC_A_TILE_FLOATS = TC_BM * TC_BK;      // 4096 floats = 16 KB
+
+// B(k, n) = transposed ? W[k*ldw + n] : W[n*ldw + k], zero beyond K.  One thread per 16-byte chunk.
+__global__ void tc_prep_weights_kernel(const float *__restrict__ W, int ldw, int transposed, int K, int KT,
+                                       float *__restrict__ img) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (kt, n, c)
+    if (idx >= KT * TC_N * 8) return;
+    const int c = idx & 7, n = (idx >> 3) & (TC_N - 1), kt = idx >> 11;
+    float4 x;
+    float *xv = reinterpret_cast<float *>(&x);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = kt * TC_BK + c * 4 + e;
+        xv[e] = (k < K) ? (transposed ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
+    }
+    float4 hi, lo;
+    split_tf32(x, hi, lo);
+    float *tile = img + (size_t)kt * (2 * TC_B_TILE_FLOATS) + n * TC_BK + ((c ^ (n & 7)) << 2);
+    *reinterpret_cast<float4 *>(tile) = hi;
+    *reinterpret_cast<float4 *>(tile + TC_B_TILE_FLOATS) = lo;
+}
+
+// ---- forward-shaped GEMM: C[M, 256] = A[M, K] * B^T, A row-major (K contiguous), B from a weight image ----------
+//
+// Accuracy: the tensor core adds into its TMEM accumulator with round-toward-zero, so one long accumulator chain
+// drifts by ~0.1 ulp per MMA, always toward zero (measured rms 7e-9 * K relative — 2.4e-6 at K = 352, 1.9e-5 at
+// K = 2720 — far from the 1.5e-7 of an fp32 FFMA chain).  The kernel therefore never lets a chain grow: each K-stage
+// (32 elements = 12 MMAs) starts a FRESH accumulator (the two 256-column TMEM buffers ping-pong per stage), and the
+// epilogue warps drain every finished stage into an fp32 register tile with round-to-nearest adds while the next
+// stage's MMAs run.  Measured: rms 2.5e-7 relative, independent of K.
+//
+// Warp roles (512 threads, 4 warpgroups; registers re-split with setmaxnreg):
+//   WG0 warps 0-3    producers: activation tile LDG -> hi/lo split -> swizzled STS; thread 0 issues the weight bulk copies
+//   WG1 warps 4-7    accumulate / epilogue, columns   0-127 (TMEM lane quarter = warp % 4, one row per thread)
+//   WG2 warps 8-11   accumulate / epilogue, columns 128-255
+//   WG3 warp 12      MMA issuer (one thread) + TMEM allocation; warps 13-15 idle
+constexpr int TCF_STAGES = 2;
+constexpr int TCF_STAGE_BYTES = 2 * TC_A_TILE_FLOATS * 4 + 2 * TC_B_TILE_FLOATS * 4;   // 96 KB
+constexpr int TCF_XPOSE_BYTES = 8 * 32 * 32 * 4;   // per-warp 32x32 store staging (XOR-swizzled columns: conflict-free)
+constexpr int TCF_SMEM_BYTES = TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES + 1024 /*align*/ + 1280 /*barriers, row stats*/;
+static_assert(TCF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int TCF_THREADS = 512;
+
+enum { TCF_EPI_STORE = 0, TCF_EPI_BIAS_RELU_LN = 1 };
+
+struct TcfParams {
+    const float *A;      // [M, lda], lda % 4 == 0, 16-byte aligned
+    const float *Bimg;   // [KT] x 64 KB
+    float *C;            // [M, ldc]: raw product (EPI_STORE) or the post-ReLU activation a (EPI_BIAS_RELU_LN, may be NULL)
+    int M, K, KT, lda, ldc;
+    // split-K for load balance when there are few row tiles (partials combined with red.global.add; C zeroed first)
+    int splits, kt_per_split;
+    // fused epilogue (EPI_BIAS_RELU_LN): a = relu(z + bias); h = LayerNorm(a) * gamma + beta (mlp.py:19-22)
+    int epi;
+    const float *bias, *gamma, *beta;
+    float *H;            // [M, ldc]
+    float *mean, *rstd;  // [M] (may be NULL)
+};
+
+__device__ __forceinline__ void red_add_f32(float *addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float *xpose = reinterpret_cast<float *>(smem + TCF_STAGES * TCF_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES);
+    uint64_t *full = bars, *empty = bars + TCF_STAGES, *tfull = bars + 2 * TCF_STAGES, *tempty = bars + 2 * TCF_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TCF_STAGES + 4);
+    float *rowstat = reinterpret_cast<float *>(bars + 16);   // [2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_work = ((p.M + TC_BM - 1) / TC_BM) * p.splits;   // work item = (row tile, K split)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TCF_STAGES; ++s) {
+            mbar_init(&full[s], 4 + 1);   // 4 producer warps + the weight-tile expect_tx arrival
+            mbar_init(&empty[s], 1);      // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);      // tcgen05.commit
+            mbar_init(&tempty[a], 8);     // 8 accumulate warps
+        }
+        fence_mbar_init();
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== producers =====
+        setmaxnreg_dec<80>();
+        const int t = threadIdx.x;            // 0..127
+        const int c = t & 7, rsub = t >> 3;   // 16-byte chunk within the 128-byte row; row within a 16-row group
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int m0 = (w / p.splits) * TC_BM;
+            const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
+            for (int kt = kt0; kt < kt1; ++kt, ++it) {
+                const int s = it % TCF_STAGES;
+                const uint32_t ph = (it / TCF_STAGES) & 1;
+                uint8_t *st = smem + s * TCF_STAGE_BYTES;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (t == 0) {
+                    mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
+                    const float *src = p.Bimg + (size_t)kt * (2 * TC_B_TILE_FLOATS);
+                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
+                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
+                                  TC_B_TILE_FLOATS * 4, &full[s]);
+                }
+                const int kcol = kt * TC_BK + c * 4;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + i * 16 + rsub;
+                    v[i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.A + (size_t)row * p.lda + kcol))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 16 + rsub;
+                    float4 hi, lo;
+                    split_tf32(v[i], hi, lo);
+                    const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4 *>(st + off) = hi;
+                    *reinterpret_cast<float4 *>(st + TC_A_TILE_FLOATS * 4 + off) = lo;
+                }
+                fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== MMA issuer: one thread of warp 12 =====
+        setmaxnreg_dec<32>();
+        if (warp == 12 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_N, 0, 0);
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
+                for (int kt = kt0; kt < kt1; ++kt, ++it) {
+                    const int s = it & 1;              // smem stage and TMEM accumulator advance together
+                    const uint32_t ph = (it >> 1) & 1;
+                    mbar_wait(&tempty[s], ph ^ 1);     // accumulator drained by the epilogue warps
+                    mbar_wait(&full[s], ph);           // operands landed
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + s * TC_N;
+                    const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
+                    const uint64_t a_hi = make_desc_sw128(sa, 16, 1024);
+                    const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, 16, 1024);
+                    const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, 16, 1024);
+                    const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
+                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);   // fresh chain per stage
+                        tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                        tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
+                    tc_commit(&tfull[s]);      // accumulator ready to drain
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== accumulate / epilogue warps 4-11 =====
+        setmaxnreg_inc<200>();
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int half = (warp - 4) >> 2;       // column half: 0 -> 0..127, 1 -> 128..255
+        const int ew = warp - 4;
+        float *xp = xpose + ew * (32 * 32);
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
+            float acc[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+            for (int kt = kt0; kt < kt1; ++kt, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&tfull[s], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + s * TC_N + half * 128 + j * 32 + lane_bits, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[s]);
+            }
+            // ---- tile epilogue from registers: thread = row (q*32 + lane), 128 columns [half*128, +128) ----
+            const int row0 = (w / p.splits) * TC_BM + q * 32;
+            const int rl = q * 32 + lane;
+            float mean = 0.f, rstd = 0.f;
+            if (p.epi == TCF_EPI_BIAS_RELU_LN) {
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    acc[i] = fmaxf(acc[i] + __ldg(p.bias + half * 128 + i), 0.f);
+                    sum += acc[i];
+                }
+                rowstat[half * 128 + rl] = sum;
+                named_bar_sync(1, 256);
+                mean = (rowstat[rl] + rowstat[128 + rl]) * (1.f / TC_N);
+                named_bar_sync(1, 256);
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) { const float d = acc[i] - mean; sq = fmaf(d, d, sq); }
+                rowstat[half * 128 + rl] = sq;
+                named_bar_sync(1, 256);
+                rstd = rsqrtf((rowstat[rl] + rowstat[128 + rl]) * (1.f / TC_N) + 1e-5f);
+                named_bar_sync(1, 256);
+                if (half == 0 && row0 + lane < p.M) {
+                    if (p.mean) p.mean[row0 + lane] = mean;
+                    if (p.rstd) p.rstd[row0 + lane] = rstd;
+                }
+            }
+            // stores through a per-warp 32x32 transpose so that every instruction writes whole 128-byte lines
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col0 = half * 128 + j * 32;
+                if (p.epi == TCF_EPI_STORE || p.C) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = acc[j * 32 + i];
+                    __syncwarp();
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        if (row0 + r < p.M) {
+                            float *dst = p.C + (size_t)(row0 + r) * p.ldc + col0 + lane;
+                            if (p.splits > 1) red_add_f32(dst, xp[r * 32 + (lane ^ r)]);
+                            else *dst = xp[r * 32 + (lane ^ r)];
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (p.epi == TCF_EPI_BIAS_RELU_LN) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = (acc[j * 32 + i] - mean) * rstd;
+                    __syncwarp();
+                    const float g = __ldg(p.gamma + col0 + lane), b = __ldg(p.beta + col0 + lane);
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r)
+                        if (row0 + r < p.M) p.H[(size_t)(row0 + r) * p.ldc + col0 + lane] = fmaf(xp[r * 32 + (lane ^ r)], g, b);
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc
+}  // namespace dcc

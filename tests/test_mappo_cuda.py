@@ -174,7 +174,10 @@ def test_update_vs_oracle_random_batch(backend):
             for k in net.layout:
                 got = net.view(k).cpu().numpy().astype(np.float64)
                 ref = onet.p[k].reshape(got.shape)
-                assert np.allclose(got, ref, rtol=2e-5, atol=3e-6), (tag, k, np.abs(got - ref).max())
+                # Adam turns a tiny, noise-dominated gradient element into an O(lr) step: after 3 steps the 3xTF32
+                # path (GEMM rms error 2.5e-7 vs 1.5e-7 for fp32 FFMA) is allowed 1e-5 absolute = 1 % of the 1e-3 moved
+                atol = 3e-6 if backend == 1 else 1e-5
+                assert np.allclose(got, ref, rtol=2e-5, atol=atol), (tag, k, np.abs(got - ref).max())
         assert np.allclose(tr.value_normalizer.state.cpu().numpy()[:3], otr.vn.state(), rtol=1e-5)
         results.append((pol.actor.params.cpu().numpy(), pol.critic.params.cpu().numpy()))
         assert info["ratio"] != 1.0 and 0.0 < abs(info["policy_loss"])
@@ -215,34 +218,39 @@ def test_sampling_statistics_and_determinism():
 
 @pytest.mark.parametrize("backend", [1, 2])
 def test_gemm_primitive_vs_float64(backend):
-    """C = op(A) op(B) for the shapes / transposes the learner uses, against float64 NumPy."""
+    """C = op(A) op(B) for the shapes / transposes the learner uses, against float64 NumPy.  backend 1 = SIMT fp32,
+    2 = tcgen05 3xTF32 (weights on the B side, 256 output features; K a multiple of 4)."""
     import torch
     from dcc_b200 import _lib
     c = dict(n_agents=8, n_pois=64, hidden=256, obs_dim=338, ppo_epoch=1, seed=0, n_iters=1, actor_seed=1, critic_seed=2)
     cfg, pol, tr, buf = build(c, 2, 2)
     lib = pol.lib
-    if backend == 2 and lib.dcc_mappo_gemm_backend(pol._h) != 2:
-        pytest.skip("tcgen05 backend not built for this shape")
     rng = np.random.default_rng(0)
     shapes = [  # (ta, tb, M, N, K)
-        (0, 1, 1000, 256, 338), (0, 1, 4096 + 17, 256, 256), (0, 1, 300, 256, 2704),      # forward  X W^T
-        (0, 0, 1000, 256, 256),                                                            # dX = dZ W
+        (0, 1, 1000, 256, 340), (0, 1, 4096 + 17, 256, 256), (0, 1, 300, 256, 2704), (0, 1, 128 * 150 + 5, 256, 352),  # X W^T
+        (0, 0, 1000, 256, 256), (0, 0, 77, 256, 64),                                       # dX = dZ W
         (1, 0, 256, 338, 5000), (1, 0, 256, 256, 4099), (1, 0, 256, 2704, 777),           # dW = dZ^T X
     ]
+    ran = 0
     for ta, tb, M, Nn, K in shapes:
+        if backend == 2 and ta:
+            continue
         A = rng.normal(0, 1, (K, M) if ta else (M, K)).astype(np.float32)
         B = rng.normal(0, 1, (Nn, K) if tb else (K, Nn)).astype(np.float32)
         C0 = rng.normal(0, 1, (M, Nn)).astype(np.float32)
         ref = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
         dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
-        for acc in (0, 1):
+        for acc in ((0,) if backend == 2 else (0, 1)):
             dC = torch.from_numpy(C0).cuda()
             _lib.check(lib.dcc_op_gemm(pol._h, backend, ta, tb, M, Nn, K, dA.data_ptr(), A.shape[1], dB.data_ptr(),
                                        B.shape[1], dC.data_ptr(), Nn, acc, None), "dcc_op_gemm")
             torch.cuda.synchronize()
             want = ref + (C0 if acc else 0)
             err = np.abs(dC.cpu().numpy() - want).max()
+            # fp32-level accuracy for both backends: |err| <~ eps_fp32 * sqrt(K) * |a||b| scale
             assert err <= 2e-6 * np.sqrt(K) * 4, (backend, ta, tb, M, Nn, K, acc, err)
+            ran += 1
+    assert ran >= 6
 
 
 def test_learner_end_to_end_small():
