@@ -161,6 +161,37 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     return DCC_OK;
 }
 
+// G[256, Nout] += dZ[R,256]^T X[R, Nout]  (tcgen05, MN-major operands; G must already hold the running sum)
+static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int ldz, const float *X, int ldx, float *G,
+                         int ldg, cudaStream_t s) {
+    if (R <= 0 || Nout <= 0) return DCC_OK;
+    if ((ldz & 3) || (ldx & 3) || ((uintptr_t)dZ & 15) || ((uintptr_t)X & 15)) return DCC_ERR_INVALID_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::TCF_SMEM_BYTES));
+        attr_set = true;
+    }
+    tc::TcwParams p;
+    memset(&p, 0, sizeof p);
+    p.dZ = dZ; p.X = X; p.G = G; p.R = R; p.Nout = Nout; p.ldz = ldz; p.ldx = ldx; p.ldg = ldg;
+    p.n_tiles = (Nout + tc::TC_N - 1) / tc::TC_N;
+    const int out_tiles = 2 * p.n_tiles;
+    // split the batch rows so that ~2 work items per SM exist, each at least 8 stages (256 rows) long
+    int ks = (2 * h->sm_count + out_tiles - 1) / out_tiles;
+    const int max_ks = (R + 255) / 256;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    p.rows_per_split = ((R + ks - 1) / ks + tc::TC_BK - 1) / tc::TC_BK * tc::TC_BK;
+    p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
+    const int work = out_tiles * p.ksplits;
+    const int grid = work < h->sm_count ? work : h->sm_count;
+    tc::tc_gemm_wgrad_kernel<<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
@@ -184,15 +215,23 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
     const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
     ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
     h->launches++;
-    int rc = h->backend == 2 ? tc_gemm_fwd(h, rows, L.inp, h->x0, L.inp, h->img_w1[net], h->a1, H, s)
-                             : launch_gemm(h, false, true, rows, H, L.in, h->x0, L.inp, w1g, L.in, h->a1, H, false, s);
+    int rc;
+    if (h->backend == 2) {
+        // tcgen05 GEMM with the block's bias + ReLU + LayerNorm fused into its epilogue (one kernel per MLP block)
+        rc = tc_gemm_fwd(h, rows, L.inp, h->x0, L.inp, h->img_w1[net], save ? h->a1 : nullptr, H, s, b1g, P + L.ln1_g,
+                         P + L.ln1_b, h->h1, save ? h->mean1 : nullptr, save ? h->rstd1 : nullptr);
+        if (rc) return rc;
+        rc = tc_gemm_fwd(h, rows, H, h->h1, H, h->img_w2[net], save ? h->a2 : nullptr, H, s, P + L.b2, P + L.ln2_g,
+                         P + L.ln2_b, h->h2, save ? h->mean2 : nullptr, save ? h->rstd2 : nullptr);
+        return rc;
+    }
+    rc = launch_gemm(h, false, true, rows, H, L.in, h->x0, L.inp, w1g, L.in, h->a1, H, false, s);
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a1, b1g, P + L.ln1_g, P + L.ln1_b,
                                                                             save ? h->a1 : nullptr, h->h1, h->mean1,
                                                                             h->rstd1, rows, H);
     h->launches++;
-    rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->h1, H, h->img_w2[net], h->a2, H, s)
-                         : launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
+    rc = launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a2, P + L.b2, P + L.ln2_g, P + L.ln2_b,
                                                                             save ? h->a2 : nullptr, h->h2, h->mean2,
@@ -211,7 +250,8 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dA, h->a2, h->mean2, h->rstd2, P + L.ln2_g, h->dA, G + L.ln2_g,
                                                G + L.ln2_b, G + L.b2, rows, H);   // dA := dz2
     h->launches++;
-    int rc = launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);          // dW2 += dz2^T h1
+    int rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, h->dA, H, h->h1, H, G + L.W2, H, s)     // dW2 += dz2^T h1
+                             : launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);
     if (rc) return rc;
     rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->dA, H, h->img_w2t[net], h->dB, H, s)                // dh1 = dz2 W2
                          : launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);
@@ -219,7 +259,8 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
                                                G + L.ln1_b, G + L.b1, rows, H);   // dB := dz1
     h->launches++;
-    rc = launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.inp, G + L.W1, L.in, true, s);    // G1 += dz1^T xhat
+    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, h->dB, H, h->x0, L.inp, G + L.W1, L.in, s)         // G1 += dz1^T xhat
+                         : launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.inp, G + L.W1, L.in, true, s);
     if (rc) return rc;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -553,6 +594,10 @@ int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, 
     if (backend == 0) backend = h->backend;
     if (backend == 2) {
         // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features)
+        if (ta && !tb && M == tc::TC_N) {   // dW = dZ^T X
+            if (!accumulate) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
+            return tc_gemm_wgrad(h, K, N, A, lda, B, ldb, C, ldc, s);
+        }
         if (ta || N != tc::TC_N || accumulate) return DCC_ERR_UNSUPPORTED;
         const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
         float *img = nullptr;

@@ -109,9 +109,15 @@ __device__ __forceinline__ void split_tf32(const float4 &x, float4 &hi, float4 &
 
 // Shared-memory matrix descriptor (sm_100 UMMA), SWIZZLE_128B: start address, leading / stride byte offsets in
 // 16-byte units, descriptor version 1, layout type 2 (bits 61-63).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                    uint64_t layout_type = 2) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+           (1ull << 46) | (layout_type << 61);
+}
+// MN-major operands of 32-bit types have ONE legal swizzled layout, SWIZZLE_128B_BASE32B (layout type 1): rows of
+// 128 B (32 features) per reduction index, atoms of 4 rows, the four 32-byte chunks of a row XOR-ed with (row & 3).
+__device__ __forceinline__ uint32_t mn32_offset(int group, int k, int chunk16, int rows_per_group) {
+    return (uint32_t)(group * rows_per_group * 128 + k * 128 + (((((chunk16 >> 1) ^ (k & 3)) << 1) | (chunk16 & 1)) << 4));
 }
 // Instruction descriptor, kind::tf32: D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9 / 10-12 = 2), majors (bit 15 / 16:
 // 0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -384,6 +390,214 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                     for (int r = 0; r < 32; ++r)
                         if (row0 + r < p.M) p.H[(size_t)(row0 + r) * p.ldc + col0 + lane] = fmaf(xp[r * 32 + (lane ^ r)], g, b);
                     __syncwarp();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- weight-gradient GEMM: G[256, Nout] += dZ[R, 256]^T X[R, Nout]  (reduction over the R batch rows) -----------
+//
+// Both operands are activations stored row-major [row][feature], i.e. MN-major for this product (the reduction index
+// is the slow one).  tcgen05 reads MN-major operands natively (instruction-descriptor major bits = 1) from the
+// canonical MN-major layout for 32-bit types (SWIZZLE_128B_BASE32B): per 32-feature group a block of [k rows][128 B],
+// 4-row atoms, 32-byte chunks XOR-ed with (k & 3); groups LBO apart.  A coalesced 128-byte global row segment is exactly one shared-memory
+// row, so the producers need no transpose.
+// A CTA owns a 128 (dZ features) x <=256 (X features) output tile and a contiguous range of batch rows; work items
+// that share a row range are adjacent in the grid so the second reader of a dZ / X tile hits L2.  Per 32-row stage the
+// accumulator chain is fresh and drained into fp32 registers (see tc_gemm_fwd_kernel); the CTA's partial tile is
+// added to G with red.global.add.f32 (coalesced through the per-warp transpose).
+struct TcwParams {
+    const float *dZ;     // [R, ldz], 256 features
+    const float *X;      // [R, ldx], Nout valid features (ldx % 4 == 0)
+    float *G;            // [256, ldg]
+    int R, Nout, ldz, ldx, ldg;
+    int n_tiles;         // ceil(Nout / 256); output tiles = 2 * n_tiles
+    int ksplits, rows_per_split;   // rows_per_split % 32 == 0
+};
+
+__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float *xpose = reinterpret_cast<float *>(smem + TCF_STAGES * TCF_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES);
+    uint64_t *full = bars, *empty = bars + TCF_STAGES, *tfull = bars + 2 * TCF_STAGES, *tempty = bars + 2 * TCF_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TCF_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int out_tiles = 2 * p.n_tiles;
+    const int num_work = out_tiles * p.ksplits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TCF_STAGES; ++s) {
+            mbar_init(&full[s], 4);       // 4 producer warps
+            mbar_init(&empty[s], 1);      // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // smem stage layout: A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB; every 32-feature group = 32 rows x 128 B
+    if (warp < 4) {
+        setmaxnreg_dec<80>();
+        const int t = threadIdx.x;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int ot = w % out_tiles, ks = w / out_tiles;
+            const int mh = ot & 1, n0 = (ot >> 1) * TC_N;
+            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);        // MMA N of this tile (multiple of 16)
+            const int ngroups = (nv + 31) >> 5;
+            const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
+            for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                uint8_t *st = smem + s * TCF_STAGE_BYTES;
+                mbar_wait(&empty[s], ph ^ 1);
+                // A: 32 rows x 128 dZ features = 1024 chunks, 8 per thread
+                float4 va[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
+                    va[i] = (r0 + k < r_end) ? __ldg(reinterpret_cast<const float4 *>(p.dZ + (size_t)(r0 + k) * p.ldz + mh * 128 + mc * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
+                    float4 hi, lo;
+                    split_tf32(va[i], hi, lo);
+                    const uint32_t off = mn32_offset(mc >> 3, k, mc & 7, TC_BK);
+                    *reinterpret_cast<float4 *>(st + off) = hi;
+                    *reinterpret_cast<float4 *>(st + TC_A_TILE_FLOATS * 4 + off) = lo;
+                }
+                // B: 32 rows x (ngroups * 32) X features, in two halves of 8 chunks per thread
+                uint8_t *sb = st + 2 * TC_A_TILE_FLOATS * 4;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 vb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * (hb * 8 + i), k = ci >> 6, nc = ci & 63;
+                        const int col = n0 + nc * 4;
+                        vb[i] = ((nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout)
+                                    ? __ldg(reinterpret_cast<const float4 *>(p.X + (size_t)(r0 + k) * p.ldx + col))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * (hb * 8 + i), k = ci >> 6, nc = ci & 63;
+                        if ((nc >> 3) < ngroups) {
+                            float4 hi, lo;
+                            split_tf32(vb[i], hi, lo);
+                            const uint32_t off = mn32_offset(nc >> 3, k, nc & 7, TC_BK);
+                            *reinterpret_cast<float4 *>(sb + off) = hi;
+                            *reinterpret_cast<float4 *>(sb + TC_B_TILE_FLOATS * 4 + off) = lo;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp >= 12) {
+        setmaxnreg_dec<32>();
+        if (warp == 12 && lane == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const int ot = w % out_tiles, ks = w / out_tiles;
+                const int n0 = (ot >> 1) * TC_N;
+                const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+                const uint32_t idesc = make_idesc_tf32(TC_BM, nv, 1, 1);
+                const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
+                for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
+                    const int s = it & 1;
+                    const uint32_t ph = (it >> 1) & 1;
+                    mbar_wait(&tempty[s], ph ^ 1);
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + s * TC_N;
+                    const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
+                    // MN-major: LBO = distance between 32-feature groups (4096 B), SBO = between 4-row atoms (512 B)
+                    const uint64_t a_hi = make_desc_sw128(sa, 4096, 512, 1);
+                    const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, 4096, 512, 1);
+                    const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, 4096, 512, 1);
+                    const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, 4096, 512, 1);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 1024) >> 4);   // next 8 reduction rows (two 4-row atoms)
+                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+                        tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                        tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    tc_commit(&empty[s]);
+                    tc_commit(&tfull[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        setmaxnreg_inc<200>();
+        const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
+        float *xp = xpose + ew * (32 * 32);
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int ot = w % out_tiles, ks = w / out_tiles;
+            const int mh = ot & 1, n0 = (ot >> 1) * TC_N;
+            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+            const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
+            float acc[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+            for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&tfull[s], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (half * 128 + j * 32 < nv) {      // warp-uniform: columns the MMA actually wrote
+                        float v[32];
+                        tmem_ld32(tmem_base + s * TC_N + half * 128 + j * 32 + lane_bits, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[s]);
+            }
+            if (r_beg < r_end) {
+                const int m_base = mh * 128 + q * 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col0 = n0 + half * 128 + j * 32;
+                    if (half * 128 + j * 32 < nv) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = acc[j * 32 + i];
+                        __syncwarp();
+                        if (col0 + lane < p.Nout) {
+#pragma unroll 4
+                            for (int r = 0; r < 32; ++r)
+                                red_add_f32(p.G + (size_t)(m_base + r) * p.ldg + col0 + lane, xp[r * 32 + (lane ^ r)]);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
         }
