@@ -19,8 +19,39 @@
 namespace dcc {
 namespace tc {
 
+// ---- optional in-kernel role timing (tools/tc_bench.cu builds with -DDCC_TC_PROFILE; off in the library) ----------
+#ifdef DCC_TC_PROFILE
+__device__ unsigned long long g_tc_prof[32];
+#define TC_PROF_DECL(...) unsigned long long __VA_ARGS__
+#define TC_PROF_NOW(t) t = clock64()
+#define TC_PROF_ADD(acc, t0, t1) acc += (t1) - (t0)
+#define TC_PROF_OUT(cond, idx, val) do { if ((cond) && blockIdx.x == 0) g_tc_prof[idx] = (val); } while (0)
+#else
+#define TC_PROF_DECL(...)
+#define TC_PROF_NOW(t)
+#define TC_PROF_ADD(acc, t0, t1)
+#define TC_PROF_OUT(cond, idx, val)
+#endif
+
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// explicit shared-space accesses: the stage pointers are derived by integer alignment of the dynamic shared-memory
+// base, which makes the compiler fall back to generic LD/ST (slow address-space resolution) unless told otherwise
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -97,11 +128,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa: what cvt.rna.tf32.f32 computes for finite inputs, without
+// the NaN/Inf special-casing its lowering carries (activations and weights here are finite)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(const float4 &x, float4 &hi, float4 &lo) {
     hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
     lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
@@ -188,10 +217,14 @@ struct TcfParams {
     const float *bias, *gamma, *beta;
     float *H;            // [M, ldc]
     float *mean, *rstd;  // [M] (may be NULL)
+    int dbg;             // tools/tc_bench only: 1 = skip the global stores of the epilogue
 };
 
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -232,60 +265,95 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
 
     if (warp < 4) {
         // ===== producers =====
-        setmaxnreg_dec<80>();
+        setmaxnreg_dec<96>();
         const int t = threadIdx.x;            // 0..127
         const int c = t & 7, rsub = t >> 3;   // 16-byte chunk within the 128-byte row; row within a 16-row group
         uint32_t it = 0;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int m0 = (w / p.splits) * TC_BM;
-            const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
-            for (int kt = kt0; kt < kt1; ++kt, ++it) {
-                const int s = it % TCF_STAGES;
-                const uint32_t ph = (it / TCF_STAGES) & 1;
-                uint8_t *st = smem + s * TCF_STAGE_BYTES;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (t == 0) {
-                    mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
-                    const float *src = p.Bimg + (size_t)kt * (2 * TC_B_TILE_FLOATS);
-                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
-                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
-                                  TC_B_TILE_FLOATS * 4, &full[s]);
-                }
-                const int kcol = kt * TC_BK + c * 4;
-                float4 v[8];
+        TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, p_wait = 0, p_work = 0);
+        // The global loads of stage i+1 are issued before stage i is split and stored, so their latency overlaps the
+        // wait for the shared-memory slot and the split of the previous stage (registers: two 8 x float4 sets).
+        int w = blockIdx.x, kt = 0, kt1 = 0;
+        auto set_work = [&](int ww) {
+            kt = (ww % p.splits) * p.kt_per_split;
+            kt1 = min(p.KT, kt + p.kt_per_split);
+        };
+        auto load_stage = [&](int ww, int kk, float4 (&v)[8]) {
+            const int m0 = (ww / p.splits) * TC_BM, kcol = kk * TC_BK + c * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = m0 + i * 16 + rsub;
-                    v[i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.A + (size_t)row * p.lda + kcol))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 16 + rsub;
-                    float4 hi, lo;
-                    split_tf32(v[i], hi, lo);
-                    const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4 *>(st + off) = hi;
-                    *reinterpret_cast<float4 *>(st + TC_A_TILE_FLOATS * 4 + off) = lo;
-                }
-                fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+            for (int i = 0; i < 8; ++i) {
+                const int row = m0 + i * 16 + rsub;
+                v[i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.A + (size_t)row * p.lda + kcol))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        float4 vn[8];
+        if (w < num_work) {
+            set_work(w);
+            load_stage(w, kt, vn);
         }
+        while (w < num_work) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = vn[i];
+            const int kt_cur = kt;
+            // advance to the next stage of this CTA and start its loads
+            if (++kt >= kt1) {
+                w += gridDim.x;
+                if (w < num_work) set_work(w);
+            }
+            if (w < num_work) load_stage(w, kt, vn);
+            const int s = it % TCF_STAGES;
+            const uint32_t ph = (it / TCF_STAGES) & 1;
+            uint8_t *st = smem + s * TCF_STAGE_BYTES;
+            const uint32_t st_u32 = smem_u32(st);
+            TC_PROF_NOW(t0);
+            mbar_wait(&empty[s], ph ^ 1);
+            TC_PROF_NOW(t1);
+            if (t == 0) {
+                mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
+                const float *src = p.Bimg + (size_t)kt_cur * (2 * TC_B_TILE_FLOATS);
+                bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
+                bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
+                              TC_B_TILE_FLOATS * 4, &full[s]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 16 + rsub;
+                float4 hi, lo;
+                split_tf32(v[i], hi, lo);
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                sts128(st_u32 + off, hi);
+                sts128(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+            }
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            TC_PROF_NOW(t2);
+            TC_PROF_ADD(p_wait, t0, t1);
+            TC_PROF_ADD(p_work, t1, t2);
+            ++it;
+        }
+        TC_PROF_OUT(t == 0, 0, p_wait);
+        TC_PROF_OUT(t == 0, 1, p_work);
+        TC_PROF_OUT(t == 0, 2, (unsigned long long)it);
     } else if (warp >= 12) {
         // ===== MMA issuer: one thread of warp 12 =====
         setmaxnreg_dec<32>();
         if (warp == 12 && lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_N, 0, 0);
             uint32_t it = 0;
+            TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
+            TC_PROF_NOW(m_begin);
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
                 for (int kt = kt0; kt < kt1; ++kt, ++it) {
                     const int s = it & 1;              // smem stage and TMEM accumulator advance together
                     const uint32_t ph = (it >> 1) & 1;
+                    TC_PROF_NOW(t0);
                     mbar_wait(&tempty[s], ph ^ 1);     // accumulator drained by the epilogue warps
+                    TC_PROF_NOW(t1);
                     mbar_wait(&full[s], ph);           // operands landed
+                    TC_PROF_NOW(t2);
                     tc_fence_after();
                     const uint32_t d = tmem_base + s * TC_N;
                     const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
@@ -302,19 +370,29 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                     }
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
                     tc_commit(&tfull[s]);      // accumulator ready to drain
+                    TC_PROF_NOW(t3);
+                    TC_PROF_ADD(m_wacc, t0, t1);
+                    TC_PROF_ADD(m_wfull, t1, t2);
+                    TC_PROF_ADD(m_issue, t2, t3);
                 }
             }
+            TC_PROF_OUT(true, 4, m_wacc);
+            TC_PROF_OUT(true, 5, m_wfull);
+            TC_PROF_OUT(true, 6, m_issue);
+            TC_PROF_OUT(true, 7, t3 - m_begin);
         }
         __syncwarp();
     } else {
         // ===== accumulate / epilogue warps 4-11 =====
-        setmaxnreg_inc<200>();
+        setmaxnreg_inc<192>();
         const int q = warp & 3;                 // TMEM lane quarter
         const int half = (warp - 4) >> 2;       // column half: 0 -> 0..127, 1 -> 128..255
         const int ew = warp - 4;
-        float *xp = xpose + ew * (32 * 32);
+        const uint32_t xp_u32 = smem_u32(xpose + ew * (32 * 32));
+        const uint32_t rs_u32 = smem_u32(rowstat);
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
+        TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, e_wait = 0, e_drain = 0, e_tile = 0);
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
             float acc[128];
@@ -323,7 +401,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
             for (int kt = kt0; kt < kt1; ++kt, ++it) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
+                TC_PROF_NOW(t0);
                 mbar_wait(&tfull[s], ph);
+                TC_PROF_NOW(t1);
                 tc_fence_after();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -335,7 +415,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[s]);
+                TC_PROF_NOW(t2);
+                TC_PROF_ADD(e_wait, t0, t1);
+                TC_PROF_ADD(e_drain, t1, t2);
             }
+            TC_PROF_NOW(t0);
             // ---- tile epilogue from registers: thread = row (q*32 + lane), 128 columns [half*128, +128) ----
             const int row0 = (w / p.splits) * TC_BM + q * 32;
             const int rl = q * 32 + lane;
@@ -343,56 +427,76 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
             if (p.epi == TCF_EPI_BIAS_RELU_LN) {
                 float sum = 0.f;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    acc[i] = fmaxf(acc[i] + __ldg(p.bias + half * 128 + i), 0.f);
-                    sum += acc[i];
+                for (int c4 = 0; c4 < 32; ++c4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                    acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
+                    acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
+                    acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
+                    acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
+                    sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
                 }
-                rowstat[half * 128 + rl] = sum;
+                sts32(rs_u32 + (half * 128 + rl) * 4, sum);
                 named_bar_sync(1, 256);
-                mean = (rowstat[rl] + rowstat[128 + rl]) * (1.f / TC_N);
+                mean = (lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4)) * (1.f / TC_N);
                 named_bar_sync(1, 256);
                 float sq = 0.f;
 #pragma unroll
                 for (int i = 0; i < 128; ++i) { const float d = acc[i] - mean; sq = fmaf(d, d, sq); }
-                rowstat[half * 128 + rl] = sq;
+                sts32(rs_u32 + (half * 128 + rl) * 4, sq);
                 named_bar_sync(1, 256);
-                rstd = rsqrtf((rowstat[rl] + rowstat[128 + rl]) * (1.f / TC_N) + 1e-5f);
+                rstd = rsqrtf((lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4)) * (1.f / TC_N) + 1e-5f);
                 named_bar_sync(1, 256);
                 if (half == 0 && row0 + lane < p.M) {
                     if (p.mean) p.mean[row0 + lane] = mean;
                     if (p.rstd) p.rstd[row0 + lane] = rstd;
                 }
             }
-            // stores through a per-warp 32x32 transpose so that every instruction writes whole 128-byte lines
+            // Stores: a thread holds 128 columns of ONE row, so a direct store would scatter 16-byte pieces over 32 rows.
+            // Rows are staged 8 at a time through the warp's 4 KB buffer (16-byte chunks XOR-ed with the row: conflict
+            // free both ways) and leave as whole 512-byte row segments, one STG.128 per row per warp.
+            const int colw = half * 128 + lane * 4;     // this lane's 4 columns on the way out
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+            if (p.epi == TCF_EPI_BIAS_RELU_LN) {
+                g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + colw));
+                b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + colw));
+            }
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                const int rr = lane & 7;
+                if ((lane >> 3) == g) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int col0 = half * 128 + j * 32;
-                if (p.epi == TCF_EPI_STORE || p.C) {
+                    for (int c = 0; c < 32; ++c)
+                        sts128(xp_u32 + ((rr * 32 + (c ^ rr)) << 4), make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]));
+                }
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = acc[j * 32 + i];
-                    __syncwarp();
-#pragma unroll 4
-                    for (int r = 0; r < 32; ++r) {
-                        if (row0 + r < p.M) {
-                            float *dst = p.C + (size_t)(row0 + r) * p.ldc + col0 + lane;
-                            if (p.splits > 1) red_add_f32(dst, xp[r * 32 + (lane ^ r)]);
-                            else *dst = xp[r * 32 + (lane ^ r)];
+                for (int r = 0; r < 8; ++r) {
+                    const int row = row0 + g * 8 + r;
+                    if (row < p.M && !(p.dbg & 1)) {
+                        const float4 v = lds128(xp_u32 + ((r * 32 + (lane ^ r)) << 4));
+                        if (p.epi == TCF_EPI_STORE) {
+                            float *dst = p.C + (size_t)row * p.ldc + colw;
+                            if (p.splits > 1) red_add_v4(dst, v.x, v.y, v.z, v.w);
+                            else *reinterpret_cast<float4 *>(dst) = v;
+                        } else {
+                            if (p.C) *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + colw) = v;
+                            // the row statistics of the 8 staged rows sit in lanes g*8 + r
+                            const float mr = __shfl_sync(0xffffffffu, mean, g * 8 + r), rs = __shfl_sync(0xffffffffu, rstd, g * 8 + r);
+                            float4 hv;
+                            hv.x = fmaf((v.x - mr) * rs, g4.x, b4.x); hv.y = fmaf((v.y - mr) * rs, g4.y, b4.y);
+                            hv.z = fmaf((v.z - mr) * rs, g4.z, b4.z); hv.w = fmaf((v.w - mr) * rs, g4.w, b4.w);
+                            *reinterpret_cast<float4 *>(p.H + (size_t)row * p.ldc + colw) = hv;
                         }
                     }
-                    __syncwarp();
                 }
-                if (p.epi == TCF_EPI_BIAS_RELU_LN) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = (acc[j * 32 + i] - mean) * rstd;
-                    __syncwarp();
-                    const float g = __ldg(p.gamma + col0 + lane), b = __ldg(p.beta + col0 + lane);
-#pragma unroll 4
-                    for (int r = 0; r < 32; ++r)
-                        if (row0 + r < p.M) p.H[(size_t)(row0 + r) * p.ldc + col0 + lane] = fmaf(xp[r * 32 + (lane ^ r)], g, b);
-                    __syncwarp();
-                }
+                __syncwarp();
             }
+            TC_PROF_NOW(t1);
+            TC_PROF_ADD(e_tile, t0, t1);
         }
+        TC_PROF_OUT(threadIdx.x == 128, 8, e_wait);
+        TC_PROF_OUT(threadIdx.x == 128, 9, e_drain);
+        TC_PROF_OUT(threadIdx.x == 128, 10, e_tile);
     }
     tc_fence_before();
     __syncthreads();
@@ -481,8 +585,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     float4 hi, lo;
                     split_tf32(va[i], hi, lo);
                     const uint32_t off = mn32_offset(mc >> 3, k, mc & 7, TC_BK);
-                    *reinterpret_cast<float4 *>(st + off) = hi;
-                    *reinterpret_cast<float4 *>(st + TC_A_TILE_FLOATS * 4 + off) = lo;
+                    sts128(smem_u32(st) + off, hi);
+                    sts128(smem_u32(st) + TC_A_TILE_FLOATS * 4 + off, lo);
                 }
                 // B: 32 rows x (ngroups * 32) X features, in two halves of 8 chunks per thread
                 uint8_t *sb = st + 2 * TC_A_TILE_FLOATS * 4;
@@ -504,8 +608,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                             float4 hi, lo;
                             split_tf32(vb[i], hi, lo);
                             const uint32_t off = mn32_offset(nc >> 3, k, nc & 7, TC_BK);
-                            *reinterpret_cast<float4 *>(sb + off) = hi;
-                            *reinterpret_cast<float4 *>(sb + TC_B_TILE_FLOATS * 4 + off) = lo;
+                            sts128(smem_u32(sb) + off, hi);
+                            sts128(smem_u32(sb) + TC_B_TILE_FLOATS * 4 + off, lo);
                         }
                     }
                 }
@@ -553,7 +657,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
     } else {
         setmaxnreg_inc<200>();
         const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
-        float *xp = xpose + ew * (32 * 32);
+        const uint32_t xp_u32 = smem_u32(xpose + ew * (32 * 32));
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -589,12 +693,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     const int col0 = n0 + half * 128 + j * 32;
                     if (half * 128 + j * 32 < nv) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) xp[lane * 32 + (i ^ lane)] = acc[j * 32 + i];
+                        for (int i = 0; i < 32; ++i) sts32(xp_u32 + ((lane * 32 + (i ^ lane)) << 2), acc[j * 32 + i]);
                         __syncwarp();
                         if (col0 + lane < p.Nout) {
 #pragma unroll 4
                             for (int r = 0; r < 32; ++r)
-                                red_add_f32(p.G + (size_t)(m_base + r) * p.ldg + col0 + lane, xp[r * 32 + (lane ^ r)]);
+                                red_add_f32(p.G + (size_t)(m_base + r) * p.ldg + col0 + lane, lds32(xp_u32 + ((r * 32 + (lane ^ r)) << 2)));
                         }
                         __syncwarp();
                     }

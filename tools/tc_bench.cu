@@ -1,0 +1,52 @@
+// tools/tc_bench.cu — standalone timing + in-kernel role profile of the tcgen05 GEMM kernels (tuning aid, not product).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DDCC_TC_PROFILE -I include \
+//        -I dynamic-coverage-control_b200/csrc -o tools/tc_bench.bin tools/tc_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "dcc_tc.cuh"
+namespace dcc { void set_last_cuda_error(cudaError_t, const char *, const char *, int) {} }
+using namespace dcc::tc;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+int main(int argc, char **argv) {
+    const int M = argc > 1 ? atoi(argv[1]) : 198408, K = argc > 2 ? atoi(argv[2]) : 352, epi = argc > 3 ? atoi(argv[3]) : 1;
+    const int KT = (K + 31) / 32;
+    float *A, *W, *img, *C, *H, *bias, *mean, *rstd;
+    CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&W, (size_t)256 * K * 4));
+    CK(cudaMalloc(&img, (size_t)KT * 2 * TC_B_TILE_FLOATS * 4));
+    CK(cudaMalloc(&C, (size_t)M * 256 * 4)); CK(cudaMalloc(&H, (size_t)M * 256 * 4));
+    CK(cudaMalloc(&bias, 3 * 256 * 4)); CK(cudaMalloc(&mean, (size_t)M * 4)); CK(cudaMalloc(&rstd, (size_t)M * 4));
+    std::vector<float> h((size_t)M * K);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = (float)((i * 2654435761u) % 2001) / 1000.f - 1.f;
+    CK(cudaMemcpy(A, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(W, h.data(), (size_t)256 * K * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(bias, 0, 3 * 256 * 4));
+    tc_prep_weights_kernel<<<(KT * 256 * 8 + 255) / 256, 256>>>(W, K, 0, K, KT, img);
+    CK(cudaFuncSetAttribute(tc_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    TcfParams p; memset(&p, 0, sizeof p);
+    p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = KT; p.lda = K; p.ldc = 256; p.splits = 1; p.kt_per_split = KT;
+    p.epi = epi; p.dbg = argc > 4 ? atoi(argv[4]) : 0; p.bias = bias; p.gamma = bias + 256; p.beta = bias + 512; p.H = H; p.mean = mean; p.rstd = rstd;
+    const int tiles = (M + 127) / 128, grid = tiles < 148 ? tiles : 148;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) tc_gemm_fwd_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    const int reps = 10;
+    for (int i = 0; i < reps; ++i) tc_gemm_fwd_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    const double flop = 2.0 * M * 256.0 * (KT * 32.0);
+    printf("fwd M=%d K=%d epi=%d: %.1f us  %.1f TFLOP/s fp32-equivalent (x3 = %.0f TF tf32 MMA)\n", M, K, epi, ms * 1e3,
+           flop / ms * 1e-9, 3 * flop / ms * 1e-9);
+    unsigned long long prof[32];
+    CK(cudaMemcpyFromSymbol(prof, g_tc_prof, sizeof prof));
+    const double st = (double)prof[2];
+    printf("CTA0: %llu stages | producer: wait_empty %.0f work %.0f cyc/stage | mma: wait_acc %.0f wait_full %.0f issue %.0f, total %.0f cyc/stage\n",
+           prof[2], prof[0] / st, prof[1] / st, prof[4] / st, prof[5] / st, prof[6] / st, prof[7] / st);
+    const double tl = st / KT;
+    printf("      epilogue warp 4: wait_tfull %.0f drain %.0f cyc/stage, tile epilogue %.0f cyc/tile (%.1f tiles)\n", prof[8] / st,
+           prof[9] / st, prof[10] / tl, tl);
+    return 0;
+}
