@@ -557,65 +557,99 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
 
     // smem stage layout: A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB; every 32-feature group = 32 rows x 128 B
     if (warp < 4) {
-        setmaxnreg_dec<80>();
+        setmaxnreg_dec<96>();
         const int t = threadIdx.x;
-        uint32_t it = 0;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int ot = w % out_tiles, ks = w / out_tiles;
-            const int mh = ot & 1, n0 = (ot >> 1) * TC_N;
-            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);        // MMA N of this tile (multiple of 16)
-            const int ngroups = (nv + 31) >> 5;
-            const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
-            for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                uint8_t *st = smem + s * TCF_STAGE_BYTES;
-                mbar_wait(&empty[s], ph ^ 1);
-                // A: 32 rows x 128 dZ features = 1024 chunks, 8 per thread
-                float4 va[8];
+        // Work is cut into load units of 8 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
+        // (B).  The loads of unit u+1 are issued before unit u is split and stored, so their latency overlaps the
+        // split / store work and the wait for the shared-memory slot.
+        int w = blockIdx.x, r0 = 0, r_end = 0, mh = 0, n0 = 0, ngroups = 0;
+        auto set_work = [&](int ww) {
+            const int ot = ww % out_tiles, ks = ww / out_tiles;
+            mh = ot & 1; n0 = (ot >> 1) * TC_N;
+            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+            ngroups = (nv + 31) >> 5;
+            r0 = ks * p.rows_per_split; r_end = min(p.R, r0 + p.rows_per_split);
+        };
+        auto load_unit = [&](int kind, float4 (&v)[8]) {
+            if (kind == 0) {       // dZ: 32 rows x 128 features = 1024 chunks
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
-                    va[i] = (r0 + k < r_end) ? __ldg(reinterpret_cast<const float4 *>(p.dZ + (size_t)(r0 + k) * p.ldz + mh * 128 + mc * 4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (r0 + k < r_end) ? __ldg(reinterpret_cast<const float4 *>(p.dZ + (size_t)(r0 + k) * p.ldz + mh * 128 + mc * 4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            } else {               // X: 32 rows x 256 features = 2048 chunks, two units
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * ((kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
+                    const int col = n0 + nc * 4;
+                    v[i] = ((nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout)
+                               ? __ldg(reinterpret_cast<const float4 *>(p.X + (size_t)(r0 + k) * p.ldx + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        // skip empty work items (a split whose row range is empty)
+        auto next_nonempty = [&]() {
+            while (w < num_work) {
+                set_work(w);
+                if (r0 < r_end) return;
+                w += gridDim.x;
+            }
+        };
+        float4 vn[8];
+        next_nonempty();
+        int kind = 0;
+        if (w < num_work) load_unit(0, vn);
+        uint32_t it = 0;
+        while (w < num_work) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = vn[i];
+            const int cur_kind = kind, cur_ngroups = ngroups;
+            // advance to the next unit and start its loads
+            if (++kind == 3) {
+                kind = 0;
+                r0 += TC_BK;
+                if (r0 >= r_end) {
+                    w += gridDim.x;
+                    next_nonempty();
+                }
+            }
+            if (w < num_work) load_unit(kind, vn);
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const uint32_t st_u32 = smem_u32(smem + s * TCF_STAGE_BYTES);
+            if (cur_kind == 0) {
+                mbar_wait(&empty[s], ph ^ 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
                     float4 hi, lo;
-                    split_tf32(va[i], hi, lo);
+                    split_tf32(v[i], hi, lo);
                     const uint32_t off = mn32_offset(mc >> 3, k, mc & 7, TC_BK);
-                    sts128(smem_u32(st) + off, hi);
-                    sts128(smem_u32(st) + TC_A_TILE_FLOATS * 4 + off, lo);
+                    sts128(st_u32 + off, hi);
+                    sts128(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
                 }
-                // B: 32 rows x (ngroups * 32) X features, in two halves of 8 chunks per thread
-                uint8_t *sb = st + 2 * TC_A_TILE_FLOATS * 4;
+            } else {
+                const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    float4 vb[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ci = t + 128 * (hb * 8 + i), k = ci >> 6, nc = ci & 63;
-                        const int col = n0 + nc * 4;
-                        vb[i] = ((nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout)
-                                    ? __ldg(reinterpret_cast<const float4 *>(p.X + (size_t)(r0 + k) * p.ldx + col))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ci = t + 128 * (hb * 8 + i), k = ci >> 6, nc = ci & 63;
-                        if ((nc >> 3) < ngroups) {
-                            float4 hi, lo;
-                            split_tf32(vb[i], hi, lo);
-                            const uint32_t off = mn32_offset(nc >> 3, k, nc & 7, TC_BK);
-                            sts128(smem_u32(sb) + off, hi);
-                            sts128(smem_u32(sb) + TC_B_TILE_FLOATS * 4 + off, lo);
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * ((cur_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
+                    if ((nc >> 3) < cur_ngroups) {
+                        float4 hi, lo;
+                        split_tf32(v[i], hi, lo);
+                        const uint32_t off = mn32_offset(nc >> 3, k, nc & 7, TC_BK);
+                        sts128(sb_u32 + off, hi);
+                        sts128(sb_u32 + TC_B_TILE_FLOATS * 4 + off, lo);
                     }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+                if (cur_kind == 2) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                    ++it;
+                }
             }
         }
     } else if (warp >= 12) {
@@ -655,7 +689,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         }
         __syncwarp();
     } else {
-        setmaxnreg_inc<200>();
+        setmaxnreg_inc<192>();
         const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
         const uint32_t xp_u32 = smem_u32(xpose + ew * (32 * 32));
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
