@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic around the learner kernels: config loading (the reference's YAMLs drive the build
+unchanged), parameter layout / checkpoint key names, env sharding and the torch.distributed plumbing (gloo,
+world_size 2) including the global-normalisation contract of the sharded PPO gradient."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/uav_dcc_control/config"
+
+
+def test_yaml_float_resolver_and_merge_order(tmp_path):
+    from dcc_b200.utils.config import load_config
+    (tmp_path / "env_config").mkdir()
+    (tmp_path / "algo_config").mkdir()
+    (tmp_path / "env_config" / "dcc.yaml").write_text("num_agents: 8\nppo_epoch: 15\nn_eval_rollout_threads: 16\n")
+    (tmp_path / "algo_config" / "mappo.yaml").write_text("actor_lr: 5e-4\nopti_eps: 1e-5\nn_eval_rollout_threads: 1\nsave_gifs: false\n")
+    (tmp_path / "expt.yaml").write_text("save_gifs: True\nload_buffer_path: None\nseed: 3\n")
+    cfg = load_config(str(tmp_path))
+    assert isinstance(cfg.actor_lr, float) and cfg.actor_lr == 5e-4 and cfg.opti_eps == 1e-5   # PyYAML alone gives str
+    assert cfg.n_eval_rollout_threads == 1 and cfg.save_gifs is True                              # later file wins
+    assert cfg.num_agents == 8 and cfg.seed == 3 and cfg.load_buffer_path is None
+    assert cfg.critic_lr == 5e-4 and cfg.gamma == 0.99                                            # defaults fill the rest
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference not mounted")
+def test_defaults_equal_the_shipped_yaml_files():
+    from dcc_b200.utils.config import DEFAULTS, load_config
+    ref = vars(load_config(REF_CFG))
+    new_keys = {"reference_compat", "pos_pois_path", "device", "chunk_rows", "gemm_backend"}
+    for k, v in DEFAULTS.items():
+        if k in new_keys:
+            continue
+        assert ref[k] == v, (k, ref[k], v)
+    assert set(ref) - new_keys == set(DEFAULTS) - new_keys
+
+
+def test_unsupported_branches_fail_loudly():
+    from dcc_b200.utils.config import check_supported, load_config
+    check_supported(load_config(None))
+    for key, val in (("use_recurrent_policy", True), ("use_popart", True), ("num_mini_batch", 2), ("use_valuenorm", False),
+                     ("layer_N", 2), ("use_huber_loss", False)):
+        cfg = load_config(None)
+        setattr(cfg, key, val)
+        with pytest.raises(NotImplementedError):
+            check_supported(cfg)
+
+
+def test_net_layout_matches_reference_parameter_counts():
+    from dcc_b200.algos.mappo import FC_H, TRUNK, net_layout
+    lay, n = net_layout(110, 256, 2, "act.action_out.fc_mean", logstd=True)
+    fc_h = 256 * 256 + 256 + 256 + 256
+    assert n + fc_h == 162272                       # R_Actor at 4 UAV / 20 PoI
+    layc, nc = net_layout(440, 256, 1, "v_out")
+    assert nc + fc_h == 247153
+    assert net_layout(338, 256, 2, "act.action_out.fc_mean", True)[1] + fc_h == 221096
+    assert net_layout(2704, 256, 1, "v_out")[1] + fc_h == 831265
+    assert list(lay)[:10] == list(TRUNK) and list(lay)[-1] == "act.action_out.logstd._bias" and len(FC_H) == 4
+    off = 0
+    for k, (o, shp) in lay.items():
+        assert o == off
+        off += int(np.prod(shp))
+    assert off == n
+
+
+def test_shard_envs_partitions_the_env_axis():
+    from dcc_b200.parallel import shard_envs
+    for total, world in ((524288, 8), (65536, 1), (10, 3), (7, 8)):
+        spans = [shard_envs(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from dcc_b200.parallel import init_from_env, shard_envs
+    from oracle import mappo_oracle as mo
+    comm = init_from_env(backend="gloo")
+    assert (comm.world, comm.rank) == (world, rank)
+    # the sharded-gradient contract of dcc_mappo_epoch_grads: each rank sums per-row gradients of ITS env shard
+    # already divided by the GLOBAL row count; a SUM all-reduce then equals the single-process big-batch gradient.
+    rng = np.random.default_rng(0)
+    E, T, D, H = 6, 5, 7, 8
+    x = rng.normal(size=(T, E, D)); dv = rng.normal(size=(T, E, 1))
+    p = {"base.feature_norm.weight": np.ones(D) + 0.1 * rng.normal(size=D), "base.feature_norm.bias": 0.1 * rng.normal(size=D),
+         "base.mlp.fc1.0.weight": rng.normal(size=(H, D)), "base.mlp.fc1.0.bias": rng.normal(size=H),
+         "base.mlp.fc1.2.weight": np.ones(H), "base.mlp.fc1.2.bias": np.zeros(H),
+         "base.mlp.fc2.0.0.weight": rng.normal(size=(H, H)), "base.mlp.fc2.0.0.bias": rng.normal(size=H),
+         "base.mlp.fc2.0.2.weight": np.ones(H), "base.mlp.fc2.0.2.bias": np.zeros(H),
+         "v_out.weight": rng.normal(size=(1, H)), "v_out.bias": np.zeros(1)}
+    net = mo.make_critic(p)
+    net.forward(x.reshape(T * E, D))
+    full = net.backward(dv.reshape(T * E, 1) / (T * E))
+    lo, hi = shard_envs(E, world, rank)
+    net.forward(x[:, lo:hi].reshape(-1, D))
+    part = net.backward(dv[:, lo:hi].reshape(-1, 1) / (T * E))          # divided by the GLOBAL count
+    flat = torch.from_numpy(np.concatenate([part[k].reshape(-1) for k in p]))
+    comm.all_reduce_sum_(flat)
+    ref = np.concatenate([full[k].reshape(-1) for k in p])
+    ok = bool(np.allclose(flat.numpy(), ref, rtol=1e-10, atol=1e-12)) and comm.calls == 1
+    t = torch.tensor([float(rank + 1)])
+    comm.broadcast_(t, src=0)
+    ok = ok and float(t) == 1.0
+    comm.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_gradient_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+def test_comm_is_a_noop_without_a_process_group():
+    import torch
+    from dcc_b200.parallel import Comm
+    c = Comm()
+    t = torch.ones(3)
+    assert (c.world, c.rank) == (1, 0) and c.all_reduce_sum_(t) is t and c.calls == 0

@@ -40,12 +40,12 @@ def make_cfg(c, E, T, **over):
     return cfg
 
 
-def build(c, E, T, **over):
+def build(c, E, T, device=0, **over):
     import torch
     from dcc_b200.algos import MAPPOPolicy, MAPPOTrainer
     from dcc_b200.buffer import SharedReplayBuffer
     from dcc_b200.envs.spaces import Box
-    cfg = make_cfg(c, E, T, **over)
+    cfg = make_cfg(c, E, T, device=device, **over)
     N, D = c["n_agents"], c["obs_dim"]
     obs_space, share_space, act_space = Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,))
     pol = MAPPOPolicy(cfg, obs_space, share_space, act_space)
