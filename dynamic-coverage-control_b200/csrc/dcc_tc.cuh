@@ -53,6 +53,14 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
     return v;
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -560,8 +568,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         setmaxnreg_dec<96>();
         const int t = threadIdx.x;
         // Work is cut into load units of 8 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
-        // (B).  The loads of unit u+1 are issued before unit u is split and stored, so their latency overlaps the
-        // split / store work and the wait for the shared-memory slot.
+        // (B).  Raw units are fetched with 16-byte cp.async (LDGSTS) into a 2-slot ring in shared memory two units
+        // ahead of their use, so the global-load latency (~1 us) overlaps the split / store work of two units and the
+        // wait for the stage slot; each thread reads back only the chunks it fetched itself (no barrier needed).
+        const uint32_t ring_u32 = smem_u32(xpose);     // 2 slots x 16 KB (the epilogue of this kernel uses no staging)
         int w = blockIdx.x, r0 = 0, r_end = 0, mh = 0, n0 = 0, ngroups = 0;
         auto set_work = [&](int ww) {
             const int ot = ww % out_tiles, ks = ww / out_tiles;
@@ -570,26 +580,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             ngroups = (nv + 31) >> 5;
             r0 = ks * p.rows_per_split; r_end = min(p.R, r0 + p.rows_per_split);
         };
-        auto load_unit = [&](int kind, float4 (&v)[8]) {
-            if (kind == 0) {       // dZ: 32 rows x 128 features = 1024 chunks
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
-                    v[i] = (r0 + k < r_end) ? __ldg(reinterpret_cast<const float4 *>(p.dZ + (size_t)(r0 + k) * p.ldz + mh * 128 + mc * 4))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {               // X: 32 rows x 256 features = 2048 chunks, two units
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ci = t + 128 * ((kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
-                    const int col = n0 + nc * 4;
-                    v[i] = ((nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout)
-                               ? __ldg(reinterpret_cast<const float4 *>(p.X + (size_t)(r0 + k) * p.ldx + col))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        };
-        // skip empty work items (a split whose row range is empty)
         auto next_nonempty = [&]() {
             while (w < num_work) {
                 set_work(w);
@@ -597,26 +587,59 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 w += gridDim.x;
             }
         };
-        float4 vn[8];
-        next_nonempty();
-        int kind = 0;
-        if (w < num_work) load_unit(0, vn);
-        uint32_t it = 0;
-        while (w < num_work) {
-            float4 v[8];
+        // fetch cursor (runs two units ahead of the consume cursor)
+        int f_kind = 0;
+        auto fetch_unit = [&](int slot) {      // issues the cp.asyncs of the unit at the fetch cursor, then advances it
+            if (w < num_work) {
+                const uint32_t dst = ring_u32 + slot * 16384 + t * 16;
+                if (f_kind == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = vn[i];
-            const int cur_kind = kind, cur_ngroups = ngroups;
-            // advance to the next unit and start its loads
-            if (++kind == 3) {
-                kind = 0;
-                r0 += TC_BK;
-                if (r0 >= r_end) {
-                    w += gridDim.x;
-                    next_nonempty();
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
+                        const bool ok = r0 + k < r_end;
+                        cp_async16(dst + i * 2048, p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + mc * 4, ok ? 16u : 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * ((f_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
+                        const int col = n0 + nc * 4;
+                        const bool ok = (nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
+                        cp_async16(dst + i * 2048, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
+                    }
+                }
+                if (++f_kind == 3) {
+                    f_kind = 0;
+                    r0 += TC_BK;
+                    if (r0 >= r_end) {
+                        w += gridDim.x;
+                        next_nonempty();
+                    }
                 }
             }
-            if (w < num_work) load_unit(kind, vn);
+            cp_async_commit();     // one group per unit, also when empty: keeps the wait_group accounting uniform
+        };
+        next_nonempty();
+        // consume cursor: the same unit sequence, replayed from a copy of the initial cursor
+        int cw = w, c_r0 = r0, c_rend = r_end, c_ngroups = ngroups, c_kind = 0;
+        auto c_set_work = [&](int ww) {
+            const int ot = ww % out_tiles, ks = ww / out_tiles;
+            const int nn0 = (ot >> 1) * TC_N;
+            const int nv = min(TC_N, (p.Nout - nn0 + 15) & ~15);
+            c_ngroups = (nv + 31) >> 5;
+            c_r0 = ks * p.rows_per_split; c_rend = min(p.R, c_r0 + p.rows_per_split);
+        };
+        fetch_unit(0);
+        fetch_unit(1);
+        uint32_t it = 0, u = 0;
+        while (cw < num_work) {
+            const int slot = u & 1;
+            cp_async_wait<1>();                  // unit u has landed (unit u+1 may still be in flight)
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + i * 2048);
+            fetch_unit(slot);                    // refill this slot with unit u+2
+            const int cur_kind = c_kind, cur_ngroups = c_ngroups;
             const int s = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             const uint32_t st_u32 = smem_u32(smem + s * TCF_STAGE_BYTES);
@@ -651,7 +674,22 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     ++it;
                 }
             }
+            // advance the consume cursor
+            ++u;
+            if (++c_kind == 3) {
+                c_kind = 0;
+                c_r0 += TC_BK;
+                if (c_r0 >= c_rend) {
+                    cw += gridDim.x;
+                    while (cw < num_work) {
+                        c_set_work(cw);
+                        if (c_r0 < c_rend) break;
+                        cw += gridDim.x;
+                    }
+                }
+            }
         }
+        cp_async_wait<0>();
     } else if (warp >= 12) {
         setmaxnreg_dec<32>();
         if (warp == 12 && lane == 0) {
@@ -691,7 +729,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
     } else {
         setmaxnreg_inc<192>();
         const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
-        const uint32_t xp_u32 = smem_u32(xpose + ew * (32 * 32));
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -721,20 +758,24 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 if (lane == 0) mbar_arrive(&tempty[s]);
             }
             if (r_beg < r_end) {
-                const int m_base = mh * 128 + q * 32;
+                // the CTA's partial tile goes to G with 16-byte vector atomics straight from the registers (thread =
+                // one dZ feature row, 4 consecutive X features per instruction); this happens once per ~40 stages
+                float *grow = p.G + (size_t)(mh * 128 + q * 32 + lane) * p.ldg;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int col0 = n0 + half * 128 + j * 32;
                     if (half * 128 + j * 32 < nv) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sts32(xp_u32 + ((lane * 32 + (i ^ lane)) << 2), acc[j * 32 + i]);
-                        __syncwarp();
-                        if (col0 + lane < p.Nout) {
-#pragma unroll 4
-                            for (int r = 0; r < 32; ++r)
-                                red_add_f32(p.G + (size_t)(m_base + r) * p.ldg + col0 + lane, lds32(xp_u32 + ((r * 32 + (lane ^ r)) << 2)));
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const int col = n0 + half * 128 + j * 32 + c4 * 4;
+                            float *dst = grow + col;
+                            if (col + 3 < p.Nout && ((p.ldg & 3) == 0)) {
+                                red_add_v4(dst, acc[j * 32 + c4 * 4], acc[j * 32 + c4 * 4 + 1], acc[j * 32 + c4 * 4 + 2], acc[j * 32 + c4 * 4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.Nout) red_add_f32(dst + e, acc[j * 32 + c4 * 4 + e]);
+                            }
                         }
-                        __syncwarp();
                     }
                 }
             }
