@@ -243,12 +243,20 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
 
 // trunk backward: dA holds dL/dh2 on entry; x0 still holds this chunk's xhat.  Accumulates into grads G; the fc1
 // weight slot receives G1 = dz1^T xhat (turned into dW1 / dgamma0 / dbeta0 by ln0_finalize once per epoch).
-static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, int rows, cudaStream_t s) {
+// `dout` = gradient w.r.t. the head output ([rows, out]); on return all parameter gradients of the net have been
+// accumulated into G (the fc1 slot holds G1, see ln0_finalize).
+static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *dout, int rows,
+                          cudaStream_t s) {
     const int H = L.H;
     const int wpb = 8;
     const int gr = grid_for_reduce(h, rows, wpb);
-    relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dA, h->a2, h->mean2, h->rstd2, P + L.ln2_g, h->dA, G + L.ln2_g,
-                                               G + L.ln2_b, G + L.b2, rows, H);   // dA := dz2
+    // head backward + ReLU/LayerNorm backward of block 2 in one pass: dA := dz2
+    if (L.out == 2)
+        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, 0, s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
+                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
+    else
+        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, 0, s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
+                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
     h->launches++;
     int rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, h->dA, H, h->h1, H, G + L.W2, H, s)     // dW2 += dz2^T h1
                              : launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);
@@ -536,10 +544,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
             h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
             d_values + r0, h->vn_gae, d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
         h->launches++;
-        head_bwd_kernel<2><<<grid_for_reduce(h, nr * N, 8), 256, 0, s>>>(h->dmu, h->h2, actor + LA.Wh, h->dA,
-                                                                        grad_actor + LA.Wh, grad_actor + LA.bh, nr * N, H);
-        h->launches++;
-        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, nr * N, s))) return rc;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s))) return rc;
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
         if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s))) return rc;
         critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
@@ -547,10 +552,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, d_vn_state, h->dv,
                                                               d_epoch_stats, nr, P);
         h->launches++;
-        head_bwd_kernel<1><<<grid_for_reduce(h, nr, 8), 256, 0, s>>>(h->dv, h->h2, critic + LC.Wh, h->dA, grad_critic + LC.Wh,
-                                                                    grad_critic + LC.bh, nr, H);
-        h->launches++;
-        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, nr, s))) return rc;
+        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nr, s))) return rc;
     }
     if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
     if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;

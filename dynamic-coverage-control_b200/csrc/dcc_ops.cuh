@@ -276,6 +276,84 @@ __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__
     }
 }
 
+// Head backward fused with the backward of the last trunk block.  The gradient w.r.t. the trunk output is rank-OUT,
+//   dh2[r,c] = sum_o dout[r,o] * Wh[o,c],
+// so it is formed on the fly instead of being written and read back; h2 (needed for dWh) is rebuilt from the saved
+// post-ReLU activation: h2 = LN(a2) * gamma + beta.  Per row: reads a2 (and mean / rstd), writes dz2; accumulates
+// dgamma, dbeta, dbias (of the Linear) and dWh, dbh with one set of float atomics per warp.  H <= 256.
+template <int OUT>
+__global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
+                                        const float *__restrict__ a, const float *__restrict__ mean,
+                                        const float *__restrict__ rstd, const float *__restrict__ gamma,
+                                        const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
+                                        float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dWh,
+                                        float *__restrict__ dbh, int rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    float g[8], be[8], w[OUT][8], acc_g[8], acc_b[8], acc_z[8], acc_w[OUT][8], acc_bh[OUT];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        g[j] = (c < H) ? gamma[c] : 0.f;
+        be[j] = (c < H) ? beta[c] : 0.f;
+        acc_g[j] = acc_b[j] = acc_z[j] = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) { w[o][j] = (c < H) ? Wh[o * H + c] : 0.f; acc_w[o][j] = 0.f; }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) acc_bh[o] = 0.f;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const float m = mean[r], rs = rstd[r];
+        float d[OUT];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) { d[o] = dout[(size_t)r * OUT + o]; acc_bh[o] += d[o]; }
+        float xh[8], dxh[8], av[8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            const bool ok = c < H;
+            av[j] = ok ? a[(size_t)r * H + c] : 0.f;
+            xh[j] = ok ? (av[j] - m) * rs : 0.f;
+            const float h2 = fmaf(xh[j], g[j], be[j]);
+            float dh = 0.f;
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { dh = fmaf(d[o], w[o][j], dh); acc_w[o][j] = fmaf(d[o], h2, acc_w[o][j]); }
+            acc_g[j] = fmaf(dh, xh[j], acc_g[j]);
+            acc_b[j] += dh;
+            dxh[j] = dh * g[j];
+            s1 += dxh[j];
+            s2 = fmaf(dxh[j], xh[j], s2);
+        }
+        const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) {
+                const float da = rs * (dxh[j] - c1 - xh[j] * c2);
+                const float v = (av[j] > 0.f) ? da : 0.f;
+                dz[(size_t)r * H + c] = v;
+                acc_z[j] += v;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < H) {
+            atomicAdd(&dgamma[c], acc_g[j]);
+            atomicAdd(&dbeta[c], acc_b[j]);
+            atomicAdd(&dbias[c], acc_z[j]);
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) atomicAdd(&dWh[o * H + c], acc_w[o][j]);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) atomicAdd(&dbh[o], acc_bh[o]);
+    }
+}
+
 // ---- counter-based RNG (Philox4x32-10) + Box-Muller: action sampling a = mu + sigma * eps ---------------
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -351,51 +429,6 @@ __global__ void critic_head_kernel(const float *__restrict__ h, const float *__r
         for (int c = lane; c < H; c += 32) s = fmaf(h[(size_t)r * H + c], wv[c], s);
         s = warp_sum_f(s);
         if (lane == 0) v_out[r] = s + bv[0];
-    }
-}
-
-// Head backward: dh[r,c] = sum_o dout[r,o] * W[o,c];  dW[o,c] += sum_r dout[r,o]*h[r,c];  db[o] += sum_r dout[r,o].
-// OUT = 2 (actor) or 1 (critic).  H <= 256.
-template <int OUT>
-__global__ void head_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ h, const float *__restrict__ W,
-                                float *__restrict__ dh, float *__restrict__ dW, float *__restrict__ db, int rows, int H) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    float w[OUT][8], aw[OUT][8], ab[OUT];
-#pragma unroll
-    for (int o = 0; o < OUT; ++o) {
-        ab[o] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            w[o][j] = (c < H) ? W[o * H + c] : 0.f;
-            aw[o][j] = 0.f;
-        }
-    }
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        float d[OUT];
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) { d[o] = dout[(size_t)r * OUT + o]; ab[o] += d[o]; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            if (c < H) {
-                const float hv = h[(size_t)r * H + c];
-                float acc = 0.f;
-#pragma unroll
-                for (int o = 0; o < OUT; ++o) { acc = fmaf(d[o], w[o][j], acc); aw[o][j] = fmaf(d[o], hv, aw[o][j]); }
-                dh[(size_t)r * H + c] = acc;
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < OUT; ++o) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            if (c < H) atomicAdd(&dW[o * H + c], aw[o][j]);
-        }
-        if (lane == 0) atomicAdd(&db[o], ab[o]);
     }
 }
 

@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
         const uint32_t rs_u32 = smem_u32(rowstat);
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
-        TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, e_wait = 0, e_drain = 0, e_tile = 0);
+        TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, e_wait = 0, e_drain = 0, e_tile = 0, e_stats = 0);
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
             float acc[128];
@@ -459,6 +459,39 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                     if (p.rstd) p.rstd[row0 + lane] = rstd;
                 }
             }
+            TC_PROF_NOW(t3);
+            TC_PROF_ADD(e_stats, t0, t3);
+            if (p.dbg & 2) {
+                // direct stores: thread = row, 16 bytes per instruction (no shared-memory staging)
+                const int row = row0 + lane;
+                if (row < p.M && !(p.dbg & 1)) {
+                    if (p.epi == TCF_EPI_STORE) {
+                        float *dst = p.C + (size_t)row * p.ldc + half * 128;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (p.splits > 1) red_add_v4(dst + 4 * c, acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                            else *reinterpret_cast<float4 *>(dst + 4 * c) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                        }
+                    } else {
+                        if (p.C) {
+                            float *dst = p.C + (size_t)row * p.ldc + half * 128;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                *reinterpret_cast<float4 *>(dst + 4 * c) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                        }
+                        float *dsth = p.H + (size_t)row * p.ldc + half * 128;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma + half * 128) + c);
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta + half * 128) + c);
+                            float4 hv;
+                            hv.x = fmaf((acc[4 * c] - mean) * rstd, g.x, b.x); hv.y = fmaf((acc[4 * c + 1] - mean) * rstd, g.y, b.y);
+                            hv.z = fmaf((acc[4 * c + 2] - mean) * rstd, g.z, b.z); hv.w = fmaf((acc[4 * c + 3] - mean) * rstd, g.w, b.w);
+                            *reinterpret_cast<float4 *>(dsth + 4 * c) = hv;
+                        }
+                    }
+                }
+            } else {
             // Stores: a thread holds 128 columns of ONE row, so a direct store would scatter 16-byte pieces over 32 rows.
             // Rows are staged 8 at a time through the warp's 4 KB buffer (16-byte chunks XOR-ed with the row: conflict
             // free both ways) and leave as whole 512-byte row segments, one STG.128 per row per warp.
@@ -499,12 +532,14 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                 }
                 __syncwarp();
             }
+            }
             TC_PROF_NOW(t1);
             TC_PROF_ADD(e_tile, t0, t1);
         }
         TC_PROF_OUT(threadIdx.x == 128, 8, e_wait);
         TC_PROF_OUT(threadIdx.x == 128, 9, e_drain);
         TC_PROF_OUT(threadIdx.x == 128, 10, e_tile);
+        TC_PROF_OUT(threadIdx.x == 128, 11, e_stats);
     }
     tc_fence_before();
     __syncthreads();

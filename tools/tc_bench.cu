@@ -46,7 +46,7 @@ int main(int argc, char **argv) {
     printf("CTA0: %llu stages | producer: wait_empty %.0f work %.0f cyc/stage | mma: wait_acc %.0f wait_full %.0f issue %.0f, total %.0f cyc/stage\n",
            prof[2], prof[0] / st, prof[1] / st, prof[4] / st, prof[5] / st, prof[6] / st, prof[7] / st);
     const double tl = st / KT;
-    printf("      epilogue warp 4: wait_tfull %.0f drain %.0f cyc/stage, tile epilogue %.0f cyc/tile (%.1f tiles)\n", prof[8] / st,
-           prof[9] / st, prof[10] / tl, tl);
+    printf("      epilogue warp 4: wait_tfull %.0f drain %.0f cyc/stage, tile epilogue %.0f cyc/tile of which bias/relu/LN-stats %.0f (%.1f tiles)\n", prof[8] / st,
+           prof[9] / st, prof[10] / tl, prof[11] / tl, tl);
     return 0;
 }
