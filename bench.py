@@ -5,7 +5,13 @@
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU arm (oracle port, all host threads)
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # one rank per GPU, envs sharded (weak scaling)
 
-One "step" = one `env.step` of all E env instances of a rank (one kernel launch).  Prints ONE JSON line:
+Workloads (`--workload`):
+  env    (default, the BASELINE.json metric: configs[1]) one "step" = one `env.step` of all E env instances of a rank
+         (one kernel launch);
+  mappo  (BASELINE configs[3] / [4]) one "step" = one full MAPPO iteration at 65 536 envs per GPU: 150-step rollout
+         (policy forward + env step + insert), GAE, 15-epoch PPO update; under torchrun the env axis is sharded and
+         the flat gradient is all-reduced over NCCL once per epoch.  Default --steps 2 --warmup 3 (~2 min).
+Prints ONE JSON line:
   value        whole-job agent-steps/s, inputs (actions) resident in HBM, device-timed with CUDA events
   e2e          same metric through the host-buffer C entry point `dcc_env_step_host` (numpy in / numpy out):
                pinned H2D of the actions and D2H of obs/reward/done/coverage inside the timed region
@@ -275,15 +281,209 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+
+# ---- MAPPO full-loop workload (BASELINE configs[3] single GPU, configs[4] sharded) -----------------------------------
+MAPPO_METRIC = "agent-steps/sec at 8 UAV / 64 PoI (full MAPPO rollout+update loop, 65536 envs per GPU)"
+T_ROLLOUT, PPO_EPOCH, HIDDEN = 150, 15, 256
+
+
+def mappo_flops_per_env_step_row(n, m, hidden=HIDDEN):
+    """Algorithmic fp32 FLOPs of ONE PPO epoch per env-step row (N actor rows + 1 critic row), as this build computes
+    it (critic evaluated once per env; no dX GEMM for layer 1): forward 2 GEMMs + backward dX2, dW2, dW1 per net."""
+    d = obs_dim(n, m)
+    per_net = lambda k: 2 * hidden * (k + hidden) + 2 * hidden * (hidden + hidden + k)   # noqa: E731
+    return n * per_net(d) + per_net(n * d)
+
+
+def time_cpu_port_mappo(n_envs, iters, seed=0):
+    """CPU arm of the full loop: the C env oracle + the float64 NumPy MAPPO oracle (hand-written backward), i.e. the
+    reference's algorithm on the host cores.  Bounded sample: n_envs envs, T = 150, 15 epochs."""
+    import numpy as np
+    from oracle.env_oracle import OracleEnv, max_threads
+    from oracle import mappo_oracle as mo
+    from dcc_b200.envs.cuda_vec_env import synthetic_pois
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mappo_util import actor_param_shapes, critic_param_shapes, make_params
+    N, M, D = N_AGENTS, N_POIS, obs_dim(N_AGENTS, N_POIS)
+    hp = dict(clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0, max_grad_norm=10.0, huber_delta=10.0, opti_eps=1e-5)
+    tr = mo.Trainer(make_params(actor_param_shapes(D, HIDDEN), 1), make_params(critic_param_shapes(N * D, HIDDEN), 2), hp)
+    env = OracleEnv(n_envs, N, M, synthetic_pois(M), comm_r_scale=0.9, contact_force=0.0, n_threads=max_threads())
+    rng = np.random.default_rng(seed)
+    T = T_ROLLOUT
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        obs = np.zeros((T + 1, n_envs, N, D), np.float32)
+        act = np.zeros((T, n_envs, N, 2), np.float32)
+        logp = np.zeros((T, n_envs, N, 1), np.float32)
+        vals = np.zeros((T + 1, n_envs, N, 1), np.float32)
+        rew = np.zeros((T, n_envs, N, 1), np.float32)
+        masks = np.ones((T + 1, n_envs, N, 1), np.float32)
+        obs[0] = env.reset()
+        logstd = tr.actor.p["act.action_out.logstd._bias"].reshape(1, -1)
+        for t in range(T):
+            mean = tr.actor.forward(obs[t].reshape(n_envs * N, D))
+            a = mean + np.exp(logstd) * rng.standard_normal(mean.shape)
+            lp, _ = mo.gaussian_logp_entropy(mean, logstd, a)
+            v = tr.critic.forward(obs[t].reshape(n_envs, N * D))
+            act[t], logp[t] = a.reshape(n_envs, N, 2), lp.reshape(n_envs, N, 1)
+            vals[t] = np.repeat(v.reshape(n_envs, 1, 1), N, axis=1)
+            o = env.step(act[t], want_aux=False)
+            obs[t + 1] = o["obs"]
+            rew[t] = o["reward"].reshape(n_envs, 1, 1)
+            masks[t + 1] = 1.0 - o["done"].reshape(n_envs, 1, 1)
+        vals[T] = np.repeat(tr.critic.forward(obs[T].reshape(n_envs, N * D)).reshape(n_envs, 1, 1), N, axis=1)
+        ret = mo.gae_returns(rew, vals, masks, tr.vn)
+        tr.train(obs, act, logp, vals, ret, 5e-4, PPO_EPOCH)
+    dt = time.perf_counter() - t0
+    return n_envs * N * T * iters / dt, dt
+
+
+def run_reference_mappo(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_envs, iters = 4, max(1, min(args.steps, 2))
+    value, dt = time_cpu_port_mappo(n_envs, iters)
+    threads = os.cpu_count() or 1
+    sample = ("%d envs x %d iterations (T=150, 15 epochs, %.1f s) of the 8 UAV / 64 PoI MAPPO loop: C env oracle + float64 "
+              "NumPy MAPPO oracle (BLAS threads: all host cores)" % (n_envs, iters, dt))
+    line = {"impl": "reference", "metric": MAPPO_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+            "warmup": 0, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "full MAPPO loop, 8 UAV / 64 PoI, bounded sample of %d envs" % n_envs, "n_agents": N_AGENTS,
+                       "n_pois": N_POIS, "envs": n_envs, "T": T_ROLLOUT, "ppo_epoch": PPO_EPOCH},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda_mappo(args):
+    import torch
+    import torch.distributed as dist
+    from dcc_b200.learner import Learner
+    from dcc_b200.parallel import Comm
+    from dcc_b200.utils.config import load_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E = args.envs or ENVS_PER_GPU
+    steps, warmup = args.steps, max(args.warmup, 3)
+    cfg = load_config(None, num_agents=N_AGENTS, num_pois=N_POIS, n_rollout_threads=E * world, max_ep_len=T_ROLLOUT,
+                      ppo_epoch=PPO_EPOCH, n_iters=steps + warmup + 1, n_eval_rollout_threads=0, save_model=False,
+                      device=local_rank)
+    lr = Learner(cfg, comm=Comm())
+
+    def one_iter(i):
+        lr.policy.lr_decay(i, cfg.n_iters)
+        ri = lr.rollout(lr.rl_buffer, lr.train_envs)     # returns python floats: the rollout's device->host read
+        ti = lr.rl_update()                              # returns python floats: the update's device->host read
+        return ri, ti
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        one_iter(i + 1)
+    sampler = ClockSampler(local_rank)
+    l0 = lr.policy.launch_count() + lr.train_envs.launch_count()
+    c0 = lr.comm.calls
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    if rank == 0:
+        sampler.start()
+    barrier()
+    if rank == 0:
+        sampler.mark()
+    t0 = time.perf_counter()
+    ev[0].record()
+    info = None
+    for i in range(steps):
+        lr.policy.lr_decay(warmup + i + 1, cfg.n_iters)
+        ri = lr.rollout(lr.rl_buffer, lr.train_envs)
+        ev[2 * i + 1].record()
+        ti = lr.rl_update()
+        ev[2 * i + 2].record()
+        info = (ri, ti)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    ms = ev[0].elapsed_time(ev[-1])
+    roll_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps))
+    upd_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lr.policy.launch_count() + lr.train_envs.launch_count() - l0 + steps * T_ROLLOUT   # + insert kernels
+    if world > 1:
+        tt = torch.tensor([ms, wall_s, upd_ms, roll_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, wall_s, upd_ms, roll_ms = (float(x) for x in tt.tolist())
+    agent_steps = world * E * N_AGENTS * T_ROLLOUT * steps
+    value = agent_steps / (ms * 1e-3)
+    if rank == 0:
+        peak_tf = 1404.7
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak_tf = float(json.load(f).get("bf16_tflops_sustained", peak_tf))
+            peak_src = "measured sustained dense bf16 (MEASURED_PEAKS.json); the kernels run 3xTF32 (TF32 peak = bf16/2, three MMAs per product => a perfect kernel reads 1/6)"
+        except Exception:
+            peak_src = "fallback"
+        flop_epoch_row = mappo_flops_per_env_step_row(N_AGENTS, N_POIS)
+        upd_flops = flop_epoch_row * float(E) * T_ROLLOUT * PPO_EPOCH * steps          # per rank
+        achieved = upd_flops / (upd_ms * 1e-3) / 1e12
+        line = {
+            "metric": MAPPO_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "full MAPPO loop (BASELINE configs[3]%s): 8 UAV / 64 PoI, %d envs per GPU, T=150 rollout + GAE + "
+                                   "15-epoch PPO update, shipped hyper-parameters, random-init policy" % ("; configs[4] sharded" if world > 1 else "", E),
+                       "n_agents": N_AGENTS, "n_pois": N_POIS, "envs_per_gpu": E, "T": T_ROLLOUT, "ppo_epoch": PPO_EPOCH,
+                       "hidden": HIDDEN, "gemm_backend": lr.policy.gemm_backend(),
+                       "l2": "no flush needed: the rollout buffer (%.0f GB of observations) is streamed every epoch" % (
+                           (T_ROLLOUT + 1) * E * N_AGENTS * obs_dim(N_AGENTS, N_POIS) * 4 / 1e9),
+                       "rollout_ms_per_iter": roll_ms / steps, "update_ms_per_iter": upd_ms / steps,
+                       "allreduce_calls_per_iter": (lr.comm.calls - c0) / steps},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "peak_source": peak_src, "alg_flops_per_env_step_row_per_epoch": flop_epoch_row,
+                         "kernel": "tc_gemm_fwd_kernel + tc_gemm_wgrad_kernel (update phase, fp32-equivalent FLOPs)"},
+            "cpu_baseline": None,
+            "e2e": {"value": agent_steps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 8,
+                    "steps": steps, "api": "Learner.rollout + Learner.rl_update (host wall clock incl. the per-iteration device->host "
+                                           "reads of rollout_info / train_info; actions are produced on the device by the policy)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "last_iter": {"rollout_info": info[0], "train_info": info[1]},
+        }
+        if not args.no_cpu_baseline:
+            v, dt = time_cpu_port_mappo(2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "2 envs x 1 iteration (T=150, 15 epochs, %.1f s): C env oracle + float64 NumPy MAPPO oracle" % dt}
+        print(json.dumps(line), flush=True)
+    lr.train_envs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="env", choices=["env", "mappo"])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (mappo workload; default 65536)")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.steps is None:
+        args.steps = 150 if args.workload == "env" else 2
+    if args.warmup is None:
+        args.warmup = 10 if args.workload == "env" else 3
+    if args.workload == "mappo":
+        (run_reference_mappo if args.impl == "reference" else run_cuda_mappo)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)
