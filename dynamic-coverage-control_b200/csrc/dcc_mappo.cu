@@ -176,9 +176,11 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
     memset(&p, 0, sizeof p);
     p.dZ = dZ; p.X = X; p.G = G; p.R = R; p.Nout = Nout; p.ldz = ldz; p.ldx = ldx; p.ldg = ldg;
     p.n_tiles = (Nout + tc::TC_N - 1) / tc::TC_N;
+    p.tile_n = ((Nout + p.n_tiles - 1) / p.n_tiles + 31) / 32 * 32;      // balanced column tiles, whole 32-feature groups
     const int out_tiles = 2 * p.n_tiles;
-    // split the batch rows so that ~2 work items per SM exist, each at least 8 stages (256 rows) long
-    int ks = (2 * h->sm_count + out_tiles - 1) / out_tiles;
+    // split the batch rows so that the work items fill two waves of the persistent grid without spilling into a
+    // third (floor, not ceil), each split at least 8 stages (256 rows) long
+    int ks = (2 * h->sm_count) / out_tiles;
     const int max_ks = (R + 255) / 256;
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
@@ -342,6 +344,9 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
         const double per_row = (double)N * (D + 6.0 * H + 16) * 4.0;
         chunk = (long)(1.5e9 / per_row);
         if (chunk > 131072) chunk = 131072;
+        // whole waves of 128-row actor tiles on the persistent grid: chunk * N a multiple of 128 * SMs
+        const long wave = (long)prop.multiProcessorCount * 128;
+        if (chunk * N >= wave) chunk = (chunk * N / wave) * wave / N;
         if (chunk < 64) chunk = 64;
     }
     h->chunk_rows = (int)chunk;

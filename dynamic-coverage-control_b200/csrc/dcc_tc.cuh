@@ -565,7 +565,8 @@ struct TcwParams {
     const float *X;      // [R, ldx], Nout valid features (ldx % 4 == 0)
     float *G;            // [256, ldg]
     int R, Nout, ldz, ldx, ldg;
-    int n_tiles;         // ceil(Nout / 256); output tiles = 2 * n_tiles
+    int n_tiles;         // column tiles; output tiles = 2 * n_tiles
+    int tile_n;          // columns per tile: a multiple of 32, <= 256, chosen to balance the tiles (338 -> 192 + 146)
     int ksplits, rows_per_split;   // rows_per_split % 32 == 0
 };
 
@@ -610,8 +611,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         int w = blockIdx.x, r0 = 0, r_end = 0, mh = 0, n0 = 0, ngroups = 0;
         auto set_work = [&](int ww) {
             const int ot = ww % out_tiles, ks = ww / out_tiles;
-            mh = ot & 1; n0 = (ot >> 1) * TC_N;
-            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+            mh = ot & 1; n0 = (ot >> 1) * p.tile_n;
+            const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
             ngroups = (nv + 31) >> 5;
             r0 = ks * p.rows_per_split; r_end = min(p.R, r0 + p.rows_per_split);
         };
@@ -659,8 +660,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         int cw = w, c_r0 = r0, c_rend = r_end, c_ngroups = ngroups, c_kind = 0;
         auto c_set_work = [&](int ww) {
             const int ot = ww % out_tiles, ks = ww / out_tiles;
-            const int nn0 = (ot >> 1) * TC_N;
-            const int nv = min(TC_N, (p.Nout - nn0 + 15) & ~15);
+            const int nn0 = (ot >> 1) * p.tile_n;
+            const int nv = min(p.tile_n, (p.Nout - nn0 + 15) & ~15);
             c_ngroups = (nv + 31) >> 5;
             c_r0 = ks * p.rows_per_split; c_rend = min(p.R, c_r0 + p.rows_per_split);
         };
@@ -731,8 +732,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             uint32_t it = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int ot = w % out_tiles, ks = w / out_tiles;
-                const int n0 = (ot >> 1) * TC_N;
-                const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+                const int n0 = (ot >> 1) * p.tile_n;
+                const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
                 const uint32_t idesc = make_idesc_tf32(TC_BM, nv, 1, 1);
                 const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
                 for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
@@ -768,8 +769,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         uint32_t it = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int ot = w % out_tiles, ks = w / out_tiles;
-            const int mh = ot & 1, n0 = (ot >> 1) * TC_N;
-            const int nv = min(TC_N, (p.Nout - n0 + 15) & ~15);
+            const int mh = ot & 1, n0 = (ot >> 1) * p.tile_n;
+            const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
             const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
             float acc[128];
 #pragma unroll
