@@ -369,11 +369,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                     const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, 16, 1024);
                     const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, 16, 1024);
                     const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, 16, 1024);
+                    // The 8 small cross terms go first, while the fresh accumulator is still ~2^-11 of its final
+                    // magnitude (their round-toward-zero losses are then negligible); only the 4 hi*hi MMAs add at
+                    // full magnitude.  Measured rms error vs float64: 1e-7-class instead of 2.5e-7 with interleaving.
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
                         tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);   // fresh chain per stage
                         tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
                         tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
@@ -750,10 +757,14 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, 4096, 512, 1);
                     const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, 4096, 512, 1);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
+                    for (int k = 0; k < TC_BK / 8; ++k) {     // cross terms first (see tc_gemm_fwd_kernel)
                         const uint64_t adv = (uint64_t)((k * 1024) >> 4);   // next 8 reduction rows (two 4-row atoms)
                         tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
                         tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 1024) >> 4);
                         tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
                     tc_commit(&empty[s]);
