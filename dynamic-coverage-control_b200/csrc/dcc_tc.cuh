@@ -205,6 +205,10 @@ __global__ void tc_prep_weights_kernel(const float *__restrict__ W, int ldw, int
 //   WG2 warps 8-11   accumulate / epilogue, columns 128-255
 //   WG3 warp 12      MMA issuer (one thread) + TMEM allocation; warps 13-15 idle
 constexpr int TCF_STAGES = 2;
+#ifndef DCC_TCF_CHAIN
+#define DCC_TCF_CHAIN 1
+#endif
+constexpr int TCF_CHAIN = DCC_TCF_CHAIN;   // K-stages accumulated in TMEM before the drain warps take the partial tile
 constexpr int TCF_STAGE_BYTES = 2 * TC_A_TILE_FLOATS * 4 + 2 * TC_B_TILE_FLOATS * 4;   // 96 KB
 constexpr int TCF_XPOSE_BYTES = 8 * 32 * 32 * 4;   // per-warp 32x32 store staging (XOR-swizzled columns: conflict-free)
 constexpr int TCF_SMEM_BYTES = TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES + 1024 /*align*/ + 1280 /*barriers, row stats*/;
@@ -349,21 +353,25 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
         setmaxnreg_dec<32>();
         if (warp == 12 && lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_N, 0, 0);
-            uint32_t it = 0;
+            uint32_t it = 0, cit = 0;     // shared-memory stage counter, accumulator-chain counter
             TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
             TC_PROF_NOW(m_begin);
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
                 for (int kt = kt0; kt < kt1; ++kt, ++it) {
-                    const int s = it & 1;              // smem stage and TMEM accumulator advance together
+                    const int s = it & 1;                          // shared-memory stage
                     const uint32_t ph = (it >> 1) & 1;
+                    const int j = kt - kt0;                        // stage within the tile
+                    const bool chain_first = (j % TCF_CHAIN) == 0; // a chain = TCF_CHAIN stages into one accumulator
+                    const bool chain_last = (j % TCF_CHAIN) == TCF_CHAIN - 1 || kt == kt1 - 1;
+                    const int ab = cit & 1;                        // TMEM accumulator buffer of this chain
                     TC_PROF_NOW(t0);
-                    mbar_wait(&tempty[s], ph ^ 1);     // accumulator drained by the epilogue warps
+                    if (chain_first) mbar_wait(&tempty[ab], ((cit >> 1) & 1) ^ 1);   // drained by the epilogue warps
                     TC_PROF_NOW(t1);
                     mbar_wait(&full[s], ph);           // operands landed
                     TC_PROF_NOW(t2);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + s * TC_N;
+                    const uint32_t d = tmem_base + ab * TC_N;
                     const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
                     const uint64_t a_hi = make_desc_sw128(sa, 16, 1024);
                     const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, 16, 1024);
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
-                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);   // fresh chain per stage
+                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, (k != 0 || !chain_first) ? 1u : 0u);   // fresh accumulator per chain
                         tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
                     }
 #pragma unroll
@@ -384,7 +392,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                         tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
-                    tc_commit(&tfull[s]);      // accumulator ready to drain
+                    if (chain_last) {
+                        tc_commit(&tfull[ab]); // accumulator ready to drain
+                        ++cit;
+                    }
                     TC_PROF_NOW(t3);
                     TC_PROF_ADD(m_wacc, t0, t1);
                     TC_PROF_ADD(m_wfull, t1, t2);
@@ -413,7 +424,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
             float acc[128];
 #pragma unroll
             for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-            for (int kt = kt0; kt < kt1; ++kt, ++it) {
+            const int nchains = (kt1 - kt0 + TCF_CHAIN - 1) / TCF_CHAIN;
+            for (int c = 0; c < nchains; ++c, ++it) {      // `it` counts accumulator chains here
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 TC_PROF_NOW(t0);
