@@ -71,10 +71,10 @@ static inline int grid_for_rows(const MappoHandle *h, long rows, int warps_per_b
     return (int)(b < 1 ? 1 : b);
 }
 
-// kernels that end with per-warp atomics into a small parameter-gradient vector: keep the grid at 2 CTAs per SM
+// kernels that end with one set of atomics per block into a small parameter-gradient vector: 4 CTAs per SM
 static inline int grid_for_reduce(const MappoHandle *h, long rows, int warps_per_block) {
     long b = (rows + warps_per_block - 1) / warps_per_block;
-    const long cap = (long)h->sm_count * 2;
+    const long cap = (long)h->sm_count * 4;
     if (b > cap) b = cap;
     return (int)(b < 1 ? 1 : b);
 }
@@ -215,7 +215,13 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
     const int H = L.H;
     const int wpb = 8;
     const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
-    ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+    // input LayerNorm (without affine): register-resident single-pass variant when the rows are 16-byte aligned
+    if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 8)
+        ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+    else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 24)
+        ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+    else
+        ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
     h->launches++;
     int rc;
     if (h->backend == 2) {
@@ -254,10 +260,10 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     const int gr = grid_for_reduce(h, rows, wpb);
     // head backward + ReLU/LayerNorm backward of block 2 in one pass: dA := dz2
     if (L.out == 2)
-        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, 0, s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
+        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
                                                           h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
     else
-        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, 0, s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
+        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
                                                           h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
     h->launches++;
     int rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, h->dA, H, h->h1, H, G + L.W2, H, s)     // dW2 += dz2^T h1
@@ -266,7 +272,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->dA, H, h->img_w2t[net], h->dB, H, s)                // dh1 = dz2 W2
                          : launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);
     if (rc) return rc;
-    relu_ln_bwd_kernel<<<gr, wpb * 32, 0, s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
+    relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
                                                G + L.ln1_b, G + L.b1, rows, H);   // dB := dz1
     h->launches++;
     rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, h->dB, H, h->x0, L.inp, G + L.W1, L.in, s)         // G1 += dz1^T xhat

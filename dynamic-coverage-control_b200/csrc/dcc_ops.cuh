@@ -141,6 +141,44 @@ __global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__res
     }
 }
 
+// Same, for rows that are 16-byte aligned and short enough to live in registers (F % 4 == 0, F <= 128 * NV): one
+// global read pass with 16-byte loads, NV float4 per lane (the critic's centralised input: F = N*D = 2704 -> NV = 22).
+template <int NV>
+__global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int F4 = F >> 2, L4 = ldo >> 2;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)r * F);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = (c < F4) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum_f(s) / (float)F;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < F4) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
+        float4 *yr = reinterpret_cast<float4 *>(xhat + (size_t)r * ldo);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < F4) yr[c] = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+            else if (c < L4) yr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int c = lane + 32 * NV; c < L4; c += 32) yr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // W1g[h,c] = W1[h,c] * gamma0[c];  b1g[h] = b1[h] + sum_c W1[h,c] * beta0[c].  One warp per output unit h.
 __global__ void fold_ln0_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ g0,
                                 const float *__restrict__ be0, float *__restrict__ W1g, float *__restrict__ b1g, int H,
@@ -221,20 +259,45 @@ __global__ void bias_relu_ln_fwd_kernel(const float *__restrict__ z, const float
     }
 }
 
+// Block-level combine of per-warp partial column sums before they go to global memory: every warp of a 256-thread
+// block deposits its NV vectors of 8 values per lane (column = lane + 32 j) in shared memory, then thread t adds up
+// column t over the warps and issues ONE atomic per vector — 8x fewer atomics than per-warp, which lets these
+// streaming kernels run 4 CTAs per SM (enough loads in flight for HBM) without flooding the L2 atomic units.
+template <int NV>
+__device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float *const (&dst)[NV], int H, float *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[(warp * NV + v) * 256 + lane + 32 * j] = acc[v][j];
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c < H) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float t = 0.f;
+            for (int w = 0; w < nw; ++w) t += sm[(w * NV + v) * 256 + c];
+            atomicAdd(&dst[v][c], t);
+        }
+    }
+}
+
 // Backward of h = LN(a)*gamma+beta, a = relu(z+bias):  given dh, a, mean, rstd -> dz (in place over dh allowed),
-// and accumulates dgamma, dbeta, dbias (float atomics, one set per warp).  H <= 256.
+// and accumulates dgamma, dbeta, dbias (one set of float atomics per block).  H <= 256, blockDim = 256,
+// dynamic shared memory = 8 * 3 * 256 floats.
 __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
                                    const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
                                    float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
                                    int H) {
+    extern __shared__ float dyn_sm[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    float g[8], acc_g[8], acc_b[8], acc_z[8];
+    float g[8], acc[3][8];   // acc: dgamma, dbeta, dbias
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
         g[j] = (c < H) ? gamma[c] : 0.f;
-        acc_g[j] = acc_b[j] = acc_z[j] = 0.f;
+        acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
     }
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
         const float m = mean[r], rs = rstd[r];
@@ -247,8 +310,8 @@ __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__
             av[j] = ok ? a[(size_t)r * H + c] : 0.f;
             const float d = ok ? dh[(size_t)r * H + c] : 0.f;
             xh[j] = ok ? (av[j] - m) * rs : 0.f;
-            acc_g[j] = fmaf(d, xh[j], acc_g[j]);
-            acc_b[j] += d;
+            acc[0][j] = fmaf(d, xh[j], acc[0][j]);
+            acc[1][j] += d;
             dxh[j] = d * g[j];
             s1 += dxh[j];
             s2 = fmaf(dxh[j], xh[j], s2);
@@ -261,26 +324,20 @@ __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
                 const float v = (av[j] > 0.f) ? da : 0.f;
                 dz[(size_t)r * H + c] = v;
-                acc_z[j] += v;
+                acc[2][j] += v;
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = lane + 32 * j;
-        if (c < H) {
-            atomicAdd(&dgamma[c], acc_g[j]);
-            atomicAdd(&dbeta[c], acc_b[j]);
-            atomicAdd(&dbias[c], acc_z[j]);
-        }
-    }
+    float *const dst[3] = {dgamma, dbeta, dbias};
+    block_combine_atomic<3>(acc, dst, H, dyn_sm);
 }
 
 // Head backward fused with the backward of the last trunk block.  The gradient w.r.t. the trunk output is rank-OUT,
 //   dh2[r,c] = sum_o dout[r,o] * Wh[o,c],
 // so it is formed on the fly instead of being written and read back; h2 (needed for dWh) is rebuilt from the saved
 // post-ReLU activation: h2 = LN(a2) * gamma + beta.  Per row: reads a2 (and mean / rstd), writes dz2; accumulates
-// dgamma, dbeta, dbias (of the Linear) and dWh, dbh with one set of float atomics per warp.  H <= 256.
+// dgamma, dbeta, dbias (of the Linear) and dWh, dbh with one set of float atomics per block.  H <= 256, blockDim = 256,
+// dynamic shared memory = 8 * (3 + OUT) * 256 floats.
 template <int OUT>
 __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
@@ -288,17 +345,18 @@ __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const fl
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
                                         float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dWh,
                                         float *__restrict__ dbh, int rows, int H) {
+    extern __shared__ float dyn_sm[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    float g[8], be[8], w[OUT][8], acc_g[8], acc_b[8], acc_z[8], acc_w[OUT][8], acc_bh[OUT];
+    float g[8], be[8], w[OUT][8], acc[3 + OUT][8], acc_bh[OUT];   // acc: dgamma, dbeta, dbias, dWh[0..OUT)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
         g[j] = (c < H) ? gamma[c] : 0.f;
         be[j] = (c < H) ? beta[c] : 0.f;
-        acc_g[j] = acc_b[j] = acc_z[j] = 0.f;
+        acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { w[o][j] = (c < H) ? Wh[o * H + c] : 0.f; acc_w[o][j] = 0.f; }
+        for (int o = 0; o < OUT; ++o) { w[o][j] = (c < H) ? Wh[o * H + c] : 0.f; acc[3 + o][j] = 0.f; }
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) acc_bh[o] = 0.f;
@@ -318,9 +376,9 @@ __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const fl
             const float h2 = fmaf(xh[j], g[j], be[j]);
             float dh = 0.f;
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) { dh = fmaf(d[o], w[o][j], dh); acc_w[o][j] = fmaf(d[o], h2, acc_w[o][j]); }
-            acc_g[j] = fmaf(dh, xh[j], acc_g[j]);
-            acc_b[j] += dh;
+            for (int o = 0; o < OUT; ++o) { dh = fmaf(d[o], w[o][j], dh); acc[3 + o][j] = fmaf(d[o], h2, acc[3 + o][j]); }
+            acc[0][j] = fmaf(dh, xh[j], acc[0][j]);
+            acc[1][j] += dh;
             dxh[j] = dh * g[j];
             s1 += dxh[j];
             s2 = fmaf(dxh[j], xh[j], s2);
@@ -333,21 +391,15 @@ __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const fl
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
                 const float v = (av[j] > 0.f) ? da : 0.f;
                 dz[(size_t)r * H + c] = v;
-                acc_z[j] += v;
+                acc[2][j] += v;
             }
         }
     }
+    float *dst[3 + OUT];
+    dst[0] = dgamma; dst[1] = dbeta; dst[2] = dbias;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = lane + 32 * j;
-        if (c < H) {
-            atomicAdd(&dgamma[c], acc_g[j]);
-            atomicAdd(&dbeta[c], acc_b[j]);
-            atomicAdd(&dbias[c], acc_z[j]);
-#pragma unroll
-            for (int o = 0; o < OUT; ++o) atomicAdd(&dWh[o * H + c], acc_w[o][j]);
-        }
-    }
+    for (int o = 0; o < OUT; ++o) dst[3 + o] = dWh + o * H;
+    block_combine_atomic<3 + OUT>(acc, dst, H, dyn_sm);
     if (lane == 0) {
 #pragma unroll
         for (int o = 0; o < OUT; ++o) atomicAdd(&dbh[o], acc_bh[o]);
