@@ -257,6 +257,42 @@ def test_gemm_primitive_vs_float64(backend):
     assert ran >= 6
 
 
+def test_learner_16_uav_256_poi_shapes():
+    """BASELINE configs[2] shapes through the learner: critic input N*D = 21 024 (657 K-tiles, split-K forward, 83
+    column tiles in the weight-gradient GEMM); one update against the float64 oracle."""
+    import torch
+    from oracle import mappo_oracle as mo
+    N, M, Hd, E, T = 16, 256, 256, 6, 4
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=2, seed=5, n_iters=10, actor_seed=31, critic_seed=32,
+             clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0, max_grad_norm=10.0, huber_delta=10.0, opti_eps=1e-5)
+    rng = np.random.default_rng(17)
+    cfg, pol, tr, buf = build(c, E, T)
+    dev = buf.device
+    obs = rng.normal(0, 1.0, (T + 1, E, N, D)).astype(np.float32)
+    act = rng.normal(0, 1.0, (T, E, N, 2)).astype(np.float32)
+    vals = rng.normal(0, 1.0, (T + 1, E)).astype(np.float32)
+    rew = rng.normal(0, 10.0, (T, E)).astype(np.float32)
+    masks = (rng.random((T + 1, E)) > 0.1).astype(np.float32)
+    for dst, a in ((buf.obs, obs), (buf.actions, act), (buf.values_te, vals), (buf.rewards_te, rew), (buf.masks_te, masks)):
+        dst.copy_(torch.from_numpy(a).to(dev))
+    _, logp, _ = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
+    lp_old = logp.cpu().numpy().reshape(T, E, N) + rng.normal(0, 0.1, (T, E, N)).astype(np.float32)
+    buf.action_log_probs_ten.copy_(torch.from_numpy(lp_old).to(dev))
+    buf.compute_returns(None, tr.value_normalizer, policy=pol)
+    ret = buf.returns_te.cpu().numpy()
+    info = tr.train(buf)
+    otr = mo.Trainer(make_params(actor_param_shapes(D, Hd), 31), make_params(critic_param_shapes(N * D, Hd), 32), c)
+    ex = lambda a: np.broadcast_to(a[:, :, None, None], a.shape + (N, 1))   # noqa: E731
+    oinfo = otr.train(obs, act, lp_old[..., None], ex(vals), ex(ret), pol.lr_actor_now, 2)
+    for k in oinfo:
+        assert abs(info[k] - oinfo[k]) <= 1e-4 * max(1.0, abs(oinfo[k])), (k, info[k], oinfo[k])
+    got = pol.critic.view("base.mlp.fc1.0.weight").cpu().numpy().astype(np.float64)
+    ref = otr.critic.p["base.mlp.fc1.0.weight"]
+    bad = np.abs(got - ref) > 1e-5 + 2e-5 * np.abs(ref)
+    assert bad.mean() <= 2e-3, bad.mean()
+
+
 def test_learner_end_to_end_small():
     """The re-hosted Learner on the reference's YAML-equivalent defaults, shrunk: runs, logs the reference's keys,
     weights change, checkpoints round-trip with reference state_dict names."""

@@ -1,0 +1,32 @@
+"""Learning-curve sanity run of the re-hosted trainer (shipped 4 UAV / 20 PoI hyper-parameters, many envs):
+prints the reference's log lines; reward and coverage_rate must go up.  Usage: python tools/train_sanity.py [iters] [envs]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+from dcc_b200.learner import Learner  # noqa: E402
+from dcc_b200.utils.config import load_config  # noqa: E402
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+envs = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+cfg = load_config(None, n_rollout_threads=envs, n_iters=iters, n_eval_rollout_threads=0, save_model=False,
+                  pos_pois_path=None)
+lr = Learner(cfg)
+hist = []
+t0 = time.time()
+for it in range(1, iters + 1):
+    lr.policy.lr_decay(it, cfg.n_iters)
+    ri = lr.rollout(lr.rl_buffer, lr.train_envs)
+    ti = lr.rl_update()
+    hist.append((ri["reward"], ri["coverage_rate"], ti["value_loss"], ti["dist_entropy"]))
+    if it % 5 == 0 or it == 1:
+        lr.log(iter_=it, rollout_info=ri, rl_train_info=ti)
+h = np.array(hist)
+out = {"iters": iters, "envs": envs, "seconds": time.time() - t0, "reward_first5": float(h[:5, 0].mean()),
+       "reward_last5": float(h[-5:, 0].mean()), "coverage_first5": float(h[:5, 1].mean()), "coverage_last5": float(h[-5:, 1].mean()),
+       "agent_steps": lr.agent_steps, "backend": lr.policy.gemm_backend()}
+print(json.dumps(out))
+assert out["reward_last5"] > out["reward_first5"] and out["coverage_last5"] >= out["coverage_first5"], "no learning signal"
