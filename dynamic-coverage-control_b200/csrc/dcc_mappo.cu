@@ -348,11 +348,14 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     long chunk = cfg->chunk_rows;
     if (chunk <= 0) {
         const double per_row = (double)N * (D + 6.0 * H + 16) * 4.0;
-        chunk = (long)(1.5e9 / per_row);
+        chunk = (long)(2.5e9 / per_row);
         if (chunk > 131072) chunk = 131072;
-        // whole waves of 128-row actor tiles on the persistent grid: chunk * N a multiple of 128 * SMs
+        // whole waves of 128-row tiles on the persistent grid (one CTA per SM).  The critic runs one row per env step,
+        // so its tile count is chunk / 128: with chunk a multiple of 128 * SMs BOTH nets fill every wave (a chunk
+        // aligned for the actor only leaves the critic's forward-shaped GEMMs with a 25 %-full second wave).
         const long wave = (long)prop.multiProcessorCount * 128;
-        if (chunk * N >= wave) chunk = (chunk * N / wave) * wave / N;
+        if (chunk >= wave) chunk = chunk / wave * wave;
+        else if (chunk * N >= wave) chunk = (chunk * N / wave) * wave / N;
         if (chunk < 64) chunk = 64;
     }
     h->chunk_rows = (int)chunk;

@@ -171,8 +171,44 @@ class CudaVecEnv:
             self._h = None
         self.closed = True
 
-    def render(self, mode="human"):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path (SURVEY.md §2 row 11)")
+    def enable_connectivity_outputs(self):
+        """Allocate the per-UAV adjacency outputs (filled by every following step)."""
+        if not self.want_connectivity:
+            with torch.cuda.device(self.device):
+                self.adj = torch.zeros((self.n_envs, self.n_agents), dtype=torch.int32, device=self.device)
+                self.adj_s = torch.zeros((self.n_envs, self.n_agents), dtype=torch.int32, device=self.device)
+            self.want_connectivity = True
+
+    def snapshot(self, max_envs=None):
+        """Compact state of the first `max_envs` env instances on the host (synchronises): dict with pos_vel
+        (e,N,4) float64, energy (e,M) uint8, connect_bits (e,) uint8 [bit0 connect, bit1 connect_], adj (e,N) uint32
+        bitmask rows of the comm graph (None until enable_connectivity_outputs), coverage_rate (e,), reward (e,)."""
+        e = self.n_envs if max_envs is None else min(int(max_envs), self.n_envs)
+        pv, en = self.get_state()
+        return dict(pos_vel=pv[:e], energy=en[:e], connect_bits=self.connect_bits[:e].cpu().numpy(),
+                    adj=None if self.adj is None else self.adj[:e].cpu().numpy().view(np.uint32),
+                    coverage_rate=self.coverage_rate[:e].cpu().numpy(), reward=self.rewards[:e, 0, 0].cpu().numpy())
+
+    def render(self, mode="human", max_envs=1, size=350):
+        """Headless replacement of the pyglet viewer (environment.py:209-330): mode "rgb_array" returns, like the
+        reference's vec-env, a list over envs of one-element lists holding an (size,size,3) uint8 frame
+        (`frame[0][0]` is what learner.py:201 keeps); "human" has no window to draw into and returns None.
+        Visualisation only — it copies the compact state to the host."""
+        if mode != "rgb_array":
+            return None
+        from .headless_render import rasterize
+        st = self.snapshot(max_envs)
+        frames = []
+        for e in range(st["pos_vel"].shape[0]):
+            pos = st["pos_vel"][e, :, :2]
+            if st["adj"] is not None:
+                rows = st["adj"][e]
+            else:   # comm graph of the frame from the positions: d < r_a + r_b (CoverageWorld.py:78-80)
+                d = np.sqrt(((pos[:, None] - pos[None]) ** 2).sum(-1)) + np.eye(self.n_agents) * 1e5
+                rows = ((d < 2.0 * self.cfg.r_comm) * (1 << np.arange(self.n_agents))[None]).sum(1).astype(np.uint32)
+            frames.append([rasterize(pos, self.pos_pois, st["energy"][e], rows, self.cfg.r_cover, self.cfg.r_comm,
+                                     self.cfg.m_energy, size=size)])
+        return frames
 
     def __del__(self):
         try:

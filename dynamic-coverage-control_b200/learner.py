@@ -3,8 +3,12 @@
 Same methods (`train`, `rollout`, `warmup`, `collect`, `insert`, `compute`, `rl_update`, `log`, `save_model`,
 `load_model`) and the same loop; what disappears is the numpy glue between them: the env kernel writes step t's
 observations straight into `buffer.obs[t+1]`, the policy kernels read them there and write actions / log-probs /
-values straight into the buffer, and `insert` is one tiny kernel (reward, mask).  Rendering is out of scope
-(SURVEY.md §2 row 11); `n_render_rollout_threads` is ignored.
+values straight into the buffer, and `insert` is one tiny kernel (reward, mask).  Render rollouts
+(`render_interval`, `n_render_rollout_threads` = 1) run headless: instead of a pyglet window they record the compact
+state per step (`models_<iter>_traj.npz`: positions, PoI energy, connect bits, adjacency) and, with `save_gifs`,
+a GIF rasterised by envs/headless_render.py.  `rollout_info` carries one key more than the reference's:
+`connect_rate`, the fraction of (env, step) pairs whose UAV comm graph was connected (`world.connect`,
+CoverageWorld.py:92 — computed by the reference every step but never surfaced; asset/cc.png plots it).
 
 Multi-GPU (torchrun, one process per GPU): `n_rollout_threads` is the GLOBAL env count, sharded contiguously across
 ranks (parallel.shard_envs); parameters are replicated (rank 0's initial weights are broadcast); the only data-path
@@ -76,6 +80,19 @@ class Learner:
             self.test_buffer = SharedReplayBuffer(test_cfg, self.train_envs.observation_space[0],
                                                   self.share_observation_space, self.train_envs.action_space[0],
                                                   device=self.train_envs.device)
+        self.render_interval = int(getattr(cfg, "render_interval", 0) or 0)
+        self.save_gifs = bool(getattr(cfg, "save_gifs", False))
+        self.n_render = int(getattr(cfg, "n_render_rollout_threads", 0) or 0) if self.comm.rank == 0 else 0
+        if self.n_render > 0:
+            assert self.n_render == 1, "n_render_rollout_threads must be 1 (learner.py:82)"
+            render_cfg = copy.copy(cfg)
+            render_cfg.n_rollout_threads = self.n_render
+            self.render_envs = make_env(render_cfg)
+            self.render_envs.enable_connectivity_outputs()
+            self.render_buffer = SharedReplayBuffer(render_cfg, self.train_envs.observation_space[0],
+                                                    self.share_observation_space, self.train_envs.action_space[0],
+                                                    device=self.train_envs.device)
+        self.last_trajectory = None
 
         # 4. train-loop parameters
         self.use_linear_lr_decay = cfg.use_linear_lr_decay
@@ -107,6 +124,8 @@ class Learner:
                 test_rollout_info = self.rollout(self.test_buffer, self.test_envs)
             else:
                 test_rollout_info = {}
+            if self.n_render > 0 and self.render_interval > 0 and iter_ % self.render_interval == 0:
+                self.rollout(self.render_buffer, self.render_envs, is_render=True, iter_=iter_)
             if iter_ % self.log_interval == 0 and self.comm.rank == 0:
                 self.log(iter_=iter_, rollout_info=rollout_info, rl_train_info=rl_train_info,
                          test_rollout_info=test_rollout_info)
@@ -118,24 +137,44 @@ class Learner:
         self.train_envs.close()
         if self.cfg.n_eval_rollout_threads > 0:
             self.test_envs.close()
+        if self.n_render > 0:
+            self.render_envs.close()
 
     # ---- collect ---------------------------------------------------------------------------------------------
     def rollout(self, r_buffer, r_envs, is_render=False, iter_=0):
-        """learner.py:178-214.  Every rollout starts from a reset; returns {"reward", "coverage_rate"}."""
+        """learner.py:178-214.  Every rollout starts from a reset; returns {"reward", "coverage_rate"} as the
+        reference does, plus "connect_rate".  is_render=True records the trajectory of the (single) render env
+        instead of drawing it (see the module docstring)."""
         self.warmup(r_buffer, r_envs)
         E = r_buffer.n_rollout_threads
         rew_sum = torch.zeros((), dtype=torch.float32, device=r_buffer.device)
         sr = torch.zeros(E, dtype=torch.float32, device=r_buffer.device)
+        conn = torch.zeros((), dtype=torch.float32, device=r_buffer.device)
+        rec = None
+        if is_render:
+            from .envs.headless_render import TrajectoryRecorder
+            rec = TrajectoryRecorder(r_envs.pos_pois, r_envs.cfg.r_cover, r_envs.cfg.r_comm)
         for cur_step in range(self.max_ep_len):
             actions = self.collect(cur_step, r_buffer)
             obs, rewards, dones, infos = r_envs.step(actions, out_obs=r_buffer.obs[cur_step + 1])
             self.insert((obs, rewards, dones, infos), r_buffer, r_envs)
             rew_sum += rewards.mean()
             torch.maximum(sr, infos.coverage_rate, out=sr)
+            conn += (r_envs.connect_bits & 1).float().mean()
+            if rec is not None:
+                st = r_envs.snapshot()
+                rec.add(st["pos_vel"], st["energy"], st["connect_bits"], st["adj"], st["coverage_rate"], st["reward"])
         self.compute(r_buffer)
-        self.agent_steps += self.max_ep_len * E * self.n_agents
-        out = torch.stack([rew_sum, sr.mean()]).tolist()     # the rollout's only device->host read
-        return {"reward": out[0], "coverage_rate": out[1]}
+        if not is_render:
+            self.agent_steps += self.max_ep_len * E * self.n_agents
+        out = torch.stack([rew_sum, sr.mean(), conn / self.max_ep_len]).tolist()   # the rollout's only device->host read
+        if rec is not None:
+            self.last_trajectory = rec
+            if self.is_save_model:
+                rec.save(os.path.join(self.output_path, "models_%d_traj.npz" % iter_))
+                if self.save_gifs:
+                    rec.save_gif(os.path.join(self.output_path, "models_%d.gif" % iter_))
+        return {"reward": out[0], "coverage_rate": out[1], "connect_rate": out[2]}
 
     def warmup(self, r_buffer, r_envs):
         r_envs.reset(out_obs=r_buffer.obs[0])

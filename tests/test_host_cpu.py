@@ -134,3 +134,31 @@ def test_comm_is_a_noop_without_a_process_group():
     c = Comm()
     t = torch.ones(3)
     assert (c.world, c.rank) == (1, 0) and c.all_reduce_sum_(t) is t and c.calls == 0
+
+
+def test_headless_render_and_trajectory_recorder(tmp_path):
+    """f-3: the pyglet viewer's replacement rasterises from the compact state; the recorder round-trips."""
+    from dcc_b200.envs.headless_render import TrajectoryRecorder, rasterize
+    rng = np.random.default_rng(0)
+    N, M = 4, 20
+    poi = rng.uniform(-1, 1, (M, 2))
+    pos = np.array([[0.0, 0.0], [0.3, 0.0], [1.5, 1.5], [-1.0, 0.5]])
+    energy = np.zeros(M, np.uint8); energy[:5] = 5; energy[5:8] = 2
+    adj = np.array([0b0010, 0b0001, 0, 0], np.uint32)
+    f = rasterize(pos, poi, energy, adj, size=200)
+    assert f.shape == (200, 200, 3) and f.dtype == np.uint8
+    assert (f != 255).any() and (f == 255).all(-1).mean() > 0.5          # something drawn on a white canvas
+    # the comm line between UAV 0 and 1 (blue) is present; without adjacency it is not
+    blue = lambda im: int(((im[..., 2] > 180) & (im[..., 0] < 80)).sum())
+    assert blue(f) > 0 and blue(rasterize(pos, poi, energy, np.zeros(4, np.uint32), size=200)) == 0
+    rec = TrajectoryRecorder(poi, 0.2, 0.4)
+    for t in range(3):
+        pv = np.zeros((1, N, 4)); pv[0, :, :2] = pos + 0.01 * t
+        rec.add(pv, energy[None], np.array([t & 1], np.uint8), adj[None], np.array([0.25]), np.array([-1.0]))
+    assert abs(rec.connectivity_rate() - 1.0 / 3.0) < 1e-12
+    path = str(tmp_path / "traj.npz")
+    rec.save(path)
+    z = np.load(path)
+    assert z["pos_vel"].shape == (3, 1, N, 4) and z["adj"].shape == (3, 1, N) and z["poi_xy"].shape == (M, 2)
+    rec.save_gif(str(tmp_path / "t.gif"), size=64)
+    assert os.path.getsize(str(tmp_path / "t.gif")) > 100
