@@ -34,6 +34,9 @@ class MappoCfg(C.Structure):
         ("clip_param", C.c_float), ("entropy_coef", C.c_float), ("value_loss_coef", C.c_float),
         ("huber_delta", C.c_float), ("max_grad_norm", C.c_float), ("gamma", C.c_float), ("gae_lambda", C.c_float),
         ("opti_eps", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("vn_beta", C.c_double),
+        ("use_huber_loss", C.c_int32), ("use_clipped_value_loss", C.c_int32), ("use_max_grad_norm", C.c_int32),
+        ("use_valuenorm", C.c_int32), ("use_gae", C.c_int32), ("reserved1", C.c_int32),
+        ("weight_decay", C.c_float), ("reserved2", C.c_float),
     ]
 
 
@@ -67,6 +70,8 @@ SIGNATURES = {
     "dcc_mappo_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "dcc_mappo_train_begin": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "dcc_mappo_epoch_grads": (C.c_int, [_VP] * 12 + [C.c_double, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_mappo_minibatch_stats": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP]),
+    "dcc_mappo_minibatch_grads": (C.c_int, [_VP] * 12 + [C.c_double, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
     "dcc_mappo_apply": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, C.c_float, C.c_int64, _VP, _VP]),
     "dcc_op_gemm": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP, C.c_int,
                               _VP, C.c_int, C.c_int, _VP]),

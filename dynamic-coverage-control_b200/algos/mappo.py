@@ -150,6 +150,12 @@ class MAPPOPolicy:
         mc.value_loss_coef, mc.huber_delta = float(cfg.value_loss_coef), float(cfg.huber_delta)
         mc.max_grad_norm, mc.gamma, mc.gae_lambda = float(cfg.max_grad_norm), float(cfg.gamma), float(cfg.gae_lambda)
         mc.opti_eps = self.opti_eps
+        mc.use_huber_loss = 1 if getattr(cfg, "use_huber_loss", True) else 0
+        mc.use_clipped_value_loss = 1 if getattr(cfg, "use_clipped_value_loss", True) else 0
+        mc.use_max_grad_norm = 1 if getattr(cfg, "use_max_grad_norm", True) else 0
+        mc.use_valuenorm = 1 if getattr(cfg, "use_valuenorm", True) else 0
+        mc.use_gae = 1 if getattr(cfg, "use_gae", True) else 0
+        mc.weight_decay = self.weight_decay
         self.mcfg = mc
         h = C.c_void_p()
         _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
@@ -304,8 +310,9 @@ class MAPPOPolicy:
 
 class MAPPOTrainer:
     """algos/mappo.py:68-247.  `train(buffer)` runs the reference's update — advantage normalisation, ppo_epoch
-    passes over the whole rollout as one minibatch, ValueNorm update each epoch, separate grad-norm clips, two
-    Adam steps — as kernels; with a process group, gradients are all-reduced once per epoch."""
+    passes over the rollout (one minibatch = the whole rollout, or `num_mini_batch` random index lists per epoch,
+    buffer/shared_buffer.py:219-279), ValueNorm update before every optimiser step, separate grad-norm clips, two
+    Adam steps — as kernels; with a process group, gradients are all-reduced once per optimiser step."""
 
     def __init__(self, cfg, policy, agent_id=0, comm=None):
         self.policy = policy
@@ -316,21 +323,42 @@ class MAPPOTrainer:
         self.entropy_coef = cfg.entropy_coef
         self.max_grad_norm = cfg.max_grad_norm
         self.huber_delta = cfg.huber_delta
-        self._use_valuenorm = cfg.use_valuenorm
-        self.value_normalizer = ValueNorm(1, device=policy.device)
+        self._use_valuenorm = bool(getattr(cfg, "use_valuenorm", True))
+        # mappo.py:96-101 (PopArt is refused by check_supported): ValueNorm, or no normaliser at all
+        self.value_normalizer = ValueNorm(1, device=policy.device) if self._use_valuenorm else None
         self.comm = comm if comm is not None else Comm()
         dev = policy.device
+        n_upd = self.ppo_epoch * self.num_mini_batch
         self._stats4 = torch.zeros(4, dtype=torch.float64, device=dev)
-        self._epoch_stats = torch.zeros((self.ppo_epoch, 4), dtype=torch.float64, device=dev)
-        self._gnorm_sq = torch.zeros((self.ppo_epoch, 2), dtype=torch.float64, device=dev)
+        self._epoch_stats = torch.zeros((n_upd, 4), dtype=torch.float64, device=dev)
+        self._gnorm_sq = torch.zeros((n_upd, 2), dtype=torch.float64, device=dev)
+        self._mb_sums = torch.zeros((n_upd, 2), dtype=torch.float64, device=dev)
+        self.permutation_fn = None   # tests inject the reference's permutations: fn(epoch, B) -> int64 tensor
         self.training = False
+
+    def _permutation(self, epoch, n):
+        """`torch.randperm(batch_size)` of feed_forward_generator (shared_buffer.py:238), drawn on the device."""
+        if self.permutation_fn is not None:
+            return torch.as_tensor(self.permutation_fn(epoch, n), dtype=torch.int64).to(self.policy.device).contiguous()
+        return torch.randperm(n, device=self.policy.device)
+
+    def _apply(self, u, update_actor):
+        p, lib, ptr, s = self.policy, self.policy.lib, self.policy._ptr, self.policy._stream()
+        self.comm.all_reduce_sum_(p.flat_grads)            # the one data-path collective (SURVEY §8e)
+        for which, net, lr in ((0, p.actor, p.lr_actor_now), (1, p.critic, p.lr_critic_now)):
+            if which == 0 and not update_actor:
+                continue
+            net.adam_step += 1
+            _lib.check(lib.dcc_mappo_apply(p._h, which, ptr(net.params), ptr(net.grads), ptr(net.adam_m),
+                                           ptr(net.adam_v), float(lr), net.adam_step,
+                                           ptr(self._gnorm_sq[u, which:which + 1]), s), "dcc_mappo_apply")
 
     def train(self, buffer, update_actor=True):
         p, lib = self.policy, self.policy.lib
         T, E, N = buffer.episode_length, buffer.n_rollout_threads, p.n_agents
         s = p._stream()
         ptr = p._ptr
-        vn = self.value_normalizer.state
+        vn = self.value_normalizer.state if self.value_normalizer is not None else None
         _lib.check(lib.dcc_mappo_train_begin(p._h, ptr(buffer.returns_te), ptr(buffer.values_te), ptr(vn), T, E,
                                              ptr(self._stats4), s), "dcc_mappo_train_begin")
         self.comm.all_reduce_sum_(self._stats4)
@@ -338,29 +366,41 @@ class MAPPOTrainer:
             else float(T) * float(buffer.n_envs_global)
         self._epoch_stats.zero_()
         self._gnorm_sq.zero_()
+        nmb = self.num_mini_batch
+        B_local = T * E * N
+        mbs = B_local // nmb                               # mini_batch_size (shared_buffer.py:236); the tail is dropped
+        mbs_global = float(mbs) * self.comm.world
         for ep in range(self.ppo_epoch):
-            _lib.check(lib.dcc_mappo_epoch_grads(
-                p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
-                ptr(buffer.obs), ptr(buffer.actions), ptr(buffer.action_log_probs_ten), ptr(buffer.values_te),
-                ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, T, E, ptr(self._epoch_stats[ep]), s),
-                "dcc_mappo_epoch_grads")
-            self.comm.all_reduce_sum_(p.flat_grads)            # the one data-path collective
-            for which, net, lr in ((0, p.actor, p.lr_actor_now), (1, p.critic, p.lr_critic_now)):
-                if which == 0 and not update_actor:
-                    continue
-                net.adam_step += 1
-                _lib.check(lib.dcc_mappo_apply(p._h, which, ptr(net.params), ptr(net.grads), ptr(net.adam_m),
-                                               ptr(net.adam_v), float(lr), net.adam_step,
-                                               ptr(self._gnorm_sq[ep, which:which + 1]), s), "dcc_mappo_apply")
-        # epoch sums -> the reference's train_info (means over epochs; one device->host read per update)
+            if nmb == 1:
+                _lib.check(lib.dcc_mappo_epoch_grads(
+                    p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
+                    ptr(buffer.obs), ptr(buffer.actions), ptr(buffer.action_log_probs_ten), ptr(buffer.values_te),
+                    ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, T, E, ptr(self._epoch_stats[ep]), s),
+                    "dcc_mappo_epoch_grads")
+                self._apply(ep, update_actor)
+                continue
+            perm = self._permutation(ep, B_local)
+            for i in range(nmb):
+                u = ep * nmb + i
+                idx = perm[i * mbs:(i + 1) * mbs]
+                _lib.check(lib.dcc_mappo_minibatch_stats(p._h, ptr(buffer.returns_te), ptr(idx), mbs,
+                                                         ptr(self._mb_sums[u]), s), "dcc_mappo_minibatch_stats")
+                self.comm.all_reduce_sum_(self._mb_sums[u])
+                _lib.check(lib.dcc_mappo_minibatch_grads(
+                    p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
+                    ptr(buffer.obs), ptr(buffer.actions), ptr(buffer.action_log_probs_ten), ptr(buffer.values_te),
+                    ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, ptr(idx), mbs,
+                    ptr(self._mb_sums[u]), mbs_global, ptr(self._epoch_stats[u]), s), "dcc_mappo_minibatch_grads")
+                self._apply(u, update_actor)
+        # per-update sums -> the reference's train_info (means over updates; one device->host read per update)
         es = self._epoch_stats.clone()
         es[:, 3] = 0
         self.comm.all_reduce_sum_(es)
         es = es.cpu().numpy()
         ent = self._epoch_stats[:, 3].cpu().numpy()
         gn = np.sqrt(self._gnorm_sq.cpu().numpy())
-        B = rows_global * N
-        k = float(self.ppo_epoch * self.num_mini_batch)
+        B = rows_global * N if nmb == 1 else mbs_global    # agent rows behind each update's loss mean
+        k = float(self.ppo_epoch * nmb)
         return {"value_loss": float(es[:, 1].sum() / B / k), "policy_loss": float(es[:, 0].sum() / B / k),
                 "dist_entropy": float(ent.sum() / k), "actor_grad_norm": float(gn[:, 0].sum() / k),
                 "critic_grad_norm": float(gn[:, 1].sum() / k), "ratio": float(es[:, 2].sum() / B / k)}
@@ -375,7 +415,8 @@ class MAPPOTrainer:
         """Reference: pickle of the policy object (mappo.py:237-240).  Here: a pickle of plain CPU tensors keyed by
         the reference's state_dict names (+ Adam moments and the ValueNorm state, which the reference drops)."""
         sd = self.policy.state_dict()
-        sd["value_normalizer"] = self.value_normalizer.state_dict()
+        if self.value_normalizer is not None:
+            sd["value_normalizer"] = self.value_normalizer.state_dict()
         cpu = _to_cpu(sd)
         with open(os.path.join(save_path, "agent.pkl"), "wb") as f:
             pickle.dump(cpu, f)
@@ -384,7 +425,7 @@ class MAPPOTrainer:
         with open(os.path.join(load_path, "agent.pkl"), "rb") as f:
             sd = pickle.load(f)
         self.policy.load_state_dict(sd)
-        if "value_normalizer" in sd:
+        if "value_normalizer" in sd and self.value_normalizer is not None:
             self.value_normalizer.load_state_dict(sd["value_normalizer"])
 
 

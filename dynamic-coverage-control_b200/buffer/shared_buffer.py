@@ -26,6 +26,8 @@ class SharedReplayBuffer(object):
         self.n_rollout_threads = int(cfg.n_rollout_threads)
         self.gamma, self.gae_lambda = float(cfg.gamma), float(cfg.gae_lambda)
         self.num_agents = int(cfg.num_agents)
+        self._use_gae = bool(getattr(cfg, "use_gae", True))
+        self._use_valuenorm = bool(getattr(cfg, "use_valuenorm", True))
         self.obs_dim = int(obs_space.shape[0])
         self.act_dim = int(act_space.shape[0])
         self.device = torch.device("cuda", int(getattr(cfg, "device", 0) or 0)) if device is None else torch.device(device)
@@ -111,7 +113,10 @@ class SharedReplayBuffer(object):
         self.step = (self.step + 1) % self.episode_length
 
     def compute_returns(self, next_value, value_normalizer, policy=None):
-        """shared_buffer.py:199-208 (use_gae + ValueNorm branch).  next_value: (E,) / (E*N,1) / (E,N,1), or None if the
+        """shared_buffer.py:154-212: GAE or plain discounted returns (`use_gae`), with or without a value normaliser
+        (`value_normalizer` None = use_valuenorm false); `use_proper_time_limits` changes nothing in the reference
+        because it never stores bad_masks (they stay 1, learner.py:272-276).  The branch taken is the learner
+        handle's cfg.  next_value: (E,) / (E*N,1) / (E,N,1), or None if the
         bootstrap value already sits in values_te[T]."""
         T, E, N = self.episode_length, self.n_rollout_threads, self.num_agents
         if next_value is not None:
@@ -122,7 +127,8 @@ class SharedReplayBuffer(object):
         h = policy._h if policy is not None else self._gae_handle()
         p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
         _lib.check(self.lib.dcc_mappo_gae(h, p(self.rewards_te), p(self.values_te), p(self.masks_te),
-                                          p(value_normalizer.state), T, E, p(self.returns_te), self._stream()),
+                                          p(value_normalizer.state) if value_normalizer is not None else None, T, E,
+                                          p(self.returns_te), self._stream()),
                    "dcc_mappo_gae")
 
     def _gae_handle(self):
@@ -132,6 +138,7 @@ class SharedReplayBuffer(object):
             _lib.check(self.lib.dcc_mappo_cfg_default(C.byref(mc)), "dcc_mappo_cfg_default")
             mc.n_agents, mc.obs_dim, mc.hidden, mc.chunk_rows = 1, 1, 1, 64
             mc.gamma, mc.gae_lambda = self.gamma, self.gae_lambda
+            mc.use_gae, mc.use_valuenorm = int(self._use_gae), int(self._use_valuenorm)
             h = C.c_void_p()
             _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
             self._h = h

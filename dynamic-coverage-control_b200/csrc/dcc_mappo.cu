@@ -56,6 +56,9 @@ struct MappoHandle {
 };
 constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
 
+// ValueNorm state as of train_begin (advantages use it), or nullptr without a value normaliser
+static inline const float *vn_snapshot(const MappoHandle *h) { return h->cfg.use_valuenorm ? h->vn_gae : nullptr; }
+
 static MappoHandle *as_mappo(void *h) {
     MappoHandle *m = static_cast<MappoHandle *>(h);
     return (m && m->magic == MAPPO_MAGIC) ? m : nullptr;
@@ -211,17 +214,17 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
 
 // trunk forward on `rows` rows of width L.in: x -> h2.  save = keep a1/a2/stats for the backward pass.
 static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int net, const float *x, int rows, bool save,
-                         cudaStream_t s) {
+                         cudaStream_t s, const long long *ridx = nullptr, int rdiv = 1) {
     const int H = L.H;
     const int wpb = 8;
     const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
     // input LayerNorm (without affine): register-resident single-pass variant when the rows are 16-byte aligned
     if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 8)
-        ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+        ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
     else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 24)
-        ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+        ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
     else
-        ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp);
+        ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
     h->launches++;
     int rc;
     if (h->backend == 2) {
@@ -319,6 +322,8 @@ int dcc_mappo_cfg_default(dcc_mappo_cfg *c) {
     c->clip_param = 0.2f; c->entropy_coef = 0.01f; c->value_loss_coef = 1.0f; c->huber_delta = 10.0f;
     c->max_grad_norm = 10.0f; c->gamma = 0.99f; c->gae_lambda = 0.95f; c->opti_eps = 1e-5f; c->vn_beta = 0.99999;
     c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f;
+    c->use_huber_loss = 1; c->use_clipped_value_loss = 1; c->use_max_grad_norm = 1; c->use_valuenorm = 1; c->use_gae = 1;
+    c->weight_decay = 0.f;
     return DCC_OK;
 }
 
@@ -492,10 +497,12 @@ int dcc_rollout_insert(const float *d_rew_in, const uint8_t *d_done_in, int n_en
 int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, const float *d_masks,
                   const float *d_vn_state, int T, int E, float *d_returns, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
-    if (!h || !d_rewards || !d_values || !d_masks || !d_vn_state || !d_returns || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    if (!h || !d_rewards || !d_values || !d_masks || !d_returns || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && h->cfg.use_gae && !d_vn_state) return DCC_ERR_INVALID_ARG;
     DCC_CUDA_TRY(cudaSetDevice(h->device));
-    gae_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_masks, d_vn_state,
-                                                                            d_returns, T, E, h->cfg.gamma, h->cfg.gae_lambda);
+    gae_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_rewards, d_values, d_masks, h->cfg.use_valuenorm ? d_vn_state : nullptr, d_returns, T, E, h->cfg.gamma,
+        h->cfg.gae_lambda, h->cfg.use_gae);
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
     return DCC_OK;
@@ -504,17 +511,45 @@ int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, c
 int dcc_mappo_train_begin(void *handle, const float *d_returns, const float *d_values, const float *d_vn_state, int T, int E,
                           double *d_stats_out, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
-    if (!h || !d_returns || !d_values || !d_vn_state || !d_stats_out || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    if (!h || !d_returns || !d_values || !d_stats_out || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
     DCC_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)T * E;
     DCC_CUDA_TRY(cudaMemsetAsync(d_stats_out, 0, 4 * sizeof(double), s));
-    DCC_CUDA_TRY(cudaMemcpyAsync(h->vn_gae, d_vn_state, 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (h->cfg.use_valuenorm)
+        DCC_CUDA_TRY(cudaMemcpyAsync(h->vn_gae, d_vn_state, 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
-    sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, d_values, h->vn_gae, d_stats_out, n);
+    sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, d_values, vn_snapshot(h), d_stats_out, n);
     sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, nullptr, nullptr, d_stats_out + 2, n);
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches += 2;
+    return DCC_OK;
+}
+
+static PpoLossParams loss_params(const MappoHandle *h, double agent_rows_global) {
+    PpoLossParams P;
+    P.clip = h->cfg.clip_param; P.huber_delta = h->cfg.huber_delta; P.value_coef = h->cfg.value_loss_coef;
+    P.inv_rows = (float)(1.0 / agent_rows_global); P.n_agents = h->cfg.n_agents;
+    P.use_huber = h->cfg.use_huber_loss; P.use_clipped = h->cfg.use_clipped_value_loss;
+    return P;
+}
+
+// shared prologue of an optimiser step: zero the gradients, ValueNorm.update with the (mini)batch return statistics
+// (cal_value_loss, mappo.py:106-107), entropy statistic, fold the input LayerNorm into fc1 / refresh weight images
+static int grads_prologue(MappoHandle *h, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                          float *d_vn_state, const double *ret_sums, double n_ret, double *d_epoch_stats, cudaStream_t s) {
+    DCC_CUDA_TRY(cudaMemsetAsync(grad_actor, 0, h->la.total * sizeof(float), s));
+    DCC_CUDA_TRY(cudaMemsetAsync(grad_critic, 0, h->lc.total * sizeof(float), s));
+    if (h->cfg.use_valuenorm) {
+        vn_update_kernel<<<1, 32, 0, s>>>(d_vn_state, ret_sums, n_ret, (float)h->cfg.vn_beta, (float)(1.0 - h->cfg.vn_beta));
+        h->launches++;
+    }
+    entropy_stat_kernel<<<1, 32, 0, s>>>(actor + h->la.logstd, h->cfg.act_dim, d_epoch_stats + 3);
+    h->launches++;
+    int rc;
+    if ((rc = fold_ln0(h, h->la, actor, 0, true, s))) return rc;
+    if ((rc = fold_ln0(h, h->lc, critic, 1, true, s))) return rc;
     return DCC_OK;
 }
 
@@ -524,25 +559,19 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
                           int E, double *d_epoch_stats, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
     if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_actions || !d_logp_old || !d_values ||
-        !d_returns || !d_vn_state || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
+        !d_returns || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
         return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
     DCC_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
     const NetLayout &LA = h->la, &LC = h->lc;
-    DCC_CUDA_TRY(cudaMemsetAsync(grad_actor, 0, LA.total * sizeof(float), s));
-    DCC_CUDA_TRY(cudaMemsetAsync(grad_critic, 0, LC.total * sizeof(float), s));
     // ValueNorm.update(return_batch) happens inside cal_value_loss, every epoch, before normalising (mappo.py:107)
-    vn_update_kernel<<<1, 32, 0, s>>>(d_vn_state, d_stats4 + 2, n_rows_global, (float)h->cfg.vn_beta,
-                                      (float)(1.0 - h->cfg.vn_beta));
-    entropy_stat_kernel<<<1, 32, 0, s>>>(actor + LA.logstd, h->cfg.act_dim, d_epoch_stats + 3);
-    h->launches += 2;
     int rc;
-    if ((rc = fold_ln0(h, LA, actor, 0, true, s))) return rc;
-    if ((rc = fold_ln0(h, LC, critic, 1, true, s))) return rc;
-    PpoLossParams P;
-    P.clip = h->cfg.clip_param; P.huber_delta = h->cfg.huber_delta; P.value_coef = h->cfg.value_loss_coef;
-    P.inv_rows = (float)(1.0 / (n_rows_global * N)); P.n_agents = N;
+    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_stats4 + 2, n_rows_global, d_epoch_stats, s)))
+        return rc;
+    const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
+    const PpoLossParams P = loss_params(h, n_rows_global * N);
     const long R = (long)T * E;
     for (long r0 = 0; r0 < R; r0 += h->chunk_rows) {
         const int nr = (int)std::min<long>(h->chunk_rows, R - r0);
@@ -556,17 +585,87 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         h->launches++;
         ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
             h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
-            d_values + r0, h->vn_gae, d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
+            d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
         h->launches++;
         if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s))) return rc;
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
         if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s))) return rc;
         critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
         h->launches++;
-        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, d_vn_state, h->dv,
+        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
                                                               d_epoch_stats, nr, P);
         h->launches++;
         if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nr, s))) return rc;
+    }
+    if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
+    if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_mappo_minibatch_stats(void *handle, const float *d_returns, const int64_t *d_row_index, int64_t n_index,
+                              double *d_ret_sums_out, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_returns || !d_row_index || !d_ret_sums_out || n_index < 1) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DCC_CUDA_TRY(cudaMemsetAsync(d_ret_sums_out, 0, 2 * sizeof(double), s));
+    const int blocks = (int)std::min<size_t>(((size_t)n_index + 255) / 256, (size_t)h->sm_count * 8);
+    sum_sumsq_kernel<<<blocks, 256, 0, s>>>(d_returns, nullptr, nullptr, d_ret_sums_out, (size_t)n_index,
+                                            reinterpret_cast<const long long *>(d_row_index), h->cfg.n_agents);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
+}
+
+int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                              const float *d_obs, const float *d_actions, const float *d_logp_old, const float *d_values,
+                              const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global,
+                              const int64_t *d_row_index, int64_t n_index, const double *d_ret_sums,
+                              double n_index_global, double *d_epoch_stats, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_actions || !d_logp_old || !d_values ||
+        !d_returns || !d_stats4 || !d_row_index || !d_ret_sums || !d_epoch_stats || n_index < 1 ||
+        !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.n_agents, H = h->cfg.hidden;
+    const NetLayout &LA = h->la, &LC = h->lc;
+    const long long *idx = reinterpret_cast<const long long *>(d_row_index);
+    int rc;
+    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_ret_sums, n_index_global, d_epoch_stats, s)))
+        return rc;
+    const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
+    const PpoLossParams P = loss_params(h, n_index_global);
+    const long RA = (long)h->chunk_rows * N;     // agent rows the actor scratch holds
+    for (long k0 = 0; k0 < n_index; k0 += RA) {
+        const int nk = (int)std::min<long>(RA, n_index - k0);
+        // actor on the minibatch's agent rows, observation rows gathered through the permutation
+        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, idx + k0, 1))) return rc;
+        actor_head_kernel<<<grid_for_rows(h, nk, 8), 256, 0, s>>>(h->h2, actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
+                                                                 const_cast<float *>(d_actions), h->mu, h->logp, nk, H, 1, 0,
+                                                                 0, 0, 0, idx + k0);
+        h->launches++;
+        ppo_policy_loss_mb_kernel<<<(nk + 127) / 128, 128, 0, s>>>(h->mu, h->logp, d_actions, actor + LA.logstd, d_logp_old,
+                                                                  d_returns, d_values, vn_snapshot(h), d_stats4, n_rows_global,
+                                                                  idx + k0, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nk, P);
+        h->launches++;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nk, s))) return rc;
+        // critic as the reference evaluates it here: one centralised row PER AGENT ROW of the minibatch (the N agent
+        // rows of an env step land in different minibatches, so the once-per-env shortcut does not apply)
+        for (long c0 = 0; c0 < nk; c0 += h->chunk_rows) {
+            const int nc = (int)std::min<long>(h->chunk_rows, nk - c0);
+            const long long *ci = idx + k0 + c0;
+            if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, ci, N))) return rc;
+            critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
+            h->launches++;
+            ppo_value_loss_kernel<<<(nc + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats,
+                                                                  nc, P, ci);
+            h->launches++;
+            if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nc, s))) return rc;
+        }
     }
     if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
     if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
@@ -594,7 +693,7 @@ int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float 
     const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
     const float bc2s = (float)sqrt(1.0 - pow((double)b2, (double)step));
     clip_adam_kernel<<<blocks, 256, 0, s>>>(params, grads, adam_m, adam_v, L.total, sq, h->cfg.max_grad_norm, lr, b1, b2,
-                                            h->cfg.opti_eps, bc1, bc2s, 1.0f);
+                                            h->cfg.opti_eps, bc1, bc2s, 1.0f, h->cfg.use_max_grad_norm, h->cfg.weight_decay);
     h->launches += 2;
     if (d_grad_norm_sq_out) DCC_CUDA_TRY(cudaMemcpyAsync(d_grad_norm_sq_out, sq, sizeof(double), cudaMemcpyDeviceToDevice, s));
     DCC_CUDA_TRY(cudaGetLastError());

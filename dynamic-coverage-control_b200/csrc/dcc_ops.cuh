@@ -125,11 +125,15 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // dX GEMM of layer 1 from the backward pass altogether (ln0_finalize_kernel).
 // The output rows have leading dimension ldo >= F; the pad columns are zero-filled (the tensor-core GEMMs read K in
 // multiples of 32).
-__global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo) {
+// ridx (optional, minibatch path): output row r is computed from source row ridx[r] / rdiv (agent-row indices of a
+// permutation; rdiv = N maps them to centralised rows for the critic).
+__global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo,
+                                       const long long *__restrict__ ridx, int rdiv) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        const float *xr = x + (size_t)r * F;
+        const size_t sr = ridx ? (size_t)(ridx[r] / rdiv) : (size_t)r;
+        const float *xr = x + sr * F;
         float s = 0.f;
         for (int c = lane; c < F; c += 32) s += xr[c];
         const float mean = warp_sum_f(s) / (float)F;
@@ -144,12 +148,14 @@ __global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__res
 // Same, for rows that are 16-byte aligned and short enough to live in registers (F % 4 == 0, F <= 128 * NV): one
 // global read pass with 16-byte loads, NV float4 per lane (the critic's centralised input: F = N*D = 2704 -> NV = 22).
 template <int NV>
-__global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo) {
+__global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo,
+                                           const long long *__restrict__ ridx, int rdiv) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int F4 = F >> 2, L4 = ldo >> 2;
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)r * F);
+        const size_t sr = ridx ? (size_t)(ridx[r] / rdiv) : (size_t)r;
+        const float4 *xr = reinterpret_cast<const float4 *>(x + sr * F);
         float4 v[NV];
         float s = 0.f;
 #pragma unroll
@@ -435,7 +441,7 @@ __device__ __forceinline__ float2 normal_pair(uint64_t seed, uint64_t offset, ui
 __global__ void actor_head_kernel(const float *__restrict__ h, const float *__restrict__ Wm, const float *__restrict__ bm,
                                   const float *__restrict__ logstd, float *__restrict__ actions, float *__restrict__ mu_out,
                                   float *__restrict__ logp_out, int rows, int H, int mode, int deterministic, uint64_t seed,
-                                  uint64_t offset, uint64_t row_base) {
+                                  uint64_t offset, uint64_t row_base, const long long *__restrict__ ridx = nullptr) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const float ls0 = logstd[0], ls1 = logstd[1];
@@ -459,7 +465,8 @@ __global__ void actor_head_kernel(const float *__restrict__ h, const float *__re
                 }
                 actions[(size_t)r * 2 + 0] = a0; actions[(size_t)r * 2 + 1] = a1;
             } else {
-                a0 = actions[(size_t)r * 2 + 0]; a1 = actions[(size_t)r * 2 + 1];
+                const size_t ar = ridx ? (size_t)ridx[r] : (size_t)r;   // minibatch path: the given actions are gathered
+                a0 = actions[ar * 2 + 0]; a1 = actions[ar * 2 + 1];
             }
             if (mu_out) { mu_out[(size_t)r * 2 + 0] = s0; mu_out[(size_t)r * 2 + 1] = s1; }
             const float d0 = a0 - s0, d1 = a1 - s1;
@@ -485,7 +492,9 @@ __global__ void critic_head_kernel(const float *__restrict__ h, const float *__r
 }
 
 // ---- ValueNorm helpers (utils/valuenorm.py:32-36): state = {running_mean, running_mean_sq, debiasing_term} ----
+// vn == nullptr: no value normaliser (use_valuenorm = false, mappo.py:100-101) -> identity.
 __device__ __forceinline__ void vn_mean_std(const float *vn, float &mean, float &stdv) {
+    if (!vn) { mean = 0.f; stdv = 1.f; return; }
     const float c = fmaxf(vn[2], 1e-5f);
     mean = vn[0] / c;
     const float var = fmaxf(vn[1] / c - mean * mean, 1e-2f);
@@ -503,10 +512,22 @@ __global__ void rollout_insert_kernel(const float *__restrict__ rew_in, const ui
 
 // GAE over the rollout (shared_buffer.py:199-208): one thread per env, backwards in time, arrays [T(+1), E]
 // (coalesced over envs); masks cut the recurrence at episode ends (the "segments").
+// use_gae == 0: plain discounted returns, bootstrapped from the RAW (not denormalised) next value, exactly as
+// shared_buffer.py:209-212 does: returns[T] = next_value; returns[t] = returns[t+1] * gamma * masks[t+1] + rewards[t].
 __global__ void gae_kernel(const float *__restrict__ rew, const float *__restrict__ val, const float *__restrict__ masks,
-                           const float *__restrict__ vn, float *__restrict__ ret, int T, int E, float gamma, float lam) {
+                           const float *__restrict__ vn, float *__restrict__ ret, int T, int E, float gamma, float lam,
+                           int use_gae) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
+    if (!use_gae) {
+        float r = val[(size_t)T * E + e];
+        ret[(size_t)T * E + e] = r;
+        for (int t = T - 1; t >= 0; --t) {
+            r = __fadd_rn(__fmul_rn(__fmul_rn(r, gamma), masks[(size_t)(t + 1) * E + e]), rew[(size_t)t * E + e]);
+            ret[(size_t)t * E + e] = r;
+        }
+        return;
+    }
     float mean, sd;
     vn_mean_std(vn, mean, sd);
     float gae = 0.f;
@@ -522,13 +543,16 @@ __global__ void gae_kernel(const float *__restrict__ rew, const float *__restric
 }
 
 // sums[0] += sum(x), sums[1] += sum(x^2) in float64 (advantage statistics, ValueNorm batch statistics)
+// ridx (optional): element i is x[ridx[i] / rdiv] (the returns of a minibatch's agent rows).
 __global__ void sum_sumsq_kernel(const float *__restrict__ x, const float *__restrict__ sub, const float *__restrict__ vn,
-                                 double *__restrict__ sums, size_t n) {
+                                 double *__restrict__ sums, size_t n, const long long *__restrict__ ridx = nullptr,
+                                 int rdiv = 1) {
     // value = x[i] - (sub ? denormalize(sub[i]) : 0)
     float mean = 0.f, sd = 1.f;
     if (sub) vn_mean_std(vn, mean, sd);
     double s = 0.0, q = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = ridx ? (size_t)(ridx[k] / rdiv) : k;
         const float v = sub ? x[i] - (sub[i] * sd + mean) : x[i];
         s += v; q += (double)v * v;
     }
@@ -550,8 +574,9 @@ __global__ void vn_update_kernel(float *vn, const double *sums, double n, float 
 }
 
 struct PpoLossParams {
-    float clip, huber_delta, value_coef, inv_rows;  // inv_rows = 1 / (total rows B of the WHOLE batch)
+    float clip, huber_delta, value_coef, inv_rows;  // inv_rows = 1 / (agent rows of the whole (mini)batch, all ranks)
     int n_agents;
+    int use_huber, use_clipped;                     // mappo.yaml use_huber_loss / use_clipped_value_loss
 };
 
 // Fused PPO loss forward + backward for one chunk (algos/mappo.py:133-169 with cal_value_loss :103-131), split into
@@ -565,6 +590,33 @@ __device__ __forceinline__ float normalized_adv(const float *ret, const float *v
     const double am = adv_stats[0] / n_adv;
     const double avar = fmax(adv_stats[1] / n_adv - am * am, 0.0);
     return (float)(((double)(ret[r] - (v_old[r] * gs + gm)) - am) / (sqrt(avar) + 1e-5));
+}
+
+// per-agent-row policy term (mappo.py:150-163): returns dlogp; accumulates the loss / ratio sums
+__device__ __forceinline__ float ppo_policy_row(float logp_new, float logp_old, float adv, const PpoLossParams &P, float &pl,
+                                                float &rs) {
+    const float ratio = expf(logp_new - logp_old);
+    const float s1 = ratio * adv;
+    const float s2 = fminf(fmaxf(ratio, 1.f - P.clip), 1.f + P.clip) * adv;
+    pl += -2.f * fminf(s1, s2);  // two equal log-prob columns (shared_buffer.py:61-62): the loss is 2x
+    rs += ratio;
+    const bool inrange = (ratio >= 1.f - P.clip) && (ratio <= 1.f + P.clip);
+    const float dmin = inrange ? adv : ((s1 < s2) ? adv : 0.f);   // torch.min / clamp sub-gradients
+    return -2.f * P.inv_rows * dmin * ratio;
+}
+
+__device__ __forceinline__ void ppo_policy_reduce(float pl, float rs, float dls0, float dls1, double *stats, float *dlogstd) {
+    double a = pl, c = rs;
+    float e0 = dls0, e1 = dls1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL_MASK, a, o); c += __shfl_xor_sync(FULL_MASK, c, o);
+        e0 += __shfl_xor_sync(FULL_MASK, e0, o); e1 += __shfl_xor_sync(FULL_MASK, e1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], a); atomicAdd(&stats[2], c);
+        atomicAdd(&dlogstd[0], e0); atomicAdd(&dlogstd[1], e1);
+    }
 }
 
 // policy part: writes dmu [rows*N,2]; accumulates dlogstd[2] and stats {0: policy_loss_sum, 2: ratio_sum} over agent rows
@@ -583,14 +635,7 @@ __global__ void ppo_policy_loss_kernel(const float *__restrict__ mu, const float
         const float iv0 = 1.f / (sd0 * sd0), iv1 = 1.f / (sd1 * sd1);
         for (int n = 0; n < N; ++n) {
             const size_t i = (size_t)r * N + n;
-            const float ratio = expf(logp_new[i] - logp_old[i]);
-            const float s1 = ratio * adv;
-            const float s2 = fminf(fmaxf(ratio, 1.f - P.clip), 1.f + P.clip) * adv;
-            pl += -2.f * fminf(s1, s2);  // two equal log-prob columns (shared_buffer.py:61-62): the loss is 2x
-            rs += ratio;
-            const bool inrange = (ratio >= 1.f - P.clip) && (ratio <= 1.f + P.clip);
-            const float dmin = inrange ? adv : ((s1 < s2) ? adv : 0.f);   // torch.min / clamp sub-gradients
-            const float dlogp = -2.f * P.inv_rows * dmin * ratio;
+            const float dlogp = ppo_policy_row(logp_new[i], logp_old[i], adv, P, pl, rs);
             const float d0 = actions[i * 2 + 0] - mu[i * 2 + 0], d1 = actions[i * 2 + 1] - mu[i * 2 + 1];
             dmu[i * 2 + 0] = dlogp * d0 * iv0;
             dmu[i * 2 + 1] = dlogp * d1 * iv1;
@@ -598,45 +643,72 @@ __global__ void ppo_policy_loss_kernel(const float *__restrict__ mu, const float
             dls1 = fmaf(dlogp, d1 * d1 * iv1 - 1.f, dls1);
         }
     }
-    double a = pl, c = rs;
-    float e0 = dls0, e1 = dls1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(FULL_MASK, a, o); c += __shfl_xor_sync(FULL_MASK, c, o);
-        e0 += __shfl_xor_sync(FULL_MASK, e0, o); e1 += __shfl_xor_sync(FULL_MASK, e1, o);
+    ppo_policy_reduce(pl, rs, dls0, dls1, stats, dlogstd);
+}
+
+// minibatch variant (num_mini_batch > 1, shared_buffer.py:219-279): one thread per agent row k of the minibatch;
+// ridx[k] = agent-row index into the rollout (actions, logp_old), ridx[k] / N = env-step row (returns, values);
+// mu / logp_new / dmu are chunk-local (row k).  ret / v_old / actions / logp_old point at the rollout's row 0.
+__global__ void ppo_policy_loss_mb_kernel(const float *__restrict__ mu, const float *__restrict__ logp_new,
+                                          const float *__restrict__ actions, const float *__restrict__ logstd,
+                                          const float *__restrict__ logp_old, const float *__restrict__ ret,
+                                          const float *__restrict__ v_old, const float *__restrict__ vn_gae,
+                                          const double *__restrict__ adv_stats, double n_adv,
+                                          const long long *__restrict__ ridx, float *__restrict__ dmu,
+                                          float *__restrict__ dlogstd, double *__restrict__ stats, int rows, PpoLossParams P) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float pl = 0.f, rs = 0.f, dls0 = 0.f, dls1 = 0.f;
+    if (k < rows) {
+        const size_t a = (size_t)ridx[k];
+        const float adv = normalized_adv(ret, v_old, vn_gae, adv_stats, n_adv, (int)(a / P.n_agents));
+        const float sd0 = expf(logstd[0]), sd1 = expf(logstd[1]);
+        const float iv0 = 1.f / (sd0 * sd0), iv1 = 1.f / (sd1 * sd1);
+        const float dlogp = ppo_policy_row(logp_new[k], logp_old[a], adv, P, pl, rs);
+        const float d0 = actions[a * 2 + 0] - mu[(size_t)k * 2 + 0], d1 = actions[a * 2 + 1] - mu[(size_t)k * 2 + 1];
+        dmu[(size_t)k * 2 + 0] = dlogp * d0 * iv0;
+        dmu[(size_t)k * 2 + 1] = dlogp * d1 * iv1;
+        dls0 = dlogp * (d0 * d0 * iv0 - 1.f);
+        dls1 = dlogp * (d1 * d1 * iv1 - 1.f);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats[0], a); atomicAdd(&stats[2], c);
-        atomicAdd(&dlogstd[0], e0); atomicAdd(&dlogstd[1], e1);
-    }
+    ppo_policy_reduce(pl, rs, dls0, dls1, stats, dlogstd);
 }
 
 // value part: writes dv [rows]; accumulates stats[1] = value_loss_sum over agent rows.  vn_now = ValueNorm state
-// AFTER this epoch's update (cal_value_loss updates before normalising, mappo.py:107-109).
+// AFTER this epoch's update (cal_value_loss updates before normalising, mappo.py:107-109); nullptr = no normaliser.
+// Whole-rollout path (ridx == nullptr): row r is an env-step row standing for its N identical agent rows (weight N).
+// Minibatch path: row k is ONE agent row; ret / v_old are read at env-step row ridx[k] / N, weight 1.
 __global__ void ppo_value_loss_kernel(const float *__restrict__ ret, const float *__restrict__ v_old,
                                       const float *__restrict__ v_new, const float *__restrict__ vn_now,
-                                      float *__restrict__ dv, double *__restrict__ stats, int rows, PpoLossParams P) {
+                                      float *__restrict__ dv, double *__restrict__ stats, int rows, PpoLossParams P,
+                                      const long long *__restrict__ ridx = nullptr) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     float vl = 0.f;
     if (r < rows) {
-        const int N = P.n_agents;
+        const size_t er = ridx ? (size_t)(ridx[r] / P.n_agents) : (size_t)r;
+        const float wgt = ridx ? 1.f : (float)P.n_agents;
         float nm, ns;
         vn_mean_std(vn_now, nm, ns);
-        const float nret = (ret[r] - nm) / ns;
-        const float v = v_new[r], vo = v_old[r];
+        const float nret = (ret[er] - nm) / ns;
+        const float v = v_new[r], vo = v_old[er];
         const float e = nret - v;
         const float ec = nret - (vo + fminf(fmaxf(v - vo, -P.clip), P.clip));
         const float d = P.huber_delta;
-        // one-sided Huber, as the reference computes it (utils/util.py:36-39): zero for e < -d
-        const float h = (fabsf(e) <= d ? e * e * 0.5f : 0.f) + (e > d ? d * (fabsf(e) - 0.5f * d) : 0.f);
-        const float hc = (fabsf(ec) <= d ? ec * ec * 0.5f : 0.f) + (ec > d ? d * (fabsf(ec) - 0.5f * d) : 0.f);
-        const float dh = (fabsf(e) <= d ? e : 0.f) + (e > d ? d : 0.f);
-        const float dhc = (fabsf(ec) <= d ? ec : 0.f) + (ec > d ? d : 0.f);
-        const float w1 = h > hc ? 1.f : (h < hc ? 0.f : 0.5f);           // torch.max splits ties evenly
+        float h, hc, dh, dhc;
+        if (P.use_huber) {
+            // one-sided Huber, as the reference computes it (utils/util.py:36-39): zero for e < -d
+            h = (fabsf(e) <= d ? e * e * 0.5f : 0.f) + (e > d ? d * (fabsf(e) - 0.5f * d) : 0.f);
+            hc = (fabsf(ec) <= d ? ec * ec * 0.5f : 0.f) + (ec > d ? d * (fabsf(ec) - 0.5f * d) : 0.f);
+            dh = (fabsf(e) <= d ? e : 0.f) + (e > d ? d : 0.f);
+            dhc = (fabsf(ec) <= d ? ec : 0.f) + (ec > d ? d : 0.f);
+        } else {   // mse_loss = e^2 / 2 (utils/util.py:42-43)
+            h = e * e * 0.5f; hc = ec * ec * 0.5f; dh = e; dhc = ec;
+        }
+        float w1 = 1.f;                                                   // use_clipped_value_loss = false: original only
+        if (P.use_clipped) w1 = h > hc ? 1.f : (h < hc ? 0.f : 0.5f);     // torch.max splits ties evenly
         const float inv = (fabsf(v - vo) <= P.clip) ? 1.f : 0.f;          // clamp passes gradient inside the range
-        vl = (float)N * fmaxf(h, hc);
-        // N identical agent rows per env step: gradient = N * per-row term / B
-        dv[r] = (w1 * (-dh) + (1.f - w1) * (-dhc) * inv) * P.inv_rows * (float)N * P.value_coef;
+        vl = wgt * (P.use_clipped ? fmaxf(h, hc) : h);
+        // whole-rollout path: N identical agent rows per env step, gradient = N * per-row term / B
+        dv[r] = (w1 * (-dh) + (1.f - w1) * (-dhc) * inv) * P.inv_rows * wgt * P.value_coef;
     }
     double b = vl;
 #pragma unroll
@@ -654,16 +726,19 @@ __global__ void sumsq_kernel(const float *__restrict__ g, size_t n, double *__re
     if ((threadIdx.x & 31) == 0) atomicAdd(out, q);
 }
 
-// clip_grad_norm_(max_norm) + Adam step (torch.optim.Adam, no weight decay / amsgrad), fused over the flat buffer.
+// clip_grad_norm_(max_norm) + Adam step (torch.optim.Adam with optional L2 weight decay, no amsgrad), fused over the flat buffer.
 // sumsq = squared global grad norm of this net (after the cross-GPU all-reduce, if any).
 __global__ void clip_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                  float *__restrict__ v, size_t n, const double *__restrict__ sumsq, float max_norm, float lr,
-                                 float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                 float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale, int do_clip,
+                                 float weight_decay) {
     const float total = (float)sqrt(*sumsq) * grad_scale;
-    const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * grad_scale;
+    // use_max_grad_norm = false (mappo.py:179-181): the norm is only reported, the gradients are applied unscaled
+    const float coef = (do_clip ? fminf(max_norm / (total + 1e-6f), 1.0f) : 1.0f) * grad_scale;
     const float step = lr / bc1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
+        float gi = g[i] * coef;
+        if (weight_decay != 0.f) gi = fmaf(weight_decay, p[i], gi);   // torch.optim.Adam: grad = grad + weight_decay * param
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;

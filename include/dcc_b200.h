@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 1
+#define DCC_ABI_VERSION 2
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -186,7 +186,7 @@ typedef struct dcc_mappo_cfg {
     int32_t obs_dim;         /* D (actor input); the critic input is N*D */
     int32_t hidden;          /* algo_hidden_size, <= 256 (mappo.yaml: 256) */
     int32_t act_dim;         /* 2 (Box(2), environment.py:52) */
-    int32_t chunk_rows;      /* env-step rows per activation chunk; 0 = auto (~1.5 GB of scratch) */
+    int32_t chunk_rows;      /* env-step rows per activation chunk; 0 = auto (~2.5 GB of scratch, whole 148-SM waves for both nets) */
     int32_t gemm_backend;    /* 0 = auto, 1 = SIMT fp32 FFMA, 2 = tcgen05 3xTF32 (hidden == 256 only) */
     float clip_param;        /* 0.2     mappo.yaml */
     float entropy_coef;      /* 0.01 */
@@ -199,6 +199,15 @@ typedef struct dcc_mappo_cfg {
     float adam_beta1;        /* 0.9 */
     float adam_beta2;        /* 0.999 */
     double vn_beta;          /* 0.99999 valuenorm.py:11 (double: torch forms 1.0 - beta in double before the float32 op) */
+    /* mappo.yaml switches of the update path (0 / 1; dcc_mappo_cfg_default sets the shipped values) */
+    int32_t use_huber_loss;          /* 1: one-sided Huber (util.py:36-39); 0: mse_loss = e^2/2 (util.py:42-43)   mappo.py:113-118 */
+    int32_t use_clipped_value_loss;  /* 1: max(original, clipped); 0: original only                               mappo.py:120-123 */
+    int32_t use_max_grad_norm;       /* 1: clip_grad_norm_(max_grad_norm); 0: norm reported, gradients unscaled   mappo.py:176-181 */
+    int32_t use_valuenorm;           /* 1: ValueNorm on returns; 0: value_normalizer = None (raw returns)         mappo.py:96-101 */
+    int32_t use_gae;                 /* 1: GAE; 0: discounted returns bootstrapped from the RAW next value        shared_buffer.py:199-212 */
+    int32_t reserved1;
+    float weight_decay;              /* 0: torch.optim.Adam L2 term, grad += weight_decay * param (after the clip) mappo.py:30-37 */
+    float reserved2;
 } dcc_mappo_cfg;
 
 int dcc_mappo_cfg_default(dcc_mappo_cfg *cfg);
@@ -246,6 +255,8 @@ int dcc_rollout_insert(const float *d_rew_in, const uint8_t *d_done_in, int n_en
  * ValueNorm.denormalize folded in (valuenorm.py:68-79).
  *   d_rewards [T,E], d_values [T+1,E] (d_values[T] = bootstrap value), d_masks [T+1,E], d_vn_state[3]
  *   -> d_returns [T+1,E] (rows 0..T-1 written)
+ * cfg.use_gae = 0 selects the discounted-return branch (:209-212; row T = the raw bootstrap value is written too);
+ * cfg.use_valuenorm = 0 drops the denormalisation (d_vn_state may then be NULL, here and in the calls below).
  */
 int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, const float *d_masks,
                   const float *d_vn_state, int T, int E, float *d_returns, dcc_stream_t stream);
@@ -276,6 +287,30 @@ int dcc_mappo_epoch_grads(void *handle, const float *d_actor, const float *d_cri
                           float *d_grad_critic, const float *d_obs, const float *d_actions, const float *d_logp_old,
                           const float *d_values, const float *d_returns, float *d_vn_state, const double *d_stats4,
                           double n_rows_global, int T, int E, double *d_epoch_stats, dcc_stream_t stream);
+
+/*
+ * num_mini_batch > 1 — SharedReplayBuffer.feed_forward_generator (buffer/shared_buffer.py:219-279) + ppo_update
+ * (algos/mappo.py:133-187) for ONE minibatch.  The reference draws `torch.randperm(T*E*N)` over AGENT rows
+ * (row = (t*E + e)*N + n) once per epoch and cuts it into num_mini_batch equal index lists; the caller passes one
+ * such list (device int64, `n_index` entries; in a multi-GPU job: this rank's share).  Rows are gathered on the
+ * fly — observations through the index inside the input-LayerNorm kernel, per-row scalars inside the loss kernels —
+ * so no minibatch copy of the rollout is ever materialised.  The critic is evaluated per agent row here, as the
+ * reference does (the N agent rows of an env step fall into different minibatches).
+ *   dcc_mappo_minibatch_stats   d_ret_sums_out[2] = {sum, sum of squares} of the returns of the indexed rows: the
+ *                               batch statistics ValueNorm.update(return_batch) needs (mappo.py:107); all-reduce
+ *                               (SUM) across ranks before the next call
+ *   dcc_mappo_minibatch_grads   as dcc_mappo_epoch_grads on the indexed rows.  n_rows_global = global T*E (the
+ *                               advantage statistics in d_stats4 stay those of the WHOLE rollout, mappo.py:189-198);
+ *                               n_index_global = global agent rows of this minibatch (the loss denominators)
+ */
+int dcc_mappo_minibatch_stats(void *handle, const float *d_returns, const int64_t *d_row_index, int64_t n_index,
+                              double *d_ret_sums_out, dcc_stream_t stream);
+int dcc_mappo_minibatch_grads(void *handle, const float *d_actor, const float *d_critic, float *d_grad_actor,
+                              float *d_grad_critic, const float *d_obs, const float *d_actions, const float *d_logp_old,
+                              const float *d_values, const float *d_returns, float *d_vn_state, const double *d_stats4,
+                              double n_rows_global, const int64_t *d_row_index, int64_t n_index,
+                              const double *d_ret_sums, double n_index_global, double *d_epoch_stats,
+                              dcc_stream_t stream);
 
 /*
  * clip_grad_norm_(max_grad_norm) + torch.optim.Adam.step for one net (algos/mappo.py:176-185), fused over the

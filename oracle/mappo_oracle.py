@@ -7,10 +7,13 @@ It restates, in float64 NumPy with hand-written backward passes (paths relative 
   actor / critic forward      algos/r_actor_critic.py:43-57,111-121 -> algos/algo_utils/mlp.py:25-29,52-58
                               -> algos/algo_utils/act.py:79-84,165-184 -> distributions.py:33-41,83-92
   ValueNorm                   utils/valuenorm.py:32-79
-  GAE returns                 buffer/shared_buffer.py:199-208
+  GAE / discounted returns    buffer/shared_buffer.py:154-212 (use_gae, with / without a value normaliser)
   advantage normalisation     algos/mappo.py:189-198
-  PPO update (all quirks)     algos/mappo.py:103-187, utils/util.py:36-39 (one-sided Huber)
-  grad clip + Adam            torch.nn.utils.clip_grad_norm_ / torch.optim.Adam as called at algos/mappo.py:176-185
+  PPO update (all quirks)     algos/mappo.py:103-187, utils/util.py:36-43 (one-sided Huber / mse), with the
+                              mappo.yaml switches use_huber_loss, use_clipped_value_loss, use_max_grad_norm,
+                              use_valuenorm, weight_decay
+  minibatches                 buffer/shared_buffer.py:219-279 (num_mini_batch index lists cut from a permutation)
+  grad clip + Adam            torch.nn.utils.clip_grad_norm_ / torch.optim.Adam as called at algos/mappo.py:30-37,176-185
 
 Pinned by tests/test_oracle_mappo.py against tests/golden/mappo_*.npz, which tests/golden/make_golden_mappo.py
 produced by running the UNMODIFIED reference learner (float32 torch) in the build container: forward values /
@@ -136,10 +139,19 @@ class ValueNorm:
 
 
 # ---- GAE (buffer/shared_buffer.py:199-208) ----------------------------------------------------------------
-def gae_returns(rewards, value_preds, masks, vn, gamma=0.99, lam=0.95):
-    """rewards (T,...), value_preds (T+1,...) with value_preds[T] = next value (normalised units), masks (T+1,...)."""
+def gae_returns(rewards, value_preds, masks, vn, gamma=0.99, lam=0.95, use_gae=True):
+    """rewards (T,...), value_preds (T+1,...) with value_preds[T] = next value (normalised units), masks (T+1,...).
+    vn None = no value normaliser.  use_gae False = shared_buffer.py:209-212: discounted returns bootstrapped from
+    the RAW next value (returns[T] = next_value, never denormalised)."""
     T = rewards.shape[0]
-    den = vn.denormalize(value_preds)
+    vp = np.asarray(value_preds, dtype=np.float64)
+    if not use_gae:
+        ret = np.zeros_like(vp)
+        ret[T] = vp[T]
+        for t in reversed(range(T)):
+            ret[t] = ret[t + 1] * gamma * masks[t + 1] + rewards[t]
+        return ret
+    den = vn.denormalize(vp) if vn is not None else vp
     ret = np.zeros_like(den)
     gae = 0.0
     for t in reversed(range(T)):
@@ -155,11 +167,15 @@ def huber(e, d):
     return a * e ** 2 / 2 + b * d * (np.abs(e) - d / 2), a * e + b * d
 
 
-class Adam:
-    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps, weight_decay=0) over a dict of float64 arrays."""
+def mse(e):
+    return e ** 2 / 2, e
 
-    def __init__(self, params, eps=1e-5, b1=0.9, b2=0.999):
-        self.p, self.eps, self.b1, self.b2 = params, eps, b1, b2
+
+class Adam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps, weight_decay) over a dict of float64 arrays."""
+
+    def __init__(self, params, eps=1e-5, b1=0.9, b2=0.999, weight_decay=0.0):
+        self.p, self.eps, self.b1, self.b2, self.wd = params, eps, b1, b2, weight_decay
         self.m = {k: np.zeros_like(v) for k, v in params.items()}
         self.v = {k: np.zeros_like(v) for k, v in params.items()}
         self.t = 0
@@ -168,79 +184,106 @@ class Adam:
         self.t += 1
         bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
         for k, g in grads.items():
+            if self.wd:
+                g = g + self.wd * self.p[k]
             self.m[k] = self.b1 * self.m[k] + (1 - self.b1) * g
             self.v[k] = self.b2 * self.v[k] + (1 - self.b2) * g * g
             self.p[k] -= (lr / bc1) * self.m[k] / (np.sqrt(self.v[k]) / np.sqrt(bc2) + self.eps)
 
 
-def clip_grads(grads, max_norm):
+def clip_grads(grads, max_norm, do_clip=True):
     total = float(np.sqrt(sum((g.astype(np.float64) ** 2).sum() for g in grads.values())))
-    coef = min(max_norm / (total + 1e-6), 1.0)
+    coef = min(max_norm / (total + 1e-6), 1.0) if do_clip else 1.0   # get_gard_norm only reports (mappo.py:179-181)
     for k in grads:
         grads[k] = grads[k] * coef
     return total
 
 
 class Trainer:
-    """MAPPOTrainer.train on a recorded rollout buffer (algos/mappo.py:189-227), one minibatch = all rows."""
+    """MAPPOTrainer.train on a recorded rollout buffer (algos/mappo.py:189-227).  hp may carry the mappo.yaml
+    switches use_huber_loss / use_clipped_value_loss / use_max_grad_norm / use_valuenorm (default True),
+    weight_decay (0) and num_mini_batch (1)."""
 
     def __init__(self, actor_params, critic_params, hp, vn_state=(0.0, 0.0, 0.0)):
         self.actor, self.critic = make_actor(actor_params), make_critic(critic_params)
         self.hp = hp
-        self.vn = ValueNorm(vn_state)
-        self.opt_a = Adam(self.actor.p, eps=hp["opti_eps"])
-        self.opt_c = Adam(self.critic.p, eps=hp["opti_eps"])
+        self.vn = ValueNorm(vn_state) if hp.get("use_valuenorm", True) else None
+        wd = float(hp.get("weight_decay", 0.0))
+        self.opt_a = Adam(self.actor.p, eps=hp["opti_eps"], weight_decay=wd)
+        self.opt_c = Adam(self.critic.p, eps=hp["opti_eps"], weight_decay=wd)
 
-    def train(self, obs, actions, logp_old, value_preds, returns, lr, ppo_epoch):
-        """obs (T+1,E,N,D); actions (T,E,N,2); logp_old (T,E,N,1); value_preds/returns (T+1,E,N,1)."""
+    def train(self, obs, actions, logp_old, value_preds, returns, lr, ppo_epoch, perms=None):
+        """obs (T+1,E,N,D); actions (T,E,N,2); logp_old (T,E,N,1); value_preds/returns (T+1,E,N,1).
+        perms (num_mini_batch > 1): per epoch, the permutation of the T*E*N agent rows the generator drew."""
         hp = self.hp
         T, E, N = actions.shape[:3]
         B = T * E * N
         c = hp["clip_param"]
-        adv = returns[:-1].astype(np.float64) - self.vn.denormalize(value_preds[:-1])
+        nmb = int(hp.get("num_mini_batch", 1))
+        vp = value_preds[:-1].astype(np.float64)
+        adv = returns[:-1].astype(np.float64) - (self.vn.denormalize(vp) if self.vn is not None else vp)
         adv = (adv - adv.mean()) / (adv.std() + 1e-5)
-        x = obs[:-1].reshape(B, -1).astype(np.float64)
-        sx = np.repeat(obs[:-1].reshape(T * E, 1, -1), N, axis=1).reshape(B, -1).astype(np.float64)
-        act = actions.reshape(B, -1).astype(np.float64)
-        lpo = logp_old.reshape(B, 1).astype(np.float64)
-        vold = value_preds[:-1].reshape(B, 1).astype(np.float64)
-        ret = returns[:-1].reshape(B, 1).astype(np.float64)
-        A = adv.reshape(B, 1)
+        x_all = obs[:-1].reshape(B, -1).astype(np.float64)
+        sx_all = np.repeat(obs[:-1].reshape(T * E, 1, -1), N, axis=1).reshape(B, -1).astype(np.float64)
+        act_all = actions.reshape(B, -1).astype(np.float64)
+        lpo_all = logp_old.reshape(B, 1).astype(np.float64)
+        vold_all = value_preds[:-1].reshape(B, 1).astype(np.float64)
+        ret_all = returns[:-1].reshape(B, 1).astype(np.float64)
+        A_all = adv.reshape(B, 1)
+        loss_fn = (lambda e: huber(e, hp["huber_delta"])) if hp.get("use_huber_loss", True) else mse
+        clipped = hp.get("use_clipped_value_loss", True)
         info = dict(value_loss=0.0, policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, critic_grad_norm=0.0,
                     ratio=0.0)
-        for _ in range(ppo_epoch):
-            mean = self.actor.forward(x)
-            logstd = self.actor.p["act.action_out.logstd._bias"].reshape(1, -1)
-            logp, ent = gaussian_logp_entropy(mean, logstd, act)
-            v = self.critic.forward(sx)
-            ratio = np.exp(logp - lpo)
-            s1, s2 = ratio * A, np.clip(ratio, 1 - c, 1 + c) * A
-            policy_loss = -(2.0 * np.minimum(s1, s2)).mean()    # 2 equal log-prob columns (shared_buffer.py:61-62)
-            inrange = (ratio >= 1 - c) & (ratio <= 1 + c)
-            dmin = np.where(inrange, A, np.where(s1 < s2, A, 0.0))
-            dlogp = -(2.0 / B) * dmin * ratio
-            # value loss (cal_value_loss, mappo.py:103-131): ValueNorm.update first
-            self.vn.update(ret)
-            nret = self.vn.normalize(ret)
-            e, dvc = nret - v, np.clip(v - vold, -c, c)
-            e_c = nret - (vold + dvc)
-            h, dh = huber(e, hp["huber_delta"])
-            h_c, dh_c = huber(e_c, hp["huber_delta"])
-            value_loss = np.maximum(h, h_c).mean()
-            w1 = np.where(h > h_c, 1.0, np.where(h < h_c, 0.0, 0.5))
-            in_v = (np.abs(v - vold) <= c).astype(np.float64)
-            dv = (w1 * (-dh) + (1 - w1) * (-dh_c) * in_v) / B * hp["value_loss_coef"]
-            # actor backward
-            std2 = np.exp(2 * logstd)
-            dmean = dlogp * (act - mean) / std2
-            ga = self.actor.backward(dmean)
-            ga["act.action_out.logstd._bias"] = ((dlogp * ((act - mean) ** 2 / std2 - 1.0)).sum(0)
-                                                 - hp["entropy_coef"]).reshape(-1, 1)
-            gc = self.critic.backward(dv)
-            an = clip_grads(ga, hp["max_grad_norm"])
-            cn = clip_grads(gc, hp["max_grad_norm"])
-            self.opt_a.step(ga, lr)
-            self.opt_c.step(gc, lr)
-            info["value_loss"] += value_loss; info["policy_loss"] += policy_loss; info["dist_entropy"] += ent
-            info["actor_grad_norm"] += an; info["critic_grad_norm"] += cn; info["ratio"] += ratio.mean()
-        return {k: v / ppo_epoch for k, v in info.items()}
+        mbs = B // nmb
+        for ep in range(ppo_epoch):
+            for i in range(nmb):
+                if nmb == 1:
+                    sel = slice(None)      # a permutation of the whole batch only reorders the sums
+                    Bm = B
+                else:
+                    sel = np.asarray(perms[ep][i * mbs:(i + 1) * mbs], dtype=np.int64)
+                    Bm = mbs
+                x, sx, act, lpo, vold, ret, A = (a[sel] for a in (x_all, sx_all, act_all, lpo_all, vold_all, ret_all, A_all))
+                mean = self.actor.forward(x)
+                logstd = self.actor.p["act.action_out.logstd._bias"].reshape(1, -1)
+                logp, ent = gaussian_logp_entropy(mean, logstd, act)
+                v = self.critic.forward(sx)
+                ratio = np.exp(logp - lpo)
+                s1, s2 = ratio * A, np.clip(ratio, 1 - c, 1 + c) * A
+                policy_loss = -(2.0 * np.minimum(s1, s2)).mean()    # 2 equal log-prob columns (shared_buffer.py:61-62)
+                inrange = (ratio >= 1 - c) & (ratio <= 1 + c)
+                dmin = np.where(inrange, A, np.where(s1 < s2, A, 0.0))
+                dlogp = -(2.0 / Bm) * dmin * ratio
+                # value loss (cal_value_loss, mappo.py:103-131): ValueNorm.update first
+                if self.vn is not None:
+                    self.vn.update(ret)
+                    nret = self.vn.normalize(ret)
+                else:
+                    nret = ret
+                e, dvc = nret - v, np.clip(v - vold, -c, c)
+                e_c = nret - (vold + dvc)
+                h, dh = loss_fn(e)
+                h_c, dh_c = loss_fn(e_c)
+                if clipped:
+                    value_loss = np.maximum(h, h_c).mean()
+                    w1 = np.where(h > h_c, 1.0, np.where(h < h_c, 0.0, 0.5))
+                else:
+                    value_loss = h.mean()
+                    w1 = np.ones_like(h)
+                in_v = (np.abs(v - vold) <= c).astype(np.float64)
+                dv = (w1 * (-dh) + (1 - w1) * (-dh_c) * in_v) / Bm * hp["value_loss_coef"]
+                # actor backward
+                std2 = np.exp(2 * logstd)
+                dmean = dlogp * (act - mean) / std2
+                ga = self.actor.backward(dmean)
+                ga["act.action_out.logstd._bias"] = ((dlogp * ((act - mean) ** 2 / std2 - 1.0)).sum(0)
+                                                     - hp["entropy_coef"]).reshape(-1, 1)
+                gc = self.critic.backward(dv)
+                do_clip = hp.get("use_max_grad_norm", True)
+                an = clip_grads(ga, hp["max_grad_norm"], do_clip)
+                cn = clip_grads(gc, hp["max_grad_norm"], do_clip)
+                self.opt_a.step(ga, lr)
+                self.opt_c.step(gc, lr)
+                info["value_loss"] += value_loss; info["policy_loss"] += policy_loss; info["dist_entropy"] += ent
+                info["actor_grad_norm"] += an; info["critic_grad_norm"] += cn; info["ratio"] += ratio.mean()
+        return {k: v / (ppo_epoch * nmb) for k, v in info.items()}

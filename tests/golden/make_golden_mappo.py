@@ -27,7 +27,7 @@ from ref_harness import REF_ROOT, load_reference  # noqa: E402
 from mappo_util import actor_param_shapes, critic_param_shapes, make_params, sample_tensor  # noqa: E402
 
 
-def build_learner(N, M, E, T, hidden, ppo_epoch, seed, force_scale=0.0):
+def build_learner(N, M, E, T, hidden, ppo_epoch, seed, force_scale=0.0, extra=None):
     import torch
     ref = load_reference()
     cwd = os.getcwd()
@@ -47,6 +47,8 @@ def build_learner(N, M, E, T, hidden, ppo_epoch, seed, force_scale=0.0):
     cfg.update(num_agents=N, num_pois=M, n_rollout_threads=E, n_eval_rollout_threads=0, n_render_rollout_threads=0,
                max_ep_len=T, algo_hidden_size=hidden, ppo_epoch=ppo_epoch, log_wandb=False, save_model=False,
                seed=seed, comm_force_scale=force_scale)
+    if extra:
+        cfg.update(**extra)     # mappo.yaml switches of the update path, flipped exactly as a user would
     mk.SubprocVecEnv = ref["wrappers"].DummyVecEnv          # in-process fan-out, same auto-reset rule
     if (N, M) != (4, 20) or force_scale > 0:
         Gen = ref["GenScenario"]
@@ -70,13 +72,16 @@ def set_params(module, params):
 
 
 def vn_state(vn):
+    if vn is None:      # use_valuenorm: false
+        return np.zeros(3, dtype=np.float64)
     return np.array([float(vn.running_mean[0] if vn.running_mean.ndim else vn.running_mean),
                      float(vn.running_mean_sq[0] if vn.running_mean_sq.ndim else vn.running_mean_sq),
                      float(vn.debiasing_term)], dtype=np.float64)
 
 
-def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2):
-    lr, cfg = build_learner(N, M, E, T, hidden, ppo_epoch, seed)
+def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
+    import torch
+    lr, cfg = build_learner(N, M, E, T, hidden, ppo_epoch, seed, extra=extra)
     D = lr.obs_dim_n[0]
     a_shapes, c_shapes = actor_param_shapes(D, hidden), critic_param_shapes(N * D, hidden)
     set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
@@ -101,7 +106,21 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2):
         out[p + "vn_before"] = vn0
         out[p + "lr"] = np.array(lrate)
         out[p + "rollout_info"] = np.array([info["reward"], info["coverage_rate"]])
-        tinfo = lr.rl_update()
+        # harness-only: record the permutations feed_forward_generator draws (buffer/shared_buffer.py:238)
+        perms, real_randperm = [], torch.randperm
+
+        def recording_randperm(n, *a, **k):
+            r = real_randperm(n, *a, **k)
+            perms.append(r.numpy().copy())
+            return r
+        torch.randperm = recording_randperm
+        try:
+            tinfo = lr.rl_update()
+        finally:
+            torch.randperm = real_randperm
+        if int(cfg.num_mini_batch) > 1:
+            assert len(perms) == ppo_epoch
+            out[p + "perms"] = np.stack(perms).astype(np.int32)
         out[p + "train_info"] = np.array([float(tinfo[k]) for k in ("value_loss", "policy_loss", "dist_entropy",
                                                                     "actor_grad_norm", "critic_grad_norm", "ratio")])
         out[p + "vn_after"] = vn_state(lr.trainer.value_normalizer)
@@ -117,7 +136,11 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2):
                 iters=iters, obs_dim=D, actor_seed=seed * 2 + 1, critic_seed=seed * 2 + 2,
                 gamma=cfg.gamma, gae_lambda=cfg.gae_lambda, clip_param=cfg.clip_param, entropy_coef=cfg.entropy_coef,
                 value_loss_coef=cfg.value_loss_coef, max_grad_norm=cfg.max_grad_norm, huber_delta=cfg.huber_delta,
-                actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr, opti_eps=cfg.opti_eps, n_iters=cfg.n_iters)
+                actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr, opti_eps=cfg.opti_eps, n_iters=cfg.n_iters,
+                use_huber_loss=bool(cfg.use_huber_loss), use_clipped_value_loss=bool(cfg.use_clipped_value_loss),
+                use_max_grad_norm=bool(cfg.use_max_grad_norm), use_valuenorm=bool(cfg.use_valuenorm),
+                use_gae=bool(cfg.use_gae), use_proper_time_limits=bool(cfg.use_proper_time_limits),
+                weight_decay=float(cfg.weight_decay), num_mini_batch=int(cfg.num_mini_batch))
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "mappo_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -130,6 +153,14 @@ def main():
     run_case("ship_4x20_h256", 4, 20, 4, 30, 256, 15, seed=0)     # shipped shapes + hyper-parameters, short rollout
     run_case("gen_8x64_h64", 8, 64, 2, 12, 64, 4, seed=1)         # BASELINE shape, small hidden size
     run_case("gen_3x20_h32", 3, 20, 3, 10, 32, 3, seed=2)
+    # mappo.yaml switches of the update path (config-reachable branches of mappo.py / shared_buffer.py)
+    run_case("flags_mse_noclip_wd", 4, 20, 3, 10, 32, 3, seed=3,
+             extra=dict(use_huber_loss=False, use_clipped_value_loss=False, use_max_grad_norm=False, weight_decay=1e-3))
+    run_case("flags_novn_nogae", 4, 20, 3, 10, 32, 3, seed=4,
+             extra=dict(use_valuenorm=False, use_gae=False, use_proper_time_limits=True))
+    run_case("flags_novn_gae", 3, 20, 2, 9, 32, 2, seed=5, extra=dict(use_valuenorm=False, use_linear_lr_decay=False))
+    run_case("mb2_4x20_h32", 4, 20, 3, 10, 32, 3, seed=6, extra=dict(num_mini_batch=2))
+    run_case("mb3_3x20_h256", 3, 20, 3, 7, 256, 2, seed=7, extra=dict(num_mini_batch=4))   # 63 rows * 3 agents, tail dropped
 
 
 if __name__ == "__main__":

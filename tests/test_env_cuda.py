@@ -174,3 +174,118 @@ def test_launch_geometry_does_not_change_results():
     for other in outs[1:]:
         for x, y in zip(outs[0], other):
             assert torch.equal(x, y)
+
+
+def _obs_from_state(pv, en, poi, N, M, m_energy=5.0):
+    """Observation rows rebuilt from the compact state with torch on the device, in float64 then rounded once to
+    float32 exactly as the reference stores them (scenarios/coverage.py:99-110 -> float32 buffer):
+    [v_i, p_i, p_k - p_i (k != i), for every PoI: q_j - p_i, energy_j, m_energy, done_j]."""
+    E = pv.shape[0]
+    p, v = pv[..., :2], pv[..., 2:]
+    rel = p[:, None, :, :] - p[:, :, None, :]                          # [e, i, k] = p_k - p_i
+    keep = ~torch.eye(N, dtype=torch.bool, device=pv.device)
+    rel = rel[:, keep].view(E, N, N - 1, 2).reshape(E, N, 2 * (N - 1))
+    dq = poi[None, None] - p[:, :, None, :]                            # [e, i, j] = q_j - p_i
+    enf = en.to(torch.float64)
+    sec = torch.cat([dq, enf[:, None, :, None].expand(E, N, M, 1), torch.full((E, N, M, 1), m_energy, dtype=torch.float64, device=pv.device),
+                     (enf >= m_energy).to(torch.float64)[:, None, :, None].expand(E, N, M, 1)], dim=-1).reshape(E, N, 5 * M)
+    return torch.cat([v, p, rel, sec], dim=-1).to(torch.float32)
+
+
+@pytest.mark.parametrize("N,M,E,force", [(8, 64, 65536, 0.0), (16, 256, 32768, 1.0)])
+def test_full_size_properties(N, M, E, force):
+    """BASELINE.json's full sizes (configs[1] and [2]), where the CPU oracle would take minutes: size-independent
+    properties of the step instead — (1) every observation row is exactly the function of the compact state the
+    reference defines, (2) reward / done are shared by the agents of an env, (3) a done env comes back reset,
+    (4) PoI energy never decreases inside an episode and the coverage rate is the done-PoI fraction, (5) the first
+    4096 envs reproduce a 4096-env run bit for bit (what sharding the env axis across GPUs relies on), and that
+    small run is itself checked against the CPU oracle, (6) connect bits agree with a float64 union-find-free
+    recomputation (adjacency powers) on a sample."""
+    from dcc_b200.envs import CudaVecEnv
+    from oracle.env_oracle import OracleEnv
+    rng = np.random.RandomState(7)
+    poi = rng.uniform(-1, 1, (M, 2))
+    Es = 4096
+    kw = dict(comm_r_scale=0.95, comm_force_scale=force, reference_compat=False, pos_pois=poi, want_connectivity=True)
+    env, small = CudaVecEnv(E, N, M, **kw), CudaVecEnv(Es, N, M, **kw)
+    orc = OracleEnv(Es, N, M, poi, comm_r_scale=0.95, contact_force=100.0 * force, n_threads=8)
+    dev = env.device
+    poi_t = torch.from_numpy(poi).to(dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    env.reset(); small.reset(); orc.reset()
+    ptrs = lambda e: e.get_state()    # noqa: E731
+    prev_en = torch.zeros((E, M), dtype=torch.uint8, device=dev)
+    n_done = 0
+    for t in range(40):
+        a = torch.randn((E, N, 2), generator=g, device=dev) * (2.0 if t % 7 == 6 else 1.0)
+        obs, rew, done, infos = env.step(a)
+        pv_h, en_h = ptrs(env)
+        pv, en = torch.from_numpy(pv_h).to(dev), torch.from_numpy(en_h).to(dev)
+        assert torch.equal(obs, _obs_from_state(pv, en, poi_t, N, M)), "t=%d obs is not f(state)" % t      # (1)
+        assert bool((rew == rew[:, :1]).all()) and bool((done == done[:, :1]).all())                       # (2)
+        d = done[:, 0]
+        n_done += int(d.sum())
+        if bool(d.any()):                                                                                  # (3)
+            assert bool((pv[d] == 0).all()) and bool((en[d] == 0).all())
+        assert bool((en[~d] >= prev_en[~d]).all())                                                         # (4)
+        live_cov = (en >= 5).float().mean(1)
+        assert torch.allclose(infos.coverage_rate[~d], live_cov[~d], atol=1e-6)
+        prev_en = en
+        o2, r2, d2, i2 = small.step(a[:Es].contiguous())                                                   # (5)
+        assert torch.equal(o2, obs[:Es]) and torch.equal(r2, rew[:Es]) and torch.equal(d2, done[:Es])
+        assert torch.equal(small.connect_bits, env.connect_bits[:Es]) and torch.equal(small.adj, env.adj[:Es])
+        if t % 8 == 0 or t == 39:
+            o = orc.step(a[:Es].cpu().numpy())
+            assert np.array_equal(o2.cpu().numpy(), o["obs"]) and np.array_equal(d2.cpu().numpy()[:, 0], o["done"])
+            cb = small.connect_bits.cpu().numpy()
+            assert np.array_equal((cb & 1).astype(bool), o["connect"])                                     # (6)
+            assert np.array_equal(((cb >> 1) & 1).astype(bool), o["connect_"])
+            ref = o["reward"].astype(np.float32)
+            assert np.all(np.abs(r2.cpu().numpy()[:, 0, 0] - ref) <= REW_RTOL * np.maximum(1.0, np.abs(ref)))
+        else:
+            orc.step(a[:Es].cpu().numpy())
+    assert n_done > 0
+    env.close(); small.close()
+
+
+def test_step_host_equals_device_step():
+    """The host-buffer entry point (what the e2e bench and numpy_compat use) returns exactly the device path's results."""
+    from dcc_b200.envs import CudaVecEnv
+    rng = np.random.RandomState(11)
+    E, N, M = 3000, 8, 64
+    poi = rng.uniform(-1, 1, (M, 2))
+    a_env, b_env = (CudaVecEnv(E, N, M, comm_force_scale=1.0, reference_compat=False, pos_pois=poi) for _ in range(2))
+    a_env.reset(); b_env.reset()
+    for t in range(6):
+        a = (rng.standard_normal((E, N, 2)) * 1.5).astype(np.float32)
+        obs, rew, done, infos = a_env.step(torch.from_numpy(a).cuda())
+        ho, hr, hd, hc = b_env.step_host(a)
+        assert np.array_equal(obs.cpu().numpy(), ho) and np.array_equal(rew.cpu().numpy()[:, :, 0], hr)
+        assert np.array_equal(done.cpu().numpy(), hd.astype(bool)) and np.array_equal(infos.coverage_rate.cpu().numpy(), hc)
+    a_env.close(); b_env.close()
+
+
+def test_render_snapshot_and_connectivity_outputs():
+    """f-3: headless render / snapshot of the compact state; adjacency outputs can be switched on after creation."""
+    from dcc_b200.envs import CudaVecEnv
+    from oracle.env_oracle import OracleEnv
+    rng = np.random.RandomState(2)
+    E, N, M = 5, 4, 20
+    poi = rng.uniform(-1, 1, (M, 2))
+    env = CudaVecEnv(E, N, M, comm_force_scale=0.0, reference_compat=False, pos_pois=poi)
+    orc = OracleEnv(E, N, M, poi, comm_r_scale=0.95, contact_force=0.0, n_threads=1)
+    env.reset(); orc.reset()
+    assert env.render("human") is None
+    f0 = env.render("rgb_array")
+    assert len(f0) == 1 and f0[0][0].shape == (350, 350, 3) and f0[0][0].dtype == np.uint8
+    env.enable_connectivity_outputs()
+    for t in range(12):
+        a = (rng.standard_normal((E, N, 2)) * 2).astype(np.float32)
+        env.step(torch.from_numpy(a).cuda())
+        o = orc.step(a)
+    st = env.snapshot()
+    assert np.array_equal(st["pos_vel"], orc.pos_vel) and np.array_equal(st["energy"], orc.energy)
+    assert np.array_equal(st["adj"], o["adj"]) and np.array_equal((st["connect_bits"] & 1).astype(bool), o["connect"])
+    frames = env.render("rgb_array", max_envs=3, size=128)
+    assert len(frames) == 3 and frames[2][0].shape == (128, 128, 3) and (frames[0][0] != f0[0][0][:128, :128]).any()
+    env.close()

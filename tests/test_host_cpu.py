@@ -40,12 +40,19 @@ def test_defaults_equal_the_shipped_yaml_files():
 def test_unsupported_branches_fail_loudly():
     from dcc_b200.utils.config import check_supported, load_config
     check_supported(load_config(None))
-    for key, val in (("use_recurrent_policy", True), ("use_popart", True), ("num_mini_batch", 2), ("use_valuenorm", False),
-                     ("layer_N", 2), ("use_huber_loss", False)):
+    for key, val in (("use_recurrent_policy", True), ("use_popart", True), ("num_mini_batch", 0), ("use_ReLU", False),
+                     ("layer_N", 2), ("use_feature_normalization", False), ("use_centralized_V", False)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         with pytest.raises(NotImplementedError):
             check_supported(cfg)
+    # update-path switches of mappo.yaml that ARE implemented
+    for key, val in (("num_mini_batch", 2), ("use_valuenorm", False), ("use_huber_loss", False), ("use_gae", False),
+                     ("use_clipped_value_loss", False), ("use_max_grad_norm", False), ("weight_decay", 1e-4),
+                     ("use_proper_time_limits", True), ("use_linear_lr_decay", False)):
+        cfg = load_config(None)
+        setattr(cfg, key, val)
+        check_supported(cfg)
 
 
 def test_net_layout_matches_reference_parameter_counts():

@@ -21,6 +21,8 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "mappo_*.npz")))
 BACKENDS = [1, 0]   # SIMT fp32, auto (tcgen05 3xTF32 where the shape allows)
+FLAG_KEYS = ("use_huber_loss", "use_clipped_value_loss", "use_max_grad_norm", "use_valuenorm", "use_gae",
+             "use_proper_time_limits", "weight_decay", "num_mini_batch")
 
 
 def load(name):
@@ -35,6 +37,9 @@ def make_cfg(c, E, T, **over):
     cfg = load_config(None, num_agents=c["n_agents"], num_pois=c["n_pois"], n_rollout_threads=E, max_ep_len=T,
                       algo_hidden_size=c["hidden"], ppo_epoch=c["ppo_epoch"], seed=c["seed"], n_iters=c["n_iters"],
                       n_eval_rollout_threads=0)
+    for k in FLAG_KEYS:          # mappo.yaml switches recorded with the golden (absent in the older files = shipped)
+        if k in c:
+            setattr(cfg, k, c[k])
     for k, v in over.items():
         setattr(cfg, k, v)
     return cfg
@@ -69,14 +74,18 @@ def fill_buffer(buf, g, p):
     buf.masks_te.copy_(t(g[p + "masks"][:, :, 0, 0]))
 
 
-def check_params(tag, net, g, prefix, rtol=2e-5, atol=3e-6):
+def check_params(tag, net, g, prefix, rtol=2e-5, atol=3e-6, max_bad_frac=0.0):
+    """max_bad_frac > 0 (minibatch goldens, ~50-row minibatches): see tests/test_oracle_mappo.py::check_params."""
     for k in net.layout:
         key = prefix + k
         stride, s, ss = g[key + ":meta"]
         flat = net.view(k).detach().cpu().numpy().astype(np.float64).reshape(-1)
         ref = g[key + ":sample"].astype(np.float64)
         got = flat[::int(stride)]
-        assert np.allclose(got, ref, rtol=rtol, atol=atol), "%s %s max|d|=%g" % (tag, k, np.abs(got - ref).max())
+        d = np.abs(got - ref)
+        bad = d > atol + rtol * np.abs(ref)
+        assert bad.mean() <= max_bad_frac and d.max() <= (5e-5 if max_bad_frac else np.inf), \
+            "%s %s max|d|=%g off-tolerance %d/%d" % (tag, k, d.max(), int(bad.sum()), bad.size)
         assert abs(flat.sum() - s) <= 1e-4 * max(1.0, np.abs(flat).sum()), (tag, k, "sum")
         assert abs((flat ** 2).sum() - ss) <= 1e-4 * max(1.0, ss), (tag, k, "sumsq")
 
@@ -84,18 +93,27 @@ def check_params(tag, net, g, prefix, rtol=2e-5, atol=3e-6):
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("name", CASES)
 def test_learner_vs_reference_golden(name, backend):
-    """Teacher-forced replay of two reference iterations: forward, GAE, the whole 15-epoch update."""
+    """Teacher-forced replay of two reference iterations: forward, GAE, the whole 15-epoch update.  The flags_* files
+    were recorded with mappo.yaml switches flipped (mse / unclipped value loss / no grad clip / weight decay; no
+    ValueNorm; discounted returns instead of GAE), the mb* files with num_mini_batch > 1 (the permutations the
+    reference's generator drew are replayed)."""
     import torch
     g = load(name)
     c = g["cfg"]
     N, D = c["n_agents"], c["obs_dim"]
     T, E = g["it1_actions"].shape[:2]
     cfg, pol, tr, buf = build(c, E, T, gemm_backend=backend)
+    use_vn, use_gae, nmb = c.get("use_valuenorm", True), c.get("use_gae", True), c.get("num_mini_batch", 1)
+    assert (tr.value_normalizer is not None) == use_vn
     for it in range(1, c["iters"] + 1):
         p = "it%d_" % it
+        if not use_gae:   # the reference's non-GAE branch keeps the bootstrap value in returns[T] (shared_buffer.py:209-210)
+            g[p + "value_preds"] = g[p + "value_preds"].copy()
+            g[p + "value_preds"][-1] = g[p + "returns"][-1]
         fill_buffer(buf, g, p)
-        vn = tr.value_normalizer.state.cpu().numpy()[:3]
-        assert np.allclose(vn, g[p + "vn_before"], rtol=1e-5, atol=1e-12)
+        if use_vn:
+            vn = tr.value_normalizer.state.cpu().numpy()[:3]
+            assert np.allclose(vn, g[p + "vn_before"], rtol=1e-5, atol=1e-12)
         # evaluate_actions on the recorded (obs, action): log-probs and values of the rollout
         v, logp, ent = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
         assert np.allclose(logp.cpu().numpy().reshape(T, E, N, 1), g[p + "logp"], rtol=1e-5, atol=2e-5)
@@ -113,16 +131,61 @@ def test_learner_vs_reference_golden(name, backend):
         buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(g[p + "returns"][:, :, 0, 0])).to(buf.device))
         pol.lr_decay(it, c["n_iters"])
         assert abs(pol.lr_actor_now - float(g[p + "lr"])) < 1e-12
+        if nmb > 1:
+            perms = g[p + "perms"]
+            tr.permutation_fn = lambda ep, n, perms=perms: perms[ep].astype(np.int64)
         info = tr.train(buf)
         ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
                        g[p + "train_info"]))
         for k in ref:
             assert abs(info[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (it, k, info[k], ref[k])
-        vn = tr.value_normalizer.state.cpu().numpy()[:3]
-        assert np.allclose(vn, g[p + "vn_after"], rtol=1e-5, atol=1e-12)
-        check_params("actor it%d" % it, pol.actor, g, p + "actor.")
-        check_params("critic it%d" % it, pol.critic, g, p + "critic.")
+        if use_vn:
+            vn = tr.value_normalizer.state.cpu().numpy()[:3]
+            assert np.allclose(vn, g[p + "vn_after"], rtol=1e-5, atol=1e-12)
+        frac = 0.02 if nmb > 1 else 0.0
+        check_params("actor it%d" % it, pol.actor, g, p + "actor.", max_bad_frac=frac)
+        check_params("critic it%d" % it, pol.critic, g, p + "critic.", max_bad_frac=frac)
         buf.after_update()
+
+
+def test_minibatch_update_vs_oracle_chunked():
+    """num_mini_batch = 3 on a batch large enough that a minibatch spans several activation chunks (chunk_rows forced
+    small), tcgen05 backend, against the float64 oracle with the same permutations; the tail the split drops
+    (B % 3 rows) must not contribute."""
+    import torch
+    from oracle import mappo_oracle as mo
+    N, M, Hd, E, T, EP, NMB = 4, 20, 256, 10, 10, 2, 3
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, ppo_epoch=EP, seed=11, n_iters=200, obs_dim=D, actor_seed=21, critic_seed=22,
+             num_mini_batch=NMB)
+    cfg, pol, tr, buf = build(c, E, T, chunk_rows=16)     # 64 actor rows / 16 critic rows per chunk
+    rng = np.random.default_rng(5)
+    obs = rng.normal(0, 1, (T + 1, E, N, D)).astype(np.float32)
+    act = rng.normal(0, 1, (T, E, N, 2)).astype(np.float32)
+    logp_old = rng.normal(-2.5, 0.4, (T, E, N, 1)).astype(np.float32)
+    vals = rng.normal(0, 1, (T + 1, E, 1, 1)).astype(np.float32).repeat(N, 2)
+    rets = (vals * 0.1 + rng.normal(0, 0.5, (T + 1, E, 1, 1))).astype(np.float32).repeat(N, 2)
+    g = {"x_obs": obs, "x_actions": act, "x_logp": logp_old, "x_value_preds": vals,
+         "x_rewards": np.zeros((T, E, N, 1), np.float32), "x_masks": np.ones((T + 1, E, N, 1), np.float32)}
+    fill_buffer(buf, g, "x_")
+    buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(rets[:, :, 0, 0])).to(buf.device))
+    B = T * E * N
+    perms = np.stack([np.random.default_rng(100 + ep).permutation(B) for ep in range(EP)])
+    tr.permutation_fn = lambda ep, n: perms[ep]
+    hp = dict(clip_param=cfg.clip_param, huber_delta=cfg.huber_delta, value_loss_coef=cfg.value_loss_coef,
+              entropy_coef=cfg.entropy_coef, max_grad_norm=cfg.max_grad_norm, opti_eps=cfg.opti_eps, num_mini_batch=NMB)
+    orc = mo.Trainer(make_params(actor_param_shapes(D, Hd), 21), make_params(critic_param_shapes(N * D, Hd), 22), hp)
+    ref = orc.train(obs, act, logp_old, vals, rets, cfg.actor_lr, EP, perms=perms)
+    info = tr.train(buf)
+    for k in ref:
+        assert abs(info[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (k, info[k], ref[k])
+    assert np.allclose(tr.value_normalizer.state.cpu().numpy()[:3], orc.vn.state(), rtol=1e-5, atol=1e-12)
+    for net, onet in ((pol.actor, orc.actor), (pol.critic, orc.critic)):
+        for k in net.layout:
+            got = net.view(k).detach().cpu().numpy().astype(np.float64).reshape(-1)
+            want = onet.p[k].reshape(-1)
+            bad = np.abs(got - want) > 3e-6 + 2e-5 * np.abs(want)
+            assert bad.mean() <= 0.02 and np.abs(got - want).max() <= 5e-5, (k, int(bad.sum()), np.abs(got - want).max())
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
@@ -312,13 +375,22 @@ def test_learner_end_to_end_small():
             ri = lr.rollout(lr.rl_buffer, lr.train_envs)
             ti = lr.rl_update()
             infos.append((ri, ti))
-            assert set(ri) == {"reward", "coverage_rate"} and 0.0 <= ri["coverage_rate"] <= 1.0
+            assert set(ri) == {"reward", "coverage_rate", "connect_rate"} and 0.0 <= ri["coverage_rate"] <= 1.0
+            assert 0.0 <= ri["connect_rate"] <= 1.0
             assert set(ti) == {"value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"}
             assert all(np.isfinite(v) for v in ti.values())
         assert abs(infos[0][1]["dist_entropy"] - 2.837877) < 1e-3   # fresh policy: 2 * (0.5 + 0.5 ln 2 pi)
         assert not torch.equal(w0, lr.policy.actor.params)
         ti = lr.rollout(lr.test_buffer, lr.test_envs)
         assert np.isfinite(ti["reward"])
+        # f-3: a render rollout runs headless and leaves the trajectory (+ GIF) next to the checkpoints
+        steps_before = lr.agent_steps
+        ri = lr.rollout(lr.render_buffer, lr.render_envs, is_render=True, iter_=3)
+        assert lr.agent_steps == steps_before and lr.last_trajectory is not None
+        z = np.load(os.path.join(lr.output_path, "models_3_traj.npz"))
+        assert z["pos_vel"].shape == (25, 1, 4, 4) and z["adj"].shape == (25, 1, 4) and z["energy"].shape == (25, 1, 20)
+        assert abs(float((z["connect_bits"] & 1).mean()) - ri["connect_rate"]) < 1e-6
+        assert os.path.getsize(os.path.join(lr.output_path, "models_3.gif")) > 1000
         d = os.path.join(tmp, "ck")
         os.makedirs(d)
         lr.save_model(d)
