@@ -9,6 +9,7 @@
 // The handle owns only activation scratch sized for `chunk_rows` env-step rows; larger batches are streamed in
 // chunks with gradient accumulation, which equals the reference's single giant minibatch (num_mini_batch = 1).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -156,6 +157,15 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     p.kt_per_split = (p.KT + p.splits - 1) / p.splits;
     p.splits = (p.KT + p.kt_per_split - 1) / p.kt_per_split;
     if (p.splits > 1) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)tc::TC_N * 4, M, s));
+    // epilogue stores through the TMA engine (see TcfParams::use_tma) unless split-K needs atomics; DCC_TC_TMA=0 keeps
+    // the st.global epilogue (tuning knob)
+    static const bool tma_env = !(getenv("DCC_TC_TMA") && atoi(getenv("DCC_TC_TMA")) == 0);
+    if (tma_env && p.splits == 1) {
+        bool ok = true;
+        if (C) ok = ok && tc::tc_make_store_map(&p.tmC, C, M, ldc);
+        if (bias && h_out) ok = ok && tc::tc_make_store_map(&p.tmH, h_out, M, ldc);
+        p.use_tma = ok ? 1 : 0;
+    }
     const int work = row_tiles * p.splits;
     const int grid = work < h->sm_count ? work : h->sm_count;
     tc::tc_gemm_fwd_kernel<<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);

@@ -14,6 +14,8 @@
 // Accumulators live in TMEM (2 x 256 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile
 // i+1); one thread issues the MMAs; tcgen05.commit arrives on the mbarriers that recycle the stages.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
 #include "dcc_common.cuh"
 
 namespace dcc {
@@ -230,7 +232,46 @@ struct TcfParams {
     float *H;            // [M, ldc]
     float *mean, *rstd;  // [M] (may be NULL)
     int dbg;             // tools/tc_bench only: 1 = skip the global stores of the epilogue
+    // TMA store path of the epilogue (splits == 1): 2-D tensor maps over C and H ([M rows, 256 cols] fp32, box
+    // 32 x 32, SWIZZLE_128B).  A thread owns one accumulator row, so it writes its row of a 32 x 32 box into the warp's
+    // 4 KB staging buffer with conflict-free 16-byte stores (chunk ^ (row & 7), the layout the tensor map un-swizzles)
+    // and ONE cp.async.bulk.tensor store per box leaves asynchronously: no shared-memory read-back, no st.global issue
+    // or store-queue stalls in the epilogue warps, rows past M are clipped by the hardware.
+    int use_tma;
+    alignas(64) CUtensorMap tmC, tmH;
 };
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+// [rows, 256] fp32 matrix with leading dimension ld (floats) -> store map with a 32 x 32 box.  Returns false when the
+// driver entry point is unavailable or the encode fails (callers then keep the st.global epilogue).
+inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
+    static PFN_tensorMapEncodeTiled enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
+    }
+    if (!enc || rows < 1 || (ld & 3) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// smem box (swizzled as the map says) -> global tile at (column x, row y), completion tracked by the bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t saddr, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)tm), "r"(saddr),
+                 "r"(x), "r"(y)
+                 : "memory");
+}
 
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -246,7 +287,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p) {
+__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __grid_constant__ TcfParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float *xpose = reinterpret_cast<float *>(smem + TCF_STAGES * TCF_STAGE_BYTES);
@@ -380,6 +421,24 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                     // The 8 small cross terms go first, while the fresh accumulator is still ~2^-11 of its final
                     // magnitude (their round-toward-zero losses are then negligible); only the 4 hi*hi MMAs add at
                     // full magnitude.  Measured rms error vs float64: 1e-7-class instead of 2.5e-7 with interleaving.
+#ifdef DCC_TCF_NSPLIT_EXPERIMENT
+                    constexpr uint32_t idesc_h = make_idesc_tf32(TC_BM, TC_N / 2, 0, 0);
+                    constexpr uint64_t bh = (uint64_t)((128 * 128) >> 4);   // rows 128..255 of the weight tile
+#pragma unroll
+                    for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            tc_mma_tf32(d + nh * 128, a_lo + adv, b_hi + adv + nh * bh, idesc_h, (k != 0 || !chain_first) ? 1u : 0u);
+                            tc_mma_tf32(d + nh * 128, a_hi + adv, b_lo + adv + nh * bh, idesc_h, 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            tc_mma_tf32(d + nh * 128, a_hi + adv, b_hi + adv + nh * bh, idesc_h, 1);
+                        }
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
@@ -391,6 +450,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
                         tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
+#endif
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
                     if (chain_last) {
                         tc_commit(&tfull[ab]); // accumulator ready to drain
@@ -510,6 +570,47 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
                         }
                     }
                 }
+            } else if (p.use_tma) {
+                // TMA store path: per 32-column block, stage this warp's 32 rows x 32 columns (thread = row) and hand the
+                // box to the TMA engine; the staging buffer is reused once the engine has READ it (wait_group.read).
+                const bool ln = p.epi == TCF_EPI_BIAS_RELU_LN;
+                const uint32_t myrow = xp_u32 + lane * 128;
+                const int sw = lane & 7;
+                if (row0 < p.M && !(p.dbg & 1)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col0 = half * 128 + j * 32;
+                        if (p.C) {
+                            if (lane == 0) bulk_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                sts128(myrow + ((c ^ sw) << 4), make_float4(acc[j * 32 + 4 * c], acc[j * 32 + 4 * c + 1],
+                                                                            acc[j * 32 + 4 * c + 2], acc[j * 32 + 4 * c + 3]));
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_2d(&p.tmC, xp_u32, col0, row0); bulk_commit(); }
+                        }
+                        if (ln && p.H) {
+                            if (lane == 0) bulk_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma + col0) + c);
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta + col0) + c);
+                                float4 hv;
+                                hv.x = fmaf((acc[j * 32 + 4 * c] - mean) * rstd, g.x, b.x);
+                                hv.y = fmaf((acc[j * 32 + 4 * c + 1] - mean) * rstd, g.y, b.y);
+                                hv.z = fmaf((acc[j * 32 + 4 * c + 2] - mean) * rstd, g.z, b.z);
+                                hv.w = fmaf((acc[j * 32 + 4 * c + 3] - mean) * rstd, g.w, b.w);
+                                sts128(myrow + ((c ^ sw) << 4), hv);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_2d(&p.tmH, xp_u32, col0, row0); bulk_commit(); }
+                        }
+                    }
+                }
             } else {
             // Stores: a thread holds 128 columns of ONE row, so a direct store would scatter 16-byte pieces over 32 rows.
             // Rows are staged 8 at a time through the warp's 4 KB buffer (16-byte chunks XOR-ed with the row: conflict
@@ -555,6 +656,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(TcfParams p
             TC_PROF_NOW(t1);
             TC_PROF_ADD(e_tile, t0, t1);
         }
+        if (p.use_tma && lane == 0) bulk_wait_all<0>();   // staged boxes fully written before the CTA's smem goes away
+        __syncwarp();
         TC_PROF_OUT(threadIdx.x == 128, 8, e_wait);
         TC_PROF_OUT(threadIdx.x == 128, 9, e_drain);
         TC_PROF_OUT(threadIdx.x == 128, 10, e_tile);

@@ -213,8 +213,15 @@ def test_full_size_properties(N, M, E, force):
     poi_t = torch.from_numpy(poi).to(dev)
     g = torch.Generator(device=dev).manual_seed(3)
     env.reset(); small.reset(); orc.reset()
+    # start from a spread-out state (positions up to the |p| > 1.5 bound, PoIs close to completion in every 5th env)
+    # so that both episode-end conditions fire within the 40 steps
+    pv0 = np.zeros((E, N, 4)); pv0[..., :2] = rng.uniform(-1.45, 1.45, (E, N, 2)) * rng.uniform(0.1, 1, (E, 1, 1))
+    pv0[..., 2:] = rng.uniform(-0.4, 0.4, (E, N, 2))
+    en0 = rng.randint(0, 5, (E, M)).astype(np.uint8)
+    en0[::5] = np.where(rng.rand(*en0[::5].shape) < 0.97, 6, 4)
+    env.set_state(pv0, en0); small.set_state(pv0[:Es], en0[:Es]); orc.set_state(pv0[:Es], en0[:Es])
     ptrs = lambda e: e.get_state()    # noqa: E731
-    prev_en = torch.zeros((E, M), dtype=torch.uint8, device=dev)
+    prev_en = torch.from_numpy(en0).to(dev)
     n_done = 0
     for t in range(40):
         a = torch.randn((E, N, 2), generator=g, device=dev) * (2.0 if t % 7 == 6 else 1.0)

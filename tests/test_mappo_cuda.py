@@ -163,8 +163,8 @@ def test_minibatch_update_vs_oracle_chunked():
     obs = rng.normal(0, 1, (T + 1, E, N, D)).astype(np.float32)
     act = rng.normal(0, 1, (T, E, N, 2)).astype(np.float32)
     logp_old = rng.normal(-2.5, 0.4, (T, E, N, 1)).astype(np.float32)
-    vals = rng.normal(0, 1, (T + 1, E, 1, 1)).astype(np.float32).repeat(N, 2)
-    rets = (vals * 0.1 + rng.normal(0, 0.5, (T + 1, E, 1, 1))).astype(np.float32).repeat(N, 2)
+    v1 = rng.normal(0, 1, (T + 1, E, 1, 1)).astype(np.float32)
+    vals, rets = v1.repeat(N, 2), (v1 * 0.1 + rng.normal(0, 0.5, (T + 1, E, 1, 1))).astype(np.float32).repeat(N, 2)
     g = {"x_obs": obs, "x_actions": act, "x_logp": logp_old, "x_value_preds": vals,
          "x_rewards": np.zeros((T, E, N, 1), np.float32), "x_masks": np.ones((T + 1, E, N, 1), np.float32)}
     fill_buffer(buf, g, "x_")

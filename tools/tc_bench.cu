@@ -28,6 +28,10 @@ int main(int argc, char **argv) {
     TcfParams p; memset(&p, 0, sizeof p);
     p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = KT; p.lda = K; p.ldc = 256; p.splits = 1; p.kt_per_split = KT;
     p.epi = epi; p.dbg = argc > 4 ? atoi(argv[4]) : 0; p.bias = bias; p.gamma = bias + 256; p.beta = bias + 512; p.H = H; p.mean = mean; p.rstd = rstd;
+    if (argc > 5 && atoi(argv[5])) {   // TMA-store epilogue
+        p.use_tma = (tc_make_store_map(&p.tmC, C, M, 256) && tc_make_store_map(&p.tmH, H, M, 256)) ? 1 : 0;
+        printf("use_tma=%d  ", p.use_tma);
+    }
     const int tiles = (M + 127) / 128, grid = tiles < 148 ? tiles : 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) tc_gemm_fwd_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
