@@ -421,24 +421,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     // The 8 small cross terms go first, while the fresh accumulator is still ~2^-11 of its final
                     // magnitude (their round-toward-zero losses are then negligible); only the 4 hi*hi MMAs add at
                     // full magnitude.  Measured rms error vs float64: 1e-7-class instead of 2.5e-7 with interleaving.
-#ifdef DCC_TCF_NSPLIT_EXPERIMENT
-                    constexpr uint32_t idesc_h = make_idesc_tf32(TC_BM, TC_N / 2, 0, 0);
-                    constexpr uint64_t bh = (uint64_t)((128 * 128) >> 4);   // rows 128..255 of the weight tile
-#pragma unroll
-                    for (int nh = 0; nh < 2; ++nh) {
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {
-                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            tc_mma_tf32(d + nh * 128, a_lo + adv, b_hi + adv + nh * bh, idesc_h, (k != 0 || !chain_first) ? 1u : 0u);
-                            tc_mma_tf32(d + nh * 128, a_hi + adv, b_lo + adv + nh * bh, idesc_h, 1);
-                        }
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {
-                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            tc_mma_tf32(d + nh * 128, a_hi + adv, b_hi + adv + nh * bh, idesc_h, 1);
-                        }
-                    }
-#else
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
@@ -450,7 +432,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
                         tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
-#endif
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
                     if (chain_last) {
                         tc_commit(&tfull[ab]); // accumulator ready to drain
