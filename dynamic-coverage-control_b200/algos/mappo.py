@@ -31,12 +31,15 @@ TRUNK = ("base.feature_norm.weight", "base.feature_norm.bias", "base.mlp.fc1.0.w
 FC_H = ("base.mlp.fc_h.0.weight", "base.mlp.fc_h.0.bias", "base.mlp.fc_h.2.weight", "base.mlp.fc_h.2.bias")
 
 
-def net_layout(in_dim, hidden, out_dim, head, logstd=False):
-    """name -> (offset, shape) of the flat parameter buffer, in the order include/dcc_b200.h documents."""
+def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True):
+    """name -> (offset, shape) of the flat parameter buffer, in the order include/dcc_b200.h documents.
+    feature_norm=False (use_feature_normalization: false): the net has no base.feature_norm.* entries (mlp.py:44-45)."""
     shapes = [(in_dim,), (in_dim,), (hidden, in_dim), (hidden,), (hidden,), (hidden,), (hidden, hidden), (hidden,),
               (hidden,), (hidden,)]
     lay, off = OrderedDict(), 0
     for k, shp in zip(TRUNK, shapes):
+        if not feature_norm and k.startswith("base.feature_norm"):
+            continue
         lay[k] = (off, shp)
         off += int(np.prod(shp))
     lay[head + ".weight"] = (off, (out_dim, hidden)); off += out_dim * hidden
@@ -46,17 +49,19 @@ def net_layout(in_dim, hidden, out_dim, head, logstd=False):
     return lay, off
 
 
-def _reference_init(in_dim, hidden, out_dim, head_gain):
+def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use_relu=True, feature_norm=True):
     """Initial parameters drawn exactly as the reference constructs a net (same torch RNG consumption order):
-    MLPBase -> LayerNorm, fc1 = Linear+orthogonal(gain sqrt 2), fc_h likewise, fc2 = deepcopy(fc_h)
-    (algos/algo_utils/mlp.py:13-23), then the head Linear with orthogonal(gain) (distributions.py:76-80,
-    r_actor_critic.py:101-107).  Host-side torch, construction time only."""
+    MLPBase -> LayerNorm, fc1 = Linear + orthogonal / xavier_uniform (`use_orthogonal`) with the gain of the trunk
+    activation (sqrt 2 for ReLU, 5/3 for tanh), fc_h likewise, fc2 = deepcopy(fc_h) (algos/algo_utils/mlp.py:13-23),
+    then the head Linear with the same init method and `head_gain` (distributions.py:76-80, r_actor_critic.py:92-107).
+    Host-side torch, construction time only."""
     import torch.nn as nn
-    gain = nn.init.calculate_gain("relu")
+    gain = nn.init.calculate_gain("relu" if use_relu else "tanh")
+    init_method = nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_
 
     def lin(i, o, g):
         m = nn.Linear(i, o)
-        nn.init.orthogonal_(m.weight.data, gain=g)
+        init_method(m.weight.data, gain=g)
         nn.init.constant_(m.bias.data, 0)
         return m
     fc1 = lin(in_dim, hidden, gain)
@@ -64,7 +69,8 @@ def _reference_init(in_dim, hidden, out_dim, head_gain):
     head = lin(hidden, out_dim, head_gain)
     ones, zeros = torch.ones, torch.zeros
     sd = OrderedDict()
-    sd["base.feature_norm.weight"], sd["base.feature_norm.bias"] = ones(in_dim), zeros(in_dim)
+    if feature_norm:
+        sd["base.feature_norm.weight"], sd["base.feature_norm.bias"] = ones(in_dim), zeros(in_dim)
     sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"] = fc1.weight.data.clone(), fc1.bias.data.clone()
     sd["base.mlp.fc1.2.weight"], sd["base.mlp.fc1.2.bias"] = ones(hidden), zeros(hidden)
     sd["base.mlp.fc_h.0.weight"], sd["base.mlp.fc_h.0.bias"] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
@@ -137,6 +143,8 @@ class MAPPOPolicy:
         self.share_dim = int(cent_obs_space.shape[0])
         if self.share_dim % self.obs_dim:
             raise ValueError("centralised obs dim %d is not a multiple of obs dim %d" % (self.share_dim, self.obs_dim))
+        # use_centralized_V: false hands obs_space in as cent_obs_space (learner.py:43-46): the critic then sees one agent's
+        # observation, i.e. the kernels run with "1 agent per env" over E*N pseudo-envs and values are per agent
         self.n_agents = self.share_dim // self.obs_dim
         self.hidden = int(cfg.algo_hidden_size)
         self.act_dim = int(act_space.shape[0])
@@ -156,24 +164,27 @@ class MAPPOPolicy:
         mc.use_valuenorm = 1 if getattr(cfg, "use_valuenorm", True) else 0
         mc.use_gae = 1 if getattr(cfg, "use_gae", True) else 0
         mc.weight_decay = self.weight_decay
+        fnorm, relu = bool(getattr(cfg, "use_feature_normalization", True)), bool(getattr(cfg, "use_ReLU", True))
+        mc.use_feature_normalization, mc.use_relu = int(fnorm), int(relu)
         self.mcfg = mc
         h = C.c_void_p()
         _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
         self._h = h
 
-        la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True)
-        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out")
+        la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True, feature_norm=fnorm)
+        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out", feature_norm=fnorm)
         assert na == self.lib.dcc_mappo_param_count(h, 0) and nc == self.lib.dcc_mappo_param_count(h, 1)
         # one flat gradient buffer for both nets: a single all-reduce per PPO epoch
         self.flat_grads = torch.zeros(na + nc, dtype=torch.float32, device=self.device)
         self.actor = _Net(la, na, self.flat_grads[:na], self.device)
         self.critic = _Net(lc, nc, self.flat_grads[na:], self.device)
         # initial weights: the reference's construction order — actor first, then critic (mappo.py:27-28)
-        sd, head = _reference_init(self.obs_dim, self.hidden, self.act_dim, float(cfg.gain))
+        init_kw = dict(use_orthogonal=bool(getattr(cfg, "use_orthogonal", True)), use_relu=relu, feature_norm=fnorm)
+        sd, head = _reference_init(self.obs_dim, self.hidden, self.act_dim, float(cfg.gain), **init_kw)
         sd["act.action_out.fc_mean.weight"], sd["act.action_out.fc_mean.bias"] = head.weight.data, head.bias.data
         sd["act.action_out.logstd._bias"] = torch.zeros(self.act_dim, 1)
         self.actor.load_state_dict(sd)
-        sd, head = _reference_init(self.share_dim, self.hidden, 1, 1.0)
+        sd, head = _reference_init(self.share_dim, self.hidden, 1, 1.0, **init_kw)
         sd["v_out.weight"], sd["v_out.bias"] = head.weight.data, head.bias.data
         self.critic.load_state_dict(sd)
 
@@ -355,7 +366,9 @@ class MAPPOTrainer:
 
     def train(self, buffer, update_actor=True):
         p, lib = self.policy, self.policy.lib
-        T, E, N = buffer.episode_length, buffer.n_rollout_threads, p.n_agents
+        # E = rows of the per-env arrays (values, returns, rewards): env instances, or (env, agent) pairs when the critic
+        # is decentralised; N = agent rows per such row (p.n_agents is 1 in that case)
+        T, E, N = buffer.episode_length, buffer.n_value_rows, p.n_agents
         s = p._stream()
         ptr = p._ptr
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
@@ -363,7 +376,7 @@ class MAPPOTrainer:
                                              ptr(self._stats4), s), "dcc_mappo_train_begin")
         self.comm.all_reduce_sum_(self._stats4)
         rows_global = float(T) * float(E) * self.comm.world if getattr(buffer, "n_envs_global", None) is None \
-            else float(T) * float(buffer.n_envs_global)
+            else float(T) * float(buffer.n_envs_global) * (E // buffer.n_rollout_threads)
         self._epoch_stats.zero_()
         self._gnorm_sq.zero_()
         nmb = self.num_mini_batch

@@ -32,23 +32,34 @@ class SharedReplayBuffer(object):
         self.act_dim = int(act_space.shape[0])
         self.device = torch.device("cuda", int(getattr(cfg, "device", 0) or 0)) if device is None else torch.device(device)
         T, E, N, D = self.episode_length, self.n_rollout_threads, self.num_agents, self.obs_dim
+        # centralised critic (share_obs = the env's N rows concatenated): one value / return / reward row per env.
+        # use_centralized_V: false (cent_obs_space is obs_space, learner.py:43-46): one per (env, agent), and the learner
+        # kernels see E*N pseudo-envs with one agent each.
+        self.centralized = int(cent_obs_space.shape[0]) != self.obs_dim or N == 1
+        self.n_value_rows = E if self.centralized else E * N
+        self.agents_per_value_row = N if self.centralized else 1
+        V = self.n_value_rows
         kw = dict(dtype=torch.float32, device=self.device)
         self.obs = torch.zeros((T + 1, E, N, D), **kw)
         self.actions = torch.zeros((T, E, N, self.act_dim), **kw)
         self.action_log_probs_ten = torch.zeros((T, E, N), **kw)   # one column (the reference stores 2 equal ones)
-        self.values_te = torch.zeros((T + 1, E), **kw)
-        self.returns_te = torch.zeros((T + 1, E), **kw)
-        self.rewards_te = torch.zeros((T, E), **kw)
-        self.masks_te = torch.ones((T + 1, E), **kw)
+        self.values_te = torch.zeros((T + 1, V), **kw)
+        self.returns_te = torch.zeros((T + 1, V), **kw)
+        self.rewards_te = torch.zeros((T, V), **kw)
+        self.masks_te = torch.ones((T + 1, V), **kw)
         self.step = 0
 
     # ---- reference-shaped views (no copies) ---------------------------------------------------------------
     @property
     def share_obs(self):
         T1, E, N, D = self.obs.shape
+        if not self.centralized:
+            return self.obs
         return self.obs.view(T1, E, 1, N * D).expand(T1, E, N, N * D)
 
     def _per_agent(self, x):
+        if not self.centralized:
+            return x.view(x.shape[0], self.n_rollout_threads, self.num_agents, 1)
         return x[:, :, None, None].expand(x.shape[0], x.shape[1], self.num_agents, 1)
 
     @property
@@ -88,9 +99,11 @@ class SharedReplayBuffer(object):
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src.reshape(dst.shape))
 
-        def per_env(x):   # (E,N,1) / (E*N,1) / (E,) -> (E,)
+        def per_env(x):   # (E,N,1) / (E*N,1) / (E,) -> one entry per value row
             x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
-            return x if x.numel() == E else x.reshape(E, N, -1)[:, 0, 0]
+            if x.numel() == self.n_value_rows:
+                return x.reshape(self.n_value_rows)
+            return x.reshape(E, N, -1)[:, 0, 0]
 
         put(self.obs[t + 1], obs)
         put(self.actions[t], actions)
@@ -106,7 +119,7 @@ class SharedReplayBuffer(object):
         and policy kernels; this stores the per-env reward and mask = 1 - done (learner.py:266-267) — one kernel."""
         t = self.step
         _lib.check(self.lib.dcc_rollout_insert(C.c_void_p(rew_en.data_ptr()), C.c_void_p(done_en.data_ptr()),
-                                               self.n_rollout_threads, self.num_agents,
+                                               self.n_value_rows, self.agents_per_value_row,
                                                C.c_void_p(self.rewards_te[t].data_ptr()),
                                                C.c_void_p(self.masks_te[t + 1].data_ptr()), self._stream()),
                    "dcc_rollout_insert")
@@ -118,10 +131,10 @@ class SharedReplayBuffer(object):
         because it never stores bad_masks (they stay 1, learner.py:272-276).  The branch taken is the learner
         handle's cfg.  next_value: (E,) / (E*N,1) / (E,N,1), or None if the
         bootstrap value already sits in values_te[T]."""
-        T, E, N = self.episode_length, self.n_rollout_threads, self.num_agents
+        T, E, N = self.episode_length, self.n_value_rows, self.num_agents
         if next_value is not None:
             nv = torch.as_tensor(next_value, dtype=torch.float32, device=self.device)
-            nv = nv if nv.numel() == E else nv.reshape(E, N, -1)[:, 0, 0]
+            nv = nv if nv.numel() == E else nv.reshape(self.n_rollout_threads, N, -1)[:, 0, 0]
             if nv.data_ptr() != self.values_te[T].data_ptr():
                 self.values_te[T].copy_(nv.reshape(E))
         h = policy._h if policy is not None else self._gae_handle()

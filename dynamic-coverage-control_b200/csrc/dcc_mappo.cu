@@ -23,11 +23,13 @@ namespace dcc {
 struct NetLayout {
     int in, H, out;
     int inp;   // `in` rounded up to a multiple of 32: leading dimension of the xhat scratch (zero-padded)
+    bool has_ln0;   // use_feature_normalization: feature_norm.weight / .bias present
     size_t ln0_g, ln0_b, W1, b1, ln1_g, ln1_b, W2, b2, ln2_g, ln2_b, Wh, bh, logstd, total;
-    void init(int in_, int H_, int out_, bool has_logstd) {
-        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32;
+    void init(int in_, int H_, int out_, bool has_logstd, bool has_ln0_) {
+        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32; has_ln0 = has_ln0_;
         size_t o = 0;
-        ln0_g = o; o += in; ln0_b = o; o += in;
+        ln0_g = o; if (has_ln0) o += in;
+        ln0_b = o; if (has_ln0) o += in;
         W1 = o; o += (size_t)H * in; b1 = o; o += H; ln1_g = o; o += H; ln1_b = o; o += H;
         W2 = o; o += (size_t)H * H; b2 = o; o += H; ln2_g = o; o += H; ln2_b = o; o += H;
         Wh = o; o += (size_t)out * H; bh = o; o += out;
@@ -59,6 +61,8 @@ constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
 
 // ValueNorm state as of train_begin (advantages use it), or nullptr without a value normaliser
 static inline const float *vn_snapshot(const MappoHandle *h) { return h->cfg.use_valuenorm ? h->vn_gae : nullptr; }
+
+static inline int act_of(const MappoHandle *h) { return h->cfg.use_relu ? ACT_RELU : ACT_TANH; }
 
 static MappoHandle *as_mappo(void *h) {
     MappoHandle *m = static_cast<MappoHandle *>(h);
@@ -146,6 +150,7 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = (K + tc::TC_BK - 1) / tc::TC_BK; p.lda = lda; p.ldc = ldc;
     p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
+    p.act = act_of(h);
     const int row_tiles = (M + tc::TC_BM - 1) / tc::TC_BM;
     // split-K only to fill the GPU when there are few row tiles and a long K (raw-store epilogue only)
     p.splits = 1;
@@ -210,7 +215,8 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
-    fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W1, P + L.b1, P + L.ln0_g, P + L.ln0_b, w1g, b1g, L.H, L.in);
+    fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W1, P + L.b1, L.has_ln0 ? P + L.ln0_g : nullptr,
+                                                  L.has_ln0 ? P + L.ln0_b : nullptr, w1g, b1g, L.H, L.in);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     if (h->backend == 2) {
@@ -230,11 +236,11 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
     const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
     // input LayerNorm (without affine): register-resident single-pass variant when the rows are 16-byte aligned
     if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 8)
-        ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
+        ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 24)
-        ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
+        ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else
-        ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv);
+        ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     h->launches++;
     int rc;
     if (h->backend == 2) {
@@ -250,13 +256,13 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a1, b1g, P + L.ln1_g, P + L.ln1_b,
                                                                             save ? h->a1 : nullptr, h->h1, h->mean1,
-                                                                            h->rstd1, rows, H);
+                                                                            h->rstd1, rows, H, act_of(h));
     h->launches++;
     rc = launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
     if (rc) return rc;
     bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a2, P + L.b2, P + L.ln2_g, P + L.ln2_b,
                                                                             save ? h->a2 : nullptr, h->h2, h->mean2,
-                                                                            h->rstd2, rows, H);
+                                                                            h->rstd2, rows, H, act_of(h));
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -274,10 +280,10 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     // head backward + ReLU/LayerNorm backward of block 2 in one pass: dA := dz2
     if (L.out == 2)
         head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
-                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
+                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H, act_of(h));
     else
         head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
-                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H);
+                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H, act_of(h));
     h->launches++;
     int rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, h->dA, H, h->h1, H, G + L.W2, H, s)     // dW2 += dz2^T h1
                              : launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);
@@ -286,7 +292,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                          : launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);
     if (rc) return rc;
     relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
-                                               G + L.ln1_b, G + L.b1, rows, H);   // dB := dz1
+                                               G + L.ln1_b, G + L.b1, rows, H, act_of(h));   // dB := dz1
     h->launches++;
     rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, h->dB, H, h->x0, L.inp, G + L.W1, L.in, s)         // G1 += dz1^T xhat
                          : launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.inp, G + L.W1, L.in, true, s);
@@ -296,6 +302,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
 }
 
 static int ln0_finalize(MappoHandle *h, const NetLayout &L, const float *P, float *G, cudaStream_t s) {
+    if (!L.has_ln0) return DCC_OK;   // no feature_norm: the fc1 slot already holds dW1 = dz1^T x
     ln0_finalize_kernel<<<(L.in + 127) / 128, 128, 0, s>>>(P + L.W1, P + L.ln0_g, P + L.ln0_b, G + L.W1, G + L.b1, G + L.ln0_g,
                                                           G + L.ln0_b, L.H, L.in);
     h->launches++;
@@ -333,7 +340,7 @@ int dcc_mappo_cfg_default(dcc_mappo_cfg *c) {
     c->max_grad_norm = 10.0f; c->gamma = 0.99f; c->gae_lambda = 0.95f; c->opti_eps = 1e-5f; c->vn_beta = 0.99999;
     c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f;
     c->use_huber_loss = 1; c->use_clipped_value_loss = 1; c->use_max_grad_norm = 1; c->use_valuenorm = 1; c->use_gae = 1;
-    c->weight_decay = 0.f;
+    c->weight_decay = 0.f; c->use_feature_normalization = 1; c->use_relu = 1;
     return DCC_OK;
 }
 
@@ -357,8 +364,8 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->magic = MAPPO_MAGIC; h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
     h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
-    h->la.init(D, H, cfg->act_dim, true);
-    h->lc.init(N * D, H, 1, false);
+    h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0);
+    h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0);
     // chunk: bound the scratch to ~1.5 GB unless the caller asks for a size
     long chunk = cfg->chunk_rows;
     if (chunk <= 0) {

@@ -111,6 +111,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
     }
 }
 
+// ---- trunk activation (mlp.py:13: [nn.Tanh(), nn.ReLU()][use_ReLU]) -----------------------------------------------
+enum { ACT_RELU = 0, ACT_TANH = 1 };
+__device__ __forceinline__ float act_fwd(float z, int act) { return act == ACT_RELU ? fmaxf(z, 0.f) : tanhf(z); }
+// derivative expressed through the saved OUTPUT a = act(z): relu' = [a > 0], tanh' = 1 - a^2
+__device__ __forceinline__ float act_bwd(float da, float a, int act) {
+    return act == ACT_RELU ? (a > 0.f ? da : 0.f) : da * (1.f - a * a);
+}
+
 // ---- row-wise kernels: one warp per row ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -127,21 +135,25 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // multiples of 32).
 // ridx (optional, minibatch path): output row r is computed from source row ridx[r] / rdiv (agent-row indices of a
 // permutation; rdiv = N maps them to centralised rows for the critic).
+// normalize == 0 (use_feature_normalization = false, mlp.py:52-53): plain copy into the padded layout.
 __global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo,
-                                       const long long *__restrict__ ridx, int rdiv) {
+                                       const long long *__restrict__ ridx, int rdiv, int normalize) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
         const size_t sr = ridx ? (size_t)(ridx[r] / rdiv) : (size_t)r;
         const float *xr = x + sr * F;
-        float s = 0.f;
-        for (int c = lane; c < F; c += 32) s += xr[c];
-        const float mean = warp_sum_f(s) / (float)F;
-        float q = 0.f;
-        for (int c = lane; c < F; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
-        const float rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
+        float mean = 0.f, rstd = 1.f;
+        if (normalize) {
+            float s = 0.f;
+            for (int c = lane; c < F; c += 32) s += xr[c];
+            mean = warp_sum_f(s) / (float)F;
+            float q = 0.f;
+            for (int c = lane; c < F; c += 32) { const float d = xr[c] - mean; q = fmaf(d, d, q); }
+            rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
+        }
         float *yr = xhat + (size_t)r * ldo;
-        for (int c = lane; c < ldo; c += 32) yr[c] = (c < F) ? (xr[c] - mean) * rstd : 0.f;
+        for (int c = lane; c < ldo; c += 32) yr[c] = (c < F) ? (normalize ? (xr[c] - mean) * rstd : xr[c]) : 0.f;
     }
 }
 
@@ -149,7 +161,7 @@ __global__ void ln_noaffine_fwd_kernel(const float *__restrict__ x, float *__res
 // global read pass with 16-byte loads, NV float4 per lane (the critic's centralised input: F = N*D = 2704 -> NV = 22).
 template <int NV>
 __global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo,
-                                           const long long *__restrict__ ridx, int rdiv) {
+                                           const long long *__restrict__ ridx, int rdiv, int normalize) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int F4 = F >> 2, L4 = ldo >> 2;
@@ -164,16 +176,19 @@ __global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *_
             v[i] = (c < F4) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
-        const float mean = warp_sum_f(s) / (float)F;
-        float q = 0.f;
+        float mean = 0.f, rstd = 1.f;
+        if (normalize) {
+            mean = warp_sum_f(s) / (float)F;
+            float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            if (lane + 32 * i < F4) {
-                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+            for (int i = 0; i < NV; ++i) {
+                if (lane + 32 * i < F4) {
+                    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                    q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+                }
             }
+            rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
         }
-        const float rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
         float4 *yr = reinterpret_cast<float4 *>(xhat + (size_t)r * ldo);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -195,8 +210,8 @@ __global__ void fold_ln0_kernel(const float *__restrict__ W1, const float *__res
     float s = 0.f;
     for (int c = lane; c < F; c += 32) {
         const float w = W1[(size_t)h * F + c];
-        W1g[(size_t)h * F + c] = w * g0[c];
-        s = fmaf(w, be0[c], s);
+        W1g[(size_t)h * F + c] = g0 ? w * g0[c] : w;      // g0 == nullptr: no feature_norm, fc1 is used as is
+        if (g0) s = fmaf(w, be0[c], s);
     }
     s = warp_sum_f(s);
     if (lane == 0) b1g[h] = b1[h] + s;
@@ -226,11 +241,11 @@ __global__ void ln0_finalize_kernel(const float *__restrict__ W1, const float *_
     dbe0[c] = ab;
 }
 
-// a = relu(z + bias); h = LayerNorm(a) * gamma + beta.  H <= 256 (8 columns per lane).  a_out optional.
+// a = act(z + bias); h = LayerNorm(a) * gamma + beta.  H <= 256 (8 columns per lane).  a_out optional.
 __global__ void bias_relu_ln_fwd_kernel(const float *__restrict__ z, const float *__restrict__ bias,
                                         const float *__restrict__ gamma, const float *__restrict__ beta,
                                         float *__restrict__ a_out, float *__restrict__ h_out, float *__restrict__ mean_out,
-                                        float *__restrict__ rstd_out, int rows, int H) {
+                                        float *__restrict__ rstd_out, int rows, int H, int act) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
@@ -239,7 +254,7 @@ __global__ void bias_relu_ln_fwd_kernel(const float *__restrict__ z, const float
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
-            a[j] = (c < H) ? fmaxf(z[(size_t)r * H + c] + bias[c], 0.f) : 0.f;
+            a[j] = (c < H) ? act_fwd(z[(size_t)r * H + c] + bias[c], act) : 0.f;
             s += a[j];
         }
         const float mean = warp_sum_f(s) / (float)H;
@@ -294,7 +309,7 @@ __device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float 
 __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
                                    const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
                                    float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
-                                   int H) {
+                                   int H, int act) {
     extern __shared__ float dyn_sm[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -328,7 +343,7 @@ __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__
             const int c = lane + 32 * j;
             if (c < H) {
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
-                const float v = (av[j] > 0.f) ? da : 0.f;
+                const float v = act_bwd(da, av[j], act);
                 dz[(size_t)r * H + c] = v;
                 acc[2][j] += v;
             }
@@ -350,7 +365,7 @@ __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const fl
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
                                         float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dWh,
-                                        float *__restrict__ dbh, int rows, int H) {
+                                        float *__restrict__ dbh, int rows, int H, int act) {
     extern __shared__ float dyn_sm[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -395,7 +410,7 @@ __global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const fl
             const int c = lane + 32 * j;
             if (c < H) {
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
-                const float v = (av[j] > 0.f) ? da : 0.f;
+                const float v = act_bwd(da, av[j], act);
                 dz[(size_t)r * H + c] = v;
                 acc[2][j] += v;
             }

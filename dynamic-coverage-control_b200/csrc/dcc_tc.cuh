@@ -226,7 +226,7 @@ struct TcfParams {
     int M, K, KT, lda, ldc;
     // split-K for load balance when there are few row tiles (partials combined with red.global.add; C zeroed first)
     int splits, kt_per_split;
-    // fused epilogue (EPI_BIAS_RELU_LN): a = relu(z + bias); h = LayerNorm(a) * gamma + beta (mlp.py:19-22)
+    // fused epilogue (EPI_BIAS_RELU_LN): a = act(z + bias); h = LayerNorm(a) * gamma + beta (mlp.py:19-22)
     int epi;
     const float *bias, *gamma, *beta;
     float *H;            // [M, ldc]
@@ -238,6 +238,7 @@ struct TcfParams {
     // and ONE cp.async.bulk.tensor store per box leaves asynchronously: no shared-memory read-back, no st.global issue
     // or store-queue stalls in the epilogue warps, rows past M are clipped by the hardware.
     int use_tma;
+    int act;             // trunk activation of the fused epilogue: 0 = ReLU, 1 = tanh (mappo.yaml use_ReLU)
     alignas(64) CUtensorMap tmC, tmH;
 };
 
@@ -494,14 +495,26 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             float mean = 0.f, rstd = 0.f;
             if (p.epi == TCF_EPI_BIAS_RELU_LN) {
                 float sum = 0.f;
+                if (p.act == 0) {
 #pragma unroll
-                for (int c4 = 0; c4 < 32; ++c4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
-                    acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
-                    acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
-                    acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
-                    acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
-                    sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                        acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
+                        acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
+                        acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
+                        acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
+                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                        acc[4 * c4 + 0] = tanhf(acc[4 * c4 + 0] + bv.x);
+                        acc[4 * c4 + 1] = tanhf(acc[4 * c4 + 1] + bv.y);
+                        acc[4 * c4 + 2] = tanhf(acc[4 * c4 + 2] + bv.z);
+                        acc[4 * c4 + 3] = tanhf(acc[4 * c4 + 3] + bv.w);
+                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    }
                 }
                 sts32(rs_u32 + (half * 128 + rl) * 4, sum);
                 named_bar_sync(1, 256);

@@ -60,7 +60,9 @@ class Learner:
         self.action_dim_n = [self.train_envs.action_space[i].shape[0] for i in range(self.n_agents)]
 
         # 2. rl agent (one shared policy for all agents, learner.py:48-57)
-        self.share_observation_space = self.train_envs.share_observation_space[0]
+        # learner.py:43-46: a decentralised critic (use_centralized_V: false) takes the agent's own observation
+        self.share_observation_space = self.train_envs.share_observation_space[0] if getattr(cfg, "use_centralized_V", True) \
+            else self.train_envs.observation_space[0]
         self.policy = MAPPOPolicy(cfg, self.train_envs.observation_space[0], self.share_observation_space,
                                   self.train_envs.action_space[0], device=self.train_envs.device)
         self.trainer = MAPPOTrainer(cfg=cfg, policy=self.policy, comm=self.comm)

@@ -73,16 +73,18 @@ def check_supported(cfg):
     """Branches of mappo.yaml the B200 path implements: everything the shipped configuration enables plus the
     update-path switches (use_huber_loss, use_clipped_value_loss, use_max_grad_norm, use_valuenorm, use_gae,
     use_proper_time_limits, weight_decay, num_mini_batch, use_linear_lr_decay, the *_active_masks flags — no-ops
-    in the reference, whose active masks are all ones).  The rest (config-dead in the reference)
-    is refused loudly instead of silently computing something else."""
+    in the reference, whose active masks are all ones) and the network switches use_ReLU (tanh trunk),
+    use_feature_normalization, use_orthogonal (xavier init), use_centralized_V (per-agent critic).
+    Refused loudly instead of silently computing something else: recurrent policies and layer_N != 1 (other kernel
+    shapes) and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
+    tensor to an nn.Parameter attribute and raises TypeError on the first update, popart.py:61)."""
     bad = []
     if getattr(cfg, "use_recurrent_policy", False) or getattr(cfg, "use_naive_recurrent_policy", False):
         bad.append("recurrent policies")
     if getattr(cfg, "use_popart", False):
         bad.append("use_popart")
-    for key in ("use_feature_normalization", "use_ReLU", "use_centralized_V"):
-        if not getattr(cfg, key, True):
-            bad.append("%s=false" % key)
+    if getattr(cfg, "use_stacked_frames", False) or int(getattr(cfg, "stacked_frames", 1)) != 1:
+        bad.append("stacked frames")
     if int(getattr(cfg, "num_mini_batch", 1)) < 1:
         bad.append("num_mini_batch < 1")
     if int(getattr(cfg, "layer_N", 1)) != 1:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 2
+#define DCC_ABI_VERSION 3
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -205,9 +205,10 @@ typedef struct dcc_mappo_cfg {
     int32_t use_max_grad_norm;       /* 1: clip_grad_norm_(max_grad_norm); 0: norm reported, gradients unscaled   mappo.py:176-181 */
     int32_t use_valuenorm;           /* 1: ValueNorm on returns; 0: value_normalizer = None (raw returns)         mappo.py:96-101 */
     int32_t use_gae;                 /* 1: GAE; 0: discounted returns bootstrapped from the RAW next value        shared_buffer.py:199-212 */
-    int32_t reserved1;
+    int32_t use_feature_normalization; /* 1: LayerNorm on the raw input (mlp.py:44-45,52-53); 0: the flat parameter buffers have no
+                                          feature_norm.weight / .bias entries and fc1 sees the raw observation */
     float weight_decay;              /* 0: torch.optim.Adam L2 term, grad += weight_decay * param (after the clip) mappo.py:30-37 */
-    float reserved2;
+    int32_t use_relu;                /* 1: ReLU trunk; 0: tanh (mlp.py:13 `[nn.Tanh(), nn.ReLU()][use_ReLU]`) */
 } dcc_mappo_cfg;
 
 int dcc_mappo_cfg_default(dcc_mappo_cfg *cfg);

@@ -44,14 +44,24 @@ def ln_bwd(dy, cache, g):
 
 
 class MLPNet:
-    """feature_norm -> [Linear, ReLU, LayerNorm] x 2 -> head   (mlp.py:19-22,46-54; fc_h is never used)."""
+    """feature_norm -> [Linear, act, LayerNorm] x 2 -> head   (mlp.py:13-29,44-58; fc_h is never used).
+    act = "relu" | "tanh" (use_ReLU); the input LayerNorm is skipped when the parameters carry no
+    base.feature_norm.* entries (use_feature_normalization: false)."""
     TRUNK = ("base.feature_norm.weight", "base.feature_norm.bias", "base.mlp.fc1.0.weight", "base.mlp.fc1.0.bias",
              "base.mlp.fc1.2.weight", "base.mlp.fc1.2.bias", "base.mlp.fc2.0.0.weight", "base.mlp.fc2.0.0.bias",
              "base.mlp.fc2.0.2.weight", "base.mlp.fc2.0.2.bias")
 
-    def __init__(self, params, head_w, head_b):
+    def __init__(self, params, head_w, head_b, act="relu"):
         self.p = {k: np.asarray(v, dtype=np.float64).copy() for k, v in params.items()}
         self.head_w, self.head_b = head_w, head_b
+        self.act = act
+        self.fnorm = "base.feature_norm.weight" in self.p
+
+    def _act(self, z):
+        return np.maximum(z, 0) if self.act == "relu" else np.tanh(z)
+
+    def _dact(self, da, z, a):
+        return da * (z > 0) if self.act == "relu" else da * (1.0 - a * a)
 
     def names(self):
         return [k for k in self.p]
@@ -59,44 +69,48 @@ class MLPNet:
     def forward(self, x):
         p = self.p
         x = np.asarray(x, dtype=np.float64)
-        h0, c0 = ln_fwd(x, p["base.feature_norm.weight"], p["base.feature_norm.bias"])
+        if self.fnorm:
+            h0, c0 = ln_fwd(x, p["base.feature_norm.weight"], p["base.feature_norm.bias"])
+        else:
+            h0, c0 = x, None
         z1 = h0 @ p["base.mlp.fc1.0.weight"].T + p["base.mlp.fc1.0.bias"]
-        a1 = np.maximum(z1, 0)
+        a1 = self._act(z1)
         h1, c1 = ln_fwd(a1, p["base.mlp.fc1.2.weight"], p["base.mlp.fc1.2.bias"])
         z2 = h1 @ p["base.mlp.fc2.0.0.weight"].T + p["base.mlp.fc2.0.0.bias"]
-        a2 = np.maximum(z2, 0)
+        a2 = self._act(z2)
         h2, c2 = ln_fwd(a2, p["base.mlp.fc2.0.2.weight"], p["base.mlp.fc2.0.2.bias"])
         out = h2 @ p[self.head_w].T + p[self.head_b]
-        self.cache = (h0, c0, z1, h1, c1, z2, h2, c2)
+        self.cache = (h0, c0, z1, a1, h1, c1, z2, a2, h2, c2)
         return out
 
     def backward(self, dout):
         p = self.p
-        h0, c0, z1, h1, c1, z2, h2, c2 = self.cache
+        h0, c0, z1, a1, h1, c1, z2, a2, h2, c2 = self.cache
         g = {}
         g[self.head_w] = dout.T @ h2
         g[self.head_b] = dout.sum(0)
         dh2 = dout @ p[self.head_w]
         da2, g["base.mlp.fc2.0.2.weight"], g["base.mlp.fc2.0.2.bias"] = ln_bwd(dh2, c2, p["base.mlp.fc2.0.2.weight"])
-        dz2 = da2 * (z2 > 0)
+        dz2 = self._dact(da2, z2, a2)
         g["base.mlp.fc2.0.0.weight"] = dz2.T @ h1
         g["base.mlp.fc2.0.0.bias"] = dz2.sum(0)
         dh1 = dz2 @ p["base.mlp.fc2.0.0.weight"]
         da1, g["base.mlp.fc1.2.weight"], g["base.mlp.fc1.2.bias"] = ln_bwd(dh1, c1, p["base.mlp.fc1.2.weight"])
-        dz1 = da1 * (z1 > 0)
+        dz1 = self._dact(da1, z1, a1)
         g["base.mlp.fc1.0.weight"] = dz1.T @ h0
         g["base.mlp.fc1.0.bias"] = dz1.sum(0)
-        dh0 = dz1 @ p["base.mlp.fc1.0.weight"]
-        _, g["base.feature_norm.weight"], g["base.feature_norm.bias"] = ln_bwd(dh0, c0, p["base.feature_norm.weight"])
+        if self.fnorm:
+            dh0 = dz1 @ p["base.mlp.fc1.0.weight"]
+            _, g["base.feature_norm.weight"], g["base.feature_norm.bias"] = ln_bwd(dh0, c0, p["base.feature_norm.weight"])
         return g
 
 
-def make_actor(params):
-    return MLPNet(params, "act.action_out.fc_mean.weight", "act.action_out.fc_mean.bias")
+def make_actor(params, act="relu"):
+    return MLPNet(params, "act.action_out.fc_mean.weight", "act.action_out.fc_mean.bias", act)
 
 
-def make_critic(params):
-    return MLPNet(params, "v_out.weight", "v_out.bias")
+def make_critic(params, act="relu"):
+    return MLPNet(params, "v_out.weight", "v_out.bias", act)
 
 
 def gaussian_logp_entropy(mean, logstd, action):
@@ -201,11 +215,12 @@ def clip_grads(grads, max_norm, do_clip=True):
 
 class Trainer:
     """MAPPOTrainer.train on a recorded rollout buffer (algos/mappo.py:189-227).  hp may carry the mappo.yaml
-    switches use_huber_loss / use_clipped_value_loss / use_max_grad_norm / use_valuenorm (default True),
-    weight_decay (0) and num_mini_batch (1)."""
+    switches use_huber_loss / use_clipped_value_loss / use_max_grad_norm / use_valuenorm / use_ReLU /
+    use_centralized_V (default True), weight_decay (0) and num_mini_batch (1)."""
 
     def __init__(self, actor_params, critic_params, hp, vn_state=(0.0, 0.0, 0.0)):
-        self.actor, self.critic = make_actor(actor_params), make_critic(critic_params)
+        act = "relu" if hp.get("use_ReLU", True) else "tanh"
+        self.actor, self.critic = make_actor(actor_params, act), make_critic(critic_params, act)
         self.hp = hp
         self.vn = ValueNorm(vn_state) if hp.get("use_valuenorm", True) else None
         wd = float(hp.get("weight_decay", 0.0))
@@ -224,7 +239,10 @@ class Trainer:
         adv = returns[:-1].astype(np.float64) - (self.vn.denormalize(vp) if self.vn is not None else vp)
         adv = (adv - adv.mean()) / (adv.std() + 1e-5)
         x_all = obs[:-1].reshape(B, -1).astype(np.float64)
-        sx_all = np.repeat(obs[:-1].reshape(T * E, 1, -1), N, axis=1).reshape(B, -1).astype(np.float64)
+        if hp.get("use_centralized_V", True):
+            sx_all = np.repeat(obs[:-1].reshape(T * E, 1, -1), N, axis=1).reshape(B, -1).astype(np.float64)
+        else:                       # decentralised critic: share_obs = obs (learner.py:221-222,272-273)
+            sx_all = x_all
         act_all = actions.reshape(B, -1).astype(np.float64)
         lpo_all = logp_old.reshape(B, 1).astype(np.float64)
         vold_all = value_preds[:-1].reshape(B, 1).astype(np.float64)

@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 from ref_harness import REF_ROOT, load_reference  # noqa: E402
-from mappo_util import actor_param_shapes, critic_param_shapes, make_params, sample_tensor  # noqa: E402
+from mappo_util import make_params, net_shapes, sample_tensor  # noqa: E402
 
 
 def build_learner(N, M, E, T, hidden, ppo_epoch, seed, force_scale=0.0, extra=None):
@@ -83,7 +83,9 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
     import torch
     lr, cfg = build_learner(N, M, E, T, hidden, ppo_epoch, seed, extra=extra)
     D = lr.obs_dim_n[0]
-    a_shapes, c_shapes = actor_param_shapes(D, hidden), critic_param_shapes(N * D, hidden)
+    centralized = bool(cfg.use_centralized_V)
+    a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden, use_centralized_V=centralized,
+                                         use_feature_normalization=bool(cfg.use_feature_normalization)))
     set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
     set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
     out = {}
@@ -98,7 +100,10 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
         out[p + "actions"] = buf.actions.copy()
         out[p + "logp"] = buf.action_log_probs[..., 0:1].copy()
         assert np.array_equal(buf.action_log_probs[..., 0], buf.action_log_probs[..., 1])
-        assert np.array_equal(buf.share_obs[:, :, 0], buf.obs.reshape(T + 1, E, -1))
+        if centralized:
+            assert np.array_equal(buf.share_obs[:, :, 0], buf.obs.reshape(T + 1, E, -1))
+        else:
+            assert np.array_equal(buf.share_obs, buf.obs)
         out[p + "value_preds"] = buf.value_preds.copy()
         out[p + "rewards"] = buf.rewards.copy()
         out[p + "masks"] = buf.masks.copy()
@@ -140,9 +145,32 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
                 use_huber_loss=bool(cfg.use_huber_loss), use_clipped_value_loss=bool(cfg.use_clipped_value_loss),
                 use_max_grad_norm=bool(cfg.use_max_grad_norm), use_valuenorm=bool(cfg.use_valuenorm),
                 use_gae=bool(cfg.use_gae), use_proper_time_limits=bool(cfg.use_proper_time_limits),
-                weight_decay=float(cfg.weight_decay), num_mini_batch=int(cfg.num_mini_batch))
+                weight_decay=float(cfg.weight_decay), num_mini_batch=int(cfg.num_mini_batch),
+                use_ReLU=bool(cfg.use_ReLU), use_feature_normalization=bool(cfg.use_feature_normalization),
+                use_centralized_V=centralized)
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "mappo_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.0f KB" % (os.path.getsize(path) / 1024))
+    lr.train_envs.close()
+
+
+def run_init_case(name, N, M, hidden, seed, extra=None):
+    """Initial parameters exactly as the reference draws them for `seed` (before the harness overwrites them): per tensor
+    a strided sample + float64 sum / sum of squares.  Pins MAPPOPolicy's reference-order initialisation."""
+    lr, cfg = build_learner(N, M, 1, 4, hidden, 1, seed, extra=extra)
+    out = {}
+    for tag, mod in (("actor", lr.policy.actor), ("critic", lr.policy.critic)):
+        for k, v in mod.state_dict().items():
+            s = sample_tensor(v.numpy(), max_full=512)
+            out[tag + "." + k + ":sample"] = s["sample"]
+            out[tag + "." + k + ":meta"] = np.array([s["stride"], s["sum"], s["sumsq"]], dtype=np.float64)
+    meta = dict(name=name, n_agents=N, n_pois=M, hidden=hidden, seed=seed, obs_dim=lr.obs_dim_n[0], gain=float(cfg.gain),
+                use_orthogonal=bool(cfg.use_orthogonal), use_ReLU=bool(cfg.use_ReLU),
+                use_feature_normalization=bool(cfg.use_feature_normalization),
+                use_centralized_V=bool(cfg.use_centralized_V))
+    out["cfg"] = np.array(json.dumps(meta))
+    path = os.path.join(HERE, "init_%s.npz" % name)
     np.savez_compressed(path, **out)
     print("wrote", path, "%.0f KB" % (os.path.getsize(path) / 1024))
     lr.train_envs.close()
@@ -161,6 +189,15 @@ def main():
     run_case("flags_novn_gae", 3, 20, 2, 9, 32, 2, seed=5, extra=dict(use_valuenorm=False, use_linear_lr_decay=False))
     run_case("mb2_4x20_h32", 4, 20, 3, 10, 32, 3, seed=6, extra=dict(num_mini_batch=2))
     run_case("mb3_3x20_h256", 3, 20, 3, 7, 256, 2, seed=7, extra=dict(num_mini_batch=4))   # 63 rows * 3 agents, tail dropped
+    # network switches: tanh trunk, no input LayerNorm, per-agent (decentralised) critic
+    run_case("net_tanh_nofn_h32", 4, 20, 3, 10, 32, 3, seed=8, extra=dict(use_ReLU=False, use_feature_normalization=False))
+    run_case("net_tanh_h256", 4, 20, 3, 8, 256, 3, seed=9, extra=dict(use_ReLU=False))
+    run_case("net_decv_h256", 3, 20, 3, 8, 256, 3, seed=10, extra=dict(use_centralized_V=False))
+    run_case("net_decv_nofn_mb2_h32", 4, 20, 2, 8, 32, 2, seed=11,
+             extra=dict(use_centralized_V=False, use_feature_normalization=False, num_mini_batch=2))
+    run_init_case("ship_4x20", 4, 20, 256, seed=0)
+    run_init_case("xavier_tanh_nofn_decv", 3, 20, 64, seed=5,
+                  extra=dict(use_orthogonal=False, use_ReLU=False, use_feature_normalization=False, use_centralized_V=False))
 
 
 if __name__ == "__main__":

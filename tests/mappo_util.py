@@ -3,8 +3,12 @@ deterministic parameter recipe with the reference's state_dict key names (SURVEY
 import numpy as np
 
 
-def actor_param_shapes(obs_dim, hidden, act_dim=2):
-    return {
+def _maybe_drop_feature_norm(shapes, feature_norm):
+    return shapes if feature_norm else {k: v for k, v in shapes.items() if not k.startswith("base.feature_norm")}
+
+
+def actor_param_shapes(obs_dim, hidden, act_dim=2, feature_norm=True):
+    return _maybe_drop_feature_norm({
         "base.feature_norm.weight": (obs_dim,), "base.feature_norm.bias": (obs_dim,),
         "base.mlp.fc1.0.weight": (hidden, obs_dim), "base.mlp.fc1.0.bias": (hidden,),
         "base.mlp.fc1.2.weight": (hidden,), "base.mlp.fc1.2.bias": (hidden,),
@@ -12,18 +16,27 @@ def actor_param_shapes(obs_dim, hidden, act_dim=2):
         "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
         "act.action_out.fc_mean.weight": (act_dim, hidden), "act.action_out.fc_mean.bias": (act_dim,),
         "act.action_out.logstd._bias": (act_dim, 1),
-    }
+    }, feature_norm)
 
 
-def critic_param_shapes(share_dim, hidden):
-    return {
+def critic_param_shapes(share_dim, hidden, feature_norm=True):
+    return _maybe_drop_feature_norm({
         "base.feature_norm.weight": (share_dim,), "base.feature_norm.bias": (share_dim,),
         "base.mlp.fc1.0.weight": (hidden, share_dim), "base.mlp.fc1.0.bias": (hidden,),
         "base.mlp.fc1.2.weight": (hidden,), "base.mlp.fc1.2.bias": (hidden,),
         "base.mlp.fc2.0.0.weight": (hidden, hidden), "base.mlp.fc2.0.0.bias": (hidden,),
         "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
         "v_out.weight": (1, hidden), "v_out.bias": (1,),
-    }
+    }, feature_norm)
+
+
+def net_shapes(c):
+    """(actor shapes, critic shapes) for a golden's cfg dict: honours use_feature_normalization and use_centralized_V
+    (a decentralised critic reads one agent's observation, learner.py:43-46)."""
+    fn = c.get("use_feature_normalization", True)
+    share = c["n_agents"] * c["obs_dim"] if c.get("use_centralized_V", True) else c["obs_dim"]
+    return (actor_param_shapes(c["obs_dim"], c["hidden"], feature_norm=fn),
+            critic_param_shapes(share, c["hidden"], feature_norm=fn))
 
 
 def make_params(shapes, seed):

@@ -40,8 +40,8 @@ def test_defaults_equal_the_shipped_yaml_files():
 def test_unsupported_branches_fail_loudly():
     from dcc_b200.utils.config import check_supported, load_config
     check_supported(load_config(None))
-    for key, val in (("use_recurrent_policy", True), ("use_popart", True), ("num_mini_batch", 0), ("use_ReLU", False),
-                     ("layer_N", 2), ("use_feature_normalization", False), ("use_centralized_V", False)):
+    for key, val in (("use_recurrent_policy", True), ("use_naive_recurrent_policy", True), ("use_popart", True),
+                     ("num_mini_batch", 0), ("layer_N", 2), ("stacked_frames", 2)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         with pytest.raises(NotImplementedError):
@@ -49,7 +49,8 @@ def test_unsupported_branches_fail_loudly():
     # update-path switches of mappo.yaml that ARE implemented
     for key, val in (("num_mini_batch", 2), ("use_valuenorm", False), ("use_huber_loss", False), ("use_gae", False),
                      ("use_clipped_value_loss", False), ("use_max_grad_norm", False), ("weight_decay", 1e-4),
-                     ("use_proper_time_limits", True), ("use_linear_lr_decay", False)):
+                     ("use_proper_time_limits", True), ("use_linear_lr_decay", False), ("use_ReLU", False),
+                     ("use_feature_normalization", False), ("use_centralized_V", False), ("use_orthogonal", False)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         check_supported(cfg)
@@ -169,3 +170,37 @@ def test_headless_render_and_trajectory_recorder(tmp_path):
     assert z["pos_vel"].shape == (3, 1, N, 4) and z["adj"].shape == (3, 1, N) and z["poi_xy"].shape == (M, 2)
     rec.save_gif(str(tmp_path / "t.gif"), size=64)
     assert os.path.getsize(str(tmp_path / "t.gif")) > 100
+
+
+@pytest.mark.parametrize("name", ["ship_4x20", "xavier_tanh_nofn_decv"])
+def test_reference_order_initialisation(name):
+    """MAPPOPolicy draws its initial weights with the reference's torch RNG consumption order (actor trunk, actor head,
+    critic trunk, critic head; orthogonal / xavier_uniform; ReLU / tanh gain): same seed => the reference's weights.
+    Goldens: tests/golden/make_golden_mappo.py::run_init_case (unmodified reference Learner, seeded by its own
+    seed_everything)."""
+    import json
+    import torch
+    from dcc_b200.algos.mappo import _reference_init
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init_%s.npz" % name))
+    c = json.loads(str(z["cfg"]))
+    D, Hd, N = c["obs_dim"], c["hidden"], c["n_agents"]
+    S = N * D if c["use_centralized_V"] else D
+    kw = dict(use_orthogonal=c["use_orthogonal"], use_relu=c["use_ReLU"], feature_norm=c["use_feature_normalization"])
+    torch.manual_seed(c["seed"])
+    sd_a, head_a = _reference_init(D, Hd, 2, c["gain"], **kw)
+    sd_a["act.action_out.fc_mean.weight"], sd_a["act.action_out.fc_mean.bias"] = head_a.weight.data, head_a.bias.data
+    sd_a["act.action_out.logstd._bias"] = torch.zeros(2, 1)
+    sd_c, head_c = _reference_init(S, Hd, 1, 1.0, **kw)
+    sd_c["v_out.weight"], sd_c["v_out.bias"] = head_c.weight.data, head_c.bias.data
+    n_checked = 0
+    for tag, sd in (("actor", sd_a), ("critic", sd_c)):
+        ref_keys = {k[len(tag) + 1:-7] for k in z.files if k.startswith(tag + ".") and k.endswith(":sample")}
+        assert ref_keys == set(sd.keys()), (tag, ref_keys ^ set(sd.keys()))
+        for k, v in sd.items():
+            flat = v.numpy().astype(np.float64).reshape(-1)
+            stride, s, ss = z["%s.%s:meta" % (tag, k)]
+            # same RNG stream; the QR inside orthogonal_ rounds differently with a different BLAS thread count (~1e-7)
+            assert np.allclose(flat[::int(stride)], z["%s.%s:sample" % (tag, k)], rtol=0, atol=2e-6), (tag, k)
+            assert abs(flat.sum() - s) <= 1e-5 * max(1.0, np.abs(flat).sum()) and abs((flat ** 2).sum() - ss) <= 1e-5 * max(1.0, ss)
+            n_checked += 1
+    assert n_checked >= 26

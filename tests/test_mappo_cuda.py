@@ -14,7 +14,7 @@ from argparse import Namespace
 import numpy as np
 import pytest
 
-from mappo_util import actor_param_shapes, critic_param_shapes, make_params
+from mappo_util import actor_param_shapes, critic_param_shapes, make_params, net_shapes
 
 pytestmark = pytest.mark.gpu
 
@@ -22,7 +22,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "mappo_*.npz")))
 BACKENDS = [1, 0]   # SIMT fp32, auto (tcgen05 3xTF32 where the shape allows)
 FLAG_KEYS = ("use_huber_loss", "use_clipped_value_loss", "use_max_grad_norm", "use_valuenorm", "use_gae",
-             "use_proper_time_limits", "weight_decay", "num_mini_batch")
+             "use_proper_time_limits", "weight_decay", "num_mini_batch", "use_ReLU", "use_feature_normalization",
+             "use_centralized_V")
 
 
 def load(name):
@@ -52,10 +53,12 @@ def build(c, E, T, device=0, **over):
     from dcc_b200.envs.spaces import Box
     cfg = make_cfg(c, E, T, device=device, **over)
     N, D = c["n_agents"], c["obs_dim"]
-    obs_space, share_space, act_space = Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,))
+    S = N * D if c.get("use_centralized_V", True) else D       # decentralised critic: cent_obs_space = obs_space
+    obs_space, share_space, act_space = Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (S,)), Box(-1, 1, (2,))
     pol = MAPPOPolicy(cfg, obs_space, share_space, act_space)
-    pol.actor.load_state_dict(make_params(actor_param_shapes(D, c["hidden"]), c["actor_seed"]))
-    pol.critic.load_state_dict(make_params(critic_param_shapes(N * D, c["hidden"]), c["critic_seed"]))
+    a_shapes, c_shapes = net_shapes(c)
+    pol.actor.load_state_dict(make_params(a_shapes, c["actor_seed"]))
+    pol.critic.load_state_dict(make_params(c_shapes, c["critic_seed"]))
     tr = MAPPOTrainer(cfg, pol)
     buf = SharedReplayBuffer(cfg, obs_space, share_space, act_space)
     torch.cuda.synchronize()
@@ -69,9 +72,10 @@ def fill_buffer(buf, g, p):
     buf.obs.copy_(t(g[p + "obs"]))
     buf.actions.copy_(t(g[p + "actions"]))
     buf.action_log_probs_ten.copy_(t(g[p + "logp"][..., 0]))
-    buf.values_te.copy_(t(g[p + "value_preds"][:, :, 0, 0]))
-    buf.rewards_te.copy_(t(g[p + "rewards"][:, :, 0, 0]))
-    buf.masks_te.copy_(t(g[p + "masks"][:, :, 0, 0]))
+    per_row = (lambda a: a[:, :, 0, 0]) if buf.centralized else (lambda a: a.reshape(a.shape[0], -1))   # noqa: E731
+    buf.values_te.copy_(t(per_row(g[p + "value_preds"])))
+    buf.rewards_te.copy_(t(per_row(g[p + "rewards"])))
+    buf.masks_te.copy_(t(per_row(g[p + "masks"])))
 
 
 def check_params(tag, net, g, prefix, rtol=2e-5, atol=3e-6, max_bad_frac=0.0):
@@ -119,16 +123,18 @@ def test_learner_vs_reference_golden(name, backend):
         assert np.allclose(logp.cpu().numpy().reshape(T, E, N, 1), g[p + "logp"], rtol=1e-5, atol=2e-5)
         vals = pol.get_values(buf.obs.view((T + 1) * E, N * D)).cpu().numpy().reshape(T + 1, E, N, 1)
         assert np.allclose(vals, g[p + "value_preds"], rtol=1e-5, atol=2e-5)
-        # the reference-style call (N identical rows per env) gives the same values
-        v2 = pol.get_values(buf.share_obs[3].reshape(E * N, N * D), rows_repeated=True).cpu().numpy().reshape(E, N, 1)
-        assert np.allclose(v2, vals[3], rtol=2e-6, atol=2e-6)   # batch size changes the split-K summation order
+        if buf.centralized:
+            # the reference-style call (N identical rows per env) gives the same values
+            v2 = pol.get_values(buf.share_obs[3].reshape(E * N, N * D), rows_repeated=True).cpu().numpy().reshape(E, N, 1)
+            assert np.allclose(v2, vals[3], rtol=2e-6, atol=2e-6)   # batch size changes the split-K summation order
         # GAE
         buf.compute_returns(None, tr.value_normalizer, policy=pol)
         ret = buf.returns_te.cpu().numpy()[:-1]
-        ref = g[p + "returns"][:-1, :, 0, 0]
+        ref_all = g[p + "returns"][:, :, 0, 0] if buf.centralized else g[p + "returns"].reshape(T + 1, -1)
+        ref = ref_all[:-1]
         assert np.allclose(ret, ref, rtol=1e-5, atol=1e-4), np.abs(ret - ref).max()
         # the reference trains on ITS returns: replay them exactly
-        buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(g[p + "returns"][:, :, 0, 0])).to(buf.device))
+        buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(ref_all)).to(buf.device))
         pol.lr_decay(it, c["n_iters"])
         assert abs(pol.lr_actor_now - float(g[p + "lr"])) < 1e-12
         if nmb > 1:

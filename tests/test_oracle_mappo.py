@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from mappo_util import actor_param_shapes, critic_param_shapes, make_params
+from mappo_util import make_params, net_shapes
 from oracle import mappo_oracle as mo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -46,9 +46,10 @@ def test_mappo_oracle_vs_reference(name):
     g = load(name)
     c = g["cfg"]
     N, D, Hd = c["n_agents"], c["obs_dim"], c["hidden"]
-    ap = make_params(actor_param_shapes(D, Hd), c["actor_seed"])
-    cp = make_params(critic_param_shapes(N * D, Hd), c["critic_seed"])
+    a_shapes, c_shapes = net_shapes(c)
+    ap, cp = make_params(a_shapes, c["actor_seed"]), make_params(c_shapes, c["critic_seed"])
     tr = mo.Trainer(ap, cp, c)
+    centralized = c.get("use_centralized_V", True)
     for it in range(1, c["iters"] + 1):
         p = "it%d_" % it
         obs, act = g[p + "obs"], g[p + "actions"]
@@ -60,7 +61,8 @@ def test_mappo_oracle_vs_reference(name):
         logp, _ = mo.gaussian_logp_entropy(mean, tr.actor.p["act.action_out.logstd._bias"].reshape(1, -1),
                                            act.reshape(-1, 2))
         assert np.allclose(logp.reshape(T, E, N, 1), g[p + "logp"], rtol=1e-5, atol=2e-5)
-        v = tr.critic.forward(obs.reshape((T + 1) * E, N * D)).reshape(T + 1, E, 1, 1)
+        v = tr.critic.forward(obs.reshape((T + 1) * E, N * D)).reshape(T + 1, E, 1, 1) if centralized else \
+            tr.critic.forward(obs.reshape((T + 1) * E * N, D)).reshape(T + 1, E, N, 1)
         vp = g[p + "value_preds"].copy()
         if not c.get("use_gae", True):
             # the non-GAE branch never stores the bootstrap value in value_preds[T] (shared_buffer.py:209-210 puts it
