@@ -36,7 +36,7 @@ class MappoCfg(C.Structure):
         ("opti_eps", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("vn_beta", C.c_double),
         ("use_huber_loss", C.c_int32), ("use_clipped_value_loss", C.c_int32), ("use_max_grad_norm", C.c_int32),
         ("use_valuenorm", C.c_int32), ("use_gae", C.c_int32), ("use_feature_normalization", C.c_int32),
-        ("weight_decay", C.c_float), ("use_relu", C.c_int32),
+        ("weight_decay", C.c_float), ("use_relu", C.c_int32), ("layer_N", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

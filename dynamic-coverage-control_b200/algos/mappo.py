@@ -27,17 +27,26 @@ from .valuenorm import ValueNorm
 
 TRUNK = ("base.feature_norm.weight", "base.feature_norm.bias", "base.mlp.fc1.0.weight", "base.mlp.fc1.0.bias",
          "base.mlp.fc1.2.weight", "base.mlp.fc1.2.bias", "base.mlp.fc2.0.0.weight", "base.mlp.fc2.0.0.bias",
-         "base.mlp.fc2.0.2.weight", "base.mlp.fc2.0.2.bias")
+         "base.mlp.fc2.0.2.weight", "base.mlp.fc2.0.2.bias")      # the shipped layer_N = 1 trunk
+
+
+def trunk_keys(layer_N=1):
+    """state_dict keys of MLPBase for `layer_N` fc2 blocks (mlp.py:16-29), without the never-used fc_h block."""
+    keys = list(TRUNK[:6])
+    for i in range(layer_N):
+        keys += ["base.mlp.fc2.%d.0.weight" % i, "base.mlp.fc2.%d.0.bias" % i, "base.mlp.fc2.%d.2.weight" % i,
+                 "base.mlp.fc2.%d.2.bias" % i]
+    return keys
 FC_H = ("base.mlp.fc_h.0.weight", "base.mlp.fc_h.0.bias", "base.mlp.fc_h.2.weight", "base.mlp.fc_h.2.bias")
 
 
-def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True):
+def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True, layer_N=1):
     """name -> (offset, shape) of the flat parameter buffer, in the order include/dcc_b200.h documents.
     feature_norm=False (use_feature_normalization: false): the net has no base.feature_norm.* entries (mlp.py:44-45)."""
-    shapes = [(in_dim,), (in_dim,), (hidden, in_dim), (hidden,), (hidden,), (hidden,), (hidden, hidden), (hidden,),
-              (hidden,), (hidden,)]
+    shapes = [(in_dim,), (in_dim,), (hidden, in_dim), (hidden,), (hidden,), (hidden,)] + \
+        [(hidden, hidden), (hidden,), (hidden,), (hidden,)] * layer_N
     lay, off = OrderedDict(), 0
-    for k, shp in zip(TRUNK, shapes):
+    for k, shp in zip(trunk_keys(layer_N), shapes):
         if not feature_norm and k.startswith("base.feature_norm"):
             continue
         lay[k] = (off, shp)
@@ -49,7 +58,7 @@ def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True):
     return lay, off
 
 
-def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use_relu=True, feature_norm=True):
+def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use_relu=True, feature_norm=True, layer_N=1):
     """Initial parameters drawn exactly as the reference constructs a net (same torch RNG consumption order):
     MLPBase -> LayerNorm, fc1 = Linear + orthogonal / xavier_uniform (`use_orthogonal`) with the gain of the trunk
     activation (sqrt 2 for ReLU, 5/3 for tanh), fc_h likewise, fc2 = deepcopy(fc_h) (algos/algo_utils/mlp.py:13-23),
@@ -75,8 +84,9 @@ def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use
     sd["base.mlp.fc1.2.weight"], sd["base.mlp.fc1.2.bias"] = ones(hidden), zeros(hidden)
     sd["base.mlp.fc_h.0.weight"], sd["base.mlp.fc_h.0.bias"] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
     sd["base.mlp.fc_h.2.weight"], sd["base.mlp.fc_h.2.bias"] = ones(hidden), zeros(hidden)
-    sd["base.mlp.fc2.0.0.weight"], sd["base.mlp.fc2.0.0.bias"] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
-    sd["base.mlp.fc2.0.2.weight"], sd["base.mlp.fc2.0.2.bias"] = ones(hidden), zeros(hidden)
+    for i in range(layer_N):     # get_clones(fc_h, layer_N): every fc2 block starts as a copy of fc_h (mlp.py:23)
+        sd["base.mlp.fc2.%d.0.weight" % i], sd["base.mlp.fc2.%d.0.bias" % i] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
+        sd["base.mlp.fc2.%d.2.weight" % i], sd["base.mlp.fc2.%d.2.bias" % i] = ones(hidden), zeros(hidden)
     return sd, head
 
 
@@ -166,20 +176,24 @@ class MAPPOPolicy:
         mc.weight_decay = self.weight_decay
         fnorm, relu = bool(getattr(cfg, "use_feature_normalization", True)), bool(getattr(cfg, "use_ReLU", True))
         mc.use_feature_normalization, mc.use_relu = int(fnorm), int(relu)
+        layer_N = int(getattr(cfg, "layer_N", 1))
+        mc.layer_N = layer_N
         self.mcfg = mc
         h = C.c_void_p()
         _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
         self._h = h
 
-        la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True, feature_norm=fnorm)
-        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out", feature_norm=fnorm)
+        la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True, feature_norm=fnorm,
+                            layer_N=layer_N)
+        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out", feature_norm=fnorm, layer_N=layer_N)
         assert na == self.lib.dcc_mappo_param_count(h, 0) and nc == self.lib.dcc_mappo_param_count(h, 1)
         # one flat gradient buffer for both nets: a single all-reduce per PPO epoch
         self.flat_grads = torch.zeros(na + nc, dtype=torch.float32, device=self.device)
         self.actor = _Net(la, na, self.flat_grads[:na], self.device)
         self.critic = _Net(lc, nc, self.flat_grads[na:], self.device)
         # initial weights: the reference's construction order — actor first, then critic (mappo.py:27-28)
-        init_kw = dict(use_orthogonal=bool(getattr(cfg, "use_orthogonal", True)), use_relu=relu, feature_norm=fnorm)
+        init_kw = dict(use_orthogonal=bool(getattr(cfg, "use_orthogonal", True)), use_relu=relu, feature_norm=fnorm,
+                       layer_N=layer_N)
         sd, head = _reference_init(self.obs_dim, self.hidden, self.act_dim, float(cfg.gain), **init_kw)
         sd["act.action_out.fc_mean.weight"], sd["act.action_out.fc_mean.bias"] = head.weight.data, head.bias.data
         sd["act.action_out.logstd._bias"] = torch.zeros(self.act_dim, 1)

@@ -20,18 +20,23 @@
 
 namespace dcc {
 
+constexpr int MAX_BLOCKS = 4;   // hidden blocks [Linear, act, LayerNorm]: fc1 + layer_N clones of fc_h (layer_N <= 3)
+
 struct NetLayout {
     int in, H, out;
     int inp;   // `in` rounded up to a multiple of 32: leading dimension of the xhat scratch (zero-padded)
+    int nblk;  // 1 + layer_N hidden blocks; block 0 = fc1 (in -> H), blocks 1.. = fc2[i] (H -> H)  (mlp.py:16-29)
     bool has_ln0;   // use_feature_normalization: feature_norm.weight / .bias present
-    size_t ln0_g, ln0_b, W1, b1, ln1_g, ln1_b, W2, b2, ln2_g, ln2_b, Wh, bh, logstd, total;
-    void init(int in_, int H_, int out_, bool has_logstd, bool has_ln0_) {
-        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32; has_ln0 = has_ln0_;
+    size_t ln0_g, ln0_b, W[MAX_BLOCKS], b[MAX_BLOCKS], lg[MAX_BLOCKS], lb[MAX_BLOCKS], Wh, bh, logstd, total;
+    void init(int in_, int H_, int out_, bool has_logstd, bool has_ln0_, int layer_N) {
+        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32; has_ln0 = has_ln0_; nblk = 1 + layer_N;
         size_t o = 0;
         ln0_g = o; if (has_ln0) o += in;
         ln0_b = o; if (has_ln0) o += in;
-        W1 = o; o += (size_t)H * in; b1 = o; o += H; ln1_g = o; o += H; ln1_b = o; o += H;
-        W2 = o; o += (size_t)H * H; b2 = o; o += H; ln2_g = o; o += H; ln2_b = o; o += H;
+        for (int k = 0; k < nblk; ++k) {
+            W[k] = o; o += (size_t)H * (k == 0 ? in : H);
+            b[k] = o; o += H; lg[k] = o; o += H; lb[k] = o; o += H;
+        }
         Wh = o; o += (size_t)out * H; bh = o; o += out;
         logstd = o; if (has_logstd) o += out;
         total = o;
@@ -47,11 +52,12 @@ struct MappoHandle {
     int chunk_rows;  // env-step rows per chunk
     // scratch
     float *x0;       // [chunk*N, D] == [chunk, N*D]: xhat = input LayerNorm without affine
-    float *a1, *h1, *a2, *h2, *dA, *dB;   // [chunk*N, H]
-    float *mean1, *rstd1, *mean2, *rstd2;   // [chunk*N]
+    float *a[MAX_BLOCKS], *hh[MAX_BLOCKS];          // per hidden block: post-activation a_k and h_k = LN(a_k), [chunk*N, H]
+    float *mean[MAX_BLOCKS], *rstd[MAX_BLOCKS];      // per hidden block: LayerNorm row statistics, [chunk*N]
+    float *dA, *dB;                                  // [chunk*N, H] gradient ping-pong
     float *w1g_a, *b1g_a, *w1g_c, *b1g_c;   // fc1 weights with the input LayerNorm affine folded in (per call)
     // tcgen05 backend: hi/lo-split, 128B-swizzled shared-memory images of the weights (per call), [actor, critic]
-    float *img_w1[2], *img_w2[2], *img_w2t[2];
+    float *img_w1[2], *img_w[2][MAX_BLOCKS], *img_wt[2][MAX_BLOCKS];   // blocks >= 1: forward / transposed (dX) images
     float *mu, *logp, *dmu, *vnew, *dv;   // [chunk*N,2], [chunk*N], [chunk*N,2], [chunk], [chunk]
     double *dsums;   // small float64 scratch: [4] actor grad sumsq, [5] critic grad sumsq
     float *vn_gae;   // ValueNorm state snapshot taken at train_begin (3 floats)
@@ -215,15 +221,17 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
-    fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W1, P + L.b1, L.has_ln0 ? P + L.ln0_g : nullptr,
+    fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W[0], P + L.b[0], L.has_ln0 ? P + L.ln0_g : nullptr,
                                                   L.has_ln0 ? P + L.ln0_b : nullptr, w1g, b1g, L.H, L.in);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     if (h->backend == 2) {
         int rc;
         if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s))) return rc;
-        if ((rc = tc_prep_weights(h, P + L.W2, L.H, false, L.H, h->img_w2[net], s))) return rc;
-        if (for_backward && (rc = tc_prep_weights(h, P + L.W2, L.H, true, L.H, h->img_w2t[net], s))) return rc;
+        for (int k = 1; k < L.nblk; ++k) {
+            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s))) return rc;
+            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s))) return rc;
+        }
     }
     return DCC_OK;
 }
@@ -243,27 +251,25 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     h->launches++;
     int rc;
-    if (h->backend == 2) {
-        // tcgen05 GEMM with the block's bias + ReLU + LayerNorm fused into its epilogue (one kernel per MLP block)
-        rc = tc_gemm_fwd(h, rows, L.inp, h->x0, L.inp, h->img_w1[net], save ? h->a1 : nullptr, H, s, b1g, P + L.ln1_g,
-                         P + L.ln1_b, h->h1, save ? h->mean1 : nullptr, save ? h->rstd1 : nullptr);
+    // hidden blocks: block 0 reads xhat (K = padded input width, folded fc1), block k >= 1 reads h_{k-1}
+    for (int k = 0; k < L.nblk; ++k) {
+        const float *in = k == 0 ? h->x0 : h->hh[k - 1];
+        const int K = k == 0 ? L.in : H, ldin = k == 0 ? L.inp : H;
+        const float *Wk = k == 0 ? w1g : P + L.W[k], *bk = k == 0 ? b1g : P + L.b[k];
+        if (h->backend == 2) {
+            // tcgen05 GEMM with the block's bias + activation + LayerNorm fused into its epilogue (one kernel per block)
+            rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
+                             bk, P + L.lg[k], P + L.lb[k], h->hh[k], save ? h->mean[k] : nullptr, save ? h->rstd[k] : nullptr);
+            if (rc) return rc;
+            continue;
+        }
+        rc = launch_gemm(h, false, true, rows, H, K, in, ldin, Wk, K, h->a[k], H, false, s);
         if (rc) return rc;
-        rc = tc_gemm_fwd(h, rows, H, h->h1, H, h->img_w2[net], save ? h->a2 : nullptr, H, s, P + L.b2, P + L.ln2_g,
-                         P + L.ln2_b, h->h2, save ? h->mean2 : nullptr, save ? h->rstd2 : nullptr);
-        return rc;
+        bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a[k], bk, P + L.lg[k], P + L.lb[k],
+                                                                                save ? h->a[k] : nullptr, h->hh[k], h->mean[k],
+                                                                                h->rstd[k], rows, H, act_of(h));
+        h->launches++;
     }
-    rc = launch_gemm(h, false, true, rows, H, L.in, h->x0, L.inp, w1g, L.in, h->a1, H, false, s);
-    if (rc) return rc;
-    bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a1, b1g, P + L.ln1_g, P + L.ln1_b,
-                                                                            save ? h->a1 : nullptr, h->h1, h->mean1,
-                                                                            h->rstd1, rows, H, act_of(h));
-    h->launches++;
-    rc = launch_gemm(h, false, true, rows, H, H, h->h1, H, P + L.W2, H, h->a2, H, false, s);
-    if (rc) return rc;
-    bias_relu_ln_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(h->a2, P + L.b2, P + L.ln2_g, P + L.ln2_b,
-                                                                            save ? h->a2 : nullptr, h->h2, h->mean2,
-                                                                            h->rstd2, rows, H, act_of(h));
-    h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
 }
@@ -277,25 +283,31 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     const int H = L.H;
     const int wpb = 8;
     const int gr = grid_for_reduce(h, rows, wpb);
-    // head backward + ReLU/LayerNorm backward of block 2 in one pass: dA := dz2
+    const int last = L.nblk - 1;
+    // head backward + activation/LayerNorm backward of the last block in one pass: dA := dz_last
     if (L.out == 2)
-        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
-                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H, act_of(h));
+        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
+                                                          h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
     else
-        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a2, h->mean2, h->rstd2, P + L.ln2_g, P + L.ln2_b,
-                                                          h->dA, G + L.ln2_g, G + L.ln2_b, G + L.b2, G + L.Wh, G + L.bh, rows, H, act_of(h));
+        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
+                                                          h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
     h->launches++;
-    int rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, h->dA, H, h->h1, H, G + L.W2, H, s)     // dW2 += dz2^T h1
-                             : launch_gemm(h, true, false, H, H, rows, h->dA, H, h->h1, H, G + L.W2, H, true, s);
-    if (rc) return rc;
-    rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, h->dA, H, h->img_w2t[net], h->dB, H, s)                // dh1 = dz2 W2
-                         : launch_gemm(h, false, false, rows, H, H, h->dA, H, P + L.W2, H, h->dB, H, false, s);
-    if (rc) return rc;
-    relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(h->dB, h->a1, h->mean1, h->rstd1, P + L.ln1_g, h->dB, G + L.ln1_g,
-                                               G + L.ln1_b, G + L.b1, rows, H, act_of(h));   // dB := dz1
-    h->launches++;
-    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, h->dB, H, h->x0, L.inp, G + L.W1, L.in, s)         // G1 += dz1^T xhat
-                         : launch_gemm(h, true, false, H, L.in, rows, h->dB, H, h->x0, L.inp, G + L.W1, L.in, true, s);
+    int rc;
+    float *dz = h->dA, *dx = h->dB;
+    for (int k = last; k >= 1; --k) {
+        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s)     // dW_k += dz_k^T h_{k-1}
+                             : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
+        if (rc) return rc;
+        rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s)                // dh_{k-1} = dz_k W_k
+                             : launch_gemm(h, false, false, rows, H, H, dz, H, P + L.W[k], H, dx, H, false, s);
+        if (rc) return rc;
+        relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx,
+                                                   G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1], rows, H, act_of(h));   // dx := dz_{k-1}
+        h->launches++;
+        float *t = dz; dz = dx; dx = t;
+    }
+    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, dz, H, h->x0, L.inp, G + L.W[0], L.in, s)         // G1 += dz_0^T xhat
+                         : launch_gemm(h, true, false, H, L.in, rows, dz, H, h->x0, L.inp, G + L.W[0], L.in, true, s);
     if (rc) return rc;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -303,7 +315,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
 
 static int ln0_finalize(MappoHandle *h, const NetLayout &L, const float *P, float *G, cudaStream_t s) {
     if (!L.has_ln0) return DCC_OK;   // no feature_norm: the fc1 slot already holds dW1 = dz1^T x
-    ln0_finalize_kernel<<<(L.in + 127) / 128, 128, 0, s>>>(P + L.W1, P + L.ln0_g, P + L.ln0_b, G + L.W1, G + L.b1, G + L.ln0_g,
+    ln0_finalize_kernel<<<(L.in + 127) / 128, 128, 0, s>>>(P + L.W[0], P + L.ln0_g, P + L.ln0_b, G + L.W[0], G + L.b[0], G + L.ln0_g,
                                                           G + L.ln0_b, L.H, L.in);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
@@ -340,7 +352,7 @@ int dcc_mappo_cfg_default(dcc_mappo_cfg *c) {
     c->max_grad_norm = 10.0f; c->gamma = 0.99f; c->gae_lambda = 0.95f; c->opti_eps = 1e-5f; c->vn_beta = 0.99999;
     c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f;
     c->use_huber_loss = 1; c->use_clipped_value_loss = 1; c->use_max_grad_norm = 1; c->use_valuenorm = 1; c->use_gae = 1;
-    c->weight_decay = 0.f; c->use_feature_normalization = 1; c->use_relu = 1;
+    c->weight_decay = 0.f; c->use_feature_normalization = 1; c->use_relu = 1; c->layer_N = 1;
     return DCC_OK;
 }
 
@@ -348,8 +360,9 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     if (!cfg || !handle) return DCC_ERR_INVALID_ARG;
     *handle = nullptr;
     if (cfg->n_agents < 1 || cfg->obs_dim < 1 || cfg->hidden < 1 || cfg->chunk_rows < 0) return DCC_ERR_INVALID_ARG;
-    if (cfg->hidden > 256 || cfg->act_dim != 2 || cfg->gemm_backend < 0 || cfg->gemm_backend > 2)
-        return DCC_ERR_UNSUPPORTED;  // MLP trunk with hidden <= 256 and the Box(2) action space of the env
+    if (cfg->hidden > 256 || cfg->act_dim != 2 || cfg->gemm_backend < 0 || cfg->gemm_backend > 2 || cfg->layer_N < 1 ||
+        cfg->layer_N > MAX_BLOCKS - 1)
+        return DCC_ERR_UNSUPPORTED;  // MLP trunk with hidden <= 256, 1..3 fc2 blocks and the Box(2) action space of the env
     if (cfg->gemm_backend == 2 && !tc_supported(cfg)) return DCC_ERR_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return DCC_ERR_NO_DEVICE;
@@ -364,12 +377,12 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->magic = MAPPO_MAGIC; h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
     h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
-    h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0);
-    h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0);
+    h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
+    h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
     // chunk: bound the scratch to ~1.5 GB unless the caller asks for a size
     long chunk = cfg->chunk_rows;
     if (chunk <= 0) {
-        const double per_row = (double)N * (D + 6.0 * H + 16) * 4.0;
+        const double per_row = (double)N * (D + (2.0 + 2.0 * (1 + cfg->layer_N)) * H + 16) * 4.0;
         chunk = (long)(2.5e9 / per_row);
         if (chunk > 131072) chunk = 131072;
         // whole waves of 128-row tiles on the persistent grid (one CTA per SM).  The critic runs one row per env step,
@@ -393,13 +406,16 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
         for (int n = 0; n < 2; ++n) {
             const size_t kt1 = Ls[n]->inp / tc::TC_BK, kt2 = (H + tc::TC_BK - 1) / tc::TC_BK;
             alloc(&h->img_w1[n], kt1 * 2 * tc::TC_B_TILE_FLOATS);
-            alloc(&h->img_w2[n], kt2 * 2 * tc::TC_B_TILE_FLOATS);
-            alloc(&h->img_w2t[n], kt2 * 2 * tc::TC_B_TILE_FLOATS);
+            for (int k = 1; k < h->la.nblk; ++k) {
+                alloc(&h->img_w[n][k], kt2 * 2 * tc::TC_B_TILE_FLOATS);
+                alloc(&h->img_wt[n][k], kt2 * 2 * tc::TC_B_TILE_FLOATS);
+            }
         }
     }
-    alloc(&h->a1, RA * H); alloc(&h->h1, RA * H); alloc(&h->a2, RA * H); alloc(&h->h2, RA * H);
+    for (int k = 0; k < h->la.nblk; ++k) {
+        alloc(&h->a[k], RA * H); alloc(&h->hh[k], RA * H); alloc(&h->mean[k], RA); alloc(&h->rstd[k], RA);
+    }
     alloc(&h->dA, RA * H); alloc(&h->dB, RA * H);
-    alloc(&h->mean1, RA); alloc(&h->rstd1, RA); alloc(&h->mean2, RA); alloc(&h->rstd2, RA);
     alloc(&h->w1g_a, (size_t)H * D); alloc(&h->b1g_a, H); alloc(&h->w1g_c, (size_t)H * N * D); alloc(&h->b1g_c, H);
     alloc(&h->mu, RA * 2); alloc(&h->logp, RA); alloc(&h->dmu, RA * 2); alloc(&h->vnew, chunk); alloc(&h->dv, chunk);
     alloc(&h->vn_gae, 4);
@@ -417,10 +433,13 @@ int dcc_mappo_destroy(void *handle) {
     MappoHandle *h = as_mappo(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
-    float *bufs[] = {h->x0, h->a1, h->h1, h->a2, h->h2, h->dA, h->dB, h->mean1, h->rstd1, h->mean2, h->rstd2,
-                     h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv, h->vn_gae,
-                     h->img_w1[0], h->img_w1[1], h->img_w2[0], h->img_w2[1], h->img_w2t[0], h->img_w2t[1]};
+    float *bufs[] = {h->x0, h->dA, h->dB, h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv,
+                     h->vn_gae, h->img_w1[0], h->img_w1[1]};
     for (float *b : bufs) cudaFree(b);
+    for (int k = 0; k < MAX_BLOCKS; ++k) {
+        float *blk[] = {h->a[k], h->hh[k], h->mean[k], h->rstd[k], h->img_w[0][k], h->img_w[1][k], h->img_wt[0][k], h->img_wt[1][k]};
+        for (float *b : blk) cudaFree(b);
+    }
     cudaFree(h->dsums);
     h->magic = 0;
     delete h;
@@ -465,14 +484,14 @@ static int policy_forward(MappoHandle *h, const float *actor, const float *criti
             const int rows = ne * N;
             if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s))) return rc;
             actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
-                h->h2, actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
+                h->hh[h->la.nblk - 1], actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
                 d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
                 deterministic, seed, offset, (uint64_t)e0 * N);
             h->launches++;
         }
         if (do_critic) {
             if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s))) return rc;
-            critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->h2, critic + h->lc.Wh, critic + h->lc.bh,
+            critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + h->lc.Wh, critic + h->lc.bh,
                                                                       d_values + e0, ne, H);
             h->launches++;
         }
@@ -597,7 +616,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
         if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s))) return rc;
         actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
-            h->h2, actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+            h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
             h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
         h->launches++;
         ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
@@ -607,7 +626,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s))) return rc;
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
         if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s))) return rc;
-        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
+        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
         h->launches++;
         ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
                                                               d_epoch_stats, nr, P);
@@ -661,7 +680,7 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
         const int nk = (int)std::min<long>(RA, n_index - k0);
         // actor on the minibatch's agent rows, observation rows gathered through the permutation
         if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, idx + k0, 1))) return rc;
-        actor_head_kernel<<<grid_for_rows(h, nk, 8), 256, 0, s>>>(h->h2, actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
+        actor_head_kernel<<<grid_for_rows(h, nk, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
                                                                  const_cast<float *>(d_actions), h->mu, h->logp, nk, H, 1, 0,
                                                                  0, 0, 0, idx + k0);
         h->launches++;
@@ -676,7 +695,7 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
             const int nc = (int)std::min<long>(h->chunk_rows, nk - c0);
             const long long *ci = idx + k0 + c0;
             if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, ci, N))) return rc;
-            critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->h2, critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
+            critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
             h->launches++;
             ppo_value_loss_kernel<<<(nc + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats,
                                                                   nc, P, ci);

@@ -74,9 +74,9 @@ def check_supported(cfg):
     update-path switches (use_huber_loss, use_clipped_value_loss, use_max_grad_norm, use_valuenorm, use_gae,
     use_proper_time_limits, weight_decay, num_mini_batch, use_linear_lr_decay, the *_active_masks flags — no-ops
     in the reference, whose active masks are all ones) and the network switches use_ReLU (tanh trunk),
-    use_feature_normalization, use_orthogonal (xavier init), use_centralized_V (per-agent critic).
-    Refused loudly instead of silently computing something else: recurrent policies and layer_N != 1 (other kernel
-    shapes) and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
+    use_feature_normalization, use_orthogonal (xavier init), use_centralized_V (per-agent critic), layer_N 1..3.
+    Refused loudly instead of silently computing something else: recurrent policies (other kernel shapes; SURVEY §8
+    f-4), stacked frames and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
     tensor to an nn.Parameter attribute and raises TypeError on the first update, popart.py:61)."""
     bad = []
     if getattr(cfg, "use_recurrent_policy", False) or getattr(cfg, "use_naive_recurrent_policy", False):
@@ -87,7 +87,7 @@ def check_supported(cfg):
         bad.append("stacked frames")
     if int(getattr(cfg, "num_mini_batch", 1)) < 1:
         bad.append("num_mini_batch < 1")
-    if int(getattr(cfg, "layer_N", 1)) != 1:
-        bad.append("layer_N != 1")
+    if not 1 <= int(getattr(cfg, "layer_N", 1)) <= 3:
+        bad.append("layer_N outside 1..3")
     if bad:
         raise NotImplementedError("not supported by the B200 hot path: " + ", ".join(bad))

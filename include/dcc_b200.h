@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 3
+#define DCC_ABI_VERSION 4
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -209,6 +209,9 @@ typedef struct dcc_mappo_cfg {
                                           feature_norm.weight / .bias entries and fc1 sees the raw observation */
     float weight_decay;              /* 0: torch.optim.Adam L2 term, grad += weight_decay * param (after the clip) mappo.py:30-37 */
     int32_t use_relu;                /* 1: ReLU trunk; 0: tanh (mlp.py:13 `[nn.Tanh(), nn.ReLU()][use_ReLU]`) */
+    int32_t layer_N;                 /* 1..3: number of fc2 blocks after fc1 (mlp.py:23,27-28); the flat buffers then hold
+                                        base.mlp.fc2.{i}.0.weight/.bias, .2.weight/.bias for i < layer_N, in order */
+    int32_t reserved1;
 } dcc_mappo_cfg;
 
 int dcc_mappo_cfg_default(dcc_mappo_cfg *cfg);

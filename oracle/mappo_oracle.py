@@ -44,7 +44,7 @@ def ln_bwd(dy, cache, g):
 
 
 class MLPNet:
-    """feature_norm -> [Linear, act, LayerNorm] x 2 -> head   (mlp.py:13-29,44-58; fc_h is never used).
+    """feature_norm -> [Linear, act, LayerNorm] x (1 + layer_N) -> head   (mlp.py:13-29,44-58; fc_h is never used).
     act = "relu" | "tanh" (use_ReLU); the input LayerNorm is skipped when the parameters carry no
     base.feature_norm.* entries (use_feature_normalization: false)."""
     TRUNK = ("base.feature_norm.weight", "base.feature_norm.bias", "base.mlp.fc1.0.weight", "base.mlp.fc1.0.bias",
@@ -66,42 +66,46 @@ class MLPNet:
     def names(self):
         return [k for k in self.p]
 
+    def _blocks(self):
+        """(Linear weight, bias, LayerNorm gain, bias) key stems of the hidden blocks: fc1, fc2.0, fc2.1, ... (layer_N)."""
+        stems = ["base.mlp.fc1"]
+        i = 0
+        while "base.mlp.fc2.%d.0.weight" % i in self.p:
+            stems.append("base.mlp.fc2.%d" % i)
+            i += 1
+        return stems
+
     def forward(self, x):
         p = self.p
         x = np.asarray(x, dtype=np.float64)
         if self.fnorm:
-            h0, c0 = ln_fwd(x, p["base.feature_norm.weight"], p["base.feature_norm.bias"])
+            h, c0 = ln_fwd(x, p["base.feature_norm.weight"], p["base.feature_norm.bias"])
         else:
-            h0, c0 = x, None
-        z1 = h0 @ p["base.mlp.fc1.0.weight"].T + p["base.mlp.fc1.0.bias"]
-        a1 = self._act(z1)
-        h1, c1 = ln_fwd(a1, p["base.mlp.fc1.2.weight"], p["base.mlp.fc1.2.bias"])
-        z2 = h1 @ p["base.mlp.fc2.0.0.weight"].T + p["base.mlp.fc2.0.0.bias"]
-        a2 = self._act(z2)
-        h2, c2 = ln_fwd(a2, p["base.mlp.fc2.0.2.weight"], p["base.mlp.fc2.0.2.bias"])
-        out = h2 @ p[self.head_w].T + p[self.head_b]
-        self.cache = (h0, c0, z1, a1, h1, c1, z2, a2, h2, c2)
-        return out
+            h, c0 = x, None
+        self.c0, self.blocks = c0, []
+        for st in self._blocks():
+            z = h @ p[st + ".0.weight"].T + p[st + ".0.bias"]
+            a = self._act(z)
+            hn, c = ln_fwd(a, p[st + ".2.weight"], p[st + ".2.bias"])
+            self.blocks.append((st, h, z, a, c))
+            h = hn
+        self.h_last = h
+        return h @ p[self.head_w].T + p[self.head_b]
 
     def backward(self, dout):
         p = self.p
-        h0, c0, z1, a1, h1, c1, z2, a2, h2, c2 = self.cache
         g = {}
-        g[self.head_w] = dout.T @ h2
+        g[self.head_w] = dout.T @ self.h_last
         g[self.head_b] = dout.sum(0)
-        dh2 = dout @ p[self.head_w]
-        da2, g["base.mlp.fc2.0.2.weight"], g["base.mlp.fc2.0.2.bias"] = ln_bwd(dh2, c2, p["base.mlp.fc2.0.2.weight"])
-        dz2 = self._dact(da2, z2, a2)
-        g["base.mlp.fc2.0.0.weight"] = dz2.T @ h1
-        g["base.mlp.fc2.0.0.bias"] = dz2.sum(0)
-        dh1 = dz2 @ p["base.mlp.fc2.0.0.weight"]
-        da1, g["base.mlp.fc1.2.weight"], g["base.mlp.fc1.2.bias"] = ln_bwd(dh1, c1, p["base.mlp.fc1.2.weight"])
-        dz1 = self._dact(da1, z1, a1)
-        g["base.mlp.fc1.0.weight"] = dz1.T @ h0
-        g["base.mlp.fc1.0.bias"] = dz1.sum(0)
+        dh = dout @ p[self.head_w]
+        for st, h_in, z, a, c in reversed(self.blocks):
+            da, g[st + ".2.weight"], g[st + ".2.bias"] = ln_bwd(dh, c, p[st + ".2.weight"])
+            dz = self._dact(da, z, a)
+            g[st + ".0.weight"] = dz.T @ h_in
+            g[st + ".0.bias"] = dz.sum(0)
+            dh = dz @ p[st + ".0.weight"]
         if self.fnorm:
-            dh0 = dz1 @ p["base.mlp.fc1.0.weight"]
-            _, g["base.feature_norm.weight"], g["base.feature_norm.bias"] = ln_bwd(dh0, c0, p["base.feature_norm.weight"])
+            _, g["base.feature_norm.weight"], g["base.feature_norm.bias"] = ln_bwd(dh, self.c0, p["base.feature_norm.weight"])
         return g
 
 

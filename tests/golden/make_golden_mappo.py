@@ -85,7 +85,8 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
     D = lr.obs_dim_n[0]
     centralized = bool(cfg.use_centralized_V)
     a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden, use_centralized_V=centralized,
-                                         use_feature_normalization=bool(cfg.use_feature_normalization)))
+                                         use_feature_normalization=bool(cfg.use_feature_normalization),
+                                         layer_N=int(cfg.layer_N)))
     set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
     set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
     out = {}
@@ -147,7 +148,7 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
                 use_gae=bool(cfg.use_gae), use_proper_time_limits=bool(cfg.use_proper_time_limits),
                 weight_decay=float(cfg.weight_decay), num_mini_batch=int(cfg.num_mini_batch),
                 use_ReLU=bool(cfg.use_ReLU), use_feature_normalization=bool(cfg.use_feature_normalization),
-                use_centralized_V=centralized)
+                use_centralized_V=centralized, layer_N=int(cfg.layer_N))
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "mappo_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -168,7 +169,7 @@ def run_init_case(name, N, M, hidden, seed, extra=None):
     meta = dict(name=name, n_agents=N, n_pois=M, hidden=hidden, seed=seed, obs_dim=lr.obs_dim_n[0], gain=float(cfg.gain),
                 use_orthogonal=bool(cfg.use_orthogonal), use_ReLU=bool(cfg.use_ReLU),
                 use_feature_normalization=bool(cfg.use_feature_normalization),
-                use_centralized_V=bool(cfg.use_centralized_V))
+                use_centralized_V=bool(cfg.use_centralized_V), layer_N=int(cfg.layer_N))
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "init_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -195,9 +196,13 @@ def main():
     run_case("net_decv_h256", 3, 20, 3, 8, 256, 3, seed=10, extra=dict(use_centralized_V=False))
     run_case("net_decv_nofn_mb2_h32", 4, 20, 2, 8, 32, 2, seed=11,
              extra=dict(use_centralized_V=False, use_feature_normalization=False, num_mini_batch=2))
+    run_case("net_layer2_h256", 4, 20, 3, 8, 256, 3, seed=12, extra=dict(layer_N=2))
+    run_case("net_layer3_tanh_nofn_h32", 3, 20, 3, 8, 32, 2, seed=13,
+             extra=dict(layer_N=3, use_ReLU=False, use_feature_normalization=False))
     run_init_case("ship_4x20", 4, 20, 256, seed=0)
     run_init_case("xavier_tanh_nofn_decv", 3, 20, 64, seed=5,
-                  extra=dict(use_orthogonal=False, use_ReLU=False, use_feature_normalization=False, use_centralized_V=False))
+                  extra=dict(use_orthogonal=False, use_ReLU=False, use_feature_normalization=False, use_centralized_V=False,
+                             layer_N=2))
 
 
 if __name__ == "__main__":

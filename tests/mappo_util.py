@@ -3,11 +3,24 @@ deterministic parameter recipe with the reference's state_dict key names (SURVEY
 import numpy as np
 
 
-def _maybe_drop_feature_norm(shapes, feature_norm):
-    return shapes if feature_norm else {k: v for k, v in shapes.items() if not k.startswith("base.feature_norm")}
+def _maybe_drop_feature_norm(shapes, feature_norm, layer_N=1, hidden=None):
+    """Drops the feature_norm entries (use_feature_normalization: false) and inserts the fc2.{1..layer_N-1} blocks
+    after fc2.0 (layer_N > 1), keeping the reference's state_dict order."""
+    out = {}
+    for k, v in shapes.items():
+        if not feature_norm and k.startswith("base.feature_norm"):
+            continue
+        out[k] = v
+        if k == "base.mlp.fc2.0.2.bias":
+            for i in range(1, layer_N):
+                out["base.mlp.fc2.%d.0.weight" % i] = (hidden, hidden)
+                out["base.mlp.fc2.%d.0.bias" % i] = (hidden,)
+                out["base.mlp.fc2.%d.2.weight" % i] = (hidden,)
+                out["base.mlp.fc2.%d.2.bias" % i] = (hidden,)
+    return out
 
 
-def actor_param_shapes(obs_dim, hidden, act_dim=2, feature_norm=True):
+def actor_param_shapes(obs_dim, hidden, act_dim=2, feature_norm=True, layer_N=1):
     return _maybe_drop_feature_norm({
         "base.feature_norm.weight": (obs_dim,), "base.feature_norm.bias": (obs_dim,),
         "base.mlp.fc1.0.weight": (hidden, obs_dim), "base.mlp.fc1.0.bias": (hidden,),
@@ -16,10 +29,10 @@ def actor_param_shapes(obs_dim, hidden, act_dim=2, feature_norm=True):
         "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
         "act.action_out.fc_mean.weight": (act_dim, hidden), "act.action_out.fc_mean.bias": (act_dim,),
         "act.action_out.logstd._bias": (act_dim, 1),
-    }, feature_norm)
+    }, feature_norm, layer_N, hidden)
 
 
-def critic_param_shapes(share_dim, hidden, feature_norm=True):
+def critic_param_shapes(share_dim, hidden, feature_norm=True, layer_N=1):
     return _maybe_drop_feature_norm({
         "base.feature_norm.weight": (share_dim,), "base.feature_norm.bias": (share_dim,),
         "base.mlp.fc1.0.weight": (hidden, share_dim), "base.mlp.fc1.0.bias": (hidden,),
@@ -27,7 +40,7 @@ def critic_param_shapes(share_dim, hidden, feature_norm=True):
         "base.mlp.fc2.0.0.weight": (hidden, hidden), "base.mlp.fc2.0.0.bias": (hidden,),
         "base.mlp.fc2.0.2.weight": (hidden,), "base.mlp.fc2.0.2.bias": (hidden,),
         "v_out.weight": (1, hidden), "v_out.bias": (1,),
-    }, feature_norm)
+    }, feature_norm, layer_N, hidden)
 
 
 def net_shapes(c):
@@ -35,8 +48,9 @@ def net_shapes(c):
     (a decentralised critic reads one agent's observation, learner.py:43-46)."""
     fn = c.get("use_feature_normalization", True)
     share = c["n_agents"] * c["obs_dim"] if c.get("use_centralized_V", True) else c["obs_dim"]
-    return (actor_param_shapes(c["obs_dim"], c["hidden"], feature_norm=fn),
-            critic_param_shapes(share, c["hidden"], feature_norm=fn))
+    ln = c.get("layer_N", 1)
+    return (actor_param_shapes(c["obs_dim"], c["hidden"], feature_norm=fn, layer_N=ln),
+            critic_param_shapes(share, c["hidden"], feature_norm=fn, layer_N=ln))
 
 
 def make_params(shapes, seed):
@@ -47,7 +61,7 @@ def make_params(shapes, seed):
     for name, shp in shapes.items():
         if name.endswith("logstd._bias"):
             v = rng.normal(0.0, 0.15, shp)
-        elif "feature_norm.weight" in name or name.endswith(".2.weight"):
+        elif "feature_norm.weight" in name or name.endswith(".2.weight"):   # LayerNorm gains (feature_norm, fc1.2, fc2.i.2)
             v = 1.0 + rng.normal(0.0, 0.1, shp)
         elif name.endswith("bias"):
             v = rng.normal(0.0, 0.05, shp)

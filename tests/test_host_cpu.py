@@ -41,7 +41,7 @@ def test_unsupported_branches_fail_loudly():
     from dcc_b200.utils.config import check_supported, load_config
     check_supported(load_config(None))
     for key, val in (("use_recurrent_policy", True), ("use_naive_recurrent_policy", True), ("use_popart", True),
-                     ("num_mini_batch", 0), ("layer_N", 2), ("stacked_frames", 2)):
+                     ("num_mini_batch", 0), ("layer_N", 4), ("layer_N", 0), ("stacked_frames", 2)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         with pytest.raises(NotImplementedError):
@@ -50,7 +50,8 @@ def test_unsupported_branches_fail_loudly():
     for key, val in (("num_mini_batch", 2), ("use_valuenorm", False), ("use_huber_loss", False), ("use_gae", False),
                      ("use_clipped_value_loss", False), ("use_max_grad_norm", False), ("weight_decay", 1e-4),
                      ("use_proper_time_limits", True), ("use_linear_lr_decay", False), ("use_ReLU", False),
-                     ("use_feature_normalization", False), ("use_centralized_V", False), ("use_orthogonal", False)):
+                     ("use_feature_normalization", False), ("use_centralized_V", False), ("use_orthogonal", False),
+                     ("layer_N", 3)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         check_supported(cfg)
@@ -185,7 +186,8 @@ def test_reference_order_initialisation(name):
     c = json.loads(str(z["cfg"]))
     D, Hd, N = c["obs_dim"], c["hidden"], c["n_agents"]
     S = N * D if c["use_centralized_V"] else D
-    kw = dict(use_orthogonal=c["use_orthogonal"], use_relu=c["use_ReLU"], feature_norm=c["use_feature_normalization"])
+    kw = dict(use_orthogonal=c["use_orthogonal"], use_relu=c["use_ReLU"], feature_norm=c["use_feature_normalization"],
+              layer_N=c.get("layer_N", 1))
     torch.manual_seed(c["seed"])
     sd_a, head_a = _reference_init(D, Hd, 2, c["gain"], **kw)
     sd_a["act.action_out.fc_mean.weight"], sd_a["act.action_out.fc_mean.bias"] = head_a.weight.data, head_a.bias.data

@@ -23,7 +23,7 @@ CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN,
 BACKENDS = [1, 0]   # SIMT fp32, auto (tcgen05 3xTF32 where the shape allows)
 FLAG_KEYS = ("use_huber_loss", "use_clipped_value_loss", "use_max_grad_norm", "use_valuenorm", "use_gae",
              "use_proper_time_limits", "weight_decay", "num_mini_batch", "use_ReLU", "use_feature_normalization",
-             "use_centralized_V")
+             "use_centralized_V", "layer_N")
 
 
 def load(name):
