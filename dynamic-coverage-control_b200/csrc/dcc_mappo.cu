@@ -247,6 +247,8 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 24)
         ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
+    else if ((L.in & 1) == 0 && ((uintptr_t)x & 7) == 0 && L.in <= 64 * 6)
+        ln_noaffine_fwd_vec2_kernel<6><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else
         ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     h->launches++;

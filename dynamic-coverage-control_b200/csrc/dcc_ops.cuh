@@ -200,6 +200,49 @@ __global__ void ln_noaffine_fwd_vec_kernel(const float *__restrict__ x, float *_
     }
 }
 
+// Same, for rows that are only 8-byte aligned (F even but not a multiple of 4 — the actor's D = 338): one global read
+// pass with 8-byte loads, NV float2 per lane (F <= 64 * NV); the padded output rows are 16-byte aligned.
+template <int NV>
+__global__ void ln_noaffine_fwd_vec2_kernel(const float *__restrict__ x, float *__restrict__ xhat, int rows, int F, int ldo,
+                                            const long long *__restrict__ ridx, int rdiv, int normalize) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int F2 = F >> 1, L2 = ldo >> 1;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+        const size_t sr = ridx ? (size_t)(ridx[r] / rdiv) : (size_t)r;
+        const float2 *xr = reinterpret_cast<const float2 *>(x + sr * F);
+        float2 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = (c < F2) ? __ldg(xr + c) : make_float2(0.f, 0.f);
+            s += v[i].x + v[i].y;
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (normalize) {
+            mean = warp_sum_f(s) / (float)F;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                if (lane + 32 * i < F2) {
+                    const float a = v[i].x - mean, b = v[i].y - mean;
+                    q = fmaf(a, a, q); q = fmaf(b, b, q);
+                }
+            }
+            rstd = rsqrtf(warp_sum_f(q) / (float)F + LN_EPS);
+        }
+        float2 *yr = reinterpret_cast<float2 *>(xhat + (size_t)r * ldo);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < F2) yr[c] = make_float2((v[i].x - mean) * rstd, (v[i].y - mean) * rstd);
+            else if (c < L2) yr[c] = make_float2(0.f, 0.f);
+        }
+        for (int c = lane + 32 * NV; c < L2; c += 32) yr[c] = make_float2(0.f, 0.f);
+    }
+}
+
 // W1g[h,c] = W1[h,c] * gamma0[c];  b1g[h] = b1[h] + sum_c W1[h,c] * beta0[c].  One warp per output unit h.
 __global__ void fold_ln0_kernel(const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ g0,
                                 const float *__restrict__ be0, float *__restrict__ W1g, float *__restrict__ b1g, int H,
@@ -306,7 +349,7 @@ __device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float 
 // Backward of h = LN(a)*gamma+beta, a = relu(z+bias):  given dh, a, mean, rstd -> dz (in place over dh allowed),
 // and accumulates dgamma, dbeta, dbias (one set of float atomics per block).  H <= 256, blockDim = 256,
 // dynamic shared memory = 8 * 3 * 256 floats.
-__global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
+__global__ void __launch_bounds__(256, 3) relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
                                    const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
                                    float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
                                    int H, int act) {
@@ -360,7 +403,7 @@ __global__ void relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__
 // dgamma, dbeta, dbias (of the Linear) and dWh, dbh with one set of float atomics per block.  H <= 256, blockDim = 256,
 // dynamic shared memory = 8 * (3 + OUT) * 256 floats.
 template <int OUT>
-__global__ void head_relu_ln_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
+__global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
@@ -460,16 +503,25 @@ __global__ void actor_head_kernel(const float *__restrict__ h, const float *__re
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const float ls0 = logstd[0], ls1 = logstd[1];
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        float s0 = 0.f, s1 = 0.f;
+    // two rows per warp iteration: twice the loads in flight per warp (the kernel is latency-, not bandwidth-bound)
+    for (int r0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 2; r0 < rows; r0 += gridDim.x * wpb * 2) {
+        const bool two = r0 + 1 < rows;
+        float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         for (int c = lane; c < H; c += 32) {
-            const float v = h[(size_t)r * H + c];
-            s0 = fmaf(v, Wm[c], s0);
-            s1 = fmaf(v, Wm[H + c], s1);
+            const float w0 = Wm[c], w1 = Wm[H + c];
+            const float v0 = h[(size_t)r0 * H + c];
+            const float v1 = two ? h[(size_t)(r0 + 1) * H + c] : 0.f;
+            s[0][0] = fmaf(v0, w0, s[0][0]); s[0][1] = fmaf(v0, w1, s[0][1]);
+            s[1][0] = fmaf(v1, w0, s[1][0]); s[1][1] = fmaf(v1, w1, s[1][1]);
         }
-        s0 = warp_sum_f(s0) + bm[0];
-        s1 = warp_sum_f(s1) + bm[1];
-        if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            s[k][0] = warp_sum_f(s[k][0]) + bm[0];
+            s[k][1] = warp_sum_f(s[k][1]) + bm[1];
+        }
+        if (lane < 2 && (lane == 0 || two)) {      // lane k finishes row r0 + k
+            const int r = r0 + lane;
+            const float s0 = lane ? s[1][0] : s[0][0], s1 = lane ? s[1][1] : s[0][1];
             const float sd0 = expf(ls0), sd1 = expf(ls1);
             float a0, a1;
             if (mode == 0) {
