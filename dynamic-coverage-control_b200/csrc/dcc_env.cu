@@ -415,7 +415,9 @@ struct EnvSpec {
     static constexpr int STAGE_FLOATS = R * D;
     static constexpr int STAGE_STRIDE = (int)((((size_t)STAGE_FLOATS * 4 + 127) / 128 * 128) / 4);
     static constexpr int PW_BYTES = (int)(((size_t)N * 32 + (size_t)STAGE_STRIDE * 4 * NBUF + 127) / 128 * 128);
-    static constexpr int WPC = 4;
+    // warps per CTA: 4, or 2 when a warp's stage is so large (16/256: 21.6 KB) that 4-warp CTAs would leave shared memory
+    // unused (2 x 86 KB of 227 KB = 8 warps per SM; 5 x 43 KB = 10 warps) — the kernel is latency-bound at that occupancy
+    static constexpr int WPC = (PW_BYTES * 4 > 64 * 1024) ? 2 : 4;
     static constexpr int SMEM = PW_BYTES * WPC;
     static constexpr int FIT = (int)(233472 / (SMEM + 1024));
     static constexpr int MIN_BLOCKS = FIT < 1 ? 1 : (FIT > 6 ? 6 : FIT);
