@@ -8,7 +8,9 @@ Same constructor and method names (`insert`, `compute_returns`, `after_update`) 
   * quantities that are identical for the N agents of an env (reward, mask, value prediction, return — shared reward
     environment.py:106-108, identical critic input) are stored once per env: (T(+1), E).  The reference-shaped
     (T(+1), E, N, 1) arrays are exposed as expanded views (`rewards`, `masks`, `value_preds`, `returns`);
-  * the unused rnn_states arrays, bad_masks, active_masks (all ones) and available_actions are not stored.
+  * the rnn_states arrays (never written with MLP policies), bad_masks and active_masks (all ones) are not stored:
+    `rnn_states`, `rnn_states_critic`, `bad_masks`, `active_masks` are zero-cost expanded views with the reference's
+    shapes; `available_actions` is None as in the reference (Box action space).
 GAE (`compute_returns`, shared_buffer.py:199-208) is one kernel, `dcc_mappo_gae`.
 Memory at 8 UAV / 64 PoI / 65 536 envs / T = 150: obs 107 GB float32 of the 180 GB HBM3e; everything else < 1 GB.
 """
@@ -48,8 +50,33 @@ class SharedReplayBuffer(object):
         self.rewards_te = torch.zeros((T, V), **kw)
         self.masks_te = torch.ones((T + 1, V), **kw)
         self.step = 0
+        self.recurrent_N = int(getattr(cfg, "recurrent_N", 1))
+        self.hidden_size = int(getattr(cfg, "algo_hidden_size", 256))
+        self.available_actions = None
+        self._zero = torch.zeros(1, **kw)
+        self._one = torch.ones(1, **kw)
 
     # ---- reference-shaped views (no copies) ---------------------------------------------------------------
+    @property
+    def rnn_states(self):
+        """(T+1, E, N, recurrent_N, hidden) zeros (shared_buffer.py:44-48): MLP policies never write them."""
+        T1, E, N, _ = self.obs.shape
+        return self._zero.view(1, 1, 1, 1, 1).expand(T1, E, N, self.recurrent_N, self.hidden_size)
+
+    @property
+    def rnn_states_critic(self):
+        return self.rnn_states
+
+    @property
+    def bad_masks(self):
+        """(T+1, E, N, 1) ones: the reference never stores bad masks (learner.py:272-276)."""
+        T1, E, N, _ = self.obs.shape
+        return self._one.view(1, 1, 1, 1).expand(T1, E, N, 1)
+
+    @property
+    def active_masks(self):
+        return self.bad_masks
+
     @property
     def share_obs(self):
         T1, E, N, D = self.obs.shape

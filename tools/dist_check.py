@@ -34,9 +34,39 @@ def main():
     comm = init_from_env()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    ok = True
+    for nmb in (1, 2):      # whole-rollout minibatch, and num_mini_batch = 2 (per-rank permutations, shared_buffer.py:219-279)
+        ok = run(comm, local, nmb) and ok
+    if comm.rank == 0 and not ok:
+        sys.exit(1)
+
+
+def run(comm, local, nmb):
     N, M, Hd, E, T, EPOCHS = 8, 64, 256, 256, 12, 3
     D = 4 + 2 * (N - 1) + 5 * M
-    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=EPOCHS, seed=5, n_iters=10, actor_seed=11, critic_seed=12)
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=EPOCHS, seed=5, n_iters=10, actor_seed=11, critic_seed=12,
+             num_mini_batch=nmb)
+    # every rank's local permutations (all ranks can compute all of them) and the equivalent global permutation: global
+    # minibatch i = union over ranks of that rank's minibatch i, local agent row (t, e, n) -> global ((t*E + lo + e)*N + n)
+    W = comm.world
+    shards = [shard_envs(E, W, r) for r in range(W)]
+    perms_local = [[np.random.default_rng(1000 * r + ep).permutation(T * (hi_ - lo_) * N) for ep in range(EPOCHS)]
+                   for r, (lo_, hi_) in enumerate(shards)]
+
+    def to_global(r, idx):
+        lo_, hi_ = shards[r]
+        El = hi_ - lo_
+        t, rem = np.divmod(idx, El * N)
+        e, n = np.divmod(rem, N)
+        return (t * E + lo_ + e) * N + n
+    perms_global = []
+    for ep in range(EPOCHS):
+        parts = []
+        for i in range(nmb):
+            for r, (lo_, hi_) in enumerate(shards):
+                mbs = T * (hi_ - lo_) * N // nmb
+                parts.append(to_global(r, perms_local[r][ep][i * mbs:(i + 1) * mbs]))
+        perms_global.append(np.concatenate(parts))
     rng = np.random.default_rng(3)
     obs = rng.normal(0, 1.2, (T + 1, E, N, D)).astype(np.float32)
     act = rng.normal(0, 1.0, (T, E, N, 2)).astype(np.float32)
@@ -49,6 +79,7 @@ def main():
         cfg, pol, tr, buf = build(c, e_hi - e_lo, T, device=local)
         tr.comm = cm
         buf.n_envs_global = E
+        tr.permutation_fn = (lambda ep, n: perms_local[comm.rank][ep]) if tag == "sharded" else (lambda ep, n: perms_global[ep])
         tr.value_normalizer.state[:3] = torch.tensor([0.3, 4.0, 0.02], device=buf.device)
         fill(buf, obs, act, np.zeros((T, E, N), np.float32), vals, rew, masks, e_lo, e_hi)
         _, logp, _ = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
@@ -63,7 +94,7 @@ def main():
     comm.barrier()
     if comm.rank == 0:
         a, b = out["sharded"], out["solo"]
-        res = {"world": comm.world, "epochs": EPOCHS, "allreduce_calls": a[4], "backend": pol.gemm_backend()}
+        res = {"world": comm.world, "epochs": EPOCHS, "num_mini_batch": nmb, "allreduce_calls": a[4], "backend": pol.gemm_backend()}
         for k in a[0]:
             res["info_" + k] = [a[0][k], b[0][k]]
         lr = pol.lr_actor_now
@@ -77,8 +108,8 @@ def main():
         ok = ok and res["actor_max_abs_diff"] <= 6 * lr and res["critic_max_abs_diff"] <= 6 * lr
         res["ok"] = bool(ok)
         print(json.dumps(res), flush=True)
-        if not ok:
-            sys.exit(1)
+        return bool(ok)
+    return True
 
 
 if __name__ == "__main__":
