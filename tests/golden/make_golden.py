@@ -75,10 +75,10 @@ def policy_runaway(rng):
 
 
 def run_traj(name, N, M, T, policy, seed, comm_r_scale=0.95, comm_force_scale=0.0, compat=False,
-             obs_every=1, poi=None):
+             obs_every=1, poi=None, r_cover=0.2, r_comm=0.4):
     rng = np.random.RandomState(seed)
-    env = RefEnv(N, M, comm_r_scale=comm_r_scale, comm_force_scale=comm_force_scale, reference_compat=compat,
-                 pos_pois=poi)
+    env = RefEnv(N, M, r_cover=r_cover, r_comm=r_comm, comm_r_scale=comm_r_scale, comm_force_scale=comm_force_scale,
+                 reference_compat=compat, pos_pois=poi)
     pol = {"random": policy_random, "seek": policy_seek, "runaway": policy_runaway}[policy](rng)
     obs0 = env.reset()
     D = obs0.shape[1]
@@ -100,7 +100,7 @@ def run_traj(name, N, M, T, policy, seed, comm_r_scale=0.95, comm_force_scale=0.
             obs_steps.append(t); obs.append(r["obs"].astype(np.float32))
     world = env.world
     cfg = dict(name=name, kind="traj", n_agents=N, n_pois=M, T=T, policy=policy, seed=seed, obs_dim=D,
-               r_cover=0.2, r_comm=0.4,
+               r_cover=r_cover, r_comm=r_comm,
                comm_r_scale=float(world.comm_r_scale), contact_force=float(world.contact_force),
                reference_compat=bool(compat))
     out = {k: np.array(v) for k, v in rec.items()}
@@ -114,10 +114,12 @@ def run_traj(name, N, M, T, policy, seed, comm_r_scale=0.95, comm_force_scale=0.
         out["coverage_rate"].max(), os.path.getsize(path) / 1024))
 
 
-def run_unit(name, N, M, K, seed, comm_r_scale=0.95, comm_force_scale=0.0, compat=False, spread=1.0):
+def run_unit(name, N, M, K, seed, comm_r_scale=0.95, comm_force_scale=0.0, compat=False, spread=1.0, r_cover=0.2,
+             r_comm=0.4):
     """K independent one-step transitions from injected random states."""
     rng = np.random.RandomState(seed)
-    env = RefEnv(N, M, comm_r_scale=comm_r_scale, comm_force_scale=comm_force_scale, reference_compat=compat)
+    env = RefEnv(N, M, r_cover=r_cover, r_comm=r_comm, comm_r_scale=comm_r_scale, comm_force_scale=comm_force_scale,
+                 reference_compat=compat)
     env.reset()
     keys = ("actions", "pos_vel_in", "energy_in", "pos_vel", "pos_vel_pre", "energy", "energy_pre", "reward", "done",
             "coverage_rate", "connect", "connect_", "adj", "adj_", "obs")
@@ -157,7 +159,7 @@ def run_unit(name, N, M, K, seed, comm_r_scale=0.95, comm_force_scale=0.0, compa
         rec["obs"].append(r["obs"].astype(np.float32))
     world = env.world
     D = rec["obs"][0].shape[1]
-    cfg = dict(name=name, kind="unit", n_agents=N, n_pois=M, K=K, seed=seed, obs_dim=D, r_cover=0.2, r_comm=0.4,
+    cfg = dict(name=name, kind="unit", n_agents=N, n_pois=M, K=K, seed=seed, obs_dim=D, r_cover=r_cover, r_comm=r_comm,
                comm_r_scale=float(world.comm_r_scale), contact_force=float(world.contact_force),
                reference_compat=bool(compat))
     out = {k: np.array(v) for k, v in rec.items()}
@@ -189,6 +191,10 @@ def main():
     run_traj("gen_32x33_force", 32, 33, 30, "random", 12, comm_force_scale=1.0, obs_every=10)
     run_traj("gen_1x7", 1, 7, 60, "seek", 13)
     run_unit("gen_5x37_force_unit", 5, 37, 60, 14, comm_force_scale=0.5, comm_r_scale=0.8)
+    # non-default cover / comm radii (dcc.yaml r_cover, r_comm)
+    run_traj("gen_6x41_radii_force", 6, 41, 80, "random", 15, comm_r_scale=0.8, comm_force_scale=1.0, obs_every=4,
+             r_cover=0.31, r_comm=0.27)
+    run_unit("gen_7x23_radii_unit", 7, 23, 64, 16, comm_r_scale=0.6, comm_force_scale=0.3, r_cover=0.12, r_comm=0.55)
 
 
 if __name__ == "__main__":

@@ -296,3 +296,37 @@ def test_render_snapshot_and_connectivity_outputs():
     frames = env.render("rgb_array", max_envs=3, size=128)
     assert len(frames) == 3 and frames[2][0].shape == (128, 128, 3) and (frames[0][0] != f0[0][0][:128, :128]).any()
     env.close()
+
+
+def test_cuda_random_shapes_and_parameters_vs_oracle():
+    """Seeded sweep over shapes the fixed list above does not hit (N up to 32, M up to 300, prime / ragged sizes) AND over
+    the env parameters (cover / comm radii, comm_r_scale, pull force), several steps each from a spread-out state: the
+    runtime-shape kernel against the CPU oracle, everything bit-exact."""
+    from dcc_b200.envs import CudaVecEnv
+    from oracle.env_oracle import OracleEnv
+    master = np.random.RandomState(2024)
+    for case in range(14):
+        N = int(master.choice([1, 2, 3, 5, 6, 7, 9, 11, 13, 17, 24, 31, 32]))
+        M = int(master.choice([1, 2, 4, 17, 31, 33, 50, 97, 128, 199, 300]))
+        E = int(master.choice([1, 2, 31, 33, 100, 257]))
+        r_cover, r_comm = float(master.uniform(0.05, 0.5)), float(master.uniform(0.1, 0.8))
+        crs, force = float(master.uniform(0.5, 1.0)), float(master.choice([0.0, 0.3, 1.0, 2.5]))
+        rng = np.random.RandomState(1000 + case)
+        poi = rng.uniform(-1, 1, (M, 2))
+        env = CudaVecEnv(E, N, M, r_cover=r_cover, r_comm=r_comm, comm_r_scale=crs, comm_force_scale=force,
+                         reference_compat=False, pos_pois=poi, want_connectivity=True)
+        orc = OracleEnv(E, N, M, poi, r_cover=r_cover, r_comm=r_comm, comm_r_scale=crs, contact_force=100.0 * force, n_threads=4)
+        pv = np.zeros((E, N, 4)); pv[..., :2] = rng.uniform(-1.4, 1.4, (E, N, 2)) * rng.uniform(0.05, 1, (E, 1, 1))
+        pv[..., 2:] = rng.uniform(-0.4, 0.4, (E, N, 2))
+        en = rng.randint(0, 7, (E, M)).astype(np.uint8)
+        env.reset(); env.set_state(pv, en); orc.set_state(pv, en)
+        tag = "case %d N=%d M=%d E=%d rc=%.3f rm=%.3f crs=%.3f f=%.1f" % (case, N, M, E, r_cover, r_comm, crs, force)
+        for t in range(6):
+            a = (rng.standard_normal((E, N, 2)) * (0.5 + t % 3)).astype(np.float32)
+            r = _result(env, *env.step(torch.from_numpy(a).cuda()))
+            o = orc.step(a)
+            for key in ("done", "connect", "connect_", "adj", "adj_", "energy", "pos_vel", "obs"):
+                assert np.array_equal(r[key], o[key]), "%s t=%d %s mismatch" % (tag, t, key)
+            ref = o["reward"].astype(np.float32)
+            assert np.all(np.abs(r["reward"] - ref) <= REW_RTOL * np.maximum(1.0, np.abs(ref))), "%s t=%d reward" % (tag, t)
+        env.close()
