@@ -175,6 +175,8 @@ def run_cuda(args):
     E, N, M = ENVS_PER_GPU, N_AGENTS, N_POIS
     D = obs_dim(N, M)
     env = CudaVecEnv(E, N, M, reference_compat=True, device=local_rank)  # shipped semantics, synthetic PoI layout
+    if args.per_env_layouts:
+        env.set_poi_layouts(np.random.default_rng(rank).uniform(-1.0, 1.0, (E, M, 2)))
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     acts = [torch.randn((E, N, 2), generator=gen, device=dev, dtype=torch.float32) for _ in range(8)]
@@ -234,7 +236,7 @@ def run_cuda(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        b_alg = alg_bytes_per_agent_step(N, M)
+        b_alg = alg_bytes_per_agent_step(N, M) + (16.0 * M / N if args.per_env_layouts else 0.0)
         launch_s = ms * 1e-3 / args.steps
         achieved = E * N * b_alg / launch_s / 1e9
         traffic = None
@@ -263,7 +265,8 @@ def run_cuda(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "env-step-only (BASELINE configs[1]): 8 UAV / 64 PoI, 65536 envs per GPU, N(0,1) float32 "
                                    "actions, auto-reset on, shipped semantics (reference_compat)",
-                       "n_agents": N, "n_pois": M, "envs_per_gpu": E, "obs_dim": D, "poi_layout": "uniform(-1,1), seed 0",
+                       "n_agents": N, "n_pois": M, "envs_per_gpu": E, "obs_dim": D, "poi_layout": ("per-env uniform(-1,1) (dcc_env_set_poi_layouts)" if args.per_env_layouts
+                                      else "uniform(-1,1), seed 0"),
                        "l2": "no flush needed: %.0f MB written per step > 126 MB L2" % (E * N * D * 4 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_agent_step": b_alg,
@@ -476,6 +479,9 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (mappo workload; default 65536)")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-env-layouts", action="store_true",
+                    help="env workload stress variant (SURVEY.md §8d): every env instance has its own uniform(-1,1) PoI layout "
+                         "(+16 M / N bytes read per agent-step)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 150 if args.workload == "env" else 2

@@ -47,6 +47,7 @@ SIGNATURES = {
     "dcc_env_obs_dim": (C.c_int, [C.c_int32, C.c_int32]),
     "dcc_env_create": (C.c_int, [C.POINTER(EnvCfg), _VP, C.c_int, C.POINTER(_VP)]),
     "dcc_env_destroy": (C.c_int, [_VP]),
+    "dcc_env_set_poi_layouts": (C.c_int, [_VP, _VP, _VP]),
     "dcc_env_reset": (C.c_int, [_VP, _VP, _VP]),
     "dcc_env_step": (C.c_int, [_VP] * 10),
     "dcc_env_step_host": (C.c_int, [_VP] * 7),

@@ -40,6 +40,7 @@ struct EnvKParams {
     double lim_force, dist_max, margin, contact_force;
     double rew_cover, rew_done, rew_out;
     const double *poi;
+    const double *poi_env;   // per-env PoI layouts [E, M, 2] (dcc_env_set_poi_layouts), or nullptr: every env uses `poi`
     double *pos_vel;
     uint8_t *energy;
     const float *actions;
@@ -122,6 +123,8 @@ __global__ void __launch_bounds__(512) dcc_env_kernel(const EnvKParams p) {
     int bufsel = 0;
 
     for (int e = blockIdx.x * wpc + warp; e < p.E; e += gridDim.x * wpc) {
+        // PoI table of this env: the shared one (in shared memory) or its own layout (global, L1/L2-cached)
+        const double *poi_e = p.poi_env ? p.poi_env + (size_t)e * 2 * M : s_poi;
         double px = 0.0, py = 0.0, vx = 0.0, vy = 0.0;
         if (STEP) {
             // ---- phase 0: load -----------------------------------------------------------------
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(512) dcc_env_kernel(const EnvKParams p) {
                 const bool valid = j < M;
                 bool now_done = false, just = false;
                 if (valid) {
-                    const double qx = s_poi[2 * j], qy = s_poi[2 * j + 1];
+                    const double qx = poi_e[2 * j], qy = poi_e[2 * j + 1];
                     int en = s_en[j];
                     int cnt = 0;
                     double mind2 = INFINITY;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(512) dcc_env_kernel(const EnvKParams p) {
                 for (int s = 0; s < p.slots; ++s) {
                     const int j = lane + 32 * s;
                     if (j < M) {
-                        const double qx = s_poi[2 * j], qy = s_poi[2 * j + 1];
+                        const double qx = poi_e[2 * j], qy = poi_e[2 * j + 1];
                         const int en = s_en[j];
                         const float fe = (float)en;
                         const float fd = (en >= p.e_thr) ? 1.f : 0.f;
@@ -486,6 +489,14 @@ dcc_env_spec_kernel(const EnvKParams p) {
     int bufsel = 0;
 
     for (int e = blockIdx.x * S::WPC + warp; e < p.E; e += gridDim.x * S::WPC) {
+        if (p.poi_env) {   // per-env PoI layout: this env's coordinates replace the shared ones in the registers
+            const double *pe = p.poi_env + (size_t)e * 2 * M;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int j = lane + 32 * s;
+                if ((M % 32 == 0) || (j < M)) { qx[s] = pe[2 * j]; qy[s] = pe[2 * j + 1]; }
+            }
+        }
         double px = 0.0, py = 0.0, vx = 0.0, vy = 0.0;
         int en[SLOTS];
         if (STEP) {
@@ -827,6 +838,7 @@ struct EnvHandle {
     int D;
     double world_comm_r_scale, world_contact_force;
     double *d_poi;
+    double *d_poi_env;   // [E, M, 2] per-env layouts (dcc_env_set_poi_layouts) or nullptr
     double *d_pos_vel;
     uint8_t *d_energy;
     EnvKParams kp;
@@ -996,11 +1008,32 @@ int dcc_env_create(const dcc_env_cfg *cfg, const double *h_poi_xy, int device, v
     return DCC_OK;
 }
 
+int dcc_env_set_poi_layouts(void *handle, const double *h_poi_xy, dcc_stream_t stream) {
+    EnvHandle *h = as_env(handle);
+    if (!h) return DCC_ERR_INVALID_ARG;
+    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    EnvKParams &k = h->kp;
+    if (!h_poi_xy) {                     // back to the shared layout given at creation
+        k.poi_env = nullptr;
+        return DCC_OK;
+    }
+    const size_t bytes = sizeof(double) * 2 * (size_t)k.M * k.E;
+    if (!h->d_poi_env) {
+        cudaError_t ce = cudaMalloc(&h->d_poi_env, bytes);
+        if (ce != cudaSuccess) { set_last_cuda_error(ce, "cudaMalloc(per-env PoI layouts)", __FILE__, __LINE__); return DCC_ERR_ALLOC; }
+    }
+    DCC_CUDA_TRY(cudaMemcpyAsync(h->d_poi_env, h_poi_xy, bytes, cudaMemcpyHostToDevice, s));
+    DCC_CUDA_TRY(cudaStreamSynchronize(s));
+    k.poi_env = h->d_poi_env;
+    return DCC_OK;
+}
+
 int dcc_env_destroy(void *handle) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
-    cudaFree(h->d_poi); cudaFree(h->d_pos_vel); cudaFree(h->d_energy);
+    cudaFree(h->d_poi); cudaFree(h->d_poi_env); cudaFree(h->d_pos_vel); cudaFree(h->d_energy);
     cudaFree(h->hs_actions); cudaFree(h->hs_obs); cudaFree(h->hs_rew); cudaFree(h->hs_cov); cudaFree(h->hs_done);
     h->magic = 0;
     delete h;

@@ -98,6 +98,7 @@ class CudaVecEnv:
                 self.adj = self.adj_s = None
         self._host = None
         self.closed = False
+        self.pos_pois_per_env = None
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _stream(self):
@@ -114,6 +115,19 @@ class CudaVecEnv:
 
     def launch_count(self):
         return int(self.lib.dcc_env_launch_count(self._h))
+
+    def set_poi_layouts(self, pos_pois_per_env):
+        """Per-env PoI layouts: array (E, M, 2), or None to return to the shared layout.  Takes effect from the next
+        reset / step (include/dcc_b200.h: dcc_env_set_poi_layouts)."""
+        if pos_pois_per_env is None:
+            self.pos_pois_per_env = None
+            _lib.check(self.lib.dcc_env_set_poi_layouts(self._h, None, self._stream()), "dcc_env_set_poi_layouts")
+            return
+        pp = np.ascontiguousarray(np.asarray(pos_pois_per_env, dtype=np.float64))
+        if pp.shape != (self.n_envs, self.n_pois, 2):
+            raise ValueError("per-env PoI layouts must have shape %s, got %s" % ((self.n_envs, self.n_pois, 2), pp.shape))
+        self.pos_pois_per_env = pp
+        _lib.check(self.lib.dcc_env_set_poi_layouts(self._h, pp.ctypes.data, self._stream()), "dcc_env_set_poi_layouts")
 
     def use_specialized(self, enable=True):
         """Toggle the compile-time specialised kernel (4/20, 8/64, 16/256).  Returns True if it is in use."""
@@ -206,7 +220,8 @@ class CudaVecEnv:
             else:   # comm graph of the frame from the positions: d < r_a + r_b (CoverageWorld.py:78-80)
                 d = np.sqrt(((pos[:, None] - pos[None]) ** 2).sum(-1)) + np.eye(self.n_agents) * 1e5
                 rows = ((d < 2.0 * self.cfg.r_comm) * (1 << np.arange(self.n_agents))[None]).sum(1).astype(np.uint32)
-            frames.append([rasterize(pos, self.pos_pois, st["energy"][e], rows, self.cfg.r_cover, self.cfg.r_comm,
+            poi = self.pos_pois if self.pos_pois_per_env is None else self.pos_pois_per_env[e]
+            frames.append([rasterize(pos, poi, st["energy"][e], rows, self.cfg.r_cover, self.cfg.r_comm,
                                      self.cfg.m_energy, size=size)])
         return frames
 

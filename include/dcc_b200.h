@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 4
+#define DCC_ABI_VERSION 5
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -92,6 +92,16 @@ int dcc_env_obs_dim(int32_t n_agents, int32_t n_pois);
 int dcc_env_create(const dcc_env_cfg *cfg, const double *h_poi_xy, int device, void **handle);
 
 /* Replaces: ShareVecEnv.close / SubprocVecEnv.close (envs/wrappers.py:56-63,187-197). */
+/*
+ * Per-env PoI layouts ("synthetic PoI layouts", BASELINE north_star; SURVEY.md §8b / §8d stress variant).  The reference
+ * gives every env instance the same table, scenarios/pos_pois.npy[0:M] (scenarios/coverage.py:15-17, with
+ * `np.random.uniform(-1, 1)` per landmark as its commented-out alternative, :71); its SubprocVecEnv workers are
+ * nevertheless independent Scenario objects, so distinct `pos_pois` per env is the natural generalisation.
+ *   h_poi_xy  host, [n_envs, M, 2] float64 (copied; the call synchronises the stream), or NULL to go back to the
+ *             shared layout passed to dcc_env_create.  Takes effect from the next reset / step; the PoI energies are
+ *             not touched (call dcc_env_reset for a fresh episode on the new layouts).
+ */
+int dcc_env_set_poi_layouts(void *handle, const double *h_poi_xy, dcc_stream_t stream);
 int dcc_env_destroy(void *handle);
 
 /*

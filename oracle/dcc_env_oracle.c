@@ -313,17 +313,27 @@ static void step_one(const dcc_oracle_cfg *c, const double *poi, const float *ac
 int dcc_oracle_obs_dim(int n_agents, int n_pois) { return 4 + 2 * (n_agents - 1) + 5 * n_pois; }
 
 /* Scenario.reset_world for E envs + reset observation. */
-int dcc_oracle_reset(const dcc_oracle_cfg *c, int n_envs, const double *poi, double *pos_vel, uint8_t *energy,
-                     float *obs) {
+/* poi_stride: doubles between the PoI tables of consecutive envs — 0 = one table shared by all envs (the reference's
+ * scenarios/pos_pois.npy), 2*M = every env instance has its own `pos_pois` (each SubprocVecEnv worker owns an
+ * independent Scenario object, wrappers.py:141-146; coverage.py:15-17,71). */
+int dcc_oracle_reset_layouts(const dcc_oracle_cfg *c, int n_envs, const double *poi, int poi_stride, double *pos_vel,
+                             uint8_t *energy, float *obs) {
     const int N = c->n_agents, M = c->n_pois;
     const int D = dcc_oracle_obs_dim(N, M);
     if (N < 1 || N > DCC_ORACLE_MAX_AGENTS || M < 1) return -1;
     for (int e = 0; e < n_envs; ++e) {
         memset(pos_vel + (size_t)e * 4 * N, 0, sizeof(double) * 4 * N);
         memset(energy + (size_t)e * M, 0, M);
-        if (obs) write_obs(c, poi, pos_vel + (size_t)e * 4 * N, energy + (size_t)e * M, obs + (size_t)e * N * D);
+        if (obs)
+            write_obs(c, poi + (size_t)e * poi_stride, pos_vel + (size_t)e * 4 * N, energy + (size_t)e * M,
+                      obs + (size_t)e * N * D);
     }
     return 0;
+}
+
+int dcc_oracle_reset(const dcc_oracle_cfg *c, int n_envs, const double *poi, double *pos_vel, uint8_t *energy,
+                     float *obs) {
+    return dcc_oracle_reset_layouts(c, n_envs, poi, 0, pos_vel, energy, obs);
 }
 
 /* E independent envs, one step each.  Arrays are env-major; optional outputs may be NULL.
@@ -335,6 +345,7 @@ typedef struct step_job {
     const dcc_oracle_cfg *c;
     int e0, e1;
     const double *poi;
+    int poi_stride;
     const float *actions;
     double *pos_vel;
     uint8_t *energy;
@@ -353,7 +364,7 @@ static void *step_range(void *arg) {
     const int N = j->c->n_agents, M = j->c->n_pois;
     const int D = 4 + 2 * (N - 1) + 5 * M;
     for (int e = j->e0; e < j->e1; ++e) {
-        step_one(j->c, j->poi, j->actions + (size_t)e * 2 * N, j->pos_vel + (size_t)e * 4 * N,
+        step_one(j->c, j->poi + (size_t)e * j->poi_stride, j->actions + (size_t)e * 2 * N, j->pos_vel + (size_t)e * 4 * N,
                  j->energy + (size_t)e * M, j->obs ? j->obs + (size_t)e * N * D : NULL,
                  j->rew64 ? j->rew64 + e : NULL, j->done ? j->done + e : NULL,
                  j->coverage_rate ? j->coverage_rate + e : NULL, j->connect ? j->connect + e : NULL,
@@ -364,10 +375,10 @@ static void *step_range(void *arg) {
     return NULL;
 }
 
-int dcc_oracle_step(const dcc_oracle_cfg *c, int n_envs, const double *poi, const float *actions, double *pos_vel,
-                    uint8_t *energy, float *obs, double *rew64, uint8_t *done, double *coverage_rate,
-                    uint8_t *connect, uint32_t *adj, uint32_t *adjs, double *pos_vel_pre, uint8_t *energy_pre,
-                    int n_threads) {
+int dcc_oracle_step_layouts(const dcc_oracle_cfg *c, int n_envs, const double *poi, int poi_stride, const float *actions,
+                            double *pos_vel, uint8_t *energy, float *obs, double *rew64, uint8_t *done,
+                            double *coverage_rate, uint8_t *connect, uint32_t *adj, uint32_t *adjs, double *pos_vel_pre,
+                            uint8_t *energy_pre, int n_threads) {
     const int N = c->n_agents, M = c->n_pois;
     if (N < 1 || N > DCC_ORACLE_MAX_AGENTS || M < 1 || n_envs < 0) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -377,7 +388,7 @@ int dcc_oracle_step(const dcc_oracle_cfg *c, int n_envs, const double *poi, cons
     pthread_t tids[256];
     for (int t = 0; t < n_threads; ++t) {
         step_job j = {c, (int)((long long)n_envs * t / n_threads), (int)((long long)n_envs * (t + 1) / n_threads),
-                      poi, actions, pos_vel, energy, obs, rew64, done, coverage_rate, connect, adj, adjs,
+                      poi, poi_stride, actions, pos_vel, energy, obs, rew64, done, coverage_rate, connect, adj, adjs,
                       pos_vel_pre, energy_pre};
         jobs[t] = j;
     }
@@ -386,6 +397,14 @@ int dcc_oracle_step(const dcc_oracle_cfg *c, int n_envs, const double *poi, cons
     step_range(&jobs[0]);
     for (int t = 1; t < n_threads; ++t) pthread_join(tids[t], NULL);
     return 0;
+}
+
+int dcc_oracle_step(const dcc_oracle_cfg *c, int n_envs, const double *poi, const float *actions, double *pos_vel,
+                    uint8_t *energy, float *obs, double *rew64, uint8_t *done, double *coverage_rate,
+                    uint8_t *connect, uint32_t *adj, uint32_t *adjs, double *pos_vel_pre, uint8_t *energy_pre,
+                    int n_threads) {
+    return dcc_oracle_step_layouts(c, n_envs, poi, 0, actions, pos_vel, energy, obs, rew64, done, coverage_rate, connect,
+                                   adj, adjs, pos_vel_pre, energy_pre, n_threads);
 }
 
 int dcc_oracle_max_threads(void) {

@@ -43,6 +43,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.dcc_oracle_step.restype = C.c_int
         _lib.dcc_oracle_reset.restype = C.c_int
+        _lib.dcc_oracle_step_layouts.restype = C.c_int
+        _lib.dcc_oracle_reset_layouts.restype = C.c_int
         _lib.dcc_oracle_max_threads.restype = C.c_int
     return _lib
 
@@ -66,15 +68,19 @@ class OracleEnv:
         self.E, self.N, self.M = n_envs, n_agents, n_pois
         self.D = 4 + 2 * (n_agents - 1) + 5 * n_pois
         self.cfg = make_cfg(n_agents, n_pois, r_cover, r_comm, comm_r_scale, contact_force)
-        self.poi = np.ascontiguousarray(poi_xy, dtype=np.float64).reshape(n_pois, 2)
+        poi_xy = np.ascontiguousarray(poi_xy, dtype=np.float64)
+        # (M, 2): one table for all envs (the reference's pos_pois.npy); (E, M, 2): every env has its own layout
+        self.per_env = poi_xy.ndim == 3
+        self.poi = poi_xy.reshape((n_envs, n_pois, 2) if self.per_env else (n_pois, 2))
+        self.poi_stride = 2 * n_pois if self.per_env else 0
         self.pos_vel = np.zeros((n_envs, n_agents, 4), dtype=np.float64)
         self.energy = np.zeros((n_envs, n_pois), dtype=np.uint8)
         self.n_threads = n_threads
 
     def reset(self, want_obs=True):
         obs = np.empty((self.E, self.N, self.D), dtype=np.float32) if want_obs else None
-        rc = lib().dcc_oracle_reset(C.byref(self.cfg), self.E, _p(self.poi, C.c_double), _p(self.pos_vel, C.c_double),
-                                    _p(self.energy, C.c_uint8), _p(obs, C.c_float))
+        rc = lib().dcc_oracle_reset_layouts(C.byref(self.cfg), self.E, _p(self.poi, C.c_double), int(self.poi_stride),
+                                            _p(self.pos_vel, C.c_double), _p(self.energy, C.c_uint8), _p(obs, C.c_float))
         assert rc == 0
         return obs
 
@@ -93,8 +99,9 @@ class OracleEnv:
             adj_=np.empty((E, N), dtype=np.uint32) if want_aux else None,
             pos_vel_pre=np.empty((E, N, 4), dtype=np.float64) if want_aux else None,
             energy_pre=np.empty((E, M), dtype=np.uint8) if want_aux else None)
-        rc = lib().dcc_oracle_step(
-            C.byref(self.cfg), E, _p(self.poi, C.c_double), _p(a, C.c_float), _p(self.pos_vel, C.c_double),
+        rc = lib().dcc_oracle_step_layouts(
+            C.byref(self.cfg), E, _p(self.poi, C.c_double), int(self.poi_stride), _p(a, C.c_float),
+            _p(self.pos_vel, C.c_double),
             _p(self.energy, C.c_uint8), _p(out["obs"], C.c_float), _p(out["reward"], C.c_double),
             _p(out["done"], C.c_uint8), _p(out["coverage_rate"], C.c_double), _p(out["connect_bits"], C.c_uint8),
             _p(out["adj"], C.c_uint32), _p(out["adj_"], C.c_uint32), _p(out["pos_vel_pre"], C.c_double),

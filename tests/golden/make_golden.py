@@ -195,6 +195,14 @@ def main():
     run_traj("gen_6x41_radii_force", 6, 41, 80, "random", 15, comm_r_scale=0.8, comm_force_scale=1.0, obs_every=4,
              r_cover=0.31, r_comm=0.27)
     run_unit("gen_7x23_radii_unit", 7, 23, 64, 16, comm_r_scale=0.6, comm_force_scale=0.3, r_cover=0.12, r_comm=0.55)
+    # synthetic PoI layouts (uniform in [-1,1]^2, the reference's commented alternative, coverage.py:71): one layout per
+    # file; the per-env-layout tests run several of these side by side in ONE vec-env
+    for tag, seed in (("a", 21), ("b", 22), ("c", 23)):
+        run_traj("layout_%s_5x12" % tag, 5, 12, 60, "seek" if tag == "b" else "random", seed, comm_force_scale=1.0,
+                 obs_every=3, poi=np.random.default_rng(seed).uniform(-1, 1, (12, 2)))
+    for tag, seed in (("a", 31), ("b", 32)):
+        run_traj("layout_%s_8x64" % tag, 8, 64, 50, "seek" if tag == "b" else "random", seed, comm_force_scale=1.0,
+                 obs_every=5, poi=np.random.default_rng(seed).uniform(-1, 1, (64, 2)))
 
 
 if __name__ == "__main__":

@@ -330,3 +330,37 @@ def test_cuda_random_shapes_and_parameters_vs_oracle():
             ref = o["reward"].astype(np.float32)
             assert np.all(np.abs(r["reward"] - ref) <= REW_RTOL * np.maximum(1.0, np.abs(ref))), "%s t=%d reward" % (tag, t)
         env.close()
+
+
+@pytest.mark.parametrize("shape,tags,spec", [("5x12", "abc", False), ("8x64", "ab", True), ("8x64", "ab", False)])
+def test_cuda_per_env_poi_layouts_vs_reference_golden(shape, tags, spec):
+    """dcc_env_set_poi_layouts: one vec-env whose instances have DIFFERENT PoI layouts; instance e replays the golden
+    the unmodified reference recorded on layout e (several replicas of each, interleaved), then the env is switched
+    back to the shared layout."""
+    gs = [load_golden("layout_%s_%s" % (t, shape)) for t in tags]
+    c = gs[0]["cfg"]
+    reps = 3
+    E, T = len(gs) * reps, min(g["cfg"]["T"] for g in gs)
+    which = [e % len(gs) for e in range(E)]                  # env e runs golden which[e]
+    env = _mk_cuda(gs[0], E)
+    assert env.use_specialized(spec) == spec
+    env.set_poi_layouts(np.stack([gs[w]["poi"] for w in which]))
+    obs0 = env.reset().cpu().numpy()
+    for e in range(E):
+        assert np.array_equal(obs0[e], gs[which[e]]["obs0"])
+    for t in range(T):
+        a = np.stack([gs[w]["actions"][t] for w in which])
+        r = _result(env, *env.step(torch.from_numpy(a).cuda()))
+        for e in range(E):
+            g = gs[which[e]]
+            obs_at = {int(tt): k for k, tt in enumerate(g["obs_steps"])}
+            k = obs_at.get(t)
+            assert_step_matches("layout %s env %d" % (shape, e), r, g, t, e=e, obs_ref=None if k is None else g["obs"][k],
+                                rew_rtol=REW_RTOL, rew_dtype=np.float32)
+    # back to the shared layout (the one given at creation = golden 0's)
+    env.set_poi_layouts(None)
+    obs0 = env.reset().cpu().numpy()
+    assert all(np.array_equal(obs0[e], gs[0]["obs0"]) for e in range(E))
+    with pytest.raises(ValueError):
+        env.set_poi_layouts(np.zeros((E + 1, c["n_pois"], 2)))
+    env.close()

@@ -51,3 +51,23 @@ def test_oracle_actions_not_mutated_and_threads_agree():
     assert np.array_equal(a, a0)
     for k in ("obs", "reward", "done", "pos_vel", "energy", "connect_bits", "adj", "adj_"):
         assert np.array_equal(r1[k], r2[k]), k
+
+
+@pytest.mark.parametrize("shape,tags", [("5x12", "abc"), ("8x64", "ab")])
+def test_oracle_per_env_poi_layouts(shape, tags):
+    """One vec-env whose instances have DIFFERENT PoI layouts: env e replays the golden recorded by the unmodified
+    reference on layout e (tests/golden/env_layout_*), all stepped together."""
+    gs = [load_golden("layout_%s_%s" % (t, shape)) for t in tags]
+    c = gs[0]["cfg"]
+    E, T = len(gs), min(g["cfg"]["T"] for g in gs)
+    poi = np.stack([g["poi"] for g in gs])
+    orc = OracleEnv(E, c["n_agents"], c["n_pois"], poi, c["r_cover"], c["r_comm"], c["comm_r_scale"], c["contact_force"])
+    obs0 = orc.reset()
+    for e, g in enumerate(gs):
+        assert np.array_equal(obs0[e], g["obs0"])
+    for t in range(T):
+        r = orc.step(np.stack([g["actions"][t] for g in gs]))
+        for e, g in enumerate(gs):
+            obs_at = {int(tt): k for k, tt in enumerate(g["obs_steps"])}
+            k = obs_at.get(t)
+            assert_step_matches("layout %s env %d" % (shape, e), r, g, t, e=e, obs_ref=None if k is None else g["obs"][k])
