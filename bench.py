@@ -241,7 +241,7 @@ def run_cuda(args):
         achieved = E * N * b_alg / launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "env_step_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not args.per_env_layouts:     # the ncu capture is of the shared-layout launch
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
