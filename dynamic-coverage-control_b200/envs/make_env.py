@@ -10,6 +10,10 @@ Optional new keys (defaults preserve the shipped behaviour):
                             (scenarios/coverage.py:34); False passes them through ("connectivity active")
   pos_pois / pos_pois_path  PoI layout (M,2) or an .npy file (the reference's scenarios/pos_pois.npy);
                             default: synthetic uniform layout, seed 0
+  per_env_layouts (False)   every env instance gets its own uniform(-1,1) PoI layout (generator seeded with
+                            `poi_seed`, default 0; rank-offset in multi-GPU jobs) — the reference's commented
+                            `np.random.uniform(-1, 1)` alternative (coverage.py:71) made per-instance;
+                            pos_pois may also be given as an (E, M, 2) array
   numpy_compat (False)      numpy in/out with the reference's dtypes instead of CUDA tensors
   device (0)                CUDA device index
 `cfg.seed` is accepted and ignored exactly like the reference (env.seed only seeds numpy, which the env
@@ -30,7 +34,13 @@ def make_env(cfg, **kwargs):
     path = getattr(cfg, "pos_pois_path", None)
     if pos_pois is None and path:
         pos_pois = np.load(path)[0:cfg.num_pois, :]
-    return CudaVecEnv(
+    per_env = None
+    if pos_pois is not None and np.asarray(pos_pois).ndim == 3:
+        per_env, pos_pois = np.asarray(pos_pois, dtype=np.float64), np.asarray(pos_pois, dtype=np.float64)[0]
+    elif getattr(cfg, "per_env_layouts", False):
+        rng = np.random.default_rng(int(getattr(cfg, "poi_seed", 0)) + 7919 * int(getattr(cfg, "env_rank", 0)))
+        per_env = rng.uniform(-1.0, 1.0, (int(cfg.n_rollout_threads), int(cfg.num_pois), 2))
+    env = CudaVecEnv(
         n_envs=cfg.n_rollout_threads,
         num_agents=cfg.num_agents,
         num_pois=cfg.num_pois,
@@ -45,3 +55,6 @@ def make_env(cfg, **kwargs):
         numpy_compat=bool(getattr(cfg, "numpy_compat", False)),
         want_connectivity=bool(getattr(cfg, "want_connectivity", False)),
     )
+    if per_env is not None:
+        env.set_poi_layouts(per_env)
+    return env

@@ -148,6 +148,13 @@ def test_make_env_boundary():
     assert tuple(r.shape) == (16, 4, 1) and tuple(d.shape) == (16, 4) and d.dtype == torch.bool
     assert "coverage_rate" in infos[0]
     env.close()
+    cfg.per_env_layouts, cfg.poi_seed = True, 3          # optional key: one synthetic layout per env instance
+    env = make_env(cfg)
+    assert env.pos_pois_per_env.shape == (16, 20, 2)
+    o = env.reset().cpu().numpy()
+    q0 = o[:, 0, 4 + 2 * 3:4 + 2 * 3 + 2]                # first PoI offset of UAV 0 (at the origin) = that env's q_0
+    assert np.array_equal(q0, env.pos_pois_per_env[:, 0].astype(np.float32)) and len(np.unique(q0[:, 0])) == 16
+    env.close()
     cfg.env_file = "something_else"
     with pytest.raises(NotImplementedError):
         make_env(cfg)
