@@ -50,6 +50,7 @@ class Learner:
         lo, hi = shard_envs(self.n_envs_global, self.comm.world, self.comm.rank)
         local = copy.copy(cfg)
         local.n_rollout_threads = hi - lo
+        local.env_rank = self.comm.rank            # per-env synthetic PoI layouts differ across ranks (make_env)
         self.local_cfg = local
 
         # 1. env
