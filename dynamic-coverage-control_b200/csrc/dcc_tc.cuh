@@ -784,9 +784,14 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         fetch_unit(0);
         fetch_unit(1);
         uint32_t it = 0, u = 0;
+        TC_PROF_DECL(p_wait_acc = 0, p_cp_acc = 0, pc0 = 0, pc1 = 0, p_begin = 0, p_end = 0);
+        TC_PROF_NOW(p_begin);
         while (cw < num_work) {
             const int slot = u & 1;
+            TC_PROF_NOW(pc0);
             cp_async_wait<1>();                  // unit u has landed (unit u+1 may still be in flight)
+            TC_PROF_NOW(pc1);
+            TC_PROF_ADD(p_cp_acc, pc0, pc1);
             float4 v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + i * 2048);
@@ -796,7 +801,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             const uint32_t ph = (it >> 1) & 1;
             const uint32_t st_u32 = smem_u32(smem + s * TCF_STAGE_BYTES);
             if (cur_kind == 0) {
+                TC_PROF_DECL(pw0 = 0, pw1 = 0);
+                TC_PROF_NOW(pw0);
                 mbar_wait(&empty[s], ph ^ 1);
+                TC_PROF_NOW(pw1);
+                TC_PROF_ADD(p_wait_acc, pw0, pw1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
@@ -842,10 +851,16 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             }
         }
         cp_async_wait<0>();
+        TC_PROF_NOW(p_end);
+        TC_PROF_OUT(t == 0, 21, p_wait_acc);
+        TC_PROF_OUT(t == 0, 22, p_cp_acc);
+        TC_PROF_OUT(t == 0, 23, p_end - p_begin);
     } else if (warp >= 12) {
         setmaxnreg_dec<32>();
         if (warp == 12 && lane == 0) {
             uint32_t it = 0;
+            TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
+            TC_PROF_NOW(m_begin);
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const int ot = w % out_tiles, ks = w / out_tiles;
                 const int n0 = (ot >> 1) * p.tile_n;
@@ -855,8 +870,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
                     const int s = it & 1;
                     const uint32_t ph = (it >> 1) & 1;
+                    TC_PROF_NOW(t0);
                     mbar_wait(&tempty[s], ph ^ 1);
+                    TC_PROF_NOW(t1);
                     mbar_wait(&full[s], ph);
+                    TC_PROF_NOW(t2);
                     tc_fence_after();
                     const uint32_t d = tmem_base + s * TC_N;
                     const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
@@ -878,8 +896,17 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     }
                     tc_commit(&empty[s]);
                     tc_commit(&tfull[s]);
+                    TC_PROF_NOW(t3);
+                    TC_PROF_ADD(m_wacc, t0, t1);
+                    TC_PROF_ADD(m_wfull, t1, t2);
+                    TC_PROF_ADD(m_issue, t2, t3);
                 }
             }
+            TC_PROF_OUT(true, 16, (unsigned long long)it);
+            TC_PROF_OUT(true, 17, m_wacc);
+            TC_PROF_OUT(true, 18, m_wfull);
+            TC_PROF_OUT(true, 19, m_issue);
+            TC_PROF_OUT(true, 20, t3 - m_begin);
         }
         __syncwarp();
     } else {
