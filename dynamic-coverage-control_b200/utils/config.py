@@ -76,15 +76,15 @@ def check_supported(cfg):
     in the reference, whose active masks are all ones) and the network switches use_ReLU (tanh trunk),
     use_feature_normalization, use_orthogonal (xavier init), use_centralized_V (per-agent critic), layer_N 1..3.
     Refused loudly instead of silently computing something else: recurrent policies (other kernel shapes; SURVEY §8
-    f-4), stacked frames and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
+    f-4) and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
     tensor to an nn.Parameter attribute and raises TypeError on the first update, popart.py:61)."""
     bad = []
     if getattr(cfg, "use_recurrent_policy", False) or getattr(cfg, "use_naive_recurrent_policy", False):
         bad.append("recurrent policies")
     if getattr(cfg, "use_popart", False):
         bad.append("use_popart")
-    if getattr(cfg, "use_stacked_frames", False) or int(getattr(cfg, "stacked_frames", 1)) != 1:
-        bad.append("stacked frames")
+    # use_stacked_frames / stacked_frames, use_obs_instead_of_state, share_policy, use_render, render_episodes, ifi:
+    # read (mlp.py:39, learner.py:40) or merely listed in mappo.yaml but never acted on by the reference -> accepted, no-ops
     if int(getattr(cfg, "num_mini_batch", 1)) < 1:
         bad.append("num_mini_batch < 1")
     if not 1 <= int(getattr(cfg, "layer_N", 1)) <= 3:

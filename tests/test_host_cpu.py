@@ -41,7 +41,7 @@ def test_unsupported_branches_fail_loudly():
     from dcc_b200.utils.config import check_supported, load_config
     check_supported(load_config(None))
     for key, val in (("use_recurrent_policy", True), ("use_naive_recurrent_policy", True), ("use_popart", True),
-                     ("num_mini_batch", 0), ("layer_N", 4), ("layer_N", 0), ("stacked_frames", 2)):
+                     ("num_mini_batch", 0), ("layer_N", 4), ("layer_N", 0)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         with pytest.raises(NotImplementedError):
@@ -51,7 +51,7 @@ def test_unsupported_branches_fail_loudly():
                      ("use_clipped_value_loss", False), ("use_max_grad_norm", False), ("weight_decay", 1e-4),
                      ("use_proper_time_limits", True), ("use_linear_lr_decay", False), ("use_ReLU", False),
                      ("use_feature_normalization", False), ("use_centralized_V", False), ("use_orthogonal", False),
-                     ("layer_N", 3)):
+                     ("layer_N", 3), ("stacked_frames", 4), ("use_stacked_frames", True), ("use_obs_instead_of_state", True)):
         cfg = load_config(None)
         setattr(cfg, key, val)
         check_supported(cfg)
