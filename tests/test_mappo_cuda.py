@@ -438,3 +438,36 @@ def test_learner_end_to_end_with_config_switches(over):
     assert not torch.equal(w0, lr.policy.actor.params) and not torch.equal(c0, lr.policy.critic.params)
     assert torch.isfinite(lr.policy.actor.params).all() and torch.isfinite(lr.policy.critic.params).all()
     lr.train_envs.close()
+
+
+def test_train_cli_reads_the_three_yaml_files(tmp_path, monkeypatch):
+    """`python -m dcc_b200.train <gpu> <config_dir> [key=value ...]` = the reference's train.py (:10-29): three YAML
+    files in the reference's layout (comments, `5e-4`-style scalars, later file wins), key=value overrides, checkpoints
+    every save_interval, a headless render rollout every render_interval."""
+    import glob
+    from dcc_b200 import train
+    cfg_dir = tmp_path / "config"
+    (cfg_dir / "env_config").mkdir(parents=True)
+    (cfg_dir / "algo_config").mkdir()
+    (cfg_dir / "env_config" / "dcc.yaml").write_text(
+        "env_file: mpe.uav_dcc\nenv_class: DCEnv\nscenario_name: \"coverage\"\n\nnum_agents: 4\nnum_pois: 20\nmax_ep_len: 12\n"
+        "r_cover: 0.2\nr_comm: 0.4\ncomm_r_scale: 0.95\ncomm_force_scale: 0.0\n\nsave_name: \"uav_dcc\"\nppo_epoch: 2\n\n"
+        "n_rollout_threads: 16  # parallel envs\nn_eval_rollout_threads: 16\nn_render_rollout_threads: 1\n")
+    (cfg_dir / "algo_config" / "mappo.yaml").write_text(
+        "algo_file: \"mappo\"\nn_eval_rollout_threads: 4  # later file wins\nalgo_hidden_size: 256\nlayer_N: 1\nuse_ReLU: true\n"
+        "use_popart: false\nuse_valuenorm: true\nactor_lr: 5e-4\ncritic_lr: 5e-4\nopti_eps: 1e-5  # adam eps\nweight_decay: 0\n"
+        "num_mini_batch: 1\nuse_linear_lr_decay: true\n")
+    (cfg_dir / "expt.yaml").write_text(
+        "seed: 0\nn_iters: 4\neval_interval: 2\nrender_interval: 4\nsave_gifs: True\nsave_interval: 2\nlog_wandb: True\n"
+        "log_interval: 1\nsave_model: True\nload_model: False\nload_buffer_path: None\nmain_save_path: \"%s/\"\n" % (tmp_path / "results"))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    train.main(["0", str(cfg_dir), "n_rollout_threads=24"])
+    runs = glob.glob(str(tmp_path / "results" / "uav_dcc" / "*"))
+    assert len(runs) == 1
+    files = sorted(os.listdir(runs[0]))
+    assert "config.json" in files and "models_2.pt" in files and "models_4.pt" in files, files
+    assert os.path.exists(os.path.join(runs[0], "models_4.pt", "agent.pkl"))
+    assert "models_4_traj.npz" in files and "models_4.gif" in files, files
+    with open(os.path.join(runs[0], "config.json")) as f:
+        saved = json.load(f)
+    assert saved["n_rollout_threads"] == 24 and saved["n_eval_rollout_threads"] == 4 and abs(saved["actor_lr"] - 5e-4) < 1e-12
