@@ -471,3 +471,74 @@ def test_train_cli_reads_the_three_yaml_files(tmp_path, monkeypatch):
     with open(os.path.join(runs[0], "config.json")) as f:
         saved = json.load(f)
     assert saved["n_rollout_threads"] == 24 and saved["n_eval_rollout_threads"] == 4 and abs(saved["actor_lr"] - 5e-4) < 1e-12
+
+
+FLAG_COMBOS = [
+    dict(use_ReLU=False, layer_N=2, use_clipped_value_loss=False, weight_decay=1e-3),
+    dict(use_feature_normalization=False, use_huber_loss=False, use_max_grad_norm=False),
+    dict(use_centralized_V=False, num_mini_batch=2, use_ReLU=False),
+    dict(use_valuenorm=False, layer_N=3),
+    dict(use_valuenorm=False, use_gae=False, use_feature_normalization=False, num_mini_batch=3),
+    dict(use_centralized_V=False, layer_N=2, use_feature_normalization=False, use_huber_loss=False, weight_decay=5e-4),
+]
+
+
+@pytest.mark.parametrize("flags", FLAG_COMBOS)
+def test_update_vs_oracle_flag_combinations(flags):
+    """The mappo.yaml switches COMBINED (each is pinned alone against a reference golden): returns + one update on a
+    seeded synthetic rollout, tcgen05 backend, against the float64 oracle with the same switches."""
+    import torch
+    from oracle import mappo_oracle as mo
+    N, M, Hd, E, T, EP = 4, 6, 256, 12, 10, 2
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=EP, seed=5, n_iters=10, actor_seed=31, critic_seed=32,
+             clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0, max_grad_norm=10.0, huber_delta=10.0, opti_eps=1e-5)
+    c.update(flags)
+    cent, use_vn, nmb = c.get("use_centralized_V", True), c.get("use_valuenorm", True), c.get("num_mini_batch", 1)
+    rng = np.random.default_rng(17)
+    obs = rng.normal(0, 1.5, (T + 1, E, N, D)).astype(np.float32)
+    act = rng.normal(0, 1.2, (T, E, N, 2)).astype(np.float32)
+    cfg, pol, tr, buf = build(c, E, T, chunk_rows=16)
+    dev = buf.device
+    buf.obs.copy_(torch.from_numpy(obs).to(dev))
+    buf.actions.copy_(torch.from_numpy(act).to(dev))
+    vn0 = (0.3, 4.0, 0.02)
+    if use_vn:
+        tr.value_normalizer.state[:3] = torch.tensor(vn0, device=dev)
+    _, logp, _ = pol.evaluate_actions(None, buf.obs[:-1], None, None, buf.actions)
+    lp_old = logp.cpu().numpy().reshape(T, E, N) + rng.normal(0, 0.25, (T, E, N)).astype(np.float32)
+    full = lambda a: np.broadcast_to(a[:, :, None], a.shape + (N,)).copy()     # noqa: E731  per-env -> per-agent
+    vals = rng.normal(0, 1.0, (T + 1, E, N)).astype(np.float32) if not cent else full(rng.normal(0, 1.0, (T + 1, E)).astype(np.float32))
+    rew = full(rng.normal(0, 3.0 if not use_vn else 30.0, (T, E)).astype(np.float32))
+    masks = full((rng.random((T + 1, E)) > 0.1).astype(np.float32))
+    per_row = (lambda a: a[:, :, 0]) if cent else (lambda a: a.reshape(a.shape[0], -1))   # noqa: E731
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    buf.action_log_probs_ten.copy_(t(lp_old))
+    buf.values_te.copy_(t(per_row(vals))); buf.rewards_te.copy_(t(per_row(rew))); buf.masks_te.copy_(t(per_row(masks)))
+    buf.compute_returns(None, tr.value_normalizer, policy=pol)
+    ret = buf.returns_te.cpu().numpy().reshape(T + 1, E, -1)
+    ret = np.broadcast_to(ret, (T + 1, E, N)) if cent else ret
+    ovn = mo.ValueNorm(vn0) if use_vn else None
+    oret = mo.gae_returns(rew, vals, masks, ovn, cfg.gamma, cfg.gae_lambda, use_gae=c.get("use_gae", True))
+    assert np.allclose(ret[:-1], oret[:-1], rtol=1e-5, atol=1e-3)
+    B = T * E * N
+    perms = np.stack([np.random.default_rng(200 + ep).permutation(B) for ep in range(EP)])
+    tr.permutation_fn = lambda ep, n: perms[ep]
+    pol.lr_decay(3, 10)
+    info = tr.train(buf)
+    a_shapes, c_shapes = net_shapes(c)
+    otr = mo.Trainer(make_params(a_shapes, 31), make_params(c_shapes, 32), c, vn_state=vn0)
+    oinfo = otr.train(obs, act, lp_old[..., None], vals[..., None], np.ascontiguousarray(ret)[..., None], pol.lr_actor_now, EP,
+                      perms=perms)
+    for k in oinfo:
+        assert abs(info[k] - oinfo[k]) <= 5e-5 * max(1.0, abs(oinfo[k])), (flags, k, info[k], oinfo[k])
+    for tag, net, onet in (("actor", pol.actor, otr.actor), ("critic", pol.critic, otr.critic)):
+        assert set(net.layout) == set(onet.p), (tag, set(net.layout) ^ set(onet.p))
+        for k in net.layout:
+            got = net.view(k).cpu().numpy().astype(np.float64)
+            ref = onet.p[k].reshape(got.shape)
+            bad = np.abs(got - ref) > 1e-5 + 2e-5 * np.abs(ref)
+            assert bad.mean() <= 5e-3 and np.abs(got - ref).max() <= 3 * EP * nmb * pol.lr_actor_now, \
+                (flags, tag, k, bad.mean(), np.abs(got - ref).max())
+    if use_vn:
+        assert np.allclose(tr.value_normalizer.state.cpu().numpy()[:3], otr.vn.state(), rtol=1e-5)
