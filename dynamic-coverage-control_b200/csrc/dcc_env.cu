@@ -414,16 +414,20 @@ struct EnvSpec {
     static constexpr bool BULK = env_block_bulk_ok(N, ROW_BYTES);
     static constexpr int R = rows_per_chunk(N, ROW_BYTES);
     static constexpr int NCHUNK = N / R;
-    static constexpr int NBUF = (BULK && NCHUNK > 1) ? 2 : 1;
+    // stage buffers per warp: ping-pong when an env block needs several chunks — except when a chunk is so large
+    // (16/256: 10.5 KB) that the second buffer costs more in resident warps than it hides in store latency.  Measured at
+    // 16/256 / 32 768 envs (µs per step): 2 buffers, 10 warps per SM 547; 1 buffer with 12 / 16 / 20 / 24 / 32 warps per SM
+    // (168 / 128 / 96 / 80 / 64 registers) 486 / 476 / 519 / 582 / 686.
+    static constexpr bool BIG_STAGE = (size_t)R * ROW_BYTES > 8 * 1024;
+    static constexpr int NBUF = (BULK && NCHUNK > 1 && !BIG_STAGE) ? 2 : 1;
     static constexpr int STAGE_FLOATS = R * D;
     static constexpr int STAGE_STRIDE = (int)((((size_t)STAGE_FLOATS * 4 + 127) / 128 * 128) / 4);
     static constexpr int PW_BYTES = (int)(((size_t)N * 32 + (size_t)STAGE_STRIDE * 4 * NBUF + 127) / 128 * 128);
-    // warps per CTA: 4, or 2 when a warp's stage is so large (16/256: 21.6 KB) that 4-warp CTAs would leave shared memory
-    // unused (2 x 86 KB of 227 KB = 8 warps per SM; 5 x 43 KB = 10 warps) — the kernel is latency-bound at that occupancy
+    // warps per CTA: 4, or 2 when a warp's stage is so large that 4-warp CTAs would leave shared memory unused
     static constexpr int WPC = (PW_BYTES * 4 > 64 * 1024) ? 2 : 4;
     static constexpr int SMEM = PW_BYTES * WPC;
     static constexpr int FIT = (int)(233472 / (SMEM + 1024));
-    static constexpr int MIN_BLOCKS = FIT < 1 ? 1 : (FIT > 6 ? 6 : FIT);
+    static constexpr int MIN_BLOCKS = (BIG_STAGE && NCHUNK > 1) ? 4 : (FIT < 1 ? 1 : (FIT > 6 ? 6 : FIT));
     static constexpr int HP = R * (N - 1);               // ordered (row, other) head pairs per chunk
     static constexpr int HPL = (HP + 31) / 32 > 0 ? (HP + 31) / 32 : 1;
     static_assert(BULK, "specialisations require a 16-byte-multiple env block");
