@@ -55,14 +55,15 @@ struct EnvKParams {
 
 // Observation staging: chunks of R rows whose byte size is a multiple of 16 (cp.async.bulk granularity) and fits the
 // per-warp stage budget.  Shared by the host-side planner and the compile-time specialisations.
-constexpr size_t STAGE_BUDGET = 12 * 1024;
+constexpr size_t STAGE_BUDGET = 12 * 1024;        // runtime-shape kernel (ping-pong staged)
+constexpr size_t SPEC_STAGE_BUDGET = 6000;        // compile-time specialisations (single buffer, more resident warps)
 __host__ __device__ constexpr bool env_block_bulk_ok(int N, size_t row_bytes) { return ((size_t)N * row_bytes) % 16 == 0; }
-__host__ __device__ constexpr int rows_per_chunk(int N, size_t row_bytes) {
+__host__ __device__ constexpr int rows_per_chunk(int N, size_t row_bytes, size_t budget = STAGE_BUDGET) {
     const bool bulk = env_block_bulk_ok(N, row_bytes);
     const int unit = !bulk ? 1 : ((row_bytes % 16 == 0) ? 1 : ((row_bytes % 8 == 0) ? 2 : 4));
     int R = unit;
     for (int r = unit; r <= N; r += unit)
-        if (N % r == 0 && r * row_bytes <= STAGE_BUDGET) R = r;
+        if (N % r == 0 && r * row_bytes <= budget) R = r;
     return R;
 }
 
@@ -412,14 +413,17 @@ struct EnvSpec {
     static constexpr int PPL = (P + 31) / 32 > 0 ? (P + 31) / 32 : 1;
     static constexpr size_t ROW_BYTES = (size_t)D * 4;
     static constexpr bool BULK = env_block_bulk_ok(N, ROW_BYTES);
-    static constexpr int R = rows_per_chunk(N, ROW_BYTES);
+    static constexpr int R = rows_per_chunk(N, ROW_BYTES, SPEC_STAGE_BUDGET);
     static constexpr int NCHUNK = N / R;
-    // stage buffers per warp: ping-pong when an env block needs several chunks — except when a chunk is so large
-    // (16/256: 10.5 KB) that the second buffer costs more in resident warps than it hides in store latency.  Measured at
-    // 16/256 / 32 768 envs (µs per step): 2 buffers, 10 warps per SM 547; 1 buffer with 12 / 16 / 20 / 24 / 32 warps per SM
-    // (168 / 128 / 96 / 80 / 64 registers) 486 / 476 / 519 / 582 / 686.
+    // ONE stage buffer per warp and small chunks: the kernel is latency-bound, so resident warps matter more than
+    // hiding the bulk store behind a second buffer (the next chunk waits for the TMA engine to have READ the stage).
+    // Measured (µs per step, launch_bounds in brackets):
+    //   8/64, 65 536 envs:   8-row chunk, 1 buffer, 20 warps/SM (92 regs) 125.5 | 4-row chunks, 1 buffer, 24 warps (80 regs)
+    //                        122.7 | 32 warps (64 regs) 123.1 | 2-row chunks, 2 buffers, 32 warps 122.7
+    //   16/256, 32 768 envs: 2 buffers, 10 warps/SM 547 | 1 buffer with 12 / 16 / 20 / 24 / 32 warps/SM (168 / 128 / 96 / 80 /
+    //                        64 registers) 486 / 476 / 519 / 582 / 686
     static constexpr bool BIG_STAGE = (size_t)R * ROW_BYTES > 8 * 1024;
-    static constexpr int NBUF = (BULK && NCHUNK > 1 && !BIG_STAGE) ? 2 : 1;
+    static constexpr int NBUF = 1;
     static constexpr int STAGE_FLOATS = R * D;
     static constexpr int STAGE_STRIDE = (int)((((size_t)STAGE_FLOATS * 4 + 127) / 128 * 128) / 4);
     static constexpr int PW_BYTES = (int)(((size_t)N * 32 + (size_t)STAGE_STRIDE * 4 * NBUF + 127) / 128 * 128);
@@ -427,7 +431,8 @@ struct EnvSpec {
     static constexpr int WPC = (PW_BYTES * 4 > 64 * 1024) ? 2 : 4;
     static constexpr int SMEM = PW_BYTES * WPC;
     static constexpr int FIT = (int)(233472 / (SMEM + 1024));
-    static constexpr int MIN_BLOCKS = (BIG_STAGE && NCHUNK > 1) ? 4 : (FIT < 1 ? 1 : (FIT > 6 ? 6 : FIT));
+    static constexpr int WANT_BLOCKS = BIG_STAGE ? 4 : 6;    // 4 x 4 warps at 128 registers, 6 x 4 warps at 80
+    static constexpr int MIN_BLOCKS = FIT < 1 ? 1 : (FIT > WANT_BLOCKS ? WANT_BLOCKS : FIT);
     static constexpr int HP = R * (N - 1);               // ordered (row, other) head pairs per chunk
     static constexpr int HPL = (HP + 31) / 32 > 0 ? (HP + 31) / 32 : 1;
     static_assert(BULK, "specialisations require a 16-byte-multiple env block");
