@@ -16,6 +16,7 @@
 //
 // Reference paths are relative to /root/reference/uav_dcc_control/envs/mpe/multiagent/.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -55,8 +56,8 @@ struct EnvKParams {
 
 // Observation staging: chunks of R rows whose byte size is a multiple of 16 (cp.async.bulk granularity) and fits the
 // per-warp stage budget.  Shared by the host-side planner and the compile-time specialisations.
-constexpr size_t STAGE_BUDGET = 12 * 1024;        // runtime-shape kernel (ping-pong staged)
-constexpr size_t SPEC_STAGE_BUDGET = 6000;        // compile-time specialisations (single buffer, more resident warps)
+constexpr size_t STAGE_BUDGET = 12 * 1024;        // upper bound of a chunk (shared-memory planning)
+constexpr size_t SPEC_STAGE_BUDGET = 6000;        // chunk size actually used: single buffer, more resident warps
 __host__ __device__ constexpr bool env_block_bulk_ok(int N, size_t row_bytes) { return ((size_t)N * row_bytes) % 16 == 0; }
 __host__ __device__ constexpr int rows_per_chunk(int N, size_t row_bytes, size_t budget = STAGE_BUDGET) {
     const bool bulk = env_block_bulk_ok(N, row_bytes);
@@ -981,10 +982,17 @@ int dcc_env_create(const dcc_env_cfg *cfg, const double *h_poi_xy, int device, v
     // observation staging: chunks of R rows whose byte size is a multiple of 16 (cp.async.bulk granularity)
     const size_t row_bytes = (size_t)h->D * 4;
     k.use_bulk = env_block_bulk_ok(N, row_bytes) ? 1 : 0;
-    const int R = rows_per_chunk(N, row_bytes);
+    // Small chunks through ONE stage buffer per warp, as in the specialisations: resident warps beat a second buffer.
+    // Measured with the runtime-shape kernel (µs per step, 12 KB chunks + 2 buffers -> 6000 B chunks + 1 buffer):
+    // 8/64 x 65 536: 254 -> 199; 16/256 x 32 768: 906 -> 572; 6/41 x 65 536: 196 -> 196 (one chunk either way).
+    size_t budget = SPEC_STAGE_BUDGET;
+    int nbuf_multi = 1;
+    if (const char *e = getenv("DCC_ENV_GENERIC_BUDGET")) budget = (size_t)atoi(e);     // tuning knobs (tools/env_generic_probe.py)
+    if (const char *e = getenv("DCC_ENV_GENERIC_NBUF")) nbuf_multi = atoi(e) == 2 ? 2 : 1;
+    const int R = rows_per_chunk(N, row_bytes, budget);
     k.rows_per_chunk = R;
     k.n_chunks = N / R;
-    k.n_buf = (k.use_bulk && k.n_chunks > 1) ? 2 : 1;
+    k.n_buf = (k.use_bulk && k.n_chunks > 1) ? nbuf_multi : 1;
     k.stage_floats = R * h->D;
 
     h->spec = nullptr;
