@@ -349,7 +349,9 @@ __device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float 
 // Backward of h = LN(a)*gamma+beta, a = relu(z+bias):  given dh, a, mean, rstd -> dz (in place over dh allowed),
 // and accumulates dgamma, dbeta, dbias (one set of float atomics per block).  H <= 256, blockDim = 256,
 // dynamic shared memory = 8 * 3 * 256 floats.
-__global__ void __launch_bounds__(256, 3) relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
+// launch bounds: 4 CTAs per SM (64 registers, 32 bytes of spill) measured 1.8 % faster end to end than 3 (80 registers); the
+// head-fused variant below loses with 3 CTAs (192 bytes of spill) and stays at 2
+__global__ void __launch_bounds__(256, 4) relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
                                    const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
                                    float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
                                    int H, int act) {
