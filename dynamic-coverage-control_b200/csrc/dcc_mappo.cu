@@ -48,6 +48,7 @@ struct MappoHandle {
     dcc_mappo_cfg cfg;
     int device, sm_count;
     int backend;     // 1 = SIMT fp32, 2 = tcgen05 3xTF32
+    bool f16_fwd;    // backend 2: forward GEMMs on LayerNorm outputs use the fp16 hi/lo split kernel (DCC_TC_F16=0 disables)
     NetLayout la, lc;
     int chunk_rows;  // env-step rows per chunk
     // scratch
@@ -129,10 +130,16 @@ static int launch_gemm(MappoHandle *h, bool ta, bool tb, int M, int N, int K, co
 }
 
 // ---- tcgen05 backend launchers ---------------------------------------------------------------------------------
-static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transposed, int K, float *img, cudaStream_t s) {
-    const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
+// power-of-two scale of the fp16-split weight images (keeps the lo halves normal; |W| < 255 stays finite)
+constexpr float TC_F16_WSCALE = 256.f;
+
+static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transposed, int K, float *img, cudaStream_t s,
+                           bool f16 = false) {
+    const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;
+    const int KT = (K + bk - 1) / bk;
     const int n = KT * tc::TC_N * 8;
-    tc::tc_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(W, ldw, transposed ? 1 : 0, K, KT, img);
+    if (f16) tc::tc_prep_weights_f16_kernel<<<(n + 255) / 256, 256, 0, s>>>(W, ldw, transposed ? 1 : 0, K, KT, TC_F16_WSCALE, img);
+    else tc::tc_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(W, ldw, transposed ? 1 : 0, K, KT, img);
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
     return DCC_OK;
@@ -142,18 +149,23 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
 // fused bias + ReLU + LayerNorm of an MLP block: a -> a_out (optional), LN(a) * gamma + beta -> h_out.
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
-                       const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr) {
+                       const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
+                       bool f16 = false) {
     if (M <= 0) return DCC_OK;
     if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
     static bool attr_set = false;
     if (!attr_set) {
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::TCF_SMEM_BYTES));
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::TCF_SMEM_BYTES));
         attr_set = true;
     }
     tc::TcfParams p;
     memset(&p, 0, sizeof p);
-    p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = (K + tc::TC_BK - 1) / tc::TC_BK; p.lda = lda; p.ldc = ldc;
+    const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;    // `img` must come from tc_prep_weights with the same f16 flag
+    p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = (K + bk - 1) / bk; p.lda = lda; p.ldc = ldc;
+    p.out_scale = f16 ? 1.f / TC_F16_WSCALE : 1.f;
     p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
     p.act = act_of(h);
@@ -177,9 +189,15 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
         if (bias && h_out) ok = ok && tc::tc_make_store_map(&p.tmH, h_out, M, ldc);
         p.use_tma = ok ? 1 : 0;
     }
+    // L2 prefetch of the activation tiles two stages (64 KB per SM) ahead of the fp16-split kernel's loads; measured:
+    // 2 stages > 4 > none > 8, and no gain for the MMA-bound 3xTF32 kernel (DCC_TC_PF=<stages> overrides, 0 = off)
+    static const int pf_env = getenv("DCC_TC_PF") ? atoi(getenv("DCC_TC_PF")) : -1;
+    p.pf_dist = pf_env >= 0 ? pf_env : (f16 ? 2 : 0);
+    if (p.pf_dist > 0 && !tc::tc_make_prefetch_map(&p.tmA, A, M, K, lda, bk)) p.pf_dist = 0;
     const int work = row_tiles * p.splits;
     const int grid = work < h->sm_count ? work : h->sm_count;
-    tc::tc_gemm_fwd_kernel<<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    if (f16) tc::tc_gemm_fwd_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    else tc::tc_gemm_fwd_kernel<false><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
     return DCC_OK;
@@ -218,6 +236,11 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
     return DCC_OK;
 }
 
+// Which forward GEMMs run the fp16-split kernel: those whose activation operand is a LayerNorm output (block 0 only
+// when the input LayerNorm is on: |xhat| <= sqrt(D); blocks >= 1 always read LN(a) * gamma + beta), i.e. values far
+// inside fp16's range.  Raw observations and the backward dX GEMMs (unbounded dynamic range) stay on 3xTF32.
+static inline bool fwd_f16(const MappoHandle *h, const NetLayout &L, int k) { return h->f16_fwd && (k > 0 || L.has_ln0); }
+
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
@@ -227,9 +250,9 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
     DCC_CUDA_TRY(cudaGetLastError());
     if (h->backend == 2) {
         int rc;
-        if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s))) return rc;
+        if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s, fwd_f16(h, L, 0)))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
-            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s))) return rc;
+            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
             if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s))) return rc;
         }
     }
@@ -261,7 +284,8 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         if (h->backend == 2) {
             // tcgen05 GEMM with the block's bias + activation + LayerNorm fused into its epilogue (one kernel per block)
             rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
-                             bk, P + L.lg[k], P + L.lb[k], h->hh[k], save ? h->mean[k] : nullptr, save ? h->rstd[k] : nullptr);
+                             bk, P + L.lg[k], P + L.lb[k], h->hh[k], save ? h->mean[k] : nullptr, save ? h->rstd[k] : nullptr,
+                             fwd_f16(h, L, k));
             if (rc) return rc;
             continue;
         }
@@ -378,6 +402,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     memset(h, 0, sizeof *h);
     h->magic = MAPPO_MAGIC; h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
     h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
+    h->f16_fwd = !(getenv("DCC_TC_F16") && atoi(getenv("DCC_TC_F16")) == 0);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
@@ -741,12 +766,15 @@ int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float 
 int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *A, int lda, const float *B,
                 int ldb, float *C, int ldc, int accumulate, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
-    if (!h || !A || !B || !C || backend < 0 || backend > 2 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
+    if (!h || !A || !B || !C || backend < 0 || backend > 3 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
     DCC_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (backend == 0) backend = h->backend;
-    if (backend == 2) {
-        // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features)
+    if (backend == 2 || backend == 3) {
+        // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features);
+        // backend 3 = the fp16-split forward kernel (|A| < 65504, |B| < 255)
+        const bool f16 = backend == 3;
+        if (f16 && ta) return DCC_ERR_UNSUPPORTED;
         if (ta && !tb && M == tc::TC_N) {   // dW = dZ^T X
             if (!accumulate) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
             return tc_gemm_wgrad(h, K, N, A, lda, B, ldb, C, ldc, s);
@@ -755,8 +783,8 @@ int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, 
         const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
         float *img = nullptr;
         DCC_CUDA_TRY(cudaMalloc(&img, (size_t)KT * 2 * tc::TC_B_TILE_FLOATS * sizeof(float)));
-        int rc = tc_prep_weights(h, B, ldb, tb == 0, K, img, s);
-        if (!rc) rc = tc_gemm_fwd(h, M, K, A, lda, img, C, ldc, s);
+        int rc = tc_prep_weights(h, B, ldb, tb == 0, K, img, s, f16);
+        if (!rc) rc = tc_gemm_fwd(h, M, K, A, lda, img, C, ldc, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, f16);
         cudaStreamSynchronize(s);
         cudaFree(img);
         return rc;

@@ -15,6 +15,7 @@
 // i+1); one thread issues the MMAs; tcgen05.commit arrives on the mbarriers that recycle the stages.
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+#include <cuda_fp16.h>
 
 #include "dcc_common.cuh"
 
@@ -42,6 +43,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // base, which makes the compiler fall back to generic LD/ST (slow address-space resolution) unless told otherwise
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4 &v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
@@ -120,6 +124,16 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, kind::f16 (fp16 operands, 16 reduction elements per instruction, twice the tf32 rate)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // 32 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -146,6 +160,22 @@ __device__ __forceinline__ void split_tf32(const float4 &x, float4 &hi, float4 &
     lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
 }
 
+// fp16 hi/lo split of 8 consecutive fp32 values: hi = fp16(x), lo = fp16(x - hi), packed in memory order (element 0 in
+// the low half of the first word).  11 + 11 significand bits: the same 2^-22 class as the tf32 split, in half the bytes.
+__device__ __forceinline__ uint32_t h2_bits(const __half2 &h) { return *reinterpret_cast<const uint32_t *>(&h); }
+__device__ __forceinline__ void split_f16_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    hi = h2_bits(h);
+    lo = h2_bits(__floats2half2_rn(a - f.x, b - f.y));
+}
+__device__ __forceinline__ void split_f16x8(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
+    split_f16_pair(a.x, a.y, hi.x, lo.x);
+    split_f16_pair(a.z, a.w, hi.y, lo.y);
+    split_f16_pair(b.x, b.y, hi.z, lo.z);
+    split_f16_pair(b.z, b.w, hi.w, lo.w);
+}
+
 // Shared-memory matrix descriptor (sm_100 UMMA), SWIZZLE_128B: start address, leading / stride byte offsets in
 // 16-byte units, descriptor version 1, layout type 2 (bits 61-63).
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -163,6 +193,12 @@ __device__ __forceinline__ uint32_t mn32_offset(int group, int k, int chunk16, i
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with fp16 operands (format code 0) and fp32 accumulation
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- weight image: [KT] x { hi tile, lo tile }, each tile = 256 (n) rows x 32 (k) floats, K-major, 128B-swizzled ----
@@ -190,6 +226,30 @@ __global__ void tc_prep_weights_kernel(const float *__restrict__ W, int ldw, int
     float *tile = img + (size_t)kt * (2 * TC_B_TILE_FLOATS) + n * TC_BK + ((c ^ (n & 7)) << 2);
     *reinterpret_cast<float4 *>(tile) = hi;
     *reinterpret_cast<float4 *>(tile + TC_B_TILE_FLOATS) = lo;
+}
+
+// fp16-split image: [KT64] x { hi tile, lo tile }, each tile = 256 (n) rows x 64 (k) halves (the same 32 KB and the
+// same 128-byte rows / swizzle as above, twice the reduction depth).  The weights are multiplied by `wscale` (a power of
+// two, undone exactly in the epilogue) so that the lo halves stay in fp16's normal range; hi saturates at the largest
+// finite fp16 instead of overflowing.
+constexpr int TC_BK16 = 64;
+__global__ void tc_prep_weights_f16_kernel(const float *__restrict__ W, int ldw, int transposed, int K, int KT,
+                                           float wscale, float *__restrict__ img) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (kt, n, c)
+    if (idx >= KT * TC_N * 8) return;
+    const int c = idx & 7, n = (idx >> 3) & (TC_N - 1), kt = idx >> 11;
+    float xv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kt * TC_BK16 + c * 8 + e;
+        const float w = (k < K) ? (transposed ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
+        xv[e] = fminf(fmaxf(w * wscale, -65504.f), 65504.f);
+    }
+    uint4 hi, lo;
+    split_f16x8(make_float4(xv[0], xv[1], xv[2], xv[3]), make_float4(xv[4], xv[5], xv[6], xv[7]), hi, lo);
+    float *tile = img + (size_t)kt * (2 * TC_B_TILE_FLOATS) + n * TC_BK + ((c ^ (n & 7)) << 2);
+    *reinterpret_cast<uint4 *>(tile) = hi;
+    *reinterpret_cast<uint4 *>(tile + TC_B_TILE_FLOATS) = lo;
 }
 
 // ---- forward-shaped GEMM: C[M, 256] = A[M, K] * B^T, A row-major (K contiguous), B from a weight image ----------
@@ -239,7 +299,13 @@ struct TcfParams {
     // or store-queue stalls in the epilogue warps, rows past M are clipped by the hardware.
     int use_tma;
     int act;             // trunk activation of the fused epilogue: 0 = ReLU, 1 = tanh (mappo.yaml use_ReLU)
+    float out_scale;     // fp16-split kernel: 1 / wscale of the weight image, applied to the drained tile
     alignas(64) CUtensorMap tmC, tmH;
+    // L2 prefetch of the activation operand: one cp.async.bulk.prefetch.tensor per K-stage, issued `pf_dist` stages ahead
+    // of the producers' loads (box = 128 rows x one stage of columns), so that their LDGs hit L2 instead of waiting
+    // ~2 k cycles for HBM with only 16 KB in flight per SM.  0 = off.
+    int pf_dist;
+    alignas(64) CUtensorMap tmA;
 };
 
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -267,6 +333,24 @@ inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int 
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// [rows, K] fp32 activation matrix (leading dimension ld) -> prefetch map with a box of 128 rows x `box_cols` columns
+inline bool tc_make_prefetch_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_cols) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return false;
+    PFN_tensorMapEncodeTiled enc = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
+    if (rows < 1 || (ld & 3) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 128}, estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(x), "r"(y) : "memory");
+}
 // smem box (swizzled as the map says) -> global tile at (column x, row y), completion tracked by the bulk async-group
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t saddr, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)tm), "r"(saddr),
@@ -288,6 +372,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// F16 = false: 3xTF32, 32 reduction elements per stage (p.KT = ceil(K / 32)).
+// F16 = true:  fp16 hi/lo split, 64 reduction elements per stage in the SAME stage bytes, tile offsets, swizzle and 12
+//              MMAs (kind::f16, K = 16 each) — half the shared-memory traffic and half the tensor time per reduction
+//              element; p.KT = ceil(K / 64), p.Bimg from tc_prep_weights_f16_kernel.  |A| must stay below 65504
+//              (LayerNorm outputs here).
+template <bool F16>
 __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __grid_constant__ TcfParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -331,6 +421,24 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             kt = (ww % p.splits) * p.kt_per_split;
             kt1 = min(p.KT, kt + p.kt_per_split);
         };
+        // prefetch cursor (thread 0): runs p.pf_dist stages ahead of the load cursor
+        int wp = blockIdx.x, ktp = 0, ktp1 = 0;
+        auto pf_set = [&]() {
+            ktp = (wp % p.splits) * p.kt_per_split;
+            ktp1 = min(p.KT, ktp + p.kt_per_split);
+        };
+        auto pf_step = [&]() {
+            if (wp >= num_work) return;
+            tma_prefetch_2d(&p.tmA, ktp * (F16 ? TC_BK16 : TC_BK), (wp / p.splits) * TC_BM);
+            if (++ktp >= ktp1) {
+                wp += gridDim.x;
+                if (wp < num_work) pf_set();
+            }
+        };
+        if (t == 0 && p.pf_dist > 0) {
+            if (wp < num_work) pf_set();
+            for (int i = 0; i < p.pf_dist; ++i) pf_step();
+        }
         auto load_stage = [&](int ww, int kk, float4 (&v)[8]) {
             const int m0 = (ww / p.splits) * TC_BM, kcol = kk * TC_BK + c * 4;
 #pragma unroll
@@ -340,52 +448,126 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 vn[8];
-        if (w < num_work) {
-            set_work(w);
-            load_stage(w, kt, vn);
-        }
-        while (w < num_work) {
-            float4 v[8];
+        if constexpr (F16) {
+            // unit of work = HALF a stage (64 rows x 64 k = 8 float4 per thread), so that the register footprint of
+            // the "loads of the next unit in flight while this one is split" scheme stays at two 8 x float4 sets
+            auto load_unit = [&](int ww, int kk, int hf, float4 (&v)[8]) {
+                const int m0 = (ww / p.splits) * TC_BM, kcol = kk * TC_BK16 + c * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = vn[i];
-            const int kt_cur = kt;
-            // advance to the next stage of this CTA and start its loads
-            if (++kt >= kt1) {
-                w += gridDim.x;
-                if (w < num_work) set_work(w);
+                for (int i = 0; i < 4; ++i) {
+                    const int row = m0 + (hf * 4 + i) * 16 + rsub;
+                    const float *src = p.A + (size_t)row * p.lda + kcol;
+                    v[2 * i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[2 * i + 1] = (row < p.M && kcol + 4 < p.K) ? __ldg(reinterpret_cast<const float4 *>(src + 4))
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            float4 vn[8];
+            int hf = 0;
+            if (w < num_work) {
+                set_work(w);
+                load_unit(w, kt, 0, vn);
             }
-            if (w < num_work) load_stage(w, kt, vn);
-            const int s = it % TCF_STAGES;
-            const uint32_t ph = (it / TCF_STAGES) & 1;
-            uint8_t *st = smem + s * TCF_STAGE_BYTES;
-            const uint32_t st_u32 = smem_u32(st);
-            TC_PROF_NOW(t0);
-            mbar_wait(&empty[s], ph ^ 1);
-            TC_PROF_NOW(t1);
-            if (t == 0) {
-                mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
-                const float *src = p.Bimg + (size_t)kt_cur * (2 * TC_B_TILE_FLOATS);
-                bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
-                bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
-                              TC_B_TILE_FLOATS * 4, &full[s]);
-            }
+            while (w < num_work) {
+                float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 16 + rsub;
-                float4 hi, lo;
-                split_tf32(v[i], hi, lo);
-                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-                sts128(st_u32 + off, hi);
-                sts128(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+                for (int i = 0; i < 8; ++i) v[i] = vn[i];
+                const int kt_cur = kt, hf_cur = hf;
+                if (hf == 0) {
+                    hf = 1;
+                } else {
+                    hf = 0;
+                    if (++kt >= kt1) {
+                        w += gridDim.x;
+                        if (w < num_work) set_work(w);
+                    }
+                }
+                if (w < num_work) load_unit(w, kt, hf, vn);
+                const int s = it % TCF_STAGES;
+                const uint32_t ph = (it / TCF_STAGES) & 1;
+                uint8_t *st = smem + s * TCF_STAGE_BYTES;
+                const uint32_t st_u32 = smem_u32(st);
+                TC_PROF_NOW(t0);
+                if (hf_cur == 0) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (t == 0) {
+                        if (p.pf_dist > 0) pf_step();
+                        mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
+                        const float *src = p.Bimg + (size_t)kt_cur * (2 * TC_B_TILE_FLOATS);
+                        bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
+                        bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
+                                      TC_B_TILE_FLOATS * 4, &full[s]);
+                    }
+                }
+                TC_PROF_NOW(t1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = (hf_cur * 4 + i) * 16 + rsub;
+                    uint4 hi, lo;
+                    split_f16x8(v[2 * i], v[2 * i + 1], hi, lo);
+                    const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                    sts128u(st_u32 + off, hi);
+                    sts128u(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+                }
+                if (hf_cur == 1) {
+                    fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                    ++it;
+                }
+                TC_PROF_NOW(t2);
+                TC_PROF_ADD(p_wait, t0, t1);
+                TC_PROF_ADD(p_work, t1, t2);
             }
-            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            TC_PROF_NOW(t2);
-            TC_PROF_ADD(p_wait, t0, t1);
-            TC_PROF_ADD(p_work, t1, t2);
-            ++it;
+        } else {
+            float4 vn[8];
+            if (w < num_work) {
+                set_work(w);
+                load_stage(w, kt, vn);
+            }
+            while (w < num_work) {
+                float4 v[8];
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = vn[i];
+                const int kt_cur = kt;
+                // advance to the next stage of this CTA and start its loads
+                if (++kt >= kt1) {
+                    w += gridDim.x;
+                    if (w < num_work) set_work(w);
+                }
+                if (w < num_work) load_stage(w, kt, vn);
+                const int s = it % TCF_STAGES;
+                const uint32_t ph = (it / TCF_STAGES) & 1;
+                uint8_t *st = smem + s * TCF_STAGE_BYTES;
+                const uint32_t st_u32 = smem_u32(st);
+                TC_PROF_NOW(t0);
+                mbar_wait(&empty[s], ph ^ 1);
+                TC_PROF_NOW(t1);
+                if (t == 0) {
+                    if (p.pf_dist > 0) pf_step();
+                    mbar_arrive_expect_tx(&full[s], 2 * TC_B_TILE_FLOATS * 4);
+                    const float *src = p.Bimg + (size_t)kt_cur * (2 * TC_B_TILE_FLOATS);
+                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
+                    bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
+                                  TC_B_TILE_FLOATS * 4, &full[s]);
+                }
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 16 + rsub;
+                    float4 hi, lo;
+                    split_tf32(v[i], hi, lo);
+                    const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                    sts128(st_u32 + off, hi);
+                    sts128(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+                }
+                fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                TC_PROF_NOW(t2);
+                TC_PROF_ADD(p_wait, t0, t1);
+                TC_PROF_ADD(p_work, t1, t2);
+                ++it;
+            }
         }
         TC_PROF_OUT(t == 0, 0, p_wait);
         TC_PROF_OUT(t == 0, 1, p_work);
@@ -394,7 +576,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
         // ===== MMA issuer: one thread of warp 12 =====
         setmaxnreg_dec<32>();
         if (warp == 12 && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_N, 0, 0);
+            constexpr uint32_t idesc = F16 ? make_idesc_f16(TC_BM, TC_N, 0, 0) : make_idesc_tf32(TC_BM, TC_N, 0, 0);
+            auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+                if constexpr (F16) tc_mma_f16(d, a, b, idesc, acc);
+                else tc_mma_tf32(d, a, b, idesc, acc);
+            };
             uint32_t it = 0, cit = 0;     // shared-memory stage counter, accumulator-chain counter
             TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
             TC_PROF_NOW(m_begin);
@@ -424,14 +610,14 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     // full magnitude.  Measured rms error vs float64: 1e-7-class instead of 2.5e-7 with interleaving.
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
-                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, (k != 0 || !chain_first) ? 1u : 0u);   // fresh accumulator per chain
-                        tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 / 16 fp16 = 32 bytes along the swizzled row
+                        mma(d, a_lo + adv, b_hi + adv, (k != 0 || !chain_first) ? 1u : 0u);   // fresh accumulator per chain
+                        mma(d, a_hi + adv, b_lo + adv, 1);
                     }
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
+                        mma(d, a_hi + adv, b_hi + adv, 1);
                     }
                     tc_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
                     if (chain_last) {
@@ -489,6 +675,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 TC_PROF_ADD(e_drain, t1, t2);
             }
             TC_PROF_NOW(t0);
+            if constexpr (F16) {
+                const float sc = p.out_scale;   // undo the power-of-two scale of the weight image (exact)
+#pragma unroll
+                for (int i = 0; i < 128; ++i) acc[i] *= sc;
+            }
             // ---- tile epilogue from registers: thread = row (q*32 + lane), 128 columns [half*128, +128) ----
             const int row0 = (w / p.splits) * TC_BM + q * 32;
             const int rl = q * 32 + lane;

@@ -18,11 +18,11 @@ for K in (32, 64, 128, 256, 352, 1024, 2720):
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     out = {}
-    for be in (1, 2):
+    for be in (1, 2, 3):
         dC = torch.zeros((M, N), dtype=torch.float32, device="cuda")
         _lib.check(lib.dcc_op_gemm(pol._h, be, 0, 1, M, N, K, dA.data_ptr(), K, dB.data_ptr(), K, dC.data_ptr(), N, 0, None), "gemm")
         torch.cuda.synchronize()
         e = dC.cpu().numpy().astype(np.float64) - ref
         out[be] = (np.abs(e).max(), np.sqrt((e ** 2).mean()), (e * np.sign(ref)).mean())
-    print("K=%5d  simt: max %.2e rms %.2e bias %+.2e | tc: max %.2e rms %.2e bias %+.2e   (|C| rms %.2f)" %
-          ((K,) + out[1] + out[2] + (np.sqrt((ref ** 2).mean()),)))
+    print("K=%5d  simt: max %.2e rms %.2e bias %+.2e | 3xtf32: max %.2e rms %.2e bias %+.2e | fp16 split: max %.2e rms %.2e bias %+.2e   (|C| rms %.2f)" %
+          ((K,) + out[1] + out[2] + out[3] + (np.sqrt((ref ** 2).mean()),)))

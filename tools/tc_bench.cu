@@ -52,7 +52,8 @@ static int bench_wgrad(int R, int Nout) {
 int main(int argc, char **argv) {
     if (argc > 3 && !strcmp(argv[1], "wgrad")) return bench_wgrad(atoi(argv[2]), atoi(argv[3]));
     const int M = argc > 1 ? atoi(argv[1]) : 198408, K = argc > 2 ? atoi(argv[2]) : 352, epi = argc > 3 ? atoi(argv[3]) : 1;
-    const int KT = (K + 31) / 32;
+    const bool f16 = argc > 6 && atoi(argv[6]);     // fp16 hi/lo split kernel (64 reduction elements per stage)
+    const int KT = f16 ? (K + 63) / 64 : (K + 31) / 32;
     float *A, *W, *img, *C, *H, *bias, *mean, *rstd;
     CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&W, (size_t)256 * K * 4));
     CK(cudaMalloc(&img, (size_t)KT * 2 * TC_B_TILE_FLOATS * 4));
@@ -63,26 +64,32 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(A, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(W, h.data(), (size_t)256 * K * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(bias, 0, 3 * 256 * 4));
-    tc_prep_weights_kernel<<<(KT * 256 * 8 + 255) / 256, 256>>>(W, K, 0, K, KT, img);
-    CK(cudaFuncSetAttribute(tc_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    if (f16) tc_prep_weights_f16_kernel<<<(KT * 256 * 8 + 255) / 256, 256>>>(W, K, 0, K, KT, 256.f, img);
+    else tc_prep_weights_kernel<<<(KT * 256 * 8 + 255) / 256, 256>>>(W, K, 0, K, KT, img);
+    auto kern = f16 ? tc_gemm_fwd_kernel<true> : tc_gemm_fwd_kernel<false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     TcfParams p; memset(&p, 0, sizeof p);
     p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = KT; p.lda = K; p.ldc = 256; p.splits = 1; p.kt_per_split = KT;
+    p.out_scale = f16 ? 1.f / 256.f : 1.f;
     p.epi = epi; p.dbg = argc > 4 ? atoi(argv[4]) : 0; p.bias = bias; p.gamma = bias + 256; p.beta = bias + 512; p.H = H; p.mean = mean; p.rstd = rstd;
     if (argc > 5 && atoi(argv[5])) {   // TMA-store epilogue
         p.use_tma = (tc_make_store_map(&p.tmC, C, M, 256) && tc_make_store_map(&p.tmH, H, M, 256)) ? 1 : 0;
         printf("use_tma=%d  ", p.use_tma);
     }
+    p.pf_dist = argc > 7 ? atoi(argv[7]) : 0;     // L2 prefetch distance of the activation operand, in stages
+    if (p.pf_dist > 0 && !tc_make_prefetch_map(&p.tmA, A, M, K, K, f16 ? 64 : 32)) { printf("prefetch map failed\n"); p.pf_dist = 0; }
+    printf("pf=%d  ", p.pf_dist);
     const int tiles = (M + 127) / 128, grid = tiles < 148 ? tiles : 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) tc_gemm_fwd_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < 3; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 10;
-    for (int i = 0; i < reps; ++i) tc_gemm_fwd_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < reps; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-    const double flop = 2.0 * M * 256.0 * (KT * 32.0);
-    printf("fwd M=%d K=%d epi=%d: %.1f us  %.1f TFLOP/s fp32-equivalent (x3 = %.0f TF tf32 MMA)\n", M, K, epi, ms * 1e3,
+    const double flop = 2.0 * M * 256.0 * (KT * (f16 ? 64.0 : 32.0));
+    printf("fwd%s M=%d K=%d epi=%d: %.1f us  %.1f TFLOP/s fp32-equivalent (x3 = %.0f TF MMA)\n", f16 ? " [fp16 split]" : "", M, K, epi, ms * 1e3,
            flop / ms * 1e-9, 3 * flop / ms * 1e-9);
 #ifndef DCC_TC_PROFILE
     return 0;   // timing-only build (no -DDCC_TC_PROFILE): the role timers cost a few percent
