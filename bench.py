@@ -432,7 +432,7 @@ def run_cuda_mappo(args):
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 peak_tf = float(json.load(f).get("bf16_tflops_sustained", peak_tf))
-            peak_src = "measured sustained dense bf16 (MEASURED_PEAKS.json); the kernels run 3xTF32 (TF32 peak = bf16/2, three MMAs per product => a perfect kernel reads 1/6)"
+            peak_src = "measured sustained dense bf16 (MEASURED_PEAKS.json); three split MMAs per product: the 3xTF32 kernels (weight gradients, dX) top out at 1/6, the fp16 hi/lo split forward kernels at 1/3"
         except Exception:
             peak_src = "fallback"
         flop_epoch_row = mappo_flops_per_env_step_row(N_AGENTS, N_POIS)

@@ -235,6 +235,8 @@ class MAPPOPolicy:
         return int(self.lib.dcc_mappo_launch_count(self._h))
 
     def gemm_backend(self):
+        # backend 2: 3xTF32 everywhere except the forward GEMMs on LayerNorm outputs, which run the fp16 hi/lo split
+        # kernel (same accuracy; DCC_TC_F16=0 keeps them on 3xTF32)
         return {1: "simt-fp32", 2: "tcgen05-3xtf32"}[int(self.lib.dcc_mappo_gemm_backend(self._h))]
 
     # ---- reference surface ---------------------------------------------------------------------------------

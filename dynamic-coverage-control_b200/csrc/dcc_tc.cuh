@@ -3,7 +3,9 @@
 // Precision: 3xTF32 split.  Every fp32 operand x is split into hi = tf32(x) and lo = tf32(x - hi); the product is
 // accumulated in fp32 TMEM as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the lo*lo term, ~2^-22 relative, is dropped).  This
 // keeps logits / values within fp32 round-off of the reference's fp32 GEMMs (plain TF32 or bf16
-// miss the 1e-5 parity bar by 1-3 orders of magnitude) at one third of the TF32 tensor rate.
+// miss the 1e-5 parity bar by 1-3 orders of magnitude) at one third of the TF32 tensor rate.  Where the activation
+// operand is a LayerNorm output (bounded), the forward kernel uses an fp16 hi/lo split instead (11 + 11 significand
+// bits, same accuracy class): half the operand bytes and twice the MMA rate (tc_gemm_fwd_kernel<true>).
 //
 // Operand staging: tcgen05.mma reads both operands from shared memory in the canonical 128-byte-swizzled layouts
 // (8 rows x 128 B atoms, 16-byte chunks XOR-ed with the row index inside the atom):

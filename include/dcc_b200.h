@@ -197,7 +197,7 @@ typedef struct dcc_mappo_cfg {
     int32_t hidden;          /* algo_hidden_size, <= 256 (mappo.yaml: 256) */
     int32_t act_dim;         /* 2 (Box(2), environment.py:52) */
     int32_t chunk_rows;      /* env-step rows per activation chunk; 0 = auto (~2.5 GB of scratch, whole 148-SM waves for both nets) */
-    int32_t gemm_backend;    /* 0 = auto, 1 = SIMT fp32 FFMA, 2 = tcgen05 3xTF32 (hidden == 256 only) */
+    int32_t gemm_backend;    /* 0 = auto, 1 = SIMT fp32 FFMA, 2 = tcgen05 split precision: 3xTF32, fp16 hi/lo on LayerNorm outputs (hidden == 256 only) */
     float clip_param;        /* 0.2     mappo.yaml */
     float entropy_coef;      /* 0.01 */
     float value_loss_coef;   /* 1.0 */
@@ -336,7 +336,8 @@ int dcc_mappo_apply(void *handle, int which, float *d_params, float *d_grads, fl
                     float lr, int64_t step, double *d_grad_norm_sq_out, dcc_stream_t stream);
 
 /* Kernel-level test hook: C[M,N] (+)= op(A)[M,K] op(B)[K,N], row-major with leading dimensions; ta/tb = operand
- * stored transposed.  backend as dcc_mappo_cfg.gemm_backend (2 requires the shapes the tcgen05 kernels cover). */
+ * stored transposed.  backend as dcc_mappo_cfg.gemm_backend (2 requires the shapes the tcgen05 kernels cover); 3 = the
+ * fp16 hi/lo split forward kernel on its own (ta == 0, N == 256, |A| < 65504, |B| < 255). */
 int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *d_A, int lda,
                 const float *d_B, int ldb, float *d_C, int ldc, int accumulate, dcc_stream_t stream);
 
