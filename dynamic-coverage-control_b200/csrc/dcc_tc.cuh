@@ -314,9 +314,8 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType,
                                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                              CUtensorMapFloatOOBfill);
-// [rows, 256] fp32 matrix with leading dimension ld (floats) -> store map with a 32 x 32 box.  Returns false when the
-// driver entry point is unavailable or the encode fails (callers then keep the st.global epilogue).
-inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no -lcuda); nullptr when unavailable
+inline PFN_tensorMapEncodeTiled tc_tensor_map_encoder() {
     static PFN_tensorMapEncodeTiled enc = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -327,28 +326,28 @@ inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int 
             q == cudaDriverEntryPointSuccess)
             enc = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
     }
-    if (!enc || rows < 1 || (ld & 3) || ((uintptr_t)base & 15)) return false;
-    const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+    return enc;
+}
+// 2-D fp32 map: `cols` x `rows` elements, row pitch ld floats, box box_cols x box_rows.  Returns false when the encoder
+// is unavailable or rejects the shape (callers then keep the st.global epilogue / skip the prefetch).
+inline bool tc_make_map_2d(CUtensorMap *tm, const float *base, int cols, int rows, int ld, int box_cols, int box_rows,
+                           CUtensorMapSwizzle swizzle) {
+    PFN_tensorMapEncodeTiled enc = tc_tensor_map_encoder();
+    if (!enc || rows < 1 || cols < 1 || (ld & 3) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// [rows, K] fp32 activation matrix (leading dimension ld) -> prefetch map with a box of 128 rows x `box_cols` columns
+// [rows, 256] output matrix -> store map with a 128B-swizzled 32 x 32 box
+inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
+    return tc_make_map_2d(tm, base, 256, rows, ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+// [rows, K] activation matrix -> L2-prefetch map with a box of 128 rows x `box_cols` columns (one K-stage of a row tile)
 inline bool tc_make_prefetch_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_cols) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-        return false;
-    PFN_tensorMapEncodeTiled enc = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
-    if (rows < 1 || (ld & 3) || ((uintptr_t)base & 15)) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 128}, estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tc_make_map_2d(tm, base, K, rows, ld, box_cols, 128, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int x, int y) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(x), "r"(y) : "memory");
