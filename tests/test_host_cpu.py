@@ -206,3 +206,54 @@ def test_reference_order_initialisation(name):
             assert abs(flat.sum() - s) <= 1e-5 * max(1.0, np.abs(flat).sum()) and abs((flat ** 2).sum() - ss) <= 1e-5 * max(1.0, ss)
             n_checked += 1
     assert n_checked >= 26
+
+
+def test_fp16_split_emulation():
+    """Numerics behind the fp16 hi/lo split GEMMs (csrc/dcc_tc.cuh, tc_gemm_fwd_kernel<true>), emulated in NumPy with
+    float64 products of the rounded halves: x = hi + lo with hi = fp16(x), lo = fp16(x - hi), product = hi*hi + hi*lo +
+    lo*hi.  With the weight image pre-scaled by 2^8 (TC_F16_WSCALE) the split is as accurate as the 3xTF32 split; an
+    unscaled image is not (the lo halves of |w| ~ 0.05 are fp16-subnormal).  Second half: the next-round plan for the
+    weight gradients — ONE power-of-two scale per dZ tensor keeps 3xTF32 accuracy over 3.5 decades of row scales."""
+    rng = np.random.default_rng(0)
+    f = lambda a: a.astype(np.float64)   # noqa: E731
+
+    def split16(a):
+        h = a.astype(np.float16)
+        return h, (a - h.astype(np.float32)).astype(np.float16)
+
+    def split_tf32(a):
+        rna = lambda v: ((v.view(np.uint32) + 0x1000) & 0xFFFFE000).view(np.float32)   # noqa: E731
+        h = rna(a.copy())
+        return h, rna((a - h).astype(np.float32))
+
+    def prod(ah, al, bh, bl):
+        return f(ah) @ f(bh).T + f(ah) @ f(bl).T + f(al) @ f(bh).T
+
+    M, K, N = 256, 352, 256
+    x = rng.normal(0, 1, (M, K)).astype(np.float32)            # a LayerNorm output
+    x[:, :40] *= 1e-3
+    W = (rng.normal(0, 1, (N, K)) * np.sqrt(2.0 / K)).astype(np.float32)
+    ref = f(x) @ f(W).T
+    rms = lambda y, r: np.sqrt(np.mean((y - r) ** 2)) / np.sqrt(np.mean(r ** 2))   # noqa: E731
+    e_tf32 = rms(prod(*split_tf32(x), *split_tf32(W)), ref)
+    e_f16_scaled = rms(prod(*split16(x), *split16(W * np.float32(256.0))) / 256.0, ref)
+    e_f16_plain = rms(prod(*split16(x), *split16(W)), ref)
+    assert e_tf32 < 1e-7 and e_f16_scaled < 1e-7 and e_f16_scaled < 1.1 * e_tf32
+    assert e_f16_plain > 2 * e_f16_scaled
+    # weight-gradient shape: G = dZ^T X, rows of dZ spread over 3.5 decades, half of the entries masked by ReLU
+    R = 2048
+    X = rng.normal(0, 1, (R, K)).astype(np.float32)
+    dz = (rng.normal(0, 1, (R, N)) * 10 ** rng.uniform(-10, -6.5, (R, 1))).astype(np.float32)
+    dz[rng.random((R, N)) < 0.5] = 0
+    refg = f(dz).T @ f(X)
+    dzh, dzl = split_tf32(dz)
+    xh, xl = split_tf32(X)
+    e_tf32 = rms(f(dzh).T @ f(xh) + f(dzh).T @ f(xl) + f(dzl).T @ f(xh), refg)
+    S = np.float32(2.0 ** (14 - np.ceil(np.log2(np.abs(dz).max()))))
+    dh, dl = split16(dz * S)
+    xh, xl = split16(X)
+    assert np.isfinite(dh.astype(np.float32)).all()
+    e_f16 = rms((f(dh).T @ f(xh) + f(dh).T @ f(xl) + f(dl).T @ f(xh)) / float(S), refg)
+    dh0, dl0 = split16(dz)                                   # unscaled: the gradients vanish into fp16 subnormals
+    e_f16_plain = rms(f(dh0).T @ f(xh) + f(dh0).T @ f(xl) + f(dl0).T @ f(xh), refg)
+    assert e_tf32 < 1e-7 and e_f16 < 1.1 * e_tf32 and e_f16_plain > 1e-3
