@@ -49,6 +49,8 @@ struct MappoHandle {
     int device, sm_count;
     int backend;     // 1 = SIMT fp32, 2 = tcgen05 3xTF32
     bool f16_fwd;    // backend 2: forward GEMMs on LayerNorm outputs use the fp16 hi/lo split kernel (DCC_TC_F16=0 disables)
+    bool f16_wgrad;  // backend 2, experimental: fp16-split weight-gradient GEMMs (DCC_TC_WGRAD_F16=1 enables)
+    uint32_t *dz_absmax;   // device scalar: bits of max |dZ| for the fp16-split weight-gradient kernel
     NetLayout la, lc;
     int chunk_rows;  // env-step rows per chunk
     // scratch
@@ -203,34 +205,47 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     return DCC_OK;
 }
 
-// G[256, Nout] += dZ[R,256]^T X[R, Nout]  (tcgen05, MN-major operands; G must already hold the running sum)
+// G[256, Nout] += dZ[R,256]^T X[R, Nout]  (tcgen05, MN-major operands; G must already hold the running sum).
+// f16 = the experimental fp16-split variant (X must be a LayerNorm output; one absmax pass over dZ supplies its scale).
 static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int ldz, const float *X, int ldx, float *G,
-                         int ldg, cudaStream_t s) {
+                         int ldg, cudaStream_t s, bool f16 = false) {
     if (R <= 0 || Nout <= 0) return DCC_OK;
     if ((ldz & 3) || (ldx & 3) || ((uintptr_t)dZ & 15) || ((uintptr_t)X & 15)) return DCC_ERR_INVALID_ARG;
     static bool attr_set = false;
     if (!attr_set) {
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::TCF_SMEM_BYTES));
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::TCF_SMEM_BYTES));
         attr_set = true;
     }
+    if (f16 && !h->dz_absmax) f16 = false;
     tc::TcwParams p;
     memset(&p, 0, sizeof p);
     p.dZ = dZ; p.X = X; p.G = G; p.R = R; p.Nout = Nout; p.ldz = ldz; p.ldx = ldx; p.ldg = ldg;
     p.n_tiles = (Nout + tc::TC_N - 1) / tc::TC_N;
     p.tile_n = ((Nout + p.n_tiles - 1) / p.n_tiles + 31) / 32 * 32;      // balanced column tiles, whole 32-feature groups
     const int out_tiles = 2 * p.n_tiles;
+    const int bkw = f16 ? 64 : tc::TC_BK;                                // batch rows per stage
     // split the batch rows so that the work items fill two waves of the persistent grid without spilling into a
-    // third (floor, not ceil), each split at least 8 stages (256 rows) long
+    // third (floor, not ceil), each split at least 8 stages long
     int ks = (2 * h->sm_count) / out_tiles;
-    const int max_ks = (R + 255) / 256;
+    const int max_ks = (R + 8 * bkw - 1) / (8 * bkw);
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
-    p.rows_per_split = ((R + ks - 1) / ks + tc::TC_BK - 1) / tc::TC_BK * tc::TC_BK;
+    p.rows_per_split = ((R + ks - 1) / ks + bkw - 1) / bkw * bkw;
     p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
     const int work = out_tiles * p.ksplits;
     const int grid = work < h->sm_count ? work : h->sm_count;
-    tc::tc_gemm_wgrad_kernel<<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    if (f16) {
+        DCC_CUDA_TRY(cudaMemsetAsync(h->dz_absmax, 0, sizeof(uint32_t), s));
+        tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
+        h->launches++;
+        p.dz_absmax_bits = h->dz_absmax;
+        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    } else {
+        tc::tc_gemm_wgrad_kernel<false><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    }
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
     return DCC_OK;
@@ -240,6 +255,8 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
 // when the input LayerNorm is on: |xhat| <= sqrt(D); blocks >= 1 always read LN(a) * gamma + beta), i.e. values far
 // inside fp16's range.  Raw observations and the backward dX GEMMs (unbounded dynamic range) stay on 3xTF32.
 static inline bool fwd_f16(const MappoHandle *h, const NetLayout &L, int k) { return h->f16_fwd && (k > 0 || L.has_ln0); }
+// same condition on the X operand of the weight-gradient GEMM of block k (experimental, DCC_TC_WGRAD_F16=1)
+static inline bool wgrad_f16(const MappoHandle *h, const NetLayout &L, int k) { return h->f16_wgrad && (k > 0 || L.has_ln0); }
 
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
@@ -321,7 +338,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     int rc;
     float *dz = h->dA, *dx = h->dB;
     for (int k = last; k >= 1; --k) {
-        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s)     // dW_k += dz_k^T h_{k-1}
+        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s, wgrad_f16(h, L, k))   // dW_k += dz_k^T h_{k-1}
                              : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
         if (rc) return rc;
         rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s)                // dh_{k-1} = dz_k W_k
@@ -332,7 +349,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
         h->launches++;
         float *t = dz; dz = dx; dx = t;
     }
-    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, dz, H, h->x0, L.inp, G + L.W[0], L.in, s)         // G1 += dz_0^T xhat
+    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, dz, H, h->x0, L.inp, G + L.W[0], L.in, s, wgrad_f16(h, L, 0))   // G1 += dz_0^T xhat
                          : launch_gemm(h, true, false, H, L.in, rows, dz, H, h->x0, L.inp, G + L.W[0], L.in, true, s);
     if (rc) return rc;
     DCC_CUDA_TRY(cudaGetLastError());
@@ -403,6 +420,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->magic = MAPPO_MAGIC; h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
     h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
     h->f16_fwd = !(getenv("DCC_TC_F16") && atoi(getenv("DCC_TC_F16")) == 0);
+    h->f16_wgrad = getenv("DCC_TC_WGRAD_F16") && atoi(getenv("DCC_TC_WGRAD_F16")) == 1;
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
@@ -447,6 +465,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     alloc(&h->mu, RA * 2); alloc(&h->logp, RA); alloc(&h->dmu, RA * 2); alloc(&h->vnew, chunk); alloc(&h->dv, chunk);
     alloc(&h->vn_gae, 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
+    if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
     if (ce != cudaSuccess) {
         set_last_cuda_error(ce, "cudaMalloc(mappo scratch)", __FILE__, __LINE__);
         dcc_mappo_destroy(h);
@@ -468,6 +487,7 @@ int dcc_mappo_destroy(void *handle) {
         for (float *b : blk) cudaFree(b);
     }
     cudaFree(h->dsums);
+    cudaFree(h->dz_absmax);
     h->magic = 0;
     delete h;
     return DCC_OK;
@@ -774,10 +794,9 @@ int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, 
         // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features);
         // backend 3 = the fp16-split forward kernel (|A| < 65504, |B| < 255)
         const bool f16 = backend == 3;
-        if (f16 && ta) return DCC_ERR_UNSUPPORTED;
-        if (ta && !tb && M == tc::TC_N) {   // dW = dZ^T X
+        if (ta && !tb && M == tc::TC_N) {   // dW = dZ^T X (backend 3: the experimental fp16-split weight-gradient kernel)
             if (!accumulate) DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
-            return tc_gemm_wgrad(h, K, N, A, lda, B, ldb, C, ldc, s);
+            return tc_gemm_wgrad(h, K, N, A, lda, B, ldb, C, ldc, s, f16);
         }
         if (ta || N != tc::TC_N || accumulate) return DCC_ERR_UNSUPPORTED;
         const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;

@@ -875,10 +875,48 @@ struct TcwParams {
     int R, Nout, ldz, ldx, ldg;
     int n_tiles;         // column tiles; output tiles = 2 * n_tiles
     int tile_n;          // columns per tile: a multiple of 32, <= 256, chosen to balance the tiles (338 -> 192 + 146)
-    int ksplits, rows_per_split;   // rows_per_split % 32 == 0
+    int ksplits, rows_per_split;   // rows_per_split % 32 == 0 (% 64 for the fp16-split kernel)
+    // fp16-split kernel only: bits of max |dZ| over the tensor (tc_absmax_bits_kernel); dZ is multiplied by the power of
+    // two that brings this maximum into [2^13, 2^14) before the split and the partial tile is scaled back before it is added
+    const uint32_t *dz_absmax_bits;
 };
 
+// max |x| over a [rows, cols] fp32 matrix (cols % 4 == 0, 16-byte aligned rows) as float bits (atomicMax on the bits of
+// non-negative floats orders them correctly); *out must be zeroed first
+__global__ void tc_absmax_bits_kernel(const float *__restrict__ x, long rows, int cols, int ld, uint32_t *__restrict__ out) {
+    const int c4n = cols >> 2;
+    const long n = rows * c4n;
+    float m = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / c4n;
+        const int c4 = (int)(i - r * c4n);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ld) + c4);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+// power-of-two scale S with absmax * S in [2^13, 2^14) (1 when absmax is zero / denormal) and its inverse, from the bits
+__device__ __forceinline__ void f16_scale_from_absmax(uint32_t bits, float &S, float &invS) {
+    const uint32_t e = (bits >> 23) & 0xffu;
+    if (e == 0) { S = 1.f; invS = 1.f; return; }
+    uint32_t be = 267u - e;                 // biased exponent of 2^(13 - (e - 127))
+    if (be > 254u) be = 254u;
+    S = __uint_as_float(be << 23);
+    invS = __uint_as_float((254u - be) << 23);
+}
+
+//
+// F16 = true (EXPERIMENTAL, off by default: DCC_TC_WGRAD_F16=1): fp16 hi/lo split of both operands, 64 batch rows per
+// stage in the same stage bytes.  16-bit MN-major operands use the ordinary SWIZZLE_128B layout: per 64-feature group a
+// block of [64 k rows][128 B], 16-byte chunks XOR-ed with (k & 7), groups 8 KB apart (descriptor LBO = 8192, SBO = 1024,
+// 2048 B per K = 16 instruction: pinned on the GPU with tools/mn16_probe.cu).  dZ is pre-scaled by one power of two per
+// tensor (TcwParams::dz_absmax_bits); X must be a LayerNorm output.
+template <bool F16>
 __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
+    constexpr int BKW = F16 ? 64 : TC_BK;          // batch rows per stage
+    constexpr int UNITS = F16 ? 6 : 3;             // 16 KB raw load units per stage: dZ 1 (2), X 2 (4)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float *xpose = reinterpret_cast<float *>(smem + TCF_STAGES * TCF_STAGE_BYTES);
@@ -921,9 +959,17 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             const int ot = ww % out_tiles, ks = ww / out_tiles;
             mh = ot & 1; n0 = (ot >> 1) * p.tile_n;
             const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
-            ngroups = (nv + 31) >> 5;
+            ngroups = F16 ? (nv + 63) >> 6 : (nv + 31) >> 5;
             r0 = ks * p.rows_per_split; r_end = min(p.R, r0 + p.rows_per_split);
         };
+        // ring offset of a thread's i-th 16-byte piece; in the fp16 form pieces 2j, 2j+1 are the two halves of one
+        // 8-feature group (32 contiguous bytes in global memory) that becomes ONE 16-byte fp16 chunk
+        auto ring_off = [](int i) { return F16 ? (uint32_t)((i & 1) * 8192 + (i >> 1) * 2048) : (uint32_t)(i * 2048); };
+        float dz_scale = 1.f;
+        if constexpr (F16) {
+            float inv;
+            f16_scale_from_absmax(__ldg(p.dz_absmax_bits), dz_scale, inv);
+        }
         auto next_nonempty = [&]() {
             while (w < num_work) {
                 set_work(w);
@@ -936,7 +982,25 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         auto fetch_unit = [&](int slot) {      // issues the cp.asyncs of the unit at the fetch cursor, then advances it
             if (w < num_work) {
                 const uint32_t dst = ring_u32 + slot * 16384 + t * 16;
-                if (f_kind == 0) {
+                if constexpr (F16) {
+                    if (f_kind < 2) {          // dZ rows [32 * f_kind, +32) of the stage: 16 chunks of 8 features per row
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int pi = t + 128 * (i >> 1), k = f_kind * 32 + (pi >> 4), c = pi & 15;
+                            const bool ok = r0 + k < r_end;
+                            cp_async16(dst + ring_off(i), p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + c * 8 + (i & 1) * 4,
+                                       ok ? 16u : 0u);
+                        }
+                    } else {                   // X rows [16 * (f_kind - 2), +16): 32 chunks of 8 features per row
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int pi = t + 128 * (i >> 1), k = (f_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                            const int col = n0 + c * 8 + (i & 1) * 4;
+                            const bool ok = (c >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
+                            cp_async16(dst + ring_off(i), p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
+                        }
+                    }
+                } else if (f_kind == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
@@ -952,9 +1016,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                         cp_async16(dst + i * 2048, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
                     }
                 }
-                if (++f_kind == 3) {
+                if (++f_kind == UNITS) {
                     f_kind = 0;
-                    r0 += TC_BK;
+                    r0 += BKW;
                     if (r0 >= r_end) {
                         w += gridDim.x;
                         next_nonempty();
@@ -970,7 +1034,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             const int ot = ww % out_tiles, ks = ww / out_tiles;
             const int nn0 = (ot >> 1) * p.tile_n;
             const int nv = min(p.tile_n, (p.Nout - nn0 + 15) & ~15);
-            c_ngroups = (nv + 31) >> 5;
+            c_ngroups = F16 ? (nv + 63) >> 6 : (nv + 31) >> 5;
             c_r0 = ks * p.rows_per_split; c_rend = min(p.R, c_r0 + p.rows_per_split);
         };
         fetch_unit(0);
@@ -986,7 +1050,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             TC_PROF_ADD(p_cp_acc, pc0, pc1);
             float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + i * 2048);
+            for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + ring_off(i));
             fetch_unit(slot);                    // refill this slot with unit u+2
             const int cur_kind = c_kind, cur_ngroups = c_ngroups;
             const int s = it & 1;
@@ -998,6 +1062,42 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 mbar_wait(&empty[s], ph ^ 1);
                 TC_PROF_NOW(pw1);
                 TC_PROF_ADD(p_wait_acc, pw0, pw1);
+            }
+            if constexpr (F16) {
+                if (cur_kind < 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pi = t + 128 * j, k = cur_kind * 32 + (pi >> 4), c = pi & 15;
+                        float4 a = v[2 * j], b = v[2 * j + 1];
+                        a.x *= dz_scale; a.y *= dz_scale; a.z *= dz_scale; a.w *= dz_scale;
+                        b.x *= dz_scale; b.y *= dz_scale; b.z *= dz_scale; b.w *= dz_scale;
+                        uint4 hi, lo;
+                        split_f16x8(a, b, hi, lo);
+                        const uint32_t off = (uint32_t)((c >> 3) * 8192 + k * 128 + (((c & 7) ^ (k & 7)) << 4));
+                        sts128u(st_u32 + off, hi);
+                        sts128u(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+                    }
+                } else {
+                    const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pi = t + 128 * j, k = (cur_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                        if ((c >> 3) < cur_ngroups) {
+                            uint4 hi, lo;
+                            split_f16x8(v[2 * j], v[2 * j + 1], hi, lo);
+                            const uint32_t off = (uint32_t)((c >> 3) * 8192 + k * 128 + (((c & 7) ^ (k & 7)) << 4));
+                            sts128u(sb_u32 + off, hi);
+                            sts128u(sb_u32 + TC_B_TILE_FLOATS * 4 + off, lo);
+                        }
+                    }
+                    if (cur_kind == UNITS - 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
+                        ++it;
+                    }
+                }
+            } else if (cur_kind == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
@@ -1029,9 +1129,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             }
             // advance the consume cursor
             ++u;
-            if (++c_kind == 3) {
+            if (++c_kind == UNITS) {
                 c_kind = 0;
-                c_r0 += TC_BK;
+                c_r0 += BKW;
                 if (c_r0 >= c_rend) {
                     cw += gridDim.x;
                     while (cw < num_work) {
@@ -1057,9 +1157,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 const int ot = w % out_tiles, ks = w / out_tiles;
                 const int n0 = (ot >> 1) * p.tile_n;
                 const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
-                const uint32_t idesc = make_idesc_tf32(TC_BM, nv, 1, 1);
+                const uint32_t idesc = F16 ? make_idesc_f16(TC_BM, nv, 1, 1) : make_idesc_tf32(TC_BM, nv, 1, 1);
                 const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
-                for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
+                for (int r0 = r_beg; r0 < r_end; r0 += BKW, ++it) {
                     const int s = it & 1;
                     const uint32_t ph = (it >> 1) & 1;
                     TC_PROF_NOW(t0);
@@ -1070,21 +1170,31 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     tc_fence_after();
                     const uint32_t d = tmem_base + s * TC_N;
                     const uint32_t sa = smem_u32(smem + s * TCF_STAGE_BYTES);
-                    // MN-major: LBO = distance between 32-feature groups (4096 B), SBO = between 4-row atoms (512 B)
-                    const uint64_t a_hi = make_desc_sw128(sa, 4096, 512, 1);
-                    const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, 4096, 512, 1);
-                    const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, 4096, 512, 1);
-                    const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, 4096, 512, 1);
+                    // MN-major.  32-bit: LBO = distance between 32-feature groups (4096 B), SBO = between 4-row atoms
+                    // (512 B), layout SWIZZLE_128B_BASE32B; 16-bit: 64-feature groups 8192 B apart, 8-row atoms (1024 B),
+                    // plain SWIZZLE_128B
+                    constexpr uint32_t LBO = F16 ? 8192 : 4096, SBO = F16 ? 1024 : 512;
+                    constexpr uint64_t LT = F16 ? 2 : 1;
+                    const uint64_t a_hi = make_desc_sw128(sa, LBO, SBO, LT);
+                    const uint64_t a_lo = make_desc_sw128(sa + TC_A_TILE_FLOATS * 4, LBO, SBO, LT);
+                    const uint64_t b_hi = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4, LBO, SBO, LT);
+                    const uint64_t b_lo = make_desc_sw128(sa + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, LBO, SBO, LT);
+                    // one instruction consumes 8 (tf32) / 16 (fp16) reduction rows = two atoms: 1024 / 2048 bytes
+                    constexpr int KSTEP = F16 ? 2048 : 1024;
+                    auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+                        if constexpr (F16) tc_mma_f16(d, a, b, idesc, acc);
+                        else tc_mma_tf32(d, a, b, idesc, acc);
+                    };
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {     // cross terms first (see tc_gemm_fwd_kernel)
-                        const uint64_t adv = (uint64_t)((k * 1024) >> 4);   // next 8 reduction rows (two 4-row atoms)
-                        tc_mma_tf32(d, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
-                        tc_mma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                    for (int k = 0; k < 4; ++k) {     // cross terms first (see tc_gemm_fwd_kernel)
+                        const uint64_t adv = (uint64_t)((k * KSTEP) >> 4);
+                        mma(a_lo + adv, b_hi + adv, k != 0 ? 1u : 0u);
+                        mma(a_hi + adv, b_lo + adv, 1);
                     }
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 1024) >> 4);
-                        tc_mma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * KSTEP) >> 4);
+                        mma(a_hi + adv, b_hi + adv, 1);
                     }
                     tc_commit(&empty[s]);
                     tc_commit(&tfull[s]);
@@ -1114,7 +1224,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             float acc[128];
 #pragma unroll
             for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-            for (int r0 = r_beg; r0 < r_end; r0 += TC_BK, ++it) {
+            for (int r0 = r_beg; r0 < r_end; r0 += BKW, ++it) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 mbar_wait(&tfull[s], ph);
@@ -1131,6 +1241,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[s]);
+            }
+            if constexpr (F16) {
+                float sc, inv;
+                f16_scale_from_absmax(__ldg(p.dz_absmax_bits), sc, inv);   // undo the power-of-two scale of dZ (exact)
+#pragma unroll
+                for (int i = 0; i < 128; ++i) acc[i] *= inv;
             }
             if (r_beg < r_end) {
                 // the CTA's partial tile goes to G with 16-byte vector atomics straight from the registers (thread =

@@ -307,8 +307,8 @@ def test_gemm_primitive_vs_float64(backend):
     ]
     ran = 0
     for ta, tb, M, Nn, K in shapes:
-        if backend == 3 and ta:
-            continue
+        if backend == 3 and ta and os.environ.get("DCC_TC_WGRAD_F16") != "1":
+            continue        # the fp16-split weight-gradient kernel is experimental (off by default)
         A = rng.normal(0, 1, (K, M) if ta else (M, K)).astype(np.float32)
         B = rng.normal(0, 1, (Nn, K) if tb else (K, Nn)).astype(np.float32)
         C0 = rng.normal(0, 1, (M, Nn)).astype(np.float32)

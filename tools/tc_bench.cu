@@ -10,47 +10,54 @@ namespace dcc { void set_last_cuda_error(cudaError_t, const char *, const char *
 using namespace dcc::tc;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
-// weight-gradient kernel: tc_bench.bin wgrad R Nout   (G[256, Nout] += dZ[R,256]^T X[R, Nout])
-static int bench_wgrad(int R, int Nout) {
+// weight-gradient kernel: tc_bench.bin wgrad R Nout [f16]   (G[256, Nout] += dZ[R,256]^T X[R, Nout])
+static int bench_wgrad(int R, int Nout, bool f16) {
     const int ldx = (Nout + 31) / 32 * 32;
     float *dZ, *X, *G;
     CK(cudaMalloc(&dZ, (size_t)R * 256 * 4)); CK(cudaMalloc(&X, (size_t)R * ldx * 4)); CK(cudaMalloc(&G, (size_t)256 * Nout * 4));
     CK(cudaMemset(dZ, 0x11, (size_t)R * 256 * 4)); CK(cudaMemset(X, 0x11, (size_t)R * ldx * 4)); CK(cudaMemset(G, 0, (size_t)256 * Nout * 4));
-    CK(cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    auto kern = f16 ? tc_gemm_wgrad_kernel<true> : tc_gemm_wgrad_kernel<false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
+    uint32_t *absmax;
+    CK(cudaMalloc(&absmax, 4)); CK(cudaMemset(absmax, 0, 4));
+    tc_absmax_bits_kernel<<<148 * 8, 256>>>(dZ, (long)R, 256, 256, absmax);
+    const int bkw = f16 ? 64 : TC_BK;
     TcwParams p; memset(&p, 0, sizeof p);
     p.dZ = dZ; p.X = X; p.G = G; p.R = R; p.Nout = Nout; p.ldz = 256; p.ldx = ldx; p.ldg = Nout;
     p.n_tiles = (Nout + TC_N - 1) / TC_N;
     p.tile_n = ((Nout + p.n_tiles - 1) / p.n_tiles + 31) / 32 * 32;
     const int out_tiles = 2 * p.n_tiles, sms = 148;
     int ks = (2 * sms) / out_tiles;
-    const int max_ks = (R + 255) / 256;
+    const int max_ks = (R + 8 * bkw - 1) / (8 * bkw);
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
-    p.rows_per_split = ((R + ks - 1) / ks + TC_BK - 1) / TC_BK * TC_BK;
+    p.rows_per_split = ((R + ks - 1) / ks + bkw - 1) / bkw * bkw;
+    p.dz_absmax_bits = absmax;
     p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
     const int work = out_tiles * p.ksplits, grid = work < sms ? work : sms;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) tc_gemm_wgrad_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < 3; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 10;
-    for (int i = 0; i < reps; ++i) tc_gemm_wgrad_kernel<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < reps; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-    printf("wgrad R=%d Nout=%d (tile_n %d, %d work items, %d rows/split): %.1f us  %.1f TFLOP/s fp32-equivalent\n", R, Nout, p.tile_n,
+    printf("wgrad%s R=%d Nout=%d (tile_n %d, %d work items, %d rows/split): %.1f us  %.1f TFLOP/s fp32-equivalent\n", f16 ? " [fp16 split]" : "", R, Nout, p.tile_n,
            work, p.rows_per_split, ms * 1e3, 2.0 * R * 256.0 * Nout / ms * 1e-9);
 #ifdef DCC_TC_PROFILE
     unsigned long long prof[32];
     CK(cudaMemcpyFromSymbol(prof, g_tc_prof, sizeof prof));
     const double st = (double)prof[16];
-    printf("CTA0: %llu stages | mma: wait_tempty %.0f wait_full %.0f issue %.0f, total %.0f cyc/stage | producer warp 0: wait_empty %.0f wait_cp.async %.0f (per unit, 3 units/stage), total %.0f cyc/stage\n",
-           prof[16], prof[17] / st, prof[18] / st, prof[19] / st, prof[20] / st, prof[21] / st, prof[22] / (3 * st), prof[23] / st);
+    const int units = f16 ? 6 : 3;
+    printf("CTA0: %llu stages | mma: wait_tempty %.0f wait_full %.0f issue %.0f, total %.0f cyc/stage | producer warp 0: wait_empty %.0f wait_cp.async %.0f (per unit, %d units/stage), total %.0f cyc/stage\n",
+           prof[16], prof[17] / st, prof[18] / st, prof[19] / st, prof[20] / st, prof[21] / st, prof[22] / (units * st), units, prof[23] / st);
 #endif
     return 0;
 }
 
 int main(int argc, char **argv) {
-    if (argc > 3 && !strcmp(argv[1], "wgrad")) return bench_wgrad(atoi(argv[2]), atoi(argv[3]));
+    if (argc > 3 && !strcmp(argv[1], "wgrad")) return bench_wgrad(atoi(argv[2]), atoi(argv[3]), argc > 4 && atoi(argv[4]));
     const int M = argc > 1 ? atoi(argv[1]) : 198408, K = argc > 2 ? atoi(argv[2]) : 352, epi = argc > 3 ? atoi(argv[3]) : 1;
     const bool f16 = argc > 6 && atoi(argv[6]);     // fp16 hi/lo split kernel (64 reduction elements per stage)
     const int KT = f16 ? (K + 63) / 64 : (K + 31) / 32;
