@@ -152,7 +152,7 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
                        const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
-                       bool f16 = false) {
+                       bool f16 = false, const uint32_t *a_absmax_bits = nullptr) {
     if (M <= 0) return DCC_OK;
     if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
     static bool attr_set = false;
@@ -161,6 +161,8 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
                                           tc::TCF_SMEM_BYTES));
         DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           tc::TCF_SMEM_BYTES));
+        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          tc::TCF_SMEM_BYTES));
         attr_set = true;
     }
     tc::TcfParams p;
@@ -168,6 +170,7 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;    // `img` must come from tc_prep_weights with the same f16 flag
     p.A = A; p.Bimg = img; p.C = C; p.M = M; p.K = K; p.KT = (K + bk - 1) / bk; p.lda = lda; p.ldc = ldc;
     p.out_scale = f16 ? 1.f / TC_F16_WSCALE : 1.f;
+    p.a_absmax_bits = f16 ? a_absmax_bits : nullptr;
     p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
     p.act = act_of(h);
@@ -198,7 +201,8 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     if (p.pf_dist > 0 && !tc::tc_make_prefetch_map(&p.tmA, A, M, K, lda, bk)) p.pf_dist = 0;
     const int work = row_tiles * p.splits;
     const int grid = work < h->sm_count ? work : h->sm_count;
-    if (f16) tc::tc_gemm_fwd_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    if (f16 && a_absmax_bits) tc::tc_gemm_fwd_kernel<true, true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    else if (f16) tc::tc_gemm_fwd_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     else tc::tc_gemm_fwd_kernel<false><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -270,7 +274,7 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
         if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s, fwd_f16(h, L, 0)))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
             if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
-            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s))) return rc;
+            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_wgrad))) return rc;
         }
     }
     return DCC_OK;
@@ -341,7 +345,9 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
         rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s, wgrad_f16(h, L, k))   // dW_k += dz_k^T h_{k-1}
                              : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
         if (rc) return rc;
-        rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s)                // dh_{k-1} = dz_k W_k
+        rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                           nullptr, h->f16_wgrad, h->f16_wgrad ? h->dz_absmax : nullptr)   // dh_{k-1} = dz_k W_k
+                                                                                                         // (max |dz_k| left by the dW_k call above)
                              : launch_gemm(h, false, false, rows, H, H, dz, H, P + L.W[k], H, dx, H, false, s);
         if (rc) return rc;
         relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx,

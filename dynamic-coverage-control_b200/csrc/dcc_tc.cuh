@@ -254,6 +254,33 @@ __global__ void tc_prep_weights_f16_kernel(const float *__restrict__ W, int ldw,
     *reinterpret_cast<uint4 *>(tile + TC_B_TILE_FLOATS) = lo;
 }
 
+// max |x| over a [rows, cols] fp32 matrix (cols % 4 == 0, 16-byte aligned rows) as float bits (atomicMax on the bits of
+// non-negative floats orders them correctly); *out must be zeroed first
+__global__ void tc_absmax_bits_kernel(const float *__restrict__ x, long rows, int cols, int ld, uint32_t *__restrict__ out) {
+    const int c4n = cols >> 2;
+    const long n = rows * c4n;
+    float m = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / c4n;
+        const int c4 = (int)(i - r * c4n);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ld) + c4);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+// power-of-two scale S with absmax * S in [2^13, 2^14) (1 when absmax is zero / denormal) and its inverse, from the bits
+__device__ __forceinline__ void f16_scale_from_absmax(uint32_t bits, float &S, float &invS) {
+    const uint32_t e = (bits >> 23) & 0xffu;
+    if (e == 0) { S = 1.f; invS = 1.f; return; }
+    uint32_t be = 267u - e;                 // biased exponent of 2^(13 - (e - 127))
+    if (be > 254u) be = 254u;
+    S = __uint_as_float(be << 23);
+    invS = __uint_as_float((254u - be) << 23);
+}
+
+
 // ---- forward-shaped GEMM: C[M, 256] = A[M, K] * B^T, A row-major (K contiguous), B from a weight image ----------
 //
 // Accuracy: the tensor core adds into its TMEM accumulator with round-toward-zero, so one long accumulator chain
@@ -302,6 +329,7 @@ struct TcfParams {
     int use_tma;
     int act;             // trunk activation of the fused epilogue: 0 = ReLU, 1 = tanh (mappo.yaml use_ReLU)
     float out_scale;     // fp16-split kernel: 1 / wscale of the weight image, applied to the drained tile
+    const uint32_t *a_absmax_bits;   // ASCALE variant: bits of max |A| (A is pre-scaled into fp16 range, see TcwParams)
     alignas(64) CUtensorMap tmC, tmH;
     // L2 prefetch of the activation operand: one cp.async.bulk.prefetch.tensor per K-stage, issued `pf_dist` stages ahead
     // of the producers' loads (box = 128 rows x one stage of columns), so that their LDGs hit L2 instead of waiting
@@ -378,7 +406,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //              MMAs (kind::f16, K = 16 each) — half the shared-memory traffic and half the tensor time per reduction
 //              element; p.KT = ceil(K / 64), p.Bimg from tc_prep_weights_f16_kernel.  |A| must stay below 65504
 //              (LayerNorm outputs here).
-template <bool F16>
+// ASCALE (with F16, EXPERIMENTAL, DCC_TC_WGRAD_F16=1): A has an unbounded dynamic range (the backward dX = dZ W): it is
+//              multiplied by the per-tensor power of two from p.a_absmax_bits before the split, undone in the epilogue.
+template <bool F16, bool ASCALE = false>
 __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __grid_constant__ TcfParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -465,6 +495,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             };
             float4 vn[8];
             int hf = 0;
+            float a_scale = 1.f;
+            if constexpr (ASCALE) {
+                float inv;
+                f16_scale_from_absmax(__ldg(p.a_absmax_bits), a_scale, inv);
+            }
             if (w < num_work) {
                 set_work(w);
                 load_unit(w, kt, 0, vn);
@@ -505,6 +540,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 for (int i = 0; i < 4; ++i) {
                     const int r = (hf_cur * 4 + i) * 16 + rsub;
                     uint4 hi, lo;
+                    if constexpr (ASCALE) {
+                        v[2 * i].x *= a_scale; v[2 * i].y *= a_scale; v[2 * i].z *= a_scale; v[2 * i].w *= a_scale;
+                        v[2 * i + 1].x *= a_scale; v[2 * i + 1].y *= a_scale; v[2 * i + 1].z *= a_scale; v[2 * i + 1].w *= a_scale;
+                    }
                     split_f16x8(v[2 * i], v[2 * i + 1], hi, lo);
                     const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
                     sts128u(st_u32 + off, hi);
@@ -677,7 +716,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             }
             TC_PROF_NOW(t0);
             if constexpr (F16) {
-                const float sc = p.out_scale;   // undo the power-of-two scale of the weight image (exact)
+                float sc = p.out_scale;         // undo the power-of-two scale of the weight image (exact)
+                if constexpr (ASCALE) {
+                    float up, inv;
+                    f16_scale_from_absmax(__ldg(p.a_absmax_bits), up, inv);
+                    sc *= inv;
+                }
 #pragma unroll
                 for (int i = 0; i < 128; ++i) acc[i] *= sc;
             }
@@ -880,32 +924,6 @@ struct TcwParams {
     // two that brings this maximum into [2^13, 2^14) before the split and the partial tile is scaled back before it is added
     const uint32_t *dz_absmax_bits;
 };
-
-// max |x| over a [rows, cols] fp32 matrix (cols % 4 == 0, 16-byte aligned rows) as float bits (atomicMax on the bits of
-// non-negative floats orders them correctly); *out must be zeroed first
-__global__ void tc_absmax_bits_kernel(const float *__restrict__ x, long rows, int cols, int ld, uint32_t *__restrict__ out) {
-    const int c4n = cols >> 2;
-    const long n = rows * c4n;
-    float m = 0.f;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / c4n;
-        const int c4 = (int)(i - r * c4n);
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ld) + c4);
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
-}
-// power-of-two scale S with absmax * S in [2^13, 2^14) (1 when absmax is zero / denormal) and its inverse, from the bits
-__device__ __forceinline__ void f16_scale_from_absmax(uint32_t bits, float &S, float &invS) {
-    const uint32_t e = (bits >> 23) & 0xffu;
-    if (e == 0) { S = 1.f; invS = 1.f; return; }
-    uint32_t be = 267u - e;                 // biased exponent of 2^(13 - (e - 127))
-    if (be > 254u) be = 254u;
-    S = __uint_as_float(be << 23);
-    invS = __uint_as_float((254u - be) << 23);
-}
 
 //
 // F16 = true (EXPERIMENTAL, off by default: DCC_TC_WGRAD_F16=1): fp16 hi/lo split of both operands, 64 batch rows per
