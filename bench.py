@@ -174,7 +174,7 @@ def run_cuda(args):
 
     E, N, M = ENVS_PER_GPU, N_AGENTS, N_POIS
     D = obs_dim(N, M)
-    env = CudaVecEnv(E, N, M, reference_compat=True, device=local_rank)  # shipped semantics, synthetic PoI layout
+    env = CudaVecEnv(E, N, M, reference_compat=True, device=local_rank, pos_pois="synthetic")  # shipped semantics, synthetic PoI layout (seed 0)
     if args.per_env_layouts:
         env.set_poi_layouts(np.random.default_rng(rank).uniform(-1.0, 1.0, (E, M, 2)))
     gen = torch.Generator(device=dev)

@@ -91,6 +91,18 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    # (re)build when the library is missing or older than its sources (content hash, build.py); a fresh clone works
+    # without a separate build step as long as nvcc is there.  DCC_NO_AUTOBUILD=1 skips the check.
+    if not os.environ.get("DCC_NO_AUTOBUILD"):
+        from . import build as _build
+        try:
+            if _build._stale():
+                _build.build()
+        except RuntimeError as e:
+            if not os.path.exists(LIB_PATH):
+                raise DccError("%s is missing and could not be built (%s). There is no CPU fallback." % (LIB_PATH, e))
+            import warnings
+            warnings.warn("libdcc_b200.so is stale and could not be rebuilt (%s); using the existing library" % e)
     if not os.path.exists(LIB_PATH):
         raise DccError("%s is missing: build it with `python -m dcc_b200.build` (nvcc, sm_100a). "
                        "There is no CPU fallback." % LIB_PATH)

@@ -442,20 +442,97 @@ class MAPPOTrainer:
 
     def save_model(self, save_path):
         """Reference: pickle of the policy object (mappo.py:237-240).  Here: a pickle of plain CPU tensors keyed by
-        the reference's state_dict names (+ Adam moments and the ValueNorm state, which the reference drops)."""
+        the reference's state_dict names (+ Adam moments, the ValueNorm state and the sampling-stream position, which
+        the reference drops), tagged with a format key."""
         sd = self.policy.state_dict()
         if self.value_normalizer is not None:
             sd["value_normalizer"] = self.value_normalizer.state_dict()
+        sd["format"] = CHECKPOINT_FORMAT
+        sd["rng"] = {"seed": int(self.policy.seed), "offset": int(self.policy._rng_offset)}
         cpu = _to_cpu(sd)
         with open(os.path.join(save_path, "agent.pkl"), "wb") as f:
             pickle.dump(cpu, f)
 
     def load_model(self, load_path):
-        with open(os.path.join(load_path, "agent.pkl"), "rb") as f:
-            sd = pickle.load(f)
+        """Reads `agent.pkl` in either format: this build's dict of tensors, or a checkpoint written by the REFERENCE
+        (`pickle.dump(self.policy, f)`, mappo.py:237-240 — the whole MAPPOPolicy object with its R_Actor / R_Critic
+        modules and Adam optimisers).  The file is read with a restricted unpickler (torch / numpy / collections
+        only; the reference's own classes become inert stand-ins), never with a bare pickle.load."""
+        path = os.path.join(load_path, "agent.pkl") if os.path.isdir(load_path) else load_path
+        sd = load_checkpoint(path)
         self.policy.load_state_dict(sd)
         if "value_normalizer" in sd and self.value_normalizer is not None:
             self.value_normalizer.load_state_dict(sd["value_normalizer"])
+        if "rng" in sd:
+            self.policy.seed, self.policy._rng_offset = int(sd["rng"]["seed"]), int(sd["rng"]["offset"])
+
+
+CHECKPOINT_FORMAT = "dcc_b200.agent.v2"
+
+
+class _InertObject:
+    """Stand-in for a class of the reference (algos.*, utils.*, gym.*) met while unpickling its agent.pkl: absorbs the
+    pickled state, runs none of the original code."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+        else:
+            self.__dict__["_state"] = state
+
+
+class _CheckpointUnpickler(pickle.Unpickler):
+    _ALLOWED_ROOTS = ("torch", "numpy", "collections", "builtins", "copyreg", "_codecs", "argparse")
+    _BUILTINS_OK = {"dict", "list", "tuple", "set", "frozenset", "int", "float", "bool", "str", "bytes", "bytearray",
+                    "complex", "slice", "range", "object", "getattr"}
+
+    def find_class(self, module, name):
+        root = module.split(".")[0]
+        if root == "builtins":
+            if name not in self._BUILTINS_OK:
+                raise pickle.UnpicklingError("refusing builtins.%s in a checkpoint" % name)
+            return super().find_class(module, name)
+        if root in self._ALLOWED_ROOTS:
+            return super().find_class(module, name)
+        return type(name, (_InertObject,), {"__module__": module})
+
+
+def _module_tensors(mod, prefix=""):
+    """state_dict of a (real or inert) nn.Module tree in torch's order: parameters, persistent buffers, submodules."""
+    out = OrderedDict()
+    d = mod.__dict__
+    for k, v in (d.get("_parameters") or {}).items():
+        if v is not None:
+            out[prefix + k] = v.detach()
+    skip = d.get("_non_persistent_buffers_set") or set()
+    for k, v in (d.get("_buffers") or {}).items():
+        if v is not None and k not in skip:
+            out[prefix + k] = v.detach()
+    for k, sub in (d.get("_modules") or {}).items():
+        if sub is not None:
+            out.update(_module_tensors(sub, prefix + k + "."))
+    return out
+
+
+def load_checkpoint(path):
+    """-> {"actor": state_dict, "critic": state_dict, [optimizers, value_normalizer, rng]} from an agent.pkl written by
+    this build OR by the reference (see MAPPOTrainer.load_model)."""
+    with open(path, "rb") as f:
+        obj = _CheckpointUnpickler(f).load()
+    if isinstance(obj, dict):
+        if "actor" not in obj or "critic" not in obj:
+            raise ValueError("%s: a dict without 'actor' / 'critic' entries is not an agent checkpoint" % path)
+        return obj
+    if hasattr(obj, "actor") and hasattr(obj, "critic"):          # the reference's pickled MAPPOPolicy object
+        sd = {"actor": _module_tensors(obj.actor), "critic": _module_tensors(obj.critic), "format": "reference.policy.pickle"}
+        if not sd["actor"] or not sd["critic"]:
+            raise ValueError("%s: no parameters found in the pickled policy object" % path)
+        return sd
+    raise ValueError("%s holds a %s, neither this build's checkpoint dict nor a reference MAPPOPolicy object"
+                     % (path, type(obj).__name__))
 
 
 def _to_cpu(x):

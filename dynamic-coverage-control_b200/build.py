@@ -20,12 +20,28 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """Content hash of everything the library is compiled from (sources, headers, flags).  Staleness is decided on
+    content, not mtimes: a snapshot copied to another box (gpurun) keeps its prebuilt .so whatever the copy did to the
+    timestamps, and an edited source always triggers a rebuild."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + sorted(os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def find_nvcc():
@@ -39,6 +55,15 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:      # one builder at a time (torchrun starts N ranks at once)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():               # another rank built it while we waited
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
@@ -48,6 +73,8 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     if verbose:
         print(res.stderr)
     return LIB_PATH

@@ -20,6 +20,34 @@ void set_last_cuda_error(cudaError_t e, const char *what, const char *file, int 
         }                                                                    \
     } while (0)
 
+// Makes `dev` the current device for the scope of an entry point and restores the caller's device on the way out
+// (a handle is bound to one GPU; the caller's current device may be another one).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != dev) {
+            err = cudaSetDevice(dev);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define DCC_DEVICE_GUARD(dev)                                                          \
+    ::dcc::DeviceGuard _dcc_dev_guard(dev);                                            \
+    do {                                                                               \
+        if (_dcc_dev_guard.err != cudaSuccess) {                                       \
+            ::dcc::set_last_cuda_error(_dcc_dev_guard.err, "cudaSetDevice(handle device)", __FILE__, __LINE__); \
+            return DCC_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "dcc_common.cuh"
@@ -877,8 +878,18 @@ static int configure_launch(EnvHandle *h) {
     k.pw_bytes = (int)align_up((size_t)k.N * 32 + align_up((size_t)k.M, 16) + stage_bytes * k.n_buf, 128);
     h->smem_bytes = k.poi_bytes + k.pw_bytes * wpc;
     if (h->smem_bytes > 227 * 1024) return DCC_ERR_UNSUPPORTED;
-    DCC_CUDA_TRY(cudaFuncSetAttribute(dcc_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    DCC_CUDA_TRY(cudaFuncSetAttribute(dcc_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    {   // the attribute is per device and shared by every handle on it: only ever RAISE it, so that a later handle with
+        // a smaller footprint cannot pull it under an earlier live handle that needs more than 48 KB
+        static std::mutex mu;
+        static int max_smem[64] = {0};
+        std::lock_guard<std::mutex> lk(mu);
+        int &mx = max_smem[h->device & 63];
+        if (h->smem_bytes > mx) {
+            DCC_CUDA_TRY(cudaFuncSetAttribute(dcc_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+            DCC_CUDA_TRY(cudaFuncSetAttribute(dcc_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+            mx = h->smem_bytes;
+        }
+    }
     int occ_step = 0, occ_reset = 0;
     DCC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_step, dcc_env_kernel<true>, wpc * 32, h->smem_bytes));
     DCC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_reset, dcc_env_kernel<false>, wpc * 32, h->smem_bytes));
@@ -938,7 +949,7 @@ int dcc_env_create(const dcc_env_cfg *cfg, const double *h_poi_xy, int device, v
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return DCC_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(device));
+    DCC_DEVICE_GUARD(device);
     cudaDeviceProp prop;
     DCC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return DCC_ERR_NO_DEVICE;  // sm_100a only: no fallback path exists
@@ -1028,7 +1039,7 @@ int dcc_env_create(const dcc_env_cfg *cfg, const double *h_poi_xy, int device, v
 int dcc_env_set_poi_layouts(void *handle, const double *h_poi_xy, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     EnvKParams &k = h->kp;
     if (!h_poi_xy) {                     // back to the shared layout given at creation
@@ -1049,7 +1060,7 @@ int dcc_env_set_poi_layouts(void *handle, const double *h_poi_xy, dcc_stream_t s
 int dcc_env_destroy(void *handle) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
-    cudaSetDevice(h->device);
+    DCC_DEVICE_GUARD(h->device);
     cudaFree(h->d_poi); cudaFree(h->d_poi_env); cudaFree(h->d_pos_vel); cudaFree(h->d_energy);
     cudaFree(h->hs_actions); cudaFree(h->hs_obs); cudaFree(h->hs_rew); cudaFree(h->hs_cov); cudaFree(h->hs_done);
     h->magic = 0;
@@ -1060,6 +1071,7 @@ int dcc_env_destroy(void *handle) {
 int dcc_env_set_launch(void *handle, int warps_per_cta, int ctas) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
     if (warps_per_cta != 1 && warps_per_cta != 2 && warps_per_cta != 4 && warps_per_cta != 8 && warps_per_cta != 16)
         return DCC_ERR_INVALID_ARG;
     const int old_w = h->warps_per_cta, old_c = h->ctas_override;
@@ -1085,6 +1097,7 @@ int64_t dcc_env_launch_count(void *handle) {
 int dcc_env_reset(void *handle, float *d_obs, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
     EnvKParams k = h->kp;
     k.actions = nullptr; k.obs = d_obs; k.rew = nullptr; k.done = nullptr; k.cov = nullptr; k.connect = nullptr;
     k.adj = nullptr; k.adjs = nullptr;
@@ -1104,6 +1117,7 @@ int dcc_env_step(void *handle, const float *d_actions, float *d_obs, float *d_re
     EnvHandle *h = as_env(handle);
     if (!h || !d_actions) return DCC_ERR_INVALID_ARG;
     if (reinterpret_cast<uintptr_t>(d_actions) & 7) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
     EnvKParams k = h->kp;
     k.actions = d_actions; k.obs = d_obs; k.rew = d_rew; k.done = d_done; k.cov = d_coverage; k.connect = d_connect;
     k.adj = d_adj; k.adjs = d_adj_s;
@@ -1133,7 +1147,7 @@ int dcc_env_step_host(void *handle, const float *h_actions, float *h_obs, float 
                       float *h_coverage, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h || !h_actions) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     int rc = ensure_host_staging(h);
     if (rc != DCC_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1153,7 +1167,7 @@ int dcc_env_step_host(void *handle, const float *h_actions, float *h_obs, float 
 int dcc_env_reset_host(void *handle, float *h_obs, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     int rc = ensure_host_staging(h);
     if (rc != DCC_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1168,6 +1182,7 @@ int dcc_env_reset_host(void *handle, float *h_obs, dcc_stream_t stream) {
 int dcc_env_get_state(void *handle, double *h_pos_vel, uint8_t *h_energy, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t E = h->cfg.n_envs, N = h->cfg.n_agents, M = h->cfg.n_pois;
     if (h_pos_vel) DCC_CUDA_TRY(cudaMemcpyAsync(h_pos_vel, h->d_pos_vel, sizeof(double) * 4 * N * E, cudaMemcpyDeviceToHost, s));
@@ -1179,6 +1194,7 @@ int dcc_env_get_state(void *handle, double *h_pos_vel, uint8_t *h_energy, dcc_st
 int dcc_env_set_state(void *handle, const double *h_pos_vel, const uint8_t *h_energy, dcc_stream_t stream) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t E = h->cfg.n_envs, N = h->cfg.n_agents, M = h->cfg.n_pois;
     if (h_pos_vel) DCC_CUDA_TRY(cudaMemcpyAsync(h->d_pos_vel, h_pos_vel, sizeof(double) * 4 * N * E, cudaMemcpyHostToDevice, s));

@@ -147,6 +147,16 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
     return DCC_OK;
 }
 
+// per-device opt-in of the tcgen05 kernels to their dynamic shared-memory footprint (current device)
+static int tc_set_kernel_attributes() {
+    DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
+    return DCC_OK;
+}
+
 // C[M,256] = A[M,K] * B^T with B given as a weight image (K-major on both sides).  With `bias` the epilogue is the
 // fused bias + ReLU + LayerNorm of an MLP block: a -> a_out (optional), LN(a) * gamma + beta -> h_out.
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
@@ -155,16 +165,6 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
                        bool f16 = false, const uint32_t *a_absmax_bits = nullptr) {
     if (M <= 0) return DCC_OK;
     if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::TCF_SMEM_BYTES));
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::TCF_SMEM_BYTES));
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::TCF_SMEM_BYTES));
-        attr_set = true;
-    }
     tc::TcfParams p;
     memset(&p, 0, sizeof p);
     const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;    // `img` must come from tc_prep_weights with the same f16 flag
@@ -215,14 +215,6 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
                          int ldg, cudaStream_t s, bool f16 = false) {
     if (R <= 0 || Nout <= 0) return DCC_OK;
     if ((ldz & 3) || (ldx & 3) || ((uintptr_t)dZ & 15) || ((uintptr_t)X & 15)) return DCC_ERR_INVALID_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::TCF_SMEM_BYTES));
-        DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          tc::TCF_SMEM_BYTES));
-        attr_set = true;
-    }
     if (f16 && !h->dz_absmax) f16 = false;
     tc::TcwParams p;
     memset(&p, 0, sizeof p);
@@ -416,10 +408,16 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return DCC_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(device));
+    DCC_DEVICE_GUARD(device);
     cudaDeviceProp prop;
     DCC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return DCC_ERR_NO_DEVICE;
+    if (cfg->gemm_backend == 2 || (cfg->gemm_backend == 0 && tc_supported(cfg))) {
+        // the opt-in above 48 KB of dynamic shared memory is a per-device function attribute: set it for THIS handle's
+        // device at creation (idempotent; no process-wide "done" flag, which would skip a second GPU)
+        int rc = tc_set_kernel_attributes();
+        if (rc) return rc;
+    }
     MappoHandle *h = new (std::nothrow) MappoHandle();
     if (!h) return DCC_ERR_ALLOC;
     memset(h, 0, sizeof *h);
@@ -484,7 +482,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
 int dcc_mappo_destroy(void *handle) {
     MappoHandle *h = as_mappo(handle);
     if (!h) return DCC_ERR_INVALID_ARG;
-    cudaSetDevice(h->device);
+    DCC_DEVICE_GUARD(h->device);
     float *bufs[] = {h->x0, h->dA, h->dB, h->w1g_a, h->b1g_a, h->w1g_c, h->b1g_c, h->mu, h->logp, h->dmu, h->vnew, h->dv,
                      h->vn_gae, h->img_w1[0], h->img_w1[1]};
     for (float *b : bufs) cudaFree(b);
@@ -559,7 +557,7 @@ int dcc_mappo_act(void *handle, const float *actor, const float *critic, const f
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
     if ((actor && !d_actions) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     return policy_forward(h, actor, critic, d_obs, n_envs, 0, seed, offset, deterministic, d_actions, d_logp, d_values,
                           nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -569,7 +567,7 @@ int dcc_mappo_evaluate(void *handle, const float *actor, const float *critic, co
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
     if ((actor && (!d_actions || !d_logp)) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     return policy_forward(h, actor, critic, d_obs, n_envs, 1, 0, 0, 0, const_cast<float *>(d_actions), d_logp, d_values,
                           d_mu, static_cast<cudaStream_t>(stream));
 }
@@ -588,7 +586,7 @@ int dcc_mappo_gae(void *handle, const float *d_rewards, const float *d_values, c
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_rewards || !d_values || !d_masks || !d_returns || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && h->cfg.use_gae && !d_vn_state) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     gae_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         d_rewards, d_values, d_masks, h->cfg.use_valuenorm ? d_vn_state : nullptr, d_returns, T, E, h->cfg.gamma,
         h->cfg.gae_lambda, h->cfg.use_gae);
@@ -602,7 +600,7 @@ int dcc_mappo_train_begin(void *handle, const float *d_returns, const float *d_v
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_returns || !d_values || !d_stats_out || T < 1 || E < 1) return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)T * E;
     DCC_CUDA_TRY(cudaMemsetAsync(d_stats_out, 0, 4 * sizeof(double), s));
@@ -651,7 +649,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         !d_returns || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
         return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
     const NetLayout &LA = h->la, &LC = h->lc;
@@ -696,7 +694,7 @@ int dcc_mappo_minibatch_stats(void *handle, const float *d_returns, const int64_
                               double *d_ret_sums_out, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_returns || !d_row_index || !d_ret_sums_out || n_index < 1) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DCC_CUDA_TRY(cudaMemsetAsync(d_ret_sums_out, 0, 2 * sizeof(double), s));
     const int blocks = (int)std::min<size_t>(((size_t)n_index + 255) / 256, (size_t)h->sm_count * 8);
@@ -718,7 +716,7 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
         !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
         return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int N = h->cfg.n_agents, H = h->cfg.hidden;
     const NetLayout &LA = h->la, &LC = h->lc;
@@ -766,7 +764,7 @@ int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float 
                     int64_t step, double *d_grad_norm_sq_out, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
     if (!h || !params || !grads || !adam_m || !adam_v || step < 1 || (which != 0 && which != 1)) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const NetLayout &L = which == 0 ? h->la : h->lc;
     if (which == 0) {
@@ -793,7 +791,7 @@ int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, 
                 int ldb, float *C, int ldc, int accumulate, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
     if (!h || !A || !B || !C || backend < 0 || backend > 3 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
-    DCC_CUDA_TRY(cudaSetDevice(h->device));
+    DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (backend == 0) backend = h->backend;
     if (backend == 2 || backend == 3) {

@@ -13,6 +13,7 @@ Two I/O modes, same kernel:
 All paths raise DccError if the CUDA library is missing; there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -23,8 +24,34 @@ from .spaces import Box
 
 def synthetic_pois(n_pois, seed=0):
     """Synthetic PoI layout: uniform in [-1,1]^2 (the reference's own commented alternative,
-    scenarios/coverage.py:18); the shipped layout is scenarios/pos_pois.npy[0:M] (pass it as pos_pois)."""
+    scenarios/coverage.py:18).  What the throughput benchmarks use (BASELINE.json: "synthetic PoI layouts")."""
     return np.random.default_rng(seed).uniform(-1.0, 1.0, (n_pois, 2))
+
+
+REFERENCE_POIS_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "pos_pois.npy")
+
+
+def reference_pois(n_pois):
+    """The reference's own PoI layout: the first `n_pois` rows of its scenarios/pos_pois.npy (scenarios/coverage.py:15-17;
+    1000 x 2 float64, shipped here as a data table).  This is the DEFAULT layout, so that the unchanged YAMLs train on
+    the same map as the reference."""
+    table = np.load(REFERENCE_POIS_PATH)
+    if n_pois > table.shape[0]:
+        raise ValueError("the reference PoI table has %d rows; num_pois = %d needs an explicit pos_pois / "
+                         "poi_layout: synthetic" % (table.shape[0], n_pois))
+    return np.ascontiguousarray(table[0:n_pois, :], dtype=np.float64)
+
+
+def resolve_pois(pos_pois, n_pois):
+    """pos_pois: None / "reference" -> reference_pois; "synthetic" (or "synthetic:<seed>") -> synthetic_pois; else an array."""
+    if pos_pois is None or (isinstance(pos_pois, str) and pos_pois == "reference"):
+        return reference_pois(n_pois)
+    if isinstance(pos_pois, str):
+        if pos_pois.startswith("synthetic"):
+            seed = int(pos_pois.split(":")[1]) if ":" in pos_pois else 0
+            return synthetic_pois(n_pois, seed)
+        raise ValueError("unknown PoI layout %r (use 'reference', 'synthetic[:seed]' or an (M,2) array)" % pos_pois)
+    return pos_pois
 
 
 class CoverageInfos:
@@ -71,8 +98,7 @@ class CudaVecEnv:
         cfg.comm_r_scale, cfg.comm_force_scale = float(comm_r_scale), float(comm_force_scale)
         cfg.reference_compat = 1 if reference_compat else 0
         self.cfg = cfg
-        if pos_pois is None:
-            pos_pois = synthetic_pois(self.n_pois)
+        pos_pois = resolve_pois(pos_pois, self.n_pois)   # default: the reference's pos_pois.npy[0:M]
         self.pos_pois = np.ascontiguousarray(np.asarray(pos_pois, dtype=np.float64)[: self.n_pois]).reshape(self.n_pois, 2)
         h = C.c_void_p()
         _lib.check(self.lib.dcc_env_create(C.byref(cfg), self.pos_pois.ctypes.data, self.device.index, C.byref(h)),

@@ -8,8 +8,10 @@ CudaVecEnv stepping all `n_rollout_threads` instances in a single launch.
 Optional new keys (defaults preserve the shipped behaviour):
   reference_compat (True)   the shipped scenario never forwards comm_r_scale/comm_force_scale to the world
                             (scenarios/coverage.py:34); False passes them through ("connectivity active")
-  pos_pois / pos_pois_path  PoI layout (M,2) or an .npy file (the reference's scenarios/pos_pois.npy);
-                            default: synthetic uniform layout, seed 0
+  pos_pois / pos_pois_path  PoI layout (M,2) or an .npy file; DEFAULT: the reference's own layout,
+                            scenarios/pos_pois.npy[0:M] (scenarios/coverage.py:15-17, shipped as envs/data/pos_pois.npy)
+  poi_layout                "reference" (default) or "synthetic" / "synthetic:<seed>" = uniform(-1,1) layout, the
+                            reference's commented alternative (coverage.py:18) used by the throughput benchmarks
   per_env_layouts (False)   every env instance gets its own uniform(-1,1) PoI layout (generator seeded with
                             `poi_seed`, default 0; rank-offset in multi-GPU jobs) — the reference's commented
                             `np.random.uniform(-1, 1)` alternative (coverage.py:71) made per-instance;
@@ -34,8 +36,10 @@ def make_env(cfg, **kwargs):
     path = getattr(cfg, "pos_pois_path", None)
     if pos_pois is None and path:
         pos_pois = np.load(path)[0:cfg.num_pois, :]
+    if pos_pois is None:
+        pos_pois = getattr(cfg, "poi_layout", None)          # None -> the reference table (CudaVecEnv default)
     per_env = None
-    if pos_pois is not None and np.asarray(pos_pois).ndim == 3:
+    if pos_pois is not None and not isinstance(pos_pois, str) and np.asarray(pos_pois).ndim == 3:
         per_env, pos_pois = np.asarray(pos_pois, dtype=np.float64), np.asarray(pos_pois, dtype=np.float64)[0]
     elif getattr(cfg, "per_env_layouts", False):
         rng = np.random.default_rng(int(getattr(cfg, "poi_seed", 0)) + 7919 * int(getattr(cfg, "env_rank", 0)))

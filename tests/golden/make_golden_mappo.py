@@ -177,8 +177,41 @@ def run_init_case(name, N, M, hidden, seed, extra=None):
     lr.train_envs.close()
 
 
+def run_pickle_case(name, N, M, hidden, seed):
+    """A checkpoint exactly as the reference writes it: MAPPOTrainer.save_model pickles the whole MAPPOPolicy object
+    (algos/mappo.py:237-240).  Stored with the state_dict values beside it, for the importer test
+    (MAPPOTrainer.load_model must read the reference's own agent.pkl)."""
+    import shutil
+    import tempfile
+    lr, cfg = build_learner(N, M, 1, 4, hidden, 1, seed)
+    D = lr.obs_dim_n[0]
+    a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden))
+    set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
+    set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
+    d = tempfile.mkdtemp()
+    lr.trainer.save_model(d)
+    dst = os.path.join(HERE, "ref_agent_%s.pkl" % name)
+    shutil.copy(os.path.join(d, "agent.pkl"), dst)
+    shutil.rmtree(d)
+    out = {}
+    for tag, mod in (("actor", lr.policy.actor), ("critic", lr.policy.critic)):
+        for k, v in mod.state_dict().items():
+            out[tag + "." + k] = v.numpy().copy()
+    out["cfg"] = np.array(json.dumps(dict(name=name, n_agents=N, n_pois=M, hidden=hidden, seed=seed, obs_dim=D)))
+    np.savez_compressed(os.path.join(HERE, "ref_agent_%s.npz" % name), **out)
+    print("wrote", dst, "%.0f KB" % (os.path.getsize(dst) / 1024))
+    lr.train_envs.close()
+
+
 def main():
     load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":      # the cases added in round 2 only
+        # the benchmarked learner shape (BASELINE configs[3]): 8/64 with hidden 256 -> the tcgen05 kernels
+        # (fp16-split forward at K = 338, split-K critic at K = 2704, weight gradients with N_out = 338 / 2704);
+        # 48 env-step rows = 384 agent rows = 3 row tiles
+        run_case("gen_8x64_h256", 8, 64, 4, 12, 256, 4, seed=14)
+        run_pickle_case("3x20_h32", 3, 20, 32, seed=15)
+        return
     run_case("ship_4x20_h256", 4, 20, 4, 30, 256, 15, seed=0)     # shipped shapes + hyper-parameters, short rollout
     run_case("gen_8x64_h64", 8, 64, 2, 12, 64, 4, seed=1)         # BASELINE shape, small hidden size
     run_case("gen_3x20_h32", 3, 20, 3, 10, 32, 3, seed=2)

@@ -371,3 +371,48 @@ def test_cuda_per_env_poi_layouts_vs_reference_golden(shape, tags, spec):
     with pytest.raises(ValueError):
         env.set_poi_layouts(np.zeros((E + 1, c["n_pois"], 2)))
     env.close()
+
+
+@pytest.mark.parametrize("name", ["gen_8x64_runaway", "ship_4x20_seek", "gen_8x64_force"])
+def test_rollout_insert_vs_reference_golden(name):
+    """Row a13 (learner.py:254-276 + shared_buffer.py:72-105): what `Learner.insert` stores per step — the shared reward
+    and mask = 1 - done — asserted against the reference trajectory's own reward / done records (runaway = episodes
+    that end, so masks of 0 appear), through SharedReplayBuffer.insert_env_step (dcc_rollout_insert) on the buffer
+    slices the rollout uses; obs[t+1] is the env kernel's in-place output (post-auto-reset observation)."""
+    from argparse import Namespace
+    from dcc_b200.buffer import SharedReplayBuffer
+    from dcc_b200.envs.spaces import Box
+    g = load_golden(name)
+    c = g["cfg"]
+    E, T, N = 3, c["T"], c["n_agents"]
+    env = _mk_cuda(g, E)
+    D = env.obs_dim
+    cfg = Namespace(max_ep_len=T, n_rollout_threads=E, gamma=0.99, gae_lambda=0.95, num_agents=N, device=0)
+    buf = SharedReplayBuffer(cfg, Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,)))
+    env.reset(out_obs=buf.obs[0])
+    for t in range(T):
+        a = torch.from_numpy(np.repeat(g["actions"][t][None], E, 0)).cuda()
+        assert buf.step == t
+        obs, rew, done, infos = env.step(a, out_obs=buf.obs[t + 1])
+        buf.insert_env_step(rew, done.view(torch.uint8))
+    torch.cuda.synchronize()
+    assert buf.step == 0                                                    # wrapped after T inserts
+    rew = buf.rewards_te.cpu().numpy()
+    masks = buf.masks_te.cpu().numpy()
+    ref_rew = g["reward"].astype(np.float32)[:T]
+    ref_done = g["done"].astype(bool)[:T]
+    assert masks.shape == (T + 1, E) and np.all(masks[0] == 1.0)
+    for e in range(E):
+        assert np.all(np.abs(rew[:, e] - ref_rew) <= REW_RTOL * np.maximum(1.0, np.abs(ref_rew))), name
+        assert np.array_equal(masks[1:, e], 1.0 - ref_done.astype(np.float32)), name
+    if "runaway" in name:
+        assert ref_done.any()
+    # the reference-shaped views expose the same numbers per agent: (T, E, N, 1)
+    assert buf.rewards.shape == (T, E, N, 1) and torch.equal(buf.rewards[:, :, 0, 0], buf.rewards_te)
+    assert buf.masks.shape == (T + 1, E, N, 1) and torch.equal(buf.masks[:, :, N - 1, 0], buf.masks_te)
+    # obs[t+1] holds the golden's post-reset observations where recorded
+    obs_at = {int(t): k for k, t in enumerate(g["obs_steps"])}
+    for t, k in obs_at.items():
+        if t < T:
+            assert np.array_equal(buf.obs[t + 1, 1].cpu().numpy(), g["obs"][k])
+    env.close()

@@ -257,3 +257,40 @@ def test_fp16_split_emulation():
     dh0, dl0 = split16(dz)                                   # unscaled: the gradients vanish into fp16 subnormals
     e_f16_plain = rms(f(dh0).T @ f(xh) + f(dh0).T @ f(xl) + f(dl0).T @ f(xh), refg)
     assert e_tf32 < 1e-7 and e_f16 < 1.1 * e_tf32 and e_f16_plain > 1e-3
+
+
+def test_load_checkpoint_reads_a_reference_written_agent_pkl(tmp_path):
+    """MAPPOTrainer.load_model must read the reference's own checkpoint: `pickle.dump(self.policy, f)`
+    (algos/mappo.py:237-240).  The fixture was written by the UNMODIFIED reference (tests/golden/make_golden_mappo.py
+    run_pickle_case); it is read here WITHOUT the reference on sys.path, through the restricted unpickler."""
+    import pickle
+    import torch
+    from dcc_b200.algos.mappo import CHECKPOINT_FORMAT, _CheckpointUnpickler, load_checkpoint
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_agent_3x20_h32.npz"))
+    sd = load_checkpoint(os.path.join(ROOT, "tests", "golden", "ref_agent_3x20_h32.pkl"))
+    assert sd["format"] == "reference.policy.pickle"
+    n = 0
+    for tag in ("actor", "critic"):
+        keys = [k[len(tag) + 1:] for k in g.files if k.startswith(tag + ".")]
+        assert list(sd[tag].keys()) == keys            # torch's state_dict order, fc_h block included
+        for k in keys:
+            assert np.array_equal(sd[tag][k].numpy(), g[tag + "." + k]), (tag, k)
+            n += 1
+    assert n == 33    # actor 17 (incl. fc_h and logstd), critic 16
+    # this build's own format round-trips through the same reader; anything else is refused with a clear error
+    own = {"actor": {"w": torch.ones(2)}, "critic": {"w": torch.zeros(2)}, "format": CHECKPOINT_FORMAT}
+    with open(tmp_path / "agent.pkl", "wb") as f:
+        pickle.dump(own, f)
+    back = load_checkpoint(str(tmp_path / "agent.pkl"))
+    assert back["format"] == CHECKPOINT_FORMAT and torch.equal(back["actor"]["w"], torch.ones(2))
+    with open(tmp_path / "bad.pkl", "wb") as f:
+        pickle.dump([1, 2, 3], f)
+    with pytest.raises(ValueError):
+        load_checkpoint(str(tmp_path / "bad.pkl"))
+    import io
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("1+1",))
+    with pytest.raises(pickle.UnpicklingError):
+        _CheckpointUnpickler(io.BytesIO(pickle.dumps(Evil()))).load()

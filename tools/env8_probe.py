@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import torch
 from dcc_b200.envs import CudaVecEnv
 E, N, M = 65536, 8, 64
-env = CudaVecEnv(E, N, M, reference_compat=True)
+env = CudaVecEnv(E, N, M, reference_compat=True, pos_pois="synthetic")
 acts = [torch.randn(E, N, 2, device="cuda") for _ in range(8)]
 env.reset()
 for t in range(30):

@@ -5,7 +5,7 @@ import torch
 from dcc_b200.envs import CudaVecEnv
 for (N, M, E) in ((8, 64, 65536), (16, 256, 32768), (6, 41, 65536)):
     for wpc in (2, 4, 8):
-        env = CudaVecEnv(E, N, M, comm_force_scale=1.0, reference_compat=False)
+        env = CudaVecEnv(E, N, M, comm_force_scale=1.0, reference_compat=False, pos_pois="synthetic")
         env.use_specialized(False)
         try:
             env.set_launch(wpc, 0)

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--generic", action="store_true")
     args = ap.parse_args()
     E, N, M = args.envs, args.n, args.m
-    env = CudaVecEnv(E, N, M, comm_force_scale=args.force, reference_compat=args.force == 0.0)
+    env = CudaVecEnv(E, N, M, comm_force_scale=args.force, reference_compat=args.force == 0.0, pos_pois="synthetic")
     acts = [torch.randn(E, N, 2, device="cuda") for _ in range(8)]
     env.reset()
     D = env.obs_dim
