@@ -54,6 +54,7 @@ SIGNATURES = {
     "dcc_env_reset_host": (C.c_int, [_VP, _VP, _VP]),
     "dcc_env_get_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "dcc_env_set_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "dcc_env_snapshot_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "dcc_env_state_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "dcc_env_set_launch": (C.c_int, [_VP, C.c_int, C.c_int]),
     "dcc_env_use_specialized": (C.c_int, [_VP, C.c_int]),
@@ -67,6 +68,11 @@ SIGNATURES = {
     "dcc_mappo_launch_count": (C.c_int64, [_VP]),
     "dcc_mappo_act": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _VP, _VP, _VP, _VP]),
     "dcc_mappo_evaluate": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "dcc_mappo_set_env_layout": (C.c_int, [_VP, C.c_int, _VP, C.c_double]),
+    "dcc_mappo_act_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _VP, _VP, _VP, _VP]),
+    "dcc_mappo_evaluate_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "dcc_mappo_epoch_grads_state": (C.c_int, [_VP] * 13 + [C.c_double, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_obs_from_state": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP]),
     "dcc_rollout_insert": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP]),
     "dcc_mappo_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "dcc_mappo_train_begin": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),

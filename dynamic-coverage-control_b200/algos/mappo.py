@@ -297,6 +297,76 @@ class MAPPOPolicy:
         ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum()
         return values.view(n, 1).expand(n, N).reshape(n * N, 1), logp.view(n * N, 1), ent
 
+    # ---- compact-state path (include/dcc_b200.h "compact-state learner path") ------------------------
+    def set_env_layout(self, pos_pois, m_energy=5.0):
+        """Hands the learner handle the env's PoI table: from then on the *_state methods evaluate the first layer of both
+        nets from the env's compact state (pos_vel (.., N, 4) float64, energy (.., M) uint8) instead of observation rows.
+        Returns False (and changes nothing) if the layout is not the env's 2N + 2 + 5M / centralised-critic one."""
+        poi = np.ascontiguousarray(np.asarray(pos_pois, dtype=np.float64)).reshape(-1, 2)
+        rc = self.lib.dcc_mappo_set_env_layout(self._h, int(poi.shape[0]), poi.ctypes.data, float(m_energy))
+        if rc == -5:
+            return False
+        _lib.check(rc, "dcc_mappo_set_env_layout")
+        self.n_pois = int(poi.shape[0])
+        return True
+
+    def _as_state(self, pos_vel, energy):
+        if not (isinstance(pos_vel, torch.Tensor) and pos_vel.is_cuda and pos_vel.dtype == torch.float64):
+            pos_vel = torch.as_tensor(np.asarray(pos_vel), dtype=torch.float64).to(self.device)
+        if not (isinstance(energy, torch.Tensor) and energy.is_cuda and energy.dtype == torch.uint8):
+            energy = torch.as_tensor(np.asarray(energy), dtype=torch.uint8).to(self.device)
+        pos_vel, energy = pos_vel.contiguous(), energy.contiguous()
+        n = pos_vel.numel() // (self.n_agents * 4)
+        if n * self.n_agents * 4 != pos_vel.numel() or energy.numel() != n * self.n_pois:
+            raise ValueError("state shapes: pos_vel (.., N, 4) float64 and energy (.., M) uint8 with the same leading rows")
+        return pos_vel, energy, n
+
+    def get_actions_state(self, pos_vel, energy, deterministic=False, out_actions=None, out_logp=None, out_values=None):
+        """get_actions on the compact state of one vec-env step.  Same outputs as get_actions."""
+        pos_vel, energy, n = self._as_state(pos_vel, energy)
+        N = self.n_agents
+        actions = out_actions if out_actions is not None else self._out("actions", (n * N, 2))
+        logp = out_logp if out_logp is not None else self._out("logp", (n * N,))
+        values = out_values if out_values is not None else self._out("values", (n,))
+        self._rng_offset += 1
+        _lib.check(self.lib.dcc_mappo_act_state(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
+                                                self._ptr(pos_vel), self._ptr(energy), n, self.seed, self._rng_offset,
+                                                1 if deterministic else 0, self._ptr(actions), self._ptr(logp),
+                                                self._ptr(values), self._stream()), "dcc_mappo_act_state")
+        v = values.view(n, 1).expand(n, N).reshape(n * N, 1)
+        return v, actions.view(n * N, 2), logp.view(n * N, 1), None, None
+
+    def get_values_state(self, pos_vel, energy, out_values=None):
+        pos_vel, energy, n = self._as_state(pos_vel, energy)
+        values = out_values if out_values is not None else self._out("values", (n,))
+        _lib.check(self.lib.dcc_mappo_act_state(self._h, None, self._ptr(self.critic.params), self._ptr(pos_vel),
+                                                self._ptr(energy), n, 0, 0, 0, None, None, self._ptr(values),
+                                                self._stream()), "dcc_mappo_act_state(values)")
+        return values.view(n, 1).expand(n, self.n_agents).reshape(n * self.n_agents, 1)
+
+    def evaluate_actions_state(self, pos_vel, energy, action):
+        """evaluate_actions on compact state rows: (values (B,1), action_log_probs (B,1), dist_entropy)."""
+        pos_vel, energy, n = self._as_state(pos_vel, energy)
+        N = self.n_agents
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
+        logp = self._out("ev_logp", (n * N,))
+        values = self._out("ev_values", (n,))
+        _lib.check(self.lib.dcc_mappo_evaluate_state(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
+                                                     self._ptr(pos_vel), self._ptr(energy), self._ptr(action), n,
+                                                     self._ptr(logp), self._ptr(values), None, self._stream()),
+                   "dcc_mappo_evaluate_state")
+        logstd = self.actor.view("act.action_out.logstd._bias")
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum()
+        return values.view(n, 1).expand(n, N).reshape(n * N, 1), logp.view(n * N, 1), ent
+
+    def obs_from_state(self, pos_vel, energy, out=None):
+        """Observation rows (rows, N, D) float32 regenerated from compact state rows (bit-identical to env.step's)."""
+        pos_vel, energy, n = self._as_state(pos_vel, energy)
+        obs = out if out is not None else torch.empty((n, self.n_agents, self.obs_dim), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dcc_obs_from_state(self._h, self._ptr(pos_vel), self._ptr(energy), n, self._ptr(obs),
+                                               self._stream()), "dcc_obs_from_state")
+        return obs
+
     def act(self, obs, rnn_states_actor=None, masks=None, available_actions=None, deterministic=False):
         obs, n = self._as_obs(obs)
         actions = self._out("actions", (n * self.n_agents, 2))
@@ -400,6 +470,16 @@ class MAPPOTrainer:
         mbs = B_local // nmb                               # mini_batch_size (shared_buffer.py:236); the tail is dropped
         mbs_global = float(mbs) * self.comm.world
         for ep in range(self.ppo_epoch):
+            if nmb == 1 and getattr(buffer, "compact", False):
+                _lib.check(lib.dcc_mappo_epoch_grads_state(
+                    p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
+                    ptr(buffer.state_pv), ptr(buffer.state_en), ptr(buffer.actions), ptr(buffer.action_log_probs_ten),
+                    ptr(buffer.values_te), ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, T, E,
+                    ptr(self._epoch_stats[ep]), s), "dcc_mappo_epoch_grads_state")
+                self._apply(ep, update_actor)
+                continue
+            if getattr(buffer, "compact", False):
+                raise NotImplementedError("num_mini_batch > 1 needs the materialised rollout (compact_rollout: false)")
             if nmb == 1:
                 _lib.check(lib.dcc_mappo_epoch_grads(
                     p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),

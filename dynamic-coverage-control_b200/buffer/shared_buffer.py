@@ -12,7 +12,16 @@ Same constructor and method names (`insert`, `compute_returns`, `after_update`) 
     `rnn_states`, `rnn_states_critic`, `bad_masks`, `active_masks` are zero-cost expanded views with the reference's
     shapes; `available_actions` is None as in the reference (Box action space).
 GAE (`compute_returns`, shared_buffer.py:199-208) is one kernel, `dcc_mappo_gae`.
-Memory at 8 UAV / 64 PoI / 65 536 envs / T = 150: obs 107 GB float32 of the 180 GB HBM3e; everything else < 1 GB.
+
+Two storage modes for the observations:
+  * materialised (`compact=False`): `obs` is the full (T+1, E, N, D) float32 tensor — 107 GB at 8 UAV / 64 PoI /
+    65 536 envs / T = 150 of the 180 GB HBM3e.  Needed when the caller hands observations in (`insert`), for
+    `num_mini_batch > 1`, per-env PoI layouts and the decentralised critic.
+  * compact (`compact=True`, what `Learner` picks whenever the path allows it): the rollout keeps the env's compact
+    state per step — `state_pv` (T+1, E, N, 4) float64 and `state_en` (T+1, E, M) uint8, 320 B per env step at 8/64,
+    3.2 GB instead of 107 GB — and the learner kernels evaluate the first layer from it directly (exact algebra,
+    csrc/dcc_compact.cuh).  `obs` then is a lazy reference-shaped view: `buffer.obs[t]` regenerates step t's
+    (E, N, D) rows bit-identically to what the env kernel would have written.
 """
 import ctypes as C
 
@@ -21,8 +30,39 @@ import torch
 from .. import _lib
 
 
+class RegeneratedObs:
+    """Reference-shaped lazy view of a compact rollout's observations: indexing a step (or a slice of steps)
+    regenerates the float32 rows from the stored compact state (dcc_obs_from_state)."""
+
+    def __init__(self, buf):
+        self._buf = buf
+        T1, E, N, _ = buf.state_pv.shape
+        self.shape = (T1, E, N, buf.obs_dim)
+        self.dtype = torch.float32
+        self.device = buf.device
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        b = self._buf
+        T1, E, N, D = self.shape
+        if isinstance(idx, int):
+            t = idx % T1
+            return b.regenerate_obs(t, t + 1)[0]
+        if isinstance(idx, slice):
+            lo, hi, st = idx.indices(T1)
+            if st != 1:
+                raise IndexError("RegeneratedObs supports contiguous step ranges only")
+            return b.regenerate_obs(lo, hi)
+        raise IndexError("RegeneratedObs is indexed by a step or a contiguous range of steps")
+
+    def materialize(self):
+        return self[0:self.shape[0]]
+
+
 class SharedReplayBuffer(object):
-    def __init__(self, cfg, obs_space, cent_obs_space, act_space, device=None):
+    def __init__(self, cfg, obs_space, cent_obs_space, act_space, device=None, compact=False, n_pois=None):
         self.lib = _lib.load()
         self.episode_length = int(cfg.max_ep_len)
         self.n_rollout_threads = int(cfg.n_rollout_threads)
@@ -42,7 +82,19 @@ class SharedReplayBuffer(object):
         self.agents_per_value_row = N if self.centralized else 1
         V = self.n_value_rows
         kw = dict(dtype=torch.float32, device=self.device)
-        self.obs = torch.zeros((T + 1, E, N, D), **kw)
+        self.compact = bool(compact)
+        self._policy = None
+        if self.compact:
+            if not self.centralized or n_pois is None:
+                raise ValueError("compact rollout storage needs the centralised critic and the env's PoI count")
+            self.n_pois = int(n_pois)
+            if D != 4 + 2 * (N - 1) + 5 * self.n_pois:
+                raise ValueError("obs_dim %d is not the env's 2N + 2 + 5M layout" % D)
+            self.state_pv = torch.zeros((T + 1, E, N, 4), dtype=torch.float64, device=self.device)
+            self.state_en = torch.zeros((T + 1, E, self.n_pois), dtype=torch.uint8, device=self.device)
+            self.obs = RegeneratedObs(self)
+        else:
+            self.obs = torch.zeros((T + 1, E, N, D), **kw)
         self.actions = torch.zeros((T, E, N, self.act_dim), **kw)
         self.action_log_probs_ten = torch.zeros((T, E, N), **kw)   # one column (the reference stores 2 equal ones)
         self.values_te = torch.zeros((T + 1, V), **kw)
@@ -82,7 +134,20 @@ class SharedReplayBuffer(object):
         T1, E, N, D = self.obs.shape
         if not self.centralized:
             return self.obs
-        return self.obs.view(T1, E, 1, N * D).expand(T1, E, N, N * D)
+        obs = self.obs.materialize() if self.compact else self.obs
+        return obs.view(T1, E, 1, N * D).expand(T1, E, N, N * D)
+
+    # ---- compact mode ------------------------------------------------------------------------------------
+    def attach_policy(self, policy):
+        """The learner handle that knows the env's PoI table (MAPPOPolicy.set_env_layout): regenerates `obs[t]`."""
+        self._policy = policy
+
+    def regenerate_obs(self, t0, t1):
+        """(t1 - t0, E, N, D) float32 observation rows of steps [t0, t1) rebuilt from the compact state."""
+        if self._policy is None:
+            raise RuntimeError("compact buffer: attach_policy(policy) first (the PoI table lives in the learner handle)")
+        return self._policy.obs_from_state(self.state_pv[t0:t1], self.state_en[t0:t1]).view(
+            t1 - t0, self.n_rollout_threads, self.num_agents, self.obs_dim)
 
     def _per_agent(self, x):
         if not self.centralized:
@@ -132,7 +197,11 @@ class SharedReplayBuffer(object):
                 return x.reshape(self.n_value_rows)
             return x.reshape(E, N, -1)[:, 0, 0]
 
-        put(self.obs[t + 1], obs)
+        if self.compact:
+            if obs is not None:
+                raise ValueError("compact rollout storage takes the env state (state_pv / state_en), not observation rows")
+        else:
+            put(self.obs[t + 1], obs)
         put(self.actions[t], actions)
         alp = torch.as_tensor(action_log_probs, dtype=torch.float32, device=self.device)
         put(self.action_log_probs_ten[t], alp if alp.numel() == E * N else alp.reshape(E, N, -1)[..., 0])
@@ -186,7 +255,11 @@ class SharedReplayBuffer(object):
 
     def after_update(self):
         """shared_buffer.py:142-152: the last step becomes the first of the next rollout."""
-        self.obs[0].copy_(self.obs[-1])
+        if self.compact:
+            self.state_pv[0].copy_(self.state_pv[-1])
+            self.state_en[0].copy_(self.state_en[-1])
+        else:
+            self.obs[0].copy_(self.obs[-1])
         self.masks_te[0].copy_(self.masks_te[-1])
 
     def close(self):

@@ -1203,6 +1203,17 @@ int dcc_env_set_state(void *handle, const double *h_pos_vel, const uint8_t *h_en
     return DCC_OK;
 }
 
+int dcc_env_snapshot_state(void *handle, double *d_pos_vel_out, uint8_t *d_energy_out, dcc_stream_t stream) {
+    EnvHandle *h = as_env(handle);
+    if (!h || !d_pos_vel_out || !d_energy_out) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t E = h->cfg.n_envs, N = h->cfg.n_agents, M = h->cfg.n_pois;
+    DCC_CUDA_TRY(cudaMemcpyAsync(d_pos_vel_out, h->d_pos_vel, sizeof(double) * 4 * N * E, cudaMemcpyDeviceToDevice, s));
+    DCC_CUDA_TRY(cudaMemcpyAsync(d_energy_out, h->d_energy, M * E, cudaMemcpyDeviceToDevice, s));
+    return DCC_OK;
+}
+
 int dcc_env_state_ptrs(void *handle, double **d_pos_vel, uint8_t **d_energy) {
     EnvHandle *h = as_env(handle);
     if (!h) return DCC_ERR_INVALID_ARG;

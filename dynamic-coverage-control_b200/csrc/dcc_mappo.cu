@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <new>
 
+#include "dcc_compact.cuh"
 #include "dcc_ops.cuh"
 #include "dcc_tc.cuh"
 
@@ -64,6 +65,13 @@ struct MappoHandle {
     float *mu, *logp, *dmu, *vnew, *dv;   // [chunk*N,2], [chunk*N], [chunk*N,2], [chunk], [chunk]
     double *dsums;   // small float64 scratch: [4] actor grad sumsq, [5] critic grad sumsq
     float *vn_gae;   // ValueNorm state snapshot taken at train_begin (3 floats)
+    // compact-state path (dcc_mappo_set_env_layout): layer 1 evaluated from the env's compact state (dcc_compact.cuh)
+    bool compact;
+    CompactDims cd;
+    double *d_poi;           // [M, 2] PoI table
+    float *fc;               // [chunk, cd.ldc] critic features (the actor's [chunk*N, cd.lda] live in x0)
+    float *wt[2];            // folded fc1 weights [H, ld] (actor, critic)
+    float *gt[2];            // running dz1^T f of the epoch [H, ld]
     int64_t launches;
 };
 constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
@@ -272,14 +280,50 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
     return DCC_OK;
 }
 
+// compact path: fold the input LayerNorm affine AND the observation structure into fc1 (Wt = (W1 * gamma0) A)
+static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
+    float *b1g = net ? h->b1g_c : h->b1g_a;
+    const int ldk = net ? h->cd.ldc : h->cd.lda, nb = net ? h->cd.N : 1;
+    fold_compact_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W[0], P + L.b[0], L.has_ln0 ? P + L.ln0_g : nullptr,
+                                                      L.has_ln0 ? P + L.ln0_b : nullptr, h->d_poi, h->wt[net], b1g, L.H, h->cd, nb, ldk);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    if (h->backend == 2) {
+        int rc;
+        if ((rc = tc_prep_weights(h, h->wt[net], ldk, false, ldk, h->img_w1[net], s, h->f16_fwd))) return rc;
+        for (int k = 1; k < L.nblk; ++k) {
+            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
+            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_wgrad))) return rc;
+        }
+    }
+    return DCC_OK;
+}
+
+// compact path: features of `rows` env-step rows -> x0 (actor, [rows*N, lda]) and fc (critic, [rows, ldc])
+static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en, int rows, bool want_actor, bool want_critic,
+                            cudaStream_t s) {
+    const int wpb = 8;
+    const size_t smem = compact_features_smem(h->cd, wpb);
+    compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, h->d_poi, want_actor ? h->x0 : nullptr,
+                                                                              want_critic ? h->fc : nullptr, rows, h->cd,
+                                                                              h->cfg.use_feature_normalization ? 1 : 0);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
 // trunk forward on `rows` rows of width L.in: x -> h2.  save = keep a1/a2/stats for the backward pass.
+// feat != nullptr (compact path): block 0 reads the precomputed feature rows [rows, ldf] against the folded weights
+// h->wt[net] instead of xhat / w1g (x is ignored; no input-LayerNorm kernel).
 static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int net, const float *x, int rows, bool save,
-                         cudaStream_t s, const long long *ridx = nullptr, int rdiv = 1) {
+                         cudaStream_t s, const long long *ridx = nullptr, int rdiv = 1, const float *feat = nullptr, int ldf = 0) {
     const int H = L.H;
     const int wpb = 8;
-    const float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
+    const float *w1g = feat ? h->wt[net] : (net ? h->w1g_c : h->w1g_a), *b1g = net ? h->b1g_c : h->b1g_a;
     // input LayerNorm (without affine): register-resident single-pass variant when the rows are 16-byte aligned
-    if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 8)
+    if (feat) {
+        // features carry the normalisation already
+    } else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 8)
         ln_noaffine_fwd_vec_kernel<8><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else if ((L.in & 3) == 0 && ((uintptr_t)x & 15) == 0 && L.in <= 128 * 24)
         ln_noaffine_fwd_vec_kernel<24><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
@@ -287,18 +331,18 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         ln_noaffine_fwd_vec2_kernel<6><<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
     else
         ln_noaffine_fwd_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, 0, s>>>(x, h->x0, rows, L.in, L.inp, ridx, rdiv, L.has_ln0 ? 1 : 0);
-    h->launches++;
+    if (!feat) h->launches++;
     int rc;
     // hidden blocks: block 0 reads xhat (K = padded input width, folded fc1), block k >= 1 reads h_{k-1}
     for (int k = 0; k < L.nblk; ++k) {
-        const float *in = k == 0 ? h->x0 : h->hh[k - 1];
-        const int K = k == 0 ? L.in : H, ldin = k == 0 ? L.inp : H;
+        const float *in = k == 0 ? (feat ? feat : h->x0) : h->hh[k - 1];
+        const int K = k == 0 ? (feat ? ldf : L.in) : H, ldin = k == 0 ? (feat ? ldf : L.inp) : H;
         const float *Wk = k == 0 ? w1g : P + L.W[k], *bk = k == 0 ? b1g : P + L.b[k];
         if (h->backend == 2) {
             // tcgen05 GEMM with the block's bias + activation + LayerNorm fused into its epilogue (one kernel per block)
             rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
                              bk, P + L.lg[k], P + L.lb[k], h->hh[k], save ? h->mean[k] : nullptr, save ? h->rstd[k] : nullptr,
-                             fwd_f16(h, L, k));
+                             (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k));   // compact features are bounded: fp16-split eligible
             if (rc) return rc;
             continue;
         }
@@ -318,7 +362,7 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
 // `dout` = gradient w.r.t. the head output ([rows, out]); on return all parameter gradients of the net have been
 // accumulated into G (the fc1 slot holds G1, see ln0_finalize).
 static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *dout, int rows,
-                          cudaStream_t s) {
+                          cudaStream_t s, const float *feat = nullptr, int ldf = 0) {
     const int H = L.H;
     const int wpb = 8;
     const int gr = grid_for_reduce(h, rows, wpb);
@@ -347,8 +391,12 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
         h->launches++;
         float *t = dz; dz = dx; dx = t;
     }
-    rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, dz, H, h->x0, L.inp, G + L.W[0], L.in, s, wgrad_f16(h, L, 0))   // G1 += dz_0^T xhat
-                         : launch_gemm(h, true, false, H, L.in, rows, dz, H, h->x0, L.inp, G + L.W[0], L.in, true, s);
+    if (feat)      // compact path: Gt += dz_0^T f  (unfolded into the fc1 slot once per optimiser step, compact_finalize)
+        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, ldf, dz, H, feat, ldf, h->gt[net], ldf, s, h->f16_wgrad)
+                             : launch_gemm(h, true, false, H, ldf, rows, dz, H, feat, ldf, h->gt[net], ldf, true, s);
+    else
+        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, L.in, dz, H, h->x0, L.inp, G + L.W[0], L.in, s, wgrad_f16(h, L, 0))   // G1 += dz_0^T xhat
+                             : launch_gemm(h, true, false, H, L.in, rows, dz, H, h->x0, L.inp, G + L.W[0], L.in, true, s);
     if (rc) return rc;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -361,6 +409,16 @@ static int ln0_finalize(MappoHandle *h, const NetLayout &L, const float *P, floa
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
+}
+
+// compact path, once per optimiser step: G (fc1 slot) = Gt A^T, then the usual input-LayerNorm finalisation
+static int compact_finalize(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, cudaStream_t s) {
+    const int ldk = net ? h->cd.ldc : h->cd.lda, nb = net ? h->cd.N : 1;
+    const size_t n = (size_t)L.H * L.in;
+    unfold_compact_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->gt[net], h->d_poi, G + L.W[0], L.H, h->cd, nb, ldk);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return ln0_finalize(h, L, P, G, s);
 }
 
 __global__ void expand_values_kernel(const float *__restrict__ v, float *__restrict__ out, int rows, int N) {
@@ -492,6 +550,8 @@ int dcc_mappo_destroy(void *handle) {
     }
     cudaFree(h->dsums);
     cudaFree(h->dz_absmax);
+    cudaFree(h->d_poi); cudaFree(h->fc);
+    for (int n = 0; n < 2; ++n) { cudaFree(h->wt[n]); cudaFree(h->gt[n]); }
     h->magic = 0;
     delete h;
     return DCC_OK;
@@ -519,21 +579,25 @@ int64_t dcc_mappo_launch_count(void *handle) {
 }
 
 // shared body of get_actions / evaluate_actions.  mode 0 = sample, 1 = evaluate given actions.
+// d_obs == nullptr: compact path, the rows come from the env state (pv [n_envs, N, 4] float64, en [n_envs, M] uint8).
 static int policy_forward(MappoHandle *h, const float *actor, const float *critic, const float *d_obs, int n_envs, int mode,
                           uint64_t seed, uint64_t offset, int deterministic, float *d_actions, float *d_logp,
-                          float *d_values, float *d_mu, cudaStream_t s) {
+                          float *d_values, float *d_mu, cudaStream_t s, const double *pv = nullptr, const uint8_t *en = nullptr) {
     const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
     const bool do_actor = actor && d_actions && (mode == 0 || d_logp);
     const bool do_critic = critic && d_values;
+    const bool cmp = d_obs == nullptr;
     int rc;
-    if (do_actor && (rc = fold_ln0(h, h->la, actor, 0, false, s))) return rc;
-    if (do_critic && (rc = fold_ln0(h, h->lc, critic, 1, false, s))) return rc;
+    if (do_actor && (rc = cmp ? fold_compact(h, h->la, actor, 0, false, s) : fold_ln0(h, h->la, actor, 0, false, s))) return rc;
+    if (do_critic && (rc = cmp ? fold_compact(h, h->lc, critic, 1, false, s) : fold_ln0(h, h->lc, critic, 1, false, s))) return rc;
     for (int e0 = 0; e0 < n_envs; e0 += h->chunk_rows) {
         const int ne = min(h->chunk_rows, n_envs - e0);
-        const float *x = d_obs + (size_t)e0 * N * D;
+        const float *x = cmp ? nullptr : d_obs + (size_t)e0 * N * D;
+        if (cmp && (rc = compact_features(h, pv + (size_t)e0 * N * 4, en + (size_t)e0 * h->cd.M, ne, do_actor, do_critic, s))) return rc;
+        const float *fa = cmp ? h->x0 : nullptr, *fcr = cmp ? h->fc : nullptr;
         if (do_actor) {
             const int rows = ne * N;
-            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s))) return rc;
+            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s, nullptr, 1, fa, h->cd.lda))) return rc;
             actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
                 h->hh[h->la.nblk - 1], actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
                 d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
@@ -541,7 +605,7 @@ static int policy_forward(MappoHandle *h, const float *actor, const float *criti
             h->launches++;
         }
         if (do_critic) {
-            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s))) return rc;
+            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s, nullptr, 1, fcr, h->cd.ldc))) return rc;
             critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + h->lc.Wh, critic + h->lc.bh,
                                                                       d_values + e0, ne, H);
             h->launches++;
@@ -570,6 +634,75 @@ int dcc_mappo_evaluate(void *handle, const float *actor, const float *critic, co
     DCC_DEVICE_GUARD(h->device);
     return policy_forward(h, actor, critic, d_obs, n_envs, 1, 0, 0, 0, const_cast<float *>(d_actions), d_logp, d_values,
                           d_mu, static_cast<cudaStream_t>(stream));
+}
+
+int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, double m_energy) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || n_pois < 1 || !h_poi_xy || !(m_energy > 0)) return DCC_ERR_INVALID_ARG;
+    const int N = h->cfg.n_agents;
+    // the observation layout must be the env's (coverage.py:99-110) and the critic centralised over the N rows
+    if (h->cfg.obs_dim != 4 + 2 * (N - 1) + 5 * n_pois || h->lc.in != N * h->cfg.obs_dim) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    CompactDims cd;
+    cd.init(N, n_pois, m_energy);
+    if ((size_t)cd.lda > (size_t)h->la.inp) return DCC_ERR_UNSUPPORTED;   // actor features live in the xhat scratch
+    if (compact_features_smem(cd, 8) > 200 * 1024) return DCC_ERR_UNSUPPORTED;
+    cudaFree(h->d_poi); cudaFree(h->fc);
+    for (int n = 0; n < 2; ++n) { cudaFree(h->wt[n]); cudaFree(h->gt[n]); h->wt[n] = h->gt[n] = nullptr; }
+    h->d_poi = nullptr; h->fc = nullptr; h->compact = false;
+    const int H = h->cfg.hidden;
+    cudaError_t ce = cudaMalloc(&h->d_poi, sizeof(double) * 2 * n_pois);
+    if (ce == cudaSuccess) ce = cudaMalloc(&h->fc, (size_t)h->chunk_rows * cd.ldc * sizeof(float));
+    const int lds[2] = {cd.lda, cd.ldc};
+    for (int n = 0; n < 2 && ce == cudaSuccess; ++n) {
+        ce = cudaMalloc(&h->wt[n], (size_t)H * lds[n] * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->gt[n], (size_t)H * lds[n] * sizeof(float));
+    }
+    if (ce != cudaSuccess) { set_last_cuda_error(ce, "cudaMalloc(compact scratch)", __FILE__, __LINE__); return DCC_ERR_ALLOC; }
+    DCC_CUDA_TRY(cudaMemcpy(h->d_poi, h_poi_xy, sizeof(double) * 2 * n_pois, cudaMemcpyHostToDevice));
+    const size_t smem = compact_features_smem(cd, 8);
+    if (smem > 48 * 1024)
+        DCC_CUDA_TRY(cudaFuncSetAttribute(compact_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->cd = cd;
+    h->compact = true;
+    return DCC_OK;
+}
+
+int dcc_mappo_act_state(void *handle, const float *actor, const float *critic, const double *d_pos_vel, const uint8_t *d_energy,
+                        int n_envs, uint64_t seed, uint64_t offset, int deterministic, float *d_actions, float *d_logp,
+                        float *d_values, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_pos_vel || !d_energy || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
+    if ((actor && !d_actions) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
+    if (!h->compact) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    return policy_forward(h, actor, critic, nullptr, n_envs, 0, seed, offset, deterministic, d_actions, d_logp, d_values,
+                          nullptr, static_cast<cudaStream_t>(stream), d_pos_vel, d_energy);
+}
+
+int dcc_mappo_evaluate_state(void *handle, const float *actor, const float *critic, const double *d_pos_vel,
+                             const uint8_t *d_energy, const float *d_actions, int n_envs, float *d_logp, float *d_values,
+                             float *d_mu, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_pos_vel || !d_energy || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
+    if ((actor && (!d_actions || !d_logp)) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
+    if (!h->compact) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    return policy_forward(h, actor, critic, nullptr, n_envs, 1, 0, 0, 0, const_cast<float *>(d_actions), d_logp, d_values,
+                          d_mu, static_cast<cudaStream_t>(stream), d_pos_vel, d_energy);
+}
+
+int dcc_obs_from_state(void *handle, const double *d_pos_vel, const uint8_t *d_energy, int n_rows, float *d_obs,
+                       dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_pos_vel || !d_energy || !d_obs || n_rows < 1) return DCC_ERR_INVALID_ARG;
+    if (!h->compact) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    obs_from_state_kernel<<<grid_for_rows(h, n_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_pos_vel, d_energy, h->d_poi,
+                                                                                                  d_obs, n_rows, h->cd);
+    DCC_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DCC_OK;
 }
 
 int dcc_rollout_insert(const float *d_rew_in, const uint8_t *d_done_in, int n_envs, int n_agents, float *d_rew_out,
@@ -625,7 +758,8 @@ static PpoLossParams loss_params(const MappoHandle *h, double agent_rows_global)
 // shared prologue of an optimiser step: zero the gradients, ValueNorm.update with the (mini)batch return statistics
 // (cal_value_loss, mappo.py:106-107), entropy statistic, fold the input LayerNorm into fc1 / refresh weight images
 static int grads_prologue(MappoHandle *h, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
-                          float *d_vn_state, const double *ret_sums, double n_ret, double *d_epoch_stats, cudaStream_t s) {
+                          float *d_vn_state, const double *ret_sums, double n_ret, double *d_epoch_stats, cudaStream_t s,
+                          bool cmp = false) {
     DCC_CUDA_TRY(cudaMemsetAsync(grad_actor, 0, h->la.total * sizeof(float), s));
     DCC_CUDA_TRY(cudaMemsetAsync(grad_critic, 0, h->lc.total * sizeof(float), s));
     if (h->cfg.use_valuenorm) {
@@ -635,8 +769,67 @@ static int grads_prologue(MappoHandle *h, const float *actor, const float *criti
     entropy_stat_kernel<<<1, 32, 0, s>>>(actor + h->la.logstd, h->cfg.act_dim, d_epoch_stats + 3);
     h->launches++;
     int rc;
+    if (cmp) {
+        DCC_CUDA_TRY(cudaMemsetAsync(h->gt[0], 0, (size_t)h->la.H * h->cd.lda * sizeof(float), s));
+        DCC_CUDA_TRY(cudaMemsetAsync(h->gt[1], 0, (size_t)h->lc.H * h->cd.ldc * sizeof(float), s));
+        if ((rc = fold_compact(h, h->la, actor, 0, true, s))) return rc;
+        if ((rc = fold_compact(h, h->lc, critic, 1, true, s))) return rc;
+        return DCC_OK;
+    }
     if ((rc = fold_ln0(h, h->la, actor, 0, true, s))) return rc;
     if ((rc = fold_ln0(h, h->lc, critic, 1, true, s))) return rc;
+    return DCC_OK;
+}
+
+static int epoch_grads_impl(MappoHandle *h, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                            const float *d_obs, const double *d_pv, const uint8_t *d_en, const float *d_actions,
+                            const float *d_logp_old, const float *d_values, const float *d_returns, float *d_vn_state,
+                            const double *d_stats4, double n_rows_global, int T, int E, double *d_epoch_stats, cudaStream_t s) {
+    const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
+    const NetLayout &LA = h->la, &LC = h->lc;
+    const bool cmp = d_obs == nullptr;
+    // ValueNorm.update(return_batch) happens inside cal_value_loss, every epoch, before normalising (mappo.py:107)
+    int rc;
+    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_stats4 + 2, n_rows_global, d_epoch_stats, s, cmp)))
+        return rc;
+    const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
+    const PpoLossParams P = loss_params(h, n_rows_global * N);
+    const long R = (long)T * E;
+    const float *fa = cmp ? h->x0 : nullptr, *fcr = cmp ? h->fc : nullptr;
+    for (long r0 = 0; r0 < R; r0 += h->chunk_rows) {
+        const int nr = (int)std::min<long>(h->chunk_rows, R - r0);
+        const float *x = cmp ? nullptr : d_obs + (size_t)r0 * N * D;
+        // compact path: one pass over the chunk's 32 N + M bytes of state per row yields both nets' layer-1 operands
+        if (cmp && (rc = compact_features(h, d_pv + (size_t)r0 * N * 4, d_en + (size_t)r0 * h->cd.M, nr, true, true, s))) return rc;
+        // actor and critic share one activation scratch, so the chunk is processed net by net:
+        // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
+        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda))) return rc;
+        actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
+            h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+            h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
+        h->launches++;
+        ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
+            h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
+            d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
+        h->launches++;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s, fa, h->cd.lda))) return rc;
+        // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
+        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s, nullptr, 1, fcr, h->cd.ldc))) return rc;
+        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
+        h->launches++;
+        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
+                                                              d_epoch_stats, nr, P);
+        h->launches++;
+        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nr, s, fcr, h->cd.ldc))) return rc;
+    }
+    if (cmp) {
+        if ((rc = compact_finalize(h, LA, actor, 0, grad_actor, s))) return rc;
+        if ((rc = compact_finalize(h, LC, critic, 1, grad_critic, s))) return rc;
+    } else {
+        if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
+        if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    }
+    DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
 }
 
@@ -650,44 +843,25 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
     DCC_DEVICE_GUARD(h->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden;
-    const NetLayout &LA = h->la, &LC = h->lc;
-    // ValueNorm.update(return_batch) happens inside cal_value_loss, every epoch, before normalising (mappo.py:107)
-    int rc;
-    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_stats4 + 2, n_rows_global, d_epoch_stats, s)))
-        return rc;
-    const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
-    const PpoLossParams P = loss_params(h, n_rows_global * N);
-    const long R = (long)T * E;
-    for (long r0 = 0; r0 < R; r0 += h->chunk_rows) {
-        const int nr = (int)std::min<long>(h->chunk_rows, R - r0);
-        const float *x = d_obs + (size_t)r0 * N * D;
-        // actor and critic share one activation scratch, so the chunk is processed net by net:
-        // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
-        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s))) return rc;
-        actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
-            h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
-            h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
-        h->launches++;
-        ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
-            h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
-            d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
-        h->launches++;
-        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s))) return rc;
-        // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
-        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s))) return rc;
-        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
-        h->launches++;
-        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
-                                                              d_epoch_stats, nr, P);
-        h->launches++;
-        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nr, s))) return rc;
-    }
-    if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
-    if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
-    DCC_CUDA_TRY(cudaGetLastError());
-    return DCC_OK;
+    return epoch_grads_impl(h, actor, critic, grad_actor, grad_critic, d_obs, nullptr, nullptr, d_actions, d_logp_old, d_values,
+                            d_returns, d_vn_state, d_stats4, n_rows_global, T, E, d_epoch_stats, static_cast<cudaStream_t>(stream));
+}
+
+int dcc_mappo_epoch_grads_state(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                                const double *d_pos_vel, const uint8_t *d_energy, const float *d_actions,
+                                const float *d_logp_old, const float *d_values, const float *d_returns, float *d_vn_state,
+                                const double *d_stats4, double n_rows_global, int T, int E, double *d_epoch_stats,
+                                dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_pos_vel || !d_energy || !d_actions || !d_logp_old ||
+        !d_values || !d_returns || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    if (!h->compact) return DCC_ERR_UNSUPPORTED;     // dcc_mappo_set_env_layout first
+    DCC_DEVICE_GUARD(h->device);
+    return epoch_grads_impl(h, actor, critic, grad_actor, grad_critic, nullptr, d_pos_vel, d_energy, d_actions, d_logp_old,
+                            d_values, d_returns, d_vn_state, d_stats4, n_rows_global, T, E, d_epoch_stats,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int dcc_mappo_minibatch_stats(void *handle, const float *d_returns, const int64_t *d_row_index, int64_t n_index,

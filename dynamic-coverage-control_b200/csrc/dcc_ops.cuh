@@ -349,15 +349,17 @@ __device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float 
 // Backward of h = LN(a)*gamma+beta, a = relu(z+bias):  given dh, a, mean, rstd -> dz (in place over dh allowed),
 // and accumulates dgamma, dbeta, dbias (one set of float atomics per block).  H <= 256, blockDim = 256,
 // dynamic shared memory = 8 * 3 * 256 floats.
-// launch bounds: 4 CTAs per SM (64 registers, 32 bytes of spill) measured 1.8 % faster end to end than 3 (80 registers); the
-// head-fused variant below loses with 3 CTAs (192 bytes of spill) and stays at 2
-__global__ void __launch_bounds__(256, 4) relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
+// Latency, not bandwidth, bounds these one-warp-per-row kernels (a warp has one row = 1-2 KB in flight): the NEXT row's
+// operands are therefore loaded into a second register set before the current row is reduced (software prefetch), which
+// doubles the bytes in flight per warp.  3 CTAs per SM (80 registers) with the prefetch beat 4 CTAs (64) without it.
+__global__ void __launch_bounds__(256, 3) relu_ln_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ a, const float *__restrict__ mean,
                                    const float *__restrict__ rstd, const float *__restrict__ gamma, float *__restrict__ dz,
                                    float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int rows,
                                    int H, int act) {
     extern __shared__ float dyn_sm[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
     float g[8], acc[3][8];   // acc: dgamma, dbeta, dbias
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -365,16 +367,30 @@ __global__ void __launch_bounds__(256, 4) relu_ln_bwd_kernel(const float *__rest
         g[j] = (c < H) ? gamma[c] : 0.f;
         acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
     }
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        const float m = mean[r], rs = rstd[r];
-        float xh[8], dxh[8], av[8];
-        float s1 = 0.f, s2 = 0.f;
+    int r = blockIdx.x * wpb + (threadIdx.x >> 5);
+    float an[8], dn[8], mn = 0.f, rn = 0.f;
+    auto fetch = [&](int row) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
             const bool ok = c < H;
-            av[j] = ok ? a[(size_t)r * H + c] : 0.f;
-            const float d = ok ? dh[(size_t)r * H + c] : 0.f;
+            an[j] = ok ? __ldg(a + (size_t)row * H + c) : 0.f;
+            dn[j] = ok ? __ldg(dh + (size_t)row * H + c) : 0.f;
+        }
+        mn = __ldg(mean + row); rn = __ldg(rstd + row);
+    };
+    if (r < rows) fetch(r);
+    for (; r < rows; r += stride) {
+        const float m = mn, rs = rn;
+        float xh[8], dxh[8], av[8], dv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { av[j] = an[j]; dv[j] = dn[j]; }
+        if (r + stride < rows) fetch(r + stride);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = lane + 32 * j < H;
+            const float d = dv[j];
             xh[j] = ok ? (av[j] - m) * rs : 0.f;
             acc[0][j] = fmaf(d, xh[j], acc[0][j]);
             acc[1][j] += d;
@@ -426,18 +442,36 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_kernel(const float *_
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) acc_bh[o] = 0.f;
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-        const float m = mean[r], rs = rstd[r];
+    // software prefetch of the next row (see relu_ln_bwd_kernel): this kernel runs 2 CTAs per SM, so a warp's single
+    // 1 KB row in flight left HBM at a third of its bandwidth
+    const int stride = gridDim.x * wpb;
+    int r = blockIdx.x * wpb + (threadIdx.x >> 5);
+    float an[8], dn[OUT], mn = 0.f, rn = 0.f;
+    auto fetch = [&](int row) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            an[j] = (c < H) ? __ldg(a + (size_t)row * H + c) : 0.f;
+        }
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dn[o] = __ldg(dout + (size_t)row * OUT + o);
+        mn = __ldg(mean + row); rn = __ldg(rstd + row);
+    };
+    if (r < rows) fetch(r);
+    for (; r < rows; r += stride) {
+        const float m = mn, rs = rn;
         float d[OUT];
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { d[o] = dout[(size_t)r * OUT + o]; acc_bh[o] += d[o]; }
+        for (int o = 0; o < OUT; ++o) { d[o] = dn[o]; acc_bh[o] += d[o]; }
         float xh[8], dxh[8], av[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = an[j];
+        if (r + stride < rows) fetch(r + stride);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
             const bool ok = c < H;
-            av[j] = ok ? a[(size_t)r * H + c] : 0.f;
             xh[j] = ok ? (av[j] - m) * rs : 0.f;
             const float h2 = fmaf(xh[j], g[j], be[j]);
             float dh = 0.f;

@@ -171,18 +171,32 @@ class CudaVecEnv:
             raise ValueError("out_obs must be a contiguous CUDA float32 tensor with E*N*D elements")
         return out_obs
 
-    def reset(self, out_obs=None):
+    def snapshot_state_into(self, pos_vel_out, energy_out):
+        """Device copy of the live compact state into rollout storage: pos_vel_out (E, N, 4) float64, energy_out (E, M)
+        uint8 CUDA tensors (SharedReplayBuffer.state_pv[t] / state_en[t] of a compact rollout)."""
+        if not (pos_vel_out.is_cuda and pos_vel_out.dtype == torch.float64 and pos_vel_out.is_contiguous() and
+                pos_vel_out.numel() == self.n_envs * self.n_agents * 4 and energy_out.is_cuda and
+                energy_out.dtype == torch.uint8 and energy_out.is_contiguous() and
+                energy_out.numel() == self.n_envs * self.n_pois):
+            raise ValueError("snapshot_state_into needs contiguous CUDA tensors (E,N,4) float64 and (E,M) uint8")
+        _lib.check(self.lib.dcc_env_snapshot_state(self._h, self._ptr(pos_vel_out), self._ptr(energy_out), self._stream()),
+                   "dcc_env_snapshot_state")
+
+    def reset(self, out_obs=None, write_obs=True):
         """out_obs (tensor mode): write the observations there instead of the env's own buffer — the rollout
-        storage passes `buffer.obs[0]` so nothing is copied afterwards."""
+        storage passes `buffer.obs[0]` so nothing is copied afterwards.  write_obs=False (compact rollouts): only the
+        state is reset, no observation row is written."""
         if self.numpy_compat:
             hb = self._host_buffers()
             _lib.check(self.lib.dcc_env_reset_host(self._h, hb["obs"].ctypes.data, self._stream()), "dcc_env_reset_host")
             return hb["obs"].astype(np.float64)
-        obs = self._obs_out(out_obs)
+        obs = self._obs_out(out_obs) if write_obs else None
         _lib.check(self.lib.dcc_env_reset(self._h, self._ptr(obs), self._stream()), "dcc_env_reset")
         return obs
 
-    def step(self, actions, out_obs=None):
+    def step(self, actions, out_obs=None, write_obs=True):
+        """write_obs=False (compact rollouts, tensor mode): the step updates the state, rewards, dones and infos but
+        writes no observation rows (returned obs is None) — the learner reads the compact state instead."""
         if self.numpy_compat:
             return self._step_numpy(actions)
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32):
@@ -190,13 +204,13 @@ class CudaVecEnv:
         if actions.numel() != self.n_envs * self.n_agents * 2:
             raise ValueError("actions has %d elements, expected E*N*2 = %d" % (actions.numel(), self.n_envs * self.n_agents * 2))
         actions = actions.contiguous()
-        obs = self._obs_out(out_obs)
+        obs = self._obs_out(out_obs) if write_obs else None
         _lib.check(self.lib.dcc_env_step(self._h, self._ptr(actions), self._ptr(obs), self._ptr(self.rewards),
                                          self._ptr(self.dones_u8), self._ptr(self.coverage_rate),
                                          self._ptr(self.connect_bits), self._ptr(self.adj), self._ptr(self.adj_s),
                                          self._stream()), "dcc_env_step")
-        return obs.view(self.n_envs, self.n_agents, self.obs_dim), self.rewards, self.dones_u8.view(torch.bool), \
-            CoverageInfos(self.coverage_rate)
+        return (None if obs is None else obs.view(self.n_envs, self.n_agents, self.obs_dim)), self.rewards, \
+            self.dones_u8.view(torch.bool), CoverageInfos(self.coverage_rate)
 
     def step_async(self, actions):
         self._pending = actions

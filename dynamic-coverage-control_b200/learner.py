@@ -72,17 +72,25 @@ class Learner:
             self.comm.broadcast_(self.policy.critic.params)
             self.policy.seed = int(cfg.seed) + 7919 * self.comm.rank   # independent exploration noise per shard
 
-        # 3. rollout storage
-        self.rl_buffer = SharedReplayBuffer(local, self.train_envs.observation_space[0], self.share_observation_space,
-                                            self.train_envs.action_space[0], device=self.train_envs.device)
+        # 3. rollout storage.  Compact whenever the path allows it: the rollout keeps the env's compact
+        # state (320 B per env step at 8/64 instead of 10.8 KB of observation rows) and the learner kernels evaluate
+        # the first layer from it.  `compact_rollout: false` forces the materialised (T+1, E, N, D) observation tensor;
+        # num_mini_batch > 1, per-env PoI layouts and a decentralised critic need it and select it automatically.
+        want = getattr(cfg, "compact_rollout", None)
+        can = (getattr(cfg, "use_centralized_V", True) and int(cfg.num_mini_batch) == 1 and
+               self.train_envs.pos_pois_per_env is None and not getattr(cfg, "numpy_compat", False))
+        if want and not can:
+            raise NotImplementedError("compact_rollout needs use_centralized_V, num_mini_batch 1 and a shared PoI layout")
+        self.compact = bool(can if want is None else want)
+        if self.compact:
+            self.compact = self.policy.set_env_layout(self.train_envs.pos_pois, self.train_envs.cfg.m_energy)
+        self.rl_buffer = self._make_buffer(local)
         self.rl_buffer.n_envs_global = self.n_envs_global
         if cfg.n_eval_rollout_threads > 0:
             test_cfg = copy.copy(cfg)
             test_cfg.n_rollout_threads = cfg.n_eval_rollout_threads
             self.test_envs = make_env(test_cfg)
-            self.test_buffer = SharedReplayBuffer(test_cfg, self.train_envs.observation_space[0],
-                                                  self.share_observation_space, self.train_envs.action_space[0],
-                                                  device=self.train_envs.device)
+            self.test_buffer = self._make_buffer(test_cfg)
         self.render_interval = int(getattr(cfg, "render_interval", 0) or 0)
         self.save_gifs = bool(getattr(cfg, "save_gifs", False))
         self.n_render = int(getattr(cfg, "n_render_rollout_threads", 0) or 0) if self.comm.rank == 0 else 0
@@ -92,9 +100,7 @@ class Learner:
             render_cfg.n_rollout_threads = self.n_render
             self.render_envs = make_env(render_cfg)
             self.render_envs.enable_connectivity_outputs()
-            self.render_buffer = SharedReplayBuffer(render_cfg, self.train_envs.observation_space[0],
-                                                    self.share_observation_space, self.train_envs.action_space[0],
-                                                    device=self.train_envs.device)
+            self.render_buffer = self._make_buffer(render_cfg)
         self.last_trajectory = None
 
         # 4. train-loop parameters
@@ -115,6 +121,14 @@ class Learner:
         self._start_time = time.time()
         self._check_time = time.time()
         self.agent_steps = 0
+
+    def _make_buffer(self, cfg):
+        buf = SharedReplayBuffer(cfg, self.train_envs.observation_space[0], self.share_observation_space,
+                                 self.train_envs.action_space[0], device=self.train_envs.device, compact=self.compact,
+                                 n_pois=self.train_envs.n_pois)
+        if self.compact:
+            buf.attach_policy(self.policy)
+        return buf
 
     def train(self):
         self.warmup(self.rl_buffer, self.train_envs)
@@ -159,7 +173,11 @@ class Learner:
             rec = TrajectoryRecorder(r_envs.pos_pois, r_envs.cfg.r_cover, r_envs.cfg.r_comm)
         for cur_step in range(self.max_ep_len):
             actions = self.collect(cur_step, r_buffer)
-            obs, rewards, dones, infos = r_envs.step(actions, out_obs=r_buffer.obs[cur_step + 1])
+            if r_buffer.compact:     # no observation rows: the step's compact state goes to slot t+1 of the rollout
+                obs, rewards, dones, infos = r_envs.step(actions, write_obs=False)
+                r_envs.snapshot_state_into(r_buffer.state_pv[cur_step + 1], r_buffer.state_en[cur_step + 1])
+            else:
+                obs, rewards, dones, infos = r_envs.step(actions, out_obs=r_buffer.obs[cur_step + 1])
             self.insert((obs, rewards, dones, infos), r_buffer, r_envs)
             rew_sum += rewards.mean()
             torch.maximum(sr, infos.coverage_rate, out=sr)
@@ -180,15 +198,22 @@ class Learner:
         return {"reward": out[0], "coverage_rate": out[1], "connect_rate": out[2]}
 
     def warmup(self, r_buffer, r_envs):
-        r_envs.reset(out_obs=r_buffer.obs[0])
+        if r_buffer.compact:
+            r_envs.reset(write_obs=False)
+            r_envs.snapshot_state_into(r_buffer.state_pv[0], r_buffer.state_en[0])
+        else:
+            r_envs.reset(out_obs=r_buffer.obs[0])
 
     def collect(self, cur_step, r_buffer):
         """learner.py:227-252: policy forward on step `cur_step`'s observations; actions, log-probs and values land
         in the buffer slices directly.  Returns the action tensor (E, N, 2) for the env."""
         self.trainer.prep_rollout()
-        self.trainer.policy.get_actions(None, r_buffer.obs[cur_step], out_actions=r_buffer.actions[cur_step],
-                                        out_logp=r_buffer.action_log_probs_ten[cur_step],
-                                        out_values=r_buffer.values_te[cur_step])
+        outs = dict(out_actions=r_buffer.actions[cur_step], out_logp=r_buffer.action_log_probs_ten[cur_step],
+                    out_values=r_buffer.values_te[cur_step])
+        if r_buffer.compact:
+            self.trainer.policy.get_actions_state(r_buffer.state_pv[cur_step], r_buffer.state_en[cur_step], **outs)
+        else:
+            self.trainer.policy.get_actions(None, r_buffer.obs[cur_step], **outs)
         return r_buffer.actions[cur_step]
 
     def insert(self, data, r_buffer, r_envs=None):
@@ -200,7 +225,10 @@ class Learner:
         """learner.py:278-287: bootstrap value from the last observations, then GAE."""
         self.trainer.prep_rollout()
         T = r_buffer.episode_length
-        self.trainer.policy.get_values(r_buffer.obs[T], out_values=r_buffer.values_te[T])
+        if r_buffer.compact:
+            self.trainer.policy.get_values_state(r_buffer.state_pv[T], r_buffer.state_en[T], out_values=r_buffer.values_te[T])
+        else:
+            self.trainer.policy.get_values(r_buffer.obs[T], out_values=r_buffer.values_te[T])
         r_buffer.compute_returns(None, self.trainer.value_normalizer, policy=self.policy)
 
     # ---- update ------------------------------------------------------------------------------------------------

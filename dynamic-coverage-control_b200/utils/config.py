@@ -31,7 +31,7 @@ DEFAULTS = dict(
     log_interval=1, save_model=True, load_model=False, load_buffer_path=None, main_save_path="results/",
     load_model_path="results/dcc/xxxx_xxxx_sdx/models_xxx.pt", hidden_sizes_mlp=[64], lr=5e-4,
     # new optional keys of the B200 build
-    reference_compat=True, pos_pois_path=None, poi_layout=None, per_env_layouts=False, poi_seed=0, device=0, chunk_rows=0, gemm_backend=0,
+    reference_compat=True, pos_pois_path=None, poi_layout=None, compact_rollout=None, per_env_layouts=False, poi_seed=0, device=0, chunk_rows=0, gemm_backend=0,
 )
 
 _FLOAT = re.compile(r"^[-+]?(\d+\.?\d*|\.\d+)([eE][-+]?\d+)?$")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 5
+#define DCC_ABI_VERSION 6
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -154,6 +154,11 @@ int dcc_env_set_state(void *handle, const double *h_pos_vel, const uint8_t *h_en
 /* Device pointers to the live compact state (for the rollout storage and for in-place checkpoints). */
 int dcc_env_state_ptrs(void *handle, double **d_pos_vel, uint8_t **d_energy);
 
+/* Device-to-device copy of the live compact state into caller-owned rollout storage (slot t+1 of the compact rollout,
+ * see "compact-state learner path" below): d_pos_vel_out [E, N, 4] float64, d_energy_out [E, M] uint8.  Asynchronous on
+ * `stream`.  Replaces the obs / share_obs copies of SharedReplayBuffer.insert (buffer/shared_buffer.py:72-80). */
+int dcc_env_snapshot_state(void *handle, double *d_pos_vel_out, uint8_t *d_energy_out, dcc_stream_t stream);
+
 /* Launch geometry knobs (tuning / tests).  warps_per_cta in {1,2,4,8,16}; ctas <= 0 = auto. */
 int dcc_env_set_launch(void *handle, int warps_per_cta, int ctas);
 /* (N, M) shapes with a compile-time specialised kernel (4/20, 8/64, 16/256) use it by default; enable = 0 forces the
@@ -255,6 +260,37 @@ int dcc_mappo_act(void *handle, const float *d_actor, const float *d_critic, con
  */
 int dcc_mappo_evaluate(void *handle, const float *d_actor, const float *d_critic, const float *d_obs,
                        const float *d_actions, int n_envs, float *d_logp, float *d_values, float *d_mu,
+                       dcc_stream_t stream);
+
+/*
+ * ---- compact-state learner path ("compact-state storage + obs regeneration") ----------------------
+ * The observation rows SharedReplayBuffer stores (buffer/shared_buffer.py:15-70: obs [T+1, E, N, D] and share_obs
+ * [T+1, E, N, N*D]) are an affine function of the env's compact state (scenarios/coverage.py:99-110), so the rollout
+ * keeps only that state — pos_vel [rows, N, 4] float64 and energy [rows, M] uint8, 32 N + M bytes per env step instead
+ * of 4 N D — and the first layer of both nets is evaluated from it directly: xhat W1^T = f (W1 A)^T with f the
+ * LayerNorm-scaled state features (csrc/dcc_compact.cuh; exact algebra, pinned by oracle/compact_oracle.py).
+ *   dcc_mappo_set_env_layout    gives the learner handle the env's PoI table (host, M x 2 float64) and m_energy; required
+ *                               before any *_state call.  DCC_ERR_UNSUPPORTED unless obs_dim == 2N + 2 + 5M and the critic
+ *                               is centralised (use_centralized_V), the only layouts the identity covers.
+ *   dcc_mappo_act_state         dcc_mappo_act            with (d_pos_vel, d_energy) in place of d_obs
+ *   dcc_mappo_evaluate_state    dcc_mappo_evaluate       likewise
+ *   dcc_mappo_epoch_grads_state dcc_mappo_epoch_grads    likewise (rows = T*E env steps, time-major like the obs buffer)
+ *   dcc_obs_from_state          regenerates the observation rows [n_rows, N, D] float32, bit-identical to dcc_env_step's
+ *                               (the reference-shaped view `buffer.obs[t]` of a compact rollout)
+ */
+int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, double m_energy);
+int dcc_mappo_act_state(void *handle, const float *d_actor, const float *d_critic, const double *d_pos_vel,
+                        const uint8_t *d_energy, int n_envs, uint64_t seed, uint64_t offset, int deterministic,
+                        float *d_actions, float *d_logp, float *d_values, dcc_stream_t stream);
+int dcc_mappo_evaluate_state(void *handle, const float *d_actor, const float *d_critic, const double *d_pos_vel,
+                             const uint8_t *d_energy, const float *d_actions, int n_envs, float *d_logp, float *d_values,
+                             float *d_mu, dcc_stream_t stream);
+int dcc_mappo_epoch_grads_state(void *handle, const float *d_actor, const float *d_critic, float *d_grad_actor,
+                                float *d_grad_critic, const double *d_pos_vel, const uint8_t *d_energy,
+                                const float *d_actions, const float *d_logp_old, const float *d_values,
+                                const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global,
+                                int T, int E, double *d_epoch_stats, dcc_stream_t stream);
+int dcc_obs_from_state(void *handle, const double *d_pos_vel, const uint8_t *d_energy, int n_rows, float *d_obs,
                        dcc_stream_t stream);
 
 /*

@@ -1,0 +1,223 @@
+"""GPU parity tests of the compact-state learner path (include/dcc_b200.h "compact-state learner
+path"): the rollout stores the env's compact state and the first layer of both nets is evaluated from it.
+
+Checked: (1) observation rows regenerated from the state are bit-identical to the env kernel's; (2) forward and the
+whole PPO update agree with the materialised-observation path on the same rollout and with the golden vectors recorded
+from the UNMODIFIED reference learner (same tolerances as tests/test_mappo_cuda.py); (3) the re-hosted Learner picks the
+compact storage by itself and its `buffer.obs[t]` view regenerates the reference-shaped observations.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mappo_util import make_params, net_shapes
+from test_mappo_cuda import BACKENDS, build, check_params, fill_buffer, load, make_cfg
+from oracle import compact_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+# goldens the compact path covers: centralised critic, one minibatch per epoch (any other switch allowed)
+COMPACT_CASES = ["ship_4x20_h256", "gen_8x64_h256", "gen_8x64_h64", "gen_3x20_h32", "flags_mse_noclip_wd", "flags_novn_gae",
+                 "net_tanh_nofn_h32", "net_layer2_h256"]
+
+
+def build_compact(c, E, T, poi, **over):
+    import torch
+    from dcc_b200.algos import MAPPOPolicy, MAPPOTrainer
+    from dcc_b200.buffer import SharedReplayBuffer
+    from dcc_b200.envs.spaces import Box
+    cfg = make_cfg(c, E, T, device=0, **over)
+    N, D, M = c["n_agents"], c["obs_dim"], c["n_pois"]
+    spaces = (Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,)))
+    pol = MAPPOPolicy(cfg, *spaces)
+    a_shapes, c_shapes = net_shapes(c)
+    pol.actor.load_state_dict(make_params(a_shapes, c["actor_seed"]))
+    pol.critic.load_state_dict(make_params(c_shapes, c["critic_seed"]))
+    assert pol.set_env_layout(poi)
+    tr = MAPPOTrainer(cfg, pol)
+    buf = SharedReplayBuffer(cfg, *spaces, compact=True, n_pois=M)
+    buf.attach_policy(pol)
+    torch.cuda.synchronize()
+    return cfg, pol, tr, buf
+
+
+def fill_compact(buf, g, p, N, M):
+    import torch
+    dev = buf.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    pv, en = co.state_from_obs(g[p + "obs"], N, M)
+    buf.state_pv.copy_(t(pv))
+    buf.state_en.copy_(t(en))
+    buf.actions.copy_(t(g[p + "actions"]))
+    buf.action_log_probs_ten.copy_(t(g[p + "logp"][..., 0]))
+    buf.values_te.copy_(t(g[p + "value_preds"][:, :, 0, 0]))
+    buf.rewards_te.copy_(t(g[p + "rewards"][:, :, 0, 0]))
+    buf.masks_te.copy_(t(g[p + "masks"][:, :, 0, 0]))
+
+
+@pytest.mark.parametrize("N,M,E,force", [(8, 64, 512, 0.0), (4, 20, 300, 1.0), (16, 256, 64, 1.0), (3, 7, 130, 1.0), (1, 5, 40, 0.0)])
+def test_obs_from_state_is_bit_identical_to_the_env_kernel(N, M, E, force):
+    import torch
+    from dcc_b200.envs import CudaVecEnv
+    rng = np.random.default_rng(N * 31 + M)
+    poi = rng.uniform(-1, 1, (M, 2))
+    env = CudaVecEnv(E, N, M, comm_force_scale=force, reference_compat=False, pos_pois=poi)
+    D = env.obs_dim
+    c = dict(n_agents=N, n_pois=M, hidden=32, obs_dim=D, ppo_epoch=1, seed=0, n_iters=1, actor_seed=1, critic_seed=2)
+    cfg, pol, tr, buf = build_compact(c, E, 2, poi)
+    pv = torch.empty((E, N, 4), dtype=torch.float64, device="cuda")
+    en = torch.empty((E, M), dtype=torch.uint8, device="cuda")
+    obs = env.reset().clone()
+    env.snapshot_state_into(pv, en)
+    assert torch.equal(pol.obs_from_state(pv, en), obs)
+    for t in range(25):
+        a = torch.from_numpy((rng.standard_normal((E, N, 2)) * 1.5).astype(np.float32)).cuda()
+        obs, rew, done, infos = env.step(a)
+        env.snapshot_state_into(pv, en)
+        assert torch.equal(pol.obs_from_state(pv, en), obs), t
+    # a step that writes no observations leaves the same state behind as one that does
+    env2 = CudaVecEnv(E, N, M, comm_force_scale=force, reference_compat=False, pos_pois=poi)
+    env2.reset(write_obs=False)
+    env.reset()
+    for t in range(5):
+        a = torch.from_numpy((rng.standard_normal((E, N, 2)) * 1.5).astype(np.float32)).cuda()
+        o1, r1, d1, _ = env.step(a)
+        o2, r2, d2, _ = env2.step(a, write_obs=False)
+        assert o2 is None and torch.equal(r1, r2) and torch.equal(d1, d2)
+    s1, s2 = env.get_state(), env2.get_state()
+    assert np.array_equal(s1[0], s2[0]) and np.array_equal(s1[1], s2[1])
+    env.close()
+    env2.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", COMPACT_CASES)
+def test_compact_learner_vs_reference_golden(name, backend):
+    """The teacher-forced replay of tests/test_mappo_cuda.py::test_learner_vs_reference_golden with the rollout held as
+    compact state (recovered from the recorded observations: positions to float32, energies exactly)."""
+    import torch
+    g = load(name)
+    c = g["cfg"]
+    N, D, M = c["n_agents"], c["obs_dim"], c["n_pois"]
+    T, E = g["it1_actions"].shape[:2]
+    from dcc_b200.envs.cuda_vec_env import reference_pois
+    cfg, pol, tr, buf = build_compact(c, E, T, reference_pois(M), gemm_backend=backend)
+    use_vn = c.get("use_valuenorm", True)
+    for it in range(1, c["iters"] + 1):
+        p = "it%d_" % it
+        fill_compact(buf, g, p, N, M)
+        ftol = 1e-5 if it == 1 else 1e-4       # see test_learner_vs_reference_golden
+        v, logp, ent = pol.evaluate_actions_state(buf.state_pv[:-1], buf.state_en[:-1], buf.actions)
+        assert np.allclose(logp.cpu().numpy().reshape(T, E, N, 1), g[p + "logp"], rtol=ftol, atol=ftol)
+        vals = pol.get_values_state(buf.state_pv, buf.state_en).cpu().numpy().reshape(T + 1, E, N, 1)
+        assert np.allclose(vals, g[p + "value_preds"], rtol=ftol, atol=ftol)
+        # the lazy reference-shaped view regenerates the recorded observations (positions are float32 here: <= 1 ulp)
+        assert np.abs(buf.obs[3].cpu().numpy() - g[p + "obs"][3]).max() <= 1.2e-7
+        buf.compute_returns(None, tr.value_normalizer, policy=pol)
+        ref_all = g[p + "returns"][:, :, 0, 0]
+        assert np.allclose(buf.returns_te.cpu().numpy()[:-1], ref_all[:-1], rtol=1e-5, atol=1e-4)
+        buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(ref_all)).to(buf.device))
+        pol.lr_decay(it, c["n_iters"])
+        info = tr.train(buf)
+        ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
+                       g[p + "train_info"]))
+        for k in ref:
+            assert abs(info[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (it, k, info[k], ref[k])
+        if use_vn:
+            assert np.allclose(tr.value_normalizer.state.cpu().numpy()[:3], g[p + "vn_after"], rtol=1e-5, atol=1e-12)
+        check_params("actor it%d" % it, pol.actor, g, p + "actor.")
+        check_params("critic it%d" % it, pol.critic, g, p + "critic.")
+        buf.after_update()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("N,M,Hd,E,T,chunk", [(8, 64, 256, 40, 12, 0), (8, 64, 256, 40, 12, 96), (4, 20, 64, 33, 9, 50),
+                                              (16, 40, 256, 10, 6, 0)])
+def test_compact_update_equals_materialised_update(N, M, Hd, E, T, chunk, backend):
+    """Same rollout (states from a real env run, random actions / old log-probs / returns), same parameters: the compact
+    and the materialised paths give the same forward outputs, losses and post-Adam parameters to float32 round-off —
+    also when the rollout spans several activation chunks."""
+    import torch
+    from dcc_b200.envs import CudaVecEnv
+    rng = np.random.default_rng(N + M + E)
+    poi = rng.uniform(-1, 1, (M, 2))
+    D = 4 + 2 * (N - 1) + 5 * M
+    c = dict(n_agents=N, n_pois=M, hidden=Hd, obs_dim=D, ppo_epoch=3, seed=5, n_iters=10, actor_seed=31, critic_seed=32)
+    cfg_m, pol_m, tr_m, buf_m = build(c, E, T, gemm_backend=backend, chunk_rows=chunk)
+    cfg_c, pol_c, tr_c, buf_c = build_compact(c, E, T, poi, gemm_backend=backend, chunk_rows=chunk)
+    env = CudaVecEnv(E, N, M, pos_pois=poi)
+    env.reset(out_obs=buf_m.obs[0])
+    env.snapshot_state_into(buf_c.state_pv[0], buf_c.state_en[0])
+    for t in range(T):
+        a = torch.from_numpy((rng.standard_normal((E, N, 2)) * 1.2).astype(np.float32)).cuda()
+        env.step(a, out_obs=buf_m.obs[t + 1])
+        env.snapshot_state_into(buf_c.state_pv[t + 1], buf_c.state_en[t + 1])
+        for b in (buf_m, buf_c):
+            b.actions[t].copy_(a)
+    assert torch.equal(buf_c.obs[0:T + 1], buf_m.obs)
+    # forward: sampled actions use the same Philox stream; log-probs / values agree to float32 round-off
+    vm, am, lm, _, _ = pol_m.get_actions(None, buf_m.obs[2])
+    vc, ac, lc, _, _ = pol_c.get_actions_state(buf_c.state_pv[2], buf_c.state_en[2])
+    assert torch.allclose(am, ac, rtol=1e-5, atol=2e-6) and torch.allclose(lm, lc, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(vm, vc, rtol=1e-5, atol=3e-6)
+    vm, lm, _ = pol_m.evaluate_actions(None, buf_m.obs[:-1], None, None, buf_m.actions)
+    vc, lc, _ = pol_c.evaluate_actions_state(buf_c.state_pv[:-1], buf_c.state_en[:-1], buf_c.actions)
+    assert torch.allclose(lm, lc, rtol=1e-5, atol=1e-5) and torch.allclose(vm, vc, rtol=1e-5, atol=3e-6)
+    lp_old = lm.reshape(T, E, N) + torch.from_numpy(rng.normal(0, 0.2, (T, E, N)).astype(np.float32)).cuda()
+    vals = torch.from_numpy(rng.normal(0, 1.0, (T + 1, E)).astype(np.float32)).cuda()
+    rew = torch.from_numpy(rng.normal(0, 30.0, (T, E)).astype(np.float32)).cuda()
+    masks = torch.from_numpy((rng.random((T + 1, E)) > 0.1).astype(np.float32)).cuda()
+    infos = []
+    for pol, tr, buf in ((pol_m, tr_m, buf_m), (pol_c, tr_c, buf_c)):
+        buf.action_log_probs_ten.copy_(lp_old)
+        buf.values_te.copy_(vals)
+        buf.rewards_te.copy_(rew)
+        buf.masks_te.copy_(masks)
+        tr.value_normalizer.state[:3] = torch.tensor([0.3, 4.0, 0.02], device=buf.device)
+        buf.compute_returns(None, tr.value_normalizer, policy=pol)
+        pol.lr_decay(3, 10)
+        infos.append(tr.train(buf))
+    for k in infos[0]:
+        assert abs(infos[0][k] - infos[1][k]) <= 2e-5 * max(1.0, abs(infos[0][k])), (k, infos[0][k], infos[1][k])
+    for tag, a, b in (("actor", pol_m.actor, pol_c.actor), ("critic", pol_m.critic, pol_c.critic)):
+        for k in a.layout:
+            x, y = a.view(k).cpu().numpy().astype(np.float64), b.view(k).cpu().numpy().astype(np.float64)
+            bad = np.abs(x - y) > 1e-5 + 2e-5 * np.abs(y)
+            # a ReLU derivative flipped by round-off moves a handful of elements by O(lr) (see test_update_vs_oracle_random_batch)
+            assert bad.mean() <= 2e-3 and np.abs(x - y).max() <= 3 * 2 * pol_m.lr_actor_now, (tag, k, bad.mean(), np.abs(x - y).max())
+    env.close()
+
+
+def test_learner_uses_compact_rollout_by_default_and_regenerates_observations():
+    import torch
+    from dcc_b200.learner import Learner
+    from dcc_b200.utils.config import load_config
+    cfg = load_config(None, num_agents=4, num_pois=20, n_rollout_threads=64, max_ep_len=20, ppo_epoch=2, n_iters=3,
+                      n_eval_rollout_threads=0, n_render_rollout_threads=0, save_model=False)
+    lr = Learner(cfg)
+    assert lr.compact and lr.rl_buffer.compact and not hasattr(lr.rl_buffer.obs, "data_ptr")
+    ri = lr.rollout(lr.rl_buffer, lr.train_envs)
+    ti = lr.rl_update()
+    assert all(np.isfinite(v) for v in list(ri.values()) + list(ti.values()))
+    # the reference-shaped view: obs[0] is the reset observation, obs[t] a function of the stored state
+    obs0 = lr.rl_buffer.obs[0]
+    assert obs0.shape == (64, 4, lr.rl_buffer.obs_dim) and lr.rl_buffer.obs.shape == (21, 64, 4, lr.rl_buffer.obs_dim)
+    pv = lr.rl_buffer.state_pv.cpu().numpy()
+    en = lr.rl_buffer.state_en.cpu().numpy()
+    want = co.obs_rows(pv[7], en[7], lr.train_envs.pos_pois)
+    assert np.array_equal(lr.rl_buffer.obs[7].cpu().numpy(), want)
+    assert lr.rl_buffer.share_obs.shape == (21, 64, 4, 4 * lr.rl_buffer.obs_dim)
+    # the same config with the materialised buffer learns the same thing: identical rollout statistics on the first
+    # iteration (same seeds, same Philox stream) up to float32 round-off in the sampled actions
+    cfg2 = load_config(None, num_agents=4, num_pois=20, n_rollout_threads=64, max_ep_len=20, ppo_epoch=2, n_iters=3,
+                       n_eval_rollout_threads=0, n_render_rollout_threads=0, save_model=False, compact_rollout=False)
+    lr2 = Learner(cfg2)
+    assert not lr2.compact and isinstance(lr2.rl_buffer.obs, torch.Tensor)
+    ri2 = lr2.rollout(lr2.rl_buffer, lr2.train_envs)
+    assert abs(ri2["reward"] - ri["reward"]) <= 0.02 * abs(ri["reward"]) and abs(ri2["coverage_rate"] - ri["coverage_rate"]) < 0.02
+    # switches that need observation rows fall back to the materialised buffer by themselves
+    cfg3 = load_config(None, num_agents=4, num_pois=20, n_rollout_threads=8, max_ep_len=6, ppo_epoch=1, n_iters=2,
+                       n_eval_rollout_threads=0, n_render_rollout_threads=0, save_model=False, num_mini_batch=2)
+    assert not Learner(cfg3).compact

@@ -22,10 +22,11 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--backend", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--compact", type=int, default=-1, help="1 / 0 = compact / materialised rollout storage (default: auto)")
     a = ap.parse_args()
     cfg = load_config(None, num_agents=a.n, num_pois=a.m, n_rollout_threads=a.envs, max_ep_len=a.T, ppo_epoch=a.epochs,
                       n_iters=a.iters + 1, n_eval_rollout_threads=0, save_model=False, gemm_backend=a.backend,
-                      chunk_rows=a.chunk)
+                      chunk_rows=a.chunk, poi_layout="synthetic", compact_rollout=None if a.compact < 0 else bool(a.compact))
     lr = Learner(cfg)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     out = []
@@ -42,7 +43,7 @@ def main():
         out.append(dict(iter=it, rollout_ms=r_ms, update_ms=u_ms, agent_steps_per_s=steps / ((r_ms + u_ms) * 1e-3),
                         rollout_info=ri, value_loss=ti["value_loss"], ratio=ti["ratio"]))
         print(json.dumps(out[-1]), flush=True)
-    print(json.dumps(dict(backend=lr.policy.gemm_backend(), chunk_rows=lr.policy.lib.dcc_mappo_chunk_rows(lr.policy._h),
+    print(json.dumps(dict(backend=lr.policy.gemm_backend(), compact=lr.compact, chunk_rows=lr.policy.lib.dcc_mappo_chunk_rows(lr.policy._h),
                           launches=lr.policy.launch_count())))
 
 
