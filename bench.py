@@ -1,25 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — agent-steps/s of the env hot path at 8 UAV / 64 PoI / 65 536 envs per GPU (BASELINE.json).
+"""bench.py — agent-steps/s of the env hot path at 8 UAV / 64 PoI / 65 536 envs per GPU (BASELINE.json), with the full
+MAPPO loop (configs[3] / [4]) measured in the same run.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU arm (oracle port, all host threads)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference on the host cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # one rank per GPU, envs sharded (weak scaling)
 
 Workloads (`--workload`):
   env    (default, the BASELINE.json metric: configs[1]) one "step" = one `env.step` of all E env instances of a rank
-         (one kernel launch);
-  mappo  (BASELINE configs[3] / [4]) one "step" = one full MAPPO iteration at 65 536 envs per GPU: 150-step rollout
-         (policy forward + env step + insert), GAE, 15-epoch PPO update; under torchrun the env axis is sharded and
-         the flat gradient is all-reduced over NCCL once per epoch.  Default --steps 2 --warmup 3 (~2 min).
+         (one kernel launch).  The line also carries `full_loop`: ONE timed iteration (after one warm-up iteration) of the
+         full MAPPO loop at 65 536 envs per GPU — 150-step rollout, GAE, 15-epoch PPO update, and under torchrun the NCCL
+         all-reduce of the flat gradient once per epoch (configs[3] on 1 GPU, configs[4] sharded) — so that the driver's
+         BENCH / SCALE runs exercise the learner and the collective too (`--no-full-loop` skips it);
+  env16  BASELINE configs[2]: 16 UAV / 256 PoI / 32 768 envs, connectivity force on, env step only;
+  mappo  the full loop as the line's own metric (one "step" = one iteration; default --steps 2 --warmup 3).
 Prints ONE JSON line:
   value        whole-job agent-steps/s, inputs (actions) resident in HBM, device-timed with CUDA events
   e2e          same metric through the host-buffer C entry point `dcc_env_step_host` (numpy in / numpy out):
                pinned H2D of the actions and D2H of obs/reward/done/coverage inside the timed region
   roofline     algorithmic bytes per launch / average launch time vs the measured HBM copy bandwidth
-  cpu_baseline the CPU oracle port (oracle/dcc_env_oracle.c) timed on this box's host cores, bounded sample
-The reference itself is pure Python and /root/reference does not exist on the GPU box, so the CPU arm is the
-C port of its algorithm (kind "port"); the unmodified reference's own numbers measured in the build container
-are in BASELINE.md §2.
+  cpu_baseline the CPU oracle port (oracle/dcc_env_oracle.c, kind "port") timed on this box's host cores, bounded
+               sample; `cpu_baseline.python_reference` = the UNMODIFIED Python reference itself timed on the same cores
+               in the same run (baseline/run_reference.py: SubprocVecEnv x cpu_count env-only at 8/64, and the shipped
+               4/20 full loop), from /root/reference or the verbatim copy under baseline/_ref
+  full_loop    see above
+`--impl reference` times the unmodified Python reference (kind "reference"; the C port's number rides along).
 """
 import argparse
 import json
@@ -116,14 +121,18 @@ class ClockSampler:
         return out
 
 
-def time_cpu_port(n_envs, steps, warmup, threads, seed=0):
+def time_cpu_port(n_envs, steps, warmup, threads, seed=0, N=N_AGENTS, M=N_POIS, env_kw=None):
     """Times the CPU oracle port (test infrastructure; here only as the measured CPU baseline)."""
     from oracle.env_oracle import OracleEnv
     from dcc_b200.envs.cuda_vec_env import synthetic_pois
-    env = OracleEnv(n_envs, N_AGENTS, N_POIS, synthetic_pois(N_POIS), comm_r_scale=0.9, contact_force=0.0,
-                    n_threads=threads)
+    env_kw = env_kw or {}
+    if env_kw.get("reference_compat", True):       # shipped semantics: the world ignores the scenario's comm arguments
+        crs, force = 0.9, 0.0
+    else:
+        crs, force = env_kw.get("comm_r_scale", 0.95), 100.0 * env_kw.get("comm_force_scale", 0.0)
+    env = OracleEnv(n_envs, N, M, synthetic_pois(M), comm_r_scale=crs, contact_force=force, n_threads=threads)
     rng = np.random.default_rng(seed)
-    acts = [rng.standard_normal((n_envs, N_AGENTS, 2)).astype(np.float32) for _ in range(4)]
+    acts = [rng.standard_normal((n_envs, N, 2)).astype(np.float32) for _ in range(4)]
     env.reset()
     for t in range(warmup):
         env.step(acts[t % 4], want_aux=False)
@@ -131,30 +140,92 @@ def time_cpu_port(n_envs, steps, warmup, threads, seed=0):
     for t in range(steps):
         env.step(acts[t % 4], want_aux=False)
     dt = time.perf_counter() - t0
-    return n_envs * N_AGENTS * steps / dt, dt
+    return n_envs * N * steps / dt, dt
+
+
+def time_python_reference(what, timeout_s=420, **kw):
+    """Runs baseline/run_reference.py (the UNMODIFIED Python reference behind the stub shim) in a subprocess on the
+    host cores and returns its JSON record, or {"unavailable": why}."""
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), what]
+    for k, v in kw.items():
+        cmd += ["--" + k, str(v)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):   # not a torchrun worker
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""        # the reference's CPU path (ptu.set_gpu_mode(False))
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+        lines = [l for l in res.stdout.strip().splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"unavailable": "run_reference.py %s failed (rc %d): %s" % (what, res.returncode, res.stderr.strip()[-300:])}
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "run_reference.py %s exceeded %d s" % (what, timeout_s)}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": repr(e)}
+
+
+def python_reference_record(env_steps=150, loop_iters=2, n=N_AGENTS, m=N_POIS):
+    """cpu_baseline.python_reference: SURVEY.md §8d (i) env-only at the benchmarked shape with SubprocVecEnv x cpu_count,
+    (ii) the shipped 4 UAV / 20 PoI full loop (16 SubprocVecEnv workers, T = 150, 15 epochs)."""
+    cores = os.cpu_count() or 1
+    out = {"cores": cores, "kind": "reference",
+           "how": "unmodified reference sources (baseline/run_reference.py; stub shim for gym/imp/omegaconf/imageio/wandb; "
+                  "make_world's 4/20 literals lifted for 8/64)"}
+    out["env_only"] = time_python_reference("env", n=n, m=m, procs=cores, steps=env_steps, warmup=10)
+    if loop_iters > 0:
+        out["full_loop_4x20_shipped"] = time_python_reference("loop", iters=loop_iters)
+    return out
 
 
 def run_reference(args):
+    """Reference arm: the UNMODIFIED Python reference, env-step-only at 8 UAV / 64 PoI through its own
+    SubprocVecEnv (one OS process per env, as many envs as host cores) — a bounded sample of the 65 536-env workload,
+    throughput-normalised.  The C port of the same algorithm (all host threads) rides along in cpu_baseline.port.
+    If the reference sources are not on the box the line falls back to the port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle.env_oracle import max_threads
     threads = max_threads()
+    cores = os.cpu_count() or 1
     n_envs = 8192
-    value, dt = time_cpu_port(n_envs, args.steps, args.warmup, threads)
-    sample = "%d envs x %d steps of the 8 UAV / 64 PoI env step, float64 C port of the reference algorithm" % (
-        n_envs, args.steps)
+    port_value, port_dt = time_cpu_port(n_envs, max(args.steps, 30), min(args.warmup, 3), threads)
+    port = {"value": port_value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs x %d steps of the 8 UAV / 64 PoI env step, float64 C port of the reference algorithm "
+                      "(oracle/dcc_env_oracle.c)" % (n_envs, max(args.steps, 30))}
+    steps = max(10, min(args.steps, 150))
+    rec = time_python_reference("env", n=N_AGENTS, m=N_POIS, procs=cores, steps=steps, warmup=max(3, min(args.warmup, 10)))
+    if "agent_steps_per_s" in rec:
+        value, dt, kind = rec["agent_steps_per_s"], rec["seconds"], "reference"
+        sample = ("%d envs (SubprocVecEnv, one process per env) x %d steps of the 8 UAV / 64 PoI env step: the unmodified "
+                  "Python reference from %s" % (rec["procs"], steps, rec["reference_root"]))
+        envs, used = rec["procs"], cores
+    else:
+        value, dt, kind, sample, envs, used, steps = port_value, port_dt, "port", port["sample"], n_envs, threads, max(args.steps, 30)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "env-step-only, 8 UAV / 64 PoI, %d envs per CPU step (bounded sample of the 65536-env "
-                               "workload)" % n_envs, "n_agents": N_AGENTS, "n_pois": N_POIS, "envs": n_envs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                               "workload)" % envs, "n_agents": N_AGENTS, "n_pois": N_POIS, "envs": envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "port": port,
+                         "python_reference": rec},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+WORKLOADS = {
+    # name: (N, M, envs per GPU, env kwargs, description, kernel)
+    "env": (8, 64, 65536, dict(reference_compat=True),
+            "env-step-only (BASELINE configs[1]): 8 UAV / 64 PoI, 65536 envs per GPU, N(0,1) float32 actions, auto-reset on, "
+            "shipped semantics (reference_compat)", "dcc_env_spec_kernel<8,64,true>"),
+    "env16": (16, 256, 32768, dict(reference_compat=False, comm_r_scale=0.95, comm_force_scale=1.0),
+              "env-step-only (BASELINE configs[2]): 16 UAV / 256 PoI, 32768 envs per GPU, connectivity constraint active "
+              "(comm_r_scale 0.95, contact force 100), N(0,1) float32 actions, auto-reset on", "dcc_env_spec_kernel<16,256,true>"),
+}
 
 
 def run_cuda(args):
@@ -172,9 +243,9 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    E, N, M = ENVS_PER_GPU, N_AGENTS, N_POIS
+    N, M, E, env_kw, workload_desc, kernel_name = WORKLOADS[args.workload]
     D = obs_dim(N, M)
-    env = CudaVecEnv(E, N, M, reference_compat=True, device=local_rank, pos_pois="synthetic")  # shipped semantics, synthetic PoI layout (seed 0)
+    env = CudaVecEnv(E, N, M, device=local_rank, pos_pois="synthetic", **env_kw)   # synthetic PoI layout (uniform, seed 0)
     if args.per_env_layouts:
         env.set_poi_layouts(np.random.default_rng(rank).uniform(-1.0, 1.0, (E, M, 2)))
     gen = torch.Generator(device=dev)
@@ -233,53 +304,69 @@ def run_cuda(args):
     e2e_value = world * E * N * e2e_steps / e2e_s
     h2d = E * N * 2 * 4
     d2h = E * N * D * 4 + E * N * 4 + E * N + E * 4
+    env.close()
+    del env, acts
+    torch.cuda.empty_cache()
+
+    # ---- the full MAPPO loop in the same run (configs[3] / [4]): every rank takes part --------------------
+    full = None
+    if args.workload == "env" and not args.no_full_loop:
+        full = measure_full_loop(args.envs or ENVS_PER_GPU, 1, 1, world, rank, local_rank, dev)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         b_alg = alg_bytes_per_agent_step(N, M) + (16.0 * M / N if args.per_env_layouts else 0.0)
         launch_s = ms * 1e-3 / args.steps
         achieved = E * N * b_alg / launch_s / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "env_step_traffic.json" if args.workload == "env" else "env16_step_traffic.json")
         if os.path.exists(tp) and not args.per_env_layouts:     # the ncu capture is of the shared-layout launch
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic_src = ("ncu --set full capture of this kernel at this shape, committed as profiles/%s — a constant "
+                               "read from that file, NOT measured in this run" % os.path.basename(tp))
             except Exception:
                 traffic = None
         cpu = None
         if not args.no_cpu_baseline:
             from oracle.env_oracle import max_threads
             threads = max_threads()
-            n_envs_cpu, steps_cpu = 8192, 30
-            v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 2, threads)
+            n_envs_cpu, steps_cpu = (8192, 30) if args.workload == "env" else (1024, 10)
+            v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 2, threads, N=N, M=M, env_kw=env_kw)
             # grow the sample to >= ~10 s of CPU work
             if dt < 10.0:
                 steps_cpu = int(min(2000, steps_cpu * 10.0 / max(dt, 1e-3)))
-                v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 0, threads)
+                v, dt = time_cpu_port(n_envs_cpu, steps_cpu, 0, threads, N=N, M=M, env_kw=env_kw)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "%d envs x %d steps (%.1f s) of the same 8/64 env step, float64 C port of the reference "
-                             "algorithm (oracle/dcc_env_oracle.c), %d POSIX threads" % (n_envs_cpu, steps_cpu, dt, threads)}
+                   "sample": "%d envs x %d steps (%.1f s) of the same %d/%d env step, float64 C port of the reference "
+                             "algorithm (oracle/dcc_env_oracle.c), %d POSIX threads" % (n_envs_cpu, steps_cpu, dt, N, M, threads)}
+            if world == 1 and not args.no_python_reference:
+                cpu["python_reference"] = python_reference_record(env_steps=150 if args.workload == "env" else 40,
+                                                                  loop_iters=2 if args.workload == "env" else 0, n=N, m=M)
+        metric = METRIC if args.workload == "env" else "agent-steps/sec at 16 UAV / 256 PoI (env step, 32768 envs per GPU, connectivity force on)"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "env-step-only (BASELINE configs[1]): 8 UAV / 64 PoI, 65536 envs per GPU, N(0,1) float32 "
-                                   "actions, auto-reset on, shipped semantics (reference_compat)",
+            "config": {"workload": workload_desc,
                        "n_agents": N, "n_pois": M, "envs_per_gpu": E, "obs_dim": D, "poi_layout": ("per-env uniform(-1,1) (dcc_env_set_poi_layouts)" if args.per_env_layouts
                                       else "uniform(-1,1), seed 0"),
                        "l2": "no flush needed: %.0f MB written per step > 126 MB L2" % (E * N * D * 4 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_agent_step": b_alg,
-                         "alg_bytes_per_launch": E * N * b_alg, "kernel": "dcc_env_spec_kernel<8,64,true>",
-                         "avg_launch_us": launch_s * 1e6},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "alg_bytes_per_agent_step": b_alg, "alg_bytes_per_launch": E * N * b_alg,
+                         "frac_obs_bytes_only": E * N * 4.0 * D / launch_s / 1e9 / peak,
+                         "frac_dram_traffic": (traffic / launch_s / 1e9 / peak) if traffic else None,
+                         "kernel": kernel_name, "avg_launch_us": launch_s * 1e6},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "CudaVecEnv.step_host -> dcc_env_step_host (pinned host buffers)"},
-            "gpu_launches": launches,
+            "gpu_launches": launches + (full["gpu_launches"] if full else 0),
             "clocks": clocks,
         }
+        if full is not None:
+            line["full_loop"] = full
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -359,34 +446,29 @@ def run_reference_mappo(args):
     print(json.dumps(line), flush=True)
 
 
-def run_cuda_mappo(args):
+def mappo_flops_compact(n, m, hidden=HIDDEN):
+    """Algorithmic fp32 FLOPs of ONE PPO epoch per env-step row with the compact-state first layer (the path the loop
+    runs): K = 2N + 4 + 2M for an actor row, N (2N + 2) + 2M + 2 for the critic row (csrc/dcc_compact.cuh)."""
+    ka, kc = 2 * n + 4 + 2 * m, n * (2 * n + 2) + 2 * m + 2
+    per_net = lambda k: 2 * hidden * (k + hidden) + 2 * hidden * (hidden + hidden + k)   # noqa: E731
+    return n * per_net(ka) + per_net(kc)
+
+
+def measure_full_loop(E, steps, warmup, world, rank, local_rank, dev):
+    """`steps` timed iterations (after `warmup`) of the full MAPPO loop at E envs per GPU: T = 150 rollout (policy forward +
+    env step + insert), GAE, 15-epoch PPO update; under torchrun the env axis is sharded and the flat actor+critic
+    gradient is all-reduced over NCCL once per epoch.  Returns the record (identical on every rank; rank 0 prints it)."""
     import torch
     import torch.distributed as dist
     from dcc_b200.learner import Learner
     from dcc_b200.parallel import Comm
     from dcc_b200.utils.config import load_config
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    E = args.envs or ENVS_PER_GPU
-    steps, warmup = args.steps, max(args.warmup, 3)
     cfg = load_config(None, num_agents=N_AGENTS, num_pois=N_POIS, n_rollout_threads=E * world, max_ep_len=T_ROLLOUT,
-                      ppo_epoch=PPO_EPOCH, n_iters=steps + warmup + 1, n_eval_rollout_threads=0, save_model=False,
-                      device=local_rank)
-    lr = Learner(cfg, comm=Comm())
-
-    def one_iter(i):
-        lr.policy.lr_decay(i, cfg.n_iters)
-        ri = lr.rollout(lr.rl_buffer, lr.train_envs)     # returns python floats: the rollout's device->host read
-        ti = lr.rl_update()                              # returns python floats: the update's device->host read
-        return ri, ti
+                      ppo_epoch=PPO_EPOCH, n_iters=steps + warmup + 1, n_eval_rollout_threads=0, n_render_rollout_threads=0,
+                      save_model=False, device=local_rank, poi_layout="synthetic")
+    comm = Comm()
+    lr = Learner(cfg, comm=comm)
 
     def barrier():
         if world > 1:
@@ -394,10 +476,14 @@ def run_cuda_mappo(args):
         torch.cuda.synchronize()
 
     for i in range(warmup):
-        one_iter(i + 1)
+        lr.policy.lr_decay(i + 1, cfg.n_iters)
+        lr.rollout(lr.rl_buffer, lr.train_envs)
+        lr.rl_update()
     sampler = ClockSampler(local_rank)
     l0 = lr.policy.launch_count() + lr.train_envs.launch_count()
-    c0 = lr.comm.calls
+    c0, b0 = comm.calls, comm.bytes
+    comm.timing = True
+    comm.collective_ms()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
     if rank == 0:
         sampler.start()
@@ -409,9 +495,9 @@ def run_cuda_mappo(args):
     info = None
     for i in range(steps):
         lr.policy.lr_decay(warmup + i + 1, cfg.n_iters)
-        ri = lr.rollout(lr.rl_buffer, lr.train_envs)
+        ri = lr.rollout(lr.rl_buffer, lr.train_envs)     # returns python floats: the rollout's device->host read
         ev[2 * i + 1].record()
-        ti = lr.rl_update()
+        ti = lr.rl_update()                              # returns python floats: the update's device->host read
         ev[2 * i + 2].record()
         info = (ri, ti)
     barrier()
@@ -419,53 +505,102 @@ def run_cuda_mappo(args):
     ms = ev[0].elapsed_time(ev[-1])
     roll_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps))
     upd_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps))
+    coll_ms = comm.collective_ms()
+    comm.timing = False
     clocks = sampler.stop() if rank == 0 else None
     launches = lr.policy.launch_count() + lr.train_envs.launch_count() - l0 + steps * T_ROLLOUT   # + insert kernels
     if world > 1:
-        tt = torch.tensor([ms, wall_s, upd_ms, roll_ms], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, wall_s, upd_ms, roll_ms, coll_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, wall_s, upd_ms, roll_ms = (float(x) for x in tt.tolist())
+        ms, wall_s, upd_ms, roll_ms, coll_ms = (float(x) for x in tt.tolist())
     agent_steps = world * E * N_AGENTS * T_ROLLOUT * steps
-    value = agent_steps / (ms * 1e-3)
-    if rank == 0:
-        peak_tf = 1404.7
+    compact = bool(lr.compact)
+    peak_tf = 1404.7
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf = float(json.load(f).get("bf16_tflops_sustained", peak_tf))
+        peak_src = ("measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-level parity needs three split MMAs per product: "
+                    "the fp16 hi/lo split kernels top out at 1/3 of it, the 3xTF32 kernels at 1/6")
+    except Exception:
+        peak_src = "fallback"
+    hbm_peak, _ = measured_peak_gbs()
+    flop_row = mappo_flops_compact(N_AGENTS, N_POIS) if compact else mappo_flops_per_env_step_row(N_AGENTS, N_POIS)
+    upd_flops = flop_row * float(E) * T_ROLLOUT * PPO_EPOCH * steps          # per rank
+    achieved = upd_flops / (upd_ms * 1e-3) / 1e12
+    chunk_rows = int(lr.policy.lib.dcc_mappo_chunk_rows(lr.policy._h))
+    chunks = steps * PPO_EPOCH * (-(-(E * T_ROLLOUT) // chunk_rows))
+    traffic, traffic_src, hbm = None, None, None
+    tp = os.path.join(ROOT, "profiles", "mappo_chunk_traffic.json")
+    if os.path.exists(tp):
         try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peak_tf = float(json.load(f).get("bf16_tflops_sustained", peak_tf))
-            peak_src = "measured sustained dense bf16 (MEASURED_PEAKS.json); three split MMAs per product: the 3xTF32 kernels (weight gradients, dX) top out at 1/6, the fp16 hi/lo split forward kernels at 1/3"
+            tj = json.load(open(tp))
+            if bool(tj.get("compact")) == compact and int(tj.get("chunk_rows", 0)) == chunk_rows:
+                traffic = tj["dram_bytes_per_chunk"]
+                traffic_src = ("sum of dram__bytes_read+write over the kernels of ONE activation chunk (ncu --set full), committed "
+                               "as profiles/mappo_chunk_traffic.json — a constant read from that file, NOT measured in this run")
+                hbm = {"bound": "hbm", "achieved": traffic * chunks / (upd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": traffic * chunks / (upd_ms * 1e-3) / 1e9 / hbm_peak, "traffic_per_chunk": traffic,
+                       "traffic_source": traffic_src}
         except Exception:
-            peak_src = "fallback"
-        flop_epoch_row = mappo_flops_per_env_step_row(N_AGENTS, N_POIS)
-        upd_flops = flop_epoch_row * float(E) * T_ROLLOUT * PPO_EPOCH * steps          # per rank
-        achieved = upd_flops / (upd_ms * 1e-3) / 1e12
-        line = {
-            "metric": MAPPO_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "full MAPPO loop (BASELINE configs[3]%s): 8 UAV / 64 PoI, %d envs per GPU, T=150 rollout + GAE + "
-                                   "15-epoch PPO update, shipped hyper-parameters, random-init policy" % ("; configs[4] sharded" if world > 1 else "", E),
-                       "n_agents": N_AGENTS, "n_pois": N_POIS, "envs_per_gpu": E, "T": T_ROLLOUT, "ppo_epoch": PPO_EPOCH,
-                       "hidden": HIDDEN, "gemm_backend": lr.policy.gemm_backend(),
-                       "l2": "no flush needed: the rollout buffer (%.0f GB of observations) is streamed every epoch" % (
-                           (T_ROLLOUT + 1) * E * N_AGENTS * obs_dim(N_AGENTS, N_POIS) * 4 / 1e9),
-                       "rollout_ms_per_iter": roll_ms / steps, "update_ms_per_iter": upd_ms / steps,
-                       "allreduce_calls_per_iter": (lr.comm.calls - c0) / steps},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src, "alg_flops_per_env_step_row_per_epoch": flop_epoch_row,
-                         "kernel": "tc_gemm_fwd_kernel + tc_gemm_wgrad_kernel (update phase, fp32-equivalent FLOPs)"},
-            "cpu_baseline": None,
-            "e2e": {"value": agent_steps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 8,
-                    "steps": steps, "api": "Learner.rollout + Learner.rl_update (host wall clock incl. the per-iteration device->host "
-                                           "reads of rollout_info / train_info; actions are produced on the device by the policy)"},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "last_iter": {"rollout_info": info[0], "train_info": info[1]},
-        }
+            traffic = None
+    buf = lr.rl_buffer
+    rollout_bytes = (buf.state_pv.numel() * 8 + buf.state_en.numel()) if compact else buf.obs.numel() * 4
+    rec = {
+        "metric": MAPPO_METRIC, "value": agent_steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "rollout_ms": roll_ms / steps, "update_ms": upd_ms / steps,
+        "allreduce_calls": (comm.calls - c0) / steps, "allreduce_ms": coll_ms / steps,
+        "allreduce_bytes": (comm.bytes - b0) / steps,
+        "allreduce_us_per_epoch": 1e3 * coll_ms / steps / PPO_EPOCH,
+        "config": {"workload": "full MAPPO loop (BASELINE configs[3]%s): 8 UAV / 64 PoI, %d envs per GPU, T=150 rollout + GAE + "
+                               "15-epoch PPO update, shipped hyper-parameters, random-init policy, synthetic PoI layout" % (
+                                   "; configs[4] sharded, NCCL gradient all-reduce once per epoch" if world > 1 else "", E),
+                   "n_agents": N_AGENTS, "n_pois": N_POIS, "envs_per_gpu": E, "T": T_ROLLOUT, "ppo_epoch": PPO_EPOCH,
+                   "hidden": HIDDEN, "gemm_backend": lr.policy.gemm_backend(), "chunk_rows": chunk_rows,
+                   "rollout_storage": ("compact state (%.2f GB: pos/vel float64 + PoI energy uint8 per env step; first layer "
+                                       "evaluated from it, csrc/dcc_compact.cuh)" % (rollout_bytes / 1e9)) if compact else
+                                      ("materialised float32 observations (%.1f GB)" % (rollout_bytes / 1e9)),
+                   "l2": "no flush needed: one epoch streams %.1f GB of rollout + activations" % (
+                       (traffic * chunks / steps / PPO_EPOCH / 1e9) if traffic else rollout_bytes / 1e9)},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "alg_flops_per_env_step_row_per_epoch": flop_row,
+                     "alg_flops_per_env_step_row_per_epoch_observation_rows": mappo_flops_per_env_step_row(N_AGENTS, N_POIS),
+                     "kernel": "tc_gemm_fwd_kernel + tc_gemm_wgrad_kernel (update phase, fp32-equivalent FLOPs of the GEMMs as "
+                               "this build evaluates them)", "hbm": hbm},
+        "e2e": {"value": agent_steps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 9 * 8,
+                "steps": steps, "api": "Learner.rollout + Learner.rl_update (host wall clock incl. the per-iteration device->host "
+                                       "reads of rollout_info / train_info; actions are produced on the device by the policy)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "last_iter": {"rollout_info": info[0], "train_info": info[1]},
+    }
+    lr.train_envs.close()
+    del lr
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_cuda_mappo(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rec = measure_full_loop(args.envs or ENVS_PER_GPU, args.steps, max(args.warmup, 1), world, rank, local_rank, dev)
+    if rank == 0:
+        line = dict(rec)
+        line.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                     "cpu_baseline": None})
         if not args.no_cpu_baseline:
             v, dt = time_cpu_port_mappo(2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "2 envs x 1 iteration (T=150, 15 epochs, %.1f s): C env oracle + float64 NumPy MAPPO oracle" % dt}
         print(json.dumps(line), flush=True)
-    lr.train_envs.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -475,18 +610,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--workload", default="env", choices=["env", "mappo"])
-    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (mappo workload; default 65536)")
+    ap.add_argument("--workload", default="env", choices=["env", "env16", "mappo"])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU of the full MAPPO loop (default 65536)")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip timing the Python reference itself")
+    ap.add_argument("--no-full-loop", action="store_true", help="env workload: skip the full_loop sub-record")
     ap.add_argument("--per-env-layouts", action="store_true",
                     help="env workload stress variant (SURVEY.md §8d): every env instance has its own uniform(-1,1) PoI layout "
                          "(+16 M / N bytes read per agent-step)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 150 if args.workload == "env" else 2
+        args.steps = 2 if args.workload == "mappo" else 150
     if args.warmup is None:
-        args.warmup = 10 if args.workload == "env" else 3
+        args.warmup = 1 if args.workload == "mappo" else 10
     if args.workload == "mappo":
         (run_reference_mappo if args.impl == "reference" else run_cuda_mappo)(args)
     elif args.impl == "reference":

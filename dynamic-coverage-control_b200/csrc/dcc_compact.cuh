@@ -13,8 +13,8 @@
 // exactly (oracle/compact_oracle.py pins the identities in float64).  The layer-1 GEMMs then reduce over
 // K = 2N + 4 + 2M (148 at 8/64, was 338) for the actor and N (2N + 2) + 2M + 2 (274, was 2704) for the critic, the rollout
 // stores 320 B per env step instead of 10.8 KB, and no observation row is ever read back during the update.
-// The LayerNorm statistics are taken over exactly the float32 observation values the reference normalises (rebuilt in
-// registers from the float64 state the same way the env kernel builds them).
+// The own-block values are float32 of the float64 state expressions, exactly as the env kernel writes them; the
+// LayerNorm statistics come from closed forms of the same state (see compact_features_kernel).
 #pragma once
 #include "dcc_ops.cuh"
 
@@ -26,6 +26,11 @@ struct CompactDims {
     int lda, ldc;          // padded leading dimensions (multiples of 32; pads are zero)
     float m_energy;        // the constant 5.0 column and the done threshold (coverage.py:107-109)
     int e_thr;             // done_j = energy_j >= e_thr
+    double Qx, Qy, Qxx, Qyy;   // sums of q_jx, q_jy, q_jx^2, q_jy^2 over the PoI table (closed-form LayerNorm statistics)
+    __host__ void set_poi(const double *poi) {
+        Qx = Qy = Qxx = Qyy = 0.0;
+        for (int j = 0; j < M; ++j) { Qx += poi[2 * j]; Qy += poi[2 * j + 1]; Qxx += poi[2 * j] * poi[2 * j]; Qyy += poi[2 * j + 1] * poi[2 * j + 1]; }
+    }
     __host__ void init(int n, int m, double me) {
         N = n; M = m; D = 4 + 2 * (n - 1) + 5 * m; OWN = 2 * n + 2;
         Ka = OWN + 2 * m + 2; Kc = n * OWN + 2 * m + 2;
@@ -40,114 +45,127 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// One warp per env-step row.  Shared memory per warp: N * 4 doubles (state) + (N * OWN + 2M) floats (un-normalised own
-// blocks of all agents, then e_j, then d_j) + 2N floats (per-agent mean, rstd).
+// One warp per env-step row; lane i < N owns UAV i.  Shared memory per warp: N * OWN floats (the own blocks
+// [v_i, p_i, p_k - p_i] of all agents as float32 of the float64 expressions, coverage.py:100-105) + the shared tail
+// [e_1..e_M, d_1..d_M, 1, 0 (slot of -mean), 0 pad] + 2N floats of per-agent (mean, rstd).
+//
+// LayerNorm statistics: the row's sum and sum of squares have CLOSED FORMS in the state — sum_j (q_jx - p_ix) =
+// Qx - M p_ix, sum_j (q_jx - p_ix)^2 = Qxx - 2 p_ix Qx + M p_ix^2 (Qx .. Qyy: constants of the PoI table, CompactDims),
+// likewise over the other UAVs, plus integer sums of e_j, e_j^2, d_j — evaluated in float64 per agent lane, so no pass
+// over the N * M relative positions is needed and var = E[x^2] - mean^2 has no cancellation problem.  They differ from
+// the statistics of the float32-rounded observation values by ~1e-8 relative (each value moves by <= 2^-24 relative).
 // Outputs (either may be NULL): Fa [rows * N, lda] actor features, Fc [rows, ldc] critic features.
-// sidx (optional): output row r is built from state row sidx[r] (unused by the whole-rollout path).
 __global__ void __launch_bounds__(256) compact_features_kernel(const double *__restrict__ pos_vel, const uint8_t *__restrict__ energy,
-                                                               const double *__restrict__ poi, float *__restrict__ Fa,
-                                                               float *__restrict__ Fc, int rows, CompactDims cd, int normalize) {
+                                                               float *__restrict__ Fa, float *__restrict__ Fc, int rows,
+                                                               CompactDims cd, int normalize) {
     extern __shared__ __align__(16) unsigned char cf_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int N = cd.N, M = cd.M, D = cd.D, OWN = cd.OWN;
-    const int ush = N * OWN + 2 * M;                      // floats of the un-normalised feature stage
-    const size_t per_warp = (size_t)N * 32 + align_up((size_t)(ush + 2 * N) * 4, 16);
+    const int nown = N * OWN;
+    const int tail = cd.ldc - nown > cd.lda - OWN ? cd.ldc - nown : cd.lda - OWN;    // floats of the shared tail (incl. pads)
+    const size_t per_warp = align_up((size_t)(nown + tail + 2 * N) * 4 + (size_t)N * 16, 16);
     unsigned char *base = cf_smem + per_warp * wib;
-    double *s_pv = reinterpret_cast<double *>(base);
-    float *s_u = reinterpret_cast<float *>(base + (size_t)N * 32);
-    float *s_stat = s_u + ush;                            // [N] mean, [N] rstd
+    double *s_p = reinterpret_cast<double *>(base);            // [N][2] positions
+    float *s_own = reinterpret_cast<float *>(base + (size_t)N * 16);
+    float *s_tail = s_own + nown;
+    float *s_stat = s_tail + tail;                             // [N] mean, [N] rstd
+    // constant part of the tail: 1 at 2M, zeros behind it
+    for (int c = 2 * M + lane; c < tail; c += 32) s_tail[c] = (c == 2 * M) ? 1.f : 0.f;
     for (int r = blockIdx.x * wpb + wib; r < rows; r += gridDim.x * wpb) {
         __syncwarp();
-        for (int i = lane; i < N * 4; i += 32) s_pv[i] = pos_vel[(size_t)r * N * 4 + i];
+        double px = 0.0, py = 0.0, vx = 0.0, vy = 0.0;
+        if (lane < N) {
+            const double2 pp = *reinterpret_cast<const double2 *>(pos_vel + ((size_t)r * N + lane) * 4);
+            const double2 vv = *reinterpret_cast<const double2 *>(pos_vel + ((size_t)r * N + lane) * 4 + 2);
+            px = pp.x; py = pp.y; vx = vv.x; vy = vv.y;
+            s_p[2 * lane] = px; s_p[2 * lane + 1] = py;
+        }
+        // PoI energies: tail values + exact integer sums of e, e^2, d
+        int se = 0, see = 0, sd = 0;
         for (int j = lane; j < M; j += 32) {
             const int e = energy[(size_t)r * M + j];
-            s_u[N * OWN + j] = (float)e;
-            s_u[N * OWN + M + j] = (e >= cd.e_thr) ? 1.f : 0.f;
+            const int d = e >= cd.e_thr ? 1 : 0;
+            s_tail[j] = (float)e;
+            s_tail[M + j] = (float)d;
+            se += e; see += e * e; sd += d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(FULL_MASK, se, o); see += __shfl_xor_sync(FULL_MASK, see, o); sd += __shfl_xor_sync(FULL_MASK, sd, o);
         }
         __syncwarp();
-        // own blocks: [v_i, p_i, p_k - p_i] as float32 of the float64 expressions (coverage.py:100-105)
-        for (int q = lane; q < N * OWN; q += 32) {
-            const int i = q / OWN, k = q - i * OWN;
-            float v;
-            if (k < 2) v = (float)s_pv[i * 4 + 2 + k];
-            else if (k < 4) v = (float)s_pv[i * 4 + (k - 2)];
-            else {
-                const int t = (k - 4) >> 1, c = (k - 4) & 1;
-                const int o = t + (t >= i ? 1 : 0);
-                v = (float)dsub(s_pv[o * 4 + c], s_pv[i * 4 + c]);
+        double rs = 0.0, rq = 0.0;      // this agent's row sum / sum of squares
+        if (lane < N) {
+            float *own = s_own + lane * OWN;
+            own[0] = (float)vx; own[1] = (float)vy; own[2] = (float)px; own[3] = (float)py;
+            double s = vx + vy + px + py, q = vx * vx + vy * vy + px * px + py * py;
+            int t = 0;
+            for (int k = 0; k < N; ++k) {
+                if (k == lane) continue;
+                const double dx = dsub(s_p[2 * k], px), dy = dsub(s_p[2 * k + 1], py);
+                own[4 + 2 * t] = (float)dx; own[5 + 2 * t] = (float)dy;
+                ++t;
+                s += dx + dy; q = fma(dx, dx, q); q = fma(dy, dy, q);
             }
-            s_u[q] = v;
-        }
-        __syncwarp();
-        // LayerNorm statistics per agent row over its D float32 observation values (two-pass, like the materialised path)
-        float csum = 0.f, cq = 0.f;       // critic: sum of the row sums, sum of the per-agent centred squares
-        for (int i = 0; i < N; ++i) {
-            const double pix = s_pv[i * 4], piy = s_pv[i * 4 + 1];
-            float mean = 0.f, rstd = 1.f, rowsum = 0.f, qsum = 0.f;
+            const double m = (double)M, me = (double)cd.m_energy;
+            s += (cd.Qx - m * px) + (cd.Qy - m * py) + (double)se + m * me + (double)sd;
+            q += (cd.Qxx - 2.0 * px * cd.Qx + m * px * px) + (cd.Qyy - 2.0 * py * cd.Qy + m * py * py) + (double)see + m * me * me + (double)sd;
+            rs = s; rq = q;
+            float mean = 0.f, rstd = 1.f;
             if (normalize) {
-                float s = 0.f;
-                for (int k = lane; k < OWN; k += 32) s += s_u[i * OWN + k];
-                for (int j = lane; j < M; j += 32) {
-                    const float dx = (float)dsub(poi[2 * j], pix), dy = (float)dsub(poi[2 * j + 1], piy);
-                    s += (dx + dy) + (s_u[N * OWN + j] + cd.m_energy + s_u[N * OWN + M + j]);
-                }
-                rowsum = warp_sum_f(s);
-                mean = rowsum / (float)D;
-                float q = 0.f;
-                for (int k = lane; k < OWN; k += 32) { const float d = s_u[i * OWN + k] - mean; q = fmaf(d, d, q); }
-                for (int j = lane; j < M; j += 32) {
-                    const float dx = (float)dsub(poi[2 * j], pix) - mean, dy = (float)dsub(poi[2 * j + 1], piy) - mean;
-                    const float de = s_u[N * OWN + j] - mean, dm = cd.m_energy - mean, dd = s_u[N * OWN + M + j] - mean;
-                    q = fmaf(dx, dx, q); q = fmaf(dy, dy, q); q = fmaf(de, de, q); q = fmaf(dm, dm, q); q = fmaf(dd, dd, q);
-                }
-                qsum = warp_sum_f(q);
-                rstd = rsqrtf(qsum / (float)D + LN_EPS);
+                const double mu = s / (double)D;
+                const double var = fmax(q / (double)D - mu * mu, 0.0);
+                mean = (float)mu;
+                rstd = (float)(1.0 / sqrt(var + (double)LN_EPS));
             }
-            if (lane == 0) { s_stat[i] = mean; s_stat[N + i] = rstd; }
-            csum += rowsum; cq += qsum;
+            s_stat[lane] = mean; s_stat[N + lane] = rstd;
         }
         __syncwarp();
         if (Fa) {
-            for (int i = 0; i < N; ++i) {
+            const int cm = OWN + 2 * M + 1;      // column of -mean * rstd
+            const int nv = cd.lda >> 2;
+            for (int q4 = lane; q4 < N * nv; q4 += 32) {
+                const int i = q4 / nv, c0 = (q4 - i * nv) << 2;
                 const float mean = s_stat[i], rstd = s_stat[N + i];
-                float *out = Fa + ((size_t)r * N + i) * cd.lda;
-                for (int c = lane; c < cd.lda; c += 32) {
-                    float v;
-                    if (c < OWN) v = s_u[i * OWN + c] * rstd;
-                    else if (c < OWN + 2 * M) v = s_u[N * OWN + (c - OWN)] * rstd;
-                    else if (c == OWN + 2 * M) v = rstd;
-                    else if (c == OWN + 2 * M + 1) v = -mean * rstd;
-                    else v = 0.f;
-                    out[c] = v;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c0 + e;
+                    const float src = c < OWN ? s_own[i * OWN + c] : s_tail[c - OWN];
+                    v[e] = (c == cm) ? -mean * rstd : src * rstd;
                 }
+                *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
         if (Fc) {
             float mean_c = 0.f, rstd_c = 1.f;
             if (normalize) {
-                // all N rows have D elements: mean_c = sum of row sums / (N D);
-                // sum (x - mean_c)^2 = sum_i [ q_i + D (mean_i - mean_c)^2 ]   (exact identity, no third pass)
-                mean_c = csum / (float)(N * D);
-                float extra = 0.f;
-                for (int i = 0; i < N; ++i) { const float d = s_stat[i] - mean_c; extra = fmaf(d, d, extra); }
-                rstd_c = rsqrtf((cq + (float)D * extra) / (float)(N * D) + LN_EPS);
+                const double S = warp_sum_d(rs), Q = warp_sum_d(rq);       // lanes >= N contribute 0
+                const double mu = S / ((double)N * D);
+                const double var = fmax(Q / ((double)N * D) - mu * mu, 0.0);
+                mean_c = (float)mu;
+                rstd_c = (float)(1.0 / sqrt(var + (double)LN_EPS));
             }
+            const int cm = nown + 2 * M + 1;
             float *out = Fc + (size_t)r * cd.ldc;
-            const int nown = N * OWN;
-            for (int c = lane; c < cd.ldc; c += 32) {
-                float v;
-                if (c < nown + 2 * M) v = s_u[c] * rstd_c;
-                else if (c == nown + 2 * M) v = rstd_c;
-                else if (c == nown + 2 * M + 1) v = -mean_c * rstd_c;
-                else v = 0.f;
-                out[c] = v;
+            for (int c0 = lane << 2; c0 < cd.ldc; c0 += 128) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c0 + e;
+                    const float src = c < nown ? s_own[c] : s_tail[c - nown];
+                    v[e] = (c == cm) ? -mean_c * rstd_c : src * rstd_c;
+                }
+                *reinterpret_cast<float4 *>(out + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
     }
 }
 
 static inline size_t compact_features_smem(const CompactDims &cd, int warps) {
-    return ((size_t)cd.N * 32 + align_up((size_t)(cd.N * cd.OWN + 2 * cd.M + 2 * cd.N) * 4, 16)) * warps;
+    const int nown = cd.N * cd.OWN;
+    const int tail = cd.ldc - nown > cd.lda - cd.OWN ? cd.ldc - nown : cd.lda - cd.OWN;
+    return align_up((size_t)(nown + tail + 2 * cd.N) * 4 + (size_t)cd.N * 16, 16) * warps;
 }
 
 // Wt[h, :] (ld = ldk, zero padded) and b1g[h] from fc1 (W1 [H, nb*D], b1) and the input LayerNorm affine (g0, be0 or

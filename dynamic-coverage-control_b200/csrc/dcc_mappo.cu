@@ -50,7 +50,10 @@ struct MappoHandle {
     int device, sm_count;
     int backend;     // 1 = SIMT fp32, 2 = tcgen05 3xTF32
     bool f16_fwd;    // backend 2: forward GEMMs on LayerNorm outputs use the fp16 hi/lo split kernel (DCC_TC_F16=0 disables)
-    bool f16_wgrad;  // backend 2, experimental: fp16-split weight-gradient GEMMs (DCC_TC_WGRAD_F16=1 enables)
+    bool f16_wgrad;  // backend 2, experimental: fp16-split weight-gradient GEMMs (DCC_TC_WGRAD_F16=1 enables; measured no faster)
+    bool f16_dx;     // backend 2: the backward dX = dZ W GEMMs run the fp16-split kernel with a per-tensor power-of-two scale of
+                     // dZ (its max |dZ| is produced for free by the LayerNorm-backward kernel that writes dZ); DCC_TC_DX_F16=0 disables
+    bool ln_pipe;    // LayerNorm-backward kernels with the bulk-async row pipeline (H % 4 == 0); DCC_LN_PIPE=0 disables
     uint32_t *dz_absmax;   // device scalar: bits of max |dZ| for the fp16-split weight-gradient kernel
     NetLayout la, lc;
     int chunk_rows;  // env-step rows per chunk
@@ -80,6 +83,13 @@ constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
 static inline const float *vn_snapshot(const MappoHandle *h) { return h->cfg.use_valuenorm ? h->vn_gae : nullptr; }
 
 static inline int act_of(const MappoHandle *h) { return h->cfg.use_relu ? ACT_RELU : ACT_TANH; }
+
+// tcgen05 backend: the output heads are fused into the last block's GEMM epilogue (TcfParams::head_*); DCC_TC_HEAD=0 keeps
+// the separate head kernels (tuning / A-B knob)
+static inline bool fused_head(const MappoHandle *h) {
+    static const bool on = !(getenv("DCC_TC_HEAD") && atoi(getenv("DCC_TC_HEAD")) == 0);
+    return on && h->backend == 2;
+}
 
 static MappoHandle *as_mappo(void *h) {
     MappoHandle *m = static_cast<MappoHandle *>(h);
@@ -170,7 +180,8 @@ static int tc_set_kernel_attributes() {
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
                        const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
-                       bool f16 = false, const uint32_t *a_absmax_bits = nullptr) {
+                       bool f16 = false, const uint32_t *a_absmax_bits = nullptr, const float *head_w = nullptr,
+                       const float *head_b = nullptr, int head_out = 0, float *head_dst = nullptr) {
     if (M <= 0) return DCC_OK;
     if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
     tc::TcfParams p;
@@ -182,6 +193,7 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
     p.act = act_of(h);
+    if (bias && head_dst && head_out > 0) { p.head_out = head_out; p.head_w = head_w; p.head_b = head_b; p.head_dst = head_dst; }
     const int row_tiles = (M + tc::TC_BM - 1) / tc::TC_BM;
     // split-K only to fill the GPU when there are few row tiles and a long K (raw-store epilogue only)
     p.splits = 1;
@@ -274,7 +286,7 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
         if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s, fwd_f16(h, L, 0)))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
             if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
-            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_wgrad))) return rc;
+            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_dx))) return rc;
         }
     }
     return DCC_OK;
@@ -293,7 +305,7 @@ static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int 
         if ((rc = tc_prep_weights(h, h->wt[net], ldk, false, ldk, h->img_w1[net], s, h->f16_fwd))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
             if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
-            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_wgrad))) return rc;
+            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_dx))) return rc;
         }
     }
     return DCC_OK;
@@ -304,7 +316,7 @@ static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en,
                             cudaStream_t s) {
     const int wpb = 8;
     const size_t smem = compact_features_smem(h->cd, wpb);
-    compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, h->d_poi, want_actor ? h->x0 : nullptr,
+    compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, want_actor ? h->x0 : nullptr,
                                                                               want_critic ? h->fc : nullptr, rows, h->cd,
                                                                               h->cfg.use_feature_normalization ? 1 : 0);
     h->launches++;
@@ -316,7 +328,10 @@ static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en,
 // feat != nullptr (compact path): block 0 reads the precomputed feature rows [rows, ldf] against the folded weights
 // h->wt[net] instead of xhat / w1g (x is ignored; no input-LayerNorm kernel).
 static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int net, const float *x, int rows, bool save,
-                         cudaStream_t s, const long long *ridx = nullptr, int rdiv = 1, const float *feat = nullptr, int ldf = 0) {
+                         cudaStream_t s, const long long *ridx = nullptr, int rdiv = 1, const float *feat = nullptr, int ldf = 0,
+                         float *head_dst = nullptr) {
+    // head_dst (tcgen05 backend only): the output head (action mean [rows, 2] / value [rows]) is evaluated inside the last
+    // block's GEMM epilogue and h_last is NOT stored (fused_head()).
     const int H = L.H;
     const int wpb = 8;
     const float *w1g = feat ? h->wt[net] : (net ? h->w1g_c : h->w1g_a), *b1g = net ? h->b1g_c : h->b1g_a;
@@ -340,9 +355,12 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         const float *Wk = k == 0 ? w1g : P + L.W[k], *bk = k == 0 ? b1g : P + L.b[k];
         if (h->backend == 2) {
             // tcgen05 GEMM with the block's bias + activation + LayerNorm fused into its epilogue (one kernel per block)
+            const bool fuse = head_dst && k == L.nblk - 1;
             rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
-                             bk, P + L.lg[k], P + L.lb[k], h->hh[k], save ? h->mean[k] : nullptr, save ? h->rstd[k] : nullptr,
-                             (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k));   // compact features are bounded: fp16-split eligible
+                             bk, P + L.lg[k], P + L.lb[k], fuse ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
+                             save ? h->rstd[k] : nullptr,
+                             (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k),   // compact features are bounded: fp16-split eligible
+                             nullptr, fuse ? P + L.Wh : nullptr, fuse ? P + L.bh : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr);
             if (rc) return rc;
             continue;
         }
@@ -368,7 +386,21 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     const int gr = grid_for_reduce(h, rows, wpb);
     const int last = L.nblk - 1;
     // head backward + activation/LayerNorm backward of the last block in one pass: dA := dz_last
-    if (L.out == 2)
+    // (f16_dx: the kernel that writes a dz also leaves max |dz| in h->dz_absmax for the fp16-split dX GEMM that reads it)
+    const bool dx16 = h->f16_dx && last >= 1;
+    uint32_t *amax = dx16 ? h->dz_absmax : nullptr;
+    if (amax) DCC_CUDA_TRY(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
+    if (h->ln_pipe) {
+        const size_t ring = (size_t)wpb * RP_SLOTS * H;
+        if (L.out == 2)
+            head_relu_ln_bwd_pipe_kernel<2><<<gr, wpb * 32, std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), s>>>(
+                dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
+                G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
+        else
+            head_relu_ln_bwd_pipe_kernel<1><<<gr, wpb * 32, std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float), s>>>(
+                dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
+                G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
+    } else if (L.out == 2)
         head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
                                                           h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
     else
@@ -382,12 +414,19 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                              : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
         if (rc) return rc;
         rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                           nullptr, h->f16_wgrad, h->f16_wgrad ? h->dz_absmax : nullptr)   // dh_{k-1} = dz_k W_k
-                                                                                                         // (max |dz_k| left by the dW_k call above)
+                                           nullptr, dx16, dx16 ? h->dz_absmax : nullptr)   // dh_{k-1} = dz_k W_k
                              : launch_gemm(h, false, false, rows, H, H, dz, H, P + L.W[k], H, dx, H, false, s);
         if (rc) return rc;
-        relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx,
-                                                   G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1], rows, H, act_of(h));   // dx := dz_{k-1}
+        if (h->ln_pipe) {
+            uint32_t *am = (dx16 && k - 1 >= 1) ? h->dz_absmax : nullptr;     // dz_{k-1} feeds another dX GEMM only if k-1 >= 1
+            if (am) DCC_CUDA_TRY(cudaMemsetAsync(am, 0, sizeof(uint32_t), s));
+            const size_t ring = (size_t)wpb * RP_SLOTS * 2 * H;
+            relu_ln_bwd_pipe_kernel<<<gr, wpb * 32, std::max(ring, (size_t)wpb * 3 * 256) * sizeof(float), s>>>(
+                dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx, G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1],
+                rows, H, act_of(h), am);   // dx := dz_{k-1}
+        } else
+            relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx,
+                                                       G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1], rows, H, act_of(h));   // dx := dz_{k-1}
         h->launches++;
         float *t = dz; dz = dx; dx = t;
     }
@@ -483,6 +522,8 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->backend = cfg->gemm_backend ? cfg->gemm_backend : (tc_supported(cfg) ? 2 : 1);
     h->f16_fwd = !(getenv("DCC_TC_F16") && atoi(getenv("DCC_TC_F16")) == 0);
     h->f16_wgrad = getenv("DCC_TC_WGRAD_F16") && atoi(getenv("DCC_TC_WGRAD_F16")) == 1;
+    h->ln_pipe = (cfg->hidden % 4 == 0) && !(getenv("DCC_LN_PIPE") && atoi(getenv("DCC_LN_PIPE")) == 0);
+    h->f16_dx = h->backend == 2 && h->ln_pipe && !(getenv("DCC_TC_DX_F16") && atoi(getenv("DCC_TC_DX_F16")) == 0);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
@@ -597,18 +638,27 @@ static int policy_forward(MappoHandle *h, const float *actor, const float *criti
         const float *fa = cmp ? h->x0 : nullptr, *fcr = cmp ? h->fc : nullptr;
         if (do_actor) {
             const int rows = ne * N;
-            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s, nullptr, 1, fa, h->cd.lda))) return rc;
-            actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
-                h->hh[h->la.nblk - 1], actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
-                d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
-                deterministic, seed, offset, (uint64_t)e0 * N);
+            const bool fh = fused_head(h);
+            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s, nullptr, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
+            if (fh)
+                gauss_finish_kernel<<<(rows + 255) / 256, 256, 0, s>>>(
+                    h->mu, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2, d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr,
+                    d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, mode, deterministic, seed, offset, (uint64_t)e0 * N);
+            else
+                actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
+                    h->hh[h->la.nblk - 1], actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2,
+                    d_mu ? d_mu + (size_t)e0 * N * 2 : nullptr, d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode,
+                    deterministic, seed, offset, (uint64_t)e0 * N);
             h->launches++;
         }
         if (do_critic) {
-            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s, nullptr, 1, fcr, h->cd.ldc))) return rc;
-            critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + h->lc.Wh, critic + h->lc.bh,
-                                                                      d_values + e0, ne, H);
-            h->launches++;
+            const bool fh = fused_head(h);
+            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s, nullptr, 1, fcr, h->cd.ldc, fh ? d_values + e0 : nullptr))) return rc;
+            if (!fh) {
+                critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + h->lc.Wh, critic + h->lc.bh,
+                                                                          d_values + e0, ne, H);
+                h->launches++;
+            }
         }
     }
     DCC_CUDA_TRY(cudaGetLastError());
@@ -645,6 +695,7 @@ int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, d
     DCC_DEVICE_GUARD(h->device);
     CompactDims cd;
     cd.init(N, n_pois, m_energy);
+    cd.set_poi(h_poi_xy);
     if ((size_t)cd.lda > (size_t)h->la.inp) return DCC_ERR_UNSUPPORTED;   // actor features live in the xhat scratch
     if (compact_features_smem(cd, 8) > 200 * 1024) return DCC_ERR_UNSUPPORTED;
     cudaFree(h->d_poi); cudaFree(h->fc);
@@ -803,10 +854,15 @@ static int epoch_grads_impl(MappoHandle *h, const float *actor, const float *cri
         if (cmp && (rc = compact_features(h, d_pv + (size_t)r0 * N * 4, d_en + (size_t)r0 * h->cd.M, nr, true, true, s))) return rc;
         // actor and critic share one activation scratch, so the chunk is processed net by net:
         // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
-        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda))) return rc;
-        actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
-            h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
-            h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
+        const bool fh = fused_head(h);
+        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
+        if (fh)
+            gauss_finish_kernel<<<(nr * N + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+                                                                    h->mu, h->logp, nr * N, 1, 0, 0, 0, 0);
+        else
+            actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
+                h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+                h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
         h->launches++;
         ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
             h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
@@ -814,9 +870,11 @@ static int epoch_grads_impl(MappoHandle *h, const float *actor, const float *cri
         h->launches++;
         if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s, fa, h->cd.lda))) return rc;
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
-        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s, nullptr, 1, fcr, h->cd.ldc))) return rc;
-        critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
-        h->launches++;
+        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s, nullptr, 1, fcr, h->cd.ldc, fh ? h->vnew : nullptr))) return rc;
+        if (!fh) {
+            critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
+            h->launches++;
+        }
         ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
                                                               d_epoch_stats, nr, P);
         h->launches++;
@@ -904,10 +962,15 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
     for (long k0 = 0; k0 < n_index; k0 += RA) {
         const int nk = (int)std::min<long>(RA, n_index - k0);
         // actor on the minibatch's agent rows, observation rows gathered through the permutation
-        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, idx + k0, 1))) return rc;
-        actor_head_kernel<<<grid_for_rows(h, nk, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
-                                                                 const_cast<float *>(d_actions), h->mu, h->logp, nk, H, 1, 0,
-                                                                 0, 0, 0, idx + k0);
+        const bool fh = fused_head(h);
+        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, idx + k0, 1, nullptr, 0, fh ? h->mu : nullptr))) return rc;
+        if (fh)
+            gauss_finish_kernel<<<(nk + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions), h->mu, h->logp,
+                                                                nk, 1, 0, 0, 0, 0, idx + k0);
+        else
+            actor_head_kernel<<<grid_for_rows(h, nk, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
+                                                                     const_cast<float *>(d_actions), h->mu, h->logp, nk, H, 1, 0,
+                                                                     0, 0, 0, idx + k0);
         h->launches++;
         ppo_policy_loss_mb_kernel<<<(nk + 127) / 128, 128, 0, s>>>(h->mu, h->logp, d_actions, actor + LA.logstd, d_logp_old,
                                                                   d_returns, d_values, vn_snapshot(h), d_stats4, n_rows_global,
@@ -919,9 +982,11 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
         for (long c0 = 0; c0 < nk; c0 += h->chunk_rows) {
             const int nc = (int)std::min<long>(h->chunk_rows, nk - c0);
             const long long *ci = idx + k0 + c0;
-            if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, ci, N))) return rc;
-            critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
-            h->launches++;
+            if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, ci, N, nullptr, 0, fh ? h->vnew : nullptr))) return rc;
+            if (!fh) {
+                critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
+                h->launches++;
+            }
             ppo_value_loss_kernel<<<(nc + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats,
                                                                   nc, P, ci);
             h->launches++;

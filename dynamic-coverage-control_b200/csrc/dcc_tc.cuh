@@ -320,6 +320,14 @@ struct TcfParams {
     const float *bias, *gamma, *beta;
     float *H;            // [M, ldc]
     float *mean, *rstd;  // [M] (may be NULL)
+    // fused output head of the LAST trunk block (EPI_BIAS_RELU_LN only): head_dst[row, o] = sum_c h[row, c] * head_w[o, c] +
+    // head_b[o] for o < head_out (2 = the actor's action mean, act.py:79-84 / distributions.py:83-92; 1 = the critic's value,
+    // r_actor_critic.py:120).  The thread that owns an accumulator row forms the dot products over its 128 columns in
+    // registers and the two column halves are combined through shared memory, so h itself need not leave the SM at all
+    // (H may then be NULL: the backward pass rebuilds h from the saved activation a).
+    int head_out;
+    const float *head_w, *head_b;
+    float *head_dst;
     int dbg;             // tools/tc_bench only: 1 = skip the global stores of the epilogue
     // TMA store path of the epilogue (splits == 1): 2-D tensor maps over C and H ([M rows, 256 cols] fp32, box
     // 32 x 32, SWIZZLE_128B).  A thread owns one accumulator row, so it writes its row of a 32 x 32 box into the warp's
@@ -767,6 +775,41 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     if (p.mean) p.mean[row0 + lane] = mean;
                     if (p.rstd) p.rstd[row0 + lane] = rstd;
                 }
+                if (p.head_out > 0) {
+                    float d0 = 0.f, d1 = 0.f;
+                    const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma + half * 128);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.beta + half * 128);
+                    const float4 *w04 = reinterpret_cast<const float4 *>(p.head_w + half * 128);
+                    const float4 *w14 = reinterpret_cast<const float4 *>(p.head_w + TC_N + half * 128);
+                    const bool two = p.head_out > 1;
+#pragma unroll
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4), w0 = __ldg(w04 + c4);
+                        const float h0 = fmaf((acc[4 * c4 + 0] - mean) * rstd, g.x, b.x), h1 = fmaf((acc[4 * c4 + 1] - mean) * rstd, g.y, b.y);
+                        const float h2 = fmaf((acc[4 * c4 + 2] - mean) * rstd, g.z, b.z), h3 = fmaf((acc[4 * c4 + 3] - mean) * rstd, g.w, b.w);
+                        d0 = fmaf(h0, w0.x, d0); d0 = fmaf(h1, w0.y, d0); d0 = fmaf(h2, w0.z, d0); d0 = fmaf(h3, w0.w, d0);
+                        if (two) {
+                            const float4 w1 = __ldg(w14 + c4);
+                            d1 = fmaf(h0, w1.x, d1); d1 = fmaf(h1, w1.y, d1); d1 = fmaf(h2, w1.z, d1); d1 = fmaf(h3, w1.w, d1);
+                        }
+                    }
+                    sts32(rs_u32 + (half * 128 + rl) * 4, d0);
+                    named_bar_sync(1, 256);
+                    const float t0s = lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4);
+                    named_bar_sync(1, 256);
+                    float t1s = 0.f;
+                    if (two) {
+                        sts32(rs_u32 + (half * 128 + rl) * 4, d1);
+                        named_bar_sync(1, 256);
+                        t1s = lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4);
+                        named_bar_sync(1, 256);
+                    }
+                    if (half == 0 && row0 + lane < p.M) {
+                        float *dst = p.head_dst + (size_t)(row0 + lane) * p.head_out;
+                        dst[0] = t0s + __ldg(p.head_b);
+                        if (two) dst[1] = t1s + __ldg(p.head_b + 1);
+                    }
+                }
             }
             TC_PROF_NOW(t3);
             TC_PROF_ADD(e_stats, t0, t3);
@@ -790,7 +833,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                         }
                         float *dsth = p.H + (size_t)row * p.ldc + half * 128;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
+                        for (int c = 0; p.H && c < 32; ++c) {
                             const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma + half * 128) + c);
                             const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta + half * 128) + c);
                             float4 hv;
@@ -876,7 +919,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                             float4 hv;
                             hv.x = fmaf((v.x - mr) * rs, g4.x, b4.x); hv.y = fmaf((v.y - mr) * rs, g4.y, b4.y);
                             hv.z = fmaf((v.z - mr) * rs, g4.z, b4.z); hv.w = fmaf((v.w - mr) * rs, g4.w, b4.w);
-                            *reinterpret_cast<float4 *>(p.H + (size_t)row * p.ldc + colw) = hv;
+                            if (p.H) *reinterpret_cast<float4 *>(p.H + (size_t)row * p.ldc + colw) = hv;
                         }
                     }
                 }

@@ -20,13 +20,33 @@ class Comm:
         else:
             self.world, self.rank = 1, 0
         self.calls = 0
+        self.bytes = 0
+        self.timing = False        # bench.py: bracket every collective with CUDA events on the launching stream
+        self._events = []
 
     def all_reduce_sum_(self, tensor):
         """In-place SUM all-reduce; returns the tensor."""
         if self.world > 1:
+            ev = None
+            if self.timing and tensor.is_cuda:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
+            if ev is not None:
+                ev[1].record()
+                self._events.append(ev)
             self.calls += 1
+            self.bytes += tensor.numel() * tensor.element_size()
         return tensor
+
+    def collective_ms(self):
+        """Device time spent inside the timed collectives since the last call (synchronises); includes waiting for peers."""
+        if not self._events:
+            return 0.0
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        self._events = []
+        return ms
 
     def broadcast_(self, tensor, src=0):
         if self.world > 1:
