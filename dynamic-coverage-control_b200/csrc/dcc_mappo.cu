@@ -165,6 +165,16 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
     return DCC_OK;
 }
 
+// per-device opt-in of the row-pipeline kernels to their dynamic shared memory (ring of RP_SLOTS rows per warp; with the
+// static mbarriers it crosses the 48 KB default at H = 256)
+static int pipe_set_kernel_attributes() {
+    const int bytes = 64 * 1024;
+    DCC_CUDA_TRY(cudaFuncSetAttribute(relu_ln_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return DCC_OK;
+}
+
 // per-device opt-in of the tcgen05 kernels to their dynamic shared-memory footprint (current device)
 static int tc_set_kernel_attributes() {
     DCC_CUDA_TRY(cudaFuncSetAttribute(tc::tc_gemm_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TCF_SMEM_BYTES));
@@ -400,6 +410,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
             head_relu_ln_bwd_pipe_kernel<1><<<gr, wpb * 32, std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float), s>>>(
                 dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
                 G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
+        DCC_CUDA_TRY(cudaGetLastError());
     } else if (L.out == 2)
         head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
                                                           h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
@@ -424,6 +435,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
             relu_ln_bwd_pipe_kernel<<<gr, wpb * 32, std::max(ring, (size_t)wpb * 3 * 256) * sizeof(float), s>>>(
                 dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx, G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1],
                 rows, H, act_of(h), am);   // dx := dz_{k-1}
+            DCC_CUDA_TRY(cudaGetLastError());
         } else
             relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dx, h->a[k - 1], h->mean[k - 1], h->rstd[k - 1], P + L.lg[k - 1], dx,
                                                        G + L.lg[k - 1], G + L.lb[k - 1], G + L.b[k - 1], rows, H, act_of(h));   // dx := dz_{k-1}
@@ -513,6 +525,10 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
         // the opt-in above 48 KB of dynamic shared memory is a per-device function attribute: set it for THIS handle's
         // device at creation (idempotent; no process-wide "done" flag, which would skip a second GPU)
         int rc = tc_set_kernel_attributes();
+        if (rc) return rc;
+    }
+    {
+        int rc = pipe_set_kernel_attributes();
         if (rc) return rc;
     }
     MappoHandle *h = new (std::nothrow) MappoHandle();
