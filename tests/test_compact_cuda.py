@@ -221,3 +221,32 @@ def test_learner_uses_compact_rollout_by_default_and_regenerates_observations():
     cfg3 = load_config(None, num_agents=4, num_pois=20, n_rollout_threads=8, max_ep_len=6, ppo_epoch=1, n_iters=2,
                        n_eval_rollout_threads=0, n_render_rollout_threads=0, save_model=False, num_mini_batch=2)
     assert not Learner(cfg3).compact
+
+
+def test_fp16_split_weight_gradient_knob_keeps_parity(monkeypatch):
+    """DCC_TC_WGRAD_F16=1 routes the weight-gradient GEMMs through tc_gemm_wgrad_kernel<true> (fp16 hi/lo split of both
+    operands, per-tensor power-of-two scale of dZ).  Measured no faster than 3xTF32 on a B200 (profiles/r02a_*), so it stays
+    off by default — but it is not dead code: the 8/64/H=256 golden update must hold with it on, in both storage modes."""
+    import torch
+    monkeypatch.setenv("DCC_TC_WGRAD_F16", "1")
+    g = load("gen_8x64_h256")
+    c = g["cfg"]
+    N, D, M = c["n_agents"], c["obs_dim"], c["n_pois"]
+    T, E = g["it1_actions"].shape[:2]
+    from dcc_b200.envs.cuda_vec_env import reference_pois
+    for compact in (True, False):
+        if compact:
+            cfg, pol, tr, buf = build_compact(c, E, T, reference_pois(M), gemm_backend=2)
+            fill_compact(buf, g, "it1_", N, M)
+        else:
+            cfg, pol, tr, buf = build(c, E, T, gemm_backend=2)
+            fill_buffer(buf, g, "it1_")
+        buf.returns_te.copy_(torch.from_numpy(np.ascontiguousarray(g["it1_returns"][:, :, 0, 0])).to(buf.device))
+        pol.lr_decay(1, c["n_iters"])
+        info = tr.train(buf)
+        ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
+                       g["it1_train_info"]))
+        for k in ref:
+            assert abs(info[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (compact, k, info[k], ref[k])
+        check_params("actor", pol.actor, g, "it1_actor.")
+        check_params("critic", pol.critic, g, "it1_critic.")
