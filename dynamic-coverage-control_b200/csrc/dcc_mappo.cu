@@ -73,6 +73,7 @@ struct MappoHandle {
     CompactDims cd;
     double *d_poi;           // [M, 2] PoI table
     float *fc;               // [chunk, cd.ldc] critic features (the actor's [chunk*N, cd.lda] live in x0)
+    float *head_fold[2];     // output head folded through the last LayerNorm affine, for the fused epilogue (head_fold_kernel)
     float *wt[2];            // folded fc1 weights [H, ld] (actor, critic)
     float *gt[2];            // running dz1^T f of the epoch [H, ld]
     int64_t launches;
@@ -190,8 +191,8 @@ static int tc_set_kernel_attributes() {
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
                        const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
-                       bool f16 = false, const uint32_t *a_absmax_bits = nullptr, const float *head_w = nullptr,
-                       const float *head_b = nullptr, int head_out = 0, float *head_dst = nullptr) {
+                       bool f16 = false, const uint32_t *a_absmax_bits = nullptr, const float *head_fold = nullptr,
+                       int head_out = 0, float *head_dst = nullptr) {
     if (M <= 0) return DCC_OK;
     if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
     tc::TcfParams p;
@@ -203,7 +204,7 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     p.epi = bias ? tc::TCF_EPI_BIAS_RELU_LN : tc::TCF_EPI_STORE;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
     p.act = act_of(h);
-    if (bias && head_dst && head_out > 0) { p.head_out = head_out; p.head_w = head_w; p.head_b = head_b; p.head_dst = head_dst; }
+    if (bias && head_dst && head_out > 0) { p.head_out = head_out; p.head_fold = head_fold; p.head_dst = head_dst; }
     const int row_tiles = (M + tc::TC_BM - 1) / tc::TC_BM;
     // split-K only to fill the GPU when there are few row tiles and a long K (raw-store epilogue only)
     p.splits = 1;
@@ -284,6 +285,16 @@ static inline bool fwd_f16(const MappoHandle *h, const NetLayout &L, int k) { re
 // same condition on the X operand of the weight-gradient GEMM of block k (experimental, DCC_TC_WGRAD_F16=1)
 static inline bool wgrad_f16(const MappoHandle *h, const NetLayout &L, int k) { return h->f16_wgrad && (k > 0 || L.has_ln0); }
 
+// output head folded through the last block's LayerNorm affine (fused epilogue, see TcfParams::head_fold); once per ABI call
+static int fold_head(MappoHandle *h, const NetLayout &L, const float *P, int net, cudaStream_t s) {
+    if (!fused_head(h)) return DCC_OK;
+    const int last = L.nblk - 1;
+    head_fold_kernel<<<1, 256, 0, s>>>(P + L.lg[last], P + L.lb[last], P + L.Wh, P + L.bh, L.H, L.out, h->head_fold[net]);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
@@ -293,6 +304,7 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
     DCC_CUDA_TRY(cudaGetLastError());
     if (h->backend == 2) {
         int rc;
+        if ((rc = fold_head(h, L, P, net, s))) return rc;
         if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s, fwd_f16(h, L, 0)))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
             if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
@@ -312,6 +324,7 @@ static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int 
     DCC_CUDA_TRY(cudaGetLastError());
     if (h->backend == 2) {
         int rc;
+        if ((rc = fold_head(h, L, P, net, s))) return rc;
         if ((rc = tc_prep_weights(h, h->wt[net], ldk, false, ldk, h->img_w1[net], s, h->f16_fwd))) return rc;
         for (int k = 1; k < L.nblk; ++k) {
             if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
@@ -370,7 +383,7 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
                              bk, P + L.lg[k], P + L.lb[k], fuse ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
                              save ? h->rstd[k] : nullptr,
                              (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k),   // compact features are bounded: fp16-split eligible
-                             nullptr, fuse ? P + L.Wh : nullptr, fuse ? P + L.bh : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr);
+                             nullptr, fuse ? h->head_fold[net] : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr);
             if (rc) return rc;
             continue;
         }
@@ -585,6 +598,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     alloc(&h->vn_gae, 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
     if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
+    for (int n = 0; n < 2 && h->backend == 2; ++n) alloc(&h->head_fold[n], 2 * 256 + 8);
     if (ce != cudaSuccess) {
         set_last_cuda_error(ce, "cudaMalloc(mappo scratch)", __FILE__, __LINE__);
         dcc_mappo_destroy(h);
@@ -608,7 +622,7 @@ int dcc_mappo_destroy(void *handle) {
     cudaFree(h->dsums);
     cudaFree(h->dz_absmax);
     cudaFree(h->d_poi); cudaFree(h->fc);
-    for (int n = 0; n < 2; ++n) { cudaFree(h->wt[n]); cudaFree(h->gt[n]); }
+    for (int n = 0; n < 2; ++n) { cudaFree(h->wt[n]); cudaFree(h->gt[n]); cudaFree(h->head_fold[n]); }
     h->magic = 0;
     delete h;
     return DCC_OK;

@@ -811,6 +811,36 @@ __global__ void actor_head_kernel(const float *__restrict__ h, const float *__re
     }
 }
 
+// Output head folded through the last block's LayerNorm affine, for the fused GEMM epilogue (TcfParams::head_fold):
+//   fold[o * 256 + c] = gamma[c] * Wh[o, c];  fold[out * 256 + o] = sum_c gamma[c] Wh[o, c];
+//   fold[out * 256 + out + o] = sum_c beta[c] Wh[o, c] + bh[o]            (one block of 256 threads, H <= 256, sums in float64)
+__global__ void head_fold_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ Wh,
+                                 const float *__restrict__ bh, int H, int out, float *__restrict__ fold) {
+    __shared__ double red[2][8];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    for (int o = 0; o < out; ++o) {
+        double gw = 0.0, bw = 0.0;
+        if (c < H) {
+            const float w = Wh[o * H + c];
+            const float g = gamma[c] * w;
+            fold[o * 256 + c] = g;
+            gw = (double)g;
+            bw = (double)beta[c] * (double)w;
+        } else if (c < 256) fold[o * 256 + c] = 0.f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) { gw += __shfl_xor_sync(FULL_MASK, gw, s); bw += __shfl_xor_sync(FULL_MASK, bw, s); }
+        if (lane == 0) { red[0][warp] = gw; red[1][warp] = bw; }
+        __syncthreads();
+        if (c == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w8 = 0; w8 < 8; ++w8) { a += red[0][w8]; b += red[1][w8]; }
+            fold[out * 256 + o] = (float)a;
+            fold[out * 256 + out + o] = (float)(b + (double)bh[o]);
+        }
+        __syncthreads();
+    }
+}
+
 // Second half of the actor head when mu was produced by the fused GEMM epilogue (tcgen05 backend): sampling / log-prob
 // from mu [rows, 2].  One thread per row; same modes, Philox keying and log-prob formula as actor_head_kernel.
 __global__ void gauss_finish_kernel(const float *__restrict__ mu, const float *__restrict__ logstd, float *__restrict__ actions,

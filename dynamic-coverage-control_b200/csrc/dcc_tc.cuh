@@ -61,6 +61,16 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
     return v;
 }
 
+// 16-byte read-only load that does not allocate in L1: the activation tiles stream through once (16-32 KB per K-stage),
+// and with the shared-memory carve-out at its maximum the L1 is ~28 KB — allocating them there evicted the per-column
+// vectors of the epilogue (bias, gamma, beta, head weights) on every stage, so each of THEIR loads paid an L2 round trip
+// (measured: 10 k cycles per tile for the fused head, profiles/r02g_tc_fwd_role_profile.txt)
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gsrc, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
@@ -303,6 +313,7 @@ constexpr int TCF_CHAIN = DCC_TCF_CHAIN;   // K-stages accumulated in TMEM befor
 constexpr int TCF_STAGE_BYTES = 2 * TC_A_TILE_FLOATS * 4 + 2 * TC_B_TILE_FLOATS * 4;   // 96 KB
 constexpr int TCF_XPOSE_BYTES = 8 * 32 * 32 * 4;   // per-warp 32x32 store staging (XOR-swizzled columns: conflict-free)
 constexpr int TCF_SMEM_BYTES = TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES + 1024 /*align*/ + 1280 /*barriers, row stats*/;
+
 static_assert(TCF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TCF_THREADS = 512;
 
@@ -320,13 +331,17 @@ struct TcfParams {
     const float *bias, *gamma, *beta;
     float *H;            // [M, ldc]
     float *mean, *rstd;  // [M] (may be NULL)
-    // fused output head of the LAST trunk block (EPI_BIAS_RELU_LN only): head_dst[row, o] = sum_c h[row, c] * head_w[o, c] +
-    // head_b[o] for o < head_out (2 = the actor's action mean, act.py:79-84 / distributions.py:83-92; 1 = the critic's value,
-    // r_actor_critic.py:120).  The thread that owns an accumulator row forms the dot products over its 128 columns in
-    // registers and the two column halves are combined through shared memory, so h itself need not leave the SM at all
-    // (H may then be NULL: the backward pass rebuilds h from the saved activation a).
+    // fused output head of the LAST trunk block (EPI_BIAS_RELU_LN only): head_dst[row, o] = sum_c h[row, c] * Wh[o, c] + bh[o]
+    // for o < head_out (2 = the actor's action mean, act.py:79-84 / distributions.py:83-92; 1 = the critic's value,
+    // r_actor_critic.py:120).  With h = (a - mean) rstd gamma + beta this is
+    //     rstd * (sum_c a_c gw[o,c] - mean * sgw[o]) + bw[o],   gw = gamma * Wh[o,:], sgw = sum_c gw, bw = beta . Wh[o,:] + bh[o]
+    // (head_fold_kernel, once per call), so the thread that owns an accumulator row accumulates sum_c a_c gw[o,c] over its
+    // 128 columns in the SAME pass that applies bias + activation, the partial sums ride along with the LayerNorm
+    // statistics through shared memory (no extra barrier), and h itself need not leave the SM at all (H may then be NULL:
+    // the backward pass rebuilds h from the saved activation a).
+    // head_fold: [head_out][256] gw, then head_out x sgw, then head_out x bw (floats, 16-byte aligned)
     int head_out;
-    const float *head_w, *head_b;
+    const float *head_fold;
     float *head_dst;
     int dbg;             // tools/tc_bench only: 1 = skip the global stores of the epilogue
     // TMA store path of the epilogue (splits == 1): 2-D tensor maps over C and H ([M rows, 256 cols] fp32, box
@@ -377,9 +392,10 @@ inline bool tc_make_map_2d(CUtensorMap *tm, const float *base, int cols, int row
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// [rows, 256] output matrix -> store map with a 128B-swizzled 32 x 32 box
+// [rows, 256] output matrix -> store map with a 64B-swizzled box of 16 columns x 32 rows (2 KB: two of them fit the
+// per-warp staging area, see the epilogue)
 inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
-    return tc_make_map_2d(tm, base, 256, rows, ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    return tc_make_map_2d(tm, base, 256, rows, ld, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 // [rows, K] activation matrix -> L2-prefetch map with a box of 128 rows x `box_cols` columns (one K-stage of a row tile)
 inline bool tc_make_prefetch_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_cols) {
@@ -424,7 +440,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES);
     uint64_t *full = bars, *empty = bars + TCF_STAGES, *tfull = bars + 2 * TCF_STAGES, *tempty = bars + 2 * TCF_STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TCF_STAGES + 4);
-    float *rowstat = reinterpret_cast<float *>(bars + 16);   // [2 halves][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_work = ((p.M + TC_BM - 1) / TC_BM) * p.splits;   // work item = (row tile, K split)
@@ -483,7 +498,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = m0 + i * 16 + rsub;
-                v[i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.A + (size_t)row * p.lda + kcol))
+                v[i] = (row < p.M && kcol < p.K) ? ldg_stream(reinterpret_cast<const float4 *>(p.A + (size_t)row * p.lda + kcol))
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -496,8 +511,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 for (int i = 0; i < 4; ++i) {
                     const int row = m0 + (hf * 4 + i) * 16 + rsub;
                     const float *src = p.A + (size_t)row * p.lda + kcol;
-                    v[2 * i] = (row < p.M && kcol < p.K) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[2 * i + 1] = (row < p.M && kcol + 4 < p.K) ? __ldg(reinterpret_cast<const float4 *>(src + 4))
+                    v[2 * i] = (row < p.M && kcol < p.K) ? ldg_stream(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[2 * i + 1] = (row < p.M && kcol + 4 < p.K) ? ldg_stream(reinterpret_cast<const float4 *>(src + 4))
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
@@ -691,10 +706,11 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
         const int half = (warp - 4) >> 2;       // column half: 0 -> 0..127, 1 -> 128..255
         const int ew = warp - 4;
         const uint32_t xp_u32 = smem_u32(xpose + ew * (32 * 32));
-        const uint32_t rs_u32 = smem_u32(rowstat);
+        const uint32_t xq_u32 = smem_u32(xpose + (ew ^ 4) * (32 * 32));   // staging buffer of the warp that owns the other column half
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, e_wait = 0, e_drain = 0, e_tile = 0, e_stats = 0);
+        TC_PROF_DECL(t4 = 0, t5 = 0, t6 = 0, e_head = 0, e_wread = 0, e_lnbar = 0);
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int kt0 = (w % p.splits) * p.kt_per_split, kt1 = min(p.KT, kt0 + p.kt_per_split);
             float acc[128];
@@ -738,76 +754,70 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             const int rl = q * 32 + lane;
             float mean = 0.f, rstd = 0.f;
             if (p.epi == TCF_EPI_BIAS_RELU_LN) {
-                float sum = 0.f;
-                if (p.act == 0) {
+                float sum = 0.f, d0 = 0.f, d1 = 0.f;
+                const int hout = p.head_out;
+                const float4 *gw0 = reinterpret_cast<const float4 *>(p.head_fold + half * 128);
+                const float4 *gw1 = reinterpret_cast<const float4 *>(p.head_fold + TC_N + half * 128);
 #pragma unroll
-                    for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                for (int c4 = 0; c4 < 32; ++c4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                    if (p.act == 0) {
                         acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
                         acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
                         acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
                         acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
-                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
+                    } else {
                         acc[4 * c4 + 0] = tanhf(acc[4 * c4 + 0] + bv.x);
                         acc[4 * c4 + 1] = tanhf(acc[4 * c4 + 1] + bv.y);
                         acc[4 * c4 + 2] = tanhf(acc[4 * c4 + 2] + bv.z);
                         acc[4 * c4 + 3] = tanhf(acc[4 * c4 + 3] + bv.w);
-                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    }
+                    sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    if (hout > 0) {
+                        const float4 w0 = __ldg(gw0 + c4);
+                        d0 = fmaf(acc[4 * c4 + 0], w0.x, d0); d0 = fmaf(acc[4 * c4 + 1], w0.y, d0);
+                        d0 = fmaf(acc[4 * c4 + 2], w0.z, d0); d0 = fmaf(acc[4 * c4 + 3], w0.w, d0);
+                        if (hout > 1) {
+                            const float4 w1 = __ldg(gw1 + c4);
+                            d1 = fmaf(acc[4 * c4 + 0], w1.x, d1); d1 = fmaf(acc[4 * c4 + 1], w1.y, d1);
+                            d1 = fmaf(acc[4 * c4 + 2], w1.z, d1); d1 = fmaf(acc[4 * c4 + 3], w1.w, d1);
+                        }
                     }
                 }
-                sts32(rs_u32 + (half * 128 + rl) * 4, sum);
-                named_bar_sync(1, 256);
-                mean = (lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4)) * (1.f / TC_N);
-                named_bar_sync(1, 256);
+                // exchange with the partner warp that owns the other 128 columns of the same 32 rows (warp w <-> w + 4): a
+                // 64-thread named barrier per row quarter instead of one over all 256 epilogue threads; the head's partial
+                // dot products ride along with the row sum (rowstat: [4 values][2 halves][128 rows])
+                // The exchange area is the first 512 bytes of each warp's own staging buffer ([4 values][32 lanes]; idle here once
+                // the previous tile's boxes have been read by the TMA engine).
+                TC_PROF_NOW(t4);
+                if (p.use_tma) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                const uint32_t mine = xp_u32 + lane * 4, other = xq_u32 + lane * 4;
+                sts32(mine, sum);
+                if (hout > 0) { sts32(mine + 128, d0); if (hout > 1) sts32(mine + 256, d1); }
+                named_bar_sync(1 + q, 64);
+                mean = (sum + lds32(other)) * (1.f / TC_N);
+                float p0 = 0.f, p1 = 0.f;
+                if (hout > 0) { p0 = d0 + lds32(other + 128); if (hout > 1) p1 = d1 + lds32(other + 256); }
                 float sq = 0.f;
 #pragma unroll
                 for (int i = 0; i < 128; ++i) { const float d = acc[i] - mean; sq = fmaf(d, d, sq); }
-                sts32(rs_u32 + (half * 128 + rl) * 4, sq);
-                named_bar_sync(1, 256);
-                rstd = rsqrtf((lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4)) * (1.f / TC_N) + 1e-5f);
-                named_bar_sync(1, 256);
+                sts32(mine + 384, sq);
+                named_bar_sync(1 + q, 64);
+                rstd = rsqrtf((sq + lds32(other + 384)) * (1.f / TC_N) + 1e-5f);
+                named_bar_sync(1 + q, 64);      // the partner has read my values: the staging buffer may be reused for the stores
+                TC_PROF_NOW(t5);
+                TC_PROF_ADD(e_lnbar, t4, t5);
                 if (half == 0 && row0 + lane < p.M) {
                     if (p.mean) p.mean[row0 + lane] = mean;
                     if (p.rstd) p.rstd[row0 + lane] = rstd;
-                }
-                if (p.head_out > 0) {
-                    float d0 = 0.f, d1 = 0.f;
-                    const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma + half * 128);
-                    const float4 *b4 = reinterpret_cast<const float4 *>(p.beta + half * 128);
-                    const float4 *w04 = reinterpret_cast<const float4 *>(p.head_w + half * 128);
-                    const float4 *w14 = reinterpret_cast<const float4 *>(p.head_w + TC_N + half * 128);
-                    const bool two = p.head_out > 1;
-#pragma unroll
-                    for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4), w0 = __ldg(w04 + c4);
-                        const float h0 = fmaf((acc[4 * c4 + 0] - mean) * rstd, g.x, b.x), h1 = fmaf((acc[4 * c4 + 1] - mean) * rstd, g.y, b.y);
-                        const float h2 = fmaf((acc[4 * c4 + 2] - mean) * rstd, g.z, b.z), h3 = fmaf((acc[4 * c4 + 3] - mean) * rstd, g.w, b.w);
-                        d0 = fmaf(h0, w0.x, d0); d0 = fmaf(h1, w0.y, d0); d0 = fmaf(h2, w0.z, d0); d0 = fmaf(h3, w0.w, d0);
-                        if (two) {
-                            const float4 w1 = __ldg(w14 + c4);
-                            d1 = fmaf(h0, w1.x, d1); d1 = fmaf(h1, w1.y, d1); d1 = fmaf(h2, w1.z, d1); d1 = fmaf(h3, w1.w, d1);
-                        }
-                    }
-                    sts32(rs_u32 + (half * 128 + rl) * 4, d0);
-                    named_bar_sync(1, 256);
-                    const float t0s = lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4);
-                    named_bar_sync(1, 256);
-                    float t1s = 0.f;
-                    if (two) {
-                        sts32(rs_u32 + (half * 128 + rl) * 4, d1);
-                        named_bar_sync(1, 256);
-                        t1s = lds32(rs_u32 + rl * 4) + lds32(rs_u32 + (128 + rl) * 4);
-                        named_bar_sync(1, 256);
-                    }
-                    if (half == 0 && row0 + lane < p.M) {
-                        float *dst = p.head_dst + (size_t)(row0 + lane) * p.head_out;
-                        dst[0] = t0s + __ldg(p.head_b);
-                        if (two) dst[1] = t1s + __ldg(p.head_b + 1);
+                    if (hout > 0) {
+                        const float *tailv = p.head_fold + hout * TC_N;      // sgw[hout], bw[hout]
+                        float *dst = p.head_dst + (size_t)(row0 + lane) * hout;
+                        dst[0] = fmaf(rstd, p0 - mean * __ldg(tailv), __ldg(tailv + hout));
+                        if (hout > 1) dst[1] = fmaf(rstd, p1 - mean * __ldg(tailv + 1), __ldg(tailv + hout + 1));
                     }
                 }
             }
@@ -844,43 +854,57 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     }
                 }
             } else if (p.use_tma) {
-                // TMA store path: per 32-column block, stage this warp's 32 rows x 32 columns (thread = row) and hand the
-                // box to the TMA engine; the staging buffer is reused once the engine has READ it (wait_group.read).
+                // TMA store path: per 16-column block, stage this warp's 32 rows x 16 columns (thread = row, 64 bytes) in one of
+                // TWO 2 KB staging buffers and hand the box to the TMA engine; a buffer is reused once the engine has READ the box
+                // staged in it two boxes ago (wait_group.read 1), so staging box k overlaps the engine's read of box k-1 (with
+                // one 4 KB buffer the warp idled ~450 cycles per box, 3.5-4.3 k cycles per tile: profiles/r02g_tc_fwd_role_profile.txt).
+                // Layout = the tensor map's SWIZZLE_64B: 16-byte chunk c of row r at r * 64 + ((c ^ ((r >> 1) & 3)) << 4), conflict-free.
                 const bool ln = p.epi == TCF_EPI_BIAS_RELU_LN;
-                const uint32_t myrow = xp_u32 + lane * 128;
-                const int sw = lane & 7;
+                const uint32_t myrow = lane * 64;
+                const int sw = (lane >> 1) & 3;
+                int nb = 0;
                 if (row0 < p.M && !(p.dbg & 1)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col0 = half * 128 + j * 32;
+                    for (int j = 0; j < 8; ++j) {
+                        const int col0 = half * 128 + j * 16;
                         if (p.C) {
-                            if (lane == 0) bulk_wait_read<0>();
+                            const uint32_t buf = xp_u32 + ((nb & 1) << 11);
+                            TC_PROF_NOW(t4);
+                            if (lane == 0) bulk_wait_read<1>();
                             __syncwarp();
+                            TC_PROF_NOW(t5);
+                            TC_PROF_ADD(e_wread, t4, t5);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                sts128(myrow + ((c ^ sw) << 4), make_float4(acc[j * 32 + 4 * c], acc[j * 32 + 4 * c + 1],
-                                                                            acc[j * 32 + 4 * c + 2], acc[j * 32 + 4 * c + 3]));
+                            for (int c = 0; c < 4; ++c)
+                                sts128(buf + myrow + ((c ^ sw) << 4), make_float4(acc[j * 16 + 4 * c], acc[j * 16 + 4 * c + 1],
+                                                                                 acc[j * 16 + 4 * c + 2], acc[j * 16 + 4 * c + 3]));
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&p.tmC, xp_u32, col0, row0); bulk_commit(); }
+                            if (lane == 0) { tma_store_2d(&p.tmC, buf, col0, row0); bulk_commit(); }
+                            ++nb;
                         }
                         if (ln && p.H) {
-                            if (lane == 0) bulk_wait_read<0>();
+                            const uint32_t buf = xp_u32 + ((nb & 1) << 11);
+                            TC_PROF_NOW(t4);
+                            if (lane == 0) bulk_wait_read<1>();
                             __syncwarp();
+                            TC_PROF_NOW(t5);
+                            TC_PROF_ADD(e_wread, t4, t5);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
+                            for (int c = 0; c < 4; ++c) {
                                 const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma + col0) + c);
                                 const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta + col0) + c);
                                 float4 hv;
-                                hv.x = fmaf((acc[j * 32 + 4 * c] - mean) * rstd, g.x, b.x);
-                                hv.y = fmaf((acc[j * 32 + 4 * c + 1] - mean) * rstd, g.y, b.y);
-                                hv.z = fmaf((acc[j * 32 + 4 * c + 2] - mean) * rstd, g.z, b.z);
-                                hv.w = fmaf((acc[j * 32 + 4 * c + 3] - mean) * rstd, g.w, b.w);
-                                sts128(myrow + ((c ^ sw) << 4), hv);
+                                hv.x = fmaf((acc[j * 16 + 4 * c] - mean) * rstd, g.x, b.x);
+                                hv.y = fmaf((acc[j * 16 + 4 * c + 1] - mean) * rstd, g.y, b.y);
+                                hv.z = fmaf((acc[j * 16 + 4 * c + 2] - mean) * rstd, g.z, b.z);
+                                hv.w = fmaf((acc[j * 16 + 4 * c + 3] - mean) * rstd, g.w, b.w);
+                                sts128(buf + myrow + ((c ^ sw) << 4), hv);
                             }
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&p.tmH, xp_u32, col0, row0); bulk_commit(); }
+                            if (lane == 0) { tma_store_2d(&p.tmH, buf, col0, row0); bulk_commit(); }
+                            ++nb;
                         }
                     }
                 }
@@ -935,6 +959,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
         TC_PROF_OUT(threadIdx.x == 128, 9, e_drain);
         TC_PROF_OUT(threadIdx.x == 128, 10, e_tile);
         TC_PROF_OUT(threadIdx.x == 128, 11, e_stats);
+        TC_PROF_OUT(threadIdx.x == 128, 12, e_head);
+        TC_PROF_OUT(threadIdx.x == 128, 13, e_wread);
+        TC_PROF_OUT(threadIdx.x == 128, 14, e_lnbar);
     }
     tc_fence_before();
     __syncthreads();

@@ -84,6 +84,15 @@ int main(int argc, char **argv) {
         printf("use_tma=%d  ", p.use_tma);
     }
     p.pf_dist = argc > 7 ? atoi(argv[7]) : 0;     // L2 prefetch distance of the activation operand, in stages
+    const int head_out = argc > 8 ? atoi(argv[8]) : 0;   // fused output head (0 / 1 / 2)
+    const int store_h = argc > 9 ? atoi(argv[9]) : 1;    // 0 = do not store h (update-mode last block)
+    const int store_c = argc > 10 ? atoi(argv[10]) : 1;  // 0 = do not store a (rollout mode)
+    float *hw, *hdst;
+    CK(cudaMalloc(&hw, 4 * 256 * 4)); CK(cudaMemset(hw, 0, 4 * 256 * 4)); CK(cudaMalloc(&hdst, (size_t)M * 2 * 4));
+    if (head_out > 0 && epi == 1) { p.head_out = head_out; p.head_fold = hw; p.head_dst = hdst; }
+    if (!store_h) p.H = nullptr;
+    if (!store_c) p.C = nullptr;
+    printf("head=%d store_h=%d store_c=%d  ", head_out, store_h, store_c);
     if (p.pf_dist > 0 && !tc_make_prefetch_map(&p.tmA, A, M, K, K, f16 ? 64 : 32)) { printf("prefetch map failed\n"); p.pf_dist = 0; }
     printf("pf=%d  ", p.pf_dist);
     const int tiles = (M + 127) / 128, grid = tiles < 148 ? tiles : 148;
@@ -107,8 +116,9 @@ int main(int argc, char **argv) {
     printf("CTA0: %llu stages | producer: wait_empty %.0f work %.0f cyc/stage | mma: wait_acc %.0f wait_full %.0f issue %.0f, total %.0f cyc/stage\n",
            prof[2], prof[0] / st, prof[1] / st, prof[4] / st, prof[5] / st, prof[6] / st, prof[7] / st);
     const double tl = st / KT;
-    printf("      epilogue warp 4: wait_tfull %.0f drain %.0f cyc/stage, tile epilogue %.0f cyc/tile of which bias/relu/LN-stats %.0f (%.1f tiles)\n", prof[8] / st,
-           prof[9] / st, prof[10] / tl, prof[11] / tl, tl);
+    printf("      epilogue warp 4: wait_tfull %.0f drain %.0f cyc/stage, tile epilogue %.0f cyc/tile of which bias/relu/LN-stats(+head) %.0f [LN barriers %.0f, head %.0f], "
+           "wait for staging reuse %.0f (%.1f tiles)\n", prof[8] / st,
+           prof[9] / st, prof[10] / tl, prof[11] / tl, prof[14] / tl, prof[12] / tl, prof[13] / tl, tl);
     return 0;
 #endif
 }
