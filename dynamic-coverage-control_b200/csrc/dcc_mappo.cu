@@ -108,9 +108,9 @@ static inline int grid_for_rows(const MappoHandle *h, long rows, int warps_per_b
 }
 
 // kernels that end with one set of atomics per block into a small parameter-gradient vector: 4 CTAs per SM
-static inline int grid_for_reduce(const MappoHandle *h, long rows, int warps_per_block) {
+static inline int grid_for_reduce(const MappoHandle *h, long rows, int warps_per_block, int ctas_per_sm = 4) {
     long b = (rows + warps_per_block - 1) / warps_per_block;
-    const long cap = (long)h->sm_count * 4;
+    const long cap = (long)h->sm_count * ctas_per_sm;      // grid-stride kernels: exactly one wave of resident CTAs
     if (b > cap) b = cap;
     return (int)(b < 1 ? 1 : b);
 }
@@ -269,9 +269,9 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
         tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
         h->launches++;
         p.dz_absmax_bits = h->dz_absmax;
-        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCW_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     } else {
-        tc::tc_gemm_wgrad_kernel<false><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+        tc::tc_gemm_wgrad_kernel<false><<<grid, tc::TCW_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     }
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -406,7 +406,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                           cudaStream_t s, const float *feat = nullptr, int ldf = 0) {
     const int H = L.H;
     const int wpb = 8;
-    const int gr = grid_for_reduce(h, rows, wpb);
+    const int gr = grid_for_reduce(h, rows, wpb, h->ln_pipe ? 3 : 4);   // the pipelined kernels run 3 CTAs per SM
     const int last = L.nblk - 1;
     // head backward + activation/LayerNorm backward of the last block in one pass: dA := dz_last
     // (f16_dx: the kernel that writes a dz also leaves max |dz| in h->dz_absmax for the fp16-split dX GEMM that reads it)

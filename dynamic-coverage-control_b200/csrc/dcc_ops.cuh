@@ -617,8 +617,13 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
 
 // head_relu_ln_bwd_kernel with the row pipeline (one array: the saved activation a).  Dynamic shared memory =
 // max(8 * RP_SLOTS * H, 8 * (3 + OUT) * 256) floats.
+// Because dh2 = dout Wh has rank OUT, three of the per-row column accumulators are not needed: with
+//   P[o][c] = sum_r dout[r,o] xhat[r,c]   and   D[o] = sum_r dout[r,o]
+// the gradients are  dWh[o,c] = gamma[c] P[o][c] + beta[c] D[o],  dgamma[c] = sum_o Wh[o,c] P[o][c],  dbeta[c] = sum_o Wh[o,c] D[o]
+// (formed once per warp after the row loop), so the loop carries OUT + 1 column accumulators (P, dbias) instead of OUT + 3 —
+// fewer registers (3 CTAs per SM instead of 2) and fewer instructions per row.
 template <int OUT>
-__global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
+__global__ void __launch_bounds__(256, 3) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
@@ -638,18 +643,17 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    float g[8], be[8], w[OUT][8], acc[3 + OUT][8], acc_bh[OUT];   // acc: dgamma, dbeta, dbias, dWh[0..OUT)
+    float g[8], wg[OUT][8], P[OUT][8], accb[8], D[OUT];   // wg = Wh * gamma: dxhat = sum_o dout[o] wg[o]
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
         g[j] = (c < H) ? gamma[c] : 0.f;
-        be[j] = (c < H) ? beta[c] : 0.f;
-        acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+        accb[j] = 0.f;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { w[o][j] = (c < H) ? Wh[o * H + c] : 0.f; acc[3 + o][j] = 0.f; }
+        for (int o = 0; o < OUT; ++o) { wg[o][j] = (c < H) ? Wh[o * H + c] * g[j] : 0.f; P[o][j] = 0.f; }
     }
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) acc_bh[o] = 0.f;
+    for (int o = 0; o < OUT; ++o) D[o] = 0.f;
     const int r0 = blockIdx.x * wpb + warp;
     const int n_my = r0 < rows ? (rows - r0 + stride - 1) / stride : 0;
     auto issue = [&](int slot, int row) {      // lane 0
@@ -674,7 +678,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
         const float m = mn, rs = rn;
         float d[OUT];
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { d[o] = dn[o]; acc_bh[o] += d[o]; }
+        for (int o = 0; o < OUT; ++o) { d[o] = dn[o]; D[o] += d[o]; }
         if (k + 1 < n_my) {
             mn = __ldg(mean + r + stride); rn = __ldg(rstd + r + stride);
 #pragma unroll
@@ -690,15 +694,12 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
             const bool ok = c < H;
             av[j] = ok ? sa[c] : 0.f;
             xh[j] = ok ? (av[j] - m) * rs : 0.f;
-            const float h2 = fmaf(xh[j], g[j], be[j]);
-            float dh = 0.f;
+            float dx = 0.f;
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) { dh = fmaf(d[o], w[o][j], dh); acc[3 + o][j] = fmaf(d[o], h2, acc[3 + o][j]); }
-            acc[0][j] = fmaf(dh, xh[j], acc[0][j]);
-            acc[1][j] += dh;
-            dxh[j] = dh * g[j];
-            s1 += dxh[j];
-            s2 = fmaf(dxh[j], xh[j], s2);
+            for (int o = 0; o < OUT; ++o) { dx = fmaf(d[o], wg[o][j], dx); P[o][j] = fmaf(d[o], xh[j], P[o][j]); }
+            dxh[j] = dx;
+            s1 += dx;
+            s2 = fmaf(dx, xh[j], s2);
         }
         __syncwarp();
         if (lane == 0 && k + RP_SLOTS < n_my) {
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
                 const float v = act_bwd(da, av[j], act);
                 dz[(size_t)r * H + c] = v;
-                acc[2][j] += v;
+                accb[j] += v;
                 amax = fmaxf(amax, fabsf(v));
             }
         }
@@ -724,6 +725,22 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL_MASK, amax, o));
         if (lane == 0 && amax > 0.f) atomicMax(absmax_out, __float_as_uint(amax));
     }
+    // this warp's contributions to dgamma, dbeta, dbias, dWh[o] from P, D (see the header)
+    float acc[3 + OUT][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        const float bj = (c < H) ? beta[c] : 0.f;
+        float dg = 0.f, db = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+            const float w = (c < H) ? Wh[o * H + c] : 0.f;
+            dg = fmaf(w, P[o][j], dg);
+            db = fmaf(w, D[o], db);
+            acc[3 + o][j] = fmaf(g[j], P[o][j], bj * D[o]);
+        }
+        acc[0][j] = dg; acc[1][j] = db; acc[2][j] = accb[j];
+    }
     __syncthreads();
     float *dst[3 + OUT];
     dst[0] = dgamma; dst[1] = dbeta; dst[2] = dbias;
@@ -732,7 +749,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
     block_combine_atomic<3 + OUT>(acc, dst, H, dyn_sm);
     if (lane == 0) {
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) atomicAdd(&dbh[o], acc_bh[o]);
+        for (int o = 0; o < OUT; ++o) atomicAdd(&dbh[o], D[o]);
     }
 }
 

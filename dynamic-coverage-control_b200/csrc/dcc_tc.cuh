@@ -65,10 +65,17 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
 // and with the shared-memory carve-out at its maximum the L1 is ~28 KB — allocating them there evicted the per-column
 // vectors of the epilogue (bias, gamma, beta, head weights) on every stage, so each of THEIR loads paid an L2 round trip
 // (measured: 10 k cycles per tile for the fused head, profiles/r02g_tc_fwd_role_profile.txt)
+#ifndef DCC_TC_STREAM_LD
+#define DCC_TC_STREAM_LD 0
+#endif
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+#if DCC_TC_STREAM_LD
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
@@ -316,6 +323,7 @@ constexpr int TCF_SMEM_BYTES = TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES + 
 
 static_assert(TCF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TCF_THREADS = 512;
+constexpr int TCW_THREADS = 640;   // weight-gradient kernel: 8 producer + 8 accumulate warps + the MMA warpgroup
 
 enum { TCF_EPI_STORE = 0, TCF_EPI_BIAS_RELU_LN = 1 };
 
@@ -392,10 +400,9 @@ inline bool tc_make_map_2d(CUtensorMap *tm, const float *base, int cols, int row
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// [rows, 256] output matrix -> store map with a 64B-swizzled box of 16 columns x 32 rows (2 KB: two of them fit the
-// per-warp staging area, see the epilogue)
+// [rows, 256] output matrix -> store map with a 128B-swizzled 32 x 32 box
 inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
-    return tc_make_map_2d(tm, base, 256, rows, ld, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    return tc_make_map_2d(tm, base, 256, rows, ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // [rows, K] activation matrix -> L2-prefetch map with a box of 128 rows x `box_cols` columns (one K-stage of a row tile)
 inline bool tc_make_prefetch_map(CUtensorMap *tm, const float *base, int rows, int K, int ld, int box_cols) {
@@ -417,6 +424,16 @@ __device__ __forceinline__ void red_add_f32(float *addr, float v) {
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// float4 held by lane `src` of the warp (compile-time lane): the epilogue keeps each per-column vector of its 128 columns as
+// ONE coalesced float4 per lane (lane l = columns 4l..4l+3) and broadcasts element c4 with four shuffles instead of
+// re-reading it from global memory in every unrolled iteration (32 broadcast loads per vector and tile, each an L2 round
+// trip because the ~28 KB L1 left beside 227 KB of shared memory is flushed by the producers' tiles; measured upper bound of
+// the gain with immediates: 10-12 % of the fused kernels, profiles/r02j_*).
+__device__ __forceinline__ float4 lane_bcast4(const float4 &v, int src) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src),
+                       __shfl_sync(0xffffffffu, v.w, src));
+}
+
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
@@ -739,6 +756,20 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 TC_PROF_ADD(e_drain, t1, t2);
             }
             TC_PROF_NOW(t0);
+            // per-column vectors of this warp's 128 columns, one float4 per lane (see lane_bcast4); issued before the
+            // scaling pass so their latency is covered
+            float4 vbias = make_float4(0.f, 0.f, 0.f, 0.f), vg = vbias, vb = vbias, vw0 = vbias, vw1 = vbias;
+            if (p.epi == TCF_EPI_BIAS_RELU_LN) {
+                vbias = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + lane);
+                if (p.H) {
+                    vg = __ldg(reinterpret_cast<const float4 *>(p.gamma + half * 128) + lane);
+                    vb = __ldg(reinterpret_cast<const float4 *>(p.beta + half * 128) + lane);
+                }
+                if (p.head_out > 0) {
+                    vw0 = __ldg(reinterpret_cast<const float4 *>(p.head_fold + half * 128) + lane);
+                    vw1 = __ldg(reinterpret_cast<const float4 *>(p.head_fold + (p.head_out > 1 ? TC_N : 0) + half * 128) + lane);
+                }
+            }
             if constexpr (F16) {
                 float sc = p.out_scale;         // undo the power-of-two scale of the weight image (exact)
                 if constexpr (ASCALE) {
@@ -756,29 +787,49 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             if (p.epi == TCF_EPI_BIAS_RELU_LN) {
                 float sum = 0.f, d0 = 0.f, d1 = 0.f;
                 const int hout = p.head_out;
-                const float4 *gw0 = reinterpret_cast<const float4 *>(p.head_fold + half * 128);
-                const float4 *gw1 = reinterpret_cast<const float4 *>(p.head_fold + TC_N + half * 128);
+                // Separate, compact unrolled loops per (activation, head) case: one merged loop with the tanh code inside
+                // every unrolled iteration was 2.7x slower for ReLU (instruction-cache misses on each skipped block).
+                if (p.act == 0 && hout == 0) {
 #pragma unroll
-                for (int c4 = 0; c4 < 32; ++c4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + c4);
-                    if (p.act == 0) {
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 bv = lane_bcast4(vbias, c4);
                         acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
                         acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
                         acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
                         acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
-                    } else {
+                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                    }
+                } else if (p.act == 0) {
+                    // (one output: the second dot product repeats the first and is ignored)
+#pragma unroll
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 bv = lane_bcast4(vbias, c4), w0 = lane_bcast4(vw0, c4), w1 = lane_bcast4(vw1, c4);
+                        acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
+                        acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
+                        acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
+                        acc[4 * c4 + 3] = fmaxf(acc[4 * c4 + 3] + bv.w, 0.f);
+                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
+                        d0 = fmaf(acc[4 * c4 + 0], w0.x, d0); d0 = fmaf(acc[4 * c4 + 1], w0.y, d0);
+                        d0 = fmaf(acc[4 * c4 + 2], w0.z, d0); d0 = fmaf(acc[4 * c4 + 3], w0.w, d0);
+                        d1 = fmaf(acc[4 * c4 + 0], w1.x, d1); d1 = fmaf(acc[4 * c4 + 1], w1.y, d1);
+                        d1 = fmaf(acc[4 * c4 + 2], w1.z, d1); d1 = fmaf(acc[4 * c4 + 3], w1.w, d1);
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 bv = lane_bcast4(vbias, c4);
                         acc[4 * c4 + 0] = tanhf(acc[4 * c4 + 0] + bv.x);
                         acc[4 * c4 + 1] = tanhf(acc[4 * c4 + 1] + bv.y);
                         acc[4 * c4 + 2] = tanhf(acc[4 * c4 + 2] + bv.z);
                         acc[4 * c4 + 3] = tanhf(acc[4 * c4 + 3] + bv.w);
+                        sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
                     }
-                    sum += (acc[4 * c4 + 0] + acc[4 * c4 + 1]) + (acc[4 * c4 + 2] + acc[4 * c4 + 3]);
                     if (hout > 0) {
-                        const float4 w0 = __ldg(gw0 + c4);
-                        d0 = fmaf(acc[4 * c4 + 0], w0.x, d0); d0 = fmaf(acc[4 * c4 + 1], w0.y, d0);
-                        d0 = fmaf(acc[4 * c4 + 2], w0.z, d0); d0 = fmaf(acc[4 * c4 + 3], w0.w, d0);
-                        if (hout > 1) {
-                            const float4 w1 = __ldg(gw1 + c4);
+#pragma unroll
+                        for (int c4 = 0; c4 < 32; ++c4) {
+                            const float4 w0 = lane_bcast4(vw0, c4), w1 = lane_bcast4(vw1, c4);
+                            d0 = fmaf(acc[4 * c4 + 0], w0.x, d0); d0 = fmaf(acc[4 * c4 + 1], w0.y, d0);
+                            d0 = fmaf(acc[4 * c4 + 2], w0.z, d0); d0 = fmaf(acc[4 * c4 + 3], w0.w, d0);
                             d1 = fmaf(acc[4 * c4 + 0], w1.x, d1); d1 = fmaf(acc[4 * c4 + 1], w1.y, d1);
                             d1 = fmaf(acc[4 * c4 + 2], w1.z, d1); d1 = fmaf(acc[4 * c4 + 3], w1.w, d1);
                         }
@@ -854,57 +905,50 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     }
                 }
             } else if (p.use_tma) {
-                // TMA store path: per 16-column block, stage this warp's 32 rows x 16 columns (thread = row, 64 bytes) in one of
-                // TWO 2 KB staging buffers and hand the box to the TMA engine; a buffer is reused once the engine has READ the box
-                // staged in it two boxes ago (wait_group.read 1), so staging box k overlaps the engine's read of box k-1 (with
-                // one 4 KB buffer the warp idled ~450 cycles per box, 3.5-4.3 k cycles per tile: profiles/r02g_tc_fwd_role_profile.txt).
-                // Layout = the tensor map's SWIZZLE_64B: 16-byte chunk c of row r at r * 64 + ((c ^ ((r >> 1) & 3)) << 4), conflict-free.
+                // TMA store path: per 32-column block, stage this warp's 32 rows x 32 columns (thread = row) and hand the
+                // box to the TMA engine; the staging buffer is reused once the engine has READ it (wait_group.read).
+                // (Two half-size boxes per buffer were measured: the wait disappears but the 8 extra fence + issue sequences
+                // per tile cost more, 15.7 k -> 16.7 k cycles per tile epilogue; profiles/r02i_*.)
                 const bool ln = p.epi == TCF_EPI_BIAS_RELU_LN;
-                const uint32_t myrow = lane * 64;
-                const int sw = (lane >> 1) & 3;
-                int nb = 0;
+                const uint32_t myrow = xp_u32 + lane * 128;
+                const int sw = lane & 7;
                 if (row0 < p.M && !(p.dbg & 1)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col0 = half * 128 + j * 16;
+                    for (int j = 0; j < 4; ++j) {
+                        const int col0 = half * 128 + j * 32;
                         if (p.C) {
-                            const uint32_t buf = xp_u32 + ((nb & 1) << 11);
                             TC_PROF_NOW(t4);
-                            if (lane == 0) bulk_wait_read<1>();
+                            if (lane == 0) bulk_wait_read<0>();
                             __syncwarp();
                             TC_PROF_NOW(t5);
                             TC_PROF_ADD(e_wread, t4, t5);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                sts128(buf + myrow + ((c ^ sw) << 4), make_float4(acc[j * 16 + 4 * c], acc[j * 16 + 4 * c + 1],
-                                                                                 acc[j * 16 + 4 * c + 2], acc[j * 16 + 4 * c + 3]));
+                            for (int c = 0; c < 8; ++c)
+                                sts128(myrow + ((c ^ sw) << 4), make_float4(acc[j * 32 + 4 * c], acc[j * 32 + 4 * c + 1],
+                                                                            acc[j * 32 + 4 * c + 2], acc[j * 32 + 4 * c + 3]));
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&p.tmC, buf, col0, row0); bulk_commit(); }
-                            ++nb;
+                            if (lane == 0) { tma_store_2d(&p.tmC, xp_u32, col0, row0); bulk_commit(); }
                         }
                         if (ln && p.H) {
-                            const uint32_t buf = xp_u32 + ((nb & 1) << 11);
                             TC_PROF_NOW(t4);
-                            if (lane == 0) bulk_wait_read<1>();
+                            if (lane == 0) bulk_wait_read<0>();
                             __syncwarp();
                             TC_PROF_NOW(t5);
                             TC_PROF_ADD(e_wread, t4, t5);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma + col0) + c);
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta + col0) + c);
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 g = lane_bcast4(vg, j * 8 + c), b = lane_bcast4(vb, j * 8 + c);
                                 float4 hv;
-                                hv.x = fmaf((acc[j * 16 + 4 * c] - mean) * rstd, g.x, b.x);
-                                hv.y = fmaf((acc[j * 16 + 4 * c + 1] - mean) * rstd, g.y, b.y);
-                                hv.z = fmaf((acc[j * 16 + 4 * c + 2] - mean) * rstd, g.z, b.z);
-                                hv.w = fmaf((acc[j * 16 + 4 * c + 3] - mean) * rstd, g.w, b.w);
-                                sts128(buf + myrow + ((c ^ sw) << 4), hv);
+                                hv.x = fmaf((acc[j * 32 + 4 * c] - mean) * rstd, g.x, b.x);
+                                hv.y = fmaf((acc[j * 32 + 4 * c + 1] - mean) * rstd, g.y, b.y);
+                                hv.z = fmaf((acc[j * 32 + 4 * c + 2] - mean) * rstd, g.z, b.z);
+                                hv.w = fmaf((acc[j * 32 + 4 * c + 3] - mean) * rstd, g.w, b.w);
+                                sts128(myrow + ((c ^ sw) << 4), hv);
                             }
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&p.tmH, buf, col0, row0); bulk_commit(); }
-                            ++nb;
+                            if (lane == 0) { tma_store_2d(&p.tmH, xp_u32, col0, row0); bulk_commit(); }
                         }
                     }
                 }
@@ -1002,7 +1046,7 @@ struct TcwParams {
 // 2048 B per K = 16 instruction: pinned on the GPU with tools/mn16_probe.cu).  dZ is pre-scaled by one power of two per
 // tensor (TcwParams::dz_absmax_bits); X must be a LayerNorm output.
 template <bool F16>
-__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
+__global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
     constexpr int BKW = F16 ? 64 : TC_BK;          // batch rows per stage
     constexpr int UNITS = F16 ? 6 : 3;             // 16 KB raw load units per stage: dZ 1 (2), X 2 (4)
     extern __shared__ uint8_t smem_raw[];
@@ -1018,7 +1062,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCF_STAGES; ++s) {
-            mbar_init(&full[s], 4);       // 4 producer warps
+            mbar_init(&full[s], 8);       // 8 producer warps
             mbar_init(&empty[s], 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -1027,17 +1071,23 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         }
         fence_mbar_init();
     }
-    if (warp == 12) tmem_alloc(tmem_slot, 512);
+    if (warp == 16) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Warp roles (640 threads, 5 warpgroups; registers re-split with setmaxnreg 72 / 72 / 152 / 152 / 24):
+    //   WG0-1 warps 0-7    producers (round 2: EIGHT warps, two per scheduler — with four, one warp per scheduler ran its ~1 100
+    //                      dependent instructions per stage at IPC 0.36 and the whole kernel waited on it: 3 050 cycles per stage
+    //                      against 1 536 of MMA, profiles/r02a_wgrad_fp16_split_tcbench.txt)
+    //   WG2-3 warps 8-15   accumulate / epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4)
+    //   WG4   warp 16      MMA issuer (one thread) + TMEM allocation; warps 17-19 idle
     // smem stage layout: A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB; every 32-feature group = 32 rows x 128 B
-    if (warp < 4) {
-        setmaxnreg_dec<96>();
-        const int t = threadIdx.x;
-        // Work is cut into load units of 8 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
+    if (warp < 8) {
+        setmaxnreg_dec<72>();
+        const int t = threadIdx.x;            // 0..255
+        // Work is cut into load units of 16 KB = 4 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
         // (B).  Raw units are fetched with 16-byte cp.async (LDGSTS) into a 2-slot ring in shared memory two units
         // ahead of their use, so the global-load latency (~1 us) overlaps the split / store work of two units and the
         // wait for the stage slot; each thread reads back only the chunks it fetched itself (no barrier needed).
@@ -1052,7 +1102,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         };
         // ring offset of a thread's i-th 16-byte piece; in the fp16 form pieces 2j, 2j+1 are the two halves of one
         // 8-feature group (32 contiguous bytes in global memory) that becomes ONE 16-byte fp16 chunk
-        auto ring_off = [](int i) { return F16 ? (uint32_t)((i & 1) * 8192 + (i >> 1) * 2048) : (uint32_t)(i * 2048); };
+        auto ring_off = [](int i) { return F16 ? (uint32_t)((i & 1) * 8192 + (i >> 1) * 4096) : (uint32_t)(i * 4096); };
         float dz_scale = 1.f;
         if constexpr (F16) {
             float inv;
@@ -1073,16 +1123,16 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 if constexpr (F16) {
                     if (f_kind < 2) {          // dZ rows [32 * f_kind, +32) of the stage: 16 chunks of 8 features per row
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int pi = t + 128 * (i >> 1), k = f_kind * 32 + (pi >> 4), c = pi & 15;
+                        for (int i = 0; i < 4; ++i) {
+                            const int pi = t + 256 * (i >> 1), k = f_kind * 32 + (pi >> 4), c = pi & 15;
                             const bool ok = r0 + k < r_end;
                             cp_async16(dst + ring_off(i), p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + c * 8 + (i & 1) * 4,
                                        ok ? 16u : 0u);
                         }
                     } else {                   // X rows [16 * (f_kind - 2), +16): 32 chunks of 8 features per row
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int pi = t + 128 * (i >> 1), k = (f_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                        for (int i = 0; i < 4; ++i) {
+                            const int pi = t + 256 * (i >> 1), k = (f_kind - 2) * 16 + (pi >> 5), c = pi & 31;
                             const int col = n0 + c * 8 + (i & 1) * 4;
                             const bool ok = (c >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
                             cp_async16(dst + ring_off(i), p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
@@ -1090,18 +1140,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     }
                 } else if (f_kind == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
+                    for (int i = 0; i < 4; ++i) {
+                        const int ci = t + 256 * i, k = ci >> 5, mc = ci & 31;
                         const bool ok = r0 + k < r_end;
-                        cp_async16(dst + i * 2048, p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + mc * 4, ok ? 16u : 0u);
+                        cp_async16(dst + i * 4096, p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + mc * 4, ok ? 16u : 0u);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ci = t + 128 * ((f_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
+                    for (int i = 0; i < 4; ++i) {
+                        const int ci = t + 256 * ((f_kind - 1) * 4 + i), k = ci >> 6, nc = ci & 63;
                         const int col = n0 + nc * 4;
                         const bool ok = (nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
-                        cp_async16(dst + i * 2048, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
+                        cp_async16(dst + i * 4096, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
                     }
                 }
                 if (++f_kind == UNITS) {
@@ -1136,9 +1186,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             cp_async_wait<1>();                  // unit u has landed (unit u+1 may still be in flight)
             TC_PROF_NOW(pc1);
             TC_PROF_ADD(p_cp_acc, pc0, pc1);
-            float4 v[8];
+            float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + ring_off(i));
+            for (int i = 0; i < 4; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + ring_off(i));
             fetch_unit(slot);                    // refill this slot with unit u+2
             const int cur_kind = c_kind, cur_ngroups = c_ngroups;
             const int s = it & 1;
@@ -1154,8 +1204,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             if constexpr (F16) {
                 if (cur_kind < 2) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int pi = t + 128 * j, k = cur_kind * 32 + (pi >> 4), c = pi & 15;
+                    for (int j = 0; j < 2; ++j) {
+                        const int pi = t + 256 * j, k = cur_kind * 32 + (pi >> 4), c = pi & 15;
                         float4 a = v[2 * j], b = v[2 * j + 1];
                         a.x *= dz_scale; a.y *= dz_scale; a.z *= dz_scale; a.w *= dz_scale;
                         b.x *= dz_scale; b.y *= dz_scale; b.z *= dz_scale; b.w *= dz_scale;
@@ -1168,8 +1218,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 } else {
                     const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int pi = t + 128 * j, k = (cur_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                    for (int j = 0; j < 2; ++j) {
+                        const int pi = t + 256 * j, k = (cur_kind - 2) * 16 + (pi >> 5), c = pi & 31;
                         if ((c >> 3) < cur_ngroups) {
                             uint4 hi, lo;
                             split_f16x8(v[2 * j], v[2 * j + 1], hi, lo);
@@ -1187,8 +1237,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 }
             } else if (cur_kind == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
+                for (int i = 0; i < 4; ++i) {
+                    const int ci = t + 256 * i, k = ci >> 5, mc = ci & 31;
                     float4 hi, lo;
                     split_tf32(v[i], hi, lo);
                     const uint32_t off = mn32_offset(mc >> 3, k, mc & 7, TC_BK);
@@ -1198,8 +1248,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             } else {
                 const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ci = t + 128 * ((cur_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
+                for (int i = 0; i < 4; ++i) {
+                    const int ci = t + 256 * ((cur_kind - 1) * 4 + i), k = ci >> 6, nc = ci & 63;
                     if ((nc >> 3) < cur_ngroups) {
                         float4 hi, lo;
                         split_tf32(v[i], hi, lo);
@@ -1235,9 +1285,9 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         TC_PROF_OUT(t == 0, 21, p_wait_acc);
         TC_PROF_OUT(t == 0, 22, p_cp_acc);
         TC_PROF_OUT(t == 0, 23, p_end - p_begin);
-    } else if (warp >= 12) {
-        setmaxnreg_dec<32>();
-        if (warp == 12 && lane == 0) {
+    } else if (warp >= 16) {
+        setmaxnreg_dec<24>();
+        if (warp == 16 && lane == 0) {
             uint32_t it = 0;
             TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
             TC_PROF_NOW(m_begin);
@@ -1300,8 +1350,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         }
         __syncwarp();
     } else {
-        setmaxnreg_inc<192>();
-        const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
+        setmaxnreg_inc<152>();
+        const int q = warp & 3, half = (warp - 8) >> 2;
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -1362,7 +1412,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == 16) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

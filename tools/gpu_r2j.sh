@@ -1,0 +1,22 @@
+#!/bin/bash
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+TAG=${1:-r02j}
+{
+for bin in tools/tc_bench.bin tools/tc_bench_fake.bin; do
+  echo "== $bin"
+  timeout 30 $bin 303104 160 1 0 1 1 2 0 1 1
+  timeout 30 $bin 303104 256 1 0 1 1 2 2 0 1
+done
+echo "== wgrad (8 producer warps)"
+for shape in "303104 256" "303104 160" "37888 288"; do
+  for bin in tools/tc_bench.bin tools/tc_bench_np.bin; do timeout 30 $bin wgrad $shape 0 | head -3; done
+done
+timeout 30 tools/tc_bench_np.bin wgrad 303104 256 1 | head -2
+} > gpurun_out/${TAG}_tcbench.log 2>&1
+cat gpurun_out/${TAG}_tcbench.log | cut -c1-330
+timeout 600 python -m pytest tests/test_mappo_cuda.py tests/test_compact_cuda.py -m gpu -q --maxfail=15 -p no:cacheprovider -x > gpurun_out/${TAG}_pytest.log 2>&1
+grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/${TAG}_pytest.log | tail -8
+timeout 300 python tools/bench_mappo.py --envs 8192 --iters 1 --epochs 4 --compact 1 > gpurun_out/${TAG}_mappo_1.log 2>&1
+echo "loop: $(tail -2 gpurun_out/${TAG}_mappo_1.log | head -1 | cut -c1-130)"
