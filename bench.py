@@ -143,7 +143,7 @@ def time_cpu_port(n_envs, steps, warmup, threads, seed=0, N=N_AGENTS, M=N_POIS, 
     return n_envs * N * steps / dt, dt
 
 
-def time_python_reference(what, timeout_s=420, **kw):
+def time_python_reference(what, timeout_s=240, **kw):
     """Runs baseline/run_reference.py (the UNMODIFIED Python reference behind the stub shim) in a subprocess on the
     host cores and returns its JSON record, or {"unavailable": why}."""
     cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), what]
@@ -168,11 +168,11 @@ def time_python_reference(what, timeout_s=420, **kw):
 def python_reference_record(env_steps=150, loop_iters=2, n=N_AGENTS, m=N_POIS):
     """cpu_baseline.python_reference: SURVEY.md §8d (i) env-only at the benchmarked shape with SubprocVecEnv x cpu_count,
     (ii) the shipped 4 UAV / 20 PoI full loop (16 SubprocVecEnv workers, T = 150, 15 epochs)."""
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)        # one OS process per env instance (SubprocVecEnv): bounded on very wide hosts
     out = {"cores": cores, "kind": "reference",
            "how": "unmodified reference sources (baseline/run_reference.py; stub shim for gym/imp/omegaconf/imageio/wandb; "
                   "make_world's 4/20 literals lifted for 8/64)"}
-    out["env_only"] = time_python_reference("env", n=n, m=m, procs=cores, steps=env_steps, warmup=10)
+    out["env_only"] = time_python_reference("env", timeout_s=150, n=n, m=m, procs=cores, steps=env_steps, warmup=10)
     if loop_iters > 0:
         out["full_loop_4x20_shipped"] = time_python_reference("loop", iters=loop_iters)
     return out
@@ -188,7 +188,7 @@ def run_reference(args):
         return
     from oracle.env_oracle import max_threads
     threads = max_threads()
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)
     n_envs = 8192
     port_value, port_dt = time_cpu_port(n_envs, max(args.steps, 30), min(args.warmup, 3), threads)
     port = {"value": port_value, "unit": UNIT, "cores": threads, "kind": "port",

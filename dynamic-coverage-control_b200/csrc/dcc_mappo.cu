@@ -269,9 +269,9 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
         tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
         h->launches++;
         p.dz_absmax_bits = h->dz_absmax;
-        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCW_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     } else {
-        tc::tc_gemm_wgrad_kernel<false><<<grid, tc::TCW_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+        tc::tc_gemm_wgrad_kernel<false><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     }
     DCC_CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -406,7 +406,8 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                           cudaStream_t s, const float *feat = nullptr, int ldf = 0) {
     const int H = L.H;
     const int wpb = 8;
-    const int gr = grid_for_reduce(h, rows, wpb, h->ln_pipe ? 3 : 4);   // the pipelined kernels run 3 CTAs per SM
+    const int gr = grid_for_reduce(h, rows, wpb, h->ln_pipe ? 3 : 4);    // relu_ln_bwd_pipe: 3 CTAs per SM
+    const int gr_head = grid_for_reduce(h, rows, wpb, h->ln_pipe ? 2 : 4);   // head_relu_ln_bwd_pipe: 2 CTAs per SM
     const int last = L.nblk - 1;
     // head backward + activation/LayerNorm backward of the last block in one pass: dA := dz_last
     // (f16_dx: the kernel that writes a dz also leaves max |dz| in h->dz_absmax for the fp16-split dX GEMM that reads it)
@@ -416,19 +417,19 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     if (h->ln_pipe) {
         const size_t ring = (size_t)wpb * RP_SLOTS * H;
         if (L.out == 2)
-            head_relu_ln_bwd_pipe_kernel<2><<<gr, wpb * 32, std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), s>>>(
+            head_relu_ln_bwd_pipe_kernel<2><<<gr_head, wpb * 32, std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), s>>>(
                 dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
                 G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
         else
-            head_relu_ln_bwd_pipe_kernel<1><<<gr, wpb * 32, std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float), s>>>(
+            head_relu_ln_bwd_pipe_kernel<1><<<gr_head, wpb * 32, std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float), s>>>(
                 dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
                 G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
         DCC_CUDA_TRY(cudaGetLastError());
     } else if (L.out == 2)
-        head_relu_ln_bwd_kernel<2><<<gr, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
+        head_relu_ln_bwd_kernel<2><<<gr_head, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
                                                           h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
     else
-        head_relu_ln_bwd_kernel<1><<<gr, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
+        head_relu_ln_bwd_kernel<1><<<gr_head, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
                                                           h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h));
     h->launches++;
     int rc;

@@ -620,10 +620,10 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
 // Because dh2 = dout Wh has rank OUT, three of the per-row column accumulators are not needed: with
 //   P[o][c] = sum_r dout[r,o] xhat[r,c]   and   D[o] = sum_r dout[r,o]
 // the gradients are  dWh[o,c] = gamma[c] P[o][c] + beta[c] D[o],  dgamma[c] = sum_o Wh[o,c] P[o][c],  dbeta[c] = sum_o Wh[o,c] D[o]
-// (formed once per warp after the row loop), so the loop carries OUT + 1 column accumulators (P, dbias) instead of OUT + 3 —
-// fewer registers (3 CTAs per SM instead of 2) and fewer instructions per row.
+// (formed once per warp after the row loop), so the loop carries OUT + 1 column accumulators (P, dbias) instead of OUT + 3
+// and fewer instructions per row.  (Squeezed into 80 registers for 3 CTAs per SM it ran SLOWER, 158 -> 188 us: kept at 2.)
 template <int OUT>
-__global__ void __launch_bounds__(256, 3) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
+__global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,

@@ -323,7 +323,6 @@ constexpr int TCF_SMEM_BYTES = TCF_STAGES * TCF_STAGE_BYTES + TCF_XPOSE_BYTES + 
 
 static_assert(TCF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int TCF_THREADS = 512;
-constexpr int TCW_THREADS = 640;   // weight-gradient kernel: 8 producer + 8 accumulate warps + the MMA warpgroup
 
 enum { TCF_EPI_STORE = 0, TCF_EPI_BIAS_RELU_LN = 1 };
 
@@ -1040,13 +1039,17 @@ struct TcwParams {
 };
 
 //
-// F16 = true (EXPERIMENTAL, off by default: DCC_TC_WGRAD_F16=1): fp16 hi/lo split of both operands, 64 batch rows per
+// Round-2 note: a variant with EIGHT producer warps (640 threads, setmaxnreg 72 / 152 / 24) was measured — no gain in isolation
+// (236 vs 235 us) and slower inside the update (dW2 227 -> 255 us, profiles/r02l_*): the producers are not issue-bound by
+// their warp count; a 32-row stage moves ~336 KB through shared memory (cp.async ring in + out, hi/lo stores, tensor-core
+// reads), i.e. ~2 600 cycles at 128 B/clk against 1 536 cycles of MMA.
+// F16 = true (off by default: DCC_TC_WGRAD_F16=1; validated, not faster): fp16 hi/lo split of both operands, 64 batch rows per
 // stage in the same stage bytes.  16-bit MN-major operands use the ordinary SWIZZLE_128B layout: per 64-feature group a
 // block of [64 k rows][128 B], 16-byte chunks XOR-ed with (k & 7), groups 8 KB apart (descriptor LBO = 8192, SBO = 1024,
 // 2048 B per K = 16 instruction: pinned on the GPU with tools/mn16_probe.cu).  dZ is pre-scaled by one power of two per
 // tensor (TcwParams::dz_absmax_bits); X must be a LayerNorm output.
 template <bool F16>
-__global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
+__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
     constexpr int BKW = F16 ? 64 : TC_BK;          // batch rows per stage
     constexpr int UNITS = F16 ? 6 : 3;             // 16 KB raw load units per stage: dZ 1 (2), X 2 (4)
     extern __shared__ uint8_t smem_raw[];
@@ -1062,7 +1065,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCF_STAGES; ++s) {
-            mbar_init(&full[s], 8);       // 8 producer warps
+            mbar_init(&full[s], 4);       // 4 producer warps
             mbar_init(&empty[s], 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -1071,23 +1074,17 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         }
         fence_mbar_init();
     }
-    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    if (warp == 12) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Warp roles (640 threads, 5 warpgroups; registers re-split with setmaxnreg 72 / 72 / 152 / 152 / 24):
-    //   WG0-1 warps 0-7    producers (round 2: EIGHT warps, two per scheduler — with four, one warp per scheduler ran its ~1 100
-    //                      dependent instructions per stage at IPC 0.36 and the whole kernel waited on it: 3 050 cycles per stage
-    //                      against 1 536 of MMA, profiles/r02a_wgrad_fp16_split_tcbench.txt)
-    //   WG2-3 warps 8-15   accumulate / epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4)
-    //   WG4   warp 16      MMA issuer (one thread) + TMEM allocation; warps 17-19 idle
     // smem stage layout: A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB; every 32-feature group = 32 rows x 128 B
-    if (warp < 8) {
-        setmaxnreg_dec<72>();
-        const int t = threadIdx.x;            // 0..255
-        // Work is cut into load units of 16 KB = 4 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
+    if (warp < 4) {
+        setmaxnreg_dec<96>();
+        const int t = threadIdx.x;
+        // Work is cut into load units of 8 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X
         // (B).  Raw units are fetched with 16-byte cp.async (LDGSTS) into a 2-slot ring in shared memory two units
         // ahead of their use, so the global-load latency (~1 us) overlaps the split / store work of two units and the
         // wait for the stage slot; each thread reads back only the chunks it fetched itself (no barrier needed).
@@ -1102,7 +1099,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         };
         // ring offset of a thread's i-th 16-byte piece; in the fp16 form pieces 2j, 2j+1 are the two halves of one
         // 8-feature group (32 contiguous bytes in global memory) that becomes ONE 16-byte fp16 chunk
-        auto ring_off = [](int i) { return F16 ? (uint32_t)((i & 1) * 8192 + (i >> 1) * 4096) : (uint32_t)(i * 4096); };
+        auto ring_off = [](int i) { return F16 ? (uint32_t)((i & 1) * 8192 + (i >> 1) * 2048) : (uint32_t)(i * 2048); };
         float dz_scale = 1.f;
         if constexpr (F16) {
             float inv;
@@ -1123,16 +1120,16 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 if constexpr (F16) {
                     if (f_kind < 2) {          // dZ rows [32 * f_kind, +32) of the stage: 16 chunks of 8 features per row
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int pi = t + 256 * (i >> 1), k = f_kind * 32 + (pi >> 4), c = pi & 15;
+                        for (int i = 0; i < 8; ++i) {
+                            const int pi = t + 128 * (i >> 1), k = f_kind * 32 + (pi >> 4), c = pi & 15;
                             const bool ok = r0 + k < r_end;
                             cp_async16(dst + ring_off(i), p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + c * 8 + (i & 1) * 4,
                                        ok ? 16u : 0u);
                         }
                     } else {                   // X rows [16 * (f_kind - 2), +16): 32 chunks of 8 features per row
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int pi = t + 256 * (i >> 1), k = (f_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                        for (int i = 0; i < 8; ++i) {
+                            const int pi = t + 128 * (i >> 1), k = (f_kind - 2) * 16 + (pi >> 5), c = pi & 31;
                             const int col = n0 + c * 8 + (i & 1) * 4;
                             const bool ok = (c >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
                             cp_async16(dst + ring_off(i), p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
@@ -1140,18 +1137,18 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                     }
                 } else if (f_kind == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int ci = t + 256 * i, k = ci >> 5, mc = ci & 31;
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
                         const bool ok = r0 + k < r_end;
-                        cp_async16(dst + i * 4096, p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + mc * 4, ok ? 16u : 0u);
+                        cp_async16(dst + i * 2048, p.dZ + (size_t)(ok ? r0 + k : 0) * p.ldz + mh * 128 + mc * 4, ok ? 16u : 0u);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int ci = t + 256 * ((f_kind - 1) * 4 + i), k = ci >> 6, nc = ci & 63;
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = t + 128 * ((f_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
                         const int col = n0 + nc * 4;
                         const bool ok = (nc >> 3) < ngroups && r0 + k < r_end && col < p.Nout;
-                        cp_async16(dst + i * 4096, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
+                        cp_async16(dst + i * 2048, p.X + (size_t)(ok ? r0 + k : 0) * p.ldx + (ok ? col : 0), ok ? 16u : 0u);
                     }
                 }
                 if (++f_kind == UNITS) {
@@ -1186,9 +1183,9 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             cp_async_wait<1>();                  // unit u has landed (unit u+1 may still be in flight)
             TC_PROF_NOW(pc1);
             TC_PROF_ADD(p_cp_acc, pc0, pc1);
-            float4 v[4];
+            float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + ring_off(i));
+            for (int i = 0; i < 8; ++i) v[i] = lds128(ring_u32 + slot * 16384 + t * 16 + ring_off(i));
             fetch_unit(slot);                    // refill this slot with unit u+2
             const int cur_kind = c_kind, cur_ngroups = c_ngroups;
             const int s = it & 1;
@@ -1204,8 +1201,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             if constexpr (F16) {
                 if (cur_kind < 2) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int pi = t + 256 * j, k = cur_kind * 32 + (pi >> 4), c = pi & 15;
+                    for (int j = 0; j < 4; ++j) {
+                        const int pi = t + 128 * j, k = cur_kind * 32 + (pi >> 4), c = pi & 15;
                         float4 a = v[2 * j], b = v[2 * j + 1];
                         a.x *= dz_scale; a.y *= dz_scale; a.z *= dz_scale; a.w *= dz_scale;
                         b.x *= dz_scale; b.y *= dz_scale; b.z *= dz_scale; b.w *= dz_scale;
@@ -1218,8 +1215,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 } else {
                     const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int pi = t + 256 * j, k = (cur_kind - 2) * 16 + (pi >> 5), c = pi & 31;
+                    for (int j = 0; j < 4; ++j) {
+                        const int pi = t + 128 * j, k = (cur_kind - 2) * 16 + (pi >> 5), c = pi & 31;
                         if ((c >> 3) < cur_ngroups) {
                             uint4 hi, lo;
                             split_f16x8(v[2 * j], v[2 * j + 1], hi, lo);
@@ -1237,8 +1234,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 }
             } else if (cur_kind == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ci = t + 256 * i, k = ci >> 5, mc = ci & 31;
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * i, k = ci >> 5, mc = ci & 31;
                     float4 hi, lo;
                     split_tf32(v[i], hi, lo);
                     const uint32_t off = mn32_offset(mc >> 3, k, mc & 7, TC_BK);
@@ -1248,8 +1245,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
             } else {
                 const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ci = t + 256 * ((cur_kind - 1) * 4 + i), k = ci >> 6, nc = ci & 63;
+                for (int i = 0; i < 8; ++i) {
+                    const int ci = t + 128 * ((cur_kind - 1) * 8 + i), k = ci >> 6, nc = ci & 63;
                     if ((nc >> 3) < cur_ngroups) {
                         float4 hi, lo;
                         split_tf32(v[i], hi, lo);
@@ -1285,9 +1282,9 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         TC_PROF_OUT(t == 0, 21, p_wait_acc);
         TC_PROF_OUT(t == 0, 22, p_cp_acc);
         TC_PROF_OUT(t == 0, 23, p_end - p_begin);
-    } else if (warp >= 16) {
-        setmaxnreg_dec<24>();
-        if (warp == 16 && lane == 0) {
+    } else if (warp >= 12) {
+        setmaxnreg_dec<32>();
+        if (warp == 12 && lane == 0) {
             uint32_t it = 0;
             TC_PROF_DECL(t0 = 0, t1 = 0, t2 = 0, t3 = 0, m_wacc = 0, m_wfull = 0, m_issue = 0, m_begin = 0);
             TC_PROF_NOW(m_begin);
@@ -1350,8 +1347,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
         }
         __syncwarp();
     } else {
-        setmaxnreg_inc<152>();
-        const int q = warp & 3, half = (warp - 8) >> 2;
+        setmaxnreg_inc<192>();
+        const int q = warp & 3, half = (warp - 4) >> 2, ew = warp - 4;
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -1412,7 +1409,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -36,11 +36,11 @@ static int bench_wgrad(int R, int Nout, bool f16) {
     p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
     const int work = out_tiles * p.ksplits, grid = work < sms ? work : sms;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) kern<<<grid, TCW_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < 3; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 10;
-    for (int i = 0; i < reps; ++i) kern<<<grid, TCW_THREADS, TCF_SMEM_BYTES>>>(p);
+    for (int i = 0; i < reps; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     printf("wgrad%s R=%d Nout=%d (tile_n %d, %d work items, %d rows/split): %.1f us  %.1f TFLOP/s fp32-equivalent\n", f16 ? " [fp16 split]" : "", R, Nout, p.tile_n,
