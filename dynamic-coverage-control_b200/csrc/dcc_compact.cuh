@@ -16,9 +16,20 @@
 // The own-block values are float32 of the float64 state expressions, exactly as the env kernel writes them; the
 // LayerNorm statistics come from closed forms of the same state (see compact_features_kernel).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "dcc_ops.cuh"
 
 namespace dcc {
+
+// fp16 hi/lo split of two fp32 values, packed in memory order (same arithmetic as tc::split_f16_pair)
+__device__ __forceinline__ void tc_split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 
 struct CompactDims {
     int N, M, D, OWN;      // OWN = 2N + 2: the [v_i, p_i, p_k - p_i] head of an observation row
@@ -57,7 +68,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // Outputs (either may be NULL): Fa [rows * N, lda] actor features, Fc [rows, ldc] critic features.
 __global__ void __launch_bounds__(256) compact_features_kernel(const double *__restrict__ pos_vel, const uint8_t *__restrict__ energy,
                                                                float *__restrict__ Fa, float *__restrict__ Fc, int rows,
-                                                               CompactDims cd, int normalize) {
+                                                               CompactDims cd, int normalize, size_t lo_a, size_t lo_c) {
+    // lo_a / lo_c != 0: the rows leave PRE-SPLIT as fp16 hi | lo (hi halves at Fa / Fc, lo halves lo_a / lo_c halves behind
+    // them, row pitch lda / ldc halves) for the TMA-fed GEMMs (tc::TcfParams::a_split); 0: plain float32 rows
     extern __shared__ __align__(16) unsigned char cf_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int N = cd.N, M = cd.M, D = cd.D, OWN = cd.OWN;
@@ -134,7 +147,15 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                     const float src = c < OWN ? s_own[i * OWN + c] : s_tail[c - OWN];
                     v[e] = (c == cm) ? -mean * rstd : src * rstd;
                 }
-                *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                if (lo_a) {
+                    uint32_t h0, l0, h1, l1;
+                    tc_split_pair(v[0], v[1], h0, l0);
+                    tc_split_pair(v[2], v[3], h1, l1);
+                    __half *hp = reinterpret_cast<__half *>(Fa) + ((size_t)r * N + i) * cd.lda + c0;
+                    *reinterpret_cast<uint2 *>(hp) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2 *>(hp + lo_a) = make_uint2(l0, l1);
+                } else
+                    *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
         if (Fc) {
@@ -156,7 +177,15 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                     const float src = c < nown ? s_own[c] : s_tail[c - nown];
                     v[e] = (c == cm) ? -mean_c * rstd_c : src * rstd_c;
                 }
-                *reinterpret_cast<float4 *>(out + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                if (lo_c) {
+                    uint32_t h0, l0, h1, l1;
+                    tc_split_pair(v[0], v[1], h0, l0);
+                    tc_split_pair(v[2], v[3], h1, l1);
+                    __half *hp = reinterpret_cast<__half *>(Fc) + (size_t)r * cd.ldc + c0;
+                    *reinterpret_cast<uint2 *>(hp) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2 *>(hp + lo_c) = make_uint2(l0, l1);
+                } else
+                    *reinterpret_cast<float4 *>(out + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
     }

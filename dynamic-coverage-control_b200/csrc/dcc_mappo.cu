@@ -54,6 +54,8 @@ struct MappoHandle {
     bool f16_dx;     // backend 2: the backward dX = dZ W GEMMs run the fp16-split kernel with a per-tensor power-of-two scale of
                      // dZ (its max |dZ| is produced for free by the LayerNorm-backward kernel that writes dZ); DCC_TC_DX_F16=0 disables
     bool ln_pipe;    // LayerNorm-backward kernels with the bulk-async row pipeline (H % 4 == 0); DCC_LN_PIPE=0 disables
+    bool split16;    // backend 2: activations that only GEMMs consume (inner trunk outputs h_k, compact features) are stored pre-split
+                     // as fp16 hi/lo by their producers and fetched by TMA in the consumers (tc::TcfParams::a_split); DCC_TC_SPLIT=0 disables
     uint32_t *dz_absmax;   // device scalar: bits of max |dZ| for the fp16-split weight-gradient kernel
     NetLayout la, lc;
     int chunk_rows;  // env-step rows per chunk
@@ -188,13 +190,24 @@ static int tc_set_kernel_attributes() {
 
 // C[M,256] = A[M,K] * B^T with B given as a weight image (K-major on both sides).  With `bias` the epilogue is the
 // fused bias + ReLU + LayerNorm of an MLP block: a -> a_out (optional), LN(a) * gamma + beta -> h_out.
+// An activation stored PRE-SPLIT as two fp16 matrices (hi = fp16(x), lo = fp16(x - hi)), row pitch `ld` halves: what the GEMM
+// kernels fetch with TMA instead of splitting fp32 values in their producer warps (tc::TcfParams::a_split).
+struct Split16 {
+    const void *hi, *lo;
+    int ld;
+};
+
+// a16 != nullptr: the A operand is pre-split (A / lda ignored; fp16-split kernel only).  h16 != nullptr (fused epilogue): h leaves
+// pre-split into h16 instead of fp32 h_out.
 static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, const float *img, float *C, int ldc,
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
                        const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
                        bool f16 = false, const uint32_t *a_absmax_bits = nullptr, const float *head_fold = nullptr,
-                       int head_out = 0, float *head_dst = nullptr) {
+                       int head_out = 0, float *head_dst = nullptr, const Split16 *a16 = nullptr, const Split16 *h16 = nullptr) {
     if (M <= 0) return DCC_OK;
-    if ((lda & 3) || (ldc & 3) || (K & 3) || ((uintptr_t)A & 15)) return DCC_ERR_INVALID_ARG;
+    if ((ldc & 3) || (K & 3)) return DCC_ERR_INVALID_ARG;
+    if (!a16 && ((lda & 3) || ((uintptr_t)A & 15))) return DCC_ERR_INVALID_ARG;
+    if (a16 && (!f16 || a_absmax_bits)) return DCC_ERR_INVALID_ARG;
     tc::TcfParams p;
     memset(&p, 0, sizeof p);
     const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;    // `img` must come from tc_prep_weights with the same f16 flag
@@ -205,6 +218,19 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.H = h_out; p.mean = mean; p.rstd = rstd;
     p.act = act_of(h);
     if (bias && head_dst && head_out > 0) { p.head_out = head_out; p.head_fold = head_fold; p.head_dst = head_dst; }
+    if (a16) {
+        p.a_split = 1;
+        if (!tc::tc_make_map_2d_f16(&p.tmAhi, a16->hi, K, M, a16->ld, tc::TC_BK16, tc::TC_BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc::tc_make_map_2d_f16(&p.tmAlo, a16->lo, K, M, a16->ld, tc::TC_BK16, tc::TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))
+            return DCC_ERR_UNSUPPORTED;
+    }
+    if (h16 && bias) {
+        p.h_split = 1;
+        p.H = reinterpret_cast<float *>(const_cast<void *>(h16->hi));     // non-NULL: "store h"
+        if (!tc::tc_make_map_2d_f16(&p.tmHhi, h16->hi, tc::TC_N, M, h16->ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc::tc_make_map_2d_f16(&p.tmHlo, h16->lo, tc::TC_N, M, h16->ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+            return DCC_ERR_UNSUPPORTED;
+    }
     const int row_tiles = (M + tc::TC_BM - 1) / tc::TC_BM;
     // split-K only to fill the GPU when there are few row tiles and a long K (raw-store epilogue only)
     p.splits = 1;
@@ -222,13 +248,14 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
     if (tma_env && p.splits == 1) {
         bool ok = true;
         if (C) ok = ok && tc::tc_make_store_map(&p.tmC, C, M, ldc);
-        if (bias && h_out) ok = ok && tc::tc_make_store_map(&p.tmH, h_out, M, ldc);
+        if (bias && h_out && !p.h_split) ok = ok && tc::tc_make_store_map(&p.tmH, h_out, M, ldc);
         p.use_tma = ok ? 1 : 0;
     }
+    if (p.h_split && !p.use_tma) return DCC_ERR_UNSUPPORTED;      // the pre-split output exists only on the TMA store path
     // L2 prefetch of the activation tiles two stages (64 KB per SM) ahead of the fp16-split kernel's loads; measured:
     // 2 stages > 4 > none > 8, and no gain for the MMA-bound 3xTF32 kernel (DCC_TC_PF=<stages> overrides, 0 = off)
     static const int pf_env = getenv("DCC_TC_PF") ? atoi(getenv("DCC_TC_PF")) : -1;
-    p.pf_dist = pf_env >= 0 ? pf_env : (f16 ? 2 : 0);
+    p.pf_dist = a16 ? 0 : (pf_env >= 0 ? pf_env : (f16 ? 2 : 0));
     if (p.pf_dist > 0 && !tc::tc_make_prefetch_map(&p.tmA, A, M, K, lda, bk)) p.pf_dist = 0;
     const int work = row_tiles * p.splits;
     const int grid = work < h->sm_count ? work : h->sm_count;
@@ -242,11 +269,15 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
 
 // G[256, Nout] += dZ[R,256]^T X[R, Nout]  (tcgen05, MN-major operands; G must already hold the running sum).
 // f16 = the experimental fp16-split variant (X must be a LayerNorm output; one absmax pass over dZ supplies its scale).
+// x16 != nullptr: X is pre-split (X / ldx ignored; forces the fp16-split kernel).  absmax_ready: h->dz_absmax already holds
+// max |dZ| (left by the kernel that wrote dZ), so the separate pass over dZ is skipped.
 static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int ldz, const float *X, int ldx, float *G,
-                         int ldg, cudaStream_t s, bool f16 = false) {
+                         int ldg, cudaStream_t s, bool f16 = false, const Split16 *x16 = nullptr, bool absmax_ready = false) {
     if (R <= 0 || Nout <= 0) return DCC_OK;
-    if ((ldz & 3) || (ldx & 3) || ((uintptr_t)dZ & 15) || ((uintptr_t)X & 15)) return DCC_ERR_INVALID_ARG;
-    if (f16 && !h->dz_absmax) f16 = false;
+    if ((ldz & 3) || ((uintptr_t)dZ & 15)) return DCC_ERR_INVALID_ARG;
+    if (!x16 && ((ldx & 3) || ((uintptr_t)X & 15))) return DCC_ERR_INVALID_ARG;
+    if (x16) f16 = true;
+    if (f16 && !h->dz_absmax) { if (x16) return DCC_ERR_UNSUPPORTED; f16 = false; }
     tc::TcwParams p;
     memset(&p, 0, sizeof p);
     p.dZ = dZ; p.X = X; p.G = G; p.R = R; p.Nout = Nout; p.ldz = ldz; p.ldx = ldx; p.ldg = ldg;
@@ -264,10 +295,18 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
     p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
     const int work = out_tiles * p.ksplits;
     const int grid = work < h->sm_count ? work : h->sm_count;
+    if (x16) {
+        p.x_split = 1;
+        if (!tc::tc_make_map_2d_f16(&p.tmXhi, x16->hi, Nout, R, x16->ld, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc::tc_make_map_2d_f16(&p.tmXlo, x16->lo, Nout, R, x16->ld, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))
+            return DCC_ERR_UNSUPPORTED;
+    }
     if (f16) {
-        DCC_CUDA_TRY(cudaMemsetAsync(h->dz_absmax, 0, sizeof(uint32_t), s));
-        tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
-        h->launches++;
+        if (!absmax_ready) {
+            DCC_CUDA_TRY(cudaMemsetAsync(h->dz_absmax, 0, sizeof(uint32_t), s));
+            tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
+            h->launches++;
+        }
         p.dz_absmax_bits = h->dz_absmax;
         tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
     } else {
@@ -314,6 +353,20 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
     return DCC_OK;
 }
 
+// pre-split storage (h->split16): hi halves at the start of the fp32-sized buffer, lo halves behind them (capacity-based offset)
+static inline Split16 hh_split(const MappoHandle *h, int k) {
+    const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cfg.hidden;
+    return Split16{h->hh[k], reinterpret_cast<const __half *>(h->hh[k]) + cap, h->cfg.hidden};
+}
+static inline Split16 feat_split(const MappoHandle *h, int net) {
+    if (net == 0) {
+        const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda;
+        return Split16{h->x0, reinterpret_cast<const __half *>(h->x0) + cap, h->cd.lda};
+    }
+    const size_t cap = (size_t)h->chunk_rows * h->cd.ldc;
+    return Split16{h->fc, reinterpret_cast<const __half *>(h->fc) + cap, h->cd.ldc};
+}
+
 // compact path: fold the input LayerNorm affine AND the observation structure into fc1 (Wt = (W1 * gamma0) A)
 static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *b1g = net ? h->b1g_c : h->b1g_a;
@@ -339,9 +392,11 @@ static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en,
                             cudaStream_t s) {
     const int wpb = 8;
     const size_t smem = compact_features_smem(h->cd, wpb);
+    const size_t lo_a = h->split16 ? (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda : 0;     // halves; 0 = fp32 rows
+    const size_t lo_c = h->split16 ? (size_t)h->chunk_rows * h->cd.ldc : 0;
     compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, want_actor ? h->x0 : nullptr,
                                                                               want_critic ? h->fc : nullptr, rows, h->cd,
-                                                                              h->cfg.use_feature_normalization ? 1 : 0);
+                                                                              h->cfg.use_feature_normalization ? 1 : 0, lo_a, lo_c);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -378,12 +433,18 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
         const float *Wk = k == 0 ? w1g : P + L.W[k], *bk = k == 0 ? b1g : P + L.b[k];
         if (h->backend == 2) {
             // tcgen05 GEMM with the block's bias + activation + LayerNorm fused into its epilogue (one kernel per block)
-            const bool fuse = head_dst && k == L.nblk - 1;
+            const bool last_blk = k == L.nblk - 1;
+            const bool fuse = head_dst && last_blk;
+            // pre-split operands: the compact features and every inner h_k exist only as fp16 hi/lo (see Split16)
+            const bool in_split = h->split16 && (k > 0 || feat != nullptr), out_split = h->split16 && !last_blk;
+            const Split16 a16 = in_split ? (k == 0 ? feat_split(h, net) : hh_split(h, k - 1)) : Split16{nullptr, nullptr, 0};
+            const Split16 h16 = out_split ? hh_split(h, k) : Split16{nullptr, nullptr, 0};
             rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
-                             bk, P + L.lg[k], P + L.lb[k], fuse ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
+                             bk, P + L.lg[k], P + L.lb[k], (fuse || out_split) ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
                              save ? h->rstd[k] : nullptr,
                              (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k),   // compact features are bounded: fp16-split eligible
-                             nullptr, fuse ? h->head_fold[net] : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr);
+                             nullptr, fuse ? h->head_fold[net] : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr,
+                             in_split ? &a16 : nullptr, out_split ? &h16 : nullptr);
             if (rc) return rc;
             continue;
         }
@@ -412,7 +473,8 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     // head backward + activation/LayerNorm backward of the last block in one pass: dA := dz_last
     // (f16_dx: the kernel that writes a dz also leaves max |dz| in h->dz_absmax for the fp16-split dX GEMM that reads it)
     const bool dx16 = h->f16_dx && last >= 1;
-    uint32_t *amax = dx16 ? h->dz_absmax : nullptr;
+    const bool sp = h->split16 && h->backend == 2;      // weight-gradient X operands (h_{k-1}, compact features) are pre-split
+    uint32_t *amax = (dx16 || sp) ? h->dz_absmax : nullptr;
     if (amax) DCC_CUDA_TRY(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
     if (h->ln_pipe) {
         const size_t ring = (size_t)wpb * RP_SLOTS * H;
@@ -435,15 +497,20 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     int rc;
     float *dz = h->dA, *dx = h->dB;
     for (int k = last; k >= 1; --k) {
-        rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s, wgrad_f16(h, L, k))   // dW_k += dz_k^T h_{k-1}
-                             : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
+        if (sp) {
+            const Split16 x16 = hh_split(h, k - 1);
+            rc = tc_gemm_wgrad(h, rows, H, dz, H, nullptr, H, G + L.W[k], H, s, true, &x16, h->ln_pipe);   // dW_k += dz_k^T h_{k-1}
+        } else
+            rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, H, dz, H, h->hh[k - 1], H, G + L.W[k], H, s, wgrad_f16(h, L, k))
+                                 : launch_gemm(h, true, false, H, H, rows, dz, H, h->hh[k - 1], H, G + L.W[k], H, true, s);
         if (rc) return rc;
         rc = h->backend == 2 ? tc_gemm_fwd(h, rows, H, dz, H, h->img_wt[net][k], dx, H, s, nullptr, nullptr, nullptr, nullptr, nullptr,
                                            nullptr, dx16, dx16 ? h->dz_absmax : nullptr)   // dh_{k-1} = dz_k W_k
                              : launch_gemm(h, false, false, rows, H, H, dz, H, P + L.W[k], H, dx, H, false, s);
         if (rc) return rc;
         if (h->ln_pipe) {
-            uint32_t *am = (dx16 && k - 1 >= 1) ? h->dz_absmax : nullptr;     // dz_{k-1} feeds another dX GEMM only if k-1 >= 1
+            // max |dz_{k-1}|: needed by the next dX GEMM (k-1 >= 1) and by the fp16-split weight-gradient GEMM of block k-1
+            uint32_t *am = ((dx16 && k - 1 >= 1) || (sp && (k - 1 >= 1 || feat))) ? h->dz_absmax : nullptr;
             if (am) DCC_CUDA_TRY(cudaMemsetAsync(am, 0, sizeof(uint32_t), s));
             const size_t ring = (size_t)wpb * RP_SLOTS * 2 * H;
             relu_ln_bwd_pipe_kernel<<<gr, wpb * 32, std::max(ring, (size_t)wpb * 3 * 256) * sizeof(float), s>>>(
@@ -456,7 +523,10 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
         h->launches++;
         float *t = dz; dz = dx; dx = t;
     }
-    if (feat)      // compact path: Gt += dz_0^T f  (unfolded into the fc1 slot once per optimiser step, compact_finalize)
+    if (feat && sp) {   // compact path, pre-split features: Gt += dz_0^T f  (unfolded once per optimiser step, compact_finalize)
+        const Split16 x16 = feat_split(h, net);
+        rc = tc_gemm_wgrad(h, rows, ldf, dz, H, nullptr, ldf, h->gt[net], ldf, s, true, &x16, h->ln_pipe);
+    } else if (feat)
         rc = h->backend == 2 ? tc_gemm_wgrad(h, rows, ldf, dz, H, feat, ldf, h->gt[net], ldf, s, h->f16_wgrad)
                              : launch_gemm(h, true, false, H, ldf, rows, dz, H, feat, ldf, h->gt[net], ldf, true, s);
     else
@@ -554,6 +624,8 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->f16_wgrad = getenv("DCC_TC_WGRAD_F16") && atoi(getenv("DCC_TC_WGRAD_F16")) == 1;
     h->ln_pipe = (cfg->hidden % 4 == 0) && !(getenv("DCC_LN_PIPE") && atoi(getenv("DCC_LN_PIPE")) == 0);
     h->f16_dx = h->backend == 2 && h->ln_pipe && !(getenv("DCC_TC_DX_F16") && atoi(getenv("DCC_TC_DX_F16")) == 0);
+    h->split16 = h->backend == 2 && h->f16_fwd && !(getenv("DCC_TC_SPLIT") && atoi(getenv("DCC_TC_SPLIT")) == 0) &&
+                 !(getenv("DCC_TC_TMA") && atoi(getenv("DCC_TC_TMA")) == 0) && tc::tc_tensor_map_encoder() != nullptr;
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
@@ -1060,10 +1132,40 @@ int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float 
 int dcc_op_gemm(void *handle, int backend, int ta, int tb, int M, int N, int K, const float *A, int lda, const float *B,
                 int ldb, float *C, int ldc, int accumulate, dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
-    if (!h || !A || !B || !C || backend < 0 || backend > 3 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
+    if (!h || !A || !B || !C || backend < 0 || backend > 5 || M < 1 || N < 1 || K < 1) return DCC_ERR_INVALID_ARG;
     DCC_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (backend == 0) backend = h->backend;
+    if (backend == 4 || backend == 5) {
+        // test hooks of the TMA-fed operand paths: 4 = forward-shaped GEMM with a PRE-SPLIT A operand (X W^T and dZ W shapes),
+        // 5 = weight-gradient GEMM dW = dZ^T X with a pre-split X operand (fp16-split kernel, max |dZ| from a separate pass)
+        if (accumulate) return DCC_ERR_UNSUPPORTED;
+        const bool wg = ta && !tb && M == tc::TC_N;
+        if ((backend == 5) != wg || (backend == 4 && (ta || N != tc::TC_N))) return DCC_ERR_UNSUPPORTED;
+        const float *src = wg ? B : A;                 // the operand that is pre-split: X [K rows, N cols] / A [M rows, K cols]
+        const long srows = wg ? K : M;
+        const int scols = wg ? N : K, sld = wg ? ldb : lda, ld16 = (scols + 7) / 8 * 8;
+        __half *hi = nullptr, *lo = nullptr;
+        float *img = nullptr;
+        DCC_CUDA_TRY(cudaMalloc(&hi, (size_t)srows * ld16 * 2));
+        DCC_CUDA_TRY(cudaMalloc(&lo, (size_t)srows * ld16 * 2));
+        tc::tc_split16_kernel<<<h->sm_count * 8, 256, 0, s>>>(src, srows, scols, sld, hi, lo, ld16);
+        const Split16 s16{hi, lo, ld16};
+        int rc;
+        if (wg) {
+            DCC_CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, s));
+            rc = tc_gemm_wgrad(h, K, N, A, lda, nullptr, 0, C, ldc, s, true, &s16, false);
+        } else {
+            const int KT = (K + tc::TC_BK - 1) / tc::TC_BK;
+            DCC_CUDA_TRY(cudaMalloc(&img, (size_t)KT * 2 * tc::TC_B_TILE_FLOATS * sizeof(float)));
+            rc = tc_prep_weights(h, B, ldb, tb == 0, K, img, s, true);
+            if (!rc) rc = tc_gemm_fwd(h, M, K, nullptr, 0, img, C, ldc, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true,
+                                      nullptr, nullptr, 0, nullptr, &s16, nullptr);
+        }
+        cudaStreamSynchronize(s);
+        cudaFree(hi); cudaFree(lo); cudaFree(img);
+        return rc;
+    }
     if (backend == 2 || backend == 3) {
         // shapes the tensor-core kernels cover: X W^T and dZ W (weights on the B side, 256 output features);
         // backend 3 = the fp16-split forward kernel (|A| < 65504, |B| < 255)

@@ -287,6 +287,22 @@ __global__ void tc_absmax_bits_kernel(const float *__restrict__ x, long rows, in
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
+// fp32 matrix [rows, cols] (row pitch ld floats) -> pre-split fp16 hi / lo matrices (row pitch ld16 halves, ld16 % 8 == 0,
+// columns cols..ld16-1 zero).  Test hook / conversion helper for the TMA-fed operand paths (TcfParams::a_split).
+__global__ void tc_split16_kernel(const float *__restrict__ x, long rows, int cols, int ld, __half *__restrict__ hi,
+                                  __half *__restrict__ lo, int ld16) {
+    const long n = rows * (ld16 >> 1);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / (ld16 >> 1);
+        const int c = (int)(i - r * (ld16 >> 1)) * 2;
+        const float a = c < cols ? x[r * ld + c] : 0.f, b = c + 1 < cols ? x[r * ld + c + 1] : 0.f;
+        uint32_t h, l;
+        split_f16_pair(a, b, h, l);
+        *reinterpret_cast<uint32_t *>(hi + r * ld16 + c) = h;
+        *reinterpret_cast<uint32_t *>(lo + r * ld16 + c) = l;
+    }
+}
+
 // power-of-two scale S with absmax * S in [2^13, 2^14) (1 when absmax is zero / denormal) and its inverse, from the bits
 __device__ __forceinline__ void f16_scale_from_absmax(uint32_t bits, float &S, float &invS) {
     const uint32_t e = (bits >> 23) & 0xffu;
@@ -366,6 +382,15 @@ struct TcfParams {
     // ~2 k cycles for HBM with only 16 KB in flight per SM.  0 = off.
     int pf_dist;
     alignas(64) CUtensorMap tmA;
+    // PRE-SPLIT operands (round 2).  An activation that only GEMMs consume — the inner trunk outputs h_k, the compact layer-1
+    // features — is stored as TWO fp16 matrices (hi = fp16(x), lo = fp16(x - hi); 4 bytes per element like fp32) by the
+    // kernel that produces it.  The consuming GEMMs then fetch their operand tiles with TMA tensor loads straight into
+    // the swizzled shared-memory layout the tensor core reads (no producer warps, no conversion traffic through shared
+    // memory); numerically identical to splitting in the consumer's producer warps.
+    //   a_split: A comes from (tmAhi, tmAlo): [M, K] fp16, box 64 (k) x 128 rows, SWIZZLE_128B.  F16 kernel only.
+    //   h_split: H leaves as (tmHhi, tmHlo): [M, 256] fp16, box 32 x 32, SWIZZLE_64B, staged hi | lo in the 4 KB buffer.
+    int a_split, h_split;
+    alignas(64) CUtensorMap tmAhi, tmAlo, tmHhi, tmHlo;
 };
 
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -399,6 +424,26 @@ inline bool tc_make_map_2d(CUtensorMap *tm, const float *base, int cols, int row
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// 2-D fp16 map: `cols` x `rows` elements, row pitch ld halves
+inline bool tc_make_map_2d_f16(CUtensorMap *tm, const void *base, int cols, int rows, int ld, int box_cols, int box_rows,
+                               CUtensorMapSwizzle swizzle) {
+    PFN_tensorMapEncodeTiled enc = tc_tensor_map_encoder();
+    if (!enc || rows < 1 || cols < 1 || (ld & 7) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// TMA tensor load global -> shared (tile at column x, row y), completion counted in bytes on an mbarrier; elements outside the
+// tensor are zero-filled
+__device__ __forceinline__ void tma_load_2d(uint32_t sdst, const CUtensorMap *tm, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(sdst),
+                 "l"((uint64_t)tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // [rows, 256] output matrix -> store map with a 128B-swizzled 32 x 32 box
 inline bool tc_make_store_map(CUtensorMap *tm, const float *base, int rows, int ld) {
     return tc_make_map_2d(tm, base, 256, rows, ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -462,7 +507,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCF_STAGES; ++s) {
-            mbar_init(&full[s], 4 + 1);   // 4 producer warps + the weight-tile expect_tx arrival
+            mbar_init(&full[s], p.a_split ? 1 : 4 + 1);   // 4 producer warps + the expect_tx arrival (pre-split A: TMA only)
             mbar_init(&empty[s], 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -518,7 +563,30 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        if constexpr (F16) {
+        if (F16 && p.a_split) {
+            // pre-split A: one thread feeds the pipeline — per stage two TMA tensor loads (A_hi, A_lo tiles, 16 KB each, rows
+            // past M and columns past K zero-filled) and the two weight bulk copies, all counted on full[s]
+            if (t == 0) {
+                while (w < num_work) {
+                    set_work(w);
+                    const int m0 = (w / p.splits) * TC_BM;
+                    for (; kt < kt1; ++kt, ++it) {
+                        const int s = it % TCF_STAGES;
+                        const uint32_t ph = (it / TCF_STAGES) & 1;
+                        uint8_t *st = smem + s * TCF_STAGE_BYTES;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[s], 2 * TC_A_TILE_FLOATS * 4 + 2 * TC_B_TILE_FLOATS * 4);
+                        tma_load_2d(smem_u32(st), &p.tmAhi, kt * TC_BK16, m0, &full[s]);
+                        tma_load_2d(smem_u32(st) + TC_A_TILE_FLOATS * 4, &p.tmAlo, kt * TC_BK16, m0, &full[s]);
+                        const float *src = p.Bimg + (size_t)kt * (2 * TC_B_TILE_FLOATS);
+                        bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4, src, TC_B_TILE_FLOATS * 4, &full[s]);
+                        bulk_load_g2s(st + 2 * TC_A_TILE_FLOATS * 4 + TC_B_TILE_FLOATS * 4, src + TC_B_TILE_FLOATS,
+                                      TC_B_TILE_FLOATS * 4, &full[s]);
+                    }
+                    w += gridDim.x;
+                }
+            }
+        } else if constexpr (F16) {
             // unit of work = HALF a stage (64 rows x 64 k = 8 float4 per thread), so that the register footprint of
             // the "loads of the next unit in flight while this one is split" scheme stays at two 8 x float4 sets
             auto load_unit = [&](int ww, int kk, int hf, float4 (&v)[8]) {
@@ -929,7 +997,40 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                             __syncwarp();
                             if (lane == 0) { tma_store_2d(&p.tmC, xp_u32, col0, row0); bulk_commit(); }
                         }
-                        if (ln && p.H) {
+                        if (ln && p.H && p.h_split) {
+                            // pre-split output: h leaves as fp16 hi | lo (2 KB boxes side by side in the staging buffer,
+                            // 64-byte rows in the tensor maps' SWIZZLE_64B layout: chunk c of row r at r*64 + ((c ^ ((r>>1)&3)) << 4))
+                            TC_PROF_NOW(t4);
+                            if (lane == 0) bulk_wait_read<0>();
+                            __syncwarp();
+                            TC_PROF_NOW(t5);
+                            TC_PROF_ADD(e_wread, t4, t5);
+                            const uint32_t r64 = xp_u32 + lane * 64;
+                            const int sw2 = (lane >> 1) & 3;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float4 g0 = lane_bcast4(vg, j * 8 + 2 * c), b0 = lane_bcast4(vb, j * 8 + 2 * c);
+                                const float4 g1 = lane_bcast4(vg, j * 8 + 2 * c + 1), b1 = lane_bcast4(vb, j * 8 + 2 * c + 1);
+                                const int e0 = j * 32 + 8 * c;
+                                float4 h0, h1;
+                                h0.x = fmaf((acc[e0 + 0] - mean) * rstd, g0.x, b0.x); h0.y = fmaf((acc[e0 + 1] - mean) * rstd, g0.y, b0.y);
+                                h0.z = fmaf((acc[e0 + 2] - mean) * rstd, g0.z, b0.z); h0.w = fmaf((acc[e0 + 3] - mean) * rstd, g0.w, b0.w);
+                                h1.x = fmaf((acc[e0 + 4] - mean) * rstd, g1.x, b1.x); h1.y = fmaf((acc[e0 + 5] - mean) * rstd, g1.y, b1.y);
+                                h1.z = fmaf((acc[e0 + 6] - mean) * rstd, g1.z, b1.z); h1.w = fmaf((acc[e0 + 7] - mean) * rstd, g1.w, b1.w);
+                                uint4 hi, lo;
+                                split_f16x8(h0, h1, hi, lo);
+                                const uint32_t off = (uint32_t)((c ^ sw2) << 4);
+                                sts128u(r64 + off, hi);
+                                sts128u(r64 + 2048 + off, lo);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&p.tmHhi, xp_u32, col0, row0);
+                                tma_store_2d(&p.tmHlo, xp_u32 + 2048, col0, row0);
+                                bulk_commit();
+                            }
+                        } else if (ln && p.H) {
                             TC_PROF_NOW(t4);
                             if (lane == 0) bulk_wait_read<0>();
                             __syncwarp();
@@ -1036,6 +1137,11 @@ struct TcwParams {
     // fp16-split kernel only: bits of max |dZ| over the tensor (tc_absmax_bits_kernel); dZ is multiplied by the power of
     // two that brings this maximum into [2^13, 2^14) before the split and the partial tile is scaled back before it is added
     const uint32_t *dz_absmax_bits;
+    // fp16-split kernel, pre-split X (see TcfParams): the X operand comes from (tmXhi, tmXlo) — [R, Nout] fp16, box 64 features
+    // x 64 rows, SWIZZLE_128B, which IS the MN-major 16-bit operand layout (64-feature groups of [64 k rows][128 B], 16-byte
+    // chunks XOR (k & 7)) — fetched by TMA tensor loads; the producer warps then convert only dZ (2 of the 6 units of a stage).
+    int x_split;
+    alignas(64) CUtensorMap tmXhi, tmXlo;
 };
 
 //
@@ -1049,9 +1155,10 @@ struct TcwParams {
 // 2048 B per K = 16 instruction: pinned on the GPU with tools/mn16_probe.cu).  dZ is pre-scaled by one power of two per
 // tensor (TcwParams::dz_absmax_bits); X must be a LayerNorm output.
 template <bool F16>
-__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams p) {
+__global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(const __grid_constant__ TcwParams p) {
     constexpr int BKW = F16 ? 64 : TC_BK;          // batch rows per stage
-    constexpr int UNITS = F16 ? 6 : 3;             // 16 KB raw load units per stage: dZ 1 (2), X 2 (4)
+    const bool xs = F16 && p.x_split;              // X operand pre-split in global memory, fetched by TMA
+    const int UNITS = F16 ? (xs ? 2 : 6) : 3;      // 16 KB raw load units per stage: dZ 1 (2), X 2 (4; 0 when pre-split)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float *xpose = reinterpret_cast<float *>(smem + TCF_STAGES * TCF_STAGE_BYTES);
@@ -1065,7 +1172,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCF_STAGES; ++s) {
-            mbar_init(&full[s], 4);       // 4 producer warps
+            mbar_init(&full[s], (F16 && p.x_split) ? 5 : 4);   // 4 producer warps (+ the expect_tx arrival of the X tiles)
             mbar_init(&empty[s], 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -1197,6 +1304,17 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                 mbar_wait(&empty[s], ph ^ 1);
                 TC_PROF_NOW(pw1);
                 TC_PROF_ADD(p_wait_acc, pw0, pw1);
+                if (xs && t == 0) {
+                    // the stage's X tiles: one 64 x 64 box per 64-feature group and half (hi, lo), 8 KB each
+                    const int ot = cw % out_tiles;
+                    const int xn0 = (ot >> 1) * p.tile_n;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)cur_ngroups * 2u * 8192u);
+                    const uint32_t sb = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
+                    for (int g = 0; g < cur_ngroups; ++g) {
+                        tma_load_2d(sb + g * 8192, &p.tmXhi, xn0 + g * 64, c_r0, &full[s]);
+                        tma_load_2d(sb + TC_B_TILE_FLOATS * 4 + g * 8192, &p.tmXlo, xn0 + g * 64, c_r0, &full[s]);
+                    }
+                }
             }
             if constexpr (F16) {
                 if (cur_kind < 2) {
@@ -1211,6 +1329,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(TcwParams
                         const uint32_t off = (uint32_t)((c >> 3) * 8192 + k * 128 + (((c & 7) ^ (k & 7)) << 4));
                         sts128u(st_u32 + off, hi);
                         sts128u(st_u32 + TC_A_TILE_FLOATS * 4 + off, lo);
+                    }
+                    if (xs && cur_kind == 1) {      // pre-split X: the stage is complete once both dZ units are stored
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
+                        ++it;
                     }
                 } else {
                     const uint32_t sb_u32 = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
