@@ -134,7 +134,29 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
             s_stat[lane] = mean; s_stat[N + lane] = rstd;
         }
         __syncwarp();
-        if (Fa) {
+        if (Fa && lo_a) {
+            // pre-split rows: 8 columns per step, one 16-byte store each for the hi and the lo halves
+            const int cm = OWN + 2 * M + 1;
+            const int nv = cd.lda >> 3;
+            __half *fa16 = reinterpret_cast<__half *>(Fa);
+            for (int q8 = lane; q8 < N * nv; q8 += 32) {
+                const int i = q8 / nv, c0 = (q8 - i * nv) << 3;
+                const float mean = s_stat[i], rstd = s_stat[N + i];
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c0 + e;
+                    const float src = c < OWN ? s_own[i * OWN + c] : s_tail[c - OWN];
+                    v[e] = (c == cm) ? -mean * rstd : src * rstd;
+                }
+                uint4 hi, lo;
+                tc_split_pair(v[0], v[1], hi.x, lo.x); tc_split_pair(v[2], v[3], hi.y, lo.y);
+                tc_split_pair(v[4], v[5], hi.z, lo.z); tc_split_pair(v[6], v[7], hi.w, lo.w);
+                __half *hp = fa16 + ((size_t)r * N + i) * cd.lda + c0;
+                *reinterpret_cast<uint4 *>(hp) = hi;
+                *reinterpret_cast<uint4 *>(hp + lo_a) = lo;
+            }
+        } else if (Fa) {
             const int cm = OWN + 2 * M + 1;      // column of -mean * rstd
             const int nv = cd.lda >> 2;
             for (int q4 = lane; q4 < N * nv; q4 += 32) {
@@ -147,15 +169,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                     const float src = c < OWN ? s_own[i * OWN + c] : s_tail[c - OWN];
                     v[e] = (c == cm) ? -mean * rstd : src * rstd;
                 }
-                if (lo_a) {
-                    uint32_t h0, l0, h1, l1;
-                    tc_split_pair(v[0], v[1], h0, l0);
-                    tc_split_pair(v[2], v[3], h1, l1);
-                    __half *hp = reinterpret_cast<__half *>(Fa) + ((size_t)r * N + i) * cd.lda + c0;
-                    *reinterpret_cast<uint2 *>(hp) = make_uint2(h0, h1);
-                    *reinterpret_cast<uint2 *>(hp + lo_a) = make_uint2(l0, l1);
-                } else
-                    *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
         if (Fc) {
