@@ -235,9 +235,10 @@ class MAPPOPolicy:
         return int(self.lib.dcc_mappo_launch_count(self._h))
 
     def gemm_backend(self):
-        # backend 2: 3xTF32 everywhere except the forward GEMMs on LayerNorm outputs, which run the fp16 hi/lo split
-        # kernel (same accuracy; DCC_TC_F16=0 keeps them on 3xTF32)
-        return {1: "simt-fp32", 2: "tcgen05-3xtf32"}[int(self.lib.dcc_mappo_gemm_backend(self._h))]
+        # backend 2: tcgen05 GEMMs in split precision at fp32-FFMA accuracy — fp16 hi/lo split (forward, dX and weight-gradient
+        # GEMMs fed by TMA from pre-split operands) with 3xTF32 where an operand is not range-bounded (raw observations);
+        # the DCC_TC_* knobs move individual GEMMs back to 3xTF32
+        return {1: "simt-fp32", 2: "tcgen05-split-fp16/3xtf32"}[int(self.lib.dcc_mappo_gemm_backend(self._h))]
 
     # ---- reference surface ---------------------------------------------------------------------------------
     def lr_decay(self, episode, episodes):
