@@ -72,6 +72,7 @@ SIGNATURES = {
     "dcc_mappo_act_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _VP, _VP, _VP, _VP]),
     "dcc_mappo_evaluate_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
     "dcc_mappo_epoch_grads_state": (C.c_int, [_VP] * 13 + [C.c_double, C.c_int, C.c_int, _VP, _VP]),
+    "dcc_mappo_minibatch_grads_state": (C.c_int, [_VP] * 13 + [C.c_double, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
     "dcc_obs_from_state": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP]),
     "dcc_rollout_insert": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP]),
     "dcc_mappo_gae": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),

@@ -479,8 +479,6 @@ class MAPPOTrainer:
                     ptr(self._epoch_stats[ep]), s), "dcc_mappo_epoch_grads_state")
                 self._apply(ep, update_actor)
                 continue
-            if getattr(buffer, "compact", False):
-                raise NotImplementedError("num_mini_batch > 1 needs the materialised rollout (compact_rollout: false)")
             if nmb == 1:
                 _lib.check(lib.dcc_mappo_epoch_grads(
                     p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
@@ -496,6 +494,14 @@ class MAPPOTrainer:
                 _lib.check(lib.dcc_mappo_minibatch_stats(p._h, ptr(buffer.returns_te), ptr(idx), mbs,
                                                          ptr(self._mb_sums[u]), s), "dcc_mappo_minibatch_stats")
                 self.comm.all_reduce_sum_(self._mb_sums[u])
+                if getattr(buffer, "compact", False):
+                    _lib.check(lib.dcc_mappo_minibatch_grads_state(
+                        p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
+                        ptr(buffer.state_pv), ptr(buffer.state_en), ptr(buffer.actions), ptr(buffer.action_log_probs_ten),
+                        ptr(buffer.values_te), ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, ptr(idx), mbs,
+                        ptr(self._mb_sums[u]), mbs_global, ptr(self._epoch_stats[u]), s), "dcc_mappo_minibatch_grads_state")
+                    self._apply(u, update_actor)
+                    continue
                 _lib.check(lib.dcc_mappo_minibatch_grads(
                     p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads),
                     ptr(buffer.obs), ptr(buffer.actions), ptr(buffer.action_log_probs_ten), ptr(buffer.values_te),

@@ -68,7 +68,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // Outputs (either may be NULL): Fa [rows * N, lda] actor features, Fc [rows, ldc] critic features.
 __global__ void __launch_bounds__(256) compact_features_kernel(const double *__restrict__ pos_vel, const uint8_t *__restrict__ energy,
                                                                float *__restrict__ Fa, float *__restrict__ Fc, int rows,
-                                                               CompactDims cd, int normalize, size_t lo_a, size_t lo_c) {
+                                                               CompactDims cd, int normalize, size_t lo_a, size_t lo_c,
+                                                               const long long *__restrict__ ridx = nullptr) {
+    // ridx (optional, minibatch path: feed_forward_generator draws AGENT rows, shared_buffer.py:238-262): output row k is
+    // built from state row ridx[k] / N; the actor row is that of agent ridx[k] % N alone (Fa [rows, lda]) and the critic row
+    // the centralised row of that env step (Fc [rows, ldc], one per sampled agent row, as the reference evaluates it).
     // lo_a / lo_c != 0: the rows leave PRE-SPLIT as fp16 hi | lo (hi halves at Fa / Fc, lo halves lo_a / lo_c halves behind
     // them, row pitch lda / ldc halves) for the TMA-fed GEMMs (tc::TcfParams::a_split); 0: plain float32 rows
     extern __shared__ __align__(16) unsigned char cf_smem[];
@@ -84,8 +88,11 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
     float *s_stat = s_tail + tail;                             // [N] mean, [N] rstd
     // constant part of the tail: 1 at 2M, zeros behind it
     for (int c = 2 * M + lane; c < tail; c += 32) s_tail[c] = (c == 2 * M) ? 1.f : 0.f;
-    for (int r = blockIdx.x * wpb + wib; r < rows; r += gridDim.x * wpb) {
+    for (int ro = blockIdx.x * wpb + wib; ro < rows; ro += gridDim.x * wpb) {
         __syncwarp();
+        // r = state row read; ro = output row; ag = the one agent whose actor row is wanted (-1: all N, whole-rollout path)
+        const size_t r = ridx ? (size_t)(ridx[ro] / N) : (size_t)ro;
+        const int ag = ridx ? (int)(ridx[ro] % N) : -1;
         double px = 0.0, py = 0.0, vx = 0.0, vy = 0.0;
         if (lane < N) {
             const double2 pp = *reinterpret_cast<const double2 *>(pos_vel + ((size_t)r * N + lane) * 4);
@@ -139,8 +146,10 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
             const int cm = OWN + 2 * M + 1;
             const int nv = cd.lda >> 3;
             __half *fa16 = reinterpret_cast<__half *>(Fa);
-            for (int q8 = lane; q8 < N * nv; q8 += 32) {
-                const int i = q8 / nv, c0 = (q8 - i * nv) << 3;
+            const int na = ag < 0 ? N : 1;                       // actor rows written for this output row
+            for (int q8 = lane; q8 < na * nv; q8 += 32) {
+                const int il = q8 / nv, c0 = (q8 - il * nv) << 3;
+                const int i = ag < 0 ? il : ag;
                 const float mean = s_stat[i], rstd = s_stat[N + i];
                 float v[8];
 #pragma unroll
@@ -152,15 +161,17 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                 uint4 hi, lo;
                 tc_split_pair(v[0], v[1], hi.x, lo.x); tc_split_pair(v[2], v[3], hi.y, lo.y);
                 tc_split_pair(v[4], v[5], hi.z, lo.z); tc_split_pair(v[6], v[7], hi.w, lo.w);
-                __half *hp = fa16 + ((size_t)r * N + i) * cd.lda + c0;
+                __half *hp = fa16 + (ag < 0 ? (size_t)ro * N + i : (size_t)ro) * cd.lda + c0;
                 *reinterpret_cast<uint4 *>(hp) = hi;
                 *reinterpret_cast<uint4 *>(hp + lo_a) = lo;
             }
         } else if (Fa) {
             const int cm = OWN + 2 * M + 1;      // column of -mean * rstd
             const int nv = cd.lda >> 2;
-            for (int q4 = lane; q4 < N * nv; q4 += 32) {
-                const int i = q4 / nv, c0 = (q4 - i * nv) << 2;
+            const int na = ag < 0 ? N : 1;
+            for (int q4 = lane; q4 < na * nv; q4 += 32) {
+                const int il = q4 / nv, c0 = (q4 - il * nv) << 2;
+                const int i = ag < 0 ? il : ag;
                 const float mean = s_stat[i], rstd = s_stat[N + i];
                 float v[4];
 #pragma unroll
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                     const float src = c < OWN ? s_own[i * OWN + c] : s_tail[c - OWN];
                     v[e] = (c == cm) ? -mean * rstd : src * rstd;
                 }
-                *reinterpret_cast<float4 *>(Fa + ((size_t)r * N + i) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(Fa + (ag < 0 ? (size_t)ro * N + i : (size_t)ro) * cd.lda + c0) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
         if (Fc) {
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                 rstd_c = (float)(1.0 / sqrt(var + (double)LN_EPS));
             }
             const int cm = nown + 2 * M + 1;
-            float *out = Fc + (size_t)r * cd.ldc;
+            float *out = Fc + (size_t)ro * cd.ldc;
             for (int c0 = lane << 2; c0 < cd.ldc; c0 += 128) {
                 float v[4];
 #pragma unroll
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                     uint32_t h0, l0, h1, l1;
                     tc_split_pair(v[0], v[1], h0, l0);
                     tc_split_pair(v[2], v[3], h1, l1);
-                    __half *hp = reinterpret_cast<__half *>(Fc) + (size_t)r * cd.ldc + c0;
+                    __half *hp = reinterpret_cast<__half *>(Fc) + (size_t)ro * cd.ldc + c0;
                     *reinterpret_cast<uint2 *>(hp) = make_uint2(h0, h1);
                     *reinterpret_cast<uint2 *>(hp + lo_c) = make_uint2(l0, l1);
                 } else

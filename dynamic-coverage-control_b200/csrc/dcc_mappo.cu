@@ -388,15 +388,16 @@ static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int 
 }
 
 // compact path: features of `rows` env-step rows -> x0 (actor, [rows*N, lda]) and fc (critic, [rows, ldc])
+// ridx != nullptr (minibatch path): output row k comes from agent row ridx[k] (see compact_features_kernel)
 static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en, int rows, bool want_actor, bool want_critic,
-                            cudaStream_t s) {
+                            cudaStream_t s, const long long *ridx = nullptr) {
     const int wpb = 8;
     const size_t smem = compact_features_smem(h->cd, wpb);
     const size_t lo_a = h->split16 ? (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda : 0;     // halves; 0 = fp32 rows
     const size_t lo_c = h->split16 ? (size_t)h->chunk_rows * h->cd.ldc : 0;
     compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, want_actor ? h->x0 : nullptr,
                                                                               want_critic ? h->fc : nullptr, rows, h->cd,
-                                                                              h->cfg.use_feature_normalization ? 1 : 0, lo_a, lo_c);
+                                                                              h->cfg.use_feature_normalization ? 1 : 0, lo_a, lo_c, ridx);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
@@ -1040,33 +1041,28 @@ int dcc_mappo_minibatch_stats(void *handle, const float *d_returns, const int64_
     return DCC_OK;
 }
 
-int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
-                              const float *d_obs, const float *d_actions, const float *d_logp_old, const float *d_values,
-                              const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global,
-                              const int64_t *d_row_index, int64_t n_index, const double *d_ret_sums,
-                              double n_index_global, double *d_epoch_stats, dcc_stream_t stream) {
-    MappoHandle *h = as_mappo(handle);
-    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_actions || !d_logp_old || !d_values ||
-        !d_returns || !d_stats4 || !d_row_index || !d_ret_sums || !d_epoch_stats || n_index < 1 ||
-        !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
-        return DCC_ERR_INVALID_ARG;
-    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
-    DCC_DEVICE_GUARD(h->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+static int minibatch_grads_impl(MappoHandle *h, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                                const float *d_obs, const double *d_pv, const uint8_t *d_en, const float *d_actions,
+                                const float *d_logp_old, const float *d_values, const float *d_returns, float *d_vn_state,
+                                const double *d_stats4, double n_rows_global, const int64_t *d_row_index, int64_t n_index,
+                                const double *d_ret_sums, double n_index_global, double *d_epoch_stats, cudaStream_t s) {
     const int N = h->cfg.n_agents, H = h->cfg.hidden;
     const NetLayout &LA = h->la, &LC = h->lc;
     const long long *idx = reinterpret_cast<const long long *>(d_row_index);
+    const bool cmp = d_obs == nullptr;      // compact rollout: rows come from the stored env state, gathered through the permutation
     int rc;
-    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_ret_sums, n_index_global, d_epoch_stats, s)))
+    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_ret_sums, n_index_global, d_epoch_stats, s, cmp)))
         return rc;
     const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
     const PpoLossParams P = loss_params(h, n_index_global);
     const long RA = (long)h->chunk_rows * N;     // agent rows the actor scratch holds
+    const float *fa = cmp ? h->x0 : nullptr, *fcr = cmp ? h->fc : nullptr;
     for (long k0 = 0; k0 < n_index; k0 += RA) {
         const int nk = (int)std::min<long>(RA, n_index - k0);
-        // actor on the minibatch's agent rows, observation rows gathered through the permutation
+        // actor on the minibatch's agent rows, observation rows (or state features) gathered through the permutation
         const bool fh = fused_head(h);
-        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, idx + k0, 1, nullptr, 0, fh ? h->mu : nullptr))) return rc;
+        if (cmp && (rc = compact_features(h, d_pv, d_en, nk, true, false, s, idx + k0))) return rc;
+        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, nk, true, s, cmp ? nullptr : idx + k0, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
         if (fh)
             gauss_finish_kernel<<<(nk + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions), h->mu, h->logp,
                                                                 nk, 1, 0, 0, 0, 0, idx + k0);
@@ -1079,13 +1075,14 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
                                                                   d_returns, d_values, vn_snapshot(h), d_stats4, n_rows_global,
                                                                   idx + k0, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nk, P);
         h->launches++;
-        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nk, s))) return rc;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nk, s, fa, h->cd.lda))) return rc;
         // critic as the reference evaluates it here: one centralised row PER AGENT ROW of the minibatch (the N agent
         // rows of an env step land in different minibatches, so the once-per-env shortcut does not apply)
         for (long c0 = 0; c0 < nk; c0 += h->chunk_rows) {
             const int nc = (int)std::min<long>(h->chunk_rows, nk - c0);
             const long long *ci = idx + k0 + c0;
-            if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, ci, N, nullptr, 0, fh ? h->vnew : nullptr))) return rc;
+            if (cmp && (rc = compact_features(h, d_pv, d_en, nc, false, true, s, ci))) return rc;
+            if ((rc = trunk_forward(h, LC, critic, 1, d_obs, nc, true, s, cmp ? nullptr : ci, N, fcr, h->cd.ldc, fh ? h->vnew : nullptr))) return rc;
             if (!fh) {
                 critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
                 h->launches++;
@@ -1093,13 +1090,53 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
             ppo_value_loss_kernel<<<(nc + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats,
                                                                   nc, P, ci);
             h->launches++;
-            if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nc, s))) return rc;
+            if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nc, s, fcr, h->cd.ldc))) return rc;
         }
     }
-    if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
-    if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    if (cmp) {
+        if ((rc = compact_finalize(h, LA, actor, 0, grad_actor, s))) return rc;
+        if ((rc = compact_finalize(h, LC, critic, 1, grad_critic, s))) return rc;
+    } else {
+        if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
+        if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    }
     DCC_CUDA_TRY(cudaGetLastError());
     return DCC_OK;
+}
+
+int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                              const float *d_obs, const float *d_actions, const float *d_logp_old, const float *d_values,
+                              const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global,
+                              const int64_t *d_row_index, int64_t n_index, const double *d_ret_sums,
+                              double n_index_global, double *d_epoch_stats, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_actions || !d_logp_old || !d_values ||
+        !d_returns || !d_stats4 || !d_row_index || !d_ret_sums || !d_epoch_stats || n_index < 1 ||
+        !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    DCC_DEVICE_GUARD(h->device);
+    return minibatch_grads_impl(h, actor, critic, grad_actor, grad_critic, d_obs, nullptr, nullptr, d_actions, d_logp_old, d_values,
+                                d_returns, d_vn_state, d_stats4, n_rows_global, d_row_index, n_index, d_ret_sums, n_index_global,
+                                d_epoch_stats, static_cast<cudaStream_t>(stream));
+}
+
+int dcc_mappo_minibatch_grads_state(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                                    const double *d_pos_vel, const uint8_t *d_energy, const float *d_actions,
+                                    const float *d_logp_old, const float *d_values, const float *d_returns, float *d_vn_state,
+                                    const double *d_stats4, double n_rows_global, const int64_t *d_row_index, int64_t n_index,
+                                    const double *d_ret_sums, double n_index_global, double *d_epoch_stats, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_pos_vel || !d_energy || !d_actions || !d_logp_old ||
+        !d_values || !d_returns || !d_stats4 || !d_row_index || !d_ret_sums || !d_epoch_stats || n_index < 1 ||
+        !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    if (!h->compact) return DCC_ERR_UNSUPPORTED;     // dcc_mappo_set_env_layout first
+    DCC_DEVICE_GUARD(h->device);
+    return minibatch_grads_impl(h, actor, critic, grad_actor, grad_critic, nullptr, d_pos_vel, d_energy, d_actions, d_logp_old,
+                                d_values, d_returns, d_vn_state, d_stats4, n_rows_global, d_row_index, n_index, d_ret_sums,
+                                n_index_global, d_epoch_stats, static_cast<cudaStream_t>(stream));
 }
 
 int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float *adam_m, float *adam_v, float lr,

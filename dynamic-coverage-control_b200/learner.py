@@ -74,13 +74,14 @@ class Learner:
 
         # 3. rollout storage.  Compact whenever the path allows it: the rollout keeps the env's compact
         # state (320 B per env step at 8/64 instead of 10.8 KB of observation rows) and the learner kernels evaluate
-        # the first layer from it.  `compact_rollout: false` forces the materialised (T+1, E, N, D) observation tensor;
-        # num_mini_batch > 1, per-env PoI layouts and a decentralised critic need it and select it automatically.
+        # the first layer from it (also for num_mini_batch > 1: rows are gathered from the state through the permutation).
+        # `compact_rollout: false` forces the materialised (T+1, E, N, D) observation tensor; per-env PoI layouts and a
+        # decentralised critic need it and select it automatically.
         want = getattr(cfg, "compact_rollout", None)
-        can = (getattr(cfg, "use_centralized_V", True) and int(cfg.num_mini_batch) == 1 and
+        can = (getattr(cfg, "use_centralized_V", True) and
                self.train_envs.pos_pois_per_env is None and not getattr(cfg, "numpy_compat", False))
         if want and not can:
-            raise NotImplementedError("compact_rollout needs use_centralized_V, num_mini_batch 1 and a shared PoI layout")
+            raise NotImplementedError("compact_rollout needs use_centralized_V and a shared PoI layout")
         self.compact = bool(can if want is None else want)
         if self.compact:
             self.compact = self.policy.set_env_layout(self.train_envs.pos_pois, self.train_envs.cfg.m_energy)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCC_ABI_VERSION 6
+#define DCC_ABI_VERSION 7
 #define DCC_MAX_AGENTS 32 /* one warp lane per UAV */
 
 typedef enum dcc_status {
@@ -275,6 +275,7 @@ int dcc_mappo_evaluate(void *handle, const float *d_actor, const float *d_critic
  *   dcc_mappo_act_state         dcc_mappo_act            with (d_pos_vel, d_energy) in place of d_obs
  *   dcc_mappo_evaluate_state    dcc_mappo_evaluate       likewise
  *   dcc_mappo_epoch_grads_state dcc_mappo_epoch_grads    likewise (rows = T*E env steps, time-major like the obs buffer)
+ *   dcc_mappo_minibatch_grads_state  dcc_mappo_minibatch_grads likewise (num_mini_batch > 1)
  *   dcc_obs_from_state          regenerates the observation rows [n_rows, N, D] float32, bit-identical to dcc_env_step's
  *                               (the reference-shaped view `buffer.obs[t]` of a compact rollout)
  */
@@ -292,6 +293,15 @@ int dcc_mappo_epoch_grads_state(void *handle, const float *d_actor, const float 
                                 int T, int E, double *d_epoch_stats, dcc_stream_t stream);
 int dcc_obs_from_state(void *handle, const double *d_pos_vel, const uint8_t *d_energy, int n_rows, float *d_obs,
                        dcc_stream_t stream);
+/* dcc_mappo_minibatch_grads on a compact rollout: the rows of the minibatch (agent-row indices of the generator's
+ * permutation, buffer/shared_buffer.py:238-262) are gathered from the stored state — the actor features of agent
+ * idx % N of state row idx / N, the critic's centralised features of that state row once per sampled agent row. */
+int dcc_mappo_minibatch_grads_state(void *handle, const float *d_actor, const float *d_critic, float *d_grad_actor,
+                                    float *d_grad_critic, const double *d_pos_vel, const uint8_t *d_energy,
+                                    const float *d_actions, const float *d_logp_old, const float *d_values,
+                                    const float *d_returns, float *d_vn_state, const double *d_stats4, double n_rows_global,
+                                    const int64_t *d_row_index, int64_t n_index, const double *d_ret_sums,
+                                    double n_index_global, double *d_epoch_stats, dcc_stream_t stream);
 
 /*
  * Replaces the per-step bookkeeping of Learner.insert (learner.py:254-276): reward of the env (entry 0 of the N

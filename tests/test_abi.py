@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.dcc_abi_version() == 6
+    assert lib.dcc_abi_version() == 7
     assert lib.dcc_status_string(0) == b"ok"
     assert b"invalid" in lib.dcc_status_string(-1)
     assert lib.dcc_env_obs_dim(4, 20) == 110 and lib.dcc_env_obs_dim(8, 64) == 338
