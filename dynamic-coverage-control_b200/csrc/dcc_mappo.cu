@@ -358,12 +358,18 @@ static inline Split16 hh_split(const MappoHandle *h, int k) {
     const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cfg.hidden;
     return Split16{h->hh[k], reinterpret_cast<const __half *>(h->hh[k]) + cap, h->cfg.hidden};
 }
+// Critic rows one pass may hold on the compact path.  The activation scratch is sized for the actor's chunk * N agent rows,
+// the critic runs ONE row per env step: it is therefore fed N chunks' worth of env steps at a time (a "super-chunk"), so that its
+// GEMMs see the same 16 waves of row tiles as the actor's instead of 2 (per tile they ran 2x slower: pipeline fill, weight
+// fetch and launch latency of a 2-wave grid).  The feature matrix `fc`, `vnew` and `dv` are sized to match.
+static inline size_t critic_cap_rows(const MappoHandle *h) { return (size_t)h->chunk_rows * h->cfg.n_agents; }
+
 static inline Split16 feat_split(const MappoHandle *h, int net) {
     if (net == 0) {
         const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda;
         return Split16{h->x0, reinterpret_cast<const __half *>(h->x0) + cap, h->cd.lda};
     }
-    const size_t cap = (size_t)h->chunk_rows * h->cd.ldc;
+    const size_t cap = critic_cap_rows(h) * h->cd.ldc;
     return Split16{h->fc, reinterpret_cast<const __half *>(h->fc) + cap, h->cd.ldc};
 }
 
@@ -389,14 +395,19 @@ static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int 
 
 // compact path: features of `rows` env-step rows -> x0 (actor, [rows*N, lda]) and fc (critic, [rows, ldc])
 // ridx != nullptr (minibatch path): output row k comes from agent row ridx[k] (see compact_features_kernel)
+// fc_row0: the critic rows land at row fc_row0 of `fc` (super-chunks: N actor chunks fill one critic pass, critic_cap_rows)
 static int compact_features(MappoHandle *h, const double *pv, const uint8_t *en, int rows, bool want_actor, bool want_critic,
-                            cudaStream_t s, const long long *ridx = nullptr) {
+                            cudaStream_t s, const long long *ridx = nullptr, size_t fc_row0 = 0) {
     const int wpb = 8;
     const size_t smem = compact_features_smem(h->cd, wpb);
     const size_t lo_a = h->split16 ? (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda : 0;     // halves; 0 = fp32 rows
-    const size_t lo_c = h->split16 ? (size_t)h->chunk_rows * h->cd.ldc : 0;
+    const size_t lo_c = h->split16 ? critic_cap_rows(h) * h->cd.ldc : 0;
+    if (fc_row0 + (size_t)rows > critic_cap_rows(h)) return DCC_ERR_INVALID_ARG;
+    // row offset into fc: rows are ldc halves apart when pre-split (hi block first), ldc floats otherwise
+    float *fc_dst = h->split16 ? reinterpret_cast<float *>(reinterpret_cast<__half *>(h->fc) + fc_row0 * h->cd.ldc)
+                               : h->fc + fc_row0 * h->cd.ldc;
     compact_features_kernel<<<grid_for_rows(h, rows, wpb), wpb * 32, smem, s>>>(pv, en, want_actor ? h->x0 : nullptr,
-                                                                              want_critic ? h->fc : nullptr, rows, h->cd,
+                                                                              want_critic ? fc_dst : nullptr, rows, h->cd,
                                                                               h->cfg.use_feature_normalization ? 1 : 0, lo_a, lo_c, ridx);
     h->launches++;
     DCC_CUDA_TRY(cudaGetLastError());
@@ -668,7 +679,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     }
     alloc(&h->dA, RA * H); alloc(&h->dB, RA * H);
     alloc(&h->w1g_a, (size_t)H * D); alloc(&h->b1g_a, H); alloc(&h->w1g_c, (size_t)H * N * D); alloc(&h->b1g_c, H);
-    alloc(&h->mu, RA * 2); alloc(&h->logp, RA); alloc(&h->dmu, RA * 2); alloc(&h->vnew, chunk); alloc(&h->dv, chunk);
+    alloc(&h->mu, RA * 2); alloc(&h->logp, RA); alloc(&h->dmu, RA * 2); alloc(&h->vnew, RA); alloc(&h->dv, RA);   // critic: critic_cap_rows
     alloc(&h->vn_gae, 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
     if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
@@ -807,7 +818,7 @@ int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, d
     h->d_poi = nullptr; h->fc = nullptr; h->compact = false;
     const int H = h->cfg.hidden;
     cudaError_t ce = cudaMalloc(&h->d_poi, sizeof(double) * 2 * n_pois);
-    if (ce == cudaSuccess) ce = cudaMalloc(&h->fc, (size_t)h->chunk_rows * cd.ldc * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&h->fc, critic_cap_rows(h) * cd.ldc * sizeof(float));
     const int lds[2] = {cd.lda, cd.ldc};
     for (int n = 0; n < 2 && ce == cudaSuccess; ++n) {
         ce = cudaMalloc(&h->wt[n], (size_t)H * lds[n] * sizeof(float));
@@ -951,38 +962,51 @@ static int epoch_grads_impl(MappoHandle *h, const float *actor, const float *cri
     const PpoLossParams P = loss_params(h, n_rows_global * N);
     const long R = (long)T * E;
     const float *fa = cmp ? h->x0 : nullptr, *fcr = cmp ? h->fc : nullptr;
-    for (long r0 = 0; r0 < R; r0 += h->chunk_rows) {
-        const int nr = (int)std::min<long>(h->chunk_rows, R - r0);
-        const float *x = cmp ? nullptr : d_obs + (size_t)r0 * N * D;
-        // compact path: one pass over the chunk's 32 N + M bytes of state per row yields both nets' layer-1 operands
-        if (cmp && (rc = compact_features(h, d_pv + (size_t)r0 * N * 4, d_en + (size_t)r0 * h->cd.M, nr, true, true, s))) return rc;
-        // actor and critic share one activation scratch, so the chunk is processed net by net:
-        // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
-        const bool fh = fused_head(h);
-        if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
-        if (fh)
-            gauss_finish_kernel<<<(nr * N + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
-                                                                    h->mu, h->logp, nr * N, 1, 0, 0, 0, 0);
-        else
-            actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
-                h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
-                h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
-        h->launches++;
-        ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
-            h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
-            d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
-        h->launches++;
-        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s, fa, h->cd.lda))) return rc;
+    // Compact path: the critic (one row per env step) is run once per SUPER-chunk of N actor chunks (critic_cap_rows): the
+    // feature kernel of every actor chunk appends that chunk's critic rows to `fc`, and the critic's forward / loss / backward
+    // then see chunk * N rows = as many row tiles as the actor's kernels.  DCC_CRITIC_SUPER=0 (A/B knob) and the
+    // materialised path (whose xhat scratch holds one chunk of critic rows) keep one critic pass per actor chunk.
+    static const bool super_env = !(getenv("DCC_CRITIC_SUPER") && atoi(getenv("DCC_CRITIC_SUPER")) == 0);
+    const long SR = (cmp && super_env) ? (long)critic_cap_rows(h) : (long)h->chunk_rows;
+    const bool fh = fused_head(h);
+    for (long s0 = 0; s0 < R; s0 += SR) {
+        const long ns = std::min<long>(SR, R - s0);
+        for (long r0 = s0; r0 < s0 + ns; r0 += h->chunk_rows) {
+            const int nr = (int)std::min<long>(h->chunk_rows, s0 + ns - r0);
+            const float *x = cmp ? nullptr : d_obs + (size_t)r0 * N * D;
+            // compact path: one pass over the chunk's 32 N + M bytes of state per row yields both nets' layer-1 operands
+            if (cmp && (rc = compact_features(h, d_pv + (size_t)r0 * N * 4, d_en + (size_t)r0 * h->cd.M, nr, true, true, s, nullptr,
+                                              (size_t)(r0 - s0))))
+                return rc;
+            // actor and critic share one activation scratch, so the nets are processed one after the other:
+            // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
+            if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
+            if (fh)
+                gauss_finish_kernel<<<(nr * N + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+                                                                        h->mu, h->logp, nr * N, 1, 0, 0, 0, 0);
+            else
+                actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
+                    h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
+                    h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
+            h->launches++;
+            ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
+                h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
+                d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
+            h->launches++;
+            if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s, fa, h->cd.lda))) return rc;
+        }
         // 2) critic (one row per env step: the N agent rows of the reference are identical): forward -> value loss -> backward
-        if ((rc = trunk_forward(h, LC, critic, 1, x, nr, true, s, nullptr, 1, fcr, h->cd.ldc, fh ? h->vnew : nullptr))) return rc;
+        const int nc = (int)ns;
+        const float *xc = cmp ? nullptr : d_obs + (size_t)s0 * N * D;
+        if ((rc = trunk_forward(h, LC, critic, 1, xc, nc, true, s, nullptr, 1, fcr, h->cd.ldc, fh ? h->vnew : nullptr))) return rc;
         if (!fh) {
-            critic_head_kernel<<<grid_for_rows(h, nr, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nr, H);
+            critic_head_kernel<<<grid_for_rows(h, nc, 8), 256, 0, s>>>(h->hh[h->la.nblk - 1], critic + LC.Wh, critic + LC.bh, h->vnew, nc, H);
             h->launches++;
         }
-        ppo_value_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(d_returns + r0, d_values + r0, h->vnew, vn_now, h->dv,
-                                                              d_epoch_stats, nr, P);
+        ppo_value_loss_kernel<<<(nc + 127) / 128, 128, 0, s>>>(d_returns + s0, d_values + s0, h->vnew, vn_now, h->dv,
+                                                              d_epoch_stats, nc, P);
         h->launches++;
-        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nr, s, fcr, h->cd.ldc))) return rc;
+        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, h->dv, nc, s, fcr, h->cd.ldc))) return rc;
     }
     if (cmp) {
         if ((rc = compact_finalize(h, LA, actor, 0, grad_actor, s))) return rc;
