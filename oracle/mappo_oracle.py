@@ -14,6 +14,9 @@ It restates, in float64 NumPy with hand-written backward passes (paths relative 
                               use_valuenorm, weight_decay
   minibatches                 buffer/shared_buffer.py:219-279 (num_mini_batch index lists cut from a permutation)
   grad clip + Adam            torch.nn.utils.clip_grad_norm_ / torch.optim.Adam as called at algos/mappo.py:30-37,176-185
+  recurrent policies          algos/algo_utils/rnn.py:8-80 (torch.nn.GRU, recurrent_N layers, + LayerNorm; hidden state times
+                              the mask before every step), algos/r_actor_critic.py:55-57,118-120, and the two sequence
+                              generators buffer/shared_buffer.py:281-376 (whole episodes) / :378-470 (data_chunk_length chunks)
 
 Pinned by tests/test_oracle_mappo.py against tests/golden/mappo_*.npz, which tests/golden/make_golden_mappo.py
 produced by running the UNMODIFIED reference learner (float32 torch) in the build container: forward values /
@@ -56,6 +59,9 @@ class MLPNet:
         self.head_w, self.head_b = head_w, head_b
         self.act = act
         self.fnorm = "base.feature_norm.weight" in self.p
+        self.rnn_layers = 0          # recurrent_N GRU layers between the trunk and the head (rnn.py:8-22)
+        while "rnn.rnn.weight_ih_l%d" % self.rnn_layers in self.p:
+            self.rnn_layers += 1
 
     def _act(self, z):
         return np.maximum(z, 0) if self.act == "relu" else np.tanh(z)
@@ -90,14 +96,24 @@ class MLPNet:
             self.blocks.append((st, h, z, a, c))
             h = hn
         self.h_last = h
-        return h @ p[self.head_w].T + p[self.head_b]
+        if self.rnn_layers:          # recurrent nets: the caller runs the GRU on h_last, then head()
+            return h
+        return self.head(h)
 
-    def backward(self, dout):
+    def head(self, y):
+        self.y_head = y
+        return y @ self.p[self.head_w].T + self.p[self.head_b]
+
+    def head_backward(self, dout, g):
+        g[self.head_w] = dout.T @ self.y_head
+        g[self.head_b] = dout.sum(0)
+        return dout @ self.p[self.head_w]
+
+    def backward(self, dout, dh_last=None):
+        """dout: gradient of the head output; recurrent nets pass dh_last (gradient of the trunk output) instead."""
         p = self.p
         g = {}
-        g[self.head_w] = dout.T @ self.h_last
-        g[self.head_b] = dout.sum(0)
-        dh = dout @ p[self.head_w]
+        dh = self.head_backward(dout, g) if dh_last is None else dh_last
         for st, h_in, z, a, c in reversed(self.blocks):
             da, g[st + ".2.weight"], g[st + ".2.bias"] = ln_bwd(dh, c, p[st + ".2.weight"])
             dz = self._dact(da, z, a)
@@ -106,6 +122,89 @@ class MLPNet:
             dh = dz @ p[st + ".0.weight"]
         if self.fnorm:
             _, g["base.feature_norm.weight"], g["base.feature_norm.bias"] = ln_bwd(dh, self.c0, p["base.feature_norm.weight"])
+        return g
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def gru_cell(p, l, x, h):
+    """torch.nn.GRU cell of layer l: gate order (r, z, n) along the 3H rows of weight_ih / weight_hh."""
+    Wi, Wh = p["rnn.rnn.weight_ih_l%d" % l], p["rnn.rnn.weight_hh_l%d" % l]
+    bi, bh = p["rnn.rnn.bias_ih_l%d" % l], p["rnn.rnn.bias_hh_l%d" % l]
+    H = Wh.shape[1]
+    gi, gh = x @ Wi.T + bi, h @ Wh.T + bh
+    r = _sigmoid(gi[:, :H] + gh[:, :H])
+    z = _sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+    n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+    hn = (1.0 - z) * n + z * h
+    return hn, (x, h, r, z, n, gh[:, 2 * H:])
+
+
+def gru_cell_bwd(p, l, dh, cache, g):
+    """dh: gradient of the cell's new state.  Accumulates the layer's parameter gradients into g; returns (dx, dh_prev)."""
+    x, h, r, z, n, ghn = cache
+    Wi, Wh = p["rnn.rnn.weight_ih_l%d" % l], p["rnn.rnn.weight_hh_l%d" % l]
+    dn = dh * (1.0 - z)
+    dz = dh * (h - n)
+    dnp = dn * (1.0 - n * n)
+    dr = dnp * ghn
+    drp, dzp = dr * r * (1.0 - r), dz * z * (1.0 - z)
+    dgi = np.concatenate([drp, dzp, dnp], axis=1)
+    dgh = np.concatenate([drp, dzp, dnp * r], axis=1)
+    for k, v in (("rnn.rnn.weight_ih_l%d" % l, dgi.T @ x), ("rnn.rnn.weight_hh_l%d" % l, dgh.T @ h),
+                 ("rnn.rnn.bias_ih_l%d" % l, dgi.sum(0)), ("rnn.rnn.bias_hh_l%d" % l, dgh.sum(0))):
+        g[k] = g.get(k, 0.0) + v
+    return dgi @ Wi, dh * z + dgh @ Wh
+
+
+class RecurrentNet:
+    """MLPBase -> RNNLayer (GRU x recurrent_N + LayerNorm) -> head  (r_actor_critic.py:43-57,111-121; rnn.py:24-80).
+    Sequences are time-major: x (L*S, in) with row t*S + s, h0 (S, recurrent_N, H), masks (L*S, 1).  The hidden state is
+    multiplied by the step's mask before every step — what rnn.py:38-69 does segment-wise (a mask of 1 is a no-op)."""
+
+    def __init__(self, net):
+        self.net, self.p = net, net.p
+
+    def forward(self, x, h0, masks, L):
+        net, p = self.net, self.p
+        feats = net.forward(x)                       # trunk only (net.rnn_layers > 0)
+        S = feats.shape[0] // L
+        R = net.rnn_layers
+        h = [np.asarray(h0, dtype=np.float64)[:, l].copy() for l in range(R)]
+        masks = np.asarray(masks, dtype=np.float64).reshape(L, S, 1)
+        self.caches, outs = [], []
+        for t in range(L):
+            inp = feats[t * S:(t + 1) * S]
+            step = []
+            for l in range(R):
+                h[l], c = gru_cell(p, l, inp, h[l] * masks[t])
+                step.append(c)
+                inp = h[l]
+            self.caches.append(step)
+            outs.append(inp)
+        self.masks, self.L, self.S = masks, L, S
+        y, self.c_norm = ln_fwd(np.concatenate(outs, 0), p["rnn.norm.weight"], p["rnn.norm.bias"])
+        self.h_final = np.stack(h, axis=1)           # (S, recurrent_N, H)
+        return net.head(y)
+
+    def backward(self, dout):
+        net, p = self.net, self.p
+        g = {}
+        dy = net.head_backward(dout, g)
+        dseq, g["rnn.norm.weight"], g["rnn.norm.bias"] = ln_bwd(dy, self.c_norm, p["rnn.norm.weight"])
+        L, S, R = self.L, self.S, net.rnn_layers
+        dh_next = [0.0] * R
+        dfeat = np.zeros_like(net.h_last)
+        for t in reversed(range(L)):
+            dout_l = dseq[t * S:(t + 1) * S]             # gradient arriving at the top layer's output of step t
+            for l in reversed(range(R)):
+                dx, dhp = gru_cell_bwd(p, l, dout_l + dh_next[l], self.caches[t][l], g)
+                dh_next[l] = dhp * self.masks[t]          # h_prev = h_{t-1} * mask_t
+                dout_l = dx
+            dfeat[t * S:(t + 1) * S] = dout_l
+        g.update(net.backward(None, dh_last=dfeat))
         return g
 
 
@@ -231,12 +330,27 @@ class Trainer:
         self.opt_a = Adam(self.actor.p, eps=hp["opti_eps"], weight_decay=wd)
         self.opt_c = Adam(self.critic.p, eps=hp["opti_eps"], weight_decay=wd)
 
-    def train(self, obs, actions, logp_old, value_preds, returns, lr, ppo_epoch, perms=None):
+    def train(self, obs, actions, logp_old, value_preds, returns, lr, ppo_epoch, perms=None, rnn_states=None,
+              rnn_states_critic=None, masks=None):
         """obs (T+1,E,N,D); actions (T,E,N,2); logp_old (T,E,N,1); value_preds/returns (T+1,E,N,1).
-        perms (num_mini_batch > 1): per epoch, the permutation of the T*E*N agent rows the generator drew."""
+        perms (num_mini_batch > 1): per epoch, the permutation of the T*E*N agent rows the generator drew.
+        Recurrent policies (use_recurrent_policy / use_naive_recurrent_policy): rnn_states / rnn_states_critic
+        (T+1,E,N,recurrent_N,H) and masks (T+1,E,N,1) as the rollout stored them; perms = per epoch the permutation of the
+        sequence chunks (shared_buffer.py:391 / :294).  Both generators cut chunks of L consecutive entries out of the
+        rollout flattened in (env, agent, time) order — L = data_chunk_length (chunked) or T (naive: whole episodes) —
+        start each chunk from the stored hidden state of its first entry and feed them time-major (L, chunks)."""
         hp = self.hp
         T, E, N = actions.shape[:3]
         B = T * E * N
+        recurrent = bool(hp.get("use_recurrent_policy", False) or hp.get("use_naive_recurrent_policy", False))
+        if recurrent:
+            L = int(hp["data_chunk_length"]) if hp.get("use_recurrent_policy", False) else T
+            n_chunks = B // L
+            ract, rcrit = RecurrentNet(self.actor), RecurrentNet(self.critic)
+            R, Hh = rnn_states.shape[3:]
+            hs_a = np.asarray(rnn_states[:-1], dtype=np.float64).reshape(B, R, Hh)
+            hs_c = np.asarray(rnn_states_critic[:-1], dtype=np.float64).reshape(B, R, Hh)
+            mk_all = np.asarray(masks[:-1], dtype=np.float64).reshape(B, 1)
         c = hp["clip_param"]
         nmb = int(hp.get("num_mini_batch", 1))
         vp = value_preds[:-1].astype(np.float64)
@@ -256,20 +370,30 @@ class Trainer:
         clipped = hp.get("use_clipped_value_loss", True)
         info = dict(value_loss=0.0, policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, critic_grad_norm=0.0,
                     ratio=0.0)
-        mbs = B // nmb
+        mbs = (n_chunks if recurrent else B) // nmb
         for ep in range(ppo_epoch):
             for i in range(nmb):
-                if nmb == 1:
+                if recurrent:
+                    ch = np.asarray(perms[ep][i * mbs:(i + 1) * mbs], dtype=np.int64)
+                    f = ch[None, :] * L + np.arange(L)[:, None]            # (L, chunks): entries in (env, agent, time) order
+                    ea, t = f // T, f % T
+                    rows = t * (E * N) + (ea // N) * N + ea % N            # the same entries as rows of the (T, E, N) arrays
+                    sel = rows.reshape(-1)
+                    Bm = sel.size
+                elif nmb == 1:
                     sel = slice(None)      # a permutation of the whole batch only reorders the sums
                     Bm = B
                 else:
                     sel = np.asarray(perms[ep][i * mbs:(i + 1) * mbs], dtype=np.int64)
                     Bm = mbs
                 x, sx, act, lpo, vold, ret, A = (a[sel] for a in (x_all, sx_all, act_all, lpo_all, vold_all, ret_all, A_all))
-                mean = self.actor.forward(x)
+                if recurrent:
+                    mean = ract.forward(x, hs_a[rows[0]], mk_all[sel], L)
+                else:
+                    mean = self.actor.forward(x)
                 logstd = self.actor.p["act.action_out.logstd._bias"].reshape(1, -1)
                 logp, ent = gaussian_logp_entropy(mean, logstd, act)
-                v = self.critic.forward(sx)
+                v = rcrit.forward(sx, hs_c[rows[0]], mk_all[sel], L) if recurrent else self.critic.forward(sx)
                 ratio = np.exp(logp - lpo)
                 s1, s2 = ratio * A, np.clip(ratio, 1 - c, 1 + c) * A
                 policy_loss = -(2.0 * np.minimum(s1, s2)).mean()    # 2 equal log-prob columns (shared_buffer.py:61-62)
@@ -297,10 +421,10 @@ class Trainer:
                 # actor backward
                 std2 = np.exp(2 * logstd)
                 dmean = dlogp * (act - mean) / std2
-                ga = self.actor.backward(dmean)
+                ga = ract.backward(dmean) if recurrent else self.actor.backward(dmean)
                 ga["act.action_out.logstd._bias"] = ((dlogp * ((act - mean) ** 2 / std2 - 1.0)).sum(0)
                                                      - hp["entropy_coef"]).reshape(-1, 1)
-                gc = self.critic.backward(dv)
+                gc = rcrit.backward(dv) if recurrent else self.critic.backward(dv)
                 do_clip = hp.get("use_max_grad_norm", True)
                 an = clip_grads(ga, hp["max_grad_norm"], do_clip)
                 cn = clip_grads(gc, hp["max_grad_norm"], do_clip)

@@ -84,9 +84,12 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
     lr, cfg = build_learner(N, M, E, T, hidden, ppo_epoch, seed, extra=extra)
     D = lr.obs_dim_n[0]
     centralized = bool(cfg.use_centralized_V)
+    recurrent = bool(cfg.use_recurrent_policy) or bool(cfg.use_naive_recurrent_policy)
     a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden, use_centralized_V=centralized,
                                          use_feature_normalization=bool(cfg.use_feature_normalization),
-                                         layer_N=int(cfg.layer_N)))
+                                         layer_N=int(cfg.layer_N), use_recurrent_policy=bool(cfg.use_recurrent_policy),
+                                         use_naive_recurrent_policy=bool(cfg.use_naive_recurrent_policy),
+                                         recurrent_N=int(cfg.recurrent_N)))
     set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
     set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
     out = {}
@@ -109,6 +112,9 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
         out[p + "rewards"] = buf.rewards.copy()
         out[p + "masks"] = buf.masks.copy()
         out[p + "returns"] = buf.returns.copy()
+        if recurrent:       # hidden states as the rollout stored them (learner.py:254-276; slot 0 = after_update's carry-over)
+            out[p + "rnn_states"] = buf.rnn_states.copy()
+            out[p + "rnn_states_critic"] = buf.rnn_states_critic.copy()
         out[p + "vn_before"] = vn0
         out[p + "lr"] = np.array(lrate)
         out[p + "rollout_info"] = np.array([info["reward"], info["coverage_rate"]])
@@ -124,7 +130,7 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
             tinfo = lr.rl_update()
         finally:
             torch.randperm = real_randperm
-        if int(cfg.num_mini_batch) > 1:
+        if int(cfg.num_mini_batch) > 1 or recurrent:     # recurrent: permutations of the sequence chunks
             assert len(perms) == ppo_epoch
             out[p + "perms"] = np.stack(perms).astype(np.int32)
         out[p + "train_info"] = np.array([float(tinfo[k]) for k in ("value_loss", "policy_loss", "dist_entropy",
@@ -149,6 +155,10 @@ def run_case(name, N, M, E, T, hidden, ppo_epoch, seed, iters=2, extra=None):
                 weight_decay=float(cfg.weight_decay), num_mini_batch=int(cfg.num_mini_batch),
                 use_ReLU=bool(cfg.use_ReLU), use_feature_normalization=bool(cfg.use_feature_normalization),
                 use_centralized_V=centralized, layer_N=int(cfg.layer_N))
+    if recurrent:
+        meta.update(use_recurrent_policy=bool(cfg.use_recurrent_policy),
+                    use_naive_recurrent_policy=bool(cfg.use_naive_recurrent_policy), recurrent_N=int(cfg.recurrent_N),
+                    data_chunk_length=int(cfg.data_chunk_length))
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "mappo_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -211,6 +221,15 @@ def main():
         # 48 env-step rows = 384 agent rows = 3 row tiles
         run_case("gen_8x64_h256", 8, 64, 4, 12, 256, 4, seed=14)
         run_pickle_case("3x20_h32", 3, 20, 32, seed=15)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rnn":         # recurrent policies: GRU + chunked / whole-episode BPTT
+        run_case("rnn_chunk_4x20_h32", 4, 20, 2, 20, 32, 3, seed=16, extra=dict(use_recurrent_policy=True))
+        run_case("rnn_naive_3x20_h32", 3, 20, 2, 12, 32, 2, seed=17, extra=dict(use_naive_recurrent_policy=True))
+        # two GRU layers, two minibatches, chunks of 5 that straddle (env, agent) sequences (T = 12 is not a multiple of 5)
+        run_case("rnn_chunk5_mb2_rn2_3x20_h32", 3, 20, 2, 12, 32, 2, seed=18,
+                 extra=dict(use_recurrent_policy=True, recurrent_N=2, data_chunk_length=5, num_mini_batch=2))
+        # the tcgen05 trunk (hidden 256) in front of the GRU
+        run_case("rnn_chunk_4x20_h256", 4, 20, 2, 20, 256, 2, seed=19, extra=dict(use_recurrent_policy=True))
         return
     run_case("ship_4x20_h256", 4, 20, 4, 30, 256, 15, seed=0)     # shipped shapes + hyper-parameters, short rollout
     run_case("gen_8x64_h64", 8, 64, 2, 12, 64, 4, seed=1)         # BASELINE shape, small hidden size

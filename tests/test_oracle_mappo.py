@@ -56,6 +56,13 @@ def test_mappo_oracle_vs_reference(name):
         T, E = act.shape[:2]
         if tr.vn is not None:
             assert np.allclose(tr.vn.state(), g[p + "vn_before"], rtol=1e-5, atol=1e-12)
+        if c.get("use_recurrent_policy", False) or c.get("use_naive_recurrent_policy", False):
+            check_recurrent_rollout(tr, g, p, c, it)
+            info = tr.train(obs, act, g[p + "logp"], g[p + "value_preds"], g[p + "returns"], float(g[p + "lr"]),
+                            c["ppo_epoch"], perms=g[p + "perms"], rnn_states=g[p + "rnn_states"],
+                            rnn_states_critic=g[p + "rnn_states_critic"], masks=g[p + "masks"])
+            check_update(tr, g, p, c, it, info)
+            continue
         # rollout forward (teacher-forced on the recorded actions): log-probs and values
         mean = tr.actor.forward(obs[:-1].reshape(T * E * N, D))
         logp, _ = mo.gaussian_logp_entropy(mean, tr.actor.p["act.action_out.logstd._bias"].reshape(1, -1),
@@ -81,12 +88,45 @@ def test_mappo_oracle_vs_reference(name):
         # update (minibatch cases replay the permutations the reference's generator drew)
         info = tr.train(obs, act, g[p + "logp"], g[p + "value_preds"], g[p + "returns"], float(g[p + "lr"]),
                         c["ppo_epoch"], perms=g.get(p + "perms"))
-        ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
-                       g[p + "train_info"]))
-        for k in ref:
-            assert abs(info[k] - ref[k]) <= 3e-5 * max(1.0, abs(ref[k])), (it, k, info[k], ref[k])
-        if tr.vn is not None:
-            assert np.allclose(tr.vn.state(), g[p + "vn_after"], rtol=1e-5, atol=1e-12)
-        frac = 0.02 if c.get("num_mini_batch", 1) > 1 else 0.0
-        check_params("actor it%d" % it, tr.actor.p, g, p + "actor.", max_bad_frac=frac)
-        check_params("critic it%d" % it, tr.critic.p, g, p + "critic.", max_bad_frac=frac)
+        check_update(tr, g, p, c, it, info)
+
+
+def check_update(tr, g, p, c, it, info):
+    ref = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"),
+                   g[p + "train_info"]))
+    for k in ref:
+        assert abs(info[k] - ref[k]) <= 3e-5 * max(1.0, abs(ref[k])), (it, k, info[k], ref[k])
+    if tr.vn is not None:
+        assert np.allclose(tr.vn.state(), g[p + "vn_after"], rtol=1e-5, atol=1e-12)
+    frac = 0.02 if c.get("num_mini_batch", 1) > 1 else 0.0
+    check_params("actor it%d" % it, tr.actor.p, g, p + "actor.", max_bad_frac=frac)
+    check_params("critic it%d" % it, tr.critic.p, g, p + "critic.", max_bad_frac=frac)
+
+
+def check_recurrent_rollout(tr, g, p, c, it):
+    """Teacher-forced replay of a recurrent rollout (learner.py:227-287 with R_Actor / R_Critic carrying a GRU): per step
+    the recorded hidden states go in, log-probs / values and the NEXT hidden states (zeroed where the episode ended,
+    learner.py:258-265) must come out; then GAE."""
+    N, D = c["n_agents"], c["obs_dim"]
+    obs, act, masks = g[p + "obs"], g[p + "actions"], g[p + "masks"]
+    hs_a, hs_c = g[p + "rnn_states"], g[p + "rnn_states_critic"]
+    T, E = act.shape[:2]
+    R, Hh = hs_a.shape[3:]
+    ract, rcrit = mo.RecurrentNet(tr.actor), mo.RecurrentNet(tr.critic)
+    logstd = tr.actor.p["act.action_out.logstd._bias"].reshape(1, -1)
+    ftol = 1e-5 if it == 1 else 1e-4
+    for t in range(T + 1):
+        sx = np.repeat(obs[t].reshape(E, 1, N * D), N, axis=1).reshape(E * N, N * D)
+        v = rcrit.forward(sx, hs_c[t].reshape(E * N, R, Hh), masks[t].reshape(E * N, 1), 1)
+        assert np.allclose(v.reshape(E, N, 1), g[p + "value_preds"][t], rtol=ftol, atol=ftol), t
+        if t == T:
+            break
+        mean = ract.forward(obs[t].reshape(E * N, D), hs_a[t].reshape(E * N, R, Hh), masks[t].reshape(E * N, 1), 1)
+        logp, _ = mo.gaussian_logp_entropy(mean, logstd, act[t].reshape(-1, 2))
+        assert np.allclose(logp.reshape(E, N, 1), g[p + "logp"][t], rtol=ftol, atol=ftol), t
+        keep = masks[t + 1].reshape(E * N, 1, 1)
+        assert np.allclose(ract.h_final * keep, hs_a[t + 1].reshape(E * N, R, Hh), rtol=ftol, atol=ftol), t
+        assert np.allclose(rcrit.h_final * keep, hs_c[t + 1].reshape(E * N, R, Hh), rtol=ftol, atol=ftol), t
+    ret = mo.gae_returns(g[p + "rewards"], g[p + "value_preds"], masks, tr.vn, c["gamma"], c["gae_lambda"],
+                         use_gae=c.get("use_gae", True))
+    assert np.allclose(ret[:-1], g[p + "returns"][:-1], rtol=1e-5, atol=1e-4)
