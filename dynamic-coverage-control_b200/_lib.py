@@ -36,7 +36,7 @@ class MappoCfg(C.Structure):
         ("opti_eps", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("vn_beta", C.c_double),
         ("use_huber_loss", C.c_int32), ("use_clipped_value_loss", C.c_int32), ("use_max_grad_norm", C.c_int32),
         ("use_valuenorm", C.c_int32), ("use_gae", C.c_int32), ("use_feature_normalization", C.c_int32),
-        ("weight_decay", C.c_float), ("use_relu", C.c_int32), ("layer_N", C.c_int32), ("reserved1", C.c_int32),
+        ("weight_decay", C.c_float), ("use_relu", C.c_int32), ("layer_N", C.c_int32), ("recurrent_N", C.c_int32),
     ]
 
 
@@ -80,6 +80,9 @@ SIGNATURES = {
     "dcc_mappo_epoch_grads": (C.c_int, [_VP] * 12 + [C.c_double, C.c_int, C.c_int, _VP, _VP]),
     "dcc_mappo_minibatch_stats": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP]),
     "dcc_mappo_minibatch_grads": (C.c_int, [_VP] * 12 + [C.c_double, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
+    "dcc_mappo_rnn_pass_seqs": (C.c_int, [_VP, C.c_int]),
+    "dcc_mappo_act_rnn": (C.c_int, [_VP] * 4 + [C.c_int, _VP, _VP, _VP, C.c_int, C.c_uint64, C.c_uint64, C.c_int] + [_VP] * 6),
+    "dcc_mappo_seq_grads": (C.c_int, [_VP] * 15 + [C.c_double, _VP, C.c_int64, C.c_int, _VP, C.c_double, _VP, _VP]),
     "dcc_mappo_apply": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, C.c_float, C.c_int64, _VP, _VP]),
     "dcc_op_gemm": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP, C.c_int,
                               _VP, C.c_int, C.c_int, _VP]),

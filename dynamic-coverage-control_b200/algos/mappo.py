@@ -7,6 +7,8 @@ the bodies call the C ABI (`dcc_mappo_*`, include/dcc_b200.h) instead of torch.n
   MAPPOPolicy.lr_decay                                           -> utils/util.py:29-33 (a float, no kernel)
   MAPPOTrainer.train                                             -> dcc_mappo_train_begin, then per epoch
                                                                     dcc_mappo_epoch_grads [+ all-reduce] + dcc_mappo_apply x2
+  recurrent policies (use_recurrent_policy / use_naive_recurrent_policy: GRU x recurrent_N + LayerNorm between trunk
+  and head, algos/algo_utils/rnn.py)                             -> dcc_mappo_act_rnn, dcc_mappo_seq_grads
 
 Parameters live in flat float32 CUDA tensors (layout in include/dcc_b200.h); `state_dict()` / `load_state_dict()`
 speak the reference's key names so weights round-trip with reference checkpoints.
@@ -40,15 +42,30 @@ def trunk_keys(layer_N=1):
 FC_H = ("base.mlp.fc_h.0.weight", "base.mlp.fc_h.0.bias", "base.mlp.fc_h.2.weight", "base.mlp.fc_h.2.bias")
 
 
-def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True, layer_N=1):
+def rnn_keys(recurrent_N, hidden):
+    """state_dict keys / shapes of the RNNLayer (rnn.py:13-22): torch.nn.GRU's per-layer tensors, then the LayerNorm."""
+    out = []
+    for i in range(recurrent_N):
+        out += [("rnn.rnn.weight_ih_l%d" % i, (3 * hidden, hidden)), ("rnn.rnn.weight_hh_l%d" % i, (3 * hidden, hidden)),
+                ("rnn.rnn.bias_ih_l%d" % i, (3 * hidden,)), ("rnn.rnn.bias_hh_l%d" % i, (3 * hidden,))]
+    if recurrent_N:
+        out += [("rnn.norm.weight", (hidden,)), ("rnn.norm.bias", (hidden,))]
+    return out
+
+
+def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True, layer_N=1, recurrent_N=0):
     """name -> (offset, shape) of the flat parameter buffer, in the order include/dcc_b200.h documents.
-    feature_norm=False (use_feature_normalization: false): the net has no base.feature_norm.* entries (mlp.py:44-45)."""
+    feature_norm=False (use_feature_normalization: false): the net has no base.feature_norm.* entries (mlp.py:44-45).
+    recurrent_N > 0: the RNNLayer's tensors sit between the trunk and the head (r_actor_critic.py:33-39)."""
     shapes = [(in_dim,), (in_dim,), (hidden, in_dim), (hidden,), (hidden,), (hidden,)] + \
         [(hidden, hidden), (hidden,), (hidden,), (hidden,)] * layer_N
     lay, off = OrderedDict(), 0
     for k, shp in zip(trunk_keys(layer_N), shapes):
         if not feature_norm and k.startswith("base.feature_norm"):
             continue
+        lay[k] = (off, shp)
+        off += int(np.prod(shp))
+    for k, shp in rnn_keys(recurrent_N, hidden):
         lay[k] = (off, shp)
         off += int(np.prod(shp))
     lay[head + ".weight"] = (off, (out_dim, hidden)); off += out_dim * hidden
@@ -58,7 +75,8 @@ def net_layout(in_dim, hidden, out_dim, head, logstd=False, feature_norm=True, l
     return lay, off
 
 
-def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use_relu=True, feature_norm=True, layer_N=1):
+def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use_relu=True, feature_norm=True, layer_N=1,
+                    recurrent_N=0):
     """Initial parameters drawn exactly as the reference constructs a net (same torch RNG consumption order):
     MLPBase -> LayerNorm, fc1 = Linear + orthogonal / xavier_uniform (`use_orthogonal`) with the gain of the trunk
     activation (sqrt 2 for ReLU, 5/3 for tanh), fc_h likewise, fc2 = deepcopy(fc_h) (algos/algo_utils/mlp.py:13-23),
@@ -75,6 +93,14 @@ def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use
         return m
     fc1 = lin(in_dim, hidden, gain)
     fc_h = lin(hidden, hidden, gain)
+    rnn = None
+    if recurrent_N:      # RNNLayer is built between the trunk and the head (r_actor_critic.py:33-39): nn.GRU draws its default
+        rnn = nn.GRU(hidden, hidden, num_layers=recurrent_N)     # init, then biases -> 0, weights -> orthogonal / xavier (rnn.py:13-21)
+        for name, param in rnn.named_parameters():
+            if "bias" in name:
+                nn.init.constant_(param, 0)
+            elif "weight" in name:
+                init_method(param)
     head = lin(hidden, out_dim, head_gain)
     ones, zeros = torch.ones, torch.zeros
     sd = OrderedDict()
@@ -87,6 +113,10 @@ def _reference_init(in_dim, hidden, out_dim, head_gain, use_orthogonal=True, use
     for i in range(layer_N):     # get_clones(fc_h, layer_N): every fc2 block starts as a copy of fc_h (mlp.py:23)
         sd["base.mlp.fc2.%d.0.weight" % i], sd["base.mlp.fc2.%d.0.bias" % i] = fc_h.weight.data.clone(), fc_h.bias.data.clone()
         sd["base.mlp.fc2.%d.2.weight" % i], sd["base.mlp.fc2.%d.2.bias" % i] = ones(hidden), zeros(hidden)
+    if rnn is not None:
+        for name, param in rnn.named_parameters():
+            sd["rnn.rnn." + name] = param.data.clone()
+        sd["rnn.norm.weight"], sd["rnn.norm.bias"] = ones(hidden), zeros(hidden)
     return sd, head
 
 
@@ -178,14 +208,18 @@ class MAPPOPolicy:
         mc.use_feature_normalization, mc.use_relu = int(fnorm), int(relu)
         layer_N = int(getattr(cfg, "layer_N", 1))
         mc.layer_N = layer_N
+        from ..utils.config import is_recurrent
+        self.recurrent_N = int(getattr(cfg, "recurrent_N", 1)) if is_recurrent(cfg) else 0
+        mc.recurrent_N = self.recurrent_N
         self.mcfg = mc
         h = C.c_void_p()
         _lib.check(self.lib.dcc_mappo_create(C.byref(mc), self.device.index, C.byref(h)), "dcc_mappo_create")
         self._h = h
 
         la, na = net_layout(self.obs_dim, self.hidden, self.act_dim, "act.action_out.fc_mean", logstd=True, feature_norm=fnorm,
-                            layer_N=layer_N)
-        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out", feature_norm=fnorm, layer_N=layer_N)
+                            layer_N=layer_N, recurrent_N=self.recurrent_N)
+        lc, nc = net_layout(self.share_dim, self.hidden, 1, "v_out", feature_norm=fnorm, layer_N=layer_N,
+                            recurrent_N=self.recurrent_N)
         assert na == self.lib.dcc_mappo_param_count(h, 0) and nc == self.lib.dcc_mappo_param_count(h, 1)
         # one flat gradient buffer for both nets: a single all-reduce per PPO epoch
         self.flat_grads = torch.zeros(na + nc, dtype=torch.float32, device=self.device)
@@ -193,7 +227,7 @@ class MAPPOPolicy:
         self.critic = _Net(lc, nc, self.flat_grads[na:], self.device)
         # initial weights: the reference's construction order — actor first, then critic (mappo.py:27-28)
         init_kw = dict(use_orthogonal=bool(getattr(cfg, "use_orthogonal", True)), use_relu=relu, feature_norm=fnorm,
-                       layer_N=layer_N)
+                       layer_N=layer_N, recurrent_N=self.recurrent_N)
         sd, head = _reference_init(self.obs_dim, self.hidden, self.act_dim, float(cfg.gain), **init_kw)
         sd["act.action_out.fc_mean.weight"], sd["act.action_out.fc_mean.bias"] = head.weight.data, head.bias.data
         sd["act.action_out.logstd._bias"] = torch.zeros(self.act_dim, 1)
@@ -247,7 +281,8 @@ class MAPPOPolicy:
         self.lr_critic_now = max(self.critic_lr - self.critic_lr * (episode / float(episodes)), 0.0)
 
     def get_actions(self, cent_obs, obs, rnn_states_actor=None, rnn_states_critic=None, masks=None,
-                    available_actions=None, deterministic=False, out_actions=None, out_logp=None, out_values=None):
+                    available_actions=None, deterministic=False, out_actions=None, out_logp=None, out_values=None,
+                    out_rnn_actor=None, out_rnn_critic=None):
         """obs: (E*N, D) or (E, N, D) CUDA float32, the env's observation buffer.  cent_obs is accepted for signature
         parity and NOT read: the centralised input of env e is its N obs rows concatenated (learner.py:219-220),
         i.e. the same memory, evaluated once per env instead of N identical times.
@@ -258,12 +293,54 @@ class MAPPOPolicy:
         logp = out_logp if out_logp is not None else self._out("logp", (n * N,))
         values = out_values if out_values is not None else self._out("values", (n,))
         self._rng_offset += 1
+        if self.recurrent_N:
+            ha, hc = self._act_rnn(obs, n, rnn_states_actor, rnn_states_critic, masks, 0, deterministic, actions, logp, values,
+                                   out_rnn_actor, out_rnn_critic)
+            v = values.view(n, 1).expand(n, N).reshape(n * N, 1)
+            return v, actions.view(n * N, 2), logp.view(n * N, 1), ha, hc
         _lib.check(self.lib.dcc_mappo_act(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
                                           self._ptr(obs), n, self.seed, self._rng_offset, 1 if deterministic else 0,
                                           self._ptr(actions), self._ptr(logp), self._ptr(values), self._stream()),
                    "dcc_mappo_act")
         v = values.view(n, 1).expand(n, N).reshape(n * N, 1)
         return v, actions.view(n * N, 2), logp.view(n * N, 1), rnn_states_actor, rnn_states_critic
+
+    # ---- recurrent policies -------------------------------------------------------------------------------
+    def _per_env(self, x, n, tail):
+        """(n*N, *tail) as the reference passes it (N identical rows per env), or (n, *tail) -> contiguous (n, *tail)."""
+        x = torch.as_tensor(x, dtype=torch.float32, device=self.device) if not isinstance(x, torch.Tensor) else x.to(self.device, torch.float32)
+        per = int(np.prod(tail)) if tail else 1
+        if x.numel() == n * per:
+            return x.reshape(n, *tail).contiguous()
+        if x.numel() == n * self.n_agents * per:
+            return x.reshape(n, self.n_agents, *tail)[:, 0].contiguous()
+        raise ValueError("expected %d or %d rows of %s, got %d elements" % (n, n * self.n_agents, tail, x.numel()))
+
+    def _act_rnn(self, obs, n, h_actor, h_critic, masks, mode, deterministic, actions, logp, values, out_ha=None, out_hc=None,
+                 do_actor=True, do_critic=True):
+        """One vec-env step of the recurrent nets (dcc_mappo_act_rnn).  h_actor (n*N, recurrent_N, H); h_critic
+        (n*N, ...) as the reference stores it or (n, ...) one per env; masks (n*N, 1) or (n,).  Returns the new states:
+        actor (n*N, recurrent_N, H) and critic expanded to the reference's (n*N, recurrent_N, H) (a view: one row per env)."""
+        N, R, H = self.n_agents, self.recurrent_N, self.hidden
+        if masks is None:
+            raise ValueError("recurrent policies need the step's masks")
+        mk = self._per_env(masks, n, ())
+        ha = hc = None
+        if do_actor:
+            ha = torch.as_tensor(h_actor, dtype=torch.float32, device=self.device).reshape(n * N, R, H).contiguous()
+            out_ha = out_ha if out_ha is not None else torch.empty((n * N, R, H), dtype=torch.float32, device=self.device)
+        if do_critic:
+            hc = self._per_env(h_critic, n, (R, H))
+            out_hc = out_hc if out_hc is not None else torch.empty((n, R, H), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dcc_mappo_act_rnn(
+            self._h, self._ptr(self.actor.params) if do_actor else None, self._ptr(self.critic.params) if do_critic else None,
+            self._ptr(obs), n, self._ptr(ha), self._ptr(hc), self._ptr(mk), int(mode), self.seed, self._rng_offset,
+            1 if deterministic else 0, self._ptr(actions) if do_actor else None, self._ptr(logp) if do_actor else None,
+            self._ptr(values) if do_critic else None, self._ptr(out_ha) if do_actor else None,
+            self._ptr(out_hc) if do_critic else None, self._stream()), "dcc_mappo_act_rnn")
+        new_ha = out_ha.view(n * N, R, H) if do_actor else None
+        new_hc = out_hc.view(n, 1, R, H).expand(n, N, R, H).reshape(n * N, R, H) if do_critic else None
+        return new_ha, new_hc
 
     def get_values(self, cent_obs, rnn_states_critic=None, masks=None, out_values=None, rows_repeated=False):
         """cent_obs: (E, N*D), or the obs buffer (E, N, D) — one centralised row per env.  rows_repeated=True takes the
@@ -279,6 +356,9 @@ class MAPPOPolicy:
         if n * S != cent_obs.numel():
             raise ValueError("cent_obs has %d elements, not a multiple of N*D = %d" % (cent_obs.numel(), S))
         values = out_values if out_values is not None else self._out("values", (n,))
+        if self.recurrent_N:
+            self._act_rnn(cent_obs, n, None, rnn_states_critic, masks, 0, False, None, None, values, do_actor=False)
+            return values.view(n, 1).expand(n, N).reshape(n * N, 1)
         _lib.check(self.lib.dcc_mappo_act(self._h, None, self._ptr(self.critic.params), self._ptr(cent_obs), n, 0, 0, 0,
                                           None, None, self._ptr(values), self._stream()), "dcc_mappo_act(values)")
         return values.view(n, 1).expand(n, N).reshape(n * N, 1)
@@ -291,9 +371,16 @@ class MAPPOPolicy:
         action = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
         logp = self._out("ev_logp", (n * N,))
         values = self._out("ev_values", (n,))
-        _lib.check(self.lib.dcc_mappo_evaluate(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
-                                               self._ptr(obs), self._ptr(action), n, self._ptr(logp), self._ptr(values),
-                                               None, self._stream()), "dcc_mappo_evaluate")
+        if self.recurrent_N:
+            # one step per row (the x.size(0) == hxs.size(0) branch of RNNLayer.forward, rnn.py:25-29); sequences are
+            # evaluated by the update itself (dcc_mappo_seq_grads)
+            if rnn_states_actor is None or int(np.prod(tuple(rnn_states_actor.shape))) != n * N * self.recurrent_N * self.hidden:
+                raise NotImplementedError("evaluate_actions on recurrent policies takes one hidden state per observation row")
+            self._act_rnn(obs, n, rnn_states_actor, rnn_states_critic, masks, 1, False, action, logp, values)
+        else:
+            _lib.check(self.lib.dcc_mappo_evaluate(self._h, self._ptr(self.actor.params), self._ptr(self.critic.params),
+                                                   self._ptr(obs), self._ptr(action), n, self._ptr(logp), self._ptr(values),
+                                                   None, self._stream()), "dcc_mappo_evaluate")
         logstd = self.actor.view("act.action_out.logstd._bias")
         ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum()
         return values.view(n, 1).expand(n, N).reshape(n * N, 1), logp.view(n * N, 1), ent
@@ -372,6 +459,9 @@ class MAPPOPolicy:
         obs, n = self._as_obs(obs)
         actions = self._out("actions", (n * self.n_agents, 2))
         self._rng_offset += 1
+        if self.recurrent_N:
+            ha, _ = self._act_rnn(obs, n, rnn_states_actor, None, masks, 0, deterministic, actions, None, None, do_critic=False)
+            return actions, ha
         _lib.check(self.lib.dcc_mappo_act(self._h, self._ptr(self.actor.params), None, self._ptr(obs), n, self.seed,
                                           self._rng_offset, 1 if deterministic else 0, self._ptr(actions), None, None,
                                           self._stream()), "dcc_mappo_act(actor)")
@@ -433,6 +523,10 @@ class MAPPOTrainer:
         self._mb_sums = torch.zeros((n_upd, 2), dtype=torch.float64, device=dev)
         self.permutation_fn = None   # tests inject the reference's permutations: fn(epoch, B) -> int64 tensor
         self.training = False
+        # mappo.py:83-84,204-209: use_recurrent_policy wins over use_naive_recurrent_policy
+        self._use_recurrent_policy = bool(getattr(cfg, "use_recurrent_policy", False))
+        self._use_naive_recurrent = bool(getattr(cfg, "use_naive_recurrent_policy", False))
+        self.data_chunk_length = int(getattr(cfg, "data_chunk_length", 10))
 
     def _permutation(self, epoch, n):
         """`torch.randperm(batch_size)` of feed_forward_generator (shared_buffer.py:238), drawn on the device."""
@@ -470,6 +564,8 @@ class MAPPOTrainer:
         B_local = T * E * N
         mbs = B_local // nmb                               # mini_batch_size (shared_buffer.py:236); the tail is dropped
         mbs_global = float(mbs) * self.comm.world
+        if p.recurrent_N:
+            return self._train_recurrent(buffer, update_actor, rows_global, vn)
         for ep in range(self.ppo_epoch):
             if nmb == 1 and getattr(buffer, "compact", False):
                 _lib.check(lib.dcc_mappo_epoch_grads_state(
@@ -508,14 +604,62 @@ class MAPPOTrainer:
                     ptr(buffer.returns_te), ptr(vn), ptr(self._stats4), rows_global, ptr(idx), mbs,
                     ptr(self._mb_sums[u]), mbs_global, ptr(self._epoch_stats[u]), s), "dcc_mappo_minibatch_grads")
                 self._apply(u, update_actor)
-        # per-update sums -> the reference's train_info (means over updates; one device->host read per update)
+        return self._train_info(rows_global * N if nmb == 1 else mbs_global)
+
+    def _train_recurrent(self, buffer, update_actor, rows_global, vn):
+        """The update of a recurrent policy (mappo.py:203-209 -> shared_buffer.py:281-470).  Both generators cut the rollout,
+        flattened in (env, agent, time) order, into chunks of L consecutive entries — L = data_chunk_length
+        (recurrent_generator) or the whole episode (naive_recurrent_generator) — permute the chunks, split them into
+        num_mini_batch minibatches (the tail is dropped) and feed each minibatch time-major, every chunk started from the
+        hidden state the rollout stored in front of its first entry.  The chunk -> rollout-row index arithmetic happens
+        here (a few tiny tensor ops per update); forward, loss and BPTT are dcc_mappo_seq_grads."""
+        p, lib, ptr, s = self.policy, self.policy.lib, self.policy._ptr, self.policy._stream()
+        T, E, N = buffer.episode_length, buffer.n_rollout_threads, p.n_agents
+        B = T * E * N
+        L = self.data_chunk_length if self._use_recurrent_policy else T
+        n_chunks = B // L
+        nmb = self.num_mini_batch
+        mbs = n_chunks // nmb
+        if mbs < 1:
+            raise ValueError("fewer sequence chunks (%d) than PPO minibatches (%d)" % (n_chunks, nmb))
+        P = int(lib.dcc_mappo_rnn_pass_seqs(p._h, L))
+        if P < 1:
+            raise _lib.DccError("sequence length %d exceeds the learner's activation chunk (%d rows): raise chunk_rows"
+                                % (L, lib.dcc_mappo_chunk_rows(p._h)))
+        rows_mb_global = float(mbs * L) * self.comm.world
+        steps = torch.arange(L, device=p.device, dtype=torch.int64)[:, None]
+        for ep in range(self.ppo_epoch):
+            perm = self._permutation(ep, n_chunks)
+            for i in range(nmb):
+                u = ep * nmb + i
+                ch = perm[i * mbs:(i + 1) * mbs]
+                f = ch[None, :] * L + steps                                  # (L, chunks): entries in (env, agent, time) order
+                ea, t = torch.div(f, T, rounding_mode="floor"), f % T
+                rows = t * (E * N) + ea                                      # ea = e * N + a: rows of the (T, E, N) arrays
+                # passes of P sequences, time-major inside a pass (the layout dcc_mappo_seq_grads reads)
+                idx = torch.cat([rows[:, q:q + P].reshape(-1) for q in range(0, mbs, P)]).contiguous()
+                _lib.check(lib.dcc_mappo_minibatch_stats(p._h, ptr(buffer.returns_te), ptr(idx), idx.numel(),
+                                                         ptr(self._mb_sums[u]), s), "dcc_mappo_minibatch_stats")
+                self.comm.all_reduce_sum_(self._mb_sums[u])
+                _lib.check(lib.dcc_mappo_seq_grads(
+                    p._h, ptr(p.actor.params), ptr(p.critic.params), ptr(p.actor.grads), ptr(p.critic.grads), ptr(buffer.obs),
+                    ptr(buffer.rnn_a), ptr(buffer.rnn_c), ptr(buffer.masks_te), ptr(buffer.actions),
+                    ptr(buffer.action_log_probs_ten), ptr(buffer.values_te), ptr(buffer.returns_te), ptr(vn), ptr(self._stats4),
+                    rows_global, ptr(idx), mbs, L, ptr(self._mb_sums[u]), rows_mb_global, ptr(self._epoch_stats[u]), s),
+                    "dcc_mappo_seq_grads")
+                self._apply(u, update_actor)
+        return self._train_info(rows_mb_global)
+
+    def _train_info(self, B):
+        """per-update sums -> the reference's train_info (means over updates; one device->host read per update).
+        B = agent rows behind each update's loss mean."""
+        nmb = self.num_mini_batch
         es = self._epoch_stats.clone()
         es[:, 3] = 0
         self.comm.all_reduce_sum_(es)
         es = es.cpu().numpy()
         ent = self._epoch_stats[:, 3].cpu().numpy()
         gn = np.sqrt(self._gnorm_sq.cpu().numpy())
-        B = rows_global * N if nmb == 1 else mbs_global    # agent rows behind each update's loss mean
         k = float(self.ppo_epoch * nmb)
         return {"value_loss": float(es[:, 1].sum() / B / k), "policy_loss": float(es[:, 0].sum() / B / k),
                 "dist_entropy": float(ent.sum() / k), "actor_grad_norm": float(gn[:, 0].sum() / k),

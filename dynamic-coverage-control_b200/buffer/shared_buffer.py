@@ -10,7 +10,10 @@ Same constructor and method names (`insert`, `compute_returns`, `after_update`) 
     (T(+1), E, N, 1) arrays are exposed as expanded views (`rewards`, `masks`, `value_preds`, `returns`);
   * the rnn_states arrays (never written with MLP policies), bad_masks and active_masks (all ones) are not stored:
     `rnn_states`, `rnn_states_critic`, `bad_masks`, `active_masks` are zero-cost expanded views with the reference's
-    shapes; `available_actions` is None as in the reference (Box action space).
+    shapes; `available_actions` is None as in the reference (Box action space).  Recurrent policies
+    (use_recurrent_policy / use_naive_recurrent_policy) DO store them: `rnn_a` (T+1, E, N, recurrent_N, H) for the actor
+    and `rnn_c` (T+1, E, recurrent_N, H) for the critic — one per env, because the N agent rows of an env feed the
+    critic identical inputs, masks and therefore hidden states; `rnn_states_critic` is the expanded view;
 GAE (`compute_returns`, shared_buffer.py:199-208) is one kernel, `dcc_mappo_gae`.
 
 Two storage modes for the observations:
@@ -104,6 +107,13 @@ class SharedReplayBuffer(object):
         self.step = 0
         self.recurrent_N = int(getattr(cfg, "recurrent_N", 1))
         self.hidden_size = int(getattr(cfg, "algo_hidden_size", 256))
+        from ..utils.config import is_recurrent
+        self.recurrent = is_recurrent(cfg)
+        if self.recurrent:
+            if self.compact or not self.centralized:
+                raise ValueError("recurrent policies use materialised observations and the centralised critic")
+            self.rnn_a = torch.zeros((T + 1, E, N, self.recurrent_N, self.hidden_size), **kw)
+            self.rnn_c = torch.zeros((T + 1, E, self.recurrent_N, self.hidden_size), **kw)
         self.available_actions = None
         self._zero = torch.zeros(1, **kw)
         self._one = torch.ones(1, **kw)
@@ -112,11 +122,16 @@ class SharedReplayBuffer(object):
     @property
     def rnn_states(self):
         """(T+1, E, N, recurrent_N, hidden) zeros (shared_buffer.py:44-48): MLP policies never write them."""
+        if self.recurrent:
+            return self.rnn_a
         T1, E, N, _ = self.obs.shape
         return self._zero.view(1, 1, 1, 1, 1).expand(T1, E, N, self.recurrent_N, self.hidden_size)
 
     @property
     def rnn_states_critic(self):
+        if self.recurrent:
+            T1, E = self.rnn_c.shape[:2]
+            return self.rnn_c[:, :, None].expand(T1, E, self.num_agents, self.recurrent_N, self.hidden_size)
         return self.rnn_states
 
     @property
@@ -202,6 +217,13 @@ class SharedReplayBuffer(object):
                 raise ValueError("compact rollout storage takes the env state (state_pv / state_en), not observation rows")
         else:
             put(self.obs[t + 1], obs)
+        if self.recurrent:      # shared_buffer.py:88-89: the states AFTER step t (already zeroed where the episode ended)
+            put(self.rnn_a[t + 1], rnn_states_actor)
+            if rnn_states_critic is not None:
+                hc = torch.as_tensor(rnn_states_critic, dtype=torch.float32, device=self.device)
+                if hc.numel() == self.rnn_c[t + 1].numel() * N:      # the reference's per-agent layout: N identical rows per env
+                    hc = hc.reshape(E, N, self.recurrent_N, self.hidden_size)[:, 0]
+                put(self.rnn_c[t + 1], hc)
         put(self.actions[t], actions)
         alp = torch.as_tensor(action_log_probs, dtype=torch.float32, device=self.device)
         put(self.action_log_probs_ten[t], alp if alp.numel() == E * N else alp.reshape(E, N, -1)[..., 0])
@@ -212,13 +234,19 @@ class SharedReplayBuffer(object):
 
     def insert_env_step(self, rew_en, done_en):
         """Zero-copy rollout step: obs[t+1], actions[t], log-probs[t] and values[t] were written in place by the env
-        and policy kernels; this stores the per-env reward and mask = 1 - done (learner.py:266-267) — one kernel."""
+        and policy kernels; this stores the per-env reward and mask = 1 - done (learner.py:266-267) — one kernel.
+        Recurrent policies: the new hidden states were written to slot t+1 by the policy kernels; those of finished
+        episodes are zeroed here (learner.py:258-265)."""
         t = self.step
         _lib.check(self.lib.dcc_rollout_insert(C.c_void_p(rew_en.data_ptr()), C.c_void_p(done_en.data_ptr()),
                                                self.n_value_rows, self.agents_per_value_row,
                                                C.c_void_p(self.rewards_te[t].data_ptr()),
                                                C.c_void_p(self.masks_te[t + 1].data_ptr()), self._stream()),
                    "dcc_rollout_insert")
+        if self.recurrent:
+            m = self.masks_te[t + 1]
+            self.rnn_a[t + 1].mul_(m.view(-1, 1, 1, 1))
+            self.rnn_c[t + 1].mul_(m.view(-1, 1, 1))
         self.step = (self.step + 1) % self.episode_length
 
     def compute_returns(self, next_value, value_normalizer, policy=None):
@@ -261,6 +289,9 @@ class SharedReplayBuffer(object):
         else:
             self.obs[0].copy_(self.obs[-1])
         self.masks_te[0].copy_(self.masks_te[-1])
+        if self.recurrent:      # shared_buffer.py:146-147: the hidden states carry over into the next rollout as well
+            self.rnn_a[0].copy_(self.rnn_a[-1])
+            self.rnn_c[0].copy_(self.rnn_c[-1])
 
     def close(self):
         if getattr(self, "_h", None) is not None:

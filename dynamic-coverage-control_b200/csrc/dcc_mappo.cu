@@ -17,11 +17,13 @@
 
 #include "dcc_compact.cuh"
 #include "dcc_ops.cuh"
+#include "dcc_rnn.cuh"
 #include "dcc_tc.cuh"
 
 namespace dcc {
 
 constexpr int MAX_BLOCKS = 4;   // hidden blocks [Linear, act, LayerNorm]: fc1 + layer_N clones of fc_h (layer_N <= 3)
+constexpr int MAX_RNN = 4;      // GRU layers of a recurrent policy (recurrent_N, rnn.py:13)
 
 struct NetLayout {
     int in, H, out;
@@ -29,8 +31,12 @@ struct NetLayout {
     int nblk;  // 1 + layer_N hidden blocks; block 0 = fc1 (in -> H), blocks 1.. = fc2[i] (H -> H)  (mlp.py:16-29)
     bool has_ln0;   // use_feature_normalization: feature_norm.weight / .bias present
     size_t ln0_g, ln0_b, W[MAX_BLOCKS], b[MAX_BLOCKS], lg[MAX_BLOCKS], lb[MAX_BLOCKS], Wh, bh, logstd, total;
-    void init(int in_, int H_, int out_, bool has_logstd, bool has_ln0_, int layer_N) {
-        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32; has_ln0 = has_ln0_; nblk = 1 + layer_N;
+    // recurrent policies: rn GRU layers (weight_ih [3H, H], weight_hh [3H, H], bias_ih [3H], bias_hh [3H] each) and the
+    // RNNLayer's LayerNorm, between the trunk and the head — the reference's state_dict order (base.*, rnn.*, act.* / v_out.*)
+    int rn;
+    size_t Wih[MAX_RNN], Whh[MAX_RNN], bih[MAX_RNN], bhh[MAX_RNN], rnn_g, rnn_b;
+    void init(int in_, int H_, int out_, bool has_logstd, bool has_ln0_, int layer_N, int recurrent_N = 0) {
+        in = in_; H = H_; out = out_; inp = (in_ + 31) / 32 * 32; has_ln0 = has_ln0_; nblk = 1 + layer_N; rn = recurrent_N;
         size_t o = 0;
         ln0_g = o; if (has_ln0) o += in;
         ln0_b = o; if (has_ln0) o += in;
@@ -38,6 +44,11 @@ struct NetLayout {
             W[k] = o; o += (size_t)H * (k == 0 ? in : H);
             b[k] = o; o += H; lg[k] = o; o += H; lb[k] = o; o += H;
         }
+        for (int l = 0; l < rn; ++l) {
+            Wih[l] = o; o += (size_t)3 * H * H; Whh[l] = o; o += (size_t)3 * H * H; bih[l] = o; o += 3 * H; bhh[l] = o; o += 3 * H;
+        }
+        rnn_g = o; if (rn) o += H;
+        rnn_b = o; if (rn) o += H;
         Wh = o; o += (size_t)out * H; bh = o; o += out;
         logstd = o; if (has_logstd) o += out;
         total = o;
@@ -78,6 +89,10 @@ struct MappoHandle {
     float *head_fold[2];     // output head folded through the last LayerNorm affine, for the fused epilogue (head_fold_kernel)
     float *wt[2];            // folded fc1 weights [H, ld] (actor, critic)
     float *gt[2];            // running dz1^T f of the epoch [H, ld]
+    // recurrent policies (dcc_rnn.cuh): per GRU layer the masked previous states, x W_ih^T / h W_hh^T (overwritten by their
+    // gradients in the backward pass), gate activations and outputs of every step of a pass; [rows, *] with rows <= chunk * N
+    float *r_Hp[MAX_RNN], *r_GI[MAX_RNN], *r_GH[MAX_RNN], *r_gates[MAX_RNN], *r_Hout[MAX_RNN];
+    float *r_dH[2], *r_Y, *r_mean, *r_rstd, *r_mask, *r_dhp[2], *r_dfeat, *r_zero, *r_dummy;
     int64_t launches;
 };
 constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
@@ -475,8 +490,10 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
 // weight slot receives G1 = dz1^T xhat (turned into dW1 / dgamma0 / dbeta0 by ln0_finalize once per epoch).
 // `dout` = gradient w.r.t. the head output ([rows, out]); on return all parameter gradients of the net have been
 // accumulated into G (the fc1 slot holds G1, see ln0_finalize).
+// dh_last != nullptr (recurrent policies): the gradient w.r.t. the trunk OUTPUT [rows, H] is given (it comes out of the GRU's
+// backward pass, rnn_backward) and the head's gradients have been accumulated already; `dout` is ignored.
 static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *dout, int rows,
-                          cudaStream_t s, const float *feat = nullptr, int ldf = 0) {
+                          cudaStream_t s, const float *feat = nullptr, int ldf = 0, const float *dh_last = nullptr) {
     const int H = L.H;
     const int wpb = 8;
     const int gr = grid_for_reduce(h, rows, wpb, h->ln_pipe ? 3 : 4);    // relu_ln_bwd_pipe: 3 CTAs per SM
@@ -488,7 +505,18 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     const bool sp = h->split16 && h->backend == 2;      // weight-gradient X operands (h_{k-1}, compact features) are pre-split
     uint32_t *amax = (dx16 || sp) ? h->dz_absmax : nullptr;
     if (amax) DCC_CUDA_TRY(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
-    if (h->ln_pipe) {
+    if (dh_last) {
+        if (h->ln_pipe) {
+            const size_t ring = (size_t)wpb * RP_SLOTS * 2 * H;
+            relu_ln_bwd_pipe_kernel<<<gr, wpb * 32, std::max(ring, (size_t)wpb * 3 * 256) * sizeof(float), s>>>(
+                dh_last, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], h->dA, G + L.lg[last], G + L.lb[last], G + L.b[last],
+                rows, H, act_of(h), amax);
+        } else
+            relu_ln_bwd_kernel<<<gr, wpb * 32, wpb * 3 * 256 * sizeof(float), s>>>(dh_last, h->a[last], h->mean[last], h->rstd[last],
+                                                                                 P + L.lg[last], h->dA, G + L.lg[last], G + L.lb[last],
+                                                                                 G + L.b[last], rows, H, act_of(h));
+        DCC_CUDA_TRY(cudaGetLastError());
+    } else if (h->ln_pipe) {
         const size_t ring = (size_t)wpb * RP_SLOTS * H;
         if (L.out == 2)
             head_relu_ln_bwd_pipe_kernel<2><<<gr_head, wpb * 32, std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), s>>>(
@@ -568,6 +596,103 @@ static int compact_finalize(MappoHandle *h, const NetLayout &L, const float *P, 
     return ln0_finalize(h, L, P, G, s);
 }
 
+// ---- recurrent policies: GRU x recurrent_N + LayerNorm between the trunk and the head (dcc_rnn.cuh) --------------------------
+// where the hidden state in front of step 0 comes from: stored states [*, rn, H], read at row gather[s] / gdiv (sequence
+// update: the rollout row of the sequence's first step) or at row s itself (one rollout step)
+struct RnnSrc {
+    const float *states;
+    const long long *gather;
+    int gdiv;
+};
+
+static inline dim3 ew_grid(size_t n) { return dim3((unsigned)((n + 255) / 256)); }
+
+// X [steps * S, H] (time-major trunk outputs) -> h->r_Y = LayerNorm(GRU(X)) [steps * S, H]; everything the backward pass needs
+// stays in the r_* scratch.  mask_rows [steps * S]: the step's mask per row (rnn.py:26-27,66-67: state *= mask before the step).
+static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, const float *X, int S, int steps, const RnnSrc &src,
+                       const float *mask_rows, cudaStream_t s) {
+    const int H = L.H, H3 = 3 * L.H;
+    const size_t rows = (size_t)S * steps, SH = (size_t)S * H;
+    int rc;
+    for (int l = 0; l < L.rn; ++l) {
+        const float *Xl = l == 0 ? X : h->r_Hout[l - 1];
+        // x W_ih^T for all steps at once (bias added in the gate kernel)
+        if ((rc = launch_gemm(h, false, true, (int)rows, H3, H, Xl, H, P + L.Wih[l], H, h->r_GI[l], H3, false, s))) return rc;
+        for (int t = 0; t < steps; ++t) {
+            float *Hp = h->r_Hp[l] + t * SH;
+            if (t == 0)
+                gru_prev_kernel<<<ew_grid(SH), 256, 0, s>>>(src.states, src.gather, src.gdiv, src.gather ? 0 : 1, L.rn, l, mask_rows, Hp, S, H);
+            else
+                gru_prev_kernel<<<ew_grid(SH), 256, 0, s>>>(h->r_Hout[l] + (t - 1) * SH, nullptr, 1, 0, L.rn, l, mask_rows + (size_t)t * S,
+                                                           Hp, S, H);
+            h->launches++;
+            float *GH = h->r_GH[l] + (size_t)t * S * H3;
+            if ((rc = launch_gemm(h, false, true, S, H3, H, Hp, H, P + L.Whh[l], H, GH, H3, false, s))) return rc;   // the recurrence
+            gru_gate_fwd_kernel<<<ew_grid(SH), 256, 0, s>>>(h->r_GI[l] + (size_t)t * S * H3, GH, P + L.bih[l], P + L.bhh[l], Hp,
+                                                           h->r_gates[l] + (size_t)t * S * 4 * H, h->r_Hout[l] + t * SH, S, H);
+            h->launches++;
+        }
+    }
+    bias_relu_ln_fwd_kernel<<<grid_for_rows(h, (long)rows, 8), 256, 0, s>>>(h->r_Hout[L.rn - 1], h->r_zero, P + L.rnn_g, P + L.rnn_b, nullptr,
+                                                                           h->r_Y, h->r_mean, h->r_rstd, (int)rows, H, ACT_IDENT);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+// Backward of head + RNNLayer: dout [steps * S, out] -> parameter gradients of the head, the LayerNorm and every GRU layer
+// accumulated into G; the gradient w.r.t. the trunk output lands in h->r_dfeat.  BPTT runs inside the pass only: the stored
+// state in front of step 0 is a constant, exactly like the reference's chunked / whole-episode generators.
+static int rnn_backward(MappoHandle *h, const NetLayout &L, const float *P, float *G, const float *X, const float *dout, int S, int steps,
+                        const float *mask_rows, cudaStream_t s) {
+    const int H = L.H, H3 = 3 * L.H, wpb = 8;
+    const size_t rows = (size_t)S * steps, SH = (size_t)S * H;
+    const int top = L.rn - 1;
+    const int gr_head = grid_for_reduce(h, (long)rows, wpb, 2);
+    int cur = 0, rc;
+    // head backward fused with the backward of the RNNLayer's LayerNorm ("activation" = identity on the GRU output)
+    if (L.out == 2)
+        head_relu_ln_bwd_kernel<2><<<gr_head, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(
+            dout, P + L.Wh, h->r_Hout[top], h->r_mean, h->r_rstd, P + L.rnn_g, P + L.rnn_b, h->r_dH[cur], G + L.rnn_g, G + L.rnn_b,
+            h->r_dummy, G + L.Wh, G + L.bh, (int)rows, H, ACT_IDENT);
+    else
+        head_relu_ln_bwd_kernel<1><<<gr_head, wpb * 32, wpb * 4 * 256 * sizeof(float), s>>>(
+            dout, P + L.Wh, h->r_Hout[top], h->r_mean, h->r_rstd, P + L.rnn_g, P + L.rnn_b, h->r_dH[cur], G + L.rnn_g, G + L.rnn_b,
+            h->r_dummy, G + L.Wh, G + L.bh, (int)rows, H, ACT_IDENT);
+    h->launches++;
+    DCC_CUDA_TRY(cudaGetLastError());
+    for (int l = top; l >= 0; --l) {
+        const float *dHl = h->r_dH[cur];
+        float *dGI = h->r_GI[l], *dGH = h->r_GH[l];     // gradients overwrite the pre-activations they belong to
+        for (int t = steps - 1; t >= 0; --t) {
+            const bool lastt = t == steps - 1;
+            gru_gate_bwd_kernel<<<ew_grid(SH), 256, 0, s>>>(dHl + t * SH, lastt ? nullptr : h->r_dhp[(t + 1) & 1],
+                                                           lastt ? nullptr : mask_rows + (size_t)(t + 1) * S,
+                                                           h->r_gates[l] + (size_t)t * S * 4 * H, h->r_Hp[l] + t * SH,
+                                                           dGI + (size_t)t * S * H3, dGH + (size_t)t * S * H3, h->r_dhp[t & 1], S, H);
+            h->launches++;
+            // gradient w.r.t. the masked previous state: dhp += dGH W_hh (not needed in front of step 0: that state is data)
+            if (t > 0 && (rc = launch_gemm(h, false, false, S, H, H3, dGH + (size_t)t * S * H3, H3, P + L.Whh[l], H, h->r_dhp[t & 1], H, true, s)))
+                return rc;
+        }
+        const float *Xl = l == 0 ? X : h->r_Hout[l - 1];
+        if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGH, H3, h->r_Hp[l], H, G + L.Whh[l], H, true, s))) return rc;
+        if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGI, H3, Xl, H, G + L.Wih[l], H, true, s))) return rc;
+        const dim3 cg((H3 + 127) / 128, (unsigned)std::min<size_t>((rows + 255) / 256, 256));
+        colsum_atomic_kernel<<<cg, 128, 0, s>>>(dGI, rows, H3, G + L.bih[l]);
+        colsum_atomic_kernel<<<cg, 128, 0, s>>>(dGH, rows, H3, G + L.bhh[l]);
+        h->launches += 2;
+        float *dX = l > 0 ? h->r_dH[cur ^ 1] : h->r_dfeat;
+        if ((rc = launch_gemm(h, false, false, (int)rows, H, H3, dGI, H3, P + L.Wih[l], H, dX, H, false, s))) return rc;
+        cur ^= 1;
+    }
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+// sequences per pass of the sequence update: whole sequences of `steps` rows within one chunk of the (critic's) scratch
+static inline int rnn_pass_seqs(const MappoHandle *h, int steps) { return steps > 0 ? h->chunk_rows / steps : 0; }
+
 __global__ void expand_values_kernel(const float *__restrict__ v, float *__restrict__ out, int rows, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * N) out[i] = v[i / N];
@@ -610,6 +735,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
         cfg->layer_N > MAX_BLOCKS - 1)
         return DCC_ERR_UNSUPPORTED;  // MLP trunk with hidden <= 256, 1..3 fc2 blocks and the Box(2) action space of the env
     if (cfg->gemm_backend == 2 && !tc_supported(cfg)) return DCC_ERR_UNSUPPORTED;
+    if (cfg->recurrent_N < 0 || cfg->recurrent_N > MAX_RNN) return DCC_ERR_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return DCC_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return DCC_ERR_INVALID_ARG;
@@ -639,14 +765,16 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->split16 = h->backend == 2 && h->f16_fwd && !(getenv("DCC_TC_SPLIT") && atoi(getenv("DCC_TC_SPLIT")) == 0) &&
                  !(getenv("DCC_TC_TMA") && atoi(getenv("DCC_TC_TMA")) == 0) && tc::tc_tensor_map_encoder() != nullptr;
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
-    h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N);
-    h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N);
+    h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
+    h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
     // chunk: bound the scratch to ~1.5 GB unless the caller asks for a size
     long chunk = cfg->chunk_rows;
     if (chunk <= 0) {
         const double per_row = (double)N * (D + (2.0 + 2.0 * (1 + cfg->layer_N)) * H + 16) * 4.0;
         chunk = (long)(2.5e9 / per_row);
         if (chunk > 131072) chunk = 131072;
+        // recurrent policies keep ~13 H floats per row and GRU layer on top: bound the pass to 65 536 agent rows
+        if (cfg->recurrent_N > 0 && chunk * N > 65536) chunk = 65536 / N;
         // whole waves of 128-row tiles on the persistent grid (one CTA per SM).  The critic runs one row per env step,
         // so its tile count is chunk / 128: with chunk a multiple of 128 * SMs BOTH nets fill every wave (a chunk
         // aligned for the actor only leaves the critic's forward-shaped GEMMs with a 25 %-full second wave).
@@ -684,6 +812,17 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
     if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
     for (int n = 0; n < 2 && h->backend == 2; ++n) alloc(&h->head_fold[n], 2 * 256 + 8);
+    if (cfg->recurrent_N > 0) {
+        for (int l = 0; l < cfg->recurrent_N; ++l) {
+            alloc(&h->r_Hp[l], RA * H); alloc(&h->r_GI[l], RA * 3 * H); alloc(&h->r_GH[l], RA * 3 * H);
+            alloc(&h->r_gates[l], RA * 4 * H); alloc(&h->r_Hout[l], RA * H);
+        }
+        for (int i = 0; i < 2; ++i) { alloc(&h->r_dH[i], RA * H); alloc(&h->r_dhp[i], RA * H); }
+        alloc(&h->r_Y, RA * H); alloc(&h->r_mean, RA); alloc(&h->r_rstd, RA); alloc(&h->r_mask, RA); alloc(&h->r_dfeat, RA * H);
+        alloc(&h->r_zero, 3 * H); alloc(&h->r_dummy, H);
+        if (ce == cudaSuccess) ce = cudaMemset(h->r_zero, 0, 3 * H * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMemset(h->r_dummy, 0, H * sizeof(float));
+    }
     if (ce != cudaSuccess) {
         set_last_cuda_error(ce, "cudaMalloc(mappo scratch)", __FILE__, __LINE__);
         dcc_mappo_destroy(h);
@@ -704,6 +843,13 @@ int dcc_mappo_destroy(void *handle) {
         float *blk[] = {h->a[k], h->hh[k], h->mean[k], h->rstd[k], h->img_w[0][k], h->img_w[1][k], h->img_wt[0][k], h->img_wt[1][k]};
         for (float *b : blk) cudaFree(b);
     }
+    for (int l = 0; l < MAX_RNN; ++l) {
+        float *rb[] = {h->r_Hp[l], h->r_GI[l], h->r_GH[l], h->r_gates[l], h->r_Hout[l]};
+        for (float *b : rb) cudaFree(b);
+    }
+    float *rbufs[] = {h->r_dH[0], h->r_dH[1], h->r_dhp[0], h->r_dhp[1], h->r_Y, h->r_mean, h->r_rstd, h->r_mask, h->r_dfeat,
+                      h->r_zero, h->r_dummy};
+    for (float *b : rbufs) cudaFree(b);
     cudaFree(h->dsums);
     cudaFree(h->dz_absmax);
     cudaFree(h->d_poi); cudaFree(h->fc);
@@ -785,6 +931,7 @@ int dcc_mappo_act(void *handle, const float *actor, const float *critic, const f
                   dcc_stream_t stream) {
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N > 0) return DCC_ERR_UNSUPPORTED;      // recurrent handles: dcc_mappo_act_rnn
     if ((actor && !d_actions) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
     DCC_DEVICE_GUARD(h->device);
     return policy_forward(h, actor, critic, d_obs, n_envs, 0, seed, offset, deterministic, d_actions, d_logp, d_values,
@@ -796,6 +943,7 @@ int dcc_mappo_evaluate(void *handle, const float *actor, const float *critic, co
     MappoHandle *h = as_mappo(handle);
     if (!h || !d_obs || n_envs < 1 || (!actor && !critic)) return DCC_ERR_INVALID_ARG;
     if ((actor && (!d_actions || !d_logp)) || (critic && !d_values)) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N > 0) return DCC_ERR_UNSUPPORTED;      // recurrent handles: dcc_mappo_act_rnn (mode 1)
     DCC_DEVICE_GUARD(h->device);
     return policy_forward(h, actor, critic, d_obs, n_envs, 1, 0, 0, 0, const_cast<float *>(d_actions), d_logp, d_values,
                           d_mu, static_cast<cudaStream_t>(stream));
@@ -807,6 +955,7 @@ int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, d
     const int N = h->cfg.n_agents;
     // the observation layout must be the env's (coverage.py:99-110) and the critic centralised over the N rows
     if (h->cfg.obs_dim != 4 + 2 * (N - 1) + 5 * n_pois || h->lc.in != N * h->cfg.obs_dim) return DCC_ERR_UNSUPPORTED;
+    if (h->cfg.recurrent_N > 0) return DCC_ERR_UNSUPPORTED;      // recurrent policies run on materialised observation rows
     DCC_DEVICE_GUARD(h->device);
     CompactDims cd;
     cd.init(N, n_pois, m_energy);
@@ -1028,6 +1177,7 @@ int dcc_mappo_epoch_grads(void *handle, const float *actor, const float *critic,
         !d_returns || !d_stats4 || !d_epoch_stats || T < 1 || E < 1 || !(n_rows_global >= 1.0))
         return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N > 0) return DCC_ERR_UNSUPPORTED;      // recurrent handles: dcc_mappo_seq_grads
     DCC_DEVICE_GUARD(h->device);
     return epoch_grads_impl(h, actor, critic, grad_actor, grad_critic, d_obs, nullptr, nullptr, d_actions, d_logp_old, d_values,
                             d_returns, d_vn_state, d_stats4, n_rows_global, T, E, d_epoch_stats, static_cast<cudaStream_t>(stream));
@@ -1139,6 +1289,7 @@ int dcc_mappo_minibatch_grads(void *handle, const float *actor, const float *cri
         !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
         return DCC_ERR_INVALID_ARG;
     if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N > 0) return DCC_ERR_UNSUPPORTED;      // recurrent handles: dcc_mappo_seq_grads
     DCC_DEVICE_GUARD(h->device);
     return minibatch_grads_impl(h, actor, critic, grad_actor, grad_critic, d_obs, nullptr, nullptr, d_actions, d_logp_old, d_values,
                                 d_returns, d_vn_state, d_stats4, n_rows_global, d_row_index, n_index, d_ret_sums, n_index_global,
@@ -1161,6 +1312,117 @@ int dcc_mappo_minibatch_grads_state(void *handle, const float *actor, const floa
     return minibatch_grads_impl(h, actor, critic, grad_actor, grad_critic, nullptr, d_pos_vel, d_energy, d_actions, d_logp_old,
                                 d_values, d_returns, d_vn_state, d_stats4, n_rows_global, d_row_index, n_index, d_ret_sums,
                                 n_index_global, d_epoch_stats, static_cast<cudaStream_t>(stream));
+}
+
+// ---- recurrent policies ------------------------------------------------------------------------------------------------------
+int dcc_mappo_rnn_pass_seqs(void *handle, int seq_len) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || seq_len < 1) return -1;
+    return rnn_pass_seqs(h, seq_len);
+}
+
+int dcc_mappo_act_rnn(void *handle, const float *actor, const float *critic, const float *d_obs, int n_envs,
+                      const float *d_h_actor, const float *d_h_critic, const float *d_masks, int mode, uint64_t seed,
+                      uint64_t offset, int deterministic, float *d_actions, float *d_logp, float *d_values, float *d_h_actor_out,
+                      float *d_h_critic_out, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !d_obs || !d_masks || n_envs < 1 || (!actor && !critic) || (mode != 0 && mode != 1)) return DCC_ERR_INVALID_ARG;
+    if ((actor && (!d_actions || !d_h_actor || (mode == 1 && !d_logp))) || (critic && (!d_values || !d_h_critic))) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N < 1) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.n_agents, D = h->cfg.obs_dim, H = h->cfg.hidden, RN = h->cfg.recurrent_N;
+    int rc;
+    if (actor && (rc = fold_ln0(h, h->la, actor, 0, false, s))) return rc;
+    if (critic && (rc = fold_ln0(h, h->lc, critic, 1, false, s))) return rc;
+    for (int e0 = 0; e0 < n_envs; e0 += h->chunk_rows) {
+        const int ne = min(h->chunk_rows, n_envs - e0);
+        const float *x = d_obs + (size_t)e0 * N * D;
+        if (actor) {
+            const int rows = ne * N;
+            rnn_mask_rows_kernel<<<(rows + 255) / 256, 256, 0, s>>>(d_masks + e0, nullptr, N, h->r_mask, rows);
+            if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s))) return rc;
+            const RnnSrc src{d_h_actor + (size_t)e0 * N * RN * H, nullptr, 1};
+            if ((rc = rnn_forward(h, h->la, actor, h->hh[h->la.nblk - 1], rows, 1, src, h->r_mask, s))) return rc;
+            for (int l = 0; l < RN && d_h_actor_out; ++l)
+                gru_store_state_kernel<<<ew_grid((size_t)rows * H), 256, 0, s>>>(h->r_Hout[l], d_h_actor_out, RN, l, rows, H, (size_t)e0 * N);
+            actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
+                h->r_Y, actor + h->la.Wh, actor + h->la.bh, actor + h->la.logstd, d_actions + (size_t)e0 * N * 2, nullptr,
+                d_logp ? d_logp + (size_t)e0 * N : nullptr, rows, H, mode, deterministic, seed, offset, (uint64_t)e0 * N);
+            h->launches += 2 + RN;
+        }
+        if (critic) {     // one row per env: the N agent rows of an env carry identical inputs, masks and hidden states
+            rnn_mask_rows_kernel<<<(ne + 255) / 256, 256, 0, s>>>(d_masks + e0, nullptr, 1, h->r_mask, ne);
+            if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s))) return rc;
+            const RnnSrc src{d_h_critic + (size_t)e0 * RN * H, nullptr, 1};
+            if ((rc = rnn_forward(h, h->lc, critic, h->hh[h->lc.nblk - 1], ne, 1, src, h->r_mask, s))) return rc;
+            for (int l = 0; l < RN && d_h_critic_out; ++l)
+                gru_store_state_kernel<<<ew_grid((size_t)ne * H), 256, 0, s>>>(h->r_Hout[l], d_h_critic_out, RN, l, ne, H, (size_t)e0);
+            critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->r_Y, critic + h->lc.Wh, critic + h->lc.bh, d_values + e0, ne, H);
+            h->launches += 2 + RN;
+        }
+    }
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
+int dcc_mappo_seq_grads(void *handle, const float *actor, const float *critic, float *grad_actor, float *grad_critic,
+                        const float *d_obs, const float *d_h_actor, const float *d_h_critic, const float *d_masks,
+                        const float *d_actions, const float *d_logp_old, const float *d_values, const float *d_returns,
+                        float *d_vn_state, const double *d_stats4, double n_rows_global, const int64_t *d_row_index, int64_t n_seq,
+                        int seq_len, const double *d_ret_sums, double n_index_global, double *d_epoch_stats, dcc_stream_t stream) {
+    MappoHandle *h = as_mappo(handle);
+    if (!h || !actor || !critic || !grad_actor || !grad_critic || !d_obs || !d_h_actor || !d_h_critic || !d_masks || !d_actions ||
+        !d_logp_old || !d_values || !d_returns || !d_stats4 || !d_row_index || !d_ret_sums || !d_epoch_stats || n_seq < 1 ||
+        seq_len < 1 || !(n_rows_global >= 1.0) || !(n_index_global >= 1.0))
+        return DCC_ERR_INVALID_ARG;
+    if (h->cfg.use_valuenorm && !d_vn_state) return DCC_ERR_INVALID_ARG;
+    if (h->cfg.recurrent_N < 1 || rnn_pass_seqs(h, seq_len) < 1) return DCC_ERR_UNSUPPORTED;
+    DCC_DEVICE_GUARD(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.n_agents, H = h->cfg.hidden;
+    const NetLayout &LA = h->la, &LC = h->lc;
+    int rc;
+    if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_ret_sums, n_index_global, d_epoch_stats, s, false)))
+        return rc;
+    const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
+    const PpoLossParams P = loss_params(h, n_index_global);
+    const long Sc = rnn_pass_seqs(h, seq_len);
+    const long long *idx = reinterpret_cast<const long long *>(d_row_index);
+    for (long q0 = 0; q0 < n_seq; q0 += Sc) {
+        const int S = (int)std::min<long>(Sc, n_seq - q0);
+        const int rows = S * seq_len;
+        const long long *pidx = idx + (size_t)q0 * seq_len;          // this pass: [seq_len, S] time-major agent-row indices
+        // the step masks of the pass's rows (masks are stored once per env step: agent row / N)
+        rnn_mask_rows_kernel<<<(rows + 255) / 256, 256, 0, s>>>(d_masks, pidx, N, h->r_mask, rows);
+        h->launches++;
+        // 1) actor: trunk -> GRU -> head -> policy loss -> backward through head / GRU (BPTT inside the pass) / trunk
+        if ((rc = trunk_forward(h, LA, actor, 0, d_obs, rows, true, s, pidx, 1))) return rc;
+        const RnnSrc sa{d_h_actor, pidx, 1};
+        if ((rc = rnn_forward(h, LA, actor, h->hh[LA.nblk - 1], S, seq_len, sa, h->r_mask, s))) return rc;
+        actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(h->r_Y, actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
+                                                                   const_cast<float *>(d_actions), h->mu, h->logp, rows, H, 1, 0, 0, 0, 0, pidx);
+        ppo_policy_loss_mb_kernel<<<(rows + 127) / 128, 128, 0, s>>>(h->mu, h->logp, d_actions, actor + LA.logstd, d_logp_old, d_returns,
+                                                                    d_values, vn_snapshot(h), d_stats4, n_rows_global, pidx, h->dmu,
+                                                                    grad_actor + LA.logstd, d_epoch_stats, rows, P);
+        h->launches += 2;
+        if ((rc = rnn_backward(h, LA, actor, grad_actor, h->hh[LA.nblk - 1], h->dmu, S, seq_len, h->r_mask, s))) return rc;
+        if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, nullptr, rows, s, nullptr, 0, h->r_dfeat))) return rc;
+        // 2) critic, as the reference evaluates it here: one centralised row per AGENT row of the sequences (hidden states and
+        //    masks are those of the env step: row / N)
+        if ((rc = trunk_forward(h, LC, critic, 1, d_obs, rows, true, s, pidx, N))) return rc;
+        const RnnSrc sc{d_h_critic, pidx, N};
+        if ((rc = rnn_forward(h, LC, critic, h->hh[LC.nblk - 1], S, seq_len, sc, h->r_mask, s))) return rc;
+        critic_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(h->r_Y, critic + LC.Wh, critic + LC.bh, h->vnew, rows, H);
+        ppo_value_loss_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats, rows, P, pidx);
+        h->launches += 2;
+        if ((rc = rnn_backward(h, LC, critic, grad_critic, h->hh[LC.nblk - 1], h->dv, S, seq_len, h->r_mask, s))) return rc;
+        if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, nullptr, rows, s, nullptr, 0, h->r_dfeat))) return rc;
+    }
+    if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;
+    if ((rc = ln0_finalize(h, LC, critic, grad_critic, s))) return rc;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
 }
 
 int dcc_mappo_apply(void *handle, int which, float *params, float *grads, float *adam_m, float *adam_v, float lr,

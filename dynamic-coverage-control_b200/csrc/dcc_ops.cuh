@@ -112,11 +112,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
 }
 
 // ---- trunk activation (mlp.py:13: [nn.Tanh(), nn.ReLU()][use_ReLU]) -----------------------------------------------
-enum { ACT_RELU = 0, ACT_TANH = 1 };
-__device__ __forceinline__ float act_fwd(float z, int act) { return act == ACT_RELU ? fmaxf(z, 0.f) : tanhf(z); }
+// ACT_IDENT: no activation — the LayerNorm behind the GRU of a recurrent policy (rnn.py:22,79) reuses the block kernels
+enum { ACT_RELU = 0, ACT_TANH = 1, ACT_IDENT = 2 };
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    return act == ACT_RELU ? fmaxf(z, 0.f) : (act == ACT_TANH ? tanhf(z) : z);
+}
 // derivative expressed through the saved OUTPUT a = act(z): relu' = [a > 0], tanh' = 1 - a^2
 __device__ __forceinline__ float act_bwd(float da, float a, int act) {
-    return act == ACT_RELU ? (a > 0.f ? da : 0.f) : da * (1.f - a * a);
+    return act == ACT_RELU ? (a > 0.f ? da : 0.f) : (act == ACT_TANH ? da * (1.f - a * a) : da);
 }
 
 // ---- row-wise kernels: one warp per row ---------------------------------------------------------------
@@ -271,17 +274,20 @@ __global__ void ln0_finalize_kernel(const float *__restrict__ W1, const float *_
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= F) return;
     const float g = g0[c], b = be0[c];
-    float ag = 0.f, ab = 0.f;
+    // float64 sums: the H terms of a column cancel by up to 5-6 orders of magnitude (the exact dgamma0 / dbeta0 of a column
+    // can sit near Adam's eps while the terms are O(0.1)); a float32 chain leaves ~1e-6 absolute, which Adam turns into a
+    // 1e-4 parameter difference for such a column.  Once per optimiser step, F threads x H terms: free.
+    double ag = 0.0, ab = 0.0;
     for (int h = 0; h < H; ++h) {
         const float w = W1[(size_t)h * F + c];
         const float gv = G[(size_t)h * F + c];
         const float d1 = db1[h];
-        ag = fmaf(w, gv, ag);
-        ab = fmaf(w, d1, ab);
+        ag = fma((double)w, (double)gv, ag);
+        ab = fma((double)w, (double)d1, ab);
         G[(size_t)h * F + c] = fmaf(gv, g, d1 * b);
     }
-    dg0[c] = ag;
-    dbe0[c] = ab;
+    dg0[c] = (float)ag;
+    dbe0[c] = (float)ab;
 }
 
 // a = act(z + bias); h = LayerNorm(a) * gamma + beta.  H <= 256 (8 columns per lane).  a_out optional.

@@ -78,10 +78,10 @@ class Learner:
         # `compact_rollout: false` forces the materialised (T+1, E, N, D) observation tensor; per-env PoI layouts and a
         # decentralised critic need it and select it automatically.
         want = getattr(cfg, "compact_rollout", None)
-        can = (getattr(cfg, "use_centralized_V", True) and
+        can = (getattr(cfg, "use_centralized_V", True) and not self.policy.recurrent_N and
                self.train_envs.pos_pois_per_env is None and not getattr(cfg, "numpy_compat", False))
         if want and not can:
-            raise NotImplementedError("compact_rollout needs use_centralized_V and a shared PoI layout")
+            raise NotImplementedError("compact_rollout needs an MLP policy, use_centralized_V and a shared PoI layout")
         self.compact = bool(can if want is None else want)
         if self.compact:
             self.compact = self.policy.set_env_layout(self.train_envs.pos_pois, self.train_envs.cfg.m_energy)
@@ -213,6 +213,10 @@ class Learner:
                     out_values=r_buffer.values_te[cur_step])
         if r_buffer.compact:
             self.trainer.policy.get_actions_state(r_buffer.state_pv[cur_step], r_buffer.state_en[cur_step], **outs)
+        elif r_buffer.recurrent:     # learner.py:231-238: the step's stored hidden states and masks go in, slot t+1 receives the new ones
+            self.trainer.policy.get_actions(None, r_buffer.obs[cur_step], r_buffer.rnn_a[cur_step], r_buffer.rnn_c[cur_step],
+                                            r_buffer.masks_te[cur_step], out_rnn_actor=r_buffer.rnn_a[cur_step + 1],
+                                            out_rnn_critic=r_buffer.rnn_c[cur_step + 1], **outs)
         else:
             self.trainer.policy.get_actions(None, r_buffer.obs[cur_step], **outs)
         return r_buffer.actions[cur_step]
@@ -228,6 +232,8 @@ class Learner:
         T = r_buffer.episode_length
         if r_buffer.compact:
             self.trainer.policy.get_values_state(r_buffer.state_pv[T], r_buffer.state_en[T], out_values=r_buffer.values_te[T])
+        elif r_buffer.recurrent:
+            self.trainer.policy.get_values(r_buffer.obs[T], r_buffer.rnn_c[T], r_buffer.masks_te[T], out_values=r_buffer.values_te[T])
         else:
             self.trainer.policy.get_values(r_buffer.obs[T], out_values=r_buffer.values_te[T])
         r_buffer.compute_returns(None, self.trainer.value_normalizer, policy=self.policy)

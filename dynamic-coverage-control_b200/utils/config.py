@@ -69,18 +69,30 @@ def load_config(config_dir=None, **overrides):
     return Namespace(**cfg)
 
 
+def is_recurrent(cfg):
+    """r_actor_critic.py:36,102: either flag puts the RNNLayer into both nets."""
+    return bool(getattr(cfg, "use_recurrent_policy", False) or getattr(cfg, "use_naive_recurrent_policy", False))
+
+
 def check_supported(cfg):
     """Branches of mappo.yaml the B200 path implements: everything the shipped configuration enables plus the
     update-path switches (use_huber_loss, use_clipped_value_loss, use_max_grad_norm, use_valuenorm, use_gae,
     use_proper_time_limits, weight_decay, num_mini_batch, use_linear_lr_decay, the *_active_masks flags — no-ops
     in the reference, whose active masks are all ones) and the network switches use_ReLU (tanh trunk),
     use_feature_normalization, use_orthogonal (xavier init), use_centralized_V (per-agent critic), layer_N 1..3.
-    Refused loudly instead of silently computing something else: recurrent policies (other kernel shapes; SURVEY §8
-    f-4) and use_popart, which the unmodified reference itself cannot run (PopArt.update assigns a
-    tensor to an nn.Parameter attribute and raises TypeError on the first update, popart.py:61)."""
+    Recurrent policies (use_recurrent_policy: chunked BPTT over data_chunk_length steps; use_naive_recurrent_policy: whole
+    episodes; recurrent_N 1..4 GRU layers) run with the centralised critic on materialised observation rows.
+    Refused loudly instead of silently computing something else: use_popart, which the unmodified reference itself
+    cannot run (PopArt.update assigns a tensor to an nn.Parameter attribute and raises TypeError on the first update,
+    popart.py:61)."""
     bad = []
-    if getattr(cfg, "use_recurrent_policy", False) or getattr(cfg, "use_naive_recurrent_policy", False):
-        bad.append("recurrent policies")
+    if is_recurrent(cfg):
+        if not 1 <= int(getattr(cfg, "recurrent_N", 1)) <= 4:
+            bad.append("recurrent_N outside 1..4")
+        if not getattr(cfg, "use_centralized_V", True):
+            bad.append("recurrent policies with use_centralized_V: false")
+        if getattr(cfg, "use_recurrent_policy", False) and int(getattr(cfg, "data_chunk_length", 10)) < 1:
+            bad.append("data_chunk_length < 1")
     if getattr(cfg, "use_popart", False):
         bad.append("use_popart")
     # use_stacked_frames / stacked_frames, use_obs_instead_of_state, share_policy, use_render, render_episodes, ifi:

@@ -226,7 +226,11 @@ typedef struct dcc_mappo_cfg {
     int32_t use_relu;                /* 1: ReLU trunk; 0: tanh (mlp.py:13 `[nn.Tanh(), nn.ReLU()][use_ReLU]`) */
     int32_t layer_N;                 /* 1..3: number of fc2 blocks after fc1 (mlp.py:23,27-28); the flat buffers then hold
                                         base.mlp.fc2.{i}.0.weight/.bias, .2.weight/.bias for i < layer_N, in order */
-    int32_t reserved1;
+    int32_t recurrent_N;             /* 0: MLP policy (shipped).  1..4: use_recurrent_policy / use_naive_recurrent_policy — an RNNLayer
+                                        (torch.nn.GRU x recurrent_N + LayerNorm, algos/algo_utils/rnn.py:8-22) between the trunk and the
+                                        head of both nets (r_actor_critic.py:36-37,102-103); the flat buffers then hold, after the last
+                                        fc2 block: rnn.rnn.weight_ih_l{i} [3H, H], weight_hh_l{i} [3H, H], bias_ih_l{i} [3H],
+                                        bias_hh_l{i} [3H] for i < recurrent_N, then rnn.norm.weight / .bias [H] */
 } dcc_mappo_cfg;
 
 int dcc_mappo_cfg_default(dcc_mappo_cfg *cfg);
@@ -380,6 +384,44 @@ int dcc_mappo_minibatch_grads(void *handle, const float *d_actor, const float *d
  */
 int dcc_mappo_apply(void *handle, int which, float *d_params, float *d_grads, float *d_adam_m, float *d_adam_v,
                     float lr, int64_t step, double *d_grad_norm_sq_out, dcc_stream_t stream);
+
+/*
+ * ---- recurrent policies (mappo.yaml use_recurrent_policy / use_naive_recurrent_policy; dcc_mappo_cfg.recurrent_N >= 1) --------
+ * Handles created with recurrent_N >= 1 use these entry points instead of dcc_mappo_act / _evaluate / _epoch_grads /
+ * _minibatch_grads (which return DCC_ERR_UNSUPPORTED for them), on materialised observation rows.
+ *
+ * dcc_mappo_act_rnn replaces MAPPOPolicy.get_actions / get_values / act / evaluate_actions for ONE vec-env step
+ * (algos/mappo.py:43-65 -> R_Actor.forward / R_Critic.forward with the RNNLayer, r_actor_critic.py:43-57,111-121,
+ * rnn.py:24-29): hidden state *= mask, one GRU step per layer, LayerNorm, head.
+ *   d_h_actor  [n_envs*N, recurrent_N, H]  hidden states in (learner.py:233-236: buffer.rnn_states[step])
+ *   d_h_critic [n_envs, recurrent_N, H]    ONE per env: the N agent rows of an env carry identical inputs, masks and states
+ *   d_masks    [n_envs]                    buffer.masks[step] (identical for the agents of an env, learner.py:266-267)
+ *   mode       0 = sample / deterministic mode (writes d_actions, d_logp optional); 1 = log-prob of the GIVEN d_actions
+ *   d_h_actor_out / d_h_critic_out        new hidden states, same shapes (may alias nothing of the inputs; optional)
+ * The caller zeroes the new states of finished episodes before storing them (learner.py:258-265).
+ *
+ * dcc_mappo_seq_grads replaces one ppo_update (algos/mappo.py:133-187) on a minibatch drawn by recurrent_generator
+ * (buffer/shared_buffer.py:378-470, chunks of data_chunk_length steps) or naive_recurrent_generator (:281-376, whole
+ * episodes): n_seq sequences of seq_len consecutive entries of the rollout flattened in (env, agent, time) order, each
+ * started from the stored hidden state of its first entry, BPTT inside the sequence.
+ *   d_row_index [n_seq * seq_len] int64  agent-row indices (t*E*N + e*N + a) of the minibatch, arranged in passes of
+ *               P = dcc_mappo_rnn_pass_seqs(handle, seq_len) sequences: pass p holds sequences [p*P, min((p+1)*P, n_seq)),
+ *               time-major inside the pass (entry l * S_p + s = step l of the pass's s-th sequence)
+ *   d_h_actor   [(T+1)*E*N, recurrent_N, H], d_h_critic [(T+1)*E, recurrent_N, H], d_masks [(T+1)*E]: the rollout's stored
+ *               hidden states and masks; the other arguments as dcc_mappo_minibatch_grads (n_index_global = n_seq * seq_len
+ *               summed over ranks; d_ret_sums from dcc_mappo_minibatch_stats over the same index list).
+ */
+int dcc_mappo_rnn_pass_seqs(void *handle, int seq_len);
+int dcc_mappo_act_rnn(void *handle, const float *d_actor, const float *d_critic, const float *d_obs, int n_envs,
+                      const float *d_h_actor, const float *d_h_critic, const float *d_masks, int mode, uint64_t seed,
+                      uint64_t offset, int deterministic, float *d_actions, float *d_logp, float *d_values,
+                      float *d_h_actor_out, float *d_h_critic_out, dcc_stream_t stream);
+int dcc_mappo_seq_grads(void *handle, const float *d_actor, const float *d_critic, float *d_grad_actor, float *d_grad_critic,
+                        const float *d_obs, const float *d_h_actor, const float *d_h_critic, const float *d_masks,
+                        const float *d_actions, const float *d_logp_old, const float *d_values, const float *d_returns,
+                        float *d_vn_state, const double *d_stats4, double n_rows_global, const int64_t *d_row_index,
+                        int64_t n_seq, int seq_len, const double *d_ret_sums, double n_index_global, double *d_epoch_stats,
+                        dcc_stream_t stream);
 
 /* Kernel-level test hook: C[M,N] (+)= op(A)[M,K] op(B)[K,N], row-major with leading dimensions; ta/tb = operand
  * stored transposed.  backend as dcc_mappo_cfg.gemm_backend (2 requires the shapes the tcgen05 kernels cover); 3 = the

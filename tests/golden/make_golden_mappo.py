@@ -222,6 +222,9 @@ def main():
         run_case("gen_8x64_h256", 8, 64, 4, 12, 256, 4, seed=14)
         run_pickle_case("3x20_h32", 3, 20, 32, seed=15)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "rnn256":
+        run_case("rnn_chunk_4x20_h256", 4, 20, 2, 20, 256, 2, seed=23, extra=dict(use_recurrent_policy=True))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "rnn":         # recurrent policies: GRU + chunked / whole-episode BPTT
         run_case("rnn_chunk_4x20_h32", 4, 20, 2, 20, 32, 3, seed=16, extra=dict(use_recurrent_policy=True))
         run_case("rnn_naive_3x20_h32", 3, 20, 2, 12, 32, 2, seed=17, extra=dict(use_naive_recurrent_policy=True))
@@ -229,7 +232,9 @@ def main():
         run_case("rnn_chunk5_mb2_rn2_3x20_h32", 3, 20, 2, 12, 32, 2, seed=18,
                  extra=dict(use_recurrent_policy=True, recurrent_N=2, data_chunk_length=5, num_mini_batch=2))
         # the tcgen05 trunk (hidden 256) in front of the GRU
-        run_case("rnn_chunk_4x20_h256", 4, 20, 2, 20, 256, 2, seed=19, extra=dict(use_recurrent_policy=True))
+        # (seed 19 puts one fc1 pre-activation of the actor within 1e-7 of zero: the ReLU derivative of that unit then depends on
+        # float32 summation order — the inherent limit described in DESIGN.md §2 — so the fixture uses another seed)
+        run_case("rnn_chunk_4x20_h256", 4, 20, 2, 20, 256, 2, seed=23, extra=dict(use_recurrent_policy=True))
         return
     run_case("ship_4x20_h256", 4, 20, 4, 30, 256, 15, seed=0)     # shipped shapes + hyper-parameters, short rollout
     run_case("gen_8x64_h64", 8, 64, 2, 12, 64, 4, seed=1)         # BASELINE shape, small hidden size

@@ -40,10 +40,23 @@ def test_defaults_equal_the_shipped_yaml_files():
 def test_unsupported_branches_fail_loudly():
     from dcc_b200.utils.config import check_supported, load_config
     check_supported(load_config(None))
-    for key, val in (("use_recurrent_policy", True), ("use_naive_recurrent_policy", True), ("use_popart", True),
-                     ("num_mini_batch", 0), ("layer_N", 4), ("layer_N", 0)):
+    for key, val in (("use_popart", True), ("num_mini_batch", 0), ("layer_N", 4), ("layer_N", 0)):
         cfg = load_config(None)
         setattr(cfg, key, val)
+        with pytest.raises(NotImplementedError):
+            check_supported(cfg)
+    # recurrent policies are implemented (GRU x recurrent_N <= 4, centralised critic)
+    for extra in (dict(use_recurrent_policy=True), dict(use_naive_recurrent_policy=True),
+                  dict(use_recurrent_policy=True, recurrent_N=2, data_chunk_length=5)):
+        cfg = load_config(None)
+        for k, v in extra.items():
+            setattr(cfg, k, v)
+        check_supported(cfg)
+    for extra in (dict(use_recurrent_policy=True, recurrent_N=5), dict(use_recurrent_policy=True, use_centralized_V=False),
+                  dict(use_recurrent_policy=True, data_chunk_length=0)):
+        cfg = load_config(None)
+        for k, v in extra.items():
+            setattr(cfg, k, v)
         with pytest.raises(NotImplementedError):
             check_supported(cfg)
     # update-path switches of mappo.yaml that ARE implemented

@@ -20,11 +20,13 @@ from mappo_util import actor_param_shapes, critic_param_shapes, make_params, net
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "mappo_*.npz")))
+ALL_CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "mappo_*.npz")))
+CASES = [n for n in ALL_CASES if not n.startswith("rnn_")]      # recurrent policies: tests/test_rnn_cuda.py
 BACKENDS = [1, 0]   # SIMT fp32, auto (tcgen05 3xTF32 where the shape allows)
 FLAG_KEYS = ("use_huber_loss", "use_clipped_value_loss", "use_max_grad_norm", "use_valuenorm", "use_gae",
              "use_proper_time_limits", "weight_decay", "num_mini_batch", "use_ReLU", "use_feature_normalization",
-             "use_centralized_V", "layer_N")
+             "use_centralized_V", "layer_N", "use_recurrent_policy", "use_naive_recurrent_policy", "recurrent_N",
+             "data_chunk_length")
 
 
 def load(name):
