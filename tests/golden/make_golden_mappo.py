@@ -179,7 +179,8 @@ def run_init_case(name, N, M, hidden, seed, extra=None):
     meta = dict(name=name, n_agents=N, n_pois=M, hidden=hidden, seed=seed, obs_dim=lr.obs_dim_n[0], gain=float(cfg.gain),
                 use_orthogonal=bool(cfg.use_orthogonal), use_ReLU=bool(cfg.use_ReLU),
                 use_feature_normalization=bool(cfg.use_feature_normalization),
-                use_centralized_V=bool(cfg.use_centralized_V), layer_N=int(cfg.layer_N))
+                use_centralized_V=bool(cfg.use_centralized_V), layer_N=int(cfg.layer_N),
+                recurrent_N=int(cfg.recurrent_N) if (cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy) else 0)
     out["cfg"] = np.array(json.dumps(meta))
     path = os.path.join(HERE, "init_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -221,6 +222,10 @@ def main():
         # 48 env-step rows = 384 agent rows = 3 row tiles
         run_case("gen_8x64_h256", 8, 64, 4, 12, 256, 4, seed=14)
         run_pickle_case("3x20_h32", 3, 20, 32, seed=15)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rnninit":     # RNNLayer's construction order / init (rnn.py:13-22), two GRU layers
+        run_init_case("rnn2_3x20", 3, 20, 32, seed=6, extra=dict(use_recurrent_policy=True, recurrent_N=2))
+        run_init_case("rnn1_xavier_4x20", 4, 20, 64, seed=7, extra=dict(use_naive_recurrent_policy=True, use_orthogonal=False))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rnn256":
         run_case("rnn_chunk_4x20_h256", 4, 20, 2, 20, 256, 2, seed=23, extra=dict(use_recurrent_policy=True))

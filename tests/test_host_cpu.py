@@ -186,7 +186,7 @@ def test_headless_render_and_trajectory_recorder(tmp_path):
     assert os.path.getsize(str(tmp_path / "t.gif")) > 100
 
 
-@pytest.mark.parametrize("name", ["ship_4x20", "xavier_tanh_nofn_decv"])
+@pytest.mark.parametrize("name", ["ship_4x20", "xavier_tanh_nofn_decv", "rnn2_3x20", "rnn1_xavier_4x20"])
 def test_reference_order_initialisation(name):
     """MAPPOPolicy draws its initial weights with the reference's torch RNG consumption order (actor trunk, actor head,
     critic trunk, critic head; orthogonal / xavier_uniform; ReLU / tanh gain): same seed => the reference's weights.
@@ -200,7 +200,7 @@ def test_reference_order_initialisation(name):
     D, Hd, N = c["obs_dim"], c["hidden"], c["n_agents"]
     S = N * D if c["use_centralized_V"] else D
     kw = dict(use_orthogonal=c["use_orthogonal"], use_relu=c["use_ReLU"], feature_norm=c["use_feature_normalization"],
-              layer_N=c.get("layer_N", 1))
+              layer_N=c.get("layer_N", 1), recurrent_N=c.get("recurrent_N", 0))
     torch.manual_seed(c["seed"])
     sd_a, head_a = _reference_init(D, Hd, 2, c["gain"], **kw)
     sd_a["act.action_out.fc_mean.weight"], sd_a["act.action_out.fc_mean.bias"] = head_a.weight.data, head_a.bias.data
