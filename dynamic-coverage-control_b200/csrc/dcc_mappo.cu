@@ -87,6 +87,14 @@ struct MappoHandle {
     double *d_poi;           // [M, 2] PoI table
     float *fc;               // [chunk, cd.ldc] critic features (the actor's [chunk*N, cd.lda] live in x0)
     float *head_fold[2];     // output head folded through the last LayerNorm affine, for the fused epilogue (head_fold_kernel)
+    // "xhat mode" (backend 2, pre-split operands, ReLU trunk): an inner block k < last stores ONLY xhat_k = (a_k - mean) rstd, pre-split
+    // (no a_k, no affine), and block k+1 runs on weights with the LayerNorm affine folded in, W_{k+1} * gamma_k and
+    // b_{k+1} + W_{k+1} beta_k — the trick of the input LayerNorm (§5.1) applied to every inner LayerNorm.  Halves the bytes the
+    // fused forward epilogue has to push out (its bound); the backward pass rebuilds the ReLU mask from xhat (relu_lnx_bwd_pipe_kernel)
+    // and gets dgamma_k / dbeta_k from G_{k+1} = dz_{k+1}^T xhat_k once per optimiser step (ln0_finalize_kernel).  DCC_TC_XHAT=0 disables.
+    bool xhat;
+    float *wf[2][MAX_BLOCKS], *bf[2][MAX_BLOCKS];   // folded weights / biases of blocks >= 1 [actor, critic]
+    float *ones, *zeros;                            // [H]: unit LayerNorm affine handed to the epilogue of inner blocks
     float *wt[2];            // folded fc1 weights [H, ld] (actor, critic)
     float *gt[2];            // running dz1^T f of the epoch [H, ld]
     // recurrent policies (dcc_rnn.cuh): per GRU layer the masked previous states, x W_ih^T / h W_hh^T (overwritten by their
@@ -188,6 +196,7 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
 static int pipe_set_kernel_attributes() {
     const int bytes = 64 * 1024;
     DCC_CUDA_TRY(cudaFuncSetAttribute(relu_ln_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return DCC_OK;
@@ -349,6 +358,25 @@ static int fold_head(MappoHandle *h, const NetLayout &L, const float *P, int net
     return DCC_OK;
 }
 
+// weight images of the blocks >= 1 (forward, and transposed for dX).  xhat mode: block k runs on the previous block's UN-affined
+// LayerNorm output, so its weights carry that LayerNorm's affine: W' = W_k * gamma_{k-1}, b' = b_k + W_k beta_{k-1} (fold_ln0_kernel)
+static int prep_inner_images(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
+    int rc;
+    for (int k = 1; k < L.nblk; ++k) {
+        const float *Wk = P + L.W[k];
+        if (h->xhat) {
+            fold_ln0_kernel<<<(L.H + 7) / 8, 256, 0, s>>>(P + L.W[k], P + L.b[k], P + L.lg[k - 1], P + L.lb[k - 1], h->wf[net][k],
+                                                          h->bf[net][k], L.H, L.H);
+            h->launches++;
+            DCC_CUDA_TRY(cudaGetLastError());
+            Wk = h->wf[net][k];
+        }
+        if ((rc = tc_prep_weights(h, Wk, L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
+        if (for_backward && (rc = tc_prep_weights(h, Wk, L.H, true, L.H, h->img_wt[net][k], s, h->f16_dx))) return rc;
+    }
+    return DCC_OK;
+}
+
 // fold the input LayerNorm affine into fc1 (done once per ABI call: the parameters change after every apply)
 static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
     float *w1g = net ? h->w1g_c : h->w1g_a, *b1g = net ? h->b1g_c : h->b1g_a;
@@ -360,10 +388,7 @@ static int fold_ln0(MappoHandle *h, const NetLayout &L, const float *P, int net,
         int rc;
         if ((rc = fold_head(h, L, P, net, s))) return rc;
         if ((rc = tc_prep_weights(h, w1g, L.in, false, L.in, h->img_w1[net], s, fwd_f16(h, L, 0)))) return rc;
-        for (int k = 1; k < L.nblk; ++k) {
-            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
-            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_dx))) return rc;
-        }
+        if ((rc = prep_inner_images(h, L, P, net, for_backward, s))) return rc;
     }
     return DCC_OK;
 }
@@ -400,10 +425,7 @@ static int fold_compact(MappoHandle *h, const NetLayout &L, const float *P, int 
         int rc;
         if ((rc = fold_head(h, L, P, net, s))) return rc;
         if ((rc = tc_prep_weights(h, h->wt[net], ldk, false, ldk, h->img_w1[net], s, h->f16_fwd))) return rc;
-        for (int k = 1; k < L.nblk; ++k) {
-            if ((rc = tc_prep_weights(h, P + L.W[k], L.H, false, L.H, h->img_w[net][k], s, fwd_f16(h, L, k)))) return rc;
-            if (for_backward && (rc = tc_prep_weights(h, P + L.W[k], L.H, true, L.H, h->img_wt[net][k], s, h->f16_dx))) return rc;
-        }
+        if ((rc = prep_inner_images(h, L, P, net, for_backward, s))) return rc;
     }
     return DCC_OK;
 }
@@ -466,8 +488,11 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
             const bool in_split = h->split16 && (k > 0 || feat != nullptr), out_split = h->split16 && !last_blk;
             const Split16 a16 = in_split ? (k == 0 ? feat_split(h, net) : hh_split(h, k - 1)) : Split16{nullptr, nullptr, 0};
             const Split16 h16 = out_split ? hh_split(h, k) : Split16{nullptr, nullptr, 0};
-            rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], save ? h->a[k] : nullptr, H, s,
-                             bk, P + L.lg[k], P + L.lb[k], (fuse || out_split) ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
+            // xhat mode: an inner block leaves only xhat_k (pre-split, unit affine; no a_k) and runs on the folded bias
+            const bool xo = h->xhat && out_split, xi = h->xhat && k > 0;
+            rc = tc_gemm_fwd(h, rows, ldin, in, ldin, k == 0 ? h->img_w1[net] : h->img_w[net][k], (save && !xo) ? h->a[k] : nullptr, H, s,
+                             xi ? h->bf[net][k] : bk, xo ? h->ones : P + L.lg[k], xo ? h->zeros : P + L.lb[k],
+                             (fuse || out_split) ? nullptr : h->hh[k], save ? h->mean[k] : nullptr,
                              save ? h->rstd[k] : nullptr,
                              (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k),   // compact features are bounded: fp16-split eligible
                              nullptr, fuse ? h->head_fold[net] : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr,
@@ -548,7 +573,17 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                                            nullptr, dx16, dx16 ? h->dz_absmax : nullptr)   // dh_{k-1} = dz_k W_k
                              : launch_gemm(h, false, false, rows, H, H, dz, H, P + L.W[k], H, dx, H, false, s);
         if (rc) return rc;
-        if (h->ln_pipe) {
+        if (h->xhat && sp) {
+            // xhat mode: dx holds the gradient w.r.t. xhat_{k-1} (folded weights); the mask comes from the stored xhat itself
+            uint32_t *am = ((dx16 && k - 1 >= 1) || (k - 1 >= 1 || feat)) ? h->dz_absmax : nullptr;
+            if (am) DCC_CUDA_TRY(cudaMemsetAsync(am, 0, sizeof(uint32_t), s));
+            const Split16 xs = hh_split(h, k - 1);
+            const size_t ring = (size_t)wpb * RP_SLOTS * 2 * H;
+            relu_lnx_bwd_pipe_kernel<<<grid_for_reduce(h, rows, wpb, 3), wpb * 32, std::max(ring, (size_t)wpb * 256) * sizeof(float), s>>>(
+                dx, static_cast<const __half *>(xs.hi), static_cast<const __half *>(xs.lo), h->mean[k - 1], h->rstd[k - 1], dx,
+                G + L.b[k - 1], rows, H, am);   // dx := dz_{k-1}
+            DCC_CUDA_TRY(cudaGetLastError());
+        } else if (h->ln_pipe) {
             // max |dz_{k-1}|: needed by the next dX GEMM (k-1 >= 1) and by the fp16-split weight-gradient GEMM of block k-1
             uint32_t *am = ((dx16 && k - 1 >= 1) || (sp && (k - 1 >= 1 || feat))) ? h->dz_absmax : nullptr;
             if (am) DCC_CUDA_TRY(cudaMemsetAsync(am, 0, sizeof(uint32_t), s));
@@ -577,7 +612,22 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     return DCC_OK;
 }
 
+// xhat mode, once per optimiser step: the weight slot of every block k >= 1 holds G_k = dz_k^T xhat_{k-1}; turn it into
+// dW_k = G_k * gamma_{k-1} + db_k (x) beta_{k-1} and produce dgamma_{k-1} = sum_h W_k * G_k, dbeta_{k-1} = W_k^T db_k
+static int inner_ln_finalize(MappoHandle *h, const NetLayout &L, const float *P, float *G, cudaStream_t s) {
+    if (!h->xhat) return DCC_OK;
+    for (int k = 1; k < L.nblk; ++k) {
+        ln0_finalize_kernel<<<(L.H + 127) / 128, 128, 0, s>>>(P + L.W[k], P + L.lg[k - 1], P + L.lb[k - 1], G + L.W[k], G + L.b[k],
+                                                             G + L.lg[k - 1], G + L.lb[k - 1], L.H, L.H);
+        h->launches++;
+    }
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
 static int ln0_finalize(MappoHandle *h, const NetLayout &L, const float *P, float *G, cudaStream_t s) {
+    int rc = inner_ln_finalize(h, L, P, G, s);
+    if (rc) return rc;
     if (!L.has_ln0) return DCC_OK;   // no feature_norm: the fc1 slot already holds dW1 = dz1^T x
     ln0_finalize_kernel<<<(L.in + 127) / 128, 128, 0, s>>>(P + L.W[0], P + L.ln0_g, P + L.ln0_b, G + L.W[0], G + L.b[0], G + L.ln0_g,
                                                           G + L.ln0_b, L.H, L.in);
@@ -764,6 +814,8 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     h->f16_dx = h->backend == 2 && h->ln_pipe && !(getenv("DCC_TC_DX_F16") && atoi(getenv("DCC_TC_DX_F16")) == 0);
     h->split16 = h->backend == 2 && h->f16_fwd && !(getenv("DCC_TC_SPLIT") && atoi(getenv("DCC_TC_SPLIT")) == 0) &&
                  !(getenv("DCC_TC_TMA") && atoi(getenv("DCC_TC_TMA")) == 0) && tc::tc_tensor_map_encoder() != nullptr;
+    // xhat mode needs the pre-split operand path, the row-pipeline kernels and ReLU (the mask is rebuilt from xhat)
+    h->xhat = h->split16 && h->ln_pipe && cfg->use_relu != 0 && !(getenv("DCC_TC_XHAT") && atoi(getenv("DCC_TC_XHAT")) == 0);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
@@ -812,6 +864,17 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
     if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
     for (int n = 0; n < 2 && h->backend == 2; ++n) alloc(&h->head_fold[n], 2 * 256 + 8);
+    if (h->xhat) {
+        for (int n = 0; n < 2; ++n)
+            for (int k = 1; k < h->la.nblk; ++k) { alloc(&h->wf[n][k], (size_t)H * H); alloc(&h->bf[n][k], H); }
+        alloc(&h->ones, H); alloc(&h->zeros, H);
+        if (ce == cudaSuccess) ce = cudaMemset(h->zeros, 0, H * sizeof(float));
+        if (ce == cudaSuccess) {
+            float one[256];
+            for (int i = 0; i < 256; ++i) one[i] = 1.f;
+            ce = cudaMemcpy(h->ones, one, H * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
     if (cfg->recurrent_N > 0) {
         for (int l = 0; l < cfg->recurrent_N; ++l) {
             alloc(&h->r_Hp[l], RA * H); alloc(&h->r_GI[l], RA * 3 * H); alloc(&h->r_GH[l], RA * 3 * H);
@@ -843,6 +906,9 @@ int dcc_mappo_destroy(void *handle) {
         float *blk[] = {h->a[k], h->hh[k], h->mean[k], h->rstd[k], h->img_w[0][k], h->img_w[1][k], h->img_wt[0][k], h->img_wt[1][k]};
         for (float *b : blk) cudaFree(b);
     }
+    for (int n = 0; n < 2; ++n)
+        for (int k = 0; k < MAX_BLOCKS; ++k) { cudaFree(h->wf[n][k]); cudaFree(h->bf[n][k]); }
+    cudaFree(h->ones); cudaFree(h->zeros);
     for (int l = 0; l < MAX_RNN; ++l) {
         float *rb[] = {h->r_Hp[l], h->r_GI[l], h->r_GH[l], h->r_gates[l], h->r_Hout[l]};
         for (float *b : rb) cudaFree(b);

@@ -5,6 +5,7 @@
 // (LayerNorm -> [Linear, ReLU, LayerNorm] x 2), algos/algo_utils/distributions.py:33-41,83-92 (diagonal Gaussian),
 // algos/mappo.py:103-187 (PPO update), buffer/shared_buffer.py:199-208 (GAE), utils/valuenorm.py:32-79.
 #pragma once
+#include <cuda_fp16.h>
 #include "dcc_common.cuh"
 
 namespace dcc {
@@ -621,6 +622,106 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
     block_combine_atomic<3>(acc, dst, H, dyn_sm);
 }
 
+// "xhat mode" backward of an inner block (dcc_mappo.cu, MappoHandle::xhat): the block's LayerNorm output was stored WITHOUT affine
+// and pre-split, xhat = hi + lo (two fp16 rows), and the gradient arriving here is already the one w.r.t. xhat (the next block ran
+// on gamma-folded weights, so dX = dz W' = (dz W) * gamma).  Per row: LayerNorm backward through the normalisation only, then the
+// ReLU mask rebuilt from xhat: a > 0  <=>  xhat > xhat(a = 0) = (0 - mean) rstd, compared after the same fp16 hi/lo rounding the
+// stored values went through (monotone, so the only rows that can differ from the exact mask are activations within 2^-22 of the
+// row's |xhat(0)| above zero).  Accumulates only the Linear's bias gradient: dgamma / dbeta of this block's LayerNorm follow once
+// per optimiser step from the next block's G = dz^T xhat (ln0_finalize_kernel).  Reads 2 KB per row (dxh fp32 + hi + lo), the same
+// bytes as relu_ln_bwd_pipe_kernel; one column accumulator instead of three.
+// Dynamic shared memory = max(8 * RP_SLOTS * 2 * H, 8 * 1 * 256) floats.  H % 8 == 0.
+__global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *dxh_in, const __half *__restrict__ xh_hi,
+                                                                   const __half *__restrict__ xh_lo, const float *__restrict__ mean,
+                                                                   const float *__restrict__ rstd, float *dz,
+                                                                   float *__restrict__ dbias, int rows, int H,
+                                                                   uint32_t *__restrict__ absmax_out) {
+    extern __shared__ __align__(128) float dyn_sm[];
+    __shared__ __align__(8) uint64_t bars[8 * RP_SLOTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int stride = gridDim.x * wpb;
+    const uint32_t row_bytes = (uint32_t)H * 4, half_bytes = (uint32_t)H * 2;
+    float *ring = dyn_sm + (size_t)warp * RP_SLOTS * 2 * H;
+    const uint32_t ring_u32 = rp_smem_u32(ring), bar_u32 = rp_smem_u32(bars + warp * RP_SLOTS);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < RP_SLOTS; ++s) rp_bar_init(bar_u32 + 8 * s);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    float accb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accb[j] = 0.f;
+    const int r0 = blockIdx.x * wpb + warp;
+    const int n_my = r0 < rows ? (rows - r0 + stride - 1) / stride : 0;
+    auto issue = [&](int slot, int row) {      // lane 0: slot = [dxh row | hi row | lo row]
+        const uint32_t bar = bar_u32 + 8 * slot, dst = ring_u32 + (uint32_t)slot * 2 * row_bytes;
+        rp_expect_tx(bar, 2 * row_bytes);
+        rp_bulk_g2s(dst, dxh_in + (size_t)row * H, row_bytes, bar);
+        rp_bulk_g2s(dst + row_bytes, xh_hi + (size_t)row * H, half_bytes, bar);
+        rp_bulk_g2s(dst + row_bytes + half_bytes, xh_lo + (size_t)row * H, half_bytes, bar);
+    };
+    if (lane == 0)
+        for (int s = 0; s < RP_SLOTS && s < n_my; ++s) issue(s, r0 + s * stride);
+    float mn = 0.f, rn = 0.f, amax = 0.f;
+    if (n_my > 0) { mn = __ldg(mean + r0); rn = __ldg(rstd + r0); }
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int k = 0; k < n_my; ++k) {
+        const int r = r0 + k * stride;
+        const float m = mn, rs = rn;
+        if (k + 1 < n_my) { mn = __ldg(mean + r + stride); rn = __ldg(rstd + r + stride); }
+        // xhat of a zero activation, through the same hi / lo rounding as the stored values
+        const float t0 = (0.f - m) * rs;
+        const float th = __half2float(__float2half_rn(t0));
+        const float thr = th + __half2float(__float2half_rn(t0 - th));
+        rp_wait(bar_u32 + 8 * slot, parity);
+        const float *sd = ring + (size_t)slot * 2 * H;
+        const __half *shi = reinterpret_cast<const __half *>(sd + H), *slo = shi + H;
+        float xh[8], dxh[8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            const bool ok = c < H;
+            dxh[j] = ok ? sd[c] : 0.f;
+            xh[j] = ok ? __half2float(shi[c]) + __half2float(slo[c]) : 0.f;
+            s1 += dxh[j];
+            s2 = fmaf(dxh[j], xh[j], s2);
+        }
+        __syncwarp();                               // every lane has read the slot
+        if (lane == 0 && k + RP_SLOTS < n_my) {
+            fence_proxy_async_smem();
+            issue(slot, r + RP_SLOTS * stride);
+        }
+        const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < H) {
+                const float da = rs * (dxh[j] - c1 - xh[j] * c2);
+                const float v = xh[j] > thr ? da : 0.f;
+                dz[(size_t)r * H + c] = v;
+                accb[j] += v;
+                amax = fmaxf(amax, fabsf(v));
+            }
+        }
+        if (++slot == RP_SLOTS) { slot = 0; parity ^= 1; }
+    }
+    if (absmax_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL_MASK, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(absmax_out, __float_as_uint(amax));
+    }
+    __syncthreads();                                // all rings idle: the combine scratch aliases them
+    float acc1[1][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc1[0][j] = accb[j];
+    float *const dst[1] = {dbias};
+    block_combine_atomic<1>(acc1, dst, H, dyn_sm);
+}
+
 // head_relu_ln_bwd_kernel with the row pipeline (one array: the saved activation a).  Dynamic shared memory =
 // max(8 * RP_SLOTS * H, 8 * (3 + OUT) * 256) floats.
 // Because dh2 = dout Wh has rank OUT, three of the per-row column accumulators are not needed: with
@@ -628,7 +729,10 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
 // the gradients are  dWh[o,c] = gamma[c] P[o][c] + beta[c] D[o],  dgamma[c] = sum_o Wh[o,c] P[o][c],  dbeta[c] = sum_o Wh[o,c] D[o]
 // (formed once per warp after the row loop), so the loop carries OUT + 1 column accumulators (P, dbias) instead of OUT + 3
 // and fewer instructions per row.  (Squeezed into 80 registers for 3 CTAs per SM it ran SLOWER, 158 -> 188 us: kept at 2.)
-template <int OUT>
+// SLOTS = rows in flight per warp.  6 instead of 3 was measured (96 KB instead of 48 KB of loads in flight per SM): no change,
+// 179.0 vs 178.4 ms per update at 8192 envs — the kernel is issue-bound (ncu: 72 % issue utilisation with 3.9 warps per scheduler,
+// 368 warp instructions per row), not latency-bound.
+template <int OUT, int SLOTS = RP_SLOTS>
 __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
@@ -636,16 +740,16 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
                                         float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dWh,
                                         float *__restrict__ dbh, int rows, int H, int act, uint32_t *__restrict__ absmax_out) {
     extern __shared__ __align__(128) float dyn_sm[];
-    __shared__ __align__(8) uint64_t bars[8 * RP_SLOTS];
+    __shared__ __align__(8) uint64_t bars[8 * SLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int stride = gridDim.x * wpb;
     const uint32_t row_bytes = (uint32_t)H * 4;
-    float *ring = dyn_sm + (size_t)warp * RP_SLOTS * H;
-    const uint32_t ring_u32 = rp_smem_u32(ring), bar_u32 = rp_smem_u32(bars + warp * RP_SLOTS);
+    float *ring = dyn_sm + (size_t)warp * SLOTS * H;
+    const uint32_t ring_u32 = rp_smem_u32(ring), bar_u32 = rp_smem_u32(bars + warp * SLOTS);
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < RP_SLOTS; ++s) rp_bar_init(bar_u32 + 8 * s);
+        for (int s = 0; s < SLOTS; ++s) rp_bar_init(bar_u32 + 8 * s);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -668,7 +772,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
         rp_bulk_g2s(ring_u32 + (uint32_t)slot * row_bytes, a + (size_t)row * H, row_bytes, bar);
     };
     if (lane == 0)
-        for (int s = 0; s < RP_SLOTS && s < n_my; ++s) issue(s, r0 + s * stride);
+        for (int s = 0; s < SLOTS && s < n_my; ++s) issue(s, r0 + s * stride);
     float mn = 0.f, rn = 0.f, dn[OUT], amax = 0.f;
 #pragma unroll
     for (int o = 0; o < OUT; ++o) dn[o] = 0.f;
@@ -708,9 +812,9 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
             s2 = fmaf(dx, xh[j], s2);
         }
         __syncwarp();
-        if (lane == 0 && k + RP_SLOTS < n_my) {
+        if (lane == 0 && k + SLOTS < n_my) {
             fence_proxy_async_smem();
-            issue(slot, r + RP_SLOTS * stride);
+            issue(slot, r + SLOTS * stride);
         }
         const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
 #pragma unroll
@@ -724,7 +828,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
                 amax = fmaxf(amax, fabsf(v));
             }
         }
-        if (++slot == RP_SLOTS) { slot = 0; parity ^= 1; }
+        if (++slot == SLOTS) { slot = 0; parity ^= 1; }
     }
     if (absmax_out) {
 #pragma unroll

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--backend", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--compact", type=int, default=-1, help="1 / 0 = compact / materialised rollout storage (default: auto)")
+    ap.add_argument("--profile-update", action="store_true",
+                    help="cudaProfilerStart/Stop around the LAST iteration's update (ncu --profile-from-start off)")
     a = ap.parse_args()
     cfg = load_config(None, num_agents=a.n, num_pois=a.m, n_rollout_threads=a.envs, max_ep_len=a.T, ppo_epoch=a.epochs,
                       n_iters=a.iters + 1, n_eval_rollout_threads=0, save_model=False, gemm_backend=a.backend,
@@ -35,7 +37,14 @@ def main():
         ev[0].record()
         ri = lr.rollout(lr.rl_buffer, lr.train_envs)
         ev[1].record()
+        prof = a.profile_update and it == a.iters + 1
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         ti = lr.rl_update()
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         ev[2].record()
         torch.cuda.synchronize()
         r_ms, u_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])

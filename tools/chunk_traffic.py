@@ -31,6 +31,11 @@ for r in rows[2:]:
                      dram_write=val(r, "dram__bytes_write.sum"),
                      tensor_pct=val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                      dram_pct=val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
+# optional window: first=<kernel-name substring> count=<n> keeps n kernels starting at the first match (one super-chunk of the update)
+opts = dict(kv.split("=", 1) for kv in sys.argv[2:] if "=" in kv)
+if "first" in opts:
+    i0 = next(i for i, k in enumerate(kern) if opts["first"] in k["kernel"])
+    kern = kern[i0:i0 + int(opts.get("count", len(kern)))]
 tot_b = sum(k["dram_read"] + k["dram_write"] for k in kern)
 tot_us = sum(k["us"] for k in kern)
 for k in kern:
@@ -41,6 +46,8 @@ if len(sys.argv) > 2 and not "=" in sys.argv[2]:
     out = dict(dram_bytes_per_chunk=tot_b, sum_kernel_us=tot_us, kernels=kern)
     for kv in sys.argv[3:]:
         k, v = kv.split("=", 1)
+        if k in ("first", "count"):
+            continue
         try:
             v = json.loads(v)
         except Exception:
