@@ -196,7 +196,10 @@ static int tc_prep_weights(MappoHandle *h, const float *W, int ldw, bool transpo
 static int pipe_set_kernel_attributes() {
     const int bytes = 64 * 1024;
     DCC_CUDA_TRY(cudaFuncSetAttribute(relu_ln_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<1, RP_SLOTS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<2, RP_SLOTS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return DCC_OK;
@@ -542,15 +545,18 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
                                                                                  G + L.b[last], rows, H, act_of(h));
         DCC_CUDA_TRY(cudaGetLastError());
     } else if (h->ln_pipe) {
+        // H == 256: the column map with 16-byte accesses (col_of<true>); DCC_LN_VEC=0 keeps the scalar map (A/B knob)
+        static const bool vec_env = !(getenv("DCC_LN_VEC") && atoi(getenv("DCC_LN_VEC")) == 0);
+        const bool vec = vec_env && H == 256;
         const size_t ring = (size_t)wpb * RP_SLOTS * H;
-        if (L.out == 2)
-            head_relu_ln_bwd_pipe_kernel<2><<<gr_head, wpb * 32, std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), s>>>(
-                dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
-                G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
-        else
-            head_relu_ln_bwd_pipe_kernel<1><<<gr_head, wpb * 32, std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float), s>>>(
-                dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last],
-                G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax);
+#define DCC_HEAD_ARGS dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last], \
+                      G + L.lb[last], G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), amax
+        const size_t sm2 = std::max(ring, (size_t)wpb * 5 * 256) * sizeof(float), sm1 = std::max(ring, (size_t)wpb * 4 * 256) * sizeof(float);
+        if (L.out == 2 && vec) head_relu_ln_bwd_pipe_kernel<2, RP_SLOTS, true><<<gr_head, wpb * 32, sm2, s>>>(DCC_HEAD_ARGS);
+        else if (L.out == 2) head_relu_ln_bwd_pipe_kernel<2><<<gr_head, wpb * 32, sm2, s>>>(DCC_HEAD_ARGS);
+        else if (vec) head_relu_ln_bwd_pipe_kernel<1, RP_SLOTS, true><<<gr_head, wpb * 32, sm1, s>>>(DCC_HEAD_ARGS);
+        else head_relu_ln_bwd_pipe_kernel<1><<<gr_head, wpb * 32, sm1, s>>>(DCC_HEAD_ARGS);
+#undef DCC_HEAD_ARGS
         DCC_CUDA_TRY(cudaGetLastError());
     } else if (L.out == 2)
         head_relu_ln_bwd_kernel<2><<<gr_head, wpb * 32, wpb * 5 * 256 * sizeof(float), s>>>(dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last],
@@ -579,9 +585,16 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
             if (am) DCC_CUDA_TRY(cudaMemsetAsync(am, 0, sizeof(uint32_t), s));
             const Split16 xs = hh_split(h, k - 1);
             const size_t ring = (size_t)wpb * RP_SLOTS * 2 * H;
-            relu_lnx_bwd_pipe_kernel<<<grid_for_reduce(h, rows, wpb, 3), wpb * 32, std::max(ring, (size_t)wpb * 256) * sizeof(float), s>>>(
-                dx, static_cast<const __half *>(xs.hi), static_cast<const __half *>(xs.lo), h->mean[k - 1], h->rstd[k - 1], dx,
-                G + L.b[k - 1], rows, H, am);   // dx := dz_{k-1}
+            static const bool vec_env = !(getenv("DCC_LN_VEC") && atoi(getenv("DCC_LN_VEC")) == 0);
+            static const int lnx_ctas = getenv("DCC_LNX_CTAS") ? atoi(getenv("DCC_LNX_CTAS")) : 4;
+            const int gx = grid_for_reduce(h, rows, wpb, lnx_ctas);
+            const size_t smx = std::max(ring, (size_t)wpb * 256) * sizeof(float);
+            if (vec_env && H == 256)
+                relu_lnx_bwd_pipe_kernel<true><<<gx, wpb * 32, smx, s>>>(dx, static_cast<const __half *>(xs.hi), static_cast<const __half *>(xs.lo),
+                                                                       h->mean[k - 1], h->rstd[k - 1], dx, G + L.b[k - 1], rows, H, am);
+            else
+                relu_lnx_bwd_pipe_kernel<false><<<gx, wpb * 32, smx, s>>>(dx, static_cast<const __half *>(xs.hi), static_cast<const __half *>(xs.lo),
+                                                                        h->mean[k - 1], h->rstd[k - 1], dx, G + L.b[k - 1], rows, H, am);   // dx := dz_{k-1}
             DCC_CUDA_TRY(cudaGetLastError());
         } else if (h->ln_pipe) {
             // max |dz_{k-1}|: needed by the next dX GEMM (k-1 >= 1) and by the fp16-split weight-gradient GEMM of block k-1

@@ -334,13 +334,21 @@ __global__ void bias_relu_ln_fwd_kernel(const float *__restrict__ z, const float
 // block deposits its NV vectors of 8 values per lane (column = lane + 32 j) in shared memory, then thread t adds up
 // column t over the warps and issues ONE atomic per vector — 8x fewer atomics than per-warp, which lets these
 // streaming kernels run 4 CTAs per SM (enough loads in flight for HBM) without flooding the L2 atomic units.
-template <int NV>
+// Column owned by element j of a lane's 8-vector.  Default map: lane + 32 j (any H <= 256, scalar accesses).  VEC map (H == 256
+// only): two runs of 4 consecutive columns, 4 lane + {0..3} and 128 + 4 lane + {0..3}, so that a row moves with two 16-byte
+// accesses per lane instead of eight 4-byte ones (the streaming kernels below are issue-bound, not bandwidth-bound).
+template <bool VEC>
+__device__ __forceinline__ int col_of(int lane, int j) {
+    return VEC ? ((j < 4) ? 4 * lane + j : 128 + 4 * lane + (j - 4)) : lane + 32 * j;
+}
+
+template <int NV, bool VEC = false>
 __device__ __forceinline__ void block_combine_atomic(float (&acc)[NV][8], float *const (&dst)[NV], int H, float *sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sm[(warp * NV + v) * 256 + lane + 32 * j] = acc[v][j];
+        for (int j = 0; j < 8; ++j) sm[(warp * NV + v) * 256 + col_of<VEC>(lane, j)] = acc[v][j];
     __syncthreads();
     const int c = threadIdx.x;
     if (c < H) {
@@ -631,7 +639,8 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
 // per optimiser step from the next block's G = dz^T xhat (ln0_finalize_kernel).  Reads 2 KB per row (dxh fp32 + hi + lo), the same
 // bytes as relu_ln_bwd_pipe_kernel; one column accumulator instead of three.
 // Dynamic shared memory = max(8 * RP_SLOTS * 2 * H, 8 * 1 * 256) floats.  H % 8 == 0.
-__global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *dxh_in, const __half *__restrict__ xh_hi,
+template <bool VEC>
+__global__ void __launch_bounds__(256, 4) relu_lnx_bwd_pipe_kernel(const float *dxh_in, const __half *__restrict__ xh_hi,
                                                                    const __half *__restrict__ xh_lo, const float *__restrict__ mean,
                                                                    const float *__restrict__ rstd, float *dz,
                                                                    float *__restrict__ dbias, int rows, int H,
@@ -681,14 +690,28 @@ __global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *
         const __half *shi = reinterpret_cast<const __half *>(sd + H), *slo = shi + H;
         float xh[8], dxh[8];
         float s1 = 0.f, s2 = 0.f;
+        if constexpr (VEC) {      // H == 256: 16-byte gradient loads, 8-byte loads of 4 halves
+            const float4 d0 = *reinterpret_cast<const float4 *>(sd + 4 * lane), d1 = *reinterpret_cast<const float4 *>(sd + 128 + 4 * lane);
+            dxh[0] = d0.x; dxh[1] = d0.y; dxh[2] = d0.z; dxh[3] = d0.w; dxh[4] = d1.x; dxh[5] = d1.y; dxh[6] = d1.z; dxh[7] = d1.w;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            const bool ok = c < H;
-            dxh[j] = ok ? sd[c] : 0.f;
-            xh[j] = ok ? __half2float(shi[c]) + __half2float(slo[c]) : 0.f;
-            s1 += dxh[j];
-            s2 = fmaf(dxh[j], xh[j], s2);
+            for (int q = 0; q < 2; ++q) {
+                const uint2 hv = *reinterpret_cast<const uint2 *>(shi + 128 * q + 4 * lane), lv = *reinterpret_cast<const uint2 *>(slo + 128 * q + 4 * lane);
+                const float2 h01 = __half22float2(*reinterpret_cast<const __half2 *>(&hv.x)), h23 = __half22float2(*reinterpret_cast<const __half2 *>(&hv.y));
+                const float2 l01 = __half22float2(*reinterpret_cast<const __half2 *>(&lv.x)), l23 = __half22float2(*reinterpret_cast<const __half2 *>(&lv.y));
+                xh[4 * q + 0] = h01.x + l01.x; xh[4 * q + 1] = h01.y + l01.y; xh[4 * q + 2] = h23.x + l23.x; xh[4 * q + 3] = h23.y + l23.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1 += dxh[j]; s2 = fmaf(dxh[j], xh[j], s2); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                const bool ok = c < H;
+                dxh[j] = ok ? sd[c] : 0.f;
+                xh[j] = ok ? __half2float(shi[c]) + __half2float(slo[c]) : 0.f;
+                s1 += dxh[j];
+                s2 = fmaf(dxh[j], xh[j], s2);
+            }
         }
         __syncwarp();                               // every lane has read the slot
         if (lane == 0 && k + RP_SLOTS < n_my) {
@@ -696,16 +719,24 @@ __global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *
             issue(slot, r + RP_SLOTS * stride);
         }
         const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
+        float vout[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            if (c < H) {
+            const int c = col_of<VEC>(lane, j);
+            vout[j] = 0.f;
+            if (VEC || c < H) {
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
                 const float v = xh[j] > thr ? da : 0.f;
-                dz[(size_t)r * H + c] = v;
+                vout[j] = v;
+                if constexpr (!VEC) dz[(size_t)r * H + c] = v;
                 accb[j] += v;
                 amax = fmaxf(amax, fabsf(v));
             }
+        }
+        if constexpr (VEC) {
+            float *drow = dz + (size_t)r * H;
+            *reinterpret_cast<float4 *>(drow + 4 * lane) = make_float4(vout[0], vout[1], vout[2], vout[3]);
+            *reinterpret_cast<float4 *>(drow + 128 + 4 * lane) = make_float4(vout[4], vout[5], vout[6], vout[7]);
         }
         if (++slot == RP_SLOTS) { slot = 0; parity ^= 1; }
     }
@@ -719,7 +750,7 @@ __global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc1[0][j] = accb[j];
     float *const dst[1] = {dbias};
-    block_combine_atomic<1>(acc1, dst, H, dyn_sm);
+    block_combine_atomic<1, VEC>(acc1, dst, H, dyn_sm);
 }
 
 // head_relu_ln_bwd_kernel with the row pipeline (one array: the saved activation a).  Dynamic shared memory =
@@ -732,7 +763,7 @@ __global__ void __launch_bounds__(256, 3) relu_lnx_bwd_pipe_kernel(const float *
 // SLOTS = rows in flight per warp.  6 instead of 3 was measured (96 KB instead of 48 KB of loads in flight per SM): no change,
 // 179.0 vs 178.4 ms per update at 8192 envs — the kernel is issue-bound (ncu: 72 % issue utilisation with 3.9 warps per scheduler,
 // 368 warp instructions per row), not latency-bound.
-template <int OUT, int SLOTS = RP_SLOTS>
+template <int OUT, int SLOTS = RP_SLOTS, bool VEC = false>
 __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
@@ -756,7 +787,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
     float g[8], wg[OUT][8], P[OUT][8], accb[8], D[OUT];   // wg = Wh * gamma: dxhat = sum_o dout[o] wg[o]
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = lane + 32 * j;
+        const int c = col_of<VEC>(lane, j);
         g[j] = (c < H) ? gamma[c] : 0.f;
         accb[j] = 0.f;
 #pragma unroll
@@ -798,11 +829,15 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
         const float *sa = ring + (size_t)slot * H;
         float xh[8], dxh[8], av[8];
         float s1 = 0.f, s2 = 0.f;
+        if constexpr (VEC) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(sa + 4 * lane), v1 = *reinterpret_cast<const float4 *>(sa + 128 + 4 * lane);
+            av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w; av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            const bool ok = c < H;
-            av[j] = ok ? sa[c] : 0.f;
+            const int c = col_of<VEC>(lane, j);
+            const bool ok = VEC || c < H;
+            if constexpr (!VEC) av[j] = ok ? sa[c] : 0.f;
             xh[j] = ok ? (av[j] - m) * rs : 0.f;
             float dx = 0.f;
 #pragma unroll
@@ -817,16 +852,24 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
             issue(slot, r + SLOTS * stride);
         }
         const float c1 = warp_sum_f(s1) / (float)H, c2 = warp_sum_f(s2) / (float)H;
+        float vout[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            if (c < H) {
+            const int c = col_of<VEC>(lane, j);
+            vout[j] = 0.f;
+            if (VEC || c < H) {
                 const float da = rs * (dxh[j] - c1 - xh[j] * c2);
                 const float v = act_bwd(da, av[j], act);
-                dz[(size_t)r * H + c] = v;
+                vout[j] = v;
+                if constexpr (!VEC) dz[(size_t)r * H + c] = v;
                 accb[j] += v;
                 amax = fmaxf(amax, fabsf(v));
             }
+        }
+        if constexpr (VEC) {
+            float *drow = dz + (size_t)r * H;
+            *reinterpret_cast<float4 *>(drow + 4 * lane) = make_float4(vout[0], vout[1], vout[2], vout[3]);
+            *reinterpret_cast<float4 *>(drow + 128 + 4 * lane) = make_float4(vout[4], vout[5], vout[6], vout[7]);
         }
         if (++slot == SLOTS) { slot = 0; parity ^= 1; }
     }
@@ -839,7 +882,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
     float acc[3 + OUT][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = lane + 32 * j;
+        const int c = col_of<VEC>(lane, j);
         const float bj = (c < H) ? beta[c] : 0.f;
         float dg = 0.f, db = 0.f;
 #pragma unroll
@@ -856,7 +899,7 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
     dst[0] = dgamma; dst[1] = dbeta; dst[2] = dbias;
 #pragma unroll
     for (int o = 0; o < OUT; ++o) dst[3 + o] = dWh + o * H;
-    block_combine_atomic<3 + OUT>(acc, dst, H, dyn_sm);
+    block_combine_atomic<3 + OUT, VEC>(acc, dst, H, dyn_sm);
     if (lane == 0) {
 #pragma unroll
         for (int o = 0; o < OUT; ++o) atomicAdd(&dbh[o], D[o]);
