@@ -251,6 +251,7 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
             !tc::tc_make_map_2d_f16(&p.tmAlo, a16->lo, K, M, a16->ld, tc::TC_BK16, tc::TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))
             return DCC_ERR_UNSUPPORTED;
     }
+    p.unit_affine = (h->xhat && gamma == h->ones) ? 1 : 0;      // xhat mode, inner block
     if (h16 && bias) {
         p.h_split = 1;
         p.H = reinterpret_cast<float *>(const_cast<void *>(h16->hi));     // non-NULL: "store h"

@@ -390,6 +390,7 @@ struct TcfParams {
     //   a_split: A comes from (tmAhi, tmAlo): [M, K] fp16, box 64 (k) x 128 rows, SWIZZLE_128B.  F16 kernel only.
     //   h_split: H leaves as (tmHhi, tmHlo): [M, 256] fp16, box 32 x 32, SWIZZLE_64B, staged hi | lo in the 4 KB buffer.
     int a_split, h_split;
+    int unit_affine;     // the LayerNorm affine of this block is the identity (xhat mode): h = (a - mean) rstd, gamma / beta not read
     alignas(64) CUtensorMap tmAhi, tmAlo, tmHhi, tmHlo;
 };
 
@@ -826,9 +827,15 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
             // per-column vectors of this warp's 128 columns, one float4 per lane (see lane_bcast4); issued before the
             // scaling pass so their latency is covered
             float4 vbias = make_float4(0.f, 0.f, 0.f, 0.f), vg = vbias, vb = vbias, vw0 = vbias, vw1 = vbias;
+            // The vectors of the statistics pass (bias, folded head weights) are then parked in this warp's own staging buffer
+            // (bytes 512..2047; idle here: the previous tile's boxes have been read by the TMA engine long ago, the exchange
+            // area is bytes 0..511) and every unrolled iteration fetches its four values with ONE broadcast LDS.128 instead of
+            // four shuffles: the shuffle unit delivers one warp instruction per clock per SM, and 8 warps x 384 shuffles per
+            // tile (bias + two head vectors) were ~3 k of the ~14 k cycles of a tile epilogue.
+            const uint32_t vec_u32 = xp_u32 + 512;
             if (p.epi == TCF_EPI_BIAS_RELU_LN) {
                 vbias = __ldg(reinterpret_cast<const float4 *>(p.bias + half * 128) + lane);
-                if (p.H) {
+                if (p.H && !p.unit_affine) {
                     vg = __ldg(reinterpret_cast<const float4 *>(p.gamma + half * 128) + lane);
                     vb = __ldg(reinterpret_cast<const float4 *>(p.beta + half * 128) + lane);
                 }
@@ -836,6 +843,13 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     vw0 = __ldg(reinterpret_cast<const float4 *>(p.head_fold + half * 128) + lane);
                     vw1 = __ldg(reinterpret_cast<const float4 *>(p.head_fold + (p.head_out > 1 ? TC_N : 0) + half * 128) + lane);
                 }
+                if (p.use_tma) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                sts128(vec_u32 + lane * 16, vbias);
+                if (p.head_out > 0) { sts128(vec_u32 + 512 + lane * 16, vw0); sts128(vec_u32 + 1024 + lane * 16, vw1); }
+                __syncwarp();
             }
             if constexpr (F16) {
                 float sc = p.out_scale;         // undo the power-of-two scale of the weight image (exact)
@@ -859,7 +873,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 if (p.act == 0 && hout == 0) {
 #pragma unroll
                     for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 bv = lane_bcast4(vbias, c4);
+                        const float4 bv = lds128(vec_u32 + c4 * 16);
                         acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
                         acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
                         acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
@@ -870,7 +884,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     // (one output: the second dot product repeats the first and is ignored)
 #pragma unroll
                     for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 bv = lane_bcast4(vbias, c4), w0 = lane_bcast4(vw0, c4), w1 = lane_bcast4(vw1, c4);
+                        const float4 bv = lds128(vec_u32 + c4 * 16), w0 = lds128(vec_u32 + 512 + c4 * 16), w1 = lds128(vec_u32 + 1024 + c4 * 16);
                         acc[4 * c4 + 0] = fmaxf(acc[4 * c4 + 0] + bv.x, 0.f);
                         acc[4 * c4 + 1] = fmaxf(acc[4 * c4 + 1] + bv.y, 0.f);
                         acc[4 * c4 + 2] = fmaxf(acc[4 * c4 + 2] + bv.z, 0.f);
@@ -884,7 +898,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 } else {
 #pragma unroll
                     for (int c4 = 0; c4 < 32; ++c4) {
-                        const float4 bv = lane_bcast4(vbias, c4);
+                        const float4 bv = lds128(vec_u32 + c4 * 16);
                         acc[4 * c4 + 0] = tanhf(acc[4 * c4 + 0] + bv.x);
                         acc[4 * c4 + 1] = tanhf(acc[4 * c4 + 1] + bv.y);
                         acc[4 * c4 + 2] = tanhf(acc[4 * c4 + 2] + bv.z);
@@ -894,7 +908,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                     if (hout > 0) {
 #pragma unroll
                         for (int c4 = 0; c4 < 32; ++c4) {
-                            const float4 w0 = lane_bcast4(vw0, c4), w1 = lane_bcast4(vw1, c4);
+                            const float4 w0 = lds128(vec_u32 + 512 + c4 * 16), w1 = lds128(vec_u32 + 1024 + c4 * 16);
                             d0 = fmaf(acc[4 * c4 + 0], w0.x, d0); d0 = fmaf(acc[4 * c4 + 1], w0.y, d0);
                             d0 = fmaf(acc[4 * c4 + 2], w0.z, d0); d0 = fmaf(acc[4 * c4 + 3], w0.w, d0);
                             d1 = fmaf(acc[4 * c4 + 0], w1.x, d1); d1 = fmaf(acc[4 * c4 + 1], w1.y, d1);
@@ -1009,14 +1023,21 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                             const int sw2 = (lane >> 1) & 3;
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const float4 g0 = lane_bcast4(vg, j * 8 + 2 * c), b0 = lane_bcast4(vb, j * 8 + 2 * c);
-                                const float4 g1 = lane_bcast4(vg, j * 8 + 2 * c + 1), b1 = lane_bcast4(vb, j * 8 + 2 * c + 1);
                                 const int e0 = j * 32 + 8 * c;
                                 float4 h0, h1;
-                                h0.x = fmaf((acc[e0 + 0] - mean) * rstd, g0.x, b0.x); h0.y = fmaf((acc[e0 + 1] - mean) * rstd, g0.y, b0.y);
-                                h0.z = fmaf((acc[e0 + 2] - mean) * rstd, g0.z, b0.z); h0.w = fmaf((acc[e0 + 3] - mean) * rstd, g0.w, b0.w);
-                                h1.x = fmaf((acc[e0 + 4] - mean) * rstd, g1.x, b1.x); h1.y = fmaf((acc[e0 + 5] - mean) * rstd, g1.y, b1.y);
-                                h1.z = fmaf((acc[e0 + 6] - mean) * rstd, g1.z, b1.z); h1.w = fmaf((acc[e0 + 7] - mean) * rstd, g1.w, b1.w);
+                                if (p.unit_affine) {      // xhat mode: the un-affined normalisation itself (same values as gamma = 1, beta = 0)
+                                    h0.x = (acc[e0 + 0] - mean) * rstd; h0.y = (acc[e0 + 1] - mean) * rstd;
+                                    h0.z = (acc[e0 + 2] - mean) * rstd; h0.w = (acc[e0 + 3] - mean) * rstd;
+                                    h1.x = (acc[e0 + 4] - mean) * rstd; h1.y = (acc[e0 + 5] - mean) * rstd;
+                                    h1.z = (acc[e0 + 6] - mean) * rstd; h1.w = (acc[e0 + 7] - mean) * rstd;
+                                } else {
+                                    const float4 g0 = lane_bcast4(vg, j * 8 + 2 * c), b0 = lane_bcast4(vb, j * 8 + 2 * c);
+                                    const float4 g1 = lane_bcast4(vg, j * 8 + 2 * c + 1), b1 = lane_bcast4(vb, j * 8 + 2 * c + 1);
+                                    h0.x = fmaf((acc[e0 + 0] - mean) * rstd, g0.x, b0.x); h0.y = fmaf((acc[e0 + 1] - mean) * rstd, g0.y, b0.y);
+                                    h0.z = fmaf((acc[e0 + 2] - mean) * rstd, g0.z, b0.z); h0.w = fmaf((acc[e0 + 3] - mean) * rstd, g0.w, b0.w);
+                                    h1.x = fmaf((acc[e0 + 4] - mean) * rstd, g1.x, b1.x); h1.y = fmaf((acc[e0 + 5] - mean) * rstd, g1.y, b1.y);
+                                    h1.z = fmaf((acc[e0 + 6] - mean) * rstd, g1.z, b1.z); h1.w = fmaf((acc[e0 + 7] - mean) * rstd, g1.w, b1.w);
+                                }
                                 uint4 hi, lo;
                                 split_f16x8(h0, h1, hi, lo);
                                 const uint32_t off = (uint32_t)((c ^ sw2) << 4);

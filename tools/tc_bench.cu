@@ -92,7 +92,27 @@ int main(int argc, char **argv) {
     if (head_out > 0 && epi == 1) { p.head_out = head_out; p.head_fold = hw; p.head_dst = hdst; }
     if (!store_h) p.H = nullptr;
     if (!store_c) p.C = nullptr;
-    printf("head=%d store_h=%d store_c=%d  ", head_out, store_h, store_c);
+    // product configurations of round 2: pre-split A operand fetched by TMA (a_split), pre-split h output (h_split), unit affine (xhat mode)
+    const int a_split = argc > 11 ? atoi(argv[11]) : 0, h_split = argc > 12 ? atoi(argv[12]) : 0, unit = argc > 13 ? atoi(argv[13]) : 0;
+    if (a_split && f16) {
+        const int ld16 = (K + 7) / 8 * 8;
+        void *ahi, *alo;
+        CK(cudaMalloc(&ahi, (size_t)M * ld16 * 2)); CK(cudaMalloc(&alo, (size_t)M * ld16 * 2));
+        CK(cudaMemset(ahi, 0x11, (size_t)M * ld16 * 2)); CK(cudaMemset(alo, 0x01, (size_t)M * ld16 * 2));
+        p.a_split = 1;
+        if (!tc_make_map_2d_f16(&p.tmAhi, ahi, K, M, ld16, TC_BK16, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc_make_map_2d_f16(&p.tmAlo, alo, K, M, ld16, TC_BK16, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("A maps failed\n"); return 1; }
+        p.pf_dist = 0;
+    }
+    if (h_split && p.H && p.use_tma) {
+        void *hhi, *hlo;
+        CK(cudaMalloc(&hhi, (size_t)M * 256 * 2)); CK(cudaMalloc(&hlo, (size_t)M * 256 * 2));
+        p.h_split = 1;
+        if (!tc_make_map_2d_f16(&p.tmHhi, hhi, TC_N, M, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc_make_map_2d_f16(&p.tmHlo, hlo, TC_N, M, 256, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) { printf("H maps failed\n"); return 1; }
+    }
+    p.unit_affine = unit;
+    printf("head=%d store_h=%d store_c=%d a_split=%d h_split=%d unit=%d  ", head_out, store_h, store_c, p.a_split, p.h_split, unit);
     if (p.pf_dist > 0 && !tc_make_prefetch_map(&p.tmA, A, M, K, K, f16 ? 64 : 32)) { printf("prefetch map failed\n"); p.pf_dist = 0; }
     printf("pf=%d  ", p.pf_dist);
     const int tiles = (M + 127) / 128, grid = tiles < 148 ? tiles : 148;
