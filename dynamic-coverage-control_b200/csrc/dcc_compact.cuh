@@ -22,15 +22,6 @@
 
 namespace dcc {
 
-// fp16 hi/lo split of two fp32 values, packed in memory order (same arithmetic as tc::split_f16_pair)
-__device__ __forceinline__ void tc_split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-
 struct CompactDims {
     int N, M, D, OWN;      // OWN = 2N + 2: the [v_i, p_i, p_k - p_i] head of an observation row
     int Ka, Kc;            // feature counts: OWN + 2M + 2, N * OWN + 2M + 2

@@ -93,6 +93,12 @@ struct MappoHandle {
     // fused forward epilogue has to push out (its bound); the backward pass rebuilds the ReLU mask from xhat (relu_lnx_bwd_pipe_kernel)
     // and gets dgamma_k / dbeta_k from G_{k+1} = dz_{k+1}^T xhat_k once per optimiser step (ln0_finalize_kernel).  DCC_TC_XHAT=0 disables.
     bool xhat;
+    // pre-split gradients (xhat mode): dz_k leaves the LayerNorm-backward kernels as fp16 hi/lo, scaled by a power of two derived from
+    // an a-priori bound of |dz_k|, so the weight-gradient and dX GEMMs are fed by TMA alone.  `sc` = device scalars
+    // (float bits): [SC_DOUT] max |dout| of the pass, [SC_RSTD + k] max rstd of block k, [SC_DXH + k] max |d xhat_k|, [SC_BND] bound of
+    // the dz tensor currently alive.  DCC_TC_DZSPLIT=0 disables.
+    bool dzsplit;
+    uint32_t *sc;
     float *wf[2][MAX_BLOCKS], *bf[2][MAX_BLOCKS];   // folded weights / biases of blocks >= 1 [actor, critic]
     float *ones, *zeros;                            // [H]: unit LayerNorm affine handed to the epilogue of inner blocks
     float *wt[2];            // folded fc1 weights [H, ld] (actor, critic)
@@ -103,6 +109,7 @@ struct MappoHandle {
     float *r_dH[2], *r_Y, *r_mean, *r_rstd, *r_mask, *r_dhp[2], *r_dfeat, *r_zero, *r_dummy;
     int64_t launches;
 };
+enum { SC_DOUT = 0, SC_RSTD = 1, SC_DXH = 1 + MAX_BLOCKS, SC_BND = 1 + 2 * MAX_BLOCKS, SC_COUNT = 2 + 2 * MAX_BLOCKS };
 constexpr uint32_t MAPPO_MAGIC = 0xDCCA0002u;
 
 // ValueNorm state as of train_begin (advantages use it), or nullptr without a value normaliser
@@ -198,6 +205,9 @@ static int pipe_set_kernel_attributes() {
     DCC_CUDA_TRY(cudaFuncSetAttribute(relu_ln_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(relu_lnx_bwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute((relu_lnx_bwd_pipe_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<1, RP_SLOTS, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<2, RP_SLOTS, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<1, RP_SLOTS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute((head_relu_ln_bwd_pipe_kernel<2, RP_SLOTS, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     DCC_CUDA_TRY(cudaFuncSetAttribute(head_relu_ln_bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -230,11 +240,13 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
                        cudaStream_t s, const float *bias = nullptr, const float *gamma = nullptr,
                        const float *beta = nullptr, float *h_out = nullptr, float *mean = nullptr, float *rstd = nullptr,
                        bool f16 = false, const uint32_t *a_absmax_bits = nullptr, const float *head_fold = nullptr,
-                       int head_out = 0, float *head_dst = nullptr, const Split16 *a16 = nullptr, const Split16 *h16 = nullptr) {
+                       int head_out = 0, float *head_dst = nullptr, const Split16 *a16 = nullptr, const Split16 *h16 = nullptr,
+                       uint32_t *rstd_max_out = nullptr, uint32_t *c_absmax_out = nullptr) {
     if (M <= 0) return DCC_OK;
     if ((ldc & 3) || (K & 3)) return DCC_ERR_INVALID_ARG;
     if (!a16 && ((lda & 3) || ((uintptr_t)A & 15))) return DCC_ERR_INVALID_ARG;
-    if (a16 && (!f16 || a_absmax_bits)) return DCC_ERR_INVALID_ARG;
+    // a16 with a_absmax_bits: the pre-split operand was stored ALREADY multiplied by the power of two of those bits (pre-split dz)
+    if (a16 && !f16) return DCC_ERR_INVALID_ARG;
     tc::TcfParams p;
     memset(&p, 0, sizeof p);
     const int bk = f16 ? tc::TC_BK16 : tc::TC_BK;    // `img` must come from tc_prep_weights with the same f16 flag
@@ -252,6 +264,8 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
             return DCC_ERR_UNSUPPORTED;
     }
     p.unit_affine = (h->xhat && gamma == h->ones) ? 1 : 0;      // xhat mode, inner block
+    p.rstd_max_out = bias ? rstd_max_out : nullptr;
+    p.c_absmax_out = bias ? nullptr : c_absmax_out;
     if (h16 && bias) {
         p.h_split = 1;
         p.H = reinterpret_cast<float *>(const_cast<void *>(h16->hi));     // non-NULL: "store h"
@@ -299,10 +313,14 @@ static int tc_gemm_fwd(MappoHandle *h, int M, int K, const float *A, int lda, co
 // f16 = the experimental fp16-split variant (X must be a LayerNorm output; one absmax pass over dZ supplies its scale).
 // x16 != nullptr: X is pre-split (X / ldx ignored; forces the fp16-split kernel).  absmax_ready: h->dz_absmax already holds
 // max |dZ| (left by the kernel that wrote dZ), so the separate pass over dZ is skipped.
+// z16 != nullptr (with x16): dZ is pre-split and pre-scaled as well (dZ / ldz ignored); bnd_bits = the device scalar whose power of
+// two it was stored with.
 static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int ldz, const float *X, int ldx, float *G,
-                         int ldg, cudaStream_t s, bool f16 = false, const Split16 *x16 = nullptr, bool absmax_ready = false) {
+                         int ldg, cudaStream_t s, bool f16 = false, const Split16 *x16 = nullptr, bool absmax_ready = false,
+                         const Split16 *z16 = nullptr, const uint32_t *bnd_bits = nullptr) {
     if (R <= 0 || Nout <= 0) return DCC_OK;
-    if ((ldz & 3) || ((uintptr_t)dZ & 15)) return DCC_ERR_INVALID_ARG;
+    if (z16 && (!x16 || !bnd_bits)) return DCC_ERR_INVALID_ARG;
+    if (!z16 && ((ldz & 3) || ((uintptr_t)dZ & 15))) return DCC_ERR_INVALID_ARG;
     if (!x16 && ((ldx & 3) || ((uintptr_t)X & 15))) return DCC_ERR_INVALID_ARG;
     if (x16) f16 = true;
     if (f16 && !h->dz_absmax) { if (x16) return DCC_ERR_UNSUPPORTED; f16 = false; }
@@ -329,7 +347,14 @@ static int tc_gemm_wgrad(MappoHandle *h, int R, int Nout, const float *dZ, int l
             !tc::tc_make_map_2d_f16(&p.tmXlo, x16->lo, Nout, R, x16->ld, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))
             return DCC_ERR_UNSUPPORTED;
     }
-    if (f16) {
+    if (z16) {
+        p.dz_split = 1;
+        if (!tc::tc_make_map_2d_f16(&p.tmZhi, z16->hi, tc::TC_N, R, z16->ld, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc::tc_make_map_2d_f16(&p.tmZlo, z16->lo, tc::TC_N, R, z16->ld, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))
+            return DCC_ERR_UNSUPPORTED;
+        p.dz_absmax_bits = bnd_bits;
+        tc::tc_gemm_wgrad_kernel<true><<<grid, tc::TCF_THREADS, tc::TCF_SMEM_BYTES, s>>>(p);
+    } else if (f16) {
         if (!absmax_ready) {
             DCC_CUDA_TRY(cudaMemsetAsync(h->dz_absmax, 0, sizeof(uint32_t), s));
             tc::tc_absmax_bits_kernel<<<h->sm_count * 8, 256, 0, s>>>(dZ, (long)R, tc::TC_N, ldz, h->dz_absmax);
@@ -408,6 +433,11 @@ static inline Split16 hh_split(const MappoHandle *h, int k) {
 // fetch and launch latency of a 2-wave grid).  The feature matrix `fc`, `vnew` and `dv` are sized to match.
 static inline size_t critic_cap_rows(const MappoHandle *h) { return (size_t)h->chunk_rows * h->cfg.n_agents; }
 
+// a gradient buffer (dA / dB, fp32-sized) holding a PRE-SPLIT dz: hi halves first, lo halves behind them (row pitch H halves)
+static inline Split16 dz_split16(const MappoHandle *h, const float *buf) {
+    const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cfg.hidden;
+    return Split16{buf, reinterpret_cast<const __half *>(buf) + cap, h->cfg.hidden};
+}
 static inline Split16 feat_split(const MappoHandle *h, int net) {
     if (net == 0) {
         const size_t cap = (size_t)h->chunk_rows * h->cfg.n_agents * h->cd.lda;
@@ -466,6 +496,8 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
     const int H = L.H;
     const int wpb = 8;
     const float *w1g = feat ? h->wt[net] : (net ? h->w1g_c : h->w1g_a), *b1g = net ? h->b1g_c : h->b1g_a;
+    const bool dzs = h->dzsplit && save;      // training pass: the forward epilogues leave max rstd per block for the dz bounds
+    if (dzs) DCC_CUDA_TRY(cudaMemsetAsync(h->sc, 0, SC_COUNT * sizeof(uint32_t), s));
     // input LayerNorm (without affine): register-resident single-pass variant when the rows are 16-byte aligned
     if (feat) {
         // features carry the normalisation already
@@ -500,7 +532,7 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
                              save ? h->rstd[k] : nullptr,
                              (feat && k == 0) ? h->f16_fwd : fwd_f16(h, L, k),   // compact features are bounded: fp16-split eligible
                              nullptr, fuse ? h->head_fold[net] : nullptr, fuse ? L.out : 0, fuse ? head_dst : nullptr,
-                             in_split ? &a16 : nullptr, out_split ? &h16 : nullptr);
+                             in_split ? &a16 : nullptr, out_split ? &h16 : nullptr, dzs ? h->sc + SC_RSTD + k : nullptr);
             if (rc) return rc;
             continue;
         }
@@ -519,6 +551,63 @@ static int trunk_forward(MappoHandle *h, const NetLayout &L, const float *P, int
 // weight slot receives G1 = dz1^T xhat (turned into dW1 / dgamma0 / dbeta0 by ln0_finalize once per epoch).
 // `dout` = gradient w.r.t. the head output ([rows, out]); on return all parameter gradients of the net have been
 // accumulated into G (the fc1 slot holds G1, see ln0_finalize).
+// trunk backward with PRE-SPLIT gradients (MappoHandle::dzsplit; xhat mode, head path): every dz_k is written by its LayerNorm-backward
+// kernel as fp16 hi/lo into dA, scaled by the power of two of an a-priori bound (published in sc[SC_BND]); the weight-gradient and dX
+// GEMMs fetch it with TMA (no producer warps), the dX GEMM leaves max |d xhat| for the next bound.  dB holds the fp32 dX outputs.
+static int trunk_backward_dzs(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *dout, int rows,
+                              cudaStream_t s, const float *feat, int ldf) {
+    const int H = L.H, wpb = 8, last = L.nblk - 1;
+    const size_t lo_off = (size_t)h->chunk_rows * h->cfg.n_agents * H;
+    int rc;
+    const size_t nd = (size_t)rows * L.out;
+    absmax_flat_kernel<<<(unsigned)std::min<size_t>((nd + 255) / 256, (size_t)h->sm_count * 4), 256, 0, s>>>(dout, nd, h->sc + SC_DOUT);
+    const int gr_head = grid_for_reduce(h, rows, wpb, 2);
+    const size_t ring1 = (size_t)wpb * RP_SLOTS * H;
+    const size_t sm2 = std::max(ring1, (size_t)wpb * 5 * 256) * sizeof(float), sm1 = std::max(ring1, (size_t)wpb * 4 * 256) * sizeof(float);
+    if (L.out == 2)
+        head_relu_ln_bwd_pipe_kernel<2, RP_SLOTS, true, true><<<gr_head, wpb * 32, sm2, s>>>(
+            dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last], G + L.lb[last],
+            G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), nullptr, h->sc + SC_DOUT, h->sc + SC_RSTD + last, h->sc + SC_BND, lo_off);
+    else
+        head_relu_ln_bwd_pipe_kernel<1, RP_SLOTS, true, true><<<gr_head, wpb * 32, sm1, s>>>(
+            dout, P + L.Wh, h->a[last], h->mean[last], h->rstd[last], P + L.lg[last], P + L.lb[last], h->dA, G + L.lg[last], G + L.lb[last],
+            G + L.b[last], G + L.Wh, G + L.bh, rows, H, act_of(h), nullptr, h->sc + SC_DOUT, h->sc + SC_RSTD + last, h->sc + SC_BND, lo_off);
+    h->launches += 2;
+    DCC_CUDA_TRY(cudaGetLastError());
+    const Split16 z16 = dz_split16(h, h->dA);
+    float *dx = h->dB;
+    static const int lnx_ctas = getenv("DCC_LNX_CTAS") ? atoi(getenv("DCC_LNX_CTAS")) : 4;
+    const int gx = grid_for_reduce(h, rows, wpb, lnx_ctas);
+    const size_t smx = std::max((size_t)wpb * RP_SLOTS * 2 * H, (size_t)wpb * 256) * sizeof(float);
+    for (int k = last; k >= 1; --k) {
+        const Split16 x16 = hh_split(h, k - 1);
+        if ((rc = tc_gemm_wgrad(h, rows, H, nullptr, H, nullptr, H, G + L.W[k], H, s, true, &x16, true, &z16, h->sc + SC_BND))) return rc;
+        // d xhat_{k-1} = dz_k (W_k * gamma_{k-1}); its maximum goes to sc[SC_DXH + k - 1]
+        if ((rc = tc_gemm_fwd(h, rows, H, nullptr, H, h->img_wt[net][k], dx, H, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true,
+                              h->sc + SC_BND, nullptr, 0, nullptr, &z16, nullptr, nullptr, h->sc + SC_DXH + (k - 1))))
+            return rc;
+        const bool split_out = (k - 1 >= 1) || feat != nullptr;     // block 0 of the materialised path keeps an fp32 dz (its X operand is fp32)
+        if (split_out)
+            relu_lnx_bwd_pipe_kernel<true, true><<<gx, wpb * 32, smx, s>>>(
+                dx, static_cast<const __half *>(x16.hi), static_cast<const __half *>(x16.lo), h->mean[k - 1], h->rstd[k - 1], h->dA,
+                G + L.b[k - 1], rows, H, nullptr, h->sc + SC_DXH + (k - 1), h->sc + SC_RSTD + (k - 1), h->sc + SC_BND, lo_off);
+        else
+            relu_lnx_bwd_pipe_kernel<true, false><<<gx, wpb * 32, smx, s>>>(
+                dx, static_cast<const __half *>(x16.hi), static_cast<const __half *>(x16.lo), h->mean[k - 1], h->rstd[k - 1], dx,
+                G + L.b[k - 1], rows, H, nullptr);
+        h->launches++;
+        DCC_CUDA_TRY(cudaGetLastError());
+    }
+    if (feat) {     // compact path: Gt += dz_0^T f, both operands pre-split
+        const Split16 x16 = feat_split(h, net);
+        rc = tc_gemm_wgrad(h, rows, ldf, nullptr, H, nullptr, ldf, h->gt[net], ldf, s, true, &x16, true, &z16, h->sc + SC_BND);
+    } else
+        rc = tc_gemm_wgrad(h, rows, L.in, dx, H, h->x0, L.inp, G + L.W[0], L.in, s, wgrad_f16(h, L, 0));   // G1 += dz_0^T xhat (fp32 dz_0 in dx)
+    if (rc) return rc;
+    DCC_CUDA_TRY(cudaGetLastError());
+    return DCC_OK;
+}
+
 // dh_last != nullptr (recurrent policies): the gradient w.r.t. the trunk OUTPUT [rows, H] is given (it comes out of the GRU's
 // backward pass, rnn_backward) and the head's gradients have been accumulated already; `dout` is ignored.
 static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *dout, int rows,
@@ -532,6 +621,7 @@ static int trunk_backward(MappoHandle *h, const NetLayout &L, const float *P, in
     // (f16_dx: the kernel that writes a dz also leaves max |dz| in h->dz_absmax for the fp16-split dX GEMM that reads it)
     const bool dx16 = h->f16_dx && last >= 1;
     const bool sp = h->split16 && h->backend == 2;      // weight-gradient X operands (h_{k-1}, compact features) are pre-split
+    if (h->dzsplit && !dh_last && sp && h->xhat && dx16 && H == tc::TC_N) return trunk_backward_dzs(h, L, P, net, G, dout, rows, s, feat, ldf);
     uint32_t *amax = (dx16 || sp) ? h->dz_absmax : nullptr;
     if (amax) DCC_CUDA_TRY(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
     if (dh_last) {
@@ -830,6 +920,7 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
                  !(getenv("DCC_TC_TMA") && atoi(getenv("DCC_TC_TMA")) == 0) && tc::tc_tensor_map_encoder() != nullptr;
     // xhat mode needs the pre-split operand path, the row-pipeline kernels and ReLU (the mask is rebuilt from xhat)
     h->xhat = h->split16 && h->ln_pipe && cfg->use_relu != 0 && !(getenv("DCC_TC_XHAT") && atoi(getenv("DCC_TC_XHAT")) == 0);
+    h->dzsplit = h->xhat && h->f16_dx && !(getenv("DCC_TC_DZSPLIT") && atoi(getenv("DCC_TC_DZSPLIT")) == 0);
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
@@ -878,6 +969,10 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     if (ce == cudaSuccess) ce = cudaMalloc(&h->dsums, 8 * sizeof(double));
     if (ce == cudaSuccess && h->backend == 2) ce = cudaMalloc(&h->dz_absmax, sizeof(uint32_t));
     for (int n = 0; n < 2 && h->backend == 2; ++n) alloc(&h->head_fold[n], 2 * 256 + 8);
+    if (h->dzsplit && ce == cudaSuccess) {
+        ce = cudaMalloc(&h->sc, SC_COUNT * sizeof(uint32_t));
+        if (ce == cudaSuccess) ce = cudaMemset(h->sc, 0, SC_COUNT * sizeof(uint32_t));
+    }
     if (h->xhat) {
         for (int n = 0; n < 2; ++n)
             for (int k = 1; k < h->la.nblk; ++k) { alloc(&h->wf[n][k], (size_t)H * H); alloc(&h->bf[n][k], H); }
@@ -922,7 +1017,7 @@ int dcc_mappo_destroy(void *handle) {
     }
     for (int n = 0; n < 2; ++n)
         for (int k = 0; k < MAX_BLOCKS; ++k) { cudaFree(h->wf[n][k]); cudaFree(h->bf[n][k]); }
-    cudaFree(h->ones); cudaFree(h->zeros);
+    cudaFree(h->ones); cudaFree(h->zeros); cudaFree(h->sc);
     for (int l = 0; l < MAX_RNN; ++l) {
         float *rb[] = {h->r_Hp[l], h->r_GI[l], h->r_GH[l], h->r_gates[l], h->r_Hout[l]};
         for (float *b : rb) cudaFree(b);

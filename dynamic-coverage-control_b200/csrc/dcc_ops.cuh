@@ -123,6 +123,34 @@ __device__ __forceinline__ float act_bwd(float da, float a, int act) {
     return act == ACT_RELU ? (a > 0.f ? da : 0.f) : (act == ACT_TANH ? da * (1.f - a * a) : da);
 }
 
+// fp16 hi/lo split of two fp32 values, packed in memory order (same arithmetic as tc::split_f16_pair)
+__device__ __forceinline__ void tc_split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Power of two that brings a tensor whose |values| are bounded by the float with these bits into [2^13, 2^14) — the scale a
+// PRE-SPLIT gradient tensor is stored with.  Must stay identical to tc::f16_scale_from_absmax (the consumers undo it from the same bits).
+__device__ __forceinline__ float split_scale_up(uint32_t bits) {
+    const uint32_t e = (bits >> 23) & 0xffu;
+    if (e == 0) return 1.f;
+    uint32_t be = 267u - e;
+    if (be > 254u) be = 254u;
+    return __uint_as_float(be << 23);
+}
+
+// max |x| over a flat array as float bits (atomicMax on the bits of non-negative floats orders them); *out zeroed first
+__global__ void absmax_flat_kernel(const float *__restrict__ x, size_t n, uint32_t *__restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 // ---- row-wise kernels: one warp per row ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -639,12 +667,29 @@ __global__ void __launch_bounds__(256, 3) relu_ln_bwd_pipe_kernel(const float *d
 // per optimiser step from the next block's G = dz^T xhat (ln0_finalize_kernel).  Reads 2 KB per row (dxh fp32 + hi + lo), the same
 // bytes as relu_ln_bwd_pipe_kernel; one column accumulator instead of three.
 // Dynamic shared memory = max(8 * RP_SLOTS * 2 * H, 8 * 1 * 256) floats.  H % 8 == 0.
-template <bool VEC>
+// SPLIT (VEC only): dz leaves PRE-SPLIT — fp16 hi at dz16, lo at dz16 + lo_off, row pitch H halves — multiplied by the power of two
+// that follows from an upper BOUND of |dz| known before a single row is processed: da / rstd = (I - 11^T/H - xhat xhat^T/H) dxh is the
+// image of dxh under a matrix with eigenvalues in [0, 1] (|xhat|^2 / H = var / (var + eps) <= 1), so every |da_c| <= rstd |dxh|_2 <=
+// max rstd * sqrt(H) * max |dxh| (x 1.25 for rounding), and |dz| <= |da|; both maxima were
+// left behind by the kernels that produced rstd / dxh (sc_rstd, sc_dxh: float bits).  Block 0 publishes the bound's bits in
+// *sc_bnd for the GEMMs that read dz (they undo the same power of two).  A loose bound costs nothing: see DESIGN.md §5.7.
+template <bool VEC, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 4) relu_lnx_bwd_pipe_kernel(const float *dxh_in, const __half *__restrict__ xh_hi,
                                                                    const __half *__restrict__ xh_lo, const float *__restrict__ mean,
                                                                    const float *__restrict__ rstd, float *dz,
                                                                    float *__restrict__ dbias, int rows, int H,
-                                                                   uint32_t *__restrict__ absmax_out) {
+                                                                   uint32_t *__restrict__ absmax_out,
+                                                                   const uint32_t *__restrict__ sc_dxh = nullptr,
+                                                                   const uint32_t *__restrict__ sc_rstd = nullptr,
+                                                                   uint32_t *__restrict__ sc_bnd = nullptr, size_t lo_off = 0) {
+    static_assert(!SPLIT || VEC, "the pre-split output uses the 16-byte column map");
+    float up = 1.f;
+    if constexpr (SPLIT) {
+        const float bound = __uint_as_float(__ldg(sc_dxh)) * __uint_as_float(__ldg(sc_rstd)) * sqrtf((float)H) * 1.25f;
+        const uint32_t bits = __float_as_uint(bound);
+        up = split_scale_up(bits);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *sc_bnd = bits;
+    }
     extern __shared__ __align__(128) float dyn_sm[];
     __shared__ __align__(8) uint64_t bars[8 * RP_SLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -733,7 +778,17 @@ __global__ void __launch_bounds__(256, 4) relu_lnx_bwd_pipe_kernel(const float *
                 amax = fmaxf(amax, fabsf(v));
             }
         }
-        if constexpr (VEC) {
+        if constexpr (SPLIT) {
+            __half *hrow = reinterpret_cast<__half *>(dz) + (size_t)r * H;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint2 hi, lo;
+                tc_split_pair(vout[4 * q] * up, vout[4 * q + 1] * up, hi.x, lo.x);
+                tc_split_pair(vout[4 * q + 2] * up, vout[4 * q + 3] * up, hi.y, lo.y);
+                *reinterpret_cast<uint2 *>(hrow + 128 * q + 4 * lane) = hi;
+                *reinterpret_cast<uint2 *>(hrow + lo_off + 128 * q + 4 * lane) = lo;
+            }
+        } else if constexpr (VEC) {
             float *drow = dz + (size_t)r * H;
             *reinterpret_cast<float4 *>(drow + 4 * lane) = make_float4(vout[0], vout[1], vout[2], vout[3]);
             *reinterpret_cast<float4 *>(drow + 128 + 4 * lane) = make_float4(vout[4], vout[5], vout[6], vout[7]);
@@ -763,13 +818,19 @@ __global__ void __launch_bounds__(256, 4) relu_lnx_bwd_pipe_kernel(const float *
 // SLOTS = rows in flight per warp.  6 instead of 3 was measured (96 KB instead of 48 KB of loads in flight per SM): no change,
 // 179.0 vs 178.4 ms per update at 8192 envs — the kernel is issue-bound (ncu: 72 % issue utilisation with 3.9 warps per scheduler,
 // 368 warp instructions per row), not latency-bound.
-template <int OUT, int SLOTS = RP_SLOTS, bool VEC = false>
+// SPLIT (VEC only): dz leaves pre-split and pre-scaled like relu_lnx_bwd_pipe_kernel<true, true>; here the gradient w.r.t. xhat is
+// dxh[c] = sum_o dout[o] Wh[o,c] gamma[c], so |dxh| <= max |dout| * S with S = sum_o max_c |Wh[o,c] gamma[c]| (formed from the
+// registers every warp holds anyway), and |dz| <= max rstd * sqrt(H) * max |dout| * S (x 1.25).
+template <int OUT, int SLOTS = RP_SLOTS, bool VEC = false, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const float *__restrict__ dout, const float *__restrict__ Wh,
                                         const float *__restrict__ a, const float *__restrict__ mean,
                                         const float *__restrict__ rstd, const float *__restrict__ gamma,
                                         const float *__restrict__ beta, float *__restrict__ dz, float *__restrict__ dgamma,
                                         float *__restrict__ dbeta, float *__restrict__ dbias, float *__restrict__ dWh,
-                                        float *__restrict__ dbh, int rows, int H, int act, uint32_t *__restrict__ absmax_out) {
+                                        float *__restrict__ dbh, int rows, int H, int act, uint32_t *__restrict__ absmax_out,
+                                        const uint32_t *__restrict__ sc_dout = nullptr, const uint32_t *__restrict__ sc_rstd = nullptr,
+                                        uint32_t *__restrict__ sc_bnd = nullptr, size_t lo_off = 0) {
+    static_assert(!SPLIT || VEC, "the pre-split output uses the 16-byte column map");
     extern __shared__ __align__(128) float dyn_sm[];
     __shared__ __align__(8) uint64_t bars[8 * SLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -795,6 +856,23 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) D[o] = 0.f;
+    float up = 1.f;
+    if constexpr (SPLIT) {
+        float S = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+            float m = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(wg[o][j]));
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, sh));
+            S += m;
+        }
+        const float bound = __uint_as_float(__ldg(sc_dout)) * S * __uint_as_float(__ldg(sc_rstd)) * sqrtf((float)H) * 1.25f;
+        const uint32_t bits = __float_as_uint(bound);
+        up = split_scale_up(bits);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *sc_bnd = bits;
+    }
     const int r0 = blockIdx.x * wpb + warp;
     const int n_my = r0 < rows ? (rows - r0 + stride - 1) / stride : 0;
     auto issue = [&](int slot, int row) {      // lane 0
@@ -866,7 +944,17 @@ __global__ void __launch_bounds__(256, 2) head_relu_ln_bwd_pipe_kernel(const flo
                 amax = fmaxf(amax, fabsf(v));
             }
         }
-        if constexpr (VEC) {
+        if constexpr (SPLIT) {
+            __half *hrow = reinterpret_cast<__half *>(dz) + (size_t)r * H;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint2 hi, lo;
+                tc_split_pair(vout[4 * q] * up, vout[4 * q + 1] * up, hi.x, lo.x);
+                tc_split_pair(vout[4 * q + 2] * up, vout[4 * q + 3] * up, hi.y, lo.y);
+                *reinterpret_cast<uint2 *>(hrow + 128 * q + 4 * lane) = hi;
+                *reinterpret_cast<uint2 *>(hrow + lo_off + 128 * q + 4 * lane) = lo;
+            }
+        } else if constexpr (VEC) {
             float *drow = dz + (size_t)r * H;
             *reinterpret_cast<float4 *>(drow + 4 * lane) = make_float4(vout[0], vout[1], vout[2], vout[3]);
             *reinterpret_cast<float4 *>(drow + 128 + 4 * lane) = make_float4(vout[4], vout[5], vout[6], vout[7]);

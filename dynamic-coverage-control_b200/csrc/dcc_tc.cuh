@@ -391,6 +391,10 @@ struct TcfParams {
     //   h_split: H leaves as (tmHhi, tmHlo): [M, 256] fp16, box 32 x 32, SWIZZLE_64B, staged hi | lo in the 4 KB buffer.
     int a_split, h_split;
     int unit_affine;     // the LayerNorm affine of this block is the identity (xhat mode): h = (a - mean) rstd, gamma / beta not read
+    // optional reductions for the pre-split gradient path (float bits, atomicMax; zeroed by the caller): the largest rstd of the
+    // rows this launch normalises (EPI_BIAS_RELU_LN) / the largest |C| it stores (EPI_STORE, after the scale) — the two factors of
+    // the a-priori bound of |dz| that lets the LayerNorm-backward kernel write dz pre-scaled (relu_lnx_bwd_pipe_kernel<true, true>)
+    uint32_t *rstd_max_out, *c_absmax_out;
     alignas(64) CUtensorMap tmAhi, tmAlo, tmHhi, tmHlo;
 };
 
@@ -942,6 +946,12 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                 named_bar_sync(1 + q, 64);      // the partner has read my values: the staging buffer may be reused for the stores
                 TC_PROF_NOW(t5);
                 TC_PROF_ADD(e_lnbar, t4, t5);
+                if (p.rstd_max_out && half == 0) {
+                    float rm = (row0 + lane < p.M) ? rstd : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+                    if (lane == 0 && rm > 0.f) atomicMax(p.rstd_max_out, __float_as_uint(rm));
+                }
                 if (half == 0 && row0 + lane < p.M) {
                     if (p.mean) p.mean[row0 + lane] = mean;
                     if (p.rstd) p.rstd[row0 + lane] = rstd;
@@ -952,6 +962,14 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_fwd_kernel(const __gri
                         if (hout > 1) dst[1] = fmaf(rstd, p1 - mean * __ldg(tailv + 1), __ldg(tailv + hout + 1));
                     }
                 }
+            }
+            if (p.c_absmax_out && p.epi == TCF_EPI_STORE) {      // rows past M hold exact zeros (zero-filled operand rows)
+                float cm = 0.f;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) cm = fmaxf(cm, fabsf(acc[i]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                if (lane == 0 && cm > 0.f) atomicMax(p.c_absmax_out, __float_as_uint(cm));
             }
             TC_PROF_NOW(t3);
             TC_PROF_ADD(e_stats, t0, t3);
@@ -1162,7 +1180,11 @@ struct TcwParams {
     // x 64 rows, SWIZZLE_128B, which IS the MN-major 16-bit operand layout (64-feature groups of [64 k rows][128 B], 16-byte
     // chunks XOR (k & 7)) — fetched by TMA tensor loads; the producer warps then convert only dZ (2 of the 6 units of a stage).
     int x_split;
-    alignas(64) CUtensorMap tmXhi, tmXlo;
+    // dz_split (with x_split): dZ is pre-split as well — two fp16 matrices [R, 256] already multiplied by the power of two that
+    // f16_scale_from_absmax derives from *dz_absmax_bits (an upper BOUND of |dZ| known before dZ is written, see dcc_mappo.cu) —
+    // and arrives as four 64 x 64 boxes per stage (tmZhi, tmZlo); no producer warp touches the data: one thread feeds the pipeline.
+    int dz_split;
+    alignas(64) CUtensorMap tmXhi, tmXlo, tmZhi, tmZlo;
 };
 
 //
@@ -1193,7 +1215,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(const __g
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCF_STAGES; ++s) {
-            mbar_init(&full[s], (F16 && p.x_split) ? 5 : 4);   // 4 producer warps (+ the expect_tx arrival of the X tiles)
+            // 4 producer warps (+ the expect_tx arrival of the X tiles); with dZ pre-split too, only the expect_tx arrival
+            mbar_init(&full[s], (F16 && p.x_split) ? (p.dz_split ? 1 : 5) : 4);
             mbar_init(&empty[s], 1);      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -1209,7 +1232,36 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) tc_gemm_wgrad_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
 
     // smem stage layout: A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB; every 32-feature group = 32 rows x 128 B
-    if (warp < 4) {
+    if (warp < 4 && F16 && p.x_split && p.dz_split) {
+        // both operands pre-split in global memory: one thread issues the stage's TMA loads, nothing is converted here
+        setmaxnreg_dec<96>();
+        if (threadIdx.x == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const int ot = w % out_tiles, ks = w / out_tiles;
+                const int mh = ot & 1, n0 = (ot >> 1) * p.tile_n;
+                const int nv = min(p.tile_n, (p.Nout - n0 + 15) & ~15);
+                const int ngroups = (nv + 63) >> 6;
+                const int r_beg = ks * p.rows_per_split, r_end = min(p.R, r_beg + p.rows_per_split);
+                for (int r0 = r_beg; r0 < r_end; r0 += BKW, ++it) {
+                    const int s = it & 1;
+                    const uint32_t ph = (it >> 1) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t st_u32 = smem_u32(smem + s * TCF_STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(4 + 2 * ngroups) * 8192u);
+                    for (int g = 0; g < 2; ++g) {      // dZ features [mh * 128 + 64 g, +64), rows [r0, r0 + 64); rows past R are zero-filled
+                        tma_load_2d(st_u32 + g * 8192, &p.tmZhi, mh * 128 + g * 64, r0, &full[s]);
+                        tma_load_2d(st_u32 + TC_A_TILE_FLOATS * 4 + g * 8192, &p.tmZlo, mh * 128 + g * 64, r0, &full[s]);
+                    }
+                    const uint32_t sb = st_u32 + 2 * TC_A_TILE_FLOATS * 4;
+                    for (int g = 0; g < ngroups; ++g) {
+                        tma_load_2d(sb + g * 8192, &p.tmXhi, n0 + g * 64, r0, &full[s]);
+                        tma_load_2d(sb + TC_B_TILE_FLOATS * 4 + g * 8192, &p.tmXlo, n0 + g * 64, r0, &full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp < 4) {
         setmaxnreg_dec<96>();
         const int t = threadIdx.x;
         // Work is cut into load units of 8 x 16 bytes per thread: per 32-row stage one unit of dZ (A) and two units of X

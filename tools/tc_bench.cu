@@ -11,7 +11,7 @@ using namespace dcc::tc;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 // weight-gradient kernel: tc_bench.bin wgrad R Nout [f16]   (G[256, Nout] += dZ[R,256]^T X[R, Nout])
-static int bench_wgrad(int R, int Nout, bool f16) {
+static int bench_wgrad(int R, int Nout, bool f16, int split = 0) {
     const int ldx = (Nout + 31) / 32 * 32;
     float *dZ, *X, *G;
     CK(cudaMalloc(&dZ, (size_t)R * 256 * 4)); CK(cudaMalloc(&X, (size_t)R * ldx * 4)); CK(cudaMalloc(&G, (size_t)256 * Nout * 4));
@@ -34,6 +34,22 @@ static int bench_wgrad(int R, int Nout, bool f16) {
     p.rows_per_split = ((R + ks - 1) / ks + bkw - 1) / bkw * bkw;
     p.dz_absmax_bits = absmax;
     p.ksplits = (R + p.rows_per_split - 1) / p.rows_per_split;
+    if (split && f16) {     // split 1: X pre-split (TMA); split 2: dZ pre-split too
+        const int ld16 = (Nout + 7) / 8 * 8;
+        void *xhi, *xlo, *zhi, *zlo;
+        CK(cudaMalloc(&xhi, (size_t)R * ld16 * 2)); CK(cudaMalloc(&xlo, (size_t)R * ld16 * 2));
+        CK(cudaMemset(xhi, 0x11, (size_t)R * ld16 * 2)); CK(cudaMemset(xlo, 0x01, (size_t)R * ld16 * 2));
+        p.x_split = 1;
+        if (!tc_make_map_2d_f16(&p.tmXhi, xhi, Nout, R, ld16, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !tc_make_map_2d_f16(&p.tmXlo, xlo, Nout, R, ld16, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("X maps failed\n"); return 1; }
+        if (split > 1) {
+            CK(cudaMalloc(&zhi, (size_t)R * 256 * 2)); CK(cudaMalloc(&zlo, (size_t)R * 256 * 2));
+            CK(cudaMemset(zhi, 0x11, (size_t)R * 256 * 2)); CK(cudaMemset(zlo, 0x01, (size_t)R * 256 * 2));
+            p.dz_split = 1;
+            if (!tc_make_map_2d_f16(&p.tmZhi, zhi, 256, R, 256, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+                !tc_make_map_2d_f16(&p.tmZlo, zlo, 256, R, 256, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("Z maps failed\n"); return 1; }
+        }
+    }
     const int work = out_tiles * p.ksplits, grid = work < sms ? work : sms;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) kern<<<grid, TCF_THREADS, TCF_SMEM_BYTES>>>(p);
@@ -57,7 +73,7 @@ static int bench_wgrad(int R, int Nout, bool f16) {
 }
 
 int main(int argc, char **argv) {
-    if (argc > 3 && !strcmp(argv[1], "wgrad")) return bench_wgrad(atoi(argv[2]), atoi(argv[3]), argc > 4 && atoi(argv[4]));
+    if (argc > 3 && !strcmp(argv[1], "wgrad")) return bench_wgrad(atoi(argv[2]), atoi(argv[3]), argc > 4 && atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0);
     const int M = argc > 1 ? atoi(argv[1]) : 198408, K = argc > 2 ? atoi(argv[2]) : 352, epi = argc > 3 ? atoi(argv[3]) : 1;
     const bool f16 = argc > 6 && atoi(argv[6]);     // fp16 hi/lo split kernel (64 reduction elements per stage)
     const int KT = f16 ? (K + 63) / 64 : (K + 31) / 32;
