@@ -22,6 +22,15 @@
 
 namespace dcc {
 
+// rstd = 1 / sqrt(v) for the LayerNorm statistics: rsqrtf + one Newton step (<= 1 ulp of the float result) instead of a float64
+// sqrt and division (two ~170-instruction sequences per env step in an issue-bound kernel)
+__device__ __forceinline__ float rstd_from_var(double var_plus_eps) {
+    const float v = (float)var_plus_eps;
+    float r = rsqrtf(v);
+    r = r * fmaf(-0.5f * v, r * r, 1.5f);
+    return r;
+}
+
 struct CompactDims {
     int N, M, D, OWN;      // OWN = 2N + 2: the [v_i, p_i, p_k - p_i] head of an observation row
     int Ka, Kc;            // feature counts: OWN + 2M + 2, N * OWN + 2M + 2
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                 const double mu = s / (double)D;
                 const double var = fmax(q / (double)D - mu * mu, 0.0);
                 mean = (float)mu;
-                rstd = (float)(1.0 / sqrt(var + (double)LN_EPS));
+                rstd = rstd_from_var(var + (double)LN_EPS);
             }
             s_stat[lane] = mean; s_stat[N + lane] = rstd;
         }
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(256) compact_features_kernel(const double *__r
                 const double mu = S / ((double)N * D);
                 const double var = fmax(Q / ((double)N * D) - mu * mu, 0.0);
                 mean_c = (float)mu;
-                rstd_c = (float)(1.0 / sqrt(var + (double)LN_EPS));
+                rstd_c = rstd_from_var(var + (double)LN_EPS);
             }
             const float nm = -mean_c * rstd_c;
             for (int c0 = lane << 3; c0 < cd.ldc; c0 += 256) {

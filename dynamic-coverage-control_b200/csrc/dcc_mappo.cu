@@ -98,6 +98,7 @@ struct MappoHandle {
     // (float bits): [SC_DOUT] max |dout| of the pass, [SC_RSTD + k] max rstd of block k, [SC_DXH + k] max |d xhat_k|, [SC_BND] bound of
     // the dz tensor currently alive.  DCC_TC_DZSPLIT=0 disables.
     bool dzsplit;
+    bool dout_ready;     // the loss kernel of this pass already left max |dout| in sc[SC_DOUT] (else trunk_backward_dzs reduces it)
     uint32_t *sc;
     float *wf[2][MAX_BLOCKS], *bf[2][MAX_BLOCKS];   // folded weights / biases of blocks >= 1 [actor, critic]
     float *ones, *zeros;                            // [H]: unit LayerNorm affine handed to the epilogue of inner blocks
@@ -560,7 +561,9 @@ static int trunk_backward_dzs(MappoHandle *h, const NetLayout &L, const float *P
     const size_t lo_off = (size_t)h->chunk_rows * h->cfg.n_agents * H;
     int rc;
     const size_t nd = (size_t)rows * L.out;
-    absmax_flat_kernel<<<(unsigned)std::min<size_t>((nd + 255) / 256, (size_t)h->sm_count * 4), 256, 0, s>>>(dout, nd, h->sc + SC_DOUT);
+    if (!h->dout_ready)
+        absmax_flat_kernel<<<(unsigned)std::min<size_t>((nd + 255) / 256, (size_t)h->sm_count * 4), 256, 0, s>>>(dout, nd, h->sc + SC_DOUT);
+    h->dout_ready = false;
     const int gr_head = grid_for_reduce(h, rows, wpb, 2);
     const size_t ring1 = (size_t)wpb * RP_SLOTS * H;
     const size_t sm2 = std::max(ring1, (size_t)wpb * 5 * 256) * sizeof(float), sm1 = std::max(ring1, (size_t)wpb * 4 * 256) * sizeof(float);
@@ -1305,17 +1308,20 @@ static int epoch_grads_impl(MappoHandle *h, const float *actor, const float *cri
             // actor and critic share one activation scratch, so the nets are processed one after the other:
             // 1) actor: forward (activations saved) -> Gaussian head -> policy loss -> backward
             if ((rc = trunk_forward(h, LA, actor, 0, x, nr * N, true, s, nullptr, 1, fa, h->cd.lda, fh ? h->mu : nullptr))) return rc;
-            if (fh)
-                gauss_finish_kernel<<<(nr * N + 255) / 256, 256, 0, s>>>(h->mu, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
-                                                                        h->mu, h->logp, nr * N, 1, 0, 0, 0, 0);
-            else
+            // fused head: mu is there already; the loss kernel forms the new log-prob itself (and, for the pre-split gradients, leaves
+            // max |dmu| behind) — no separate log-prob pass
+            if (!fh) {
                 actor_head_kernel<<<grid_for_rows(h, nr * N, 8), 256, 0, s>>>(
                     h->hh[h->la.nblk - 1], actor + LA.Wh, actor + LA.bh, actor + LA.logstd, const_cast<float *>(d_actions) + (size_t)r0 * N * 2,
                     h->mu, h->logp, nr * N, H, 1, 0, 0, 0, 0);
-            h->launches++;
+                h->launches++;
+            }
+            const bool dmax = h->dzsplit && h->sc;
             ppo_policy_loss_kernel<<<(nr + 127) / 128, 128, 0, s>>>(
-                h->mu, h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
-                d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P);
+                h->mu, fh ? nullptr : h->logp, d_actions + (size_t)r0 * N * 2, actor + LA.logstd, d_logp_old + (size_t)r0 * N, d_returns + r0,
+                d_values + r0, vn_snapshot(h), d_stats4, n_rows_global, h->dmu, grad_actor + LA.logstd, d_epoch_stats, nr, P,
+                dmax ? h->sc + SC_DOUT : nullptr);
+            h->dout_ready = dmax;
             h->launches++;
             if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, h->dmu, nr * N, s, fa, h->cd.lda))) return rc;
         }

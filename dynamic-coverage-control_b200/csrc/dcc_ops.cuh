@@ -1101,6 +1101,12 @@ __global__ void head_fold_kernel(const float *__restrict__ gamma, const float *_
 
 // Second half of the actor head when mu was produced by the fused GEMM epilogue (tcgen05 backend): sampling / log-prob
 // from mu [rows, 2].  One thread per row; same modes, Philox keying and log-prob formula as actor_head_kernel.
+// Normal.log_prob summed over the 2 action dims (distributions.py:33-35); ONE expression for every kernel that forms it
+__device__ __forceinline__ float gauss_logp2(float a0, float a1, float s0, float s1, float ls0, float ls1, float sd0, float sd1) {
+    const float d0 = a0 - s0, d1 = a1 - s1;
+    return -(d0 * d0) / (2.f * sd0 * sd0) - ls0 - 0.5f * LOG_2PI - (d1 * d1) / (2.f * sd1 * sd1) - ls1 - 0.5f * LOG_2PI;
+}
+
 __global__ void gauss_finish_kernel(const float *__restrict__ mu, const float *__restrict__ logstd, float *__restrict__ actions,
                                     float *__restrict__ mu_out, float *__restrict__ logp_out, int rows, int mode, int deterministic,
                                     uint64_t seed, uint64_t offset, uint64_t row_base, const long long *__restrict__ ridx = nullptr) {
@@ -1123,9 +1129,7 @@ __global__ void gauss_finish_kernel(const float *__restrict__ mu, const float *_
         a0 = actions[ar * 2 + 0]; a1 = actions[ar * 2 + 1];
     }
     if (mu_out && mu_out != mu) { mu_out[(size_t)r * 2 + 0] = s0; mu_out[(size_t)r * 2 + 1] = s1; }
-    const float d0 = a0 - s0, d1 = a1 - s1;
-    const float lp = -(d0 * d0) / (2.f * sd0 * sd0) - ls0 - 0.5f * LOG_2PI - (d1 * d1) / (2.f * sd1 * sd1) - ls1 -
-                     0.5f * LOG_2PI;
+    const float lp = gauss_logp2(a0, a1, s0, s1, ls0, ls1, sd0, sd1);
     if (logp_out) logp_out[r] = lp;
 }
 
@@ -1270,31 +1274,45 @@ __device__ __forceinline__ void ppo_policy_reduce(float pl, float rs, float dls0
     }
 }
 
-// policy part: writes dmu [rows*N,2]; accumulates dlogstd[2] and stats {0: policy_loss_sum, 2: ratio_sum} over agent rows
+// policy part: writes dmu [rows*N,2]; accumulates dlogstd[2] and stats {0: policy_loss_sum, 2: ratio_sum} over agent rows.
+// logp_new == nullptr: the new log-prob is formed here from mu and the given action (what gauss_finish_kernel would have written:
+// the same expression, gauss_logp2) — the fused-head update path then needs no separate log-prob pass.  dout_max (optional):
+// atomicMax of the float bits of max |dmu| (first factor of the a-priori bound of the pre-split gradients).
 __global__ void ppo_policy_loss_kernel(const float *__restrict__ mu, const float *__restrict__ logp_new,
                                        const float *__restrict__ actions, const float *__restrict__ logstd,
                                        const float *__restrict__ logp_old, const float *__restrict__ ret,
                                        const float *__restrict__ v_old, const float *__restrict__ vn_gae,
                                        const double *__restrict__ adv_stats, double n_adv, float *__restrict__ dmu,
-                                       float *__restrict__ dlogstd, double *__restrict__ stats, int rows, PpoLossParams P) {
+                                       float *__restrict__ dlogstd, double *__restrict__ stats, int rows, PpoLossParams P,
+                                       uint32_t *__restrict__ dout_max = nullptr) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    float pl = 0.f, rs = 0.f, dls0 = 0.f, dls1 = 0.f;
+    float pl = 0.f, rs = 0.f, dls0 = 0.f, dls1 = 0.f, dm = 0.f;
     if (r < rows) {
         const int N = P.n_agents;
         const float adv = normalized_adv(ret, v_old, vn_gae, adv_stats, n_adv, r);
-        const float sd0 = expf(logstd[0]), sd1 = expf(logstd[1]);
+        const float ls0 = logstd[0], ls1 = logstd[1];
+        const float sd0 = expf(ls0), sd1 = expf(ls1);
         const float iv0 = 1.f / (sd0 * sd0), iv1 = 1.f / (sd1 * sd1);
         for (int n = 0; n < N; ++n) {
             const size_t i = (size_t)r * N + n;
-            const float dlogp = ppo_policy_row(logp_new[i], logp_old[i], adv, P, pl, rs);
-            const float d0 = actions[i * 2 + 0] - mu[i * 2 + 0], d1 = actions[i * 2 + 1] - mu[i * 2 + 1];
-            dmu[i * 2 + 0] = dlogp * d0 * iv0;
-            dmu[i * 2 + 1] = dlogp * d1 * iv1;
+            const float a0 = actions[i * 2 + 0], a1 = actions[i * 2 + 1], m0 = mu[i * 2 + 0], m1 = mu[i * 2 + 1];
+            const float lpn = logp_new ? logp_new[i] : gauss_logp2(a0, a1, m0, m1, ls0, ls1, sd0, sd1);
+            const float dlogp = ppo_policy_row(lpn, logp_old[i], adv, P, pl, rs);
+            const float d0 = a0 - m0, d1 = a1 - m1;
+            const float g0 = dlogp * d0 * iv0, g1 = dlogp * d1 * iv1;
+            dmu[i * 2 + 0] = g0;
+            dmu[i * 2 + 1] = g1;
+            dm = fmaxf(dm, fmaxf(fabsf(g0), fabsf(g1)));
             dls0 = fmaf(dlogp, d0 * d0 * iv0 - 1.f, dls0);
             dls1 = fmaf(dlogp, d1 * d1 * iv1 - 1.f, dls1);
         }
     }
     ppo_policy_reduce(pl, rs, dls0, dls1, stats, dlogstd);
+    if (dout_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(FULL_MASK, dm, o));
+        if ((threadIdx.x & 31) == 0 && dm > 0.f) atomicMax(dout_max, __float_as_uint(dm));
+    }
 }
 
 // minibatch variant (num_mini_batch > 1, shared_buffer.py:219-279): one thread per agent row k of the minibatch;
