@@ -188,15 +188,15 @@ def run_init_case(name, N, M, hidden, seed, extra=None):
     lr.train_envs.close()
 
 
-def run_pickle_case(name, N, M, hidden, seed):
+def run_pickle_case(name, N, M, hidden, seed, extra=None):
     """A checkpoint exactly as the reference writes it: MAPPOTrainer.save_model pickles the whole MAPPOPolicy object
     (algos/mappo.py:237-240).  Stored with the state_dict values beside it, for the importer test
     (MAPPOTrainer.load_model must read the reference's own agent.pkl)."""
     import shutil
     import tempfile
-    lr, cfg = build_learner(N, M, 1, 4, hidden, 1, seed)
+    lr, cfg = build_learner(N, M, 1, 4, hidden, 1, seed, extra=extra)
     D = lr.obs_dim_n[0]
-    a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden))
+    a_shapes, c_shapes = net_shapes(dict(n_agents=N, obs_dim=D, hidden=hidden, **(extra or {})))
     set_params(lr.policy.actor, make_params(a_shapes, seed * 2 + 1))
     set_params(lr.policy.critic, make_params(c_shapes, seed * 2 + 2))
     d = tempfile.mkdtemp()
@@ -222,6 +222,9 @@ def main():
         # 48 env-step rows = 384 agent rows = 3 row tiles
         run_case("gen_8x64_h256", 8, 64, 4, 12, 256, 4, seed=14)
         run_pickle_case("3x20_h32", 3, 20, 32, seed=15)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rnnpkl":      # a reference-written checkpoint of a recurrent policy (GRU modules inside)
+        run_pickle_case("rnn2_3x20_h32", 3, 20, 32, seed=21, extra=dict(use_recurrent_policy=True, recurrent_N=2))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rnninit":     # RNNLayer's construction order / init (rnn.py:13-22), two GRU layers
         run_init_case("rnn2_3x20", 3, 20, 32, seed=6, extra=dict(use_recurrent_policy=True, recurrent_N=2))

@@ -290,6 +290,14 @@ def test_load_checkpoint_reads_a_reference_written_agent_pkl(tmp_path):
             assert np.array_equal(sd[tag][k].numpy(), g[tag + "." + k]), (tag, k)
             n += 1
     assert n == 33    # actor 17 (incl. fc_h and logstd), critic 16
+    # a recurrent policy written by the reference (R_Actor / R_Critic with an RNNLayer: nn.GRU x 2 + LayerNorm, rnn.py:8-22)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_agent_rnn2_3x20_h32.npz"))
+    sd = load_checkpoint(os.path.join(ROOT, "tests", "golden", "ref_agent_rnn2_3x20_h32.pkl"))
+    for tag in ("actor", "critic"):
+        keys = [k[len(tag) + 1:] for k in g.files if k.startswith(tag + ".")]
+        assert list(sd[tag].keys()) == keys and "rnn.rnn.weight_hh_l1" in keys and "rnn.norm.bias" in keys
+        for k in keys:
+            assert np.array_equal(sd[tag][k].numpy(), g[tag + "." + k]), (tag, k)
     # this build's own format round-trips through the same reader; anything else is refused with a clear error
     own = {"actor": {"w": torch.ones(2)}, "critic": {"w": torch.zeros(2)}, "format": CHECKPOINT_FORMAT}
     with open(tmp_path / "agent.pkl", "wb") as f:

@@ -126,3 +126,56 @@ def test_recurrent_learner_end_to_end(over):
                                                                  lr.policy._stream()), "dcc_mappo_act")
     sd = lr.policy.state_dict()
     assert "rnn.rnn.weight_ih_l0" in sd["actor"] and "rnn.norm.bias" in sd["critic"]
+
+
+def test_reference_recurrent_checkpoint_loads_and_acts(tmp_path):
+    """An agent.pkl written by the UNMODIFIED reference with use_recurrent_policy / recurrent_N = 2 (pickled MAPPOPolicy object,
+    mappo.py:237-240) loads into the recurrent MAPPOPolicy; one step of get_actions / get_values / evaluate_actions on it equals
+    the float64 oracle run on the same parameters; save_model -> load_model round-trips the GRU tensors."""
+    import os
+    import torch
+    from oracle import mappo_oracle as mo
+    from dcc_b200.algos import MAPPOPolicy, MAPPOTrainer
+    from dcc_b200.envs.spaces import Box
+    from dcc_b200.utils.config import load_config
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(here, "ref_agent_rnn2_3x20_h32.npz"))
+    N, M, Hd, R = 3, 20, 32, 2
+    D = 4 + 2 * (N - 1) + 5 * M
+    cfg = load_config(None, num_agents=N, num_pois=M, algo_hidden_size=Hd, use_recurrent_policy=True, recurrent_N=R,
+                      n_rollout_threads=8, n_eval_rollout_threads=0)
+    pol = MAPPOPolicy(cfg, Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,)))
+    tr = MAPPOTrainer(cfg, pol)
+    tr.load_model(os.path.join(here, "ref_agent_rnn2_3x20_h32.pkl"))
+    ap = {k[6:]: g[k] for k in g.files if k.startswith("actor.") and "fc_h" not in k}
+    cp = {k[7:]: g[k] for k in g.files if k.startswith("critic.") and "fc_h" not in k}
+    for k in pol.actor.layout:
+        assert np.array_equal(pol.actor.view(k).cpu().numpy().reshape(-1), ap[k].reshape(-1)), k
+    rng = np.random.default_rng(3)
+    E = 8
+    obs = rng.normal(0, 1, (E, N, D)).astype(np.float32)
+    ha = rng.normal(0, 0.5, (E * N, R, Hd)).astype(np.float32)
+    hc = np.repeat(rng.normal(0, 0.5, (E, 1, R, Hd)).astype(np.float32), N, axis=1).reshape(E * N, R, Hd)
+    masks = (rng.random((E, 1)) > 0.3).astype(np.float32).repeat(N, 1).reshape(E * N, 1)
+    act = rng.normal(0, 1, (E * N, 2)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()   # noqa: E731
+    v, lp, ent = pol.evaluate_actions(None, t(obs), t(ha), t(hc), t(act), t(masks))
+    oa, oc = mo.RecurrentNet(mo.make_actor(ap)), mo.RecurrentNet(mo.make_critic(cp))
+    mean = oa.forward(obs.reshape(E * N, D), ha, masks, 1)
+    lp_ref, ent_ref = mo.gaussian_logp_entropy(mean, ap["act.action_out.logstd._bias"].reshape(1, -1).astype(np.float64), act)
+    sx = np.repeat(obs.reshape(E, 1, N * D), N, axis=1).reshape(E * N, N * D)
+    v_ref = oc.forward(sx, hc, masks, 1)
+    assert np.allclose(lp.cpu().numpy(), lp_ref, rtol=1e-5, atol=1e-5)
+    assert np.allclose(v.cpu().numpy(), v_ref, rtol=1e-5, atol=1e-5)
+    assert abs(float(ent) - float(ent_ref)) < 1e-6
+    # deterministic get_actions returns the mean and the new hidden states of both nets
+    vals, a_det, _, ha2, hc2 = pol.get_actions(None, t(obs), t(ha), t(hc), t(masks), deterministic=True)
+    assert np.allclose(a_det.cpu().numpy(), mean, rtol=1e-5, atol=1e-5)
+    assert np.allclose(ha2.cpu().numpy(), oa.h_final, rtol=1e-5, atol=1e-5) and np.allclose(hc2.cpu().numpy(), oc.h_final, rtol=1e-5, atol=1e-5)
+    a_only, ha3 = pol.act(t(obs), t(ha), t(masks), deterministic=True)
+    assert torch.allclose(a_only.view(-1, 2), a_det) and torch.allclose(ha3, ha2)
+    # this build's checkpoint format carries the GRU tensors too
+    tr.save_model(str(tmp_path))
+    pol2 = MAPPOPolicy(cfg, Box(-np.inf, np.inf, (D,)), Box(-np.inf, np.inf, (N * D,)), Box(-1, 1, (2,)))
+    MAPPOTrainer(cfg, pol2).load_model(str(tmp_path))
+    assert torch.equal(pol2.actor.params, pol.actor.params) and torch.equal(pol2.critic.params, pol.critic.params)
