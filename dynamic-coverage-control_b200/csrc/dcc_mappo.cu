@@ -108,6 +108,10 @@ struct MappoHandle {
     // gradients in the backward pass), gate activations and outputs of every step of a pass; [rows, *] with rows <= chunk * N
     float *r_Hp[MAX_RNN], *r_GI[MAX_RNN], *r_GH[MAX_RNN], *r_gates[MAX_RNN], *r_Hout[MAX_RNN];
     float *r_dH[2], *r_Y, *r_mean, *r_rstd, *r_mask, *r_dhp[2], *r_dfeat, *r_zero, *r_dummy;
+    // tcgen05 backend: weight images of the GRU matrices (per net and layer, rebuilt once per ABI call): the three 256-row gate
+    // slices of weight_ih / weight_hh for the forward products (fp16 split) and the two matrices transposed for dGI W_ih / dGH W_hh
+    // (3xTF32, K = 768); r_dT: the per-step dGH W_hh products (the tensor-core GEMM writes, it does not accumulate)
+    float *r_img_ih[2][MAX_RNN][3], *r_img_hh[2][MAX_RNN][3], *r_img_ihT[2][MAX_RNN], *r_img_hhT[2][MAX_RNN], *r_dT[2];
     int64_t launches;
 };
 enum { SC_DOUT = 0, SC_RSTD = 1, SC_DXH = 1 + MAX_BLOCKS, SC_BND = 1 + 2 * MAX_BLOCKS, SC_COUNT = 2 + 2 * MAX_BLOCKS };
@@ -766,7 +770,34 @@ static inline dim3 ew_grid(size_t n) { return dim3((unsigned)((n + 255) / 256));
 
 // X [steps * S, H] (time-major trunk outputs) -> h->r_Y = LayerNorm(GRU(X)) [steps * S, H]; everything the backward pass needs
 // stays in the r_* scratch.  mask_rows [steps * S]: the step's mask per row (rnn.py:26-27,66-67: state *= mask before the step).
-static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, const float *X, int S, int steps, const RnnSrc &src,
+// weight images of the GRU matrices for the tensor-core GEMMs (backend 2), once per ABI call
+static int rnn_prep_images(MappoHandle *h, const NetLayout &L, const float *P, int net, bool for_backward, cudaStream_t s) {
+    if (h->backend != 2) return DCC_OK;
+    int rc;
+    for (int l = 0; l < L.rn; ++l) {
+        for (int j = 0; j < 3; ++j) {
+            if ((rc = tc_prep_weights(h, P + L.Wih[l] + (size_t)j * L.H * L.H, L.H, false, L.H, h->r_img_ih[net][l][j], s, true))) return rc;
+            if ((rc = tc_prep_weights(h, P + L.Whh[l] + (size_t)j * L.H * L.H, L.H, false, L.H, h->r_img_hh[net][l][j], s, true))) return rc;
+        }
+        if (for_backward) {
+            if ((rc = tc_prep_weights(h, P + L.Wih[l], L.H, true, 3 * L.H, h->r_img_ihT[net][l], s, false))) return rc;
+            if ((rc = tc_prep_weights(h, P + L.Whh[l], L.H, true, 3 * L.H, h->r_img_hhT[net][l], s, false))) return rc;
+        }
+    }
+    return DCC_OK;
+}
+
+// C[M, 3H] = A[M, H] W^T for a GRU matrix W [3H, H]: three 256-column slices on the fp16-split tensor-core kernel, or one FFMA GEMM
+static int rnn_gemm_gates(MappoHandle *h, int M, const float *A, const float *W, float *const (&img)[3], float *C, cudaStream_t s) {
+    const int H = h->cfg.hidden;
+    if (h->backend != 2) return launch_gemm(h, false, true, M, 3 * H, H, A, H, W, H, C, 3 * H, false, s);
+    int rc;
+    for (int j = 0; j < 3; ++j)
+        if ((rc = tc_gemm_fwd(h, M, H, A, H, img[j], C + j * H, 3 * H, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true))) return rc;
+    return DCC_OK;
+}
+
+static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, int net, const float *X, int S, int steps, const RnnSrc &src,
                        const float *mask_rows, cudaStream_t s) {
     const int H = L.H, H3 = 3 * L.H;
     const size_t rows = (size_t)S * steps, SH = (size_t)S * H;
@@ -774,7 +805,7 @@ static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, const
     for (int l = 0; l < L.rn; ++l) {
         const float *Xl = l == 0 ? X : h->r_Hout[l - 1];
         // x W_ih^T for all steps at once (bias added in the gate kernel)
-        if ((rc = launch_gemm(h, false, true, (int)rows, H3, H, Xl, H, P + L.Wih[l], H, h->r_GI[l], H3, false, s))) return rc;
+        if ((rc = rnn_gemm_gates(h, (int)rows, Xl, P + L.Wih[l], h->r_img_ih[net][l], h->r_GI[l], s))) return rc;
         for (int t = 0; t < steps; ++t) {
             float *Hp = h->r_Hp[l] + t * SH;
             if (t == 0)
@@ -784,7 +815,7 @@ static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, const
                                                            Hp, S, H);
             h->launches++;
             float *GH = h->r_GH[l] + (size_t)t * S * H3;
-            if ((rc = launch_gemm(h, false, true, S, H3, H, Hp, H, P + L.Whh[l], H, GH, H3, false, s))) return rc;   // the recurrence
+            if ((rc = rnn_gemm_gates(h, S, Hp, P + L.Whh[l], h->r_img_hh[net][l], GH, s))) return rc;   // the recurrence
             gru_gate_fwd_kernel<<<ew_grid(SH), 256, 0, s>>>(h->r_GI[l] + (size_t)t * S * H3, GH, P + L.bih[l], P + L.bhh[l], Hp,
                                                            h->r_gates[l] + (size_t)t * S * 4 * H, h->r_Hout[l] + t * SH, S, H);
             h->launches++;
@@ -800,8 +831,9 @@ static int rnn_forward(MappoHandle *h, const NetLayout &L, const float *P, const
 // Backward of head + RNNLayer: dout [steps * S, out] -> parameter gradients of the head, the LayerNorm and every GRU layer
 // accumulated into G; the gradient w.r.t. the trunk output lands in h->r_dfeat.  BPTT runs inside the pass only: the stored
 // state in front of step 0 is a constant, exactly like the reference's chunked / whole-episode generators.
-static int rnn_backward(MappoHandle *h, const NetLayout &L, const float *P, float *G, const float *X, const float *dout, int S, int steps,
-                        const float *mask_rows, cudaStream_t s) {
+static int rnn_backward(MappoHandle *h, const NetLayout &L, const float *P, int net, float *G, const float *X, const float *dout, int S,
+                        int steps, const float *mask_rows, cudaStream_t s) {
+    const bool tcg = h->backend == 2;
     const int H = L.H, H3 = 3 * L.H, wpb = 8;
     const size_t rows = (size_t)S * steps, SH = (size_t)S * H;
     const int top = L.rn - 1;
@@ -826,21 +858,35 @@ static int rnn_backward(MappoHandle *h, const NetLayout &L, const float *P, floa
             gru_gate_bwd_kernel<<<ew_grid(SH), 256, 0, s>>>(dHl + t * SH, lastt ? nullptr : h->r_dhp[(t + 1) & 1],
                                                            lastt ? nullptr : mask_rows + (size_t)(t + 1) * S,
                                                            h->r_gates[l] + (size_t)t * S * 4 * H, h->r_Hp[l] + t * SH,
-                                                           dGI + (size_t)t * S * H3, dGH + (size_t)t * S * H3, h->r_dhp[t & 1], S, H);
+                                                           dGI + (size_t)t * S * H3, dGH + (size_t)t * S * H3, h->r_dhp[t & 1], S, H,
+                                                           (tcg && !lastt) ? h->r_dT[(t + 1) & 1] : nullptr);
             h->launches++;
-            // gradient w.r.t. the masked previous state: dhp += dGH W_hh (not needed in front of step 0: that state is data)
-            if (t > 0 && (rc = launch_gemm(h, false, false, S, H, H3, dGH + (size_t)t * S * H3, H3, P + L.Whh[l], H, h->r_dhp[t & 1], H, true, s)))
-                return rc;
+            // gradient w.r.t. the masked previous state: dhp += dGH W_hh (not needed in front of step 0: that state is data);
+            // the tensor-core GEMM writes its product to r_dT, which the next (earlier) step's gate kernel adds
+            if (t > 0) {
+                rc = tcg ? tc_gemm_fwd(h, S, H3, dGH + (size_t)t * S * H3, H3, h->r_img_hhT[net][l], h->r_dT[t & 1], H, s)
+                         : launch_gemm(h, false, false, S, H, H3, dGH + (size_t)t * S * H3, H3, P + L.Whh[l], H, h->r_dhp[t & 1], H, true, s);
+                if (rc) return rc;
+            }
         }
         const float *Xl = l == 0 ? X : h->r_Hout[l - 1];
-        if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGH, H3, h->r_Hp[l], H, G + L.Whh[l], H, true, s))) return rc;
-        if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGI, H3, Xl, H, G + L.Wih[l], H, true, s))) return rc;
+        if (tcg) {      // dW += dG^T X on the 3xTF32 weight-gradient kernel, one 256-row gate slice at a time
+            for (int j = 0; j < 3; ++j) {
+                if ((rc = tc_gemm_wgrad(h, (int)rows, H, dGH + j * H, H3, h->r_Hp[l], H, G + L.Whh[l] + (size_t)j * H * H, H, s))) return rc;
+                if ((rc = tc_gemm_wgrad(h, (int)rows, H, dGI + j * H, H3, Xl, H, G + L.Wih[l] + (size_t)j * H * H, H, s))) return rc;
+            }
+        } else {
+            if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGH, H3, h->r_Hp[l], H, G + L.Whh[l], H, true, s))) return rc;
+            if ((rc = launch_gemm(h, true, false, H3, H, (int)rows, dGI, H3, Xl, H, G + L.Wih[l], H, true, s))) return rc;
+        }
         const dim3 cg((H3 + 127) / 128, (unsigned)std::min<size_t>((rows + 255) / 256, 256));
         colsum_atomic_kernel<<<cg, 128, 0, s>>>(dGI, rows, H3, G + L.bih[l]);
         colsum_atomic_kernel<<<cg, 128, 0, s>>>(dGH, rows, H3, G + L.bhh[l]);
         h->launches += 2;
         float *dX = l > 0 ? h->r_dH[cur ^ 1] : h->r_dfeat;
-        if ((rc = launch_gemm(h, false, false, (int)rows, H, H3, dGI, H3, P + L.Wih[l], H, dX, H, false, s))) return rc;
+        rc = tcg ? tc_gemm_fwd(h, (int)rows, H3, dGI, H3, h->r_img_ihT[net][l], dX, H, s)
+                 : launch_gemm(h, false, false, (int)rows, H, H3, dGI, H3, P + L.Wih[l], H, dX, H, false, s);
+        if (rc) return rc;
         cur ^= 1;
     }
     DCC_CUDA_TRY(cudaGetLastError());
@@ -993,6 +1039,19 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
             alloc(&h->r_gates[l], RA * 4 * H); alloc(&h->r_Hout[l], RA * H);
         }
         for (int i = 0; i < 2; ++i) { alloc(&h->r_dH[i], RA * H); alloc(&h->r_dhp[i], RA * H); }
+        if (h->backend == 2) {
+            const size_t kt16 = (H + tc::TC_BK16 - 1) / tc::TC_BK16, kt32 = (3 * H + tc::TC_BK - 1) / tc::TC_BK;
+            for (int n = 0; n < 2; ++n)
+                for (int l = 0; l < cfg->recurrent_N; ++l) {
+                    for (int j = 0; j < 3; ++j) {
+                        alloc(&h->r_img_ih[n][l][j], kt16 * 2 * tc::TC_B_TILE_FLOATS);
+                        alloc(&h->r_img_hh[n][l][j], kt16 * 2 * tc::TC_B_TILE_FLOATS);
+                    }
+                    alloc(&h->r_img_ihT[n][l], kt32 * 2 * tc::TC_B_TILE_FLOATS);
+                    alloc(&h->r_img_hhT[n][l], kt32 * 2 * tc::TC_B_TILE_FLOATS);
+                }
+            for (int i = 0; i < 2; ++i) alloc(&h->r_dT[i], RA * H);
+        }
         alloc(&h->r_Y, RA * H); alloc(&h->r_mean, RA); alloc(&h->r_rstd, RA); alloc(&h->r_mask, RA); alloc(&h->r_dfeat, RA * H);
         alloc(&h->r_zero, 3 * H); alloc(&h->r_dummy, H);
         if (ce == cudaSuccess) ce = cudaMemset(h->r_zero, 0, 3 * H * sizeof(float));
@@ -1025,8 +1084,13 @@ int dcc_mappo_destroy(void *handle) {
         float *rb[] = {h->r_Hp[l], h->r_GI[l], h->r_GH[l], h->r_gates[l], h->r_Hout[l]};
         for (float *b : rb) cudaFree(b);
     }
+    for (int n = 0; n < 2; ++n)
+        for (int l = 0; l < MAX_RNN; ++l) {
+            for (int j = 0; j < 3; ++j) { cudaFree(h->r_img_ih[n][l][j]); cudaFree(h->r_img_hh[n][l][j]); }
+            cudaFree(h->r_img_ihT[n][l]); cudaFree(h->r_img_hhT[n][l]);
+        }
     float *rbufs[] = {h->r_dH[0], h->r_dH[1], h->r_dhp[0], h->r_dhp[1], h->r_Y, h->r_mean, h->r_rstd, h->r_mask, h->r_dfeat,
-                      h->r_zero, h->r_dummy};
+                      h->r_zero, h->r_dummy, h->r_dT[0], h->r_dT[1]};
     for (float *b : rbufs) cudaFree(b);
     cudaFree(h->dsums);
     cudaFree(h->dz_absmax);
@@ -1516,6 +1580,8 @@ int dcc_mappo_act_rnn(void *handle, const float *actor, const float *critic, con
     int rc;
     if (actor && (rc = fold_ln0(h, h->la, actor, 0, false, s))) return rc;
     if (critic && (rc = fold_ln0(h, h->lc, critic, 1, false, s))) return rc;
+    if (actor && (rc = rnn_prep_images(h, h->la, actor, 0, false, s))) return rc;
+    if (critic && (rc = rnn_prep_images(h, h->lc, critic, 1, false, s))) return rc;
     for (int e0 = 0; e0 < n_envs; e0 += h->chunk_rows) {
         const int ne = min(h->chunk_rows, n_envs - e0);
         const float *x = d_obs + (size_t)e0 * N * D;
@@ -1524,7 +1590,7 @@ int dcc_mappo_act_rnn(void *handle, const float *actor, const float *critic, con
             rnn_mask_rows_kernel<<<(rows + 255) / 256, 256, 0, s>>>(d_masks + e0, nullptr, N, h->r_mask, rows);
             if ((rc = trunk_forward(h, h->la, actor, 0, x, rows, false, s))) return rc;
             const RnnSrc src{d_h_actor + (size_t)e0 * N * RN * H, nullptr, 1};
-            if ((rc = rnn_forward(h, h->la, actor, h->hh[h->la.nblk - 1], rows, 1, src, h->r_mask, s))) return rc;
+            if ((rc = rnn_forward(h, h->la, actor, 0, h->hh[h->la.nblk - 1], rows, 1, src, h->r_mask, s))) return rc;
             for (int l = 0; l < RN && d_h_actor_out; ++l)
                 gru_store_state_kernel<<<ew_grid((size_t)rows * H), 256, 0, s>>>(h->r_Hout[l], d_h_actor_out, RN, l, rows, H, (size_t)e0 * N);
             actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(
@@ -1536,7 +1602,7 @@ int dcc_mappo_act_rnn(void *handle, const float *actor, const float *critic, con
             rnn_mask_rows_kernel<<<(ne + 255) / 256, 256, 0, s>>>(d_masks + e0, nullptr, 1, h->r_mask, ne);
             if ((rc = trunk_forward(h, h->lc, critic, 1, x, ne, false, s))) return rc;
             const RnnSrc src{d_h_critic + (size_t)e0 * RN * H, nullptr, 1};
-            if ((rc = rnn_forward(h, h->lc, critic, h->hh[h->lc.nblk - 1], ne, 1, src, h->r_mask, s))) return rc;
+            if ((rc = rnn_forward(h, h->lc, critic, 1, h->hh[h->lc.nblk - 1], ne, 1, src, h->r_mask, s))) return rc;
             for (int l = 0; l < RN && d_h_critic_out; ++l)
                 gru_store_state_kernel<<<ew_grid((size_t)ne * H), 256, 0, s>>>(h->r_Hout[l], d_h_critic_out, RN, l, ne, H, (size_t)e0);
             critic_head_kernel<<<grid_for_rows(h, ne, 8), 256, 0, s>>>(h->r_Y, critic + h->lc.Wh, critic + h->lc.bh, d_values + e0, ne, H);
@@ -1566,6 +1632,8 @@ int dcc_mappo_seq_grads(void *handle, const float *actor, const float *critic, f
     int rc;
     if ((rc = grads_prologue(h, actor, critic, grad_actor, grad_critic, d_vn_state, d_ret_sums, n_index_global, d_epoch_stats, s, false)))
         return rc;
+    if ((rc = rnn_prep_images(h, LA, actor, 0, true, s))) return rc;
+    if ((rc = rnn_prep_images(h, LC, critic, 1, true, s))) return rc;
     const float *vn_now = h->cfg.use_valuenorm ? d_vn_state : nullptr;
     const PpoLossParams P = loss_params(h, n_index_global);
     const long Sc = rnn_pass_seqs(h, seq_len);
@@ -1580,24 +1648,24 @@ int dcc_mappo_seq_grads(void *handle, const float *actor, const float *critic, f
         // 1) actor: trunk -> GRU -> head -> policy loss -> backward through head / GRU (BPTT inside the pass) / trunk
         if ((rc = trunk_forward(h, LA, actor, 0, d_obs, rows, true, s, pidx, 1))) return rc;
         const RnnSrc sa{d_h_actor, pidx, 1};
-        if ((rc = rnn_forward(h, LA, actor, h->hh[LA.nblk - 1], S, seq_len, sa, h->r_mask, s))) return rc;
+        if ((rc = rnn_forward(h, LA, actor, 0, h->hh[LA.nblk - 1], S, seq_len, sa, h->r_mask, s))) return rc;
         actor_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(h->r_Y, actor + LA.Wh, actor + LA.bh, actor + LA.logstd,
                                                                    const_cast<float *>(d_actions), h->mu, h->logp, rows, H, 1, 0, 0, 0, 0, pidx);
         ppo_policy_loss_mb_kernel<<<(rows + 127) / 128, 128, 0, s>>>(h->mu, h->logp, d_actions, actor + LA.logstd, d_logp_old, d_returns,
                                                                     d_values, vn_snapshot(h), d_stats4, n_rows_global, pidx, h->dmu,
                                                                     grad_actor + LA.logstd, d_epoch_stats, rows, P);
         h->launches += 2;
-        if ((rc = rnn_backward(h, LA, actor, grad_actor, h->hh[LA.nblk - 1], h->dmu, S, seq_len, h->r_mask, s))) return rc;
+        if ((rc = rnn_backward(h, LA, actor, 0, grad_actor, h->hh[LA.nblk - 1], h->dmu, S, seq_len, h->r_mask, s))) return rc;
         if ((rc = trunk_backward(h, LA, actor, 0, grad_actor, nullptr, rows, s, nullptr, 0, h->r_dfeat))) return rc;
         // 2) critic, as the reference evaluates it here: one centralised row per AGENT row of the sequences (hidden states and
         //    masks are those of the env step: row / N)
         if ((rc = trunk_forward(h, LC, critic, 1, d_obs, rows, true, s, pidx, N))) return rc;
         const RnnSrc sc{d_h_critic, pidx, N};
-        if ((rc = rnn_forward(h, LC, critic, h->hh[LC.nblk - 1], S, seq_len, sc, h->r_mask, s))) return rc;
+        if ((rc = rnn_forward(h, LC, critic, 1, h->hh[LC.nblk - 1], S, seq_len, sc, h->r_mask, s))) return rc;
         critic_head_kernel<<<grid_for_rows(h, rows, 8), 256, 0, s>>>(h->r_Y, critic + LC.Wh, critic + LC.bh, h->vnew, rows, H);
         ppo_value_loss_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_returns, d_values, h->vnew, vn_now, h->dv, d_epoch_stats, rows, P, pidx);
         h->launches += 2;
-        if ((rc = rnn_backward(h, LC, critic, grad_critic, h->hh[LC.nblk - 1], h->dv, S, seq_len, h->r_mask, s))) return rc;
+        if ((rc = rnn_backward(h, LC, critic, 1, grad_critic, h->hh[LC.nblk - 1], h->dv, S, seq_len, h->r_mask, s))) return rc;
         if ((rc = trunk_backward(h, LC, critic, 1, grad_critic, nullptr, rows, s, nullptr, 0, h->r_dfeat))) return rc;
     }
     if ((rc = ln0_finalize(h, LA, actor, grad_actor, s))) return rc;

@@ -10,7 +10,9 @@
 // fp32 GEMMs (gemm_kernel: x W_ih^T for ALL steps of a pass at once, h W_hh^T per step — the recurrence); the kernels here
 // are the element-wise halves: masking / gathering the previous state, the gates forward, the gates backward (BPTT), and
 // column sums for the bias gradients.  float32 throughout, fmaf-free gate algebra in the reference's operation order.
-// Not on the benchmarked path (BASELINE configs are MLP policies): written for parity, not tuned.
+// The GEMMs run on the tcgen05 kernels when the handle's backend is 2 (hidden 256: fp16 hi/lo split for the forward products —
+// trunk outputs and GRU states are bounded —, 3xTF32 for everything that multiplies a gradient) and on the fp32 FFMA kernel
+// otherwise.  Not on the benchmarked path (BASELINE configs are MLP policies): written for parity first.
 #pragma once
 #include "dcc_ops.cuh"
 
@@ -65,16 +67,18 @@ __global__ void gru_gate_fwd_kernel(const float *__restrict__ GI, const float *_
 // the gradient flowing back from step t+1 into h_t passes through h_prev(t+1) = h_t * mask_{t+1}).  Writes the pre-activation
 // gradients dGI = [dr', dz', dn'] and dGH = [dr', dz', dn' * r] (both [S, 3H], in place over GI / GH) and the direct part of the
 // gradient w.r.t. the masked previous state, dhp = dh * z (the GEMM dGH W_hh is accumulated onto it afterwards).
+// dh_next2 (optional): a second addend of the gradient from step t+1 (the dGH W_hh product when it is formed by a GEMM that
+// writes rather than accumulates: the tensor-core path).
 __global__ void gru_gate_bwd_kernel(const float *__restrict__ dHout, const float *__restrict__ dh_next,
                                     const float *__restrict__ mask_next, const float *__restrict__ gates,
                                     const float *__restrict__ Hp, float *__restrict__ dGI, float *__restrict__ dGH,
-                                    float *__restrict__ dhp, int S, int H) {
+                                    float *__restrict__ dhp, int S, int H, const float *__restrict__ dh_next2 = nullptr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)S * H) return;
     const size_t s = i / H;
     const int c = (int)(i % H);
     float dh = dHout[i];
-    if (dh_next) dh += dh_next[i] * mask_next[s];
+    if (dh_next) dh += (dh_next2 ? dh_next[i] + dh_next2[i] : dh_next[i]) * mask_next[s];
     const float *g = gates + s * 4 * H;
     const float r = g[c], z = g[H + c], n = g[2 * H + c], ghn = g[3 * H + c];
     const float dn = dh * (1.f - z);
