@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #include "dcc_compact.cuh"
@@ -1218,8 +1219,18 @@ int dcc_mappo_set_env_layout(void *handle, int n_pois, const double *h_poi_xy, d
     if (ce != cudaSuccess) { set_last_cuda_error(ce, "cudaMalloc(compact scratch)", __FILE__, __LINE__); return DCC_ERR_ALLOC; }
     DCC_CUDA_TRY(cudaMemcpy(h->d_poi, h_poi_xy, sizeof(double) * 2 * n_pois, cudaMemcpyHostToDevice));
     const size_t smem = compact_features_smem(cd, 8);
-    if (smem > 48 * 1024)
-        DCC_CUDA_TRY(cudaFuncSetAttribute(compact_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        // the opt-in is a per-device attribute of the kernel: only ever RAISE it, so that a later handle with a smaller layout
+        // cannot pull it under an earlier live handle's footprint
+        static std::mutex mu;
+        static int max_smem[64] = {0};
+        std::lock_guard<std::mutex> lk(mu);
+        int &mx = max_smem[h->device & 63];
+        if ((int)smem > mx) {
+            DCC_CUDA_TRY(cudaFuncSetAttribute(compact_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mx = (int)smem;
+        }
+    }
     h->cd = cd;
     h->compact = true;
     return DCC_OK;
