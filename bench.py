@@ -534,10 +534,13 @@ def measure_full_loop(E, steps, warmup, world, rank, local_rank, dev):
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if bool(tj.get("compact")) == compact and int(tj.get("chunk_rows", 0)) == chunk_rows:
-                traffic = tj["dram_bytes_per_chunk"]
-                traffic_src = ("sum of dram__bytes_read+write over the kernels of ONE activation chunk (ncu --set full), committed "
-                               "as profiles/mappo_chunk_traffic.json — a constant read from that file, NOT measured in this run")
+            if bool(tj.get("compact")) == compact and int(tj.get("chunk_rows", 0)) > 0:
+                # the capture is per 37 888 env steps; every kernel of the update streams its rows once, so the traffic of a chunk
+                # scales with its row count
+                traffic = tj["dram_bytes_per_chunk"] * chunk_rows / float(tj["chunk_rows"])
+                traffic_src = ("sum of dram__bytes_read+write over the kernels of ONE activation chunk (ncu --set full, captured at %d "
+                               "env steps per chunk and scaled to this run's %d), committed as profiles/mappo_chunk_traffic.json — a "
+                               "constant read from that file, NOT measured in this run" % (int(tj["chunk_rows"]), chunk_rows))
                 hbm = {"bound": "hbm", "achieved": traffic * chunks / (upd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                        "frac": traffic * chunks / (upd_ms * 1e-3) / 1e9 / hbm_peak, "traffic_per_chunk": traffic,
                        "traffic_source": traffic_src}

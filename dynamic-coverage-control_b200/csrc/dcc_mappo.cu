@@ -974,11 +974,13 @@ int dcc_mappo_create(const dcc_mappo_cfg *cfg, int device, void **handle) {
     const int N = cfg->n_agents, D = cfg->obs_dim, H = cfg->hidden;
     h->la.init(D, H, cfg->act_dim, true, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
     h->lc.init(N * D, H, 1, false, cfg->use_feature_normalization != 0, cfg->layer_N, cfg->recurrent_N);
-    // chunk: bound the scratch to ~1.5 GB unless the caller asks for a size
+    // chunk: bound the activation scratch to ~7.5 GB unless the caller asks for a size.  Larger chunks mean fewer, longer launches:
+    // 113 664 env steps per chunk (6 waves of critic tiles, 48 of actor tiles per kernel) instead of 37 888 took 4.9 % off the update at
+    // 8/64/65 536 (ramp-up / drain of ~20 kernels per chunk); beyond that the gain saturates (profiles/r02end_chunk_size_sweep.txt)
     long chunk = cfg->chunk_rows;
     if (chunk <= 0) {
         const double per_row = (double)N * (D + (2.0 + 2.0 * (1 + cfg->layer_N)) * H + 16) * 4.0;
-        chunk = (long)(2.5e9 / per_row);
+        chunk = (long)(7.5e9 / per_row);
         if (chunk > 131072) chunk = 131072;
         // recurrent policies keep ~13 H floats per row and GRU layer on top: bound the pass to 65 536 agent rows
         if (cfg->recurrent_N > 0 && chunk * N > 65536) chunk = 65536 / N;
